@@ -1,0 +1,700 @@
+// lance_oracle.cc -- CPU restatement of the reference's IVF-PQ hot path.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing under lance_b200/ may include, link or call this file;
+// only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it.
+//
+// Every function cites the reference file:line (relative to /root/reference/rust) whose operation
+// ORDER it follows.  It is compiled with FP contraction off (see Makefile), because Rust/LLVM never
+// fuses `a*b+c` for the reference's scalar loops.
+//
+// Parity pinning: the known-answer literals from the reference's own unit tests are stored in
+// tests/golden/reference_known_answers.json and checked against this file by tests/test_oracle_golden.py.
+// What is NOT pinned (reference is unseeded / implementation-defined there):
+//   * the k-means RNG stream (init rows, split_clusters donors)  -> we define our own (splitmix64),
+//   * the order among EQUAL centroid distances in find_partitions (arrow-ord partial sort)
+//       -> we define ascending (distance, id).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+template <class F>
+void parallel_for(size_t n, int nthreads, F f) {
+  if (nthreads <= 1 || n < 2) {
+    f(size_t(0), n);
+    return;
+  }
+  size_t nt = std::min<size_t>(size_t(nthreads), n);
+  std::atomic<size_t> next{0};
+  // dynamic chunks, like rayon's work stealing; per-row results are independent so scheduling
+  // cannot change any output.
+  size_t chunk = std::max<size_t>(1, n / (nt * 16));
+  std::vector<std::thread> th;
+  for (size_t t = 0; t < nt; ++t)
+    th.emplace_back([&] {
+      for (;;) {
+        size_t b = next.fetch_add(chunk);
+        if (b >= n) break;
+        f(b, std::min(n, b + chunk));
+      }
+    });
+  for (auto& x : th) x.join();
+}
+
+// splitmix64: OUR rng for init / split_clusters (reference uses an unseeded SmallRng,
+// lance-index/src/vector/kmeans.rs:181,646 -> parity unpinned by design).
+struct SplitMix64 {
+  uint64_t s;
+  explicit SplitMix64(uint64_t seed) : s(seed) {}
+  uint64_t next() {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  }
+  // uniform in [0,1) with 24 bits, like rand's Standard f32 sampling
+  float next_f32() { return float(next() >> 40) * (1.0f / 16777216.0f); }
+};
+
+inline float half_to_float(uint16_t h) {
+  uint32_t sign = (uint32_t(h) & 0x8000u) << 16;
+  uint32_t exp = (h >> 10) & 0x1f;
+  uint32_t man = h & 0x3ff;
+  uint32_t f;
+  if (exp == 0) {
+    if (man == 0) {
+      f = sign;
+    } else {
+      int e = -1;
+      do {
+        man <<= 1;
+        ++e;
+      } while (!(man & 0x400));
+      f = sign | uint32_t(127 - 15 - e) << 23 | (man & 0x3ff) << 13;
+    }
+  } else if (exp == 31) {
+    f = sign | 0x7f800000u | man << 13;
+  } else {
+    f = sign | (exp + 112) << 23 | man << 13;
+  }
+  float out;
+  std::memcpy(&out, &f, 4);
+  return out;
+}
+inline float bf16_to_float(uint16_t h) {
+  uint32_t f = uint32_t(h) << 16;
+  float out;
+  std::memcpy(&out, &f, 4);
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A1. squared L2, f32, 16 lanes   (lance-linalg/src/distance/l2.rs:57-91, LANES=16 at :161-168)
+// ---------------------------------------------------------------------------------------------
+template <class T, class Conv>
+inline float l2_lanes16(const T* x, const T* y, size_t d, Conv conv) {
+  const size_t n16 = d / 16 * 16;
+  // remainder first: `.sum::<f32>()` folds left-to-right (l2.rs:69-79)
+  float s = 0.0f;
+  for (size_t i = n16; i < d; ++i) {
+    float diff = conv(x[i]) - conv(y[i]);
+    s += diff * diff;
+  }
+  float sums[16];
+  for (int l = 0; l < 16; ++l) sums[l] = 0.0f;
+  for (size_t c = 0; c < n16; c += 16)  // l2.rs:82-88
+    for (int l = 0; l < 16; ++l) {
+      float diff = conv(x[c + l]) - conv(y[c + l]);
+      sums[l] += diff * diff;
+    }
+  float t = 0.0f;  // `sums.iter().copied().sum()` (l2.rs:90)
+  for (int l = 0; l < 16; ++l) t += sums[l];
+  return s + t;
+}
+inline float l2_f32(const float* x, const float* y, size_t d) {
+  return l2_lanes16(x, y, d, [](float v) { return v; });
+}
+
+// A2. dot, f32, 16 lanes (lance-linalg/src/distance/dot.rs:30-58, LANES=16 at :138-143)
+inline float dot_f32(const float* x, const float* y, size_t d) {
+  const size_t n16 = d / 16 * 16;
+  float s = 0.0f;
+  for (size_t i = n16; i < d; ++i) s += x[i] * y[i];
+  float sums[16];
+  for (int l = 0; l < 16; ++l) sums[l] = 0.0f;
+  for (size_t c = 0; c < n16; c += 16)
+    for (int l = 0; l < 16; ++l) sums[l] += x[c + l] * y[c + l];
+  float t = 0.0f;
+  for (int l = 0; l < 16; ++l) t += sums[l];
+  return s + t;
+}
+// norm_l2 f32 (lance-linalg/src/distance/norm_l2.rs:106-130, LANES=16 for f32)
+inline float norm_l2_f32(const float* x, size_t d) {
+  const size_t n16 = d / 16 * 16;
+  float s = 0.0f;
+  for (size_t i = n16; i < d; ++i) s += x[i] * x[i];
+  float sums[16];
+  for (int l = 0; l < 16; ++l) sums[l] = 0.0f;
+  for (size_t c = 0; c < n16; c += 16)
+    for (int l = 0; l < 16; ++l) sums[l] += x[c + l] * x[c + l];
+  float t = 0.0f;
+  for (int l = 0; l < 16; ++l) t += sums[l];
+  return std::sqrt(s + t);
+}
+
+inline float metric_dist(int metric, const float* x, const float* y, size_t d) {
+  // 0 = L2, 2 = Dot (dot_distance = 1 - dot, dot.rs:68-70)
+  return metric == 2 ? 1.0f - dot_f32(x, y, d) : l2_f32(x, y, d);
+}
+
+// A4. argmin with bias (lance-linalg/src/kernels.rs:79-111)
+//   strict `<` against +inf start -> first minimum wins, NaN / +inf never win.
+inline bool argmin_row(const float* centroids, size_t k, size_t d, const float* v, int metric,
+                       const float* bias, uint32_t* idx_out, float* val_out) {
+  float min_value = std::numeric_limits<float>::infinity();
+  float min_orig = std::numeric_limits<float>::infinity();
+  bool found = false;
+  uint32_t min_idx = 0;
+  for (size_t c = 0; c < k; ++c) {
+    float val = metric_dist(metric, v, centroids + c * d, d);
+    float cmp = bias ? val + bias[c] : val;
+    if (cmp < min_value) {
+      min_value = cmp;
+      min_orig = val;
+      min_idx = uint32_t(c);
+      found = true;
+    }
+  }
+  *idx_out = min_idx;
+  *val_out = min_orig;
+  return found;
+}
+
+// Rust std::collections::BinaryHeap<OrderedNode> restated (push = sift_up, pop = swap-with-last +
+// sift_down_to_bottom + sift_up), ordered by f32::total_cmp on dist
+// (lance-index/src/vector/graph.rs:66-121).  Rust std is third-party to /root/reference; its
+// algorithm is restated from the published std source (library/alloc/src/collections/binary_heap).
+struct Node {
+  uint64_t id;
+  float dist;
+};
+inline int32_t total_key(float f) {
+  int32_t b;
+  std::memcpy(&b, &f, 4);
+  return b ^ int32_t(uint32_t(b >> 31) >> 1);
+}
+inline bool le(const Node& a, const Node& b) { return total_key(a.dist) <= total_key(b.dist); }
+inline bool gt(float a, float b) { return total_key(a) > total_key(b); }
+struct RustMaxHeap {
+  std::vector<Node> data;
+  void sift_up(size_t start, size_t pos) {
+    Node elt = data[pos];
+    while (pos > start) {
+      size_t parent = (pos - 1) / 2;
+      if (le(elt, data[parent])) break;
+      data[pos] = data[parent];
+      pos = parent;
+    }
+    data[pos] = elt;
+  }
+  void push(Node n) {
+    size_t old = data.size();
+    data.push_back(n);
+    sift_up(0, old);
+  }
+  void sift_down_to_bottom(size_t pos) {
+    size_t end = data.size();
+    size_t start = pos;
+    Node elt = data[pos];
+    size_t child = 2 * pos + 1;
+    while (child + 1 < end) {  // child <= end.saturating_sub(2)
+      if (le(data[child], data[child + 1])) child += 1;
+      data[pos] = data[child];
+      pos = child;
+      child = 2 * pos + 1;
+    }
+    if (child + 1 == end) {
+      data[pos] = data[child];
+      pos = child;
+    }
+    data[pos] = elt;
+    sift_up(start, pos);
+  }
+  Node pop() {
+    Node item = data.back();
+    data.pop_back();
+    if (!data.empty()) {
+      std::swap(item, data[0]);
+      sift_down_to_bottom(0);
+    }
+    return item;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------
+// distances
+// ---------------------------------------------------------------------------------------------
+float lo_l2_f32(const float* x, const float* y, uint64_t d) { return l2_f32(x, y, d); }
+float lo_dot_f32(const float* x, const float* y, uint64_t d) { return dot_f32(x, y, d); }
+float lo_norm_l2_f32(const float* x, uint64_t d) { return norm_l2_f32(x, d); }
+// u8: sum |x-y|^2 in u32, cast to f32 (l2.rs:44-49)
+float lo_l2_u8(const uint8_t* x, const uint8_t* y, uint64_t d) {
+  uint32_t s = 0;
+  for (uint64_t i = 0; i < d; ++i) {
+    uint32_t a = x[i] > y[i] ? x[i] - y[i] : y[i] - x[i];
+    s += a * a;
+  }
+  return float(s);
+}
+// f16 / bf16 scalar path: convert each element to f32, LANES=16 (l2.rs:100-106,156)
+float lo_l2_f16(const uint16_t* x, const uint16_t* y, uint64_t d) {
+  return l2_lanes16(x, y, d, [](uint16_t v) { return half_to_float(v); });
+}
+float lo_l2_bf16(const uint16_t* x, const uint16_t* y, uint64_t d) {
+  return l2_lanes16(x, y, d, [](uint16_t v) { return bf16_to_float(v); });
+}
+// cosine distance, scalar fallback form (cosine.rs:233-238 cosine_scalar with x_norm = norm_l2(x)).
+// The reference f32 path uses f32x16 FMA + platform reduce_sum (cosine.rs:143-174) whose summation
+// order is ISA-specific: tolerance parity only (the reference itself tests at assert_relative_eq).
+float lo_cosine_f32(const float* x, const float* y, uint64_t d) {
+  float xn = norm_l2_f32(x, d);
+  float y_sq = dot_f32(y, y, d);
+  float xy = dot_f32(x, y, d);
+  return 1.0f - xy / (xn * std::sqrt(y_sq));
+}
+void lo_l2_batch_f32(const float* from, const float* to, uint64_t n, uint64_t d, float* out) {
+  for (uint64_t i = 0; i < n; ++i) out[i] = l2_f32(from, to + i * d, d);  // l2.rs:194-203
+}
+
+// A3. normalize (lance-linalg/src/kernels.rs:141-146): norm = sqrt(sum x^2) sequential in T,
+// then x / norm.  Returns the norm.
+float lo_normalize_f32(const float* x, uint64_t d, float* out) {
+  float s = 0.0f;
+  for (uint64_t i = 0; i < d; ++i) s += x[i] * x[i];  // powi(2) == x*x
+  float norm = std::sqrt(s);
+  for (uint64_t i = 0; i < d; ++i) out[i] = x[i] / norm;
+  return norm;
+}
+void lo_normalize_rows_f32(const float* x, uint64_t n, uint64_t d, float* out, int nthreads) {
+  parallel_for(n, nthreads, [&](size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) lo_normalize_f32(x + i * d, d, out + i * d);
+  });
+}
+// KeepFiniteVectors (lance-index/src/vector/transform.rs:112-159): row is kept iff all finite.
+void lo_is_finite_rows_f32(const float* x, uint64_t n, uint64_t d, uint8_t* keep) {
+  for (uint64_t i = 0; i < n; ++i) {
+    bool ok = true;
+    for (uint64_t j = 0; j < d; ++j) ok = ok && std::isfinite(x[i * d + j]);
+    keep[i] = ok;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a5/a8  compute_membership_and_dist (kmeans.rs:317-369) / compute_partitions_with_dists (:1275)
+//   bias[c] = balance_factor * cluster_sizes[c] as f32 when cluster_sizes != NULL (kmeans.rs:341-345)
+// ---------------------------------------------------------------------------------------------
+void lo_compute_membership(const float* centroids, uint64_t k, uint64_t d, const float* data,
+                           uint64_t n, int metric, float balance_factor,
+                           const uint64_t* cluster_sizes, uint32_t* ids, float* dists,
+                           uint8_t* valid, int nthreads) {
+  std::vector<float> bias;
+  if (cluster_sizes) {
+    bias.resize(k);
+    for (uint64_t c = 0; c < k; ++c) bias[c] = balance_factor * float(cluster_sizes[c]);
+  }
+  const float* bp = cluster_sizes ? bias.data() : nullptr;
+  parallel_for(n, nthreads, [&](size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) {
+      uint32_t id;
+      float val;
+      bool ok = argmin_row(centroids, k, d, data + i * d, metric, bp, &id, &val);
+      ids[i] = ok ? id : 0;
+      if (dists) dists[i] = ok ? val : std::numeric_limits<float>::quiet_NaN();
+      if (valid) valid[i] = ok;
+    }
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// a6/a7  Lloyd loop (kmeans.rs:610-719), update (:371-446), split_clusters (:174-207),
+//        compute_cluster_sizes (:210-232), compute_balance_loss (:234-237)
+//   init_centroids == NULL -> choose k distinct rows with OUR rng (partial Fisher-Yates).
+//   balance_factor is the value AFTER `params.balance_factor /= n` (kmeans.rs:1344).
+// Returns the number of iterations executed.
+// ---------------------------------------------------------------------------------------------
+int lo_kmeans_train(const float* data_in, uint64_t n_in, uint64_t d, uint64_t k, int max_iters,
+                    double tolerance, float balance_factor_param, int metric, uint64_t seed,
+                    const float* init_centroids, float* centroids_out, double* loss_out,
+                    int nthreads) {
+  // kmeans.rs:623-627: keep only the first 512*k rows
+  uint64_t n = n_in >= k * 512 ? k * 512 : n_in;
+  const float* data = data_in;
+  std::vector<float> cent(k * d);
+  SplitMix64 rng(seed);
+  if (init_centroids) {
+    std::memcpy(cent.data(), init_centroids, sizeof(float) * k * d);
+  } else {
+    std::vector<uint32_t> idx(n);
+    for (uint64_t i = 0; i < n; ++i) idx[i] = uint32_t(i);
+    for (uint64_t i = 0; i < k; ++i) {
+      uint64_t j = i + rng.next() % (n - i);
+      std::swap(idx[i], idx[j]);
+      std::memcpy(&cent[i * d], data + uint64_t(idx[i]) * d, sizeof(float) * d);
+    }
+  }
+  std::vector<uint64_t> cluster_sizes(k, 0);
+  std::vector<uint32_t> ids(n);
+  std::vector<float> dists(n);
+  std::vector<uint8_t> valid(n);
+  float adjusted_balance_factor = std::numeric_limits<float>::max();
+  double loss = std::numeric_limits<double>::max();
+  double last_loss = loss;
+  int it = 0;
+  for (it = 1; it <= max_iters; ++it) {
+    float balance_factor = std::min(adjusted_balance_factor, balance_factor_param);
+    lo_compute_membership(cent.data(), k, d, data, n, metric, balance_factor, cluster_sizes.data(),
+                          ids.data(), dists.data(), valid.data(), nthreads);
+    // compute_membership_and_loss (kmeans.rs:266-280): radius = max, loss = f64 sum in row order
+    std::vector<float> radius(k, 0.0f);
+    std::vector<double> losses(k, 0.0);
+    for (uint64_t i = 0; i < n; ++i)
+      if (valid[i]) {
+        radius[ids[i]] = std::max(radius[ids[i]], dists[i]);
+        losses[ids[i]] += double(dists[i]);
+      }
+    // compute_cluster_sizes (kmeans.rs:210-232)
+    std::fill(cluster_sizes.begin(), cluster_sizes.end(), 0);
+    uint64_t max_id = 0, max_size = 0;
+    for (uint64_t i = 0; i < n; ++i)
+      if (valid[i]) {
+        uint64_t c = ids[i];
+        cluster_sizes[c] += 1;
+        if (cluster_sizes[c] > max_size) {
+          max_size = cluster_sizes[c];
+          max_id = c;
+        }
+      }
+    adjusted_balance_factor =
+        (radius[max_id] - float(losses[max_id]) / float(cluster_sizes[max_id])) / float(n);
+    // compute_balance_loss (kmeans.rs:234-237)
+    uint64_t size_sq = 0;
+    for (uint64_t c = 0; c < k; ++c) size_sq += cluster_sizes[c] * cluster_sizes[c];
+    float balance_loss = balance_factor * (float(size_sq) - float(n * n) / float(k));
+    double sum_losses = 0.0;
+    for (uint64_t c = 0; c < k; ++c) sum_losses += losses[c];
+    last_loss = sum_losses + double(balance_loss);
+    // to_kmeans (kmeans.rs:371-446): per-cluster sum in row order IN T, then *= 1/cnt
+    std::fill(cent.begin(), cent.end(), 0.0f);
+    for (uint64_t i = 0; i < n; ++i)
+      if (valid[i]) {
+        float* c = &cent[uint64_t(ids[i]) * d];
+        const float* v = data + i * d;
+        for (uint64_t j = 0; j < d; ++j) c[j] += v[j];
+      }
+    for (uint64_t c = 0; c < k; ++c)
+      if (cluster_sizes[c] > 0) {
+        float norm = 1.0f / float(cluster_sizes[c]);
+        for (uint64_t j = 0; j < d; ++j) cent[c * d + j] *= norm;
+      }
+    // split_clusters (kmeans.rs:174-207), our rng
+    {
+      const float eps = 1.0f / 1024.0f;
+      for (uint64_t i = 0; i < k; ++i)
+        if (cluster_sizes[i] == 0) {
+          uint64_t j = 0;
+          for (;;) {
+            float p = (float(cluster_sizes[j]) - 1.0f) / float(n - k);
+            if (rng.next_f32() < p) break;
+            j = (j + 1) % k;
+          }
+          cluster_sizes[i] = cluster_sizes[j] / 2;
+          cluster_sizes[j] -= cluster_sizes[i];
+          for (uint64_t t = 0; t < d; ++t) {
+            if (t % 2 == 0) {
+              cent[i * d + t] = cent[j * d + t] * (1.0f + eps);
+              cent[j * d + t] *= 1.0f - eps;
+            } else {
+              cent[i * d + t] = cent[j * d + t] * (1.0f - eps);
+              cent[j * d + t] *= 1.0f + eps;
+            }
+          }
+        }
+    }
+    if (std::fabs(loss - last_loss) < tolerance * last_loss) break;  // kmeans.rs:704
+    loss = last_loss;
+  }
+  if (it > max_iters) it = max_iters;
+  std::memcpy(centroids_out, cent.data(), sizeof(float) * k * d);
+  if (loss_out) *loss_out = last_loss;
+  return it;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a12  kmeans_find_partitions (kmeans.rs:1134-1158): all K distances, ascending partial sort.
+//   tie order among equal distances: arrow-ord is unpinned -> ascending (dist, id); NaN last.
+// ---------------------------------------------------------------------------------------------
+void lo_find_partitions(const float* centroids, uint64_t k, uint64_t d, const float* query,
+                        uint64_t nprobes, int metric, uint32_t* ids, float* dists) {
+  std::vector<float> dv(k);
+  for (uint64_t c = 0; c < k; ++c) dv[c] = metric_dist(metric, query, centroids + c * d, d);
+  std::vector<uint32_t> order(k);
+  for (uint64_t c = 0; c < k; ++c) order[c] = uint32_t(c);
+  auto cmp = [&](uint32_t a, uint32_t b) {
+    bool an = std::isnan(dv[a]), bn = std::isnan(dv[b]);
+    if (an != bn) return bn;
+    if (!an && dv[a] != dv[b]) return dv[a] < dv[b];
+    return a < b;
+  };
+  uint64_t p = std::min(nprobes, k);
+  std::partial_sort(order.begin(), order.begin() + p, order.end(), cmp);
+  for (uint64_t i = 0; i < p; ++i) {
+    ids[i] = order[i];
+    dists[i] = dv[order[i]];
+  }
+}
+
+// a9  residual (residual.rs:86-95): r = x - centroid[part] elementwise in T
+void lo_compute_residual(const float* centroids, uint64_t d, const float* vectors, uint64_t n,
+                         const uint32_t* part_ids, float* out, int nthreads) {
+  parallel_for(n, nthreads, [&](size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) {
+      const float* c = centroids + uint64_t(part_ids[i]) * d;
+      for (uint64_t j = 0; j < d; ++j) out[i * d + j] = vectors[i * d + j] - c[j];
+    }
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// a11  PQ training (pq/builder.rs:89-157): M independent k-means (k = 2^nbits) on the sub-vector
+//   columns (pq/utils.rs:14-49), each through the free fn train_kmeans (kmeans.rs:1309-1347:
+//   first sample_rate*k rows, balance 0).  Sub-space m uses seed + m.  init_codebook may be NULL.
+//   iters_out[M] (nullable) receives the iteration counts.
+// ---------------------------------------------------------------------------------------------
+void lo_pq_train(const float* data, uint64_t n, uint64_t d, uint64_t M, int nbits, int max_iters,
+                 uint64_t sample_rate, int metric, uint64_t seed, const float* init_codebook,
+                 float* codebook_out, int* iters_out, int nthreads) {
+  const uint64_t k = uint64_t(1) << nbits;
+  const uint64_t ds = d / M;
+  uint64_t rows = n > sample_rate * k ? sample_rate * k : n;
+  std::vector<float> sub(rows * ds);
+  for (uint64_t m = 0; m < M; ++m) {
+    for (uint64_t i = 0; i < rows; ++i)
+      std::memcpy(&sub[i * ds], data + i * d + m * ds, sizeof(float) * ds);
+    double loss;
+    int it = lo_kmeans_train(sub.data(), rows, ds, k, max_iters, 1e-4, 0.0f, metric, seed + m,
+                             init_codebook ? init_codebook + m * k * ds : nullptr,
+                             codebook_out + m * k * ds, &loss, nthreads);
+    if (iters_out) iters_out[m] = it;
+  }
+}
+
+// a10  PQ encode (pq.rs:116-191): per row, per sub-vector argmin over the codebook rows
+//   (compute_partition kmeans.rs:1350-1369, no bias), None -> 0; 4-bit packs (v[1]<<4)|v[0].
+void lo_pq_encode(const float* codebook, uint64_t M, int nbits, uint64_t d, int metric,
+                  const float* vectors, uint64_t n, uint8_t* codes_out, int nthreads) {
+  const uint64_t k = uint64_t(1) << nbits;
+  const uint64_t ds = d / M;
+  const uint64_t bytes_per_row = nbits == 4 ? M / 2 : M;
+  parallel_for(n, nthreads, [&](size_t b, size_t e) {
+    std::vector<uint8_t> tmp(M);
+    for (size_t i = b; i < e; ++i) {
+      for (uint64_t m = 0; m < M; ++m) {
+        uint32_t id;
+        float val;
+        bool ok = argmin_row(codebook + m * k * ds, k, ds, vectors + i * d + m * ds, metric,
+                             nullptr, &id, &val);
+        tmp[m] = ok ? uint8_t(id) : 0;
+      }
+      if (nbits == 4)
+        for (uint64_t j = 0; j < M / 2; ++j)
+          codes_out[i * bytes_per_row + j] = uint8_t((tmp[2 * j + 1] << 4) | tmp[2 * j]);
+      else
+        std::memcpy(codes_out + i * bytes_per_row, tmp.data(), M);
+    }
+  });
+}
+
+// a14  ADC lookup table (pq/distance.rs:24-92): LUT[m*2^nbits + c] = dist(q_m, cb[m][c])
+void lo_build_lut(const float* codebook, int nbits, uint64_t M, uint64_t d, int metric,
+                  const float* query, float* lut) {
+  const uint64_t k = uint64_t(1) << nbits;
+  const uint64_t ds = d / M;
+  for (uint64_t m = 0; m < M; ++m)
+    for (uint64_t c = 0; c < k; ++c)
+      lut[m * k + c] = metric_dist(metric, query + m * ds, codebook + (m * k + c) * ds, ds);
+}
+
+// a18  transpose [n][M] -> [M][n] (pq/storage.rs:430-450)
+void lo_transpose_codes(const uint8_t* codes, uint64_t n, uint64_t M, uint8_t* out) {
+  for (uint64_t i = 0; i < n; ++i)
+    for (uint64_t m = 0; m < M; ++m) out[m * n + i] = codes[i * M + m];
+}
+
+// a15  compute_pq_distance, 8-bit, transposed codes (pq/distance.rs:109-144):
+//   dist[j] = 0; for m: dist[j] += LUT[m*256 + codeT[m*n + j]]   (f32 adds in m order)
+//   Dot: PQDistCalculator::distance_all subtracts (M-1) afterwards (pq/storage.rs:957-958).
+void lo_pq_scan(const float* lut, uint64_t M, const uint8_t* codes_t, uint64_t n, int metric,
+                float* dists) {
+  for (uint64_t j = 0; j < n; ++j) dists[j] = 0.0f;
+  for (uint64_t m = 0; m < M; ++m) {
+    const float* t = lut + m * 256;
+    const uint8_t* c = codes_t + m * n;
+    for (uint64_t j = 0; j < n; ++j) dists[j] += t[c[j]];
+  }
+  if (metric == 2)
+    for (uint64_t j = 0; j < n; ++j) dists[j] -= float(M) - 1.0f;
+}
+
+// a16  FlatIndex::search fast path (flat/index.rs:97-127): size-k Rust BinaryHeap, push while
+//   len<k else replace the root iff root.dist > dist (total_cmp).  Output = heap's internal
+//   vector order (`into_iter`), unsorted.  Optional [lower, upper) range (flat/index.rs:101-115).
+uint64_t lo_flat_topk(const float* dists, const uint64_t* row_ids, uint64_t n, uint64_t k,
+                      int use_range, float lower, float upper, uint64_t* out_ids,
+                      float* out_dists) {
+  RustMaxHeap h;
+  if (k == 0) return 0;
+  for (uint64_t j = 0; j < n; ++j) {
+    float dist = dists[j];
+    if (use_range && (total_key(dist) < total_key(lower) || total_key(dist) >= total_key(upper)))
+      continue;
+    if (h.data.size() < k) {
+      h.push({row_ids ? row_ids[j] : j, dist});
+    } else if (gt(h.data[0].dist, dist)) {
+      h.pop();
+      h.push({row_ids ? row_ids[j] : j, dist});
+    }
+  }
+  for (size_t i = 0; i < h.data.size(); ++i) {
+    out_ids[i] = h.data[i].id;
+    out_dists[i] = h.data[i].dist;
+  }
+  return h.data.size();
+}
+
+// a17  FlatDistanceCal::distance_all (flat/storage.rs:397-403): exact distances to every row
+void lo_flat_distance_all(const float* query, const float* vectors, uint64_t n, uint64_t d,
+                          int metric, float* out, int nthreads) {
+  parallel_for(n, nthreads, [&](size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) {
+      const float* v = vectors + i * d;
+      out[i] = metric == 1 ? lo_cosine_f32(query, v, d) : metric_dist(metric, query, v, d);
+    }
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// Query pipeline for one IVF_PQ index held as CSR-by-partition arrays (the same arrays the
+// product keeps on the device).  Follows rust/lance/src/index/vector/ivf/v2.rs:455-500:
+//   find_partitions -> per probed partition: residual query (v2.rs:316-332), LUT, scan, heap top-k
+//   -> global merge sorted by (_distance asc, _rowid asc), first k (scanner.rs:3450-3466).
+// codes: row-major [n][M] in partition order (transposed internally per partition as the
+// reference storage does).  Parallel over queries (reference: one query at a time, partitions in
+// parallel; results are independent of that schedule).
+// out arrays are [nq][k]; out_counts[nq].
+// ---------------------------------------------------------------------------------------------
+void lo_ivfpq_search(const float* centroids, uint64_t K, uint64_t d, int metric,
+                     const float* codebook, uint64_t M, int nbits, const uint64_t* part_offsets,
+                     const uint8_t* codes, const uint64_t* row_ids, const float* queries,
+                     uint64_t nq, uint64_t k, uint64_t nprobes, uint64_t* out_ids,
+                     float* out_dists, uint32_t* out_counts, int nthreads) {
+  const uint64_t ncode = uint64_t(1) << nbits;
+  uint64_t max_part = 0;
+  for (uint64_t p = 0; p < K; ++p) max_part = std::max(max_part, part_offsets[p + 1] - part_offsets[p]);
+  // transposed copies per partition, built once (ProductQuantizationStorage::new transposes)
+  std::vector<uint8_t> codes_t(part_offsets[K] * M);
+  for (uint64_t p = 0; p < K; ++p) {
+    uint64_t n = part_offsets[p + 1] - part_offsets[p];
+    lo_transpose_codes(codes + part_offsets[p] * M, n, M, codes_t.data() + part_offsets[p] * M);
+  }
+  const int cmetric = metric == 1 ? 0 : metric;  // cosine -> L2 on normalised vectors
+  parallel_for(nq, nthreads, [&](size_t b, size_t e) {
+    std::vector<uint32_t> pids(nprobes);
+    std::vector<float> pd(nprobes), q(d), qr(d), lut(M * ncode), dist(max_part);
+    std::vector<uint64_t> hid(k);
+    std::vector<float> hd(k);
+    std::vector<Node> cand;
+    for (size_t qi = b; qi < e; ++qi) {
+      const float* qin = queries + qi * d;
+      if (metric == 1)
+        lo_normalize_f32(qin, d, q.data());  // knn.rs:497-499
+      else
+        std::memcpy(q.data(), qin, sizeof(float) * d);
+      uint64_t np = std::min(nprobes, K);
+      lo_find_partitions(centroids, K, d, q.data(), np, cmetric, pids.data(), pd.data());
+      cand.clear();
+      for (uint64_t pi = 0; pi < np; ++pi) {
+        uint64_t p = pids[pi];
+        uint64_t n = part_offsets[p + 1] - part_offsets[p];
+        if (n == 0) continue;
+        const float* qq = q.data();
+        if (cmetric == 0) {  // residual query for L2/cosine (v2.rs:316-332)
+          for (uint64_t j = 0; j < d; ++j) qr[j] = q[j] - centroids[p * d + j];
+          qq = qr.data();
+        }
+        lo_build_lut(codebook, nbits, M, d, cmetric, qq, lut.data());
+        lo_pq_scan(lut.data(), M, codes_t.data() + part_offsets[p] * M, n, cmetric, dist.data());
+        uint64_t got = lo_flat_topk(dist.data(), row_ids + part_offsets[p], n, k, 0, 0, 0,
+                                    hid.data(), hd.data());
+        for (uint64_t i = 0; i < got; ++i) cand.push_back({hid[i], hd[i]});
+      }
+      std::sort(cand.begin(), cand.end(), [](const Node& a, const Node& c) {
+        int32_t ka = total_key(a.dist), kc = total_key(c.dist);
+        if (ka != kc) return ka < kc;
+        return a.id < c.id;
+      });
+      uint64_t got = std::min<uint64_t>(k, cand.size());
+      for (uint64_t i = 0; i < got; ++i) {
+        out_ids[qi * k + i] = cand[i].id;
+        out_dists[qi * k + i] = cand[i].dist;
+      }
+      for (uint64_t i = got; i < k; ++i) {
+        out_ids[qi * k + i] = ~uint64_t(0);
+        out_dists[qi * k + i] = std::numeric_limits<float>::infinity();
+      }
+      out_counts[qi] = uint32_t(got);
+    }
+  });
+}
+
+// exact brute-force ground truth (rust/lance/src/index/vector/ivf/v2.rs:959-983 `ground_truth`)
+void lo_brute_force_topk(const float* data, uint64_t n, uint64_t d, int metric,
+                         const float* queries, uint64_t nq, uint64_t k, uint64_t* out_ids,
+                         float* out_dists, int nthreads) {
+  parallel_for(nq, nthreads, [&](size_t b, size_t e) {
+    std::vector<Node> all(n);
+    for (size_t qi = b; qi < e; ++qi) {
+      for (uint64_t i = 0; i < n; ++i) {
+        const float* v = data + i * d;
+        float dd = metric == 1 ? lo_cosine_f32(queries + qi * d, v, d)
+                               : metric_dist(metric, queries + qi * d, v, d);
+        all[i] = {i, dd};
+      }
+      uint64_t kk = std::min(k, n);
+      std::partial_sort(all.begin(), all.begin() + kk, all.end(), [](const Node& a, const Node& c) {
+        if (a.dist != c.dist) return a.dist < c.dist;
+        return a.id < c.id;
+      });
+      for (uint64_t i = 0; i < kk; ++i) {
+        out_ids[qi * k + i] = all[i].id;
+        out_dists[qi * k + i] = all[i].dist;
+      }
+    }
+  });
+}
+
+int lo_hardware_threads() { return int(std::thread::hardware_concurrency()); }
+
+}  // extern "C"

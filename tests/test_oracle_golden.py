@@ -1,0 +1,196 @@
+"""The oracle (oracle/lance_oracle.cc) against the reference's own known-answer tests
+(tests/golden/reference_known_answers.json, transcribed by tests/golden/make_known_answers.py)
+and against the two reference C kernels compiled from /root/reference (oracle/_ref)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = json.load(open(os.path.join(HERE, "golden", "reference_known_answers.json")))
+
+
+def _check(got, c):
+    exp = np.asarray(c["expect"], dtype=np.float64)
+    got = np.asarray(got, dtype=np.float64)
+    if c.get("exact"):
+        assert np.array_equal(got, exp), (c["name"], got, exp)
+    elif "abs" in c:
+        assert np.all(np.abs(got - exp) <= c["abs"]), (c["name"], got, exp)
+    else:
+        assert np.all(np.abs(got - exp) <= c["rel"] * np.maximum(np.abs(got), np.abs(exp))), (c["name"], got, exp)
+
+
+@pytest.mark.parametrize("c", [c for c in CASES if c["op"] == "l2_batch"], ids=lambda c: c["name"])
+def test_l2_known_answers(c):
+    _check(ob.l2_batch(c["frm"], c["to"], c["d"]), c)
+
+
+@pytest.mark.parametrize("c", [c for c in CASES if c["op"] == "l2_u8"], ids=lambda c: c["name"])
+def test_l2_u8_known_answers(c):
+    _check(ob.l2_u8(c["x"], c["y"]), c)
+    _check(ob.l2_u8(c["y"], c["x"]), c)
+
+
+@pytest.mark.parametrize("c", [c for c in CASES if c["op"] == "cosine"], ids=lambda c: c["name"])
+def test_cosine_known_answers(c):
+    _check(ob.cosine(c["x"], c["y"]), c)
+
+
+def test_pq_scan_transposed_identity():
+    # lance-index/src/vector/pq/distance.rs:337-365, fully deterministic inputs
+    c = [c for c in CASES if c["op"] == "pq_scan_identity"][0]
+    nv, M, d = c["num_vectors"], c["num_sub_vectors"], c["dimension"]
+    codebook = np.arange(M * nv * d, dtype=np.float32)[: 256 * d].reshape(M, 256, d // M)
+    # reference builds a codebook of M*nv*d values but only the first 256*d are addressed
+    query = np.arange(d, dtype=np.float32)
+    lut = ob.build_lut(codebook, query)
+    codes = (np.arange(nv * M) % 256).astype(np.uint8).reshape(nv, M)
+    got = ob.pq_scan(lut, ob.transpose_codes(codes))
+    # row-major evaluation (compute_l2_distance_without_transposing): same m-ascending f32 sum
+    exp = np.zeros(nv, np.float32)
+    for m in range(M):
+        exp = (exp + lut[m * 256 + codes[:, m].astype(np.int64)]).astype(np.float32)
+    assert np.array_equal(got, exp)
+    # hand value: code row 0 = [0,1,2,3]; LUT[m][c] = sum_t (q[m*4+t] - cb[m][c][t])^2
+    cb = codebook.astype(np.float64)
+    q = query.astype(np.float64)
+    d0 = sum(((q[m * 4:(m + 1) * 4] - cb[m, m]) ** 2).sum() for m in range(M))
+    assert got[0] == np.float32(d0)
+
+
+def test_l2_lane_order_is_reference_order():
+    # property from l2.rs:57-91: result = tail + sum_l(sum_c (x-y)^2) with 16 lane accumulators.
+    rng = np.random.default_rng(0)
+    for d in (1, 7, 8, 16, 17, 33, 128, 131, 768):
+        x = rng.standard_normal(d).astype(np.float32)
+        y = rng.standard_normal(d).astype(np.float32)
+        n16 = d // 16 * 16
+        sq = ((x - y).astype(np.float32) ** 2).astype(np.float32)
+        s = np.float32(0)
+        for v in sq[n16:]:
+            s = np.float32(s + v)
+        lanes = np.zeros(16, np.float32)
+        for c in range(0, n16, 16):
+            lanes = (lanes + sq[c:c + 16]).astype(np.float32)
+        t = np.float32(0)
+        for v in lanes:
+            t = np.float32(t + v)
+        assert ob.l2(x, y) == np.float32(s + t)
+        # and within the reference's own tolerance vs f64 (l2.rs:394 max_relative=1e-6)
+        ref = float(((x.astype(np.float64) - y.astype(np.float64)) ** 2).sum())
+        assert abs(ob.l2(x, y) - ref) <= 1e-6 * max(ref, 1e-30) + 1e-30
+
+
+def test_f16_l2_against_reference_c_kernel():
+    so = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libref_simd.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    ref = C.CDLL(so)
+    ref.l2_f16_avx2.restype = C.c_float
+    ref.l2_f16_avx2.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    rng = np.random.default_rng(1)
+    for d in (8, 16, 128, 130, 768):
+        x = rng.standard_normal(d).astype(np.float16)
+        y = rng.standard_normal(d).astype(np.float16)
+        r = ref.l2_f16_avx2(x.ctypes.data, y.ctypes.data, d)
+        o = ob.l2_f16(x, y)
+        # the C kernel is built -ffast-math (build.rs:99): association unspecified -> tolerance
+        assert abs(r - o) <= 1e-5 * max(abs(r), 1e-6)
+
+
+def test_argmin_semantics():
+    # kernels.rs:79-89: first minimum wins; NaN / inf rows -> None (kmeans.rs:1447-1486)
+    cent = np.array([[0, 0], [1, 1], [0, 0]], np.float32)
+    data = np.array([[0, 0], [np.nan, 0], [np.inf, 0], [0.9, 0.9]], np.float32)
+    ids, dists, valid = ob.compute_membership(cent, data)
+    assert list(valid) == [True, False, False, True]
+    assert ids[0] == 0 and ids[3] == 1
+    assert dists[0] == 0.0
+
+
+def test_compute_partitions_is_argmin_of_l2():
+    # kmeans.rs:1398-1422 test_compute_partitions
+    rng = np.random.default_rng(2)
+    cent = rng.standard_normal((17, 32)).astype(np.float32)
+    data = rng.standard_normal((200, 32)).astype(np.float32)
+    ids, dists, valid = ob.compute_membership(cent, data, nthreads=4)
+    for i in range(200):
+        dd = np.array([ob.l2(data[i], c) for c in cent], np.float32)
+        assert ids[i] == int(np.argmin(dd)) and dists[i] == dd.min()
+
+
+def test_pq_encode_is_argmin_per_subvector_and_adc_identity():
+    # pq.rs:628-665 test_pq_transform ; pq.rs:580-625 test_l2_distance (eps 1e-4)
+    rng = np.random.default_rng(3)
+    M, d = 4, 16
+    cb = rng.standard_normal((M, 256, d // M)).astype(np.float32)
+    vec = rng.standard_normal((50, d)).astype(np.float32)
+    codes = ob.pq_encode(cb, vec)
+    for i in range(50):
+        for m in range(M):
+            dd = [ob.l2(vec[i, m * 4:(m + 1) * 4], cb[m, c]) for c in range(256)]
+            assert codes[i, m] == int(np.argmin(np.array(dd, np.float32)))
+    q = rng.standard_normal(d).astype(np.float32)
+    lut = ob.build_lut(cb, q)
+    dist = ob.pq_scan(lut, ob.transpose_codes(codes))
+    for i in range(50):
+        exp = sum(ob.l2(q[m * 4:(m + 1) * 4], cb[m, codes[i, m]]) for m in range(M))
+        assert abs(dist[i] - exp) <= 1e-4 * max(1.0, abs(exp))
+
+
+def test_4bit_packing():
+    rng = np.random.default_rng(4)
+    M, d = 4, 16
+    cb = rng.standard_normal((M, 16, d // M)).astype(np.float32)
+    vec = rng.standard_normal((20, d)).astype(np.float32)
+    packed = ob.pq_encode(cb, vec, nbits=4)
+    assert packed.shape == (20, 2)
+    for i in range(20):
+        c = []
+        for m in range(M):
+            dd = np.array([ob.l2(vec[i, m * 4:(m + 1) * 4], cb[m, j]) for j in range(16)], np.float32)
+            c.append(int(np.argmin(dd)))
+        assert packed[i, 0] == (c[1] << 4 | c[0]) and packed[i, 1] == (c[3] << 4 | c[2])
+
+
+def test_flat_topk_heap_semantics():
+    # flat/index.rs:117-127: keeps the k smallest distances.  WHICH row survives among rows
+    # tied at the k-th distance depends on Rust's BinaryHeap sift order (restated in the oracle):
+    # here the later 3.0 (row 104) survives, not the earlier one -> boundary ties are
+    # implementation-defined in the reference; parity tests compare distance multisets and the
+    # ids strictly below the k-th distance.
+    d = np.array([5, 3, 5, 1, 3, 9, 1], np.float32)
+    ids, dist = ob.flat_topk(d, np.arange(7, dtype=np.uint64) + 100, 3)
+    assert sorted(dist.tolist()) == [1.0, 1.0, 3.0]
+    assert {103, 106} <= set(ids.tolist()) and set(ids.tolist()) - {103, 106} <= {101, 104}
+    ids, dist = ob.flat_topk(d, None, 10)
+    assert len(ids) == 7
+    ids, dist = ob.flat_topk(d, None, 3, lower=3.0, upper=9.0)
+    assert sorted(dist.tolist()) == [3.0, 3.0, 5.0]
+
+
+def test_kmeans_train_converges_and_is_deterministic():
+    rng = np.random.default_rng(5)
+    centers = rng.standard_normal((8, 16)).astype(np.float32) * 10
+    data = (centers[rng.integers(0, 8, 4000)] + rng.standard_normal((4000, 16))).astype(np.float32)
+    c1, loss1, it1 = ob.kmeans_train(data, 8, seed=7, nthreads=4)
+    c2, loss2, it2 = ob.kmeans_train(data, 8, seed=7, nthreads=1)
+    assert np.array_equal(c1, c2) and loss1 == loss2 and it1 == it2
+    assert 1 <= it1 <= 50 and np.isfinite(c1).all()
+    ids, dists, _ = ob.compute_membership(c1, data)
+    assert dists.mean() < 40.0
+
+
+def test_find_partitions_sorted():
+    rng = np.random.default_rng(6)
+    cent = rng.standard_normal((64, 24)).astype(np.float32)
+    q = rng.standard_normal(24).astype(np.float32)
+    ids, dists = ob.find_partitions(cent, q, 10)
+    dd = ob.l2_batch(q, cent, 24)
+    order = np.lexsort((np.arange(64), dd))[:10]
+    assert np.array_equal(ids, order.astype(np.uint32)) and np.array_equal(dists, dd[order])
