@@ -1,0 +1,222 @@
+/*
+ * lance_b200.h -- C ABI of the B200-native IVF-PQ / IVF-FLAT hot path.
+ *
+ * This is the drop-in boundary for lancedb/lance: every entry point replaces one function (or one
+ * trait method) of the reference's `lance-index::vector::{kmeans,ivf,pq,flat}` / `lance-linalg`
+ * crates; the reference file:line it replaces is cited above each declaration (paths relative to
+ * /root/reference/rust).  INTEGRATION.md shows the Rust `extern "C"` block + shim a maintainer adds.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Every data pointer may be a HOST pointer (pageable or pinned)
+ *     or a DEVICE pointer of the current device; the library detects which (cudaPointerGetAttributes)
+ *     and stages host buffers through the device itself.  Outputs are written where they point.
+ *   - Caller allocates inputs AND outputs; the library never frees or keeps a caller pointer after
+ *     the call returns, except inside an `lb2_index` handle, which owns private device copies.
+ *   - Vectors are Arrow FixedSizeList values buffers: contiguous row-major n x d.
+ *   - Every function returns lb2_status and never unwinds/aborts across the boundary; the message
+ *     of the last failure on the calling thread is available from lb2_last_error().
+ *   - There is NO CPU fallback: without a usable CUDA device every compute entry point returns
+ *     LB2_NO_DEVICE.
+ *   - Calls are blocking (results are complete on return).  All entry points are thread-safe;
+ *     each calling thread uses the CUDA device selected by lb2_set_device() on that thread.
+ */
+#ifndef LANCE_B200_H_
+#define LANCE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  LB2_OK = 0,
+  LB2_INVALID_ARG = 1,
+  LB2_UNSUPPORTED = 2, /* valid request that this build does not implement (never silently emulated) */
+  LB2_CUDA_ERROR = 3,
+  LB2_NCCL_ERROR = 4,
+  LB2_OOM = 5,
+  LB2_NO_DEVICE = 6
+} lb2_status;
+
+/* element type of a vector buffer (arrow DataType of the FixedSizeList child) */
+typedef enum { LB2_F32 = 0, LB2_F16 = 1, LB2_BF16 = 2, LB2_U8 = 3 } lb2_dtype;
+
+/* lance_linalg::distance::DistanceType (lance-linalg/src/distance.rs) */
+typedef enum { LB2_L2 = 0, LB2_COSINE = 1, LB2_DOT = 2 } lb2_metric;
+
+typedef struct lb2_index lb2_index; /* device-resident IVF_PQ / IVF_FLAT index */
+
+/* ---- runtime -------------------------------------------------------------------------------- */
+const char* lb2_version(void);
+size_t lb2_last_error(char* buf, size_t len); /* copies the calling thread's last message */
+int lb2_device_count(void);                   /* 0 when no CUDA device is usable */
+lb2_status lb2_set_device(int device);
+lb2_status lb2_synchronize(void);
+/* device / pinned-host buffers for callers that keep data resident (bench, the Rust shim's ring) */
+lb2_status lb2_malloc(void** ptr, size_t bytes);
+lb2_status lb2_free(void* ptr);
+lb2_status lb2_malloc_host(void** ptr, size_t bytes); /* pinned */
+lb2_status lb2_free_host(void* ptr);
+lb2_status lb2_memcpy(void* dst, const void* src, size_t bytes); /* direction auto-detected */
+/* instrumentation: number of kernels this library launched on the calling thread's device since
+ * the last reset, and per-kernel CUDA-event timing (name = kernel family, e.g. "pq_scan"). */
+lb2_status lb2_launch_count(uint64_t* count, int reset);
+lb2_status lb2_profile_enable(int on);
+lb2_status lb2_profile_get(const char* name, uint64_t* launches, double* total_ms);
+lb2_status lb2_profile_reset(void);
+lb2_status lb2_timer_start(void);          /* CUDA event on the library's stream */
+lb2_status lb2_timer_stop(float* ms_out);  /* records, synchronises, returns elapsed ms */
+
+/* ---- lance-linalg distance API -------------------------------------------------------------- */
+/* l2_distance_batch / dot_distance_batch / cosine_distance_batch
+ * (lance-linalg/src/distance/l2.rs:194-203, dot.rs:164-172, cosine.rs:266-290):
+ * out[i] = dist(from, to[i]) for i < n.  f32 L2/Dot are bit-exact to the reference's 16-lane order. */
+lb2_status lb2_distance_batch(const void* from, const void* to, uint64_t n, uint32_t d,
+                              lb2_dtype dtype, lb2_metric metric, float* out);
+/* normalize_fsl (lance-linalg/src/kernels.rs:141-146,201-211): out[i] = x[i] / ||x[i]|| */
+lb2_status lb2_normalize(const void* vectors, uint64_t n, uint32_t d, lb2_dtype dtype, void* out);
+
+/* ---- k-means (lance-index/src/vector/kmeans.rs) --------------------------------------------- */
+typedef struct {
+  uint32_t max_iters;      /* KMeansParams::max_iters, default 50 (kmeans.rs:92-103) */
+  double tolerance;        /* 1e-4 */
+  uint32_t redos;          /* 1 */
+  float balance_factor;    /* BEFORE the division by n that train_kmeans applies (kmeans.rs:1344);
+                              IVF training passes 1.0 (rust/lance/src/index/vector/ivf.rs:1858) */
+  uint32_t hierarchical_k; /* 16; hierarchical training for k > 256 is not implemented on the
+                              device yet: flat Lloyd is used for every k */
+  uint64_t sample_rate;    /* 256: only the first sample_rate*k rows are used (kmeans.rs:1328-1340) */
+  uint64_t seed;           /* the reference is unseeded (kmeans.rs:645); we are reproducible */
+  const void* init_centroids; /* KMeanInit::Incremental (k x d, same dtype) or NULL = random rows */
+  lb2_metric metric;       /* L2 or DOT (cosine callers normalise first, as the reference does) */
+} lb2_kmeans_params;
+void lb2_kmeans_params_default(lb2_kmeans_params* p);
+
+/* train_kmeans<T>(array, params, dimension, k, sample_rate) -> KMeans  (kmeans.rs:1309-1347) */
+lb2_status lb2_kmeans_train(const void* data, uint64_t n, uint32_t d, lb2_dtype dtype, uint32_t k,
+                            const lb2_kmeans_params* params, void* centroids_out, double* loss_out,
+                            uint32_t* iters_out);
+
+/* compute_partitions_arrow_array / compute_partitions_with_dists (kmeans.rs:1187-1294):
+ * part_out[i] = argmin_k dist(vectors[i], centroids[k]) (first minimum), dist_out[i] that distance,
+ * valid_out[i] = 0 where the reference returns None (all NaN/Inf).  dist_out/valid_out nullable. */
+lb2_status lb2_compute_partitions(const void* centroids, uint32_t k, uint32_t d, lb2_dtype dtype,
+                                  lb2_metric metric, const void* vectors, uint64_t n,
+                                  uint32_t* part_out, float* dist_out, uint8_t* valid_out);
+
+/* kmeans_find_partitions_arrow_array (kmeans.rs:1076-1158), batched over nq queries:
+ * ids/dists are [nq][nprobes], ascending by (distance, id). */
+lb2_status lb2_find_partitions(const void* centroids, uint32_t k, uint32_t d, lb2_dtype dtype,
+                               lb2_metric metric, const void* queries, uint64_t nq,
+                               uint32_t nprobes, uint32_t* ids_out, float* dists_out);
+
+/* compute_residual (lance-index/src/vector/residual.rs:111-154): out[i] = v[i] - centroids[part[i]] */
+lb2_status lb2_compute_residual(const void* centroids, uint32_t k, uint32_t d, lb2_dtype dtype,
+                                const void* vectors, uint64_t n, const uint32_t* part_ids,
+                                void* out);
+
+/* ---- product quantisation (lance-index/src/vector/pq*.rs) ------------------------------------ */
+typedef struct {
+  uint32_t num_sub_vectors; /* PQBuildParams (pq/builder.rs:27-59): 16 */
+  uint32_t num_bits;        /* 8 (4 is not implemented on the device yet -> LB2_UNSUPPORTED) */
+  uint32_t max_iters;       /* 50 */
+  uint32_t kmeans_redos;    /* 1 */
+  uint64_t sample_rate;     /* 256 */
+  const void* codebook;     /* user codebook to continue from, or NULL */
+  uint64_t seed;
+} lb2_pq_params;
+void lb2_pq_params_default(lb2_pq_params* p);
+
+/* PQBuildParams::build(data, distance_type) -> ProductQuantizer (pq/builder.rs:162-194):
+ * codebook_out is the flat [M][2^nbits][d/M] layout of pq/utils.rs:59-76; iters_out[M] nullable. */
+lb2_status lb2_pq_train(const void* data, uint64_t n, uint32_t d, lb2_dtype dtype,
+                        lb2_metric metric, const lb2_pq_params* params, void* codebook_out,
+                        uint32_t* iters_out);
+
+/* ProductQuantizer::quantize / transform_impl (pq.rs:116-191,430).  When `centroids` and
+ * `part_ids` are given the residual (residual.rs:161-205) is fused: codes of v - centroids[part].
+ * codes_out is row-major [n][M] (8-bit). */
+lb2_status lb2_pq_encode(const void* codebook, uint32_t num_sub_vectors, uint32_t num_bits,
+                         uint32_t d, lb2_dtype dtype, lb2_metric metric, const void* centroids,
+                         const uint32_t* part_ids, const void* vectors, uint64_t n,
+                         uint8_t* codes_out);
+
+/* build_distance_table_l2 / _dot (pq/distance.rs:24-92): lut_out[M * 2^nbits] f32 */
+lb2_status lb2_pq_build_lut(const void* codebook, uint32_t num_sub_vectors, uint32_t num_bits,
+                            uint32_t d, lb2_metric metric, const float* query, float* lut_out);
+
+/* compute_pq_distance (pq/distance.rs:109-144) on TRANSPOSED codes [M][n], as the reference's
+ * storage holds them; PQDistCalculator::distance_all's Dot correction (pq/storage.rs:957-958)
+ * is applied when metric == LB2_DOT. */
+lb2_status lb2_pq_scan(const float* lut, uint32_t num_sub_vectors, uint32_t num_bits,
+                       lb2_metric metric, const uint8_t* codes_transposed, uint64_t n,
+                       float* dists_out);
+
+/* FlatIndex::search fast path over a distance array (flat/index.rs:97-127): the k smallest
+ * (distance, position) pairs; out sorted ascending by (distance, row id).  *count_out <= k. */
+lb2_status lb2_flat_topk(const float* dists, const uint64_t* row_ids, uint64_t n, uint32_t k,
+                         uint64_t* ids_out, float* dists_out, uint32_t* count_out);
+
+/* IvfTransformer::transform for IVF_PQ (lance-index/src/vector/ivf.rs:188-236,357): for a batch,
+ * [normalise if cosine] -> partition id -> residual -> PQ code, in one pass over the vectors.
+ * valid_out[i] = 0 marks rows KeepFiniteVectors would drop (transform.rs:112-159). */
+lb2_status lb2_ivfpq_transform(const void* centroids, uint32_t k, const void* codebook,
+                               uint32_t num_sub_vectors, uint32_t num_bits, uint32_t d,
+                               lb2_dtype dtype, lb2_metric metric, const void* vectors, uint64_t n,
+                               uint32_t* part_out, uint8_t* codes_out, uint8_t* valid_out);
+
+/* ---- device-resident index: IVFIndex<FlatIndex, ProductQuantizer> ----------------------------
+ * (rust/lance/src/index/vector/ivf/v2.rs:104; storage lance-index/src/vector/pq/storage.rs:151) */
+lb2_status lb2_index_create(const void* centroids, uint32_t k, uint32_t d, lb2_dtype dtype,
+                            lb2_metric metric, const void* codebook, uint32_t num_sub_vectors,
+                            uint32_t num_bits, lb2_index** out);
+/* load the (row_id, __ivf_part_id, __pq_code) shuffle output (builder.rs:685-937): rows are grouped
+ * by partition on the device (stable, i.e. input order inside a partition). Replaces prior content. */
+lb2_status lb2_index_load(lb2_index* index, const uint32_t* part_ids, const uint8_t* codes,
+                          const uint64_t* row_ids /* NULL = 0..n */, uint64_t n);
+/* IVFIndex::find_partitions + search_in_partition for a BATCH of queries, then the global merge
+ * SortExec(_distance, _rowid).fetch(k) (v2.rs:455-500, rust/lance/src/dataset/scanner.rs:3450-3466).
+ * Outputs [nq][k]; unused slots: row id = UINT64_MAX, distance = +inf; counts_out[nq] nullable. */
+lb2_status lb2_index_search(lb2_index* index, const void* queries, uint64_t nq, uint32_t k,
+                            uint32_t nprobes, uint64_t* row_ids_out, float* dists_out,
+                            uint32_t* counts_out);
+lb2_status lb2_index_info(const lb2_index* index, uint32_t* k, uint32_t* d, uint32_t* num_sub_vectors,
+                          uint32_t* num_bits, uint64_t* num_rows);
+/* export for the host to write index files: any pointer may be NULL.
+ * part_offsets[k+1]; codes [num_rows][M] and row_ids [num_rows] in partition order. */
+lb2_status lb2_index_export(const lb2_index* index, void* centroids_out, void* codebook_out,
+                            uint64_t* part_offsets_out, uint8_t* codes_out, uint64_t* row_ids_out);
+lb2_status lb2_index_destroy(lb2_index* index);
+
+/* IvfIndexBuilder::build (rust/lance/src/index/vector/builder.rs:236): sample -> train IVF ->
+ * residuals -> train PQ -> assign + encode every row -> group by partition, all on the device. */
+typedef struct {
+  uint32_t num_partitions;
+  lb2_kmeans_params ivf;  /* balance_factor 1.0, sample_rate 256 (ivf/builder.rs:62-78) */
+  lb2_pq_params pq;
+  uint64_t seed;          /* training-sample selection */
+} lb2_ivfpq_build_params;
+void lb2_ivfpq_build_params_default(lb2_ivfpq_build_params* p);
+typedef struct {
+  float ms_ivf_train, ms_pq_train, ms_transform, ms_group, ms_total; /* CUDA-event times */
+  uint32_t ivf_iters, pq_iters_max;
+  double ivf_loss;
+} lb2_build_stats;
+lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype dtype,
+                           lb2_metric metric, const lb2_ivfpq_build_params* params,
+                           const uint64_t* row_ids /* NULL = 0..n */, lb2_index** out,
+                           lb2_build_stats* stats /* nullable */);
+
+/* ---- multi-GPU (one process per GPU; NCCL all-reduce of centroid sums during training) ------- */
+/* unique_id is the 128-byte ncclUniqueId produced by rank 0 (lb2_comm_unique_id) and broadcast by
+ * the host runtime (torch.distributed / MPI / the Rust side). */
+lb2_status lb2_comm_unique_id(void* unique_id_128);
+lb2_status lb2_comm_init(const void* unique_id_128, int rank, int nranks);
+lb2_status lb2_comm_destroy(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LANCE_B200_H_ */

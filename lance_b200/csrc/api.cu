@@ -1,0 +1,810 @@
+// api.cu -- the extern "C" surface declared in include/lance_b200.h, the per-thread runtime
+// context, the device-resident index handle and the whole-index builder.
+#include <algorithm>
+#include <cmath>
+#include <unordered_set>
+
+#include "assign.cuh"
+#include "common.cuh"
+#include "exact.cuh"
+#include "kmeans.cuh"
+#include "search.cuh"
+
+namespace lb2 {
+
+// ------------------------------------------------------------------------------------------------
+// runtime context
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static thread_local Ctx* g_ctx = nullptr;
+static thread_local int g_requested_device = 0;
+
+void set_last_error(const std::string& m) { g_last_error = m; }
+
+static int usable_devices() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+Ctx& ctx() {
+  if (g_ctx && g_ctx->device == g_requested_device) {
+    return *g_ctx;
+  }
+  if (usable_devices() <= 0)
+    fail(LB2_NO_DEVICE, "no CUDA device: lance_b200 has no CPU fallback (needs an sm_100a GPU)");
+  LB2_CUDA(cudaSetDevice(g_requested_device));
+  Ctx* c = new Ctx();  // one per (thread, device); lives for the thread's lifetime
+  c->device = g_requested_device;
+  LB2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  LB2_CUDA(cudaEventCreate(&c->t0));
+  LB2_CUDA(cudaEventCreate(&c->t1));
+  cudaDeviceProp prop;
+  LB2_CUDA(cudaGetDeviceProperties(&prop, c->device));
+  c->num_sms = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  // keep freed blocks in the pool: the training loop allocates per iteration
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+    uint64_t thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  g_ctx = c;
+  return *c;
+}
+
+void Ctx::flush_profile() {
+  if (pending.empty()) return;
+  cudaStreamSynchronize(stream);
+  for (auto& e : pending) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.second.first, e.second.second);
+    auto& pe = prof[e.first];
+    pe.launches++;
+    pe.total_ms += ms;
+    cudaEventDestroy(e.second.first);
+    cudaEventDestroy(e.second.second);
+  }
+  pending.clear();
+}
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small elementwise kernels
+// ------------------------------------------------------------------------------------------------
+// x and out may alias (in-place residual of the PQ training sample)
+__global__ void residual_kernel(const float* x, const float* __restrict__ cent,
+                                const uint32_t* __restrict__ part, uint64_t n, int d, float* out) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n * d) return;
+  const uint64_t r = g / d;
+  const int t = g % d;
+  out[g] = __fsub_rn(x[g], cent[(size_t)part[r] * d + t]);  // residual.rs:93
+}
+
+// kernels.rs:141-146: norm = sqrt(sum x^2) accumulated sequentially in f32, then x / norm
+__global__ void normalize_kernel(const float* __restrict__ x, uint64_t n, int d,
+                                 float* __restrict__ out) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float* v = x + r * d;
+  float s = 0.0f;
+  for (int i = 0; i < d; ++i) s = f_add(s, __fmul_rn(v[i], v[i]));
+  const float norm = __fsqrt_rn(s);
+  for (int i = 0; i < d; ++i) out[r * d + i] = __fdiv_rn(v[i], norm);
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ x, const uint64_t* __restrict__ rows,
+                                   uint64_t s, int d, float* __restrict__ out) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= s * d) return;
+  out[g] = x[rows[g / d] * d + g % d];
+}
+
+__global__ void group_kernel(const uint32_t* __restrict__ members, uint64_t n, int M,
+                             const uint8_t* __restrict__ codes, const uint64_t* __restrict__ row_ids,
+                             uint8_t* __restrict__ codes_out, uint64_t* __restrict__ row_ids_out) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const uint32_t src = members[g];
+  row_ids_out[g] = row_ids ? row_ids[src] : (uint64_t)src;
+  for (int m = 0; m < M; ++m) codes_out[g * M + m] = codes[(size_t)src * M + m];
+}
+
+__global__ void widen_offsets_kernel(const uint32_t* __restrict__ off32, int K,
+                                     uint64_t* __restrict__ off64) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= K) off64[i] = off32[i];
+}
+
+static void require_f32(lb2_dtype dt, const char* what) {
+  if (dt != LB2_F32)
+    fail(LB2_UNSUPPORTED, "%s: element type %d is not implemented on the device yet (f32 only)", what,
+         (int)dt);
+}
+static int metric_of(lb2_metric m) {
+  switch (m) {
+    case LB2_L2: return METRIC_L2;
+    case LB2_COSINE: return METRIC_COSINE;
+    case LB2_DOT: return METRIC_DOT;
+  }
+  fail(LB2_INVALID_ARG, "unknown metric %d", (int)m);
+}
+
+}  // namespace lb2
+
+using namespace lb2;
+
+// the handle
+struct lb2_index {
+  int K = 0, d = 0, M = 0, nbits = 8, metric = 0;
+  uint64_t n = 0;
+  DevBuf<float> centroids, codebook;
+  DevBuf<uint64_t> part_offsets, row_ids;
+  DevBuf<uint8_t> codes;
+};
+
+namespace lb2 {
+
+static void index_load_dev(lb2_index* ix, const uint32_t* part_ids, const uint8_t* codes,
+                           const uint64_t* row_ids, uint64_t n) {
+  LB2_REQUIRE(n < 0xffffffffull, "more than 2^32-1 rows per index shard");
+  MemberSort ms;
+  ms.run(part_ids, nullptr, n, ix->K, 1, nullptr);
+  ix->part_offsets.alloc(ix->K + 1);
+  LB2_LAUNCH("widen_offsets", widen_offsets_kernel, cdiv(ix->K + 1, 256), 256, 0, ms.offsets.p,
+             ix->K, ix->part_offsets.p);
+  ix->codes.alloc(std::max<uint64_t>(1, n * ix->M));
+  ix->row_ids.alloc(std::max<uint64_t>(1, n));
+  if (n)
+    LB2_LAUNCH("group_by_partition", group_kernel, cdiv(n, 256), 256, 0, ms.members.p, n, ix->M,
+               codes, row_ids, ix->codes.p, ix->row_ids.p);
+  ix->n = n;
+  sync_stream();
+}
+
+// s distinct rows out of n, ascending (Floyd's algorithm; our rng)
+static std::vector<uint64_t> sample_rows(uint64_t n, uint64_t s, uint64_t seed) {
+  std::vector<uint64_t> out;
+  if (s >= n) {
+    out.resize(n);
+    for (uint64_t i = 0; i < n; ++i) out[i] = i;
+    return out;
+  }
+  SplitMix64 rng(seed);
+  std::unordered_set<uint64_t> chosen;
+  chosen.reserve(s * 2);
+  for (uint64_t j = n - s; j < n; ++j) {
+    uint64_t t = rng.next() % (j + 1);
+    if (!chosen.insert(t).second) chosen.insert(j);
+  }
+  out.assign(chosen.begin(), chosen.end());
+  std::sort(out.begin(), out.end());
+  return out;
+}
+
+static void pq_train_dev(const float* data, uint64_t n, int d, int metric, const lb2_pq_params* p,
+                         float* codebook, std::vector<uint32_t>* iters) {
+  const int M = p->num_sub_vectors, K = 1 << p->num_bits;
+  LB2_REQUIRE(M > 0 && d % M == 0, "num_sub_vectors must divide vector dimension %d, but got %d", d, M);
+  if (p->num_bits != 8) fail(LB2_UNSUPPORTED, "num_bits %u is not implemented on the device", p->num_bits);
+  LB2_REQUIRE(n >= (uint64_t)K, "Not enough rows to train PQ. Requires %d rows but only %llu available",
+              K, (unsigned long long)n);
+  // free fn train_kmeans (kmeans.rs:1328-1340): first sample_rate*k rows
+  const uint64_t rows = n > p->sample_rate * K ? p->sample_rate * K : n;
+  InArg<float> init(p->codebook, (size_t)M * K * (d / M));
+  lloyd_train(data, rows, d, M, d / M, K, metric == METRIC_DOT ? METRIC_DOT : METRIC_L2, 0.0f,
+              (int)p->max_iters, 1e-4, p->seed, init.get(), codebook, nullptr, iters);
+}
+
+}  // namespace lb2
+
+extern "C" {
+
+const char* lb2_version(void) { return "lance_b200 0.1.0 (sm_100a)"; }
+
+size_t lb2_last_error(char* buf, size_t len) {
+  if (buf && len) {
+    size_t c = std::min(len - 1, g_last_error.size());
+    memcpy(buf, g_last_error.data(), c);
+    buf[c] = 0;
+  }
+  return g_last_error.size();
+}
+
+int lb2_device_count(void) { return usable_devices(); }
+
+lb2_status lb2_set_device(int device) {
+  LB2_API_BEGIN
+  int n = usable_devices();
+  if (n <= 0) fail(LB2_NO_DEVICE, "no CUDA device");
+  LB2_REQUIRE(device >= 0 && device < n, "device %d out of range (0..%d)", device, n - 1);
+  g_requested_device = device;
+  LB2_CUDA(cudaSetDevice(device));
+  ctx();
+  LB2_API_END
+}
+lb2_status lb2_synchronize(void) {
+  LB2_API_BEGIN
+  sync_stream();
+  LB2_API_END
+}
+lb2_status lb2_malloc(void** ptr, size_t bytes) {
+  LB2_API_BEGIN
+  ctx();
+  LB2_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));
+  LB2_API_END
+}
+lb2_status lb2_free(void* ptr) {
+  LB2_API_BEGIN
+  ctx();
+  LB2_CUDA(cudaFree(ptr));
+  LB2_API_END
+}
+lb2_status lb2_malloc_host(void** ptr, size_t bytes) {
+  LB2_API_BEGIN
+  ctx();
+  LB2_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1));
+  LB2_API_END
+}
+lb2_status lb2_free_host(void* ptr) {
+  LB2_API_BEGIN
+  ctx();
+  LB2_CUDA(cudaFreeHost(ptr));
+  LB2_API_END
+}
+lb2_status lb2_memcpy(void* dst, const void* src, size_t bytes) {
+  LB2_API_BEGIN
+  LB2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx().stream));
+  sync_stream();
+  LB2_API_END
+}
+lb2_status lb2_launch_count(uint64_t* count, int reset) {
+  LB2_API_BEGIN
+  if (count) *count = ctx().launches;
+  if (reset) ctx().launches = 0;
+  LB2_API_END
+}
+lb2_status lb2_profile_enable(int on) {
+  LB2_API_BEGIN
+  ctx().flush_profile();
+  ctx().profiling = on != 0;
+  LB2_API_END
+}
+lb2_status lb2_profile_get(const char* name, uint64_t* launches, double* total_ms) {
+  LB2_API_BEGIN
+  ctx().flush_profile();
+  auto it = ctx().prof.find(name ? name : "");
+  if (launches) *launches = it == ctx().prof.end() ? 0 : it->second.launches;
+  if (total_ms) *total_ms = it == ctx().prof.end() ? 0.0 : it->second.total_ms;
+  LB2_API_END
+}
+lb2_status lb2_profile_reset(void) {
+  LB2_API_BEGIN
+  ctx().flush_profile();
+  ctx().prof.clear();
+  LB2_API_END
+}
+lb2_status lb2_timer_start(void) {
+  LB2_API_BEGIN
+  LB2_CUDA(cudaEventRecord(ctx().t0, ctx().stream));
+  LB2_API_END
+}
+lb2_status lb2_timer_stop(float* ms_out) {
+  LB2_API_BEGIN
+  LB2_CUDA(cudaEventRecord(ctx().t1, ctx().stream));
+  LB2_CUDA(cudaEventSynchronize(ctx().t1));
+  float ms = 0.f;
+  LB2_CUDA(cudaEventElapsedTime(&ms, ctx().t0, ctx().t1));
+  if (ms_out) *ms_out = ms;
+  LB2_API_END
+}
+
+void lb2_kmeans_params_default(lb2_kmeans_params* p) {
+  p->max_iters = 50;
+  p->tolerance = 1e-4;
+  p->redos = 1;
+  p->balance_factor = 0.0f;
+  p->hierarchical_k = 16;
+  p->sample_rate = 256;
+  p->seed = 0;
+  p->init_centroids = nullptr;
+  p->metric = LB2_L2;
+}
+void lb2_pq_params_default(lb2_pq_params* p) {
+  p->num_sub_vectors = 16;
+  p->num_bits = 8;
+  p->max_iters = 50;
+  p->kmeans_redos = 1;
+  p->sample_rate = 256;
+  p->codebook = nullptr;
+  p->seed = 0;
+}
+void lb2_ivfpq_build_params_default(lb2_ivfpq_build_params* p) {
+  p->num_partitions = 256;
+  lb2_kmeans_params_default(&p->ivf);
+  p->ivf.balance_factor = 1.0f;  // rust/lance/src/index/vector/ivf.rs:1858
+  lb2_pq_params_default(&p->pq);
+  p->seed = 0;
+}
+
+lb2_status lb2_distance_batch(const void* from, const void* to, uint64_t n, uint32_t d,
+                              lb2_dtype dtype, lb2_metric metric, float* out) {
+  LB2_API_BEGIN
+  require_f32(dtype, "distance_batch");
+  const int m = metric_of(metric);
+  if (m == METRIC_COSINE) fail(LB2_UNSUPPORTED, "cosine_distance_batch is not implemented yet");
+  LB2_REQUIRE(d > 0, "dimension must be positive");
+  LB2_REQUIRE(n < (1ull << 31), "too many rows");
+  InArg<float> f(from, d), t(to, (size_t)n * d);
+  OutArg<float> o(out, n);
+  assign_f32(f.get(), 1, d, t.get(), (int)n, m, nullptr, nullptr, nullptr, nullptr, o.get());
+  o.commit();
+  sync_stream();
+  LB2_API_END
+}
+
+lb2_status lb2_normalize(const void* vectors, uint64_t n, uint32_t d, lb2_dtype dtype, void* out) {
+  LB2_API_BEGIN
+  require_f32(dtype, "normalize");
+  InArg<float> x(vectors, (size_t)n * d);
+  OutArg<float> o(out, (size_t)n * d);
+  if (n) LB2_LAUNCH("normalize", normalize_kernel, cdiv(n, 128), 128, 0, x.get(), n, (int)d, o.get());
+  o.commit();
+  sync_stream();
+  LB2_API_END
+}
+
+lb2_status lb2_kmeans_train(const void* data, uint64_t n, uint32_t d, lb2_dtype dtype, uint32_t k,
+                            const lb2_kmeans_params* params, void* centroids_out, double* loss_out,
+                            uint32_t* iters_out) {
+  LB2_API_BEGIN
+  require_f32(dtype, "kmeans_train");
+  LB2_REQUIRE(params && data && centroids_out, "null argument");
+  const int m = metric_of(params->metric);
+  if (m == METRIC_COSINE)
+    fail(LB2_INVALID_ARG, "KMeans: cosine is trained as L2 on normalised vectors (normalise first)");
+  LB2_REQUIRE(n >= k, "KMeans: can not train %u centroids with %llu vectors, choose a smaller K (< %llu) instead",
+              k, (unsigned long long)n, (unsigned long long)n);
+  // free fn train_kmeans (kmeans.rs:1328-1344)
+  const uint64_t rows = n > params->sample_rate * k ? params->sample_rate * k : n;
+  InArg<float> x(data, (size_t)rows * d);
+  InArg<float> init(params->init_centroids, (size_t)k * d);
+  DevBuf<float> cent((size_t)k * d);
+  std::vector<double> loss;
+  std::vector<uint32_t> iters;
+  lloyd_train(x.get(), rows, d, 1, d, k, m, params->balance_factor / (float)rows,
+              (int)params->max_iters, params->tolerance, params->seed, init.get(), cent.p, &loss,
+              &iters);
+  OutArg<float> o(centroids_out, (size_t)k * d);
+  d2d(o.get(), cent.p, (size_t)k * d);
+  o.commit();
+  sync_stream();
+  if (loss_out) *loss_out = loss[0];
+  if (iters_out) *iters_out = iters[0];
+  LB2_API_END
+}
+
+lb2_status lb2_compute_partitions(const void* centroids, uint32_t k, uint32_t d, lb2_dtype dtype,
+                                  lb2_metric metric, const void* vectors, uint64_t n,
+                                  uint32_t* part_out, float* dist_out, uint8_t* valid_out) {
+  LB2_API_BEGIN
+  require_f32(dtype, "compute_partitions");
+  const int m = metric_of(metric);
+  if (m == METRIC_COSINE) fail(LB2_INVALID_ARG, "compute_partitions: normalise and use L2 for cosine");
+  InArg<float> c(centroids, (size_t)k * d), x(vectors, (size_t)n * d);
+  OutArg<uint32_t> p(part_out, n);
+  OutArg<float> dd(dist_out, n);
+  OutArg<uint8_t> v(valid_out, n);
+  assign_f32(x.get(), n, d, c.get(), k, m, nullptr, p.get(), dd.get(), v.get(), nullptr);
+  p.commit(); dd.commit(); v.commit();
+  sync_stream();
+  LB2_API_END
+}
+
+lb2_status lb2_find_partitions(const void* centroids, uint32_t k, uint32_t d, lb2_dtype dtype,
+                               lb2_metric metric, const void* queries, uint64_t nq,
+                               uint32_t nprobes, uint32_t* ids_out, float* dists_out) {
+  LB2_API_BEGIN
+  require_f32(dtype, "find_partitions");
+  const int m = metric_of(metric);
+  if (m == METRIC_COSINE) fail(LB2_INVALID_ARG, "find_partitions: normalise and use L2 for cosine");
+  const uint32_t np = std::min(nprobes, k);
+  LB2_REQUIRE(np == nprobes, "nprobes %u exceeds the number of partitions %u", nprobes, k);
+  InArg<float> c(centroids, (size_t)k * d), q(queries, (size_t)nq * d);
+  OutArg<uint32_t> ids(ids_out, (size_t)nq * np);
+  OutArg<float> dd(dists_out, (size_t)nq * np);
+  find_partitions_f32(c.get(), k, d, m, q.get(), nq, np, ids.get(), dd.get());
+  ids.commit(); dd.commit();
+  sync_stream();
+  LB2_API_END
+}
+
+lb2_status lb2_compute_residual(const void* centroids, uint32_t k, uint32_t d, lb2_dtype dtype,
+                                const void* vectors, uint64_t n, const uint32_t* part_ids,
+                                void* out) {
+  LB2_API_BEGIN
+  require_f32(dtype, "compute_residual");
+  InArg<float> c(centroids, (size_t)k * d), x(vectors, (size_t)n * d);
+  InArg<uint32_t> p(part_ids, n);
+  OutArg<float> o(out, (size_t)n * d);
+  if (n)
+    LB2_LAUNCH("residual", residual_kernel, cdiv(n * d, 256), 256, 0, x.get(), c.get(), p.get(), n,
+               (int)d, o.get());
+  o.commit();
+  sync_stream();
+  LB2_API_END
+}
+
+lb2_status lb2_pq_train(const void* data, uint64_t n, uint32_t d, lb2_dtype dtype,
+                        lb2_metric metric, const lb2_pq_params* params, void* codebook_out,
+                        uint32_t* iters_out) {
+  LB2_API_BEGIN
+  require_f32(dtype, "pq_train");
+  LB2_REQUIRE(params && data && codebook_out, "null argument");
+  const int m = metric_of(metric);
+  if (m == METRIC_COSINE) fail(LB2_INVALID_ARG, "PQ code does not support cosine");  // pq/builder.rs:98-102
+  InArg<float> x(data, (size_t)n * d);
+  const size_t cb = (size_t)(1u << params->num_bits) * d;
+  DevBuf<float> codebook(cb);
+  std::vector<uint32_t> iters;
+  pq_train_dev(x.get(), n, d, m, params, codebook.p, &iters);
+  OutArg<float> o(codebook_out, cb);
+  d2d(o.get(), codebook.p, cb);
+  o.commit();
+  sync_stream();
+  if (iters_out)
+    for (uint32_t i = 0; i < params->num_sub_vectors; ++i) iters_out[i] = iters[i];
+  LB2_API_END
+}
+
+lb2_status lb2_pq_encode(const void* codebook, uint32_t num_sub_vectors, uint32_t num_bits,
+                         uint32_t d, lb2_dtype dtype, lb2_metric metric, const void* centroids,
+                         const uint32_t* part_ids, const void* vectors, uint64_t n,
+                         uint8_t* codes_out) {
+  LB2_API_BEGIN
+  require_f32(dtype, "pq_encode");
+  if (num_bits != 8) fail(LB2_UNSUPPORTED, "num_bits %u is not implemented on the device", num_bits);
+  const int M = num_sub_vectors, ds = d / M;
+  LB2_REQUIRE(M > 0 && d % M == 0, "num_sub_vectors must divide vector dimension %u, but got %d", d, M);
+  LB2_REQUIRE((centroids == nullptr) == (part_ids == nullptr),
+              "centroids and part_ids must be given together");
+  const int m = metric_of(metric) == METRIC_DOT ? METRIC_DOT : METRIC_L2;
+  if (!small_d_supported(ds)) fail(LB2_UNSUPPORTED, "PQ sub-vector width %d not supported yet", ds);
+  InArg<float> cb(codebook, (size_t)256 * d), x(vectors, (size_t)n * d);
+  uint64_t kmax = 0;
+  InArg<float> c;
+  InArg<uint32_t> p(part_ids, n);
+  if (centroids) {
+    // the number of IVF centroids is implied by part_ids; stage what the caller holds
+    if (is_device_ptr(centroids)) {
+      c.dev = (const float*)centroids;
+    } else {
+      for (uint64_t i = 0; i < n && !is_device_ptr(part_ids); ++i) kmax = std::max<uint64_t>(kmax, part_ids[i]);
+      if (is_device_ptr(part_ids)) fail(LB2_INVALID_ARG, "host centroids with device part_ids");
+      c.set(centroids, (size_t)(kmax + 1) * d);
+    }
+  }
+  OutArg<uint8_t> o(codes_out, (size_t)n * M);
+  small_d_assign_f32(x.get(), n, d, M, ds, cb.get(), 256, m, c.get(), p.get(), nullptr, o.get(),
+                     nullptr, nullptr, nullptr, nullptr);
+  o.commit();
+  sync_stream();
+  LB2_API_END
+}
+
+lb2_status lb2_pq_build_lut(const void* codebook, uint32_t num_sub_vectors, uint32_t num_bits,
+                            uint32_t d, lb2_metric metric, const float* query, float* lut_out) {
+  LB2_API_BEGIN
+  const int ncode = 1 << num_bits;
+  LB2_REQUIRE(num_sub_vectors > 0 && d % num_sub_vectors == 0, "num_sub_vectors must divide d");
+  InArg<float> cb(codebook, (size_t)ncode * d), q(query, d);
+  OutArg<float> o(lut_out, (size_t)num_sub_vectors * ncode);
+  build_lut_f32(cb.get(), num_sub_vectors, num_bits, d,
+                metric_of(metric) == METRIC_DOT ? METRIC_DOT : METRIC_L2, q.get(), o.get());
+  o.commit();
+  sync_stream();
+  LB2_API_END
+}
+
+lb2_status lb2_pq_scan(const float* lut, uint32_t num_sub_vectors, uint32_t num_bits,
+                       lb2_metric metric, const uint8_t* codes_transposed, uint64_t n,
+                       float* dists_out) {
+  LB2_API_BEGIN
+  if (num_bits != 8) fail(LB2_UNSUPPORTED, "num_bits %u is not implemented on the device", num_bits);
+  InArg<float> l(lut, (size_t)num_sub_vectors * 256);
+  InArg<uint8_t> c(codes_transposed, (size_t)n * num_sub_vectors);
+  OutArg<float> o(dists_out, n);
+  pq_scan_transposed_f32(l.get(), num_sub_vectors, metric_of(metric), c.get(), n, o.get());
+  o.commit();
+  sync_stream();
+  LB2_API_END
+}
+
+lb2_status lb2_flat_topk(const float* dists, const uint64_t* row_ids, uint64_t n, uint32_t k,
+                         uint64_t* ids_out, float* dists_out, uint32_t* count_out) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(k > 0, "k must be positive");
+  LB2_REQUIRE(n < 0xffffffffull, "too many rows");
+  InArg<float> dd(dists, n);
+  InArg<uint64_t> r(row_ids, n);
+  OutArg<uint64_t> oi(ids_out, k);
+  OutArg<float> od(dists_out, k);
+  OutArg<uint32_t> oc(count_out, 1);
+  DevBuf<uint32_t> cnt_tmp;
+  uint32_t* cp = oc.get();
+  if (!cp) { cnt_tmp.alloc(1); cp = cnt_tmp.p; }
+  flat_topk_f32(dd.get(), r.get(), n, k, oi.get(), od.get(), cp);
+  oi.commit(); od.commit(); oc.commit();
+  sync_stream();
+  LB2_API_END
+}
+
+lb2_status lb2_ivfpq_transform(const void* centroids, uint32_t k, const void* codebook,
+                               uint32_t num_sub_vectors, uint32_t num_bits, uint32_t d,
+                               lb2_dtype dtype, lb2_metric metric, const void* vectors, uint64_t n,
+                               uint32_t* part_out, uint8_t* codes_out, uint8_t* valid_out) {
+  LB2_API_BEGIN
+  require_f32(dtype, "ivfpq_transform");
+  if (num_bits != 8) fail(LB2_UNSUPPORTED, "num_bits %u is not implemented on the device", num_bits);
+  const int M = num_sub_vectors, ds = d / M;
+  LB2_REQUIRE(M > 0 && d % M == 0, "num_sub_vectors must divide vector dimension %u, but got %d", d, M);
+  if (!small_d_supported(ds)) fail(LB2_UNSUPPORTED, "PQ sub-vector width %d not supported yet", ds);
+  const int m = metric_of(metric);
+  InArg<float> c(centroids, (size_t)k * d), cb(codebook, (size_t)256 * d), x(vectors, (size_t)n * d);
+  OutArg<uint32_t> p(part_out, n);
+  OutArg<uint8_t> co(codes_out, (size_t)n * M), v(valid_out, n);
+  DevBuf<uint8_t> vtmp;
+  uint8_t* vp = v.get();
+  if (!vp) { vtmp.alloc(std::max<uint64_t>(n, 1)); vp = vtmp.p; }
+  const float* xp = x.get();
+  DevBuf<float> xn;
+  if (m == METRIC_COSINE) {  // ivf.rs:198-205: normalise, then L2
+    xn.alloc((size_t)n * d);
+    if (n) LB2_LAUNCH("normalize", normalize_kernel, cdiv(n, 128), 128, 0, xp, n, (int)d, xn.p);
+    xp = xn.p;
+  }
+  const int am = m == METRIC_DOT ? METRIC_DOT : METRIC_L2;
+  assign_f32(xp, n, d, c.get(), k, am, nullptr, p.get(), nullptr, vp, nullptr);
+  small_d_assign_f32(xp, n, d, M, ds, cb.get(), 256, am, am == METRIC_DOT ? nullptr : c.get(),
+                     am == METRIC_DOT ? nullptr : p.get(), vp, co.get(), nullptr, nullptr, nullptr,
+                     nullptr);
+  p.commit(); co.commit(); v.commit();
+  sync_stream();
+  LB2_API_END
+}
+
+lb2_status lb2_index_create(const void* centroids, uint32_t k, uint32_t d, lb2_dtype dtype,
+                            lb2_metric metric, const void* codebook, uint32_t num_sub_vectors,
+                            uint32_t num_bits, lb2_index** out) {
+  LB2_API_BEGIN
+  require_f32(dtype, "index_create");
+  LB2_REQUIRE(out && centroids && codebook, "null argument");
+  LB2_REQUIRE(num_sub_vectors > 0 && d % num_sub_vectors == 0, "num_sub_vectors must divide d");
+  if (num_bits != 8) fail(LB2_UNSUPPORTED, "num_bits %u is not implemented on the device", num_bits);
+  ctx();
+  lb2_index* ix = new lb2_index();
+  ix->K = k; ix->d = d; ix->M = num_sub_vectors; ix->nbits = num_bits; ix->metric = metric_of(metric);
+  ix->centroids.alloc((size_t)k * d);
+  ix->codebook.alloc((size_t)256 * d);
+  LB2_CUDA(cudaMemcpyAsync(ix->centroids.p, centroids, sizeof(float) * k * d, cudaMemcpyDefault, ctx().stream));
+  LB2_CUDA(cudaMemcpyAsync(ix->codebook.p, codebook, sizeof(float) * 256 * d, cudaMemcpyDefault, ctx().stream));
+  ix->part_offsets.alloc(k + 1);
+  ix->part_offsets.zero();
+  sync_stream();
+  *out = ix;
+  LB2_API_END
+}
+
+lb2_status lb2_index_load(lb2_index* index, const uint32_t* part_ids, const uint8_t* codes,
+                          const uint64_t* row_ids, uint64_t n) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(index, "null index");
+  InArg<uint32_t> p(part_ids, n);
+  InArg<uint8_t> c(codes, (size_t)n * index->M);
+  InArg<uint64_t> r(row_ids, n);
+  index_load_dev(index, p.get(), c.get(), r.get(), n);
+  LB2_API_END
+}
+
+lb2_status lb2_index_search(lb2_index* index, const void* queries, uint64_t nq, uint32_t k,
+                            uint32_t nprobes, uint64_t* row_ids_out, float* dists_out,
+                            uint32_t* counts_out) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(index && k > 0 && nprobes > 0, "bad argument");
+  const int d = index->d;
+  InArg<float> q(queries, (size_t)nq * d);
+  const float* qp = q.get();
+  DevBuf<float> qn;
+  if (index->metric == METRIC_COSINE) {  // knn.rs:497-499
+    qn.alloc((size_t)nq * d);
+    if (nq) LB2_LAUNCH("normalize", normalize_kernel, cdiv(nq, 128), 128, 0, qp, nq, d, qn.p);
+    qp = qn.p;
+  }
+  OutArg<uint64_t> oi(row_ids_out, (size_t)nq * k);
+  OutArg<float> od(dists_out, (size_t)nq * k);
+  OutArg<uint32_t> oc(counts_out, nq);
+  ivfpq_search_f32(index->centroids.p, index->K, d, index->metric, index->codebook.p, index->M,
+                   index->nbits, index->part_offsets.p, index->codes.p, index->row_ids.p, qp, nq, k,
+                   nprobes, oi.get(), od.get(), oc.get());
+  oi.commit(); od.commit(); oc.commit();
+  sync_stream();
+  LB2_API_END
+}
+
+lb2_status lb2_index_info(const lb2_index* index, uint32_t* k, uint32_t* d, uint32_t* num_sub_vectors,
+                          uint32_t* num_bits, uint64_t* num_rows) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(index, "null index");
+  if (k) *k = index->K;
+  if (d) *d = index->d;
+  if (num_sub_vectors) *num_sub_vectors = index->M;
+  if (num_bits) *num_bits = index->nbits;
+  if (num_rows) *num_rows = index->n;
+  LB2_API_END
+}
+
+lb2_status lb2_index_export(const lb2_index* index, void* centroids_out, void* codebook_out,
+                            uint64_t* part_offsets_out, uint8_t* codes_out, uint64_t* row_ids_out) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(index, "null index");
+  cudaStream_t s = ctx().stream;
+  if (centroids_out)
+    LB2_CUDA(cudaMemcpyAsync(centroids_out, index->centroids.p, sizeof(float) * index->K * index->d, cudaMemcpyDefault, s));
+  if (codebook_out)
+    LB2_CUDA(cudaMemcpyAsync(codebook_out, index->codebook.p, sizeof(float) * 256 * index->d, cudaMemcpyDefault, s));
+  if (part_offsets_out)
+    LB2_CUDA(cudaMemcpyAsync(part_offsets_out, index->part_offsets.p, sizeof(uint64_t) * (index->K + 1), cudaMemcpyDefault, s));
+  if (codes_out && index->n)
+    LB2_CUDA(cudaMemcpyAsync(codes_out, index->codes.p, index->n * index->M, cudaMemcpyDefault, s));
+  if (row_ids_out && index->n)
+    LB2_CUDA(cudaMemcpyAsync(row_ids_out, index->row_ids.p, sizeof(uint64_t) * index->n, cudaMemcpyDefault, s));
+  sync_stream();
+  LB2_API_END
+}
+
+lb2_status lb2_index_destroy(lb2_index* index) {
+  LB2_API_BEGIN
+  if (index) {
+    ctx();
+    delete index;
+    sync_stream();
+  }
+  LB2_API_END
+}
+
+lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype dtype,
+                           lb2_metric metric, const lb2_ivfpq_build_params* params,
+                           const uint64_t* row_ids, lb2_index** out, lb2_build_stats* stats) {
+  LB2_API_BEGIN
+  require_f32(dtype, "ivfpq_build");
+  LB2_REQUIRE(data && params && out, "null argument");
+  const int m = metric_of(metric);
+  const int K = params->num_partitions, M = params->pq.num_sub_vectors;
+  LB2_REQUIRE(K > 0 && n >= (uint64_t)K, "KMeans: can not train %d centroids with %llu vectors", K,
+              (unsigned long long)n);
+  LB2_REQUIRE(M > 0 && d % M == 0, "num_sub_vectors must divide vector dimension %u, but got %d", d, M);
+  if (params->pq.num_bits != 8) fail(LB2_UNSUPPORTED, "num_bits %u is not implemented", params->pq.num_bits);
+  const int ds = d / M;
+  if (!small_d_supported(ds)) fail(LB2_UNSUPPORTED, "PQ sub-vector width %d not supported yet", ds);
+  Ctx& c = ctx();
+  cudaEvent_t ev[5];
+  for (auto& e : ev) LB2_CUDA(cudaEventCreate(&e));
+  LB2_CUDA(cudaEventRecord(ev[0], c.stream));
+
+  InArg<float> xin(data, (size_t)n * d);
+  const float* x = xin.get();
+  DevBuf<float> xnorm;
+  if (m == METRIC_COSINE) {  // normalise once; the reference normalises samples and every batch
+    xnorm.alloc((size_t)n * d);
+    LB2_LAUNCH("normalize", normalize_kernel, cdiv(n, 128), 128, 0, x, n, (int)d, xnorm.p);
+    x = xnorm.p;
+  }
+  const int am = m == METRIC_DOT ? METRIC_DOT : METRIC_L2;
+
+  lb2_index* ix = new lb2_index();
+  ix->K = K; ix->d = d; ix->M = M; ix->nbits = 8; ix->metric = m;
+  ix->centroids.alloc((size_t)K * d);
+  ix->codebook.alloc((size_t)256 * d);
+  std::vector<double> ivf_loss;
+  std::vector<uint32_t> ivf_iters, pq_iters;
+  try {
+    // 1. IVF: sample K*sample_rate rows (rust/lance/src/index/vector/ivf.rs:1237-1241)
+    {
+      const uint64_t s = std::min<uint64_t>(n, (uint64_t)K * params->ivf.sample_rate);
+      const float* xs = x;
+      DevBuf<float> sample;
+      if (s < n) {
+        std::vector<uint64_t> rows = sample_rows(n, s, params->seed);
+        DevBuf<uint64_t> rows_d(s);
+        h2d(rows_d.p, rows.data(), s);
+        sample.alloc((size_t)s * d);
+        LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(s * d, 256), 256, 0, x, rows_d.p, s, (int)d, sample.p);
+        sync_stream();
+        xs = sample.p;
+      }
+      InArg<float> init(params->ivf.init_centroids, (size_t)K * d);
+      lloyd_train(xs, s, d, 1, d, K, am, params->ivf.balance_factor / (float)s,
+                  (int)params->ivf.max_iters, params->ivf.tolerance, params->ivf.seed, init.get(),
+                  ix->centroids.p, &ivf_loss, &ivf_iters);
+    }
+    LB2_CUDA(cudaEventRecord(ev[1], c.stream));
+    // 2. PQ: sample 256*2^nbits rows, residuals w.r.t. the IVF centroids (builder.rs:410-450)
+    {
+      const uint64_t s = std::min<uint64_t>(n, params->pq.sample_rate * 256);
+      std::vector<uint64_t> rows = sample_rows(n, s, params->seed + 1);
+      DevBuf<uint64_t> rows_d(s);
+      h2d(rows_d.p, rows.data(), s);
+      DevBuf<float> sample((size_t)s * d);
+      LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(s * d, 256), 256, 0, x, rows_d.p, s, (int)d, sample.p);
+      sync_stream();
+      if (am == METRIC_L2) {
+        DevBuf<uint32_t> part(s);
+        assign_f32(sample.p, s, d, ix->centroids.p, K, METRIC_L2, nullptr, part.p, nullptr, nullptr, nullptr);
+        LB2_LAUNCH("residual", residual_kernel, cdiv(s * d, 256), 256, 0, sample.p, ix->centroids.p,
+                   part.p, s, (int)d, sample.p);
+      }
+      pq_train_dev(sample.p, s, d, am, &params->pq, ix->codebook.p, &pq_iters);
+    }
+    LB2_CUDA(cudaEventRecord(ev[2], c.stream));
+    // 3. transform every row (lance-index/src/vector/ivf.rs:357: partition -> residual -> PQ)
+    DevBuf<uint32_t> part(n);
+    DevBuf<uint8_t> codes((size_t)n * M), valid(n);
+    assign_f32(x, n, d, ix->centroids.p, K, am, nullptr, part.p, nullptr, valid.p, nullptr);
+    small_d_assign_f32(x, n, d, M, ds, ix->codebook.p, 256, am,
+                       am == METRIC_DOT ? nullptr : ix->centroids.p,
+                       am == METRIC_DOT ? nullptr : part.p, valid.p, codes.p, nullptr, nullptr,
+                       nullptr, nullptr);
+    LB2_CUDA(cudaEventRecord(ev[3], c.stream));
+    // 4. group rows by partition (shuffle + build_partitions, builder.rs:501-937)
+    InArg<uint64_t> rid(row_ids, n);
+    index_load_dev(ix, part.p, codes.p, rid.get(), n);
+    LB2_CUDA(cudaEventRecord(ev[4], c.stream));
+    sync_stream();
+  } catch (...) {
+    delete ix;
+    throw;
+  }
+  if (stats) {
+    cudaEventElapsedTime(&stats->ms_ivf_train, ev[0], ev[1]);
+    cudaEventElapsedTime(&stats->ms_pq_train, ev[1], ev[2]);
+    cudaEventElapsedTime(&stats->ms_transform, ev[2], ev[3]);
+    cudaEventElapsedTime(&stats->ms_group, ev[3], ev[4]);
+    cudaEventElapsedTime(&stats->ms_total, ev[0], ev[4]);
+    stats->ivf_iters = ivf_iters.empty() ? 0 : ivf_iters[0];
+    stats->pq_iters_max = 0;
+    for (auto v : pq_iters) stats->pq_iters_max = std::max(stats->pq_iters_max, v);
+    stats->ivf_loss = ivf_loss.empty() ? 0.0 : ivf_loss[0];
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  *out = ix;
+  LB2_API_END
+}
+
+lb2_status lb2_comm_unique_id(void*) {
+  LB2_API_BEGIN
+  fail(LB2_UNSUPPORTED, "multi-GPU communicator is not built yet");
+  LB2_API_END
+}
+lb2_status lb2_comm_init(const void*, int, int) {
+  LB2_API_BEGIN
+  fail(LB2_UNSUPPORTED, "multi-GPU communicator is not built yet");
+  LB2_API_END
+}
+lb2_status lb2_comm_destroy(void) {
+  LB2_API_BEGIN
+  LB2_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,421 @@
+// assign.cu -- EXACT (reference-order f32) nearest-centroid kernels.
+//
+// Replaces the inner loops of
+//   KMeansAlgoFloat::compute_membership_and_dist   lance-index/src/vector/kmeans.rs:317-369
+//   compute_partitions_with_dists                   kmeans.rs:1275-1294
+//   compute_partition (PQ code assignment)          kmeans.rs:1350-1369, pq.rs:148-178
+//   l2_distance_batch / dot_distance_batch          lance-linalg/src/distance/l2.rs:194, dot.rs:164
+// Three kernels, all producing bit-identical distances to the reference's 16-lane scalar loops:
+//   (a) assign_tile_kernel   d % 16 == 0, d <= 256: 64 rows x 64 centroids per tile, 4x4 per thread,
+//       lane-outer / chunk-inner so only two accumulators per pair are live;
+//   (b) small_d_kernel       d < 16 (PQ sub-vectors, tail-only path of l2.rs:69-79), batched over
+//       the M sub-spaces, optional fused residual (residual.rs:86-95), u8 codes or u32 ids out;
+//   (c) generic_kernel       any d: half-warp per centroid, lane l owns lane-accumulator l.
+#include "assign.cuh"
+#include "common.cuh"
+#include "exact.cuh"
+
+namespace lb2 {
+
+// ------------------------------------------------------------------------------------------------
+// transposed, padded copy of the centroids: cT[e][Kp], pad columns = NaN (never win an argmin)
+// ------------------------------------------------------------------------------------------------
+__global__ void transpose_pad_kernel(const float* __restrict__ c, int K, int d, int Kp,
+                                     float* __restrict__ cT) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= d * Kp) return;
+  int e = idx / Kp, k = idx % Kp;
+  cT[idx] = k < K ? c[(size_t)k * d + e] : __int_as_float(0x7fc00000);
+}
+
+// ------------------------------------------------------------------------------------------------
+// (a) tile kernel
+// ------------------------------------------------------------------------------------------------
+template <int METRIC, bool WRITE_ALL>
+__global__ void __launch_bounds__(256)
+assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __restrict__ cT,
+                   int K, int Kp, const float* __restrict__ bias, uint32_t* __restrict__ part,
+                   float* __restrict__ dist, uint8_t* __restrict__ valid,
+                   float* __restrict__ all_out) {
+  extern __shared__ float smem[];
+  const int ld = d + 1;
+  float* xs = smem;            // [64][d+1]
+  float* cs = smem + 64 * ld;  // [d][64]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const uint64_t row0 = (uint64_t)blockIdx.x * 64;
+
+  for (int idx = tid; idx < 16 * d; idx += 256) {  // 64*d/4 float4
+    int r = (idx * 4) / d, e = (idx * 4) % d;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < n) v = *reinterpret_cast<const float4*>(x + (row0 + r) * d + e);
+    float* dst = xs + r * ld + e;
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+  }
+  float best_key[4], best_val[4];
+  uint32_t best_idx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    best_key[i] = __int_as_float(0x7f800000);
+    best_val[i] = __int_as_float(0x7f800000);
+    best_idx[i] = 0xffffffffu;
+  }
+  const int nchunk = d >> 4;
+  const float* xrow = xs + (ty * 4) * ld;
+  for (int ct = 0; ct < Kp; ct += 64) {
+    __syncthreads();
+    for (int idx = tid; idx < d * 16; idx += 256) {
+      int e = idx >> 4, q = idx & 15;
+      *reinterpret_cast<float4*>(cs + e * 64 + q * 4) =
+          *reinterpret_cast<const float4*>(cT + (size_t)e * Kp + ct + q * 4);
+    }
+    __syncthreads();
+    float total[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) total[i][j] = 0.0f;
+    for (int l = 0; l < 16; ++l) {
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+#pragma unroll 2
+      for (int c = 0; c < nchunk; ++c) {
+        const int e = c * 16 + l;
+        const float4 cv = *reinterpret_cast<const float4*>(cs + e * 64 + tx * 4);
+        float xv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv[i] = xrow[i * ld + e];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[i][0] = f_add(acc[i][0], term<METRIC>(xv[i], cv.x));
+          acc[i][1] = f_add(acc[i][1], term<METRIC>(xv[i], cv.y));
+          acc[i][2] = f_add(acc[i][2], term<METRIC>(xv[i], cv.z));
+          acc[i][3] = f_add(acc[i][3], term<METRIC>(xv[i], cv.w));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) total[i][j] = f_add(total[i][j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t cidx = ct + tx * 4 + j;
+        const float v = finish<METRIC>(total[i][j]);
+        if (WRITE_ALL) {
+          const uint64_t r = row0 + ty * 4 + i;
+          if (r < n && cidx < (uint32_t)K) all_out[r * K + cidx] = v;
+        } else {
+          const float key = bias ? f_add(v, bias[cidx < (uint32_t)K ? cidx : 0]) : v;
+          if (key < best_key[i]) {
+            best_key[i] = key;
+            best_val[i] = v;
+            best_idx[i] = cidx;
+          }
+        }
+      }
+    }
+  }
+  if (WRITE_ALL) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {
+      float ok = __shfl_xor_sync(0xffffffffu, best_key[i], off);
+      float ov = __shfl_xor_sync(0xffffffffu, best_val[i], off);
+      uint32_t oi = __shfl_xor_sync(0xffffffffu, best_idx[i], off);
+      if (better(ok, oi, best_key[i], best_idx[i])) {
+        best_key[i] = ok; best_val[i] = ov; best_idx[i] = oi;
+      }
+    }
+    const uint64_t r = row0 + ty * 4 + i;
+    if (tx == 0 && r < n) {
+      const bool ok = best_idx[i] != 0xffffffffu;
+      part[r] = ok ? best_idx[i] : 0u;
+      if (dist) dist[r] = ok ? best_val[i] : __int_as_float(0x7fc00000);
+      if (valid) valid[r] = ok ? 1 : 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (b) small-d kernel (d < 16: only the sequential "remainder" loop of l2.rs:69-79 runs)
+//   grid = (row tiles of 64, M).  x element (row, t) = x[row*ldx + m*DS + t] (- centroid[part[row]]).
+// ------------------------------------------------------------------------------------------------
+template <int DS, int METRIC, bool CODES>
+__global__ void __launch_bounds__(256)
+small_d_kernel(const float* __restrict__ x, uint64_t n, int ldx, const float* __restrict__ codebook,
+               int Kc, const float* __restrict__ ivf_centroids, const uint32_t* __restrict__ part_ids,
+               const uint8_t* __restrict__ row_valid, uint8_t* __restrict__ codes, int M,
+               uint32_t* __restrict__ ids, float* __restrict__ dists, uint8_t* __restrict__ valid,
+               const uint8_t* __restrict__ active) {
+  const int m = blockIdx.y;
+  if (active && !active[m]) return;
+  __shared__ __align__(16) float cs[DS][64];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const uint64_t row0 = (uint64_t)blockIdx.x * 64;
+  const float* cb = codebook + (size_t)m * Kc * DS;
+
+  float xr[4][DS];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint64_t r = row0 + ty * 4 + i;
+    if (r < n) {
+      const float* src = x + r * (uint64_t)ldx + m * DS;
+      if (ivf_centroids) {
+        const float* c = ivf_centroids + (uint64_t)part_ids[r] * ldx + m * DS;
+#pragma unroll
+        for (int t = 0; t < DS; ++t) xr[i][t] = __fsub_rn(src[t], c[t]);  // residual.rs:93
+      } else {
+#pragma unroll
+        for (int t = 0; t < DS; ++t) xr[i][t] = src[t];
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < DS; ++t) xr[i][t] = 0.0f;
+    }
+  }
+  float best_val[4];
+  uint32_t best_idx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    best_val[i] = __int_as_float(0x7f800000);
+    best_idx[i] = 0xffffffffu;
+  }
+  for (int ct = 0; ct < Kc; ct += 64) {
+    __syncthreads();
+    for (int idx = tid; idx < 64 * DS; idx += 256) {
+      int k = idx / DS, t = idx % DS;
+      cs[t][k] = (ct + k < Kc) ? cb[(size_t)(ct + k) * DS + t] : __int_as_float(0x7fc00000);
+    }
+    __syncthreads();
+    float tot[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tot[i][j] = 0.0f;
+#pragma unroll
+    for (int t = 0; t < DS; ++t) {
+      const float4 cv = *reinterpret_cast<const float4*>(&cs[t][tx * 4]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        tot[i][0] = f_add(tot[i][0], term<METRIC>(xr[i][t], cv.x));
+        tot[i][1] = f_add(tot[i][1], term<METRIC>(xr[i][t], cv.y));
+        tot[i][2] = f_add(tot[i][2], term<METRIC>(xr[i][t], cv.z));
+        tot[i][3] = f_add(tot[i][3], term<METRIC>(xr[i][t], cv.w));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v = finish<METRIC>(f_add(tot[i][j], 0.0f));
+        const uint32_t cidx = ct + tx * 4 + j;
+        if (v < best_val[i]) {
+          best_val[i] = v;
+          best_idx[i] = cidx;
+        }
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best_val[i], off);
+      uint32_t oi = __shfl_xor_sync(0xffffffffu, best_idx[i], off);
+      if (better(ov, oi, best_val[i], best_idx[i])) {
+        best_val[i] = ov; best_idx[i] = oi;
+      }
+    }
+    const uint64_t r = row0 + ty * 4 + i;
+    if (tx == 0 && r < n) {
+      const bool ok = best_idx[i] != 0xffffffffu;
+      if (CODES) {
+        // pq.rs:165 `unwrap_or(0)`; rows KeepFinite would drop get all-zero codes
+        const bool rv = row_valid ? row_valid[r] != 0 : true;
+        codes[r * (uint64_t)M + m] = (ok && rv) ? (uint8_t)best_idx[i] : (uint8_t)0;
+      } else {
+        ids[(uint64_t)m * n + r] = ok ? best_idx[i] : 0u;
+        if (dists) dists[(uint64_t)m * n + r] = ok ? best_val[i] : __int_as_float(0x7fc00000);
+        if (valid) valid[(uint64_t)m * n + r] = ok ? 1 : 0;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (c) generic kernel: 8 rows per CTA in smem, 16 half-warps stride over the centroids, lane l of a
+// half-warp owns lane-accumulator l (elements 16c+l) -> coalesced 64-byte centroid reads.
+// ------------------------------------------------------------------------------------------------
+template <int METRIC, bool WRITE_ALL>
+__global__ void __launch_bounds__(256)
+generic_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __restrict__ cent, int K,
+               const float* __restrict__ bias, uint32_t* __restrict__ part, float* __restrict__ dist,
+               uint8_t* __restrict__ valid, float* __restrict__ all_out) {
+  extern __shared__ float smem[];
+  constexpr int R = 8;
+  float* xs = smem;  // [R][d]
+  __shared__ float red_key[16][R];
+  __shared__ float red_val[16][R];
+  __shared__ uint32_t red_idx[16][R];
+  const int tid = threadIdx.x, hw = tid >> 4, l = tid & 15;
+  const uint64_t row0 = (uint64_t)blockIdx.x * R;
+  for (int idx = tid; idx < R * d; idx += 256) {
+    int r = idx / d, e = idx % d;
+    xs[idx] = (row0 + r < n) ? x[(row0 + r) * d + e] : 0.0f;
+  }
+  __syncthreads();
+  const int n16 = d & ~15;
+  float bkey = __int_as_float(0x7f800000), bval = __int_as_float(0x7f800000);
+  uint32_t bidx = 0xffffffffu;  // lane (l & 7) tracks row (l & 7)
+  const unsigned hmask = 0xffffu << (16 * ((tid >> 4) & 1));
+  for (int c = hw; c < K; c += 16) {
+    const float* cp = cent + (size_t)c * d;
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.0f;
+    for (int e = l; e < n16; e += 16) {
+      const float cv = cp[e];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = f_add(acc[r], term<METRIC>(xs[r * d + e], cv));
+    }
+    float mine = 0.0f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float s = 0.0f;  // sequential tail (l2.rs:69-79), every lane computes it redundantly
+      for (int e = n16; e < d; ++e) s = f_add(s, term<METRIC>(xs[r * d + e], cp[e]));
+      float t = 0.0f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        t = f_add(t, __shfl_sync(hmask, acc[r], q, 16));
+      const float v = finish<METRIC>(f_add(s, t));
+      if (WRITE_ALL) {
+        if (l == r && row0 + r < n) all_out[(row0 + r) * K + c] = v;
+      } else if ((l & 7) == r) {
+        mine = v;
+      }
+    }
+    if (!WRITE_ALL) {
+      const float key = bias ? f_add(mine, bias[c]) : mine;
+      if (key < bkey) { bkey = key; bval = mine; bidx = c; }
+    }
+  }
+  if (WRITE_ALL) return;
+  if (l < R) { red_key[hw][l] = bkey; red_val[hw][l] = bval; red_idx[hw][l] = bidx; }
+  __syncthreads();
+  if (tid < R) {
+    float k0 = red_key[0][tid], v0 = red_val[0][tid];
+    uint32_t i0 = red_idx[0][tid];
+    for (int h = 1; h < 16; ++h)
+      if (better(red_key[h][tid], red_idx[h][tid], k0, i0)) {
+        k0 = red_key[h][tid]; v0 = red_val[h][tid]; i0 = red_idx[h][tid];
+      }
+    const uint64_t r = row0 + tid;
+    if (r < n) {
+      const bool ok = i0 != 0xffffffffu;
+      part[r] = ok ? i0 : 0u;
+      if (dist) dist[r] = ok ? v0 : __int_as_float(0x7fc00000);
+      if (valid) valid[r] = ok ? 1 : 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host dispatch
+// ------------------------------------------------------------------------------------------------
+template <int METRIC>
+static void assign_dispatch(const float* x, uint64_t n, int d, const float* cent, int K,
+                            const float* bias, uint32_t* part, float* dist, uint8_t* valid,
+                            float* all_out) {
+  if (n == 0) return;
+  if (d % 16 == 0 && d <= 256) {
+    const int Kp = (K + 63) / 64 * 64;
+    DevBuf<float> cT((size_t)d * Kp);
+    LB2_LAUNCH("transpose_centroids", transpose_pad_kernel, cdiv((uint64_t)d * Kp, 256), 256, 0,
+               cent, K, d, Kp, cT.get());
+    DevBuf<float> biasp;
+    const float* bp = nullptr;
+    if (bias) {
+      biasp.alloc(Kp);
+      biasp.zero();
+      d2d(biasp.get(), bias, K);
+      bp = biasp.get();
+    }
+    const size_t smem = sizeof(float) * (64 * (d + 1) + (size_t)d * 64);
+    const unsigned grid = cdiv(n, 64);
+    if (all_out) {
+      set_smem(assign_tile_kernel<METRIC, true>, smem);
+      LB2_LAUNCH("assign_exact", (assign_tile_kernel<METRIC, true>), grid, 256, smem, x, n, d,
+                 cT.get(), K, Kp, bp, part, dist, valid, all_out);
+    } else {
+      set_smem(assign_tile_kernel<METRIC, false>, smem);
+      LB2_LAUNCH("assign_exact", (assign_tile_kernel<METRIC, false>), grid, 256, smem, x, n, d,
+                 cT.get(), K, Kp, bp, part, dist, valid, all_out);
+    }
+    return;
+  }
+  const size_t smem = sizeof(float) * 8 * (size_t)d;
+  if (smem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "dimension %d too large for the exact kernel", d);
+  const unsigned grid = cdiv(n, 8);
+  if (all_out) {
+    set_smem(generic_kernel<METRIC, true>, smem);
+    LB2_LAUNCH("assign_exact_generic", (generic_kernel<METRIC, true>), grid, 256, smem, x, n, d,
+               cent, K, bias, part, dist, valid, all_out);
+  } else {
+    set_smem(generic_kernel<METRIC, false>, smem);
+    LB2_LAUNCH("assign_exact_generic", (generic_kernel<METRIC, false>), grid, 256, smem, x, n, d,
+               cent, K, bias, part, dist, valid, all_out);
+  }
+}
+
+void assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, int metric,
+                const float* bias, uint32_t* part, float* dist, uint8_t* valid, float* all_out) {
+  if (metric == METRIC_DOT)
+    assign_dispatch<METRIC_DOT>(x, n, d, cent, K, bias, part, dist, valid, all_out);
+  else
+    assign_dispatch<METRIC_L2>(x, n, d, cent, K, bias, part, dist, valid, all_out);
+}
+
+template <int DS, int METRIC>
+static void small_d_launch(const float* x, uint64_t n, int ldx, int M, const float* codebook, int Kc,
+                           const float* ivf_centroids, const uint32_t* part_ids,
+                           const uint8_t* row_valid, uint8_t* codes, uint32_t* ids, float* dists,
+                           uint8_t* valid, const uint8_t* active) {
+  dim3 grid(cdiv(n, 64), M);
+  if (codes)
+    LB2_LAUNCH("pq_assign_exact", (small_d_kernel<DS, METRIC, true>), grid, 256, 0, x, n, ldx,
+               codebook, Kc, ivf_centroids, part_ids, row_valid, codes, M, ids, dists, valid, active);
+  else
+    LB2_LAUNCH("pq_assign_exact", (small_d_kernel<DS, METRIC, false>), grid, 256, 0, x, n, ldx,
+               codebook, Kc, ivf_centroids, part_ids, row_valid, codes, M, ids, dists, valid, active);
+}
+
+bool small_d_supported(int ds) { return ds == 1 || ds == 2 || ds == 4 || ds == 8 || ds == 12; }
+
+void small_d_assign_f32(const float* x, uint64_t n, int ldx, int M, int ds, const float* codebook,
+                        int Kc, int metric, const float* ivf_centroids, const uint32_t* part_ids,
+                        const uint8_t* row_valid, uint8_t* codes, uint32_t* ids, float* dists,
+                        uint8_t* valid, const uint8_t* active) {
+  if (n == 0) return;
+#define LB2_SD(DSV)                                                                              \
+  case DSV:                                                                                      \
+    if (metric == METRIC_DOT)                                                                    \
+      small_d_launch<DSV, METRIC_DOT>(x, n, ldx, M, codebook, Kc, ivf_centroids, part_ids,       \
+                                      row_valid, codes, ids, dists, valid, active);              \
+    else                                                                                         \
+      small_d_launch<DSV, METRIC_L2>(x, n, ldx, M, codebook, Kc, ivf_centroids, part_ids,        \
+                                     row_valid, codes, ids, dists, valid, active);               \
+    break;
+  switch (ds) {
+    LB2_SD(1) LB2_SD(2) LB2_SD(4) LB2_SD(8) LB2_SD(12)
+    default:
+      fail(LB2_UNSUPPORTED, "sub-vector width %d has no small-d kernel", ds);
+  }
+#undef LB2_SD
+}
+
+}  // namespace lb2

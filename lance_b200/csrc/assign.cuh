@@ -1,0 +1,16 @@
+// assign.cuh -- internal interface of the exact nearest-centroid kernels (assign.cu)
+#pragma once
+#include <stdint.h>
+namespace lb2 {
+// part/dist/valid are [n]; all_out (nullable) receives the full [n][K] distance matrix instead.
+// bias (nullable, [K]) is added for the comparison only (kernels.rs:92-111).
+void assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, int metric,
+                const float* bias, uint32_t* part, float* dist, uint8_t* valid, float* all_out);
+// d < 16 path, batched over M sub-spaces; x row stride ldx, sub-space m reads columns [m*ds,(m+1)*ds).
+// codes != NULL -> u8 [n][M] out (PQ encode), else ids/dists/valid [M][n] (PQ training).
+bool small_d_supported(int ds);
+void small_d_assign_f32(const float* x, uint64_t n, int ldx, int M, int ds, const float* codebook,
+                        int Kc, int metric, const float* ivf_centroids, const uint32_t* part_ids,
+                        const uint8_t* row_valid, uint8_t* codes, uint32_t* ids, float* dists,
+                        uint8_t* valid, const uint8_t* active);
+}  // namespace lb2

@@ -1,0 +1,373 @@
+// kmeans.cu -- Lloyd iterations on the device, batched over B independent problems
+// (B = 1 for the IVF coarse quantiser, B = M for the PQ sub-space codebooks).
+//
+// Replaces  KMeans::train_kmeans            lance-index/src/vector/kmeans.rs:610-719
+//           KMeansAlgoFloat::to_kmeans      kmeans.rs:371-446   (centroid update)
+//           compute_membership_and_loss     kmeans.rs:250-281   (radius / f64 loss per cluster)
+//           compute_cluster_sizes           kmeans.rs:210-232
+//           split_clusters                  kmeans.rs:174-207
+//
+// Design: the reference sums each cluster's rows SEQUENTIALLY IN ROW ORDER in f32 and its losses in
+// f64, so the result depends on the order.  Instead of atomics (fast but order-free) we build, per
+// iteration, a stable counting sort of the rows by cluster (member lists in ascending row order)
+// and let one thread per (cluster, dimension) add its members in that order.  Given the same
+// initial centroids the trained model is therefore BIT-IDENTICAL to the reference loop (checked
+// against the oracle), at the cost of a sort of n 4-byte keys per iteration.
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+#include "assign.cuh"
+#include "common.cuh"
+#include "exact.cuh"
+#include "kmeans.cuh"
+
+namespace lb2 {
+
+// ------------------------------------------------------------------------------------------------
+// stable counting sort of rows by cluster id
+// ------------------------------------------------------------------------------------------------
+__global__ void hist_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ valid,
+                            uint64_t n, int K, int chunk_rows, uint32_t* __restrict__ chunk_hist,
+                            const uint8_t* __restrict__ active) {
+  const int b = blockIdx.y;
+  if (active && !active[b]) return;
+  const uint64_t r0 = (uint64_t)blockIdx.x * chunk_rows;
+  const uint64_t r1 = min(n, r0 + (uint64_t)chunk_rows);
+  uint32_t* h = chunk_hist + ((size_t)b * gridDim.x + blockIdx.x) * K;
+  for (uint64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x)
+    if (!valid || valid[(size_t)b * n + r]) atomicAdd(&h[ids[(size_t)b * n + r]], 1u);
+}
+
+// per (b, k): exclusive scan over chunks (in place), total -> counts
+__global__ void scan_chunks_kernel(uint32_t* __restrict__ chunk_hist, int nchunks, int K, int B,
+                                   uint32_t* __restrict__ counts) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= B * K) return;
+  const int b = g / K, k = g % K;
+  uint32_t run = 0;
+  for (int c = 0; c < nchunks; ++c) {
+    uint32_t* p = chunk_hist + ((size_t)b * nchunks + c) * K + k;
+    const uint32_t t = *p;
+    *p = run;
+    run += t;
+  }
+  counts[g] = run;
+}
+
+// per b: offsets[b][0..K] = exclusive scan of counts[b][:]
+__global__ void offsets_kernel(const uint32_t* __restrict__ counts, int K,
+                               uint32_t* __restrict__ offsets) {
+  __shared__ uint32_t part[1024];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int seg = (K + 1023) / 1024;
+  const int s = t * seg, e = min(K, s + seg);
+  uint32_t sum = 0;
+  for (int k = s; k < e; ++k) sum += counts[(size_t)b * K + k];
+  part[t] = sum;
+  __syncthreads();
+  if (t == 0) {
+    uint32_t run = 0;
+    for (int i = 0; i < 1024; ++i) {
+      uint32_t v = part[i];
+      part[i] = run;
+      run += v;
+    }
+    offsets[(size_t)b * (K + 1) + K] = run;
+  }
+  __syncthreads();
+  uint32_t run = part[t];
+  for (int k = s; k < e; ++k) {
+    offsets[(size_t)b * (K + 1) + k] = run;
+    run += counts[(size_t)b * K + k];
+  }
+}
+
+// one warp per (chunk, b): rows in ascending order, rank inside a batch of 32 by match_any
+__global__ void scatter_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ valid,
+                               uint64_t n, int K, int chunk_rows, uint32_t* __restrict__ chunk_hist,
+                               const uint32_t* __restrict__ offsets, uint32_t* __restrict__ members,
+                               const uint8_t* __restrict__ active) {
+  const int b = blockIdx.y;
+  if (active && !active[b]) return;
+  const int lane = threadIdx.x;
+  const uint64_t r0 = (uint64_t)blockIdx.x * chunk_rows;
+  const uint64_t r1 = min(n, r0 + (uint64_t)chunk_rows);
+  uint32_t* h = chunk_hist + ((size_t)b * gridDim.x + blockIdx.x) * K;
+  const uint32_t* off = offsets + (size_t)b * (K + 1);
+  for (uint64_t base = r0; base < r1; base += 32) {
+    const uint64_t r = base + lane;
+    const bool ok = r < r1 && (!valid || valid[(size_t)b * n + r]);
+    const unsigned act = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const uint32_t key = ids[(size_t)b * n + r];
+      const unsigned grp = __match_any_sync(act, key);
+      const int rank = __popc(grp & ((1u << lane) - 1));
+      const uint32_t start = h[key];
+      members[(size_t)b * n + off[key] + start + rank] = (uint32_t)r;
+      __syncwarp(act);
+      if (rank == 0) h[key] = start + __popc(grp);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ordered centroid update (kmeans.rs:388-418): one thread per (b, cluster, t)
+// ------------------------------------------------------------------------------------------------
+__global__ void update_kernel(const float* __restrict__ x, int ldx, int ds, int K, int B, uint64_t n,
+                              const uint32_t* __restrict__ members,
+                              const uint32_t* __restrict__ offsets, float* __restrict__ centroids,
+                              const uint8_t* __restrict__ active, int scale) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (size_t)B * K * ds) return;
+  const int b = g / ((size_t)K * ds);
+  if (active && !active[b]) return;
+  const int k = (g / ds) % K, t = g % ds;
+  const uint32_t* off = offsets + (size_t)b * (K + 1);
+  const uint32_t s = off[k], e = off[k + 1];
+  const uint32_t* mem = members + (size_t)b * n;
+  const float* col = x + (size_t)b * ds + t;
+  float acc = 0.0f;
+  uint32_t j = s;
+  for (; j + 8 <= e; j += 8) {
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = col[(size_t)mem[j + q] * ldx];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc = f_add(acc, v[q]);
+  }
+  for (; j < e; ++j) acc = f_add(acc, col[(size_t)mem[j] * ldx]);
+  const uint32_t cnt = e - s;
+  if (scale && cnt > 0) acc = __fmul_rn(acc, __fdiv_rn(1.0f, (float)cnt));  // kmeans.rs:414-416
+  centroids[g] = acc;
+}
+
+// per (b, cluster): f64 loss in row order, radius (max), last member row (kmeans.rs:266-280)
+__global__ void stats_kernel(const float* __restrict__ dists, uint64_t n, int K, int B,
+                             const uint32_t* __restrict__ members,
+                             const uint32_t* __restrict__ offsets, double* __restrict__ losses,
+                             float* __restrict__ radius, uint32_t* __restrict__ last_row,
+                             const uint8_t* __restrict__ active) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= B * K) return;
+  const int b = w / K, k = w % K;
+  if (active && !active[b]) return;
+  const uint32_t* off = offsets + (size_t)b * (K + 1);
+  const uint32_t s = off[k], e = off[k + 1];
+  const uint32_t* mem = members + (size_t)b * n;
+  const float* dv = dists + (size_t)b * n;
+  double loss = 0.0;
+  float rad = 0.0f;
+  for (uint32_t base = s; base < e; base += 32) {
+    const uint32_t j = base + lane;
+    const float v = j < e ? dv[mem[j]] : 0.0f;
+    const int cnt = min(32u, e - base);
+    for (int q = 0; q < cnt; ++q) {
+      const float u = __shfl_sync(0xffffffffu, v, q);
+      loss += (double)u;
+      rad = fmaxf(rad, u);  // f32::max ignores NaN like fmaxf; dists of members are never NaN
+    }
+  }
+  if (lane == 0) {
+    losses[w] = loss;
+    radius[w] = rad;
+    last_row[w] = e > s ? mem[e - 1] : 0xffffffffu;
+  }
+}
+
+__global__ void split_kernel(float* __restrict__ c, int i, int j, int ds) {
+  const float eps = 1.0f / 1024.0f;
+  for (int t = threadIdx.x; t < ds; t += blockDim.x) {
+    const float cj = c[(size_t)j * ds + t];
+    if ((t & 1) == 0) {
+      c[(size_t)i * ds + t] = __fmul_rn(cj, 1.0f + eps);
+      c[(size_t)j * ds + t] = __fmul_rn(cj, 1.0f - eps);
+    } else {
+      c[(size_t)i * ds + t] = __fmul_rn(cj, 1.0f - eps);
+      c[(size_t)j * ds + t] = __fmul_rn(cj, 1.0f + eps);
+    }
+  }
+}
+
+__global__ void gather_init_kernel(const float* __restrict__ x, int ldx, int ds, int K, int B,
+                                   const uint32_t* __restrict__ rows, float* __restrict__ out) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (size_t)B * K * ds) return;
+  const int b = g / ((size_t)K * ds), k = (g / ds) % K, t = g % ds;
+  out[g] = x[(size_t)rows[(size_t)b * K + k] * ldx + (size_t)b * ds + t];
+}
+
+// ------------------------------------------------------------------------------------------------
+// member lists (also used to group rows by partition when an index is loaded)
+// ------------------------------------------------------------------------------------------------
+void MemberSort::run(const uint32_t* ids, const uint8_t* valid, uint64_t n, int K, int B,
+                     const uint8_t* active) {
+  // chunk size: keep the per-chunk histogram table below ~256 MB
+  int chunk_rows = 2048;
+  while ((double)B * (double)cdiv(n, chunk_rows) * K * 4.0 > 256e6) chunk_rows *= 2;
+  const int nchunks = std::max(1u, cdiv(n, chunk_rows));
+  if (chunk_hist.n < (size_t)B * nchunks * K) chunk_hist.alloc((size_t)B * nchunks * K);
+  if (counts.n < (size_t)B * K) counts.alloc((size_t)B * K);
+  if (offsets.n < (size_t)B * (K + 1)) offsets.alloc((size_t)B * (K + 1));
+  if (members.n < (size_t)B * n) members.alloc((size_t)B * std::max<uint64_t>(n, 1));
+  LB2_CUDA(cudaMemsetAsync(chunk_hist.p, 0, sizeof(uint32_t) * (size_t)B * nchunks * K, ctx().stream));
+  dim3 grid(nchunks, B);
+  LB2_LAUNCH("member_sort", hist_kernel, grid, 256, 0, ids, valid, n, K, chunk_rows, chunk_hist.p, active);
+  LB2_LAUNCH("member_sort", scan_chunks_kernel, cdiv((uint64_t)B * K, 128), 128, 0, chunk_hist.p,
+             nchunks, K, B, counts.p);
+  LB2_LAUNCH("member_sort", offsets_kernel, B, 1024, 0, counts.p, K, offsets.p);
+  LB2_LAUNCH("member_sort", scatter_kernel, grid, 32, 0, ids, valid, n, K, chunk_rows, chunk_hist.p,
+             offsets.p, members.p, active);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the Lloyd loop
+// ------------------------------------------------------------------------------------------------
+void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, int metric,
+                 float balance_factor_param, int max_iters, double tolerance, uint64_t seed,
+                 const float* init_dev, float* centroids, std::vector<double>* loss_out,
+                 std::vector<uint32_t>* iters_out) {
+  LB2_REQUIRE(n_in >= (uint64_t)K, "KMeans: can not train %d centroids with %llu vectors", K,
+              (unsigned long long)n_in);
+  // kmeans.rs:623-627: only the first 512*k rows are used
+  const uint64_t n = n_in >= (uint64_t)K * 512 ? (uint64_t)K * 512 : n_in;
+  LB2_REQUIRE(n < 0xffffffffull, "training sample too large");
+  const size_t BK = (size_t)B * K;
+
+  // ---- init (kmeans.rs:149-170; our rng): k distinct rows by a partial Fisher-Yates ------------
+  if (init_dev) {
+    if (init_dev != centroids) d2d(centroids, init_dev, BK * ds);
+  } else {
+    std::vector<uint32_t> rows(BK), idx(n);
+    for (int b = 0; b < B; ++b) {
+      SplitMix64 rng(seed + b);
+      for (uint64_t i = 0; i < n; ++i) idx[i] = (uint32_t)i;
+      for (int i = 0; i < K; ++i) {
+        uint64_t j = i + rng.next() % (n - i);
+        std::swap(idx[i], idx[j]);
+        rows[(size_t)b * K + i] = idx[i];
+      }
+    }
+    DevBuf<uint32_t> rows_d(BK);
+    h2d(rows_d.p, rows.data(), BK);
+    LB2_LAUNCH("kmeans_init", gather_init_kernel, cdiv(BK * ds, 256), 256, 0, x, ldx, ds, K, B,
+               rows_d.p, centroids);
+    sync_stream();  // rows (host vector) must outlive the copy
+  }
+  // split_clusters continues the stream that chose the init rows in the single-problem oracle:
+  // oracle: one SplitMix64(seed) for init AND splits.  Mirror that per problem.
+  std::vector<SplitMix64> rngs;
+  for (int b = 0; b < B; ++b) {
+    SplitMix64 r(seed + b);
+    if (!init_dev)
+      for (int i = 0; i < K; ++i) r.next();
+    rngs.push_back(r);
+  }
+
+  DevBuf<uint32_t> ids((size_t)B * n), last_row(BK);
+  DevBuf<float> dists((size_t)B * n), radius(BK), bias;
+  DevBuf<uint8_t> valid((size_t)B * n), active_d(B);
+  DevBuf<double> losses(BK);
+  MemberSort ms;
+  std::vector<uint8_t> active(B, 1);
+  std::vector<uint64_t> cluster_sizes(BK, 0);
+  std::vector<float> adjusted(B, std::numeric_limits<float>::max());
+  std::vector<double> loss(B, std::numeric_limits<double>::max()), last_loss(B, 0.0);
+  std::vector<uint32_t> iters(B, 0);
+  std::vector<uint32_t> h_counts(BK), h_last(BK);
+  std::vector<float> h_radius(BK), h_bias(K);
+  std::vector<double> h_losses(BK);
+  if (B == 1) bias.alloc(K);
+  const bool small = B > 1;
+  if (small && !small_d_supported(ds))
+    fail(LB2_UNSUPPORTED, "PQ sub-vector width %d is not supported by the device trainer yet", ds);
+
+  for (int it = 1; it <= max_iters; ++it) {
+    bool any = false;
+    for (int b = 0; b < B; ++b) any = any || active[b];
+    if (!any) break;
+    h2d(active_d.p, active.data(), B);
+    std::vector<float> bf(B);
+    for (int b = 0; b < B; ++b) bf[b] = std::fmin(adjusted[b], balance_factor_param);
+    // ---- membership (kmeans.rs:317-369) --------------------------------------------------------
+    if (!small) {
+      for (int k = 0; k < K; ++k) h_bias[k] = bf[0] * (float)cluster_sizes[k];
+      h2d(bias.p, h_bias.data(), K);
+      assign_f32(x, n, ds, centroids, K, metric, bias.p, ids.p, dists.p, valid.p, nullptr);
+    } else {
+      small_d_assign_f32(x, n, ldx, B, ds, centroids, K, metric, nullptr, nullptr, nullptr, nullptr,
+                         ids.p, dists.p, valid.p, active_d.p);
+    }
+    // ---- member lists, stats, update -----------------------------------------------------------
+    ms.run(ids.p, valid.p, n, K, B, active_d.p);
+    LB2_LAUNCH("kmeans_stats", stats_kernel, cdiv((uint64_t)BK * 32, 256), 256, 0, dists.p, n, K, B,
+               ms.members.p, ms.offsets.p, losses.p, radius.p, last_row.p, active_d.p);
+    LB2_LAUNCH("kmeans_update", update_kernel, cdiv(BK * ds, 128), 128, 0, x, ldx, ds, K, B, n,
+               ms.members.p, ms.offsets.p, centroids, active_d.p, 1);
+    d2h(h_counts.data(), ms.counts.p, BK);
+    d2h(h_losses.data(), losses.p, BK);
+    d2h(h_radius.data(), radius.p, BK);
+    d2h(h_last.data(), last_row.p, BK);
+    sync_stream();
+    // ---- host epilogue: exactly the reference's scalar bookkeeping ------------------------------
+    for (int b = 0; b < B; ++b) {
+      if (!active[b]) continue;
+      iters[b] = it;
+      uint64_t* cs = &cluster_sizes[(size_t)b * K];
+      const uint32_t* cnt = &h_counts[(size_t)b * K];
+      // compute_cluster_sizes (kmeans.rs:210-232): the cluster that FIRST reaches the final
+      // maximum size = among the largest clusters the one whose last member comes first.
+      uint64_t max_size = 0;
+      int max_id = 0;
+      uint32_t best_last = 0xffffffffu;
+      for (int k = 0; k < K; ++k) {
+        cs[k] = cnt[k];
+        if (cnt[k] > max_size || (cnt[k] == max_size && cnt[k] > 0 && h_last[(size_t)b * K + k] < best_last)) {
+          max_size = cnt[k];
+          max_id = k;
+          best_last = h_last[(size_t)b * K + k];
+        }
+      }
+      const double* ls = &h_losses[(size_t)b * K];
+      adjusted[b] = (h_radius[(size_t)b * K + max_id] - (float)ls[max_id] / (float)cs[max_id]) / (float)n;
+      uint64_t size_sq = 0;
+      for (int k = 0; k < K; ++k) size_sq += cs[k] * cs[k];
+      const float balance_loss = bf[b] * ((float)size_sq - (float)(n * n) / (float)K);  // :234-237
+      double sum_losses = 0.0;
+      for (int k = 0; k < K; ++k) sum_losses += ls[k];
+      last_loss[b] = sum_losses + (double)balance_loss;
+      // split_clusters (kmeans.rs:174-207)
+      float* cb = centroids + (size_t)b * K * ds;
+      for (int i = 0; i < K; ++i) {
+        if (cs[i] != 0) continue;
+        uint64_t j = 0;
+        for (uint64_t tries = 0;; ++tries) {
+          const float p = ((float)cs[j] - 1.0f) / (float)(n - K);
+          if (rngs[b].next_f32() < p) break;
+          j = (j + 1) % K;
+          if (tries >= 64ull * K) {
+            j = 0;
+            for (int c = 1; c < K; ++c)
+              if (cs[c] > cs[j]) j = c;
+            break;
+          }
+        }
+        cs[i] = cs[j] / 2;
+        cs[j] -= cs[i];
+        LB2_LAUNCH("kmeans_split", split_kernel, 1, 128, 0, cb, i, (int)j, ds);
+      }
+      if (std::fabs(loss[b] - last_loss[b]) < tolerance * last_loss[b]) {  // kmeans.rs:704
+        active[b] = 0;
+        continue;
+      }
+      loss[b] = last_loss[b];
+    }
+  }
+  sync_stream();
+  if (loss_out) *loss_out = last_loss;
+  if (iters_out) *iters_out = iters;
+}
+
+}  // namespace lb2

@@ -1,0 +1,414 @@
+// search.cu -- query-time kernels.
+//
+// Replaces  kmeans_find_partitions               lance-index/src/vector/kmeans.rs:1134-1158
+//           IVFIndex::preprocess_query           rust/lance/src/index/vector/ivf/v2.rs:316-332
+//           build_distance_table_l2/_dot         lance-index/src/vector/pq/distance.rs:24-92
+//           compute_pq_distance (+ Dot fix-up)   pq/distance.rs:109-144, pq/storage.rs:921-962
+//           FlatIndex::search heap top-k         lance-index/src/vector/flat/index.rs:82-177
+//           SortExec(_distance,_rowid).fetch(k)  rust/lance/src/dataset/scanner.rs:3450-3466
+//
+// One CTA per (query, probed partition): the residual query and its M x 256 f32 lookup table are
+// built in shared memory (never written to HBM), the partition's codes are streamed once with
+// 128-bit loads, each row's distance is the reference's m-ascending f32 sum (bit-exact), and a
+// per-thread sorted list + block argmin rounds produce the k smallest (distance, position) pairs.
+#include "assign.cuh"
+#include "common.cuh"
+#include "exact.cuh"
+#include "search.cuh"
+
+namespace lb2 {
+
+// ------------------------------------------------------------------------------------------------
+// block-level helpers
+// ------------------------------------------------------------------------------------------------
+struct KeyIdx {
+  int32_t key;   // total-order key of the distance
+  uint32_t idx;  // tie-breaker (position / id)
+};
+__device__ __forceinline__ bool ki_less(int32_t k1, uint64_t i1, int32_t k2, uint64_t i2) {
+  return k1 < k2 || (k1 == k2 && i1 < i2);
+}
+
+// argmin over (key, tie) proposed by every thread of a 256/128-thread block; returns the winning
+// thread id (all threads get it).  Threads with nothing to propose pass has=false.
+template <int NT>
+__device__ inline int block_argmin(bool has, int32_t key, uint64_t tie, int32_t* s_key,
+                                   uint64_t* s_tie, int* s_tid) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int who = has ? tid : -1;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const int32_t ok = __shfl_xor_sync(0xffffffffu, key, off);
+    const uint64_t ot = __shfl_xor_sync(0xffffffffu, tie, off);
+    const int ow = __shfl_xor_sync(0xffffffffu, who, off);
+    if (ow >= 0 && (who < 0 || ki_less(ok, ot, key, tie))) {
+      key = ok; tie = ot; who = ow;
+    }
+  }
+  if (lane == 0) { s_key[warp] = key; s_tie[warp] = tie; s_tid[warp] = who; }
+  __syncthreads();
+  if (tid == 0) {
+    int bw = s_tid[0];
+    int32_t bk = s_key[0];
+    uint64_t bt = s_tie[0];
+    for (int w = 1; w < NT / 32; ++w)
+      if (s_tid[w] >= 0 && (bw < 0 || ki_less(s_key[w], s_tie[w], bk, bt))) {
+        bw = s_tid[w]; bk = s_key[w]; bt = s_tie[w];
+      }
+    s_tid[NT / 32] = bw;
+  }
+  __syncthreads();
+  const int winner = s_tid[NT / 32];
+  __syncthreads();
+  return winner;
+}
+
+// per-thread sorted (ascending) list of the k best (distance, position) seen by this thread
+template <int KMAX>
+struct ThreadTopK {
+  float d[KMAX];
+  uint32_t j[KMAX];
+  int cnt = 0;
+  __device__ __forceinline__ void push(float dist, uint32_t pos, int k) {
+    const int32_t key = total_order_key(dist);
+    if (cnt == k && !(key < total_order_key(d[cnt - 1]))) return;  // ties keep earlier rows
+    int p = cnt < k ? cnt : k - 1;
+    while (p > 0 && total_order_key(d[p - 1]) > key) {
+      d[p] = d[p - 1];
+      j[p] = j[p - 1];
+      --p;
+    }
+    d[p] = dist;
+    j[p] = pos;
+    if (cnt < k) ++cnt;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// coarse probe selection: nprobes smallest (distance, id), ascending (kmeans.rs:1152-1157)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+select_probes_kernel(const float* __restrict__ all_dists, int K, int nprobes,
+                     uint32_t* __restrict__ ids, float* __restrict__ dists) {
+  __shared__ int32_t s_key[4];
+  __shared__ uint64_t s_tie[4];
+  __shared__ int s_tid[5];
+  __shared__ int32_t prev_key;
+  __shared__ uint32_t prev_id;
+  const float* row = all_dists + (size_t)blockIdx.x * K;
+  const int tid = threadIdx.x;
+  bool first = true;
+  for (int r = 0; r < nprobes; ++r) {
+    int32_t bk = 0;
+    uint32_t bi = 0;
+    bool has = false;
+    const int32_t pk = first ? 0 : prev_key;
+    const uint32_t pi = first ? 0 : prev_id;
+    for (int c = tid; c < K; c += 128) {
+      const int32_t key = total_order_key(row[c]);
+      if (!first && !ki_less(pk, pi, key, c)) continue;  // already emitted
+      if (!has || ki_less(key, c, bk, bi)) { bk = key; bi = c; has = true; }
+    }
+    const int w = block_argmin<128>(has, bk, bi, s_key, s_tie, s_tid);
+    if (w < 0) break;
+    if (tid == w) {
+      prev_key = bk;
+      prev_id = bi;
+      ids[(size_t)blockIdx.x * nprobes + r] = bi;
+      dists[(size_t)blockIdx.x * nprobes + r] = row[bi];
+    }
+    __syncthreads();
+    first = false;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused (residual query -> LUT -> code scan -> top-k) kernel
+// ------------------------------------------------------------------------------------------------
+template <int METRIC, int KMAX>
+__global__ void __launch_bounds__(256)
+ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restrict__ centroids,
+                  const float* __restrict__ codebook, int M, int ds,
+                  const uint32_t* __restrict__ probe_ids, int np,
+                  const uint64_t* __restrict__ part_offsets, const uint8_t* __restrict__ codes,
+                  const uint64_t* __restrict__ row_ids, int k, float* __restrict__ cand_d,
+                  uint64_t* __restrict__ cand_id, uint32_t* __restrict__ cand_cnt) {
+  extern __shared__ float smem[];
+  float* lut = smem;           // [M*256]
+  float* qr = smem + M * 256;  // [d]
+  __shared__ int32_t s_key[8];
+  __shared__ uint64_t s_tie[8];
+  __shared__ int s_tid[9];
+  const int tid = threadIdx.x;
+  const int pi = blockIdx.x;
+  const size_t qi = blockIdx.y;
+  const uint32_t p = probe_ids[qi * np + pi];
+  const uint64_t off = part_offsets[p];
+  const uint32_t n_p = (uint32_t)(part_offsets[p + 1] - off);
+  const size_t slot = qi * np + pi;
+  if (n_p == 0) {
+    if (tid == 0) cand_cnt[slot] = 0;
+    return;
+  }
+  const float* q = queries + qi * d;
+  for (int t = tid; t < d; t += 256)
+    qr[t] = METRIC == METRIC_DOT ? q[t] : __fsub_rn(q[t], centroids[(size_t)p * d + t]);  // v2.rs:316-332
+  __syncthreads();
+  for (int idx = tid; idx < M * 256; idx += 256) {  // pq/distance.rs:38-56
+    const int m = idx >> 8;
+    lut[idx] = dist_exact_thread<METRIC>(qr + m * ds, codebook + (size_t)idx * ds, ds);
+  }
+  __syncthreads();
+
+  ThreadTopK<KMAX> top;
+  const uint8_t* pc = codes + off * M;
+  const float dot_fix = (float)M - 1.0f;
+  if ((M & 15) == 0) {
+    for (uint32_t j = tid; j < n_p; j += 256) {
+      const uint4* rp = reinterpret_cast<const uint4*>(pc + (size_t)j * M);
+      float dist = 0.0f;
+      for (int c16 = 0; c16 < M / 16; ++c16) {
+        const uint4 v = __ldg(rp + c16);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const float* l0 = lut + c16 * 16 * 256;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            dist = f_add(dist, l0[(a * 4 + b) * 256 + ((w[a] >> (8 * b)) & 0xff)]);
+      }
+      if (METRIC == METRIC_DOT) dist = __fsub_rn(dist, dot_fix);  // pq/storage.rs:957-958
+      top.push(dist, j, k);
+    }
+  } else {
+    for (uint32_t j = tid; j < n_p; j += 256) {
+      const uint8_t* rp = pc + (size_t)j * M;
+      float dist = 0.0f;
+      for (int m = 0; m < M; ++m) dist = f_add(dist, lut[m * 256 + rp[m]]);
+      if (METRIC == METRIC_DOT) dist = __fsub_rn(dist, dot_fix);
+      top.push(dist, j, k);
+    }
+  }
+  // block merge: k rounds of argmin over the threads' list heads
+  int head = 0;
+  const uint32_t rounds = n_p < (uint32_t)k ? n_p : (uint32_t)k;
+  for (uint32_t r = 0; r < rounds; ++r) {
+    const bool has = head < top.cnt;
+    const int32_t key = has ? total_order_key(top.d[head]) : 0;
+    const uint64_t tie = has ? top.j[head] : 0;
+    const int w = block_argmin<256>(has, key, tie, s_key, s_tie, s_tid);
+    if (tid == w) {
+      cand_d[slot * k + r] = top.d[head];
+      cand_id[slot * k + r] = row_ids[off + top.j[head]];
+      ++head;
+    }
+  }
+  if (tid == 0) cand_cnt[slot] = rounds;
+}
+
+// global merge per query: ascending (distance, row id), first k
+__global__ void __launch_bounds__(128)
+merge_kernel(const float* __restrict__ cand_d, const uint64_t* __restrict__ cand_id,
+             const uint32_t* __restrict__ cand_cnt, int np, int k, uint64_t* __restrict__ out_id,
+             float* __restrict__ out_d, uint32_t* __restrict__ out_cnt) {
+  __shared__ int32_t s_key[4];
+  __shared__ uint64_t s_tie[4];
+  __shared__ int s_tid[5];
+  __shared__ int32_t prev_key;
+  __shared__ uint64_t prev_id;
+  const size_t qi = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int total = np * k;
+  bool first = true;
+  int r = 0;
+  for (; r < k; ++r) {
+    int32_t bk = 0;
+    uint64_t bi = 0;
+    int bslot = -1;
+    const int32_t pk = first ? 0 : prev_key;
+    const uint64_t pid = first ? 0 : prev_id;
+    for (int c = tid; c < total; c += 128) {
+      const int pi = c / k, e = c % k;
+      if ((uint32_t)e >= cand_cnt[qi * np + pi]) continue;
+      const size_t g = (qi * np + pi) * k + e;
+      const int32_t key = total_order_key(cand_d[g]);
+      const uint64_t id = cand_id[g];
+      if (!first && !ki_less(pk, pid, key, id)) continue;
+      if (bslot < 0 || ki_less(key, id, bk, bi)) { bk = key; bi = id; bslot = (int)(g - qi * np * k); }
+    }
+    const int w = block_argmin<128>(bslot >= 0, bk, bi, s_key, s_tie, s_tid);
+    if (w < 0) break;
+    if (tid == w) {
+      prev_key = bk;
+      prev_id = bi;
+      out_id[qi * k + r] = bi;
+      out_d[qi * k + r] = cand_d[qi * np * k + bslot];
+    }
+    __syncthreads();
+    first = false;
+  }
+  for (int e = r + tid; e < k; e += 128) {
+    out_id[qi * k + e] = ~0ull;
+    out_d[qi * k + e] = __int_as_float(0x7f800000);
+  }
+  if (tid == 0 && out_cnt) out_cnt[qi] = r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// primitives exported one-to-one (used by the trait-level shim and by the parity tests)
+// ------------------------------------------------------------------------------------------------
+template <int METRIC>
+__global__ void build_lut_kernel(const float* __restrict__ codebook, int M, int ncode, int ds,
+                                 const float* __restrict__ query, float* __restrict__ lut) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * ncode) return;
+  const int m = idx / ncode;
+  lut[idx] = dist_exact_thread<METRIC>(query + m * ds, codebook + (size_t)idx * ds, ds);
+}
+
+__global__ void pq_scan_transposed_kernel(const float* __restrict__ lut, int M,
+                                          const uint8_t* __restrict__ codes_t, uint64_t n,
+                                          int is_dot, float* __restrict__ out) {
+  extern __shared__ float s_lut[];
+  for (int i = threadIdx.x; i < M * 256; i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float dist = 0.0f;
+  for (int m = 0; m < M; ++m) dist = f_add(dist, s_lut[m * 256 + codes_t[(size_t)m * n + j]]);
+  if (is_dot) dist = __fsub_rn(dist, (float)M - 1.0f);
+  out[j] = dist;
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(256)
+flat_topk_kernel(const float* __restrict__ dists, const uint64_t* __restrict__ row_ids, uint64_t n,
+                 int k, uint64_t* __restrict__ out_id, float* __restrict__ out_d,
+                 uint32_t* __restrict__ out_cnt) {
+  __shared__ int32_t s_key[8];
+  __shared__ uint64_t s_tie[8];
+  __shared__ int s_tid[9];
+  const int tid = threadIdx.x;
+  ThreadTopK<KMAX> top;
+  for (uint64_t j = tid; j < n; j += 256) top.push(dists[j], (uint32_t)j, k);
+  int head = 0;
+  const uint32_t rounds = n < (uint64_t)k ? (uint32_t)n : (uint32_t)k;
+  for (uint32_t r = 0; r < rounds; ++r) {
+    const bool has = head < top.cnt;
+    const int32_t key = has ? total_order_key(top.d[head]) : 0;
+    const uint64_t tie = has ? top.j[head] : 0;
+    const int w = block_argmin<256>(has, key, tie, s_key, s_tie, s_tid);
+    if (tid == w) {
+      out_d[r] = top.d[head];
+      out_id[r] = row_ids ? row_ids[top.j[head]] : (uint64_t)top.j[head];
+      ++head;
+    }
+  }
+  if (tid == 0) *out_cnt = rounds;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+void find_partitions_f32(const float* centroids, int K, int d, int metric, const float* queries,
+                         uint64_t nq, int nprobes, uint32_t* ids, float* dists) {
+  if (nq == 0) return;
+  DevBuf<float> all((size_t)nq * K);
+  assign_f32(queries, nq, d, centroids, K, metric, nullptr, nullptr, nullptr, nullptr, all.p);
+  LB2_LAUNCH("select_probes", select_probes_kernel, (unsigned)nq, 128, 0, all.p, K, nprobes, ids, dists);
+}
+
+template <int METRIC>
+static void scan_launch(int kmax, dim3 grid, size_t smem, const float* queries, int d,
+                        const float* centroids, const float* codebook, int M, int ds,
+                        const uint32_t* probe_ids, int np, const uint64_t* part_offsets,
+                        const uint8_t* codes, const uint64_t* row_ids, int k, float* cand_d,
+                        uint64_t* cand_id, uint32_t* cand_cnt) {
+#define LB2_SCAN(KM)                                                                              \
+  {                                                                                               \
+    set_smem(ivfpq_scan_kernel<METRIC, KM>, smem);                                                \
+    LB2_LAUNCH("pq_scan", (ivfpq_scan_kernel<METRIC, KM>), grid, 256, smem, queries, d, centroids, \
+               codebook, M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id,  \
+               cand_cnt);                                                                         \
+  }
+  if (kmax <= 16) LB2_SCAN(16)
+  else if (kmax <= 128) LB2_SCAN(128)
+  else LB2_SCAN(1024)
+#undef LB2_SCAN
+}
+
+void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const float* codebook, int M,
+                      int nbits, const uint64_t* part_offsets, const uint8_t* codes,
+                      const uint64_t* row_ids, const float* queries, uint64_t nq, int k, int nprobes,
+                      uint64_t* out_ids, float* out_dists, uint32_t* out_counts) {
+  if (nq == 0 || k == 0) return;
+  if (nbits != 8) fail(LB2_UNSUPPORTED, "only 8-bit PQ is implemented on the device");
+  if (k > 1024) fail(LB2_UNSUPPORTED, "k (incl. refine factor) > 1024 is not implemented");
+  const int np = nprobes < K ? nprobes : K;
+  const int ds = d / M;
+  const int cmetric = metric == METRIC_DOT ? METRIC_DOT : METRIC_L2;
+  DevBuf<uint32_t> pids((size_t)nq * np), cand_cnt((size_t)nq * np);
+  DevBuf<float> pd((size_t)nq * np), cand_d((size_t)nq * np * k);
+  DevBuf<uint64_t> cand_id((size_t)nq * np * k);
+  find_partitions_f32(centroids, K, d, cmetric, queries, nq, np, pids.p, pd.p);
+  const size_t smem = sizeof(float) * ((size_t)M * 256 + d);
+  if (smem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "LUT of %zu bytes exceeds shared memory", smem);
+  dim3 grid(np, (unsigned)nq);
+  if (nq > 65535) {
+    // grid.y limit: process in slabs
+    for (uint64_t q0 = 0; q0 < nq; q0 += 32768) {
+      const uint64_t qn = std::min<uint64_t>(32768, nq - q0);
+      dim3 g(np, (unsigned)qn);
+      if (cmetric == METRIC_DOT)
+        scan_launch<METRIC_DOT>(k, g, smem, queries + q0 * d, d, centroids, codebook, M, ds,
+                                pids.p + q0 * np, np, part_offsets, codes, row_ids, k,
+                                cand_d.p + q0 * np * k, cand_id.p + q0 * np * k, cand_cnt.p + q0 * np);
+      else
+        scan_launch<METRIC_L2>(k, g, smem, queries + q0 * d, d, centroids, codebook, M, ds,
+                               pids.p + q0 * np, np, part_offsets, codes, row_ids, k,
+                               cand_d.p + q0 * np * k, cand_id.p + q0 * np * k, cand_cnt.p + q0 * np);
+    }
+  } else if (cmetric == METRIC_DOT) {
+    scan_launch<METRIC_DOT>(k, grid, smem, queries, d, centroids, codebook, M, ds, pids.p, np,
+                            part_offsets, codes, row_ids, k, cand_d.p, cand_id.p, cand_cnt.p);
+  } else {
+    scan_launch<METRIC_L2>(k, grid, smem, queries, d, centroids, codebook, M, ds, pids.p, np,
+                           part_offsets, codes, row_ids, k, cand_d.p, cand_id.p, cand_cnt.p);
+  }
+  LB2_LAUNCH("merge_topk", merge_kernel, (unsigned)nq, 128, 0, cand_d.p, cand_id.p, cand_cnt.p, np,
+             k, out_ids, out_dists, out_counts);
+}
+
+void build_lut_f32(const float* codebook, int M, int nbits, int d, int metric, const float* query,
+                   float* lut) {
+  const int ncode = 1 << nbits, ds = d / M;
+  if (metric == METRIC_DOT)
+    LB2_LAUNCH("build_lut", build_lut_kernel<METRIC_DOT>, cdiv((uint64_t)M * ncode, 128), 128, 0,
+               codebook, M, ncode, ds, query, lut);
+  else
+    LB2_LAUNCH("build_lut", build_lut_kernel<METRIC_L2>, cdiv((uint64_t)M * ncode, 128), 128, 0,
+               codebook, M, ncode, ds, query, lut);
+}
+
+void pq_scan_transposed_f32(const float* lut, int M, int metric, const uint8_t* codes_t, uint64_t n,
+                            float* out) {
+  if (n == 0) return;
+  const size_t smem = sizeof(float) * (size_t)M * 256;
+  if (smem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "LUT of %zu bytes exceeds shared memory", smem);
+  set_smem(pq_scan_transposed_kernel, smem);
+  LB2_LAUNCH("pq_scan_transposed", pq_scan_transposed_kernel, cdiv(n, 256), 256, smem, lut, M,
+             codes_t, n, metric == METRIC_DOT ? 1 : 0, out);
+}
+
+void flat_topk_f32(const float* dists, const uint64_t* row_ids, uint64_t n, int k, uint64_t* out_id,
+                   float* out_d, uint32_t* out_cnt) {
+  if (k > 1024) fail(LB2_UNSUPPORTED, "k > 1024 is not implemented");
+  if (k <= 16)
+    LB2_LAUNCH("flat_topk", flat_topk_kernel<16>, 1, 256, 0, dists, row_ids, n, k, out_id, out_d, out_cnt);
+  else if (k <= 128)
+    LB2_LAUNCH("flat_topk", flat_topk_kernel<128>, 1, 256, 0, dists, row_ids, n, k, out_id, out_d, out_cnt);
+  else
+    LB2_LAUNCH("flat_topk", flat_topk_kernel<1024>, 1, 256, 0, dists, row_ids, n, k, out_id, out_d, out_cnt);
+}
+
+}  // namespace lb2

@@ -1,0 +1,17 @@
+// search.cuh -- internal interface of search.cu
+#pragma once
+#include <stdint.h>
+namespace lb2 {
+void find_partitions_f32(const float* centroids, int K, int d, int metric, const float* queries,
+                         uint64_t nq, int nprobes, uint32_t* ids, float* dists);
+void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const float* codebook, int M,
+                      int nbits, const uint64_t* part_offsets, const uint8_t* codes,
+                      const uint64_t* row_ids, const float* queries, uint64_t nq, int k, int nprobes,
+                      uint64_t* out_ids, float* out_dists, uint32_t* out_counts);
+void build_lut_f32(const float* codebook, int M, int nbits, int d, int metric, const float* query,
+                   float* lut);
+void pq_scan_transposed_f32(const float* lut, int M, int metric, const uint8_t* codes_t, uint64_t n,
+                            float* out);
+void flat_topk_f32(const float* dists, const uint64_t* row_ids, uint64_t n, int k, uint64_t* out_id,
+                   float* out_d, uint32_t* out_cnt);
+}  // namespace lb2

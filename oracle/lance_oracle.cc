@@ -364,7 +364,8 @@ int lo_kmeans_train(const float* data_in, uint64_t n_in, uint64_t d, uint64_t k,
   double last_loss = loss;
   int it = 0;
   for (it = 1; it <= max_iters; ++it) {
-    float balance_factor = std::min(adjusted_balance_factor, balance_factor_param);
+    // f32::min returns the non-NaN operand (kmeans.rs:679)
+    float balance_factor = std::fmin(adjusted_balance_factor, balance_factor_param);
     lo_compute_membership(cent.data(), k, d, data, n, metric, balance_factor, cluster_sizes.data(),
                           ids.data(), dists.data(), valid.data(), nthreads);
     // compute_membership_and_loss (kmeans.rs:266-280): radius = max, loss = f64 sum in row order
@@ -415,10 +416,16 @@ int lo_kmeans_train(const float* data_in, uint64_t n_in, uint64_t d, uint64_t k,
       for (uint64_t i = 0; i < k; ++i)
         if (cluster_sizes[i] == 0) {
           uint64_t j = 0;
-          for (;;) {
+          for (uint64_t tries = 0;; ++tries) {
             float p = (float(cluster_sizes[j]) - 1.0f) / float(n - k);
             if (rng.next_f32() < p) break;
             j = (j + 1) % k;
+            if (tries >= 64 * k) {  // guard (ours): the reference would spin forever when no
+              j = 0;                // cluster has more than one row; take the largest instead
+              for (uint64_t c = 1; c < k; ++c)
+                if (cluster_sizes[c] > cluster_sizes[j]) j = c;
+              break;
+            }
           }
           cluster_sizes[i] = cluster_sizes[j] / 2;
           cluster_sizes[j] -= cluster_sizes[i];

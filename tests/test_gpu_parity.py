@@ -1,0 +1,300 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Integer outputs (partition ids, PQ codes, probe ids) and f32 L2/Dot/ADC distances must be
+BIT-EXACT; trained models are bit-exact given the same initial centroids (our training is
+deterministic by construction, see lance_b200/csrc/kmeans.cu)."""
+import numpy as np
+import pytest
+
+import lance_b200 as lb
+from lance_b200 import synth
+from oracle import binding as ob
+
+pytestmark = pytest.mark.gpu
+NT = 16
+
+
+def test_device_present_and_native_library_loaded():
+    assert lb.device_count() >= 1, "no GPU: -m gpu tests must run on a B200"
+    lb.set_device(0)
+    assert lb.launch_count(reset=True) >= 0
+
+
+@pytest.mark.parametrize("d", [8, 5, 16, 32, 128, 100, 768])
+def test_l2_distance_batch_bit_exact(d):
+    rng = np.random.default_rng(d)
+    x = rng.standard_normal(d).astype(np.float32)
+    y = rng.standard_normal((77, d)).astype(np.float32)
+    assert np.array_equal(lb.l2_distance_batch(x, y, d), ob.l2_batch(x, y, d))
+
+
+def test_dot_distance_batch_bit_exact():
+    rng = np.random.default_rng(0)
+    for d in (8, 24, 128):
+        x = rng.standard_normal(d).astype(np.float32)
+        y = rng.standard_normal((33, d)).astype(np.float32)
+        exp = np.array([np.float32(1.0) - np.float32(ob.dot(x, v)) for v in y], np.float32)
+        assert np.array_equal(lb.dot_distance_batch(x, y, d), exp)
+
+
+def test_reference_known_answers_on_gpu():
+    import json, os
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_known_answers.json")))
+    for c in cases:
+        if c["op"] != "l2_batch":
+            continue
+        got = lb.l2_distance_batch(c["frm"], c["to"], c["d"])
+        exp = np.asarray(c["expect"], np.float64)
+        if c.get("exact"):
+            assert np.array_equal(got.astype(np.float64), exp), c["name"]
+        else:
+            assert np.all(np.abs(got - exp) <= c["rel"] * np.abs(exp)), c["name"]
+
+
+@pytest.mark.parametrize("n,d,k", [(1000, 128, 256), (777, 128, 100), (513, 64, 17), (300, 8, 16),
+                                   (300, 4, 256), (257, 40, 33), (100, 200, 7), (64, 768, 50)])
+def test_compute_partitions_bit_exact(n, d, k):
+    rng = np.random.default_rng(n + d + k)
+    cent = rng.standard_normal((k, d)).astype(np.float32)
+    data = rng.standard_normal((n, d)).astype(np.float32)
+    p, dist, valid = lb.compute_partitions(cent, data)
+    po, do, vo = ob.compute_membership(cent, data, nthreads=NT)
+    assert np.array_equal(valid, vo) and valid.all()
+    assert np.array_equal(p, po)
+    assert np.array_equal(dist, do)
+
+
+def test_compute_partitions_sift_shaped_integers_have_ties():
+    # SIFT-like small integers -> many exactly equal distances: first-minimum rule must hold
+    data = synth.sift_like(5000, 128, n_components=32, seed=3)
+    cent = data[:256].copy()
+    cent[10] = cent[3]  # duplicate centroid: index 3 must always win over 10
+    p, dist, _ = lb.compute_partitions(cent, data)
+    po, do, _ = ob.compute_membership(cent, data, nthreads=NT)
+    assert np.array_equal(p, po) and np.array_equal(dist, do)
+    assert not (p == 10).any()
+
+
+def test_compute_partitions_nan_inf_rows_are_none():
+    # kmeans.rs:1447-1486
+    rng = np.random.default_rng(9)
+    cent = rng.standard_normal((20, 32)).astype(np.float32)
+    data = rng.standard_normal((50, 32)).astype(np.float32)
+    data[3, 5] = np.nan
+    data[7, :] = np.nan
+    data[11, 0] = np.inf
+    p, dist, valid = lb.compute_partitions(cent, data)
+    po, do, vo = ob.compute_membership(cent, data)
+    assert np.array_equal(valid, vo) and not valid[3] and not valid[7] and not valid[11]
+    assert np.array_equal(p[valid], po[vo]) and np.array_equal(dist[valid], do[vo])
+
+
+def test_compute_partitions_dot_metric():
+    rng = np.random.default_rng(10)
+    cent = rng.standard_normal((40, 64)).astype(np.float32)
+    data = rng.standard_normal((333, 64)).astype(np.float32)
+    p, dist, _ = lb.compute_partitions(cent, data, "dot")
+    po, do, _ = ob.compute_membership(cent, data, metric="dot", nthreads=NT)
+    assert np.array_equal(p, po) and np.array_equal(dist, do)
+
+
+@pytest.mark.parametrize("n,d,k", [(6000, 32, 16), (20000, 128, 64), (3000, 8, 256)])
+def test_kmeans_training_bit_exact_given_init(n, d, k):
+    data = synth.gaussian_mixture(n, d, n_components=k, seed=n)
+    init = data[np.random.default_rng(1).choice(n, k, replace=False)].copy()
+    km = lb.train_kmeans(data, d, k, max_iters=20, centroids=init, balance_factor=1.0)
+    nn = min(n, 256 * k)
+    co, loss_o, it_o = ob.kmeans_train(data[:nn], k, max_iters=20,
+                                       balance_factor=float(np.float32(1.0) / np.float32(nn)),
+                                       init_centroids=init, nthreads=NT)
+    assert km.iters == it_o
+    assert np.array_equal(km.centroids, co)
+    assert km.loss == loss_o
+
+
+def test_kmeans_training_seeded_random_init_matches_oracle():
+    data = synth.gaussian_mixture(8000, 32, n_components=32, seed=5)
+    km = lb.train_kmeans(data, 32, 32, max_iters=15, seed=42)
+    co, loss_o, it_o = ob.kmeans_train(data, 32, max_iters=15, seed=42, nthreads=NT)
+    assert km.iters == it_o and np.array_equal(km.centroids, co) and km.loss == loss_o
+
+
+def test_kmeans_empty_cluster_split():
+    # duplicate init centroids force empty clusters -> split_clusters path (kmeans.rs:174-207)
+    data = synth.gaussian_mixture(4000, 16, n_components=4, seed=8)
+    init = np.repeat(data[:4], 4, axis=0).copy()  # 16 centroids, only 4 distinct
+    km = lb.train_kmeans(data, 16, 16, max_iters=8, centroids=init, seed=3)
+    co, loss_o, it_o = ob.kmeans_train(data, 16, max_iters=8, init_centroids=init, seed=3, nthreads=NT)
+    assert km.iters == it_o and np.array_equal(km.centroids, co)
+    assert np.isfinite(km.centroids).all()
+
+
+def test_pq_training_bit_exact_given_codebook_init():
+    rng = np.random.default_rng(4)
+    n, d, M = 8000, 64, 8
+    data = synth.gaussian_mixture(n, d, n_components=300, seed=4)
+    init = np.stack([data[rng.choice(n, 256, replace=False)][:, m * 8:(m + 1) * 8] for m in range(M)])
+    pq = lb.PQBuildParams(M, 8, max_iters=12, codebook=init).build(data)
+    cbo, iters_o = ob.pq_train(data, M, max_iters=12, init_codebook=init, nthreads=NT)
+    assert np.array_equal(pq.train_iters.astype(np.int32), iters_o)
+    assert np.array_equal(pq.codebook, cbo)
+
+
+def test_pq_training_seeded_random_init_matches_oracle():
+    data = synth.gaussian_mixture(5000, 32, n_components=300, seed=6)
+    pq = lb.PQBuildParams(8, 8, max_iters=6, seed=11).build(data)
+    cbo, iters_o = ob.pq_train(data, 8, max_iters=6, seed=11, nthreads=NT)
+    assert np.array_equal(pq.codebook, cbo)
+
+
+@pytest.mark.parametrize("d,M", [(128, 16), (64, 16), (32, 32), (96, 8)])
+def test_pq_encode_bit_exact(d, M):
+    rng = np.random.default_rng(d + M)
+    cb = rng.standard_normal((M, 256, d // M)).astype(np.float32)
+    vec = rng.standard_normal((1500, d)).astype(np.float32)
+    pq = lb.ProductQuantizer(M, 8, d, cb)
+    assert np.array_equal(pq.quantize(vec), ob.pq_encode(cb, vec, nthreads=NT))
+
+
+def test_pq_encode_fused_residual_bit_exact():
+    rng = np.random.default_rng(77)
+    d, M, K = 128, 16, 50
+    cent = rng.standard_normal((K, d)).astype(np.float32)
+    cb = (rng.standard_normal((M, 256, d // M)) * 0.5).astype(np.float32)
+    vec = rng.standard_normal((2000, d)).astype(np.float32)
+    part, _, _ = ob.compute_membership(cent, vec, nthreads=NT)
+    res = ob.compute_residual(cent, vec, part, nthreads=NT)
+    assert np.array_equal(lb.compute_residual(cent, vec, part), res)
+    pq = lb.ProductQuantizer(M, 8, d, cb)
+    assert np.array_equal(pq.quantize(vec, centroids=cent, part_ids=part), ob.pq_encode(cb, res, nthreads=NT))
+    p2, c2, v2 = lb.ivfpq_transform(cent, cb, vec)
+    assert np.array_equal(p2, part) and np.array_equal(c2, ob.pq_encode(cb, res, nthreads=NT)) and v2.all()
+
+
+def test_lut_and_scan_bit_exact():
+    rng = np.random.default_rng(12)
+    d, M = 128, 16
+    cb = rng.standard_normal((M, 256, d // M)).astype(np.float32)
+    q = rng.standard_normal(d).astype(np.float32)
+    lut = lb.build_distance_table_l2(cb, 8, M, q)
+    assert np.array_equal(lut, ob.build_lut(cb, q))
+    codes = rng.integers(0, 256, size=(5000, M), dtype=np.uint8)
+    ct = ob.transpose_codes(codes)
+    assert np.array_equal(lb.compute_pq_distance(lut, 8, M, ct), ob.pq_scan(lut, ct))
+    lut_dot = lb.build_distance_table_l2(cb, 8, M, q, "dot")
+    assert np.array_equal(lut_dot, ob.build_lut(cb, q, metric="dot"))
+    assert np.array_equal(lb.compute_pq_distance(lut_dot, 8, M, ct, "dot"), ob.pq_scan(lut_dot, ct, metric="dot"))
+
+
+def test_pq_scan_reference_deterministic_case():
+    # lance-index/src/vector/pq/distance.rs:337-365
+    nv, M, d = 100, 4, 16
+    codebook = np.arange(256 * d, dtype=np.float32).reshape(M, 256, d // M)
+    query = np.arange(d, dtype=np.float32)
+    lut = lb.build_distance_table_l2(codebook, 8, M, query)
+    codes = (np.arange(nv * M) % 256).astype(np.uint8).reshape(nv, M)
+    got = lb.compute_pq_distance(lut, 8, M, ob.transpose_codes(codes))
+    exp = np.zeros(nv, np.float32)
+    for m in range(M):
+        exp = (exp + lut[m * 256 + codes[:, m].astype(np.int64)]).astype(np.float32)
+    assert np.array_equal(got, exp)
+
+
+def _check_topk(ids, dists, oi, od, k):
+    """distance multisets identical; ids identical strictly below the k-th distance (rows tied
+    at the boundary are implementation-defined in the reference's BinaryHeap)."""
+    assert np.array_equal(np.sort(dists), np.sort(od))
+    if len(od) == 0:
+        return
+    kth = np.sort(od)[-1]
+    a = set(ids[dists < kth].tolist())
+    b = set(oi[od < kth].tolist())
+    assert a == b
+
+
+def test_flat_topk_matches_heap_semantics():
+    rng = np.random.default_rng(13)
+    d = rng.integers(0, 50, size=3000).astype(np.float32)  # lots of ties
+    rid = rng.permutation(3000).astype(np.uint64)
+    for k in (1, 10, 100, 500):
+        ids, dist = lb.flat_topk(d, rid, k)
+        oi, od = ob.flat_topk(d, rid, k)
+        _check_topk(ids, dist, oi, od, k)
+    ids, dist = lb.flat_topk(d[:5], rid[:5], 10)
+    assert len(ids) == 5
+
+
+def test_find_partitions_bit_exact():
+    rng = np.random.default_rng(14)
+    cent = rng.standard_normal((300, 128)).astype(np.float32)
+    q = rng.standard_normal((40, 128)).astype(np.float32)
+    ids, dists = lb.kmeans_find_partitions(cent, q, 20)
+    for i in range(40):
+        oi, od = ob.find_partitions(cent, q[i], 20)
+        assert np.array_equal(ids[i], oi) and np.array_equal(dists[i], od)
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+def test_index_search_matches_oracle(metric):
+    rng = np.random.default_rng(15)
+    n, d, K, M = 30000, 64, 40, 16
+    data = synth.gaussian_mixture(n, d, n_components=K, seed=15)
+    if metric == "dot":
+        data /= np.linalg.norm(data, axis=1, keepdims=True)
+    ix = lb.IvfPqIndex.build(data, metric, lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, max_iters=10, pq_max_iters=8))
+    parts = ix.export()
+    assert parts["part_offsets"][-1] == n and sorted(parts["row_ids"].tolist()) == list(range(n))
+    q = synth.gaussian_mixture(50, d, n_components=K, seed=16)
+    for k, nprobes in ((10, 1), (10, 8), (100, 5)):
+        ids, dists = ix.search(q, k=k, nprobes=nprobes)
+        oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"],
+                                     parts["codes"], parts["row_ids"], q, k, nprobes, metric=metric, nthreads=NT)
+        for i in range(len(q)):
+            c = int(oc[i])
+            assert np.isinf(dists[i, c:]).all()
+            _check_topk(ids[i, :c], dists[i, :c], oi[i, :c], od[i, :c], k)
+            assert np.all(np.diff(dists[i, :c]) >= 0)
+
+
+def test_build_transform_equals_oracle_and_recall():
+    # v2.rs:1310-1384: IVF_PQ recall floor on random data; here against exact brute force
+    n, d, K, M = 50000, 128, 64, 16
+    data = synth.sift_like(n, d, n_components=256, seed=21)
+    ix = lb.IvfPqIndex.build(data, "l2", lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M))
+    parts = ix.export()
+    order = np.argsort(parts["row_ids"])
+    p_ref, _, _ = ob.compute_membership(parts["centroids"], data, nthreads=NT)
+    sizes = np.diff(parts["part_offsets"]).astype(np.int64)
+    assert np.array_equal(np.repeat(np.arange(K, dtype=np.uint32), sizes)[order], p_ref)
+    res = ob.compute_residual(parts["centroids"], data, p_ref, nthreads=NT)
+    assert np.array_equal(parts["codes"][order], ob.pq_encode(parts["codebook"], res, nthreads=NT))
+    # rows inside a partition keep input order (stable grouping)
+    for p in range(0, K, 7):
+        r = parts["row_ids"][parts["part_offsets"][p]:parts["part_offsets"][p + 1]]
+        assert np.all(np.diff(r.astype(np.int64)) > 0)
+    q = synth.sift_like_queries(100, d, n_components=256, seed=21)
+    gt, _ = ob.brute_force_topk(data, q, 10, nthreads=NT)
+    ids, _ = ix.search(q, k=10, nprobes=K)
+    recall = np.mean([len(set(ids[i].tolist()) & set(gt[i].tolist())) / 10 for i in range(len(q))])
+    assert recall >= 0.5, recall  # PQ-only ceiling on SIFT-like data is ~0.6
+    ids100, _ = ix.search(q, k=100, nprobes=K)
+    r100 = np.mean([len(set(ids100[i].tolist()) & set(gt[i].tolist())) / 10 for i in range(len(q))])
+    assert r100 >= 0.95, r100
+
+
+def test_device_resident_inputs():
+    rng = np.random.default_rng(30)
+    cent = rng.standard_normal((64, 128)).astype(np.float32)
+    data = rng.standard_normal((4096, 128)).astype(np.float32)
+    dd = lb.DeviceArray.from_numpy(data)
+    p1, d1, _ = lb.compute_partitions(cent, dd)
+    p2, d2, _ = lb.compute_partitions(cent, data)
+    assert np.array_equal(p1, p2) and np.array_equal(d1, d2)
+    assert np.array_equal(dd.numpy(), data)
+
+
+def test_unsupported_is_surfaced_not_masked():
+    with pytest.raises(lb.LanceB200Error) as e:
+        lb.PQBuildParams(4, 4).build(np.zeros((300, 16), np.float32))
+    assert e.value.status == 2
+    with pytest.raises(lb.LanceB200Error):
+        lb.train_kmeans(np.zeros((10, 8), np.float32), 8, 20)

@@ -182,8 +182,11 @@ def test_kmeans_train_converges_and_is_deterministic():
     c2, loss2, it2 = ob.kmeans_train(data, 8, seed=7, nthreads=1)
     assert np.array_equal(c1, c2) and loss1 == loss2 and it1 == it2
     assert 1 <= it1 <= 50 and np.isfinite(c1).all()
-    ids, dists, _ = ob.compute_membership(c1, data)
-    assert dists.mean() < 40.0
+    # Lloyd never increases the loss: full training must not be worse than a single iteration
+    c_one, loss_one, _ = ob.kmeans_train(data, 8, seed=7, max_iters=1)
+    _, d_full, _ = ob.compute_membership(c1, data)
+    _, d_one, _ = ob.compute_membership(c_one, data)
+    assert d_full.sum() <= d_one.sum()
 
 
 def test_find_partitions_sorted():
