@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- IVF_PQ index-build Mvec/s and QPS@recall@10 on a SIFT-1M-shaped workload.
+
+    python bench.py --gpus N --steps K --warmup W          # our arm (CUDA, through the C ABI)
+    python bench.py --impl reference --steps K --warmup W  # the reference's CPU path (oracle port)
+
+A "step" of the headline metric is ONE complete IVF_PQ(256,16) index build over the 1M x 128 f32
+dataset: sample -> k-means (IVF) -> residuals -> 16 sub-space k-means (PQ) -> partition id +
+residual + PQ code for every row -> group by partition.  `value` is measured with the dataset
+already resident in HBM; `e2e` is the same build through the C ABI from a pinned HOST buffer with
+the results (partition offsets, codes, row ids, centroids, codebook) copied back to the host.
+The query half of BASELINE.json's metric (QPS at recall@10) is reported in the "query" object.
+
+torch is used only to synthesise the dataset on the device, for the ground truth of recall, and
+for torch.distributed; nothing on the measured path is a torch op.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ROWS, DIM, NUM_PARTITIONS, NUM_SUB_VECTORS = 1_000_000, 128, 256, 16
+NQ, TOPK, NPROBES = 10_000, 10, 10
+WORKLOAD = "C1: SIFT-1M-shaped synthetic 1M x 128 f32, IVF_PQ num_partitions=256 num_sub_vectors=16, L2"
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], 0, set()
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9 or not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data on the device (same law as lance_b200/synth.py:sift_like)
+# ------------------------------------------------------------------------------------------------
+def device_dataset(torch, n, nq, seed, device):
+    from lance_b200 import synth
+    W, cm = synth.sift_model(DIM, 24, 1024, 1234)
+    W, cm = torch.from_numpy(W).to(device), torch.from_numpy(cm).to(device)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+
+    def draw(rows):
+        out = torch.empty((rows, DIM), dtype=torch.float32, device=device)
+        for s in range(0, rows, 1 << 18):
+            e = min(rows, s + (1 << 18))
+            comp = torch.randint(0, cm.shape[0], (e - s,), device=device, generator=g)
+            z = cm[comp] + torch.randn((e - s, 24), device=device, generator=g)
+            x = torch.clamp(z @ W * 12.0 + 20.0, min=0.0)
+            x += torch.randn((e - s, DIM), device=device, generator=g) * 3.0
+            out[s:e] = torch.clamp(torch.round(x), 0.0, 255.0)
+        return out
+
+    return draw(n), draw(nq)
+
+
+def ground_truth(torch, data, queries, k):
+    """exact top-k by brute force on the device (integer-valued f32 -> sums are exact in fp32)"""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    xn = (data * data).sum(1)
+    out = []
+    for s in range(0, queries.shape[0], 256):
+        q = queries[s:s + 256]
+        d2 = xn[None, :] - 2.0 * (q @ data.T) + (q * q).sum(1)[:, None]
+        out.append(torch.topk(d2, k, dim=1, largest=False).indices)
+    return torch.cat(out).cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path (the oracle port of the reference loops), used by --impl reference and cpu_baseline
+# ------------------------------------------------------------------------------------------------
+def cpu_build(ob, data_host, init_centroids, init_codebook_rows, max_iters, threads, transform_rows, sample_ivf, sample_pq):
+    """Returns (seconds for a full build extrapolated from `transform_rows`, detail dict).
+    Training runs in full (its cost does not depend on N); the per-row transform runs on
+    `transform_rows` rows and is scaled to N_ROWS."""
+    n = data_host.shape[0]
+    t0 = time.perf_counter()
+    xs = data_host[sample_ivf]
+    cent, loss, it_ivf = ob.kmeans_train(xs, NUM_PARTITIONS, max_iters=max_iters,
+                                         balance_factor=float(np.float32(1.0) / np.float32(len(xs))),
+                                         init_centroids=init_centroids, nthreads=threads)
+    t1 = time.perf_counter()
+    xp = data_host[sample_pq]
+    part, _, _ = ob.compute_membership(cent, xp, nthreads=threads)
+    res = ob.compute_residual(cent, xp, part, nthreads=threads)
+    cb, it_pq = ob.pq_train(res, NUM_SUB_VECTORS, max_iters=max_iters, init_codebook=init_codebook_rows, nthreads=threads)
+    t2 = time.perf_counter()
+    rows = data_host[:transform_rows]
+    p, _, _ = ob.compute_membership(cent, rows, nthreads=threads)
+    r = ob.compute_residual(cent, rows, p, nthreads=threads)
+    codes = ob.pq_encode(cb, r, nthreads=threads)
+    t3 = time.perf_counter()
+    # grouping (stable sort by partition) is negligible on the CPU side and left out (favours the CPU)
+    scale = N_ROWS / float(transform_rows)
+    total = (t1 - t0) + (t2 - t1) + (t3 - t2) * scale
+    return total, {"ivf_train_s": t1 - t0, "pq_train_s": t2 - t1, "transform_s_measured": t3 - t2,
+                   "transform_rows": int(transform_rows), "ivf_iters": int(it_ivf), "pq_iters_max": int(max(it_pq)),
+                   "model": (cent, cb)}
+
+
+def cpu_query_qps(ob, model, data_host, queries_host, threads, nq):
+    cent, cb = model
+    p, _, _ = ob.compute_membership(cent, data_host, nthreads=threads)
+    res = ob.compute_residual(cent, data_host, p, nthreads=threads)
+    codes = ob.pq_encode(cb, res, nthreads=threads)
+    order = np.argsort(p, kind="stable")
+    off = np.zeros(NUM_PARTITIONS + 1, np.uint64)
+    off[1:] = np.cumsum(np.bincount(p, minlength=NUM_PARTITIONS))
+    codes_s, rid = codes[order], order.astype(np.uint64)
+    t0 = time.perf_counter()
+    ob.ivfpq_search(cent, cb, off, codes_s, rid, queries_host[:nq], TOPK, NPROBES, nthreads=threads)
+    return nq / (time.perf_counter() - t0)
+
+
+def host_dataset_numpy(n, nq):
+    from lance_b200 import synth
+    return synth.sift_like(n, DIM), synth.sift_like_queries(nq, DIM)
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path (oracle port; the Rust toolchain and
+    pylance are absent), all host threads, same config/metric as our arm."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import binding as ob
+    threads = ob.nthreads_default()
+    transform_rows = 200_000
+    data, queries = host_dataset_numpy(max(transform_rows, 65536 * 2), 2000)
+    rng = np.random.default_rng(0)
+    n = data.shape[0]
+    s_ivf = np.sort(rng.choice(n, 65536, replace=False))
+    s_pq = np.sort(rng.choice(n, 65536, replace=False))
+    times = []
+    detail = None
+    budget_s = 150.0
+    t_begin = time.perf_counter()
+    done = 0
+    for i in range(args.warmup + args.steps):
+        if i >= 1 and (time.perf_counter() - t_begin) > budget_s and done >= 1:
+            break
+        t, detail = cpu_build(ob, data, None, None, 50, threads, transform_rows, s_ivf, s_pq)
+        if i >= min(args.warmup, 1):
+            times.append(t)
+            done += 1
+    sec = float(np.mean(times))
+    value = N_ROWS / sec / 1e6
+    model = detail.pop("model")
+    qps = cpu_query_qps(ob, model, data[:transform_rows], queries, threads, 2000)
+    sample = (f"IVF + PQ training in full (2 x 65536-row samples, <=50 iters), transform on {transform_rows} of "
+              f"{N_ROWS} rows scaled linearly; {len(times)} timed steps")
+    line = {
+        "impl": "reference", "metric": "ivf_pq_index_build_mvec_per_s", "value": value, "unit": "Mvec/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "k": TOPK, "nprobes": NPROBES},
+        "cpu_baseline": {"value": value, "unit": "Mvec/s", "cores": threads, "kind": "port", "sample": sample, **detail},
+        "e2e": {"value": value, "unit": "Mvec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "query": {"qps": qps, "nprobes": NPROBES, "k": TOPK, "note": "index over the transform sample only"},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+KERNEL_BYTES = {
+    # algorithmic bytes per launch (DESIGN.md "kernels"): rows*d*4 read + outputs written
+    "ivf_train:assign_exact": lambda ns, n: ns * DIM * 4 + ns * 9,
+    "pq_train:pq_assign_exact": lambda ns, n: ns * DIM * 4 + ns * NUM_SUB_VECTORS * 9,
+    "pq_train:assign_exact": lambda ns, n: ns * DIM * 4 + ns * 4,
+    "transform:assign_exact": lambda ns, n: n * DIM * 4 + n * 5,
+    "transform:pq_assign_exact": lambda ns, n: n * DIM * 4 + n * 4 + n * NUM_SUB_VECTORS,
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--rows", type=int, default=N_ROWS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    assert args.warmup >= 0 and args.steps >= 1
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import torch
+    import torch.distributed as dist
+
+    import lance_b200 as lb
+    if lb.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (lance_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    lb.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        lb.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    n = args.rows
+    # each rank owns an independent shard of n rows (weak scaling: no data-path collective)
+    data_t, queries_t = device_dataset(torch, n, NQ, 1000 + rank, device)
+    data_dev = lb.DeviceArray.__new__(lb.DeviceArray)
+    data_dev.shape, data_dev.dtype, data_dev.ptr, data_dev.nbytes = (n, DIM), np.dtype(np.float32), data_t.data_ptr(), n * DIM * 4
+    data_dev.free = lambda: None
+    q_dev = lb.DeviceArray.__new__(lb.DeviceArray)
+    q_dev.shape, q_dev.dtype, q_dev.ptr, q_dev.nbytes = (NQ, DIM), np.dtype(np.float32), queries_t.data_ptr(), NQ * DIM * 4
+    q_dev.free = lambda: None
+    params = lb.IvfBuildParams(num_partitions=NUM_PARTITIONS, num_sub_vectors=NUM_SUB_VECTORS, seed=7)
+
+    # ---- resident build: W warm-up, K timed ----------------------------------------------------
+    for _ in range(args.warmup):
+        lb.IvfPqIndex.build(data_dev, "l2", params).close()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    lb.launch_count(reset=True)
+    lb.profile.reset()
+    lb.profile.enable(True)
+    t_wall0 = time.time()
+    lb.timer_start()
+    stats = None
+    for _ in range(args.steps):
+        ix = lb.IvfPqIndex.build(data_dev, "l2", params)
+        stats = ix.stats
+        ix.close()
+    ms_total = lb.timer_stop()
+    barrier()
+    t_wall1 = time.time()
+    lb.profile.enable(False)
+    launches = lb.launch_count()
+    ms_step = max_over_ranks(ms_total / args.steps)
+    clocks = sampler.summary(t_wall0, t_wall1)
+    value = world * n / (ms_step * 1e-3) / 1e6
+
+    # ---- kernel breakdown + roofline of the dominant kernel -------------------------------------
+    hbm_peak, peak_src = peaks()
+    fams = {}
+    for fam in ["ivf_train:assign_exact", "ivf_train:member_sort", "ivf_train:kmeans_update", "ivf_train:kmeans_stats",
+                "ivf_train:transpose_centroids", "pq_train:pq_assign_exact", "pq_train:member_sort",
+                "pq_train:kmeans_update", "pq_train:kmeans_stats", "pq_train:assign_exact", "transform:assign_exact",
+                "transform:pq_assign_exact", "group:member_sort", "group:group_by_partition"]:
+        cnt, ms = lb.profile.get(fam)
+        if cnt:
+            fams[fam] = {"launches_per_step": cnt / args.steps, "ms_per_step": ms / args.steps,
+                         "share": ms / ms_total}
+    dom = max((f for f in fams if f in KERNEL_BYTES), key=lambda f: fams[f]["ms_per_step"])
+    per_launch_ms = fams[dom]["ms_per_step"] / fams[dom]["launches_per_step"]
+    alg_bytes = KERNEL_BYTES[dom](65536, n)
+    achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": per_launch_ms,
+                "note": "exact-order f32 kernels are FP32-pipe bound (3 non-fused ops per element pair), "
+                        "not HBM bound; see DESIGN.md"}
+
+    # ---- e2e build: pinned host -> device -> host, through the C ABI ---------------------------
+    pin = lb.PinnedArray((n, DIM), np.float32)
+    import ctypes as C
+    lb._lib.check(lb.lib().lb2_memcpy(C.c_void_p(pin.ptr), C.c_void_p(data_t.data_ptr()), C.c_size_t(n * DIM * 4)))
+
+    def e2e_step():
+        ix = lb.IvfPqIndex.build(pin, "l2", params)
+        parts = ix.export()
+        ix.close()
+        return parts
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        parts = e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+    d2h = int(parts["codes"].nbytes + parts["row_ids"].nbytes + parts["part_offsets"].nbytes +
+              parts["centroids"].nbytes + parts["codebook"].nbytes)
+    e2e = {"value": world * n / (e2e_ms * 1e-3) / 1e6, "unit": "Mvec/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": n * DIM * 4, "d2h_bytes_per_step": d2h}
+
+    # ---- query: QPS @ recall@10 ------------------------------------------------------------------
+    ix = lb.IvfPqIndex.build(data_dev, "l2", params)
+    ids_dev = lb.DeviceArray((NQ, TOPK), np.uint64)
+    d_dev = lb.DeviceArray((NQ, TOPK), np.float32)
+    for _ in range(max(args.warmup, 1)):
+        ix.search(q_dev, TOPK, NPROBES, out=(ids_dev, d_dev))
+    barrier()
+    lb.profile.reset()
+    lb.profile.enable(True)
+    lb.timer_start()
+    for _ in range(args.steps):
+        ix.search(q_dev, TOPK, NPROBES, out=(ids_dev, d_dev))
+    q_ms = max_over_ranks(lb.timer_stop() / args.steps)
+    lb.profile.enable(False)
+    scan_cnt, scan_ms = lb.profile.get("search:pq_scan")
+    q_host = queries_t.cpu().numpy()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ids_h, d_h = ix.search(q_host, TOPK, NPROBES)
+    q_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    gt = ground_truth(torch, data_t, queries_t[:1000], TOPK)
+    recall = float(np.mean([len(set(ids_h[i].tolist()) & set(gt[i].tolist())) / TOPK for i in range(1000)]))
+    scan_bytes = NQ * NPROBES * (n / NUM_PARTITIONS) * NUM_SUB_VECTORS + NQ * DIM * 4
+    scan_launch_ms = scan_ms / max(scan_cnt, 1)
+    query = {"qps": world * NQ / (q_ms * 1e-3), "e2e_qps": world * NQ / (q_e2e_ms * 1e-3), "recall_at_10": recall,
+             "nprobes": NPROBES, "k": TOPK, "batch": NQ, "refine_factor": None, "ms_per_batch": q_ms,
+             "roofline": {"kernel": "search:pq_scan", "bound": "hbm", "achieved": scan_bytes / (scan_launch_ms * 1e-3) / 1e9,
+                          "peak": hbm_peak, "unit": "GB/s", "frac": scan_bytes / (scan_launch_ms * 1e-3) / 1e9 / hbm_peak,
+                          "traffic": None, "avg_launch_ms": scan_launch_ms}}
+    sampler.stop()
+
+    # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import binding as ob
+        threads = ob.nthreads_default()
+        rows = min(n, 200_000)
+        host = pin.array
+        rng = np.random.default_rng(0)
+        s_ivf = np.sort(rng.choice(n, min(n, 65536), replace=False))
+        s_pq = np.sort(rng.choice(n, min(n, 65536), replace=False))
+        sec, detail = cpu_build(ob, host, None, None, 50, threads, rows, s_ivf, s_pq)
+        detail.pop("model")
+        cpu_baseline = {"value": N_ROWS / sec / 1e6, "unit": "Mvec/s", "cores": threads, "kind": "port",
+                        "sample": f"IVF + PQ training in full (<=50 iters each), transform on {rows} of {n} rows scaled linearly",
+                        **detail}
+
+    if rank == 0:
+        line = {
+            "metric": "ivf_pq_index_build_mvec_per_s", "value": value, "unit": "Mvec/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rows_per_gpu": n, "sharding": "independent index shard per GPU (no data-path collective)",
+                       "cache": "inputs (512 MB) larger than L2 (126 MB)", "k": TOPK, "nprobes": NPROBES},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "build_phases_ms": {"ivf_train": stats.ms_ivf_train, "pq_train": stats.ms_pq_train, "transform": stats.ms_transform,
+                                "group": stats.ms_group, "ivf_iters": stats.ivf_iters, "pq_iters_max": stats.pq_iters_max},
+            "kernels": fams, "roofline": roofline, "query": query, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

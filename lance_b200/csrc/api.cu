@@ -635,6 +635,7 @@ lb2_status lb2_index_search(lb2_index* index, const void* queries, uint64_t nq, 
   OutArg<uint64_t> oi(row_ids_out, (size_t)nq * k);
   OutArg<float> od(dists_out, (size_t)nq * k);
   OutArg<uint32_t> oc(counts_out, nq);
+  TagScope tg("search");
   ivfpq_search_f32(index->centroids.p, index->K, d, index->metric, index->codebook.p, index->M,
                    index->nbits, index->part_offsets.p, index->codes.p, index->row_ids.p, qp, nq, k,
                    nprobes, oi.get(), od.get(), oc.get());
@@ -722,6 +723,7 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
   try {
     // 1. IVF: sample K*sample_rate rows (rust/lance/src/index/vector/ivf.rs:1237-1241)
     {
+      TagScope tg("ivf_train");
       const uint64_t s = std::min<uint64_t>(n, (uint64_t)K * params->ivf.sample_rate);
       const float* xs = x;
       DevBuf<float> sample;
@@ -742,6 +744,7 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
     LB2_CUDA(cudaEventRecord(ev[1], c.stream));
     // 2. PQ: sample 256*2^nbits rows, residuals w.r.t. the IVF centroids (builder.rs:410-450)
     {
+      TagScope tg("pq_train");
       const uint64_t s = std::min<uint64_t>(n, params->pq.sample_rate * 256);
       std::vector<uint64_t> rows = sample_rows(n, s, params->seed + 1);
       DevBuf<uint64_t> rows_d(s);
@@ -761,12 +764,15 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
     // 3. transform every row (lance-index/src/vector/ivf.rs:357: partition -> residual -> PQ)
     DevBuf<uint32_t> part(n);
     DevBuf<uint8_t> codes((size_t)n * M), valid(n);
+    TagScope* tg3 = new TagScope("transform");
     assign_f32(x, n, d, ix->centroids.p, K, am, nullptr, part.p, nullptr, valid.p, nullptr);
     small_d_assign_f32(x, n, d, M, ds, ix->codebook.p, 256, am,
                        am == METRIC_DOT ? nullptr : ix->centroids.p,
                        am == METRIC_DOT ? nullptr : part.p, valid.p, codes.p, nullptr, nullptr,
                        nullptr, nullptr);
+    delete tg3;
     LB2_CUDA(cudaEventRecord(ev[3], c.stream));
+    TagScope tg4("group");
     // 4. group rows by partition (shuffle + build_partitions, builder.rs:501-937)
     InArg<uint64_t> rid(row_ids, n);
     index_load_dev(ix, part.p, codes.p, rid.get(), n);

@@ -81,6 +81,7 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   uint64_t launches = 0;
   bool profiling = false;
+  std::string tag;  // phase prefix of the profile key: "ivf_train", "pq_train", "transform", "search" ...
   std::map<std::string, ProfEntry> prof;
   std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -106,7 +107,7 @@ struct LaunchScope {
   ~LaunchScope() {
     if (c.profiling) {
       cudaEventRecord(e1, c.stream);
-      c.pending.push_back({name, {e0, e1}});
+      c.pending.push_back({c.tag.empty() ? std::string(name) : c.tag + ":" + name, {e0, e1}});
     }
   }
 };
@@ -215,6 +216,12 @@ template <class T>
 inline void d2d(T* dst, const T* src, size_t count) {
   LB2_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToDevice, ctx().stream));
 }
+
+struct TagScope {
+  std::string prev;
+  explicit TagScope(const char* t) : prev(ctx().tag) { ctx().tag = t; }
+  ~TagScope() { ctx().tag = prev; }
+};
 
 inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 
