@@ -242,6 +242,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--rows", type=int, default=N_ROWS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", default="all", choices=["all", "build", "query"],
+                    help="profiling aid (ncu): restrict the run to the resident build or to the query batch")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -334,28 +336,35 @@ def main():
                 "note": "exact-order f32 kernels are FP32-pipe bound (3 non-fused ops per element pair), "
                         "not HBM bound; see DESIGN.md"}
 
+    if args.only == "build":
+        if rank == 0:
+            print(json.dumps({"only": "build", "ms_per_step": ms_step, "value": value, "kernels": fams}))
+        return
     # ---- e2e build: pinned host -> device -> host, through the C ABI ---------------------------
-    pin = lb.PinnedArray((n, DIM), np.float32)
-    import ctypes as C
-    lb._lib.check(lb.lib().lb2_memcpy(C.c_void_p(pin.ptr), C.c_void_p(data_t.data_ptr()), C.c_size_t(n * DIM * 4)))
+    e2e = None
+    pin = None
+    if args.only == "all":
+        pin = lb.PinnedArray((n, DIM), np.float32)
+        import ctypes as C
+        lb._lib.check(lb.lib().lb2_memcpy(C.c_void_p(pin.ptr), C.c_void_p(data_t.data_ptr()), C.c_size_t(n * DIM * 4)))
 
-    def e2e_step():
-        ix = lb.IvfPqIndex.build(pin, "l2", params)
-        parts = ix.export()
-        ix.close()
-        return parts
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(e2e_steps):
-        parts = e2e_step()
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
-    d2h = int(parts["codes"].nbytes + parts["row_ids"].nbytes + parts["part_offsets"].nbytes +
-              parts["centroids"].nbytes + parts["codebook"].nbytes)
-    e2e = {"value": world * n / (e2e_ms * 1e-3) / 1e6, "unit": "Mvec/s", "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": n * DIM * 4, "d2h_bytes_per_step": d2h}
+        def e2e_step():
+            ix = lb.IvfPqIndex.build(pin, "l2", params)
+            parts = ix.export()
+            ix.close()
+            return parts
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            parts = e2e_step()
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+        d2h = int(parts["codes"].nbytes + parts["row_ids"].nbytes + parts["part_offsets"].nbytes +
+                  parts["centroids"].nbytes + parts["codebook"].nbytes)
+        e2e = {"value": world * n / (e2e_ms * 1e-3) / 1e6, "unit": "Mvec/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": n * DIM * 4, "d2h_bytes_per_step": d2h}
 
     # ---- query: QPS @ recall@10 ------------------------------------------------------------------
     ix = lb.IvfPqIndex.build(data_dev, "l2", params)
@@ -373,6 +382,8 @@ def main():
     lb.profile.enable(False)
     scan_cnt, scan_ms = lb.profile.get("search:pq_scan")
     q_host = queries_t.cpu().numpy()
+    ix.search(q_host, TOPK, NPROBES)
+    barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ids_h, d_h = ix.search(q_host, TOPK, NPROBES)
@@ -390,7 +401,7 @@ def main():
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and pin is not None:
         from oracle import binding as ob
         threads = ob.nthreads_default()
         rows = min(n, 200_000)
