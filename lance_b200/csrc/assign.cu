@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(256)
 assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __restrict__ cT,
                    int K, int Kp, const float* __restrict__ bias, uint32_t* __restrict__ part,
                    float* __restrict__ dist, uint8_t* __restrict__ valid,
-                   float* __restrict__ all_out) {
+                   float* __restrict__ all_out, const uint8_t* __restrict__ active) {
+  if (active && !active[0]) return;
   extern __shared__ float smem[];
   const int ld = d + 1;
   float* xs = smem;            // [64][d+1]
@@ -255,7 +256,9 @@ template <int METRIC, bool WRITE_ALL>
 __global__ void __launch_bounds__(256)
 generic_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __restrict__ cent, int K,
                const float* __restrict__ bias, uint32_t* __restrict__ part, float* __restrict__ dist,
-               uint8_t* __restrict__ valid, float* __restrict__ all_out) {
+               uint8_t* __restrict__ valid, float* __restrict__ all_out,
+               const uint8_t* __restrict__ active) {
+  if (active && !active[0]) return;
   extern __shared__ float smem[];
   constexpr int R = 8;
   float* xs = smem;  // [R][d]
@@ -329,8 +332,8 @@ generic_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __re
 // ------------------------------------------------------------------------------------------------
 template <int METRIC>
 static void assign_dispatch(const float* x, uint64_t n, int d, const float* cent, int K,
-                            const float* bias, uint32_t* part, float* dist, uint8_t* valid,
-                            float* all_out) {
+                            const float* bias, bool bias_padded, uint32_t* part, float* dist,
+                            uint8_t* valid, float* all_out, const uint8_t* active) {
   if (n == 0) return;
   if (d % 16 == 0 && d <= 256) {
     const int Kp = (K + 63) / 64 * 64;
@@ -339,7 +342,9 @@ static void assign_dispatch(const float* x, uint64_t n, int d, const float* cent
                cent, K, d, Kp, cT.get());
     DevBuf<float> biasp;
     const float* bp = nullptr;
-    if (bias) {
+    if (bias && bias_padded) {
+      bp = bias;
+    } else if (bias) {
       biasp.alloc(Kp);
       biasp.zero();
       d2d(biasp.get(), bias, K);
@@ -350,11 +355,11 @@ static void assign_dispatch(const float* x, uint64_t n, int d, const float* cent
     if (all_out) {
       set_smem(assign_tile_kernel<METRIC, true>, smem);
       LB2_LAUNCH("assign_exact", (assign_tile_kernel<METRIC, true>), grid, 256, smem, x, n, d,
-                 cT.get(), K, Kp, bp, part, dist, valid, all_out);
+                 cT.get(), K, Kp, bp, part, dist, valid, all_out, active);
     } else {
       set_smem(assign_tile_kernel<METRIC, false>, smem);
       LB2_LAUNCH("assign_exact", (assign_tile_kernel<METRIC, false>), grid, 256, smem, x, n, d,
-                 cT.get(), K, Kp, bp, part, dist, valid, all_out);
+                 cT.get(), K, Kp, bp, part, dist, valid, all_out, active);
     }
     return;
   }
@@ -364,20 +369,25 @@ static void assign_dispatch(const float* x, uint64_t n, int d, const float* cent
   if (all_out) {
     set_smem(generic_kernel<METRIC, true>, smem);
     LB2_LAUNCH("assign_exact_generic", (generic_kernel<METRIC, true>), grid, 256, smem, x, n, d,
-               cent, K, bias, part, dist, valid, all_out);
+               cent, K, bias, part, dist, valid, all_out, active);
   } else {
     set_smem(generic_kernel<METRIC, false>, smem);
     LB2_LAUNCH("assign_exact_generic", (generic_kernel<METRIC, false>), grid, 256, smem, x, n, d,
-               cent, K, bias, part, dist, valid, all_out);
+               cent, K, bias, part, dist, valid, all_out, active);
   }
 }
 
+void assign_f32_ex(const float* x, uint64_t n, int d, const float* cent, int K, int metric,
+                   const float* bias, bool bias_padded, uint32_t* part, float* dist, uint8_t* valid,
+                   float* all_out, const uint8_t* active) {
+  if (metric == METRIC_DOT)
+    assign_dispatch<METRIC_DOT>(x, n, d, cent, K, bias, bias_padded, part, dist, valid, all_out, active);
+  else
+    assign_dispatch<METRIC_L2>(x, n, d, cent, K, bias, bias_padded, part, dist, valid, all_out, active);
+}
 void assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, int metric,
                 const float* bias, uint32_t* part, float* dist, uint8_t* valid, float* all_out) {
-  if (metric == METRIC_DOT)
-    assign_dispatch<METRIC_DOT>(x, n, d, cent, K, bias, part, dist, valid, all_out);
-  else
-    assign_dispatch<METRIC_L2>(x, n, d, cent, K, bias, part, dist, valid, all_out);
+  assign_f32_ex(x, n, d, cent, K, metric, bias, false, part, dist, valid, all_out, nullptr);
 }
 
 template <int DS, int METRIC>

@@ -6,6 +6,11 @@ namespace lb2 {
 // bias (nullable, [K]) is added for the comparison only (kernels.rs:92-111).
 void assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, int metric,
                 const float* bias, uint32_t* part, float* dist, uint8_t* valid, float* all_out);
+// same, with a bias already padded to ceil(K/64)*64 floats and an optional device-side `active`
+// flag (active[0] == 0 -> the kernel returns immediately; used by the Lloyd loop)
+void assign_f32_ex(const float* x, uint64_t n, int d, const float* cent, int K, int metric,
+                   const float* bias, bool bias_padded, uint32_t* part, float* dist, uint8_t* valid,
+                   float* all_out, const uint8_t* active);
 // d < 16 path, batched over M sub-spaces; x row stride ldx, sub-space m reads columns [m*ds,(m+1)*ds).
 // codes != NULL -> u8 [n][M] out (PQ encode), else ids/dists/valid [M][n] (PQ training).
 bool small_d_supported(int ds);

@@ -223,7 +223,131 @@ void MemberSort::run(const uint32_t* ids, const uint8_t* valid, uint64_t n, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// the Lloyd loop
+// per-iteration scalar epilogue ON THE DEVICE: exactly the reference's bookkeeping
+//   compute_cluster_sizes (kmeans.rs:210-232), compute_balance_loss (:234-237), loss sum (:693),
+//   split_clusters (:174-207, our rng), tolerance test (:704), next iteration's bias (:341-345).
+// One block per problem; thread 0 runs the order-dependent scalar parts.
+// ------------------------------------------------------------------------------------------------
+struct LloydState {  // one per problem, device resident
+  double loss;        // previous iteration's loss (f64::MAX at start)
+  double last_loss;   // this iteration's loss
+  float adjusted;     // adjusted_balance_factor (f32::MAX at start)
+  float bf_cur;       // balance factor used by the membership step that just ran
+  uint64_t rng;       // splitmix64 state
+  uint32_t iters;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ uint64_t sm64_next(uint64_t& s) {
+  uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+epilogue_kernel(int K, int ds, uint64_t n, float bf_param, double tolerance, uint32_t it,
+                const uint32_t* __restrict__ counts, const double* __restrict__ losses,
+                const float* __restrict__ radius, const uint32_t* __restrict__ last_row,
+                uint64_t* __restrict__ cluster_sizes, float* __restrict__ bias, int bias_ld,
+                float* __restrict__ centroids, LloydState* __restrict__ states,
+                uint8_t* __restrict__ active) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (!active[b]) return;
+  __shared__ int s_i, s_j;
+  LloydState& st = states[b];
+  uint64_t* cs = cluster_sizes + (size_t)b * K;
+  const uint32_t* cnt = counts + (size_t)b * K;
+  const double* ls = losses + (size_t)b * K;
+  float* cb = centroids + (size_t)b * K * ds;
+  if (tid == 0) {
+    uint64_t max_size = 0;
+    int max_id = 0;
+    uint32_t best_last = 0xffffffffu;
+    for (int k = 0; k < K; ++k) {
+      const uint32_t c = cnt[k];
+      cs[k] = c;
+      const uint32_t lr = last_row[(size_t)b * K + k];
+      if (c > max_size || (c == max_size && c > 0 && lr < best_last)) {
+        max_size = c;
+        max_id = k;
+        best_last = lr;
+      }
+    }
+    st.adjusted = __fdiv_rn(__fsub_rn(radius[(size_t)b * K + max_id],
+                                      __fdiv_rn((float)ls[max_id], (float)cs[max_id])),
+                            (float)n);
+    uint64_t size_sq = 0;
+    for (int k = 0; k < K; ++k) size_sq += cs[k] * cs[k];
+    const float balance_loss =
+        __fmul_rn(st.bf_cur, __fsub_rn((float)size_sq, __fdiv_rn((float)(n * n), (float)K)));
+    double sum = 0.0;
+    for (int k = 0; k < K; ++k) sum += ls[k];
+    st.last_loss = sum + (double)balance_loss;
+    st.iters = it;
+  }
+  // split_clusters: sequential over empty clusters, vector part by the whole block
+  int next = 0;
+  for (;;) {
+    if (tid == 0) {
+      int i = next;
+      while (i < K && cs[i] != 0) ++i;
+      s_i = i < K ? i : -1;
+      if (i < K) {
+        uint64_t j = 0;
+        for (uint64_t tries = 0;; ++tries) {
+          const float p = __fdiv_rn(__fsub_rn((float)cs[j], 1.0f), (float)(n - (uint64_t)K));
+          const float u = (float)(sm64_next(st.rng) >> 40) * (1.0f / 16777216.0f);
+          if (u < p) break;
+          j = (j + 1) % (uint64_t)K;
+          if (tries >= 64ull * K) {
+            j = 0;
+            for (int c = 1; c < K; ++c)
+              if (cs[c] > cs[j]) j = c;
+            break;
+          }
+        }
+        cs[i] = cs[j] / 2;
+        cs[j] -= cs[i];
+        s_j = (int)j;
+      }
+    }
+    __syncthreads();
+    const int i = s_i, j = s_j;
+    if (i < 0) break;
+    const float eps = 1.0f / 1024.0f;
+    for (int t = tid; t < ds; t += blockDim.x) {
+      const float cj = cb[(size_t)j * ds + t];
+      if ((t & 1) == 0) {
+        cb[(size_t)i * ds + t] = __fmul_rn(cj, 1.0f + eps);
+        cb[(size_t)j * ds + t] = __fmul_rn(cj, 1.0f - eps);
+      } else {
+        cb[(size_t)i * ds + t] = __fmul_rn(cj, 1.0f - eps);
+        cb[(size_t)j * ds + t] = __fmul_rn(cj, 1.0f + eps);
+      }
+    }
+    next = i + 1;
+    __syncthreads();
+  }
+  // convergence (kmeans.rs:704) and the next iteration's balance factor / bias
+  __shared__ float s_bf;
+  if (tid == 0) {
+    if (fabs(st.loss - st.last_loss) < tolerance * st.last_loss) {
+      active[b] = 0;
+    } else {
+      st.loss = st.last_loss;
+    }
+    st.bf_cur = fminf(st.adjusted, bf_param);  // f32::min: the non-NaN operand
+    s_bf = st.bf_cur;
+  }
+  __syncthreads();
+  if (bias)
+    for (int k = tid; k < K; k += blockDim.x)
+      bias[(size_t)b * bias_ld + k] = __fmul_rn(s_bf, (float)cs[k]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the Lloyd loop: no host round trip per iteration; the host only polls the `active` flags
 // ------------------------------------------------------------------------------------------------
 void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, int metric,
                  float balance_factor_param, int max_iters, double tolerance, uint64_t seed,
@@ -235,10 +359,23 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
   const uint64_t n = n_in >= (uint64_t)K * 512 ? (uint64_t)K * 512 : n_in;
   LB2_REQUIRE(n < 0xffffffffull, "training sample too large");
   const size_t BK = (size_t)B * K;
+  const bool small = B > 1;
+  if (small && !small_d_supported(ds))
+    fail(LB2_UNSUPPORTED, "PQ sub-vector width %d is not supported by the device trainer yet", ds);
 
   // ---- init (kmeans.rs:149-170; our rng): k distinct rows by a partial Fisher-Yates ------------
+  std::vector<LloydState> h_states(B);
+  for (int b = 0; b < B; ++b) {
+    h_states[b].loss = std::numeric_limits<double>::max();
+    h_states[b].last_loss = 0.0;
+    h_states[b].adjusted = std::numeric_limits<float>::max();
+    h_states[b].bf_cur = std::fmin(std::numeric_limits<float>::max(), balance_factor_param);
+    h_states[b].iters = 0;
+    h_states[b].pad = 0;
+  }
   if (init_dev) {
     if (init_dev != centroids) d2d(centroids, init_dev, BK * ds);
+    for (int b = 0; b < B; ++b) h_states[b].rng = seed + b;
   } else {
     std::vector<uint32_t> rows(BK), idx(n);
     for (int b = 0; b < B; ++b) {
@@ -249,6 +386,7 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
         std::swap(idx[i], idx[j]);
         rows[(size_t)b * K + i] = idx[i];
       }
+      h_states[b].rng = rng.s;  // split_clusters continues the same stream
     }
     DevBuf<uint32_t> rows_d(BK);
     h2d(rows_d.p, rows.data(), BK);
@@ -256,118 +394,61 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
                rows_d.p, centroids);
     sync_stream();  // rows (host vector) must outlive the copy
   }
-  // split_clusters continues the stream that chose the init rows in the single-problem oracle:
-  // oracle: one SplitMix64(seed) for init AND splits.  Mirror that per problem.
-  std::vector<SplitMix64> rngs;
-  for (int b = 0; b < B; ++b) {
-    SplitMix64 r(seed + b);
-    if (!init_dev)
-      for (int i = 0; i < K; ++i) r.next();
-    rngs.push_back(r);
-  }
 
+  const int Kp = (K + 63) / 64 * 64;
   DevBuf<uint32_t> ids((size_t)B * n), last_row(BK);
   DevBuf<float> dists((size_t)B * n), radius(BK), bias;
   DevBuf<uint8_t> valid((size_t)B * n), active_d(B);
   DevBuf<double> losses(BK);
-  MemberSort ms;
+  DevBuf<uint64_t> cluster_sizes(BK);
+  DevBuf<LloydState> states(B);
+  cluster_sizes.zero();
+  h2d(states.p, h_states.data(), B);
   std::vector<uint8_t> active(B, 1);
-  std::vector<uint64_t> cluster_sizes(BK, 0);
-  std::vector<float> adjusted(B, std::numeric_limits<float>::max());
-  std::vector<double> loss(B, std::numeric_limits<double>::max()), last_loss(B, 0.0);
-  std::vector<uint32_t> iters(B, 0);
-  std::vector<uint32_t> h_counts(BK), h_last(BK);
-  std::vector<float> h_radius(BK), h_bias(K);
-  std::vector<double> h_losses(BK);
-  if (B == 1) bias.alloc(K);
-  const bool small = B > 1;
-  if (small && !small_d_supported(ds))
-    fail(LB2_UNSUPPORTED, "PQ sub-vector width %d is not supported by the device trainer yet", ds);
+  h2d(active_d.p, active.data(), B);
+  if (!small) {
+    bias.alloc(Kp);
+    bias.zero();  // iteration 1: cluster sizes are all zero -> bias 0
+  }
+  MemberSort ms;
+  sync_stream();
 
   for (int it = 1; it <= max_iters; ++it) {
-    bool any = false;
-    for (int b = 0; b < B; ++b) any = any || active[b];
-    if (!any) break;
-    h2d(active_d.p, active.data(), B);
-    std::vector<float> bf(B);
-    for (int b = 0; b < B; ++b) bf[b] = std::fmin(adjusted[b], balance_factor_param);
     // ---- membership (kmeans.rs:317-369) --------------------------------------------------------
     if (!small) {
-      for (int k = 0; k < K; ++k) h_bias[k] = bf[0] * (float)cluster_sizes[k];
-      h2d(bias.p, h_bias.data(), K);
-      assign_f32(x, n, ds, centroids, K, metric, bias.p, ids.p, dists.p, valid.p, nullptr);
+      assign_f32_ex(x, n, ds, centroids, K, metric, bias.p, /*bias_padded=*/true, ids.p, dists.p,
+                    valid.p, nullptr, active_d.p);
     } else {
       small_d_assign_f32(x, n, ldx, B, ds, centroids, K, metric, nullptr, nullptr, nullptr, nullptr,
                          ids.p, dists.p, valid.p, active_d.p);
     }
-    // ---- member lists, stats, update -----------------------------------------------------------
+    // ---- member lists, stats, update, scalar epilogue ------------------------------------------
     ms.run(ids.p, valid.p, n, K, B, active_d.p);
     LB2_LAUNCH("kmeans_stats", stats_kernel, cdiv((uint64_t)BK * 32, 256), 256, 0, dists.p, n, K, B,
                ms.members.p, ms.offsets.p, losses.p, radius.p, last_row.p, active_d.p);
     LB2_LAUNCH("kmeans_update", update_kernel, cdiv(BK * ds, 128), 128, 0, x, ldx, ds, K, B, n,
                ms.members.p, ms.offsets.p, centroids, active_d.p, 1);
-    d2h(h_counts.data(), ms.counts.p, BK);
-    d2h(h_losses.data(), losses.p, BK);
-    d2h(h_radius.data(), radius.p, BK);
-    d2h(h_last.data(), last_row.p, BK);
-    sync_stream();
-    // ---- host epilogue: exactly the reference's scalar bookkeeping ------------------------------
-    for (int b = 0; b < B; ++b) {
-      if (!active[b]) continue;
-      iters[b] = it;
-      uint64_t* cs = &cluster_sizes[(size_t)b * K];
-      const uint32_t* cnt = &h_counts[(size_t)b * K];
-      // compute_cluster_sizes (kmeans.rs:210-232): the cluster that FIRST reaches the final
-      // maximum size = among the largest clusters the one whose last member comes first.
-      uint64_t max_size = 0;
-      int max_id = 0;
-      uint32_t best_last = 0xffffffffu;
-      for (int k = 0; k < K; ++k) {
-        cs[k] = cnt[k];
-        if (cnt[k] > max_size || (cnt[k] == max_size && cnt[k] > 0 && h_last[(size_t)b * K + k] < best_last)) {
-          max_size = cnt[k];
-          max_id = k;
-          best_last = h_last[(size_t)b * K + k];
-        }
-      }
-      const double* ls = &h_losses[(size_t)b * K];
-      adjusted[b] = (h_radius[(size_t)b * K + max_id] - (float)ls[max_id] / (float)cs[max_id]) / (float)n;
-      uint64_t size_sq = 0;
-      for (int k = 0; k < K; ++k) size_sq += cs[k] * cs[k];
-      const float balance_loss = bf[b] * ((float)size_sq - (float)(n * n) / (float)K);  // :234-237
-      double sum_losses = 0.0;
-      for (int k = 0; k < K; ++k) sum_losses += ls[k];
-      last_loss[b] = sum_losses + (double)balance_loss;
-      // split_clusters (kmeans.rs:174-207)
-      float* cb = centroids + (size_t)b * K * ds;
-      for (int i = 0; i < K; ++i) {
-        if (cs[i] != 0) continue;
-        uint64_t j = 0;
-        for (uint64_t tries = 0;; ++tries) {
-          const float p = ((float)cs[j] - 1.0f) / (float)(n - K);
-          if (rngs[b].next_f32() < p) break;
-          j = (j + 1) % K;
-          if (tries >= 64ull * K) {
-            j = 0;
-            for (int c = 1; c < K; ++c)
-              if (cs[c] > cs[j]) j = c;
-            break;
-          }
-        }
-        cs[i] = cs[j] / 2;
-        cs[j] -= cs[i];
-        LB2_LAUNCH("kmeans_split", split_kernel, 1, 128, 0, cb, i, (int)j, ds);
-      }
-      if (std::fabs(loss[b] - last_loss[b]) < tolerance * last_loss[b]) {  // kmeans.rs:704
-        active[b] = 0;
-        continue;
-      }
-      loss[b] = last_loss[b];
+    LB2_LAUNCH("kmeans_epilogue", epilogue_kernel, B, 256, 0, K, ds, n, balance_factor_param,
+               tolerance, (uint32_t)it, ms.counts.p, losses.p, radius.p, last_row.p,
+               cluster_sizes.p, small ? nullptr : bias.p, Kp, centroids, states.p, active_d.p);
+    if ((it & 3) == 0 || it == max_iters) {  // poll convergence every 4 iterations
+      d2h(active.data(), active_d.p, B);
+      sync_stream();
+      bool any = false;
+      for (int b = 0; b < B; ++b) any = any || active[b];
+      if (!any) break;
     }
   }
+  d2h(h_states.data(), states.p, B);
   sync_stream();
-  if (loss_out) *loss_out = last_loss;
-  if (iters_out) *iters_out = iters;
+  if (loss_out) {
+    loss_out->resize(B);
+    for (int b = 0; b < B; ++b) (*loss_out)[b] = h_states[b].last_loss;
+  }
+  if (iters_out) {
+    iters_out->resize(B);
+    for (int b = 0; b < B; ++b) (*iters_out)[b] = h_states[b].iters;
+  }
 }
 
 }  // namespace lb2
