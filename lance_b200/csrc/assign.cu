@@ -14,6 +14,7 @@
 #include "assign.cuh"
 #include "common.cuh"
 #include "exact.cuh"
+#include "tc_assign.cuh"
 
 namespace lb2 {
 
@@ -36,19 +37,27 @@ __global__ void __launch_bounds__(256)
 assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __restrict__ cT,
                    int K, int Kp, const float* __restrict__ bias, uint32_t* __restrict__ part,
                    float* __restrict__ dist, uint8_t* __restrict__ valid,
-                   float* __restrict__ all_out, const uint8_t* __restrict__ active) {
+                   float* __restrict__ all_out, const uint8_t* __restrict__ active,
+                   const uint32_t* __restrict__ row_list, const uint32_t* __restrict__ row_count) {
   if (active && !active[0]) return;
+  // optional indirection: process only rows row_list[0 .. *row_count) (the tensor-core filter's
+  // ambiguous rows); outputs are written at the ORIGINAL row positions
+  if (row_list) n = *row_count;
   extern __shared__ float smem[];
   const int ld = d + 1;
   float* xs = smem;            // [64][d+1]
   float* cs = smem + 64 * ld;  // [d][64]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const uint64_t row0 = (uint64_t)blockIdx.x * 64;
+  if (row0 >= n) return;
 
   for (int idx = tid; idx < 16 * d; idx += 256) {  // 64*d/4 float4
     int r = (idx * 4) / d, e = (idx * 4) % d;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row0 + r < n) v = *reinterpret_cast<const float4*>(x + (row0 + r) * d + e);
+    if (row0 + r < n) {
+      const uint64_t src = row_list ? row_list[row0 + r] : row0 + r;
+      v = *reinterpret_cast<const float4*>(x + src * d + e);
+    }
     float* dst = xs + r * ld + e;
     dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
   }
@@ -133,8 +142,9 @@ assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* 
         best_key[i] = ok; best_val[i] = ov; best_idx[i] = oi;
       }
     }
-    const uint64_t r = row0 + ty * 4 + i;
-    if (tx == 0 && r < n) {
+    const uint64_t rr = row0 + ty * 4 + i;
+    if (tx == 0 && rr < n) {
+      const uint64_t r = row_list ? row_list[rr] : rr;
       const bool ok = best_idx[i] != 0xffffffffu;
       part[r] = ok ? best_idx[i] : 0u;
       if (dist) dist[r] = ok ? best_val[i] : __int_as_float(0x7fc00000);
@@ -355,11 +365,11 @@ static void assign_dispatch(const float* x, uint64_t n, int d, const float* cent
     if (all_out) {
       set_smem(assign_tile_kernel<METRIC, true>, smem);
       LB2_LAUNCH("assign_exact", (assign_tile_kernel<METRIC, true>), grid, 256, smem, x, n, d,
-                 cT.get(), K, Kp, bp, part, dist, valid, all_out, active);
+                 cT.get(), K, Kp, bp, part, dist, valid, all_out, active, nullptr, nullptr);
     } else {
       set_smem(assign_tile_kernel<METRIC, false>, smem);
       LB2_LAUNCH("assign_exact", (assign_tile_kernel<METRIC, false>), grid, 256, smem, x, n, d,
-                 cT.get(), K, Kp, bp, part, dist, valid, all_out, active);
+                 cT.get(), K, Kp, bp, part, dist, valid, all_out, active, nullptr, nullptr);
     }
     return;
   }
@@ -377,9 +387,39 @@ static void assign_dispatch(const float* x, uint64_t n, int d, const float* cent
   }
 }
 
+// exact tile kernel over a device-side row list (count read on the device: no host sync)
+void assign_rows_f32(const float* x, uint64_t n_max, int d, const float* cent, int K, int metric,
+                     const float* bias_padded, const uint32_t* row_list, const uint32_t* row_count,
+                     uint32_t* part, float* dist, uint8_t* valid, const uint8_t* active) {
+  if (!(d % 16 == 0 && d <= 256) || metric != METRIC_L2)
+    fail(LB2_UNSUPPORTED, "assign_rows_f32: shape not supported");
+  const int Kp = (K + 63) / 64 * 64;
+  DevBuf<float> cT((size_t)d * Kp);
+  LB2_LAUNCH("transpose_centroids", transpose_pad_kernel, cdiv((uint64_t)d * Kp, 256), 256, 0, cent,
+             K, d, Kp, cT.get());
+  const size_t smem = sizeof(float) * (64 * (d + 1) + (size_t)d * 64);
+  set_smem(assign_tile_kernel<METRIC_L2, false>, smem);
+  LB2_LAUNCH("assign_exact_fallback", (assign_tile_kernel<METRIC_L2, false>), cdiv(n_max, 64), 256,
+             smem, x, n_max, d, cT.get(), K, Kp, bias_padded, part, dist, valid, nullptr, active,
+             row_list, row_count);
+}
+
 void assign_f32_ex(const float* x, uint64_t n, int d, const float* cent, int K, int metric,
                    const float* bias, bool bias_padded, uint32_t* part, float* dist, uint8_t* valid,
-                   float* all_out, const uint8_t* active) {
+                   float* all_out, const uint8_t* active, TcWorkspace* ws) {
+  if (!all_out && n >= 256 && tc_assign_supported(n, d, K, metric, x)) {
+    // tensor-core filter + exact re-rank: bit-identical outputs, ~10x less FP32 work
+    DevBuf<float> biasp;
+    const float* bp = bias;
+    if (bias && !bias_padded) {
+      biasp.alloc(256);
+      biasp.zero();
+      d2d(biasp.get(), bias, K);
+      bp = biasp.get();
+    }
+    tc_assign_f32(x, n, d, cent, K, bp, part, dist, valid, active, ws);
+    return;
+  }
   if (metric == METRIC_DOT)
     assign_dispatch<METRIC_DOT>(x, n, d, cent, K, bias, bias_padded, part, dist, valid, all_out, active);
   else
@@ -387,7 +427,7 @@ void assign_f32_ex(const float* x, uint64_t n, int d, const float* cent, int K, 
 }
 void assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, int metric,
                 const float* bias, uint32_t* part, float* dist, uint8_t* valid, float* all_out) {
-  assign_f32_ex(x, n, d, cent, K, metric, bias, false, part, dist, valid, all_out, nullptr);
+  assign_f32_ex(x, n, d, cent, K, metric, bias, false, part, dist, valid, all_out, nullptr, nullptr);
 }
 
 template <int DS, int METRIC>

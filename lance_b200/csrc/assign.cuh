@@ -8,9 +8,14 @@ void assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, int
                 const float* bias, uint32_t* part, float* dist, uint8_t* valid, float* all_out);
 // same, with a bias already padded to ceil(K/64)*64 floats and an optional device-side `active`
 // flag (active[0] == 0 -> the kernel returns immediately; used by the Lloyd loop)
+struct TcWorkspace;
 void assign_f32_ex(const float* x, uint64_t n, int d, const float* cent, int K, int metric,
                    const float* bias, bool bias_padded, uint32_t* part, float* dist, uint8_t* valid,
-                   float* all_out, const uint8_t* active);
+                   float* all_out, const uint8_t* active, TcWorkspace* ws);
+// exact tile kernel restricted to row_list[0 .. *row_count) (both on the device)
+void assign_rows_f32(const float* x, uint64_t n_max, int d, const float* cent, int K, int metric,
+                     const float* bias_padded, const uint32_t* row_list, const uint32_t* row_count,
+                     uint32_t* part, float* dist, uint8_t* valid, const uint8_t* active);
 // d < 16 path, batched over M sub-spaces; x row stride ldx, sub-space m reads columns [m*ds,(m+1)*ds).
 // codes != NULL -> u8 [n][M] out (PQ encode), else ids/dists/valid [M][n] (PQ training).
 bool small_d_supported(int ds);

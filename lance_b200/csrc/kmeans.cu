@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "exact.cuh"
 #include "kmeans.cuh"
+#include "tc_assign.cuh"
 
 namespace lb2 {
 
@@ -260,35 +261,74 @@ epilogue_kernel(int K, int ds, uint64_t n, float bf_param, double tolerance, uin
   const uint32_t* cnt = counts + (size_t)b * K;
   const double* ls = losses + (size_t)b * K;
   float* cb = centroids + (size_t)b * K * ds;
-  if (tid == 0) {
-    uint64_t max_size = 0;
-    int max_id = 0;
-    uint32_t best_last = 0xffffffffu;
-    for (int k = 0; k < K; ++k) {
+  // (1) order-independent parts in parallel: cluster sizes, sum of squares, and the
+  //     "first cluster to reach the final maximum" = max count, then smallest last member row
+  __shared__ unsigned long long s_red_a[256];  // packed (count << 32 | ~last_row) -> max
+  __shared__ unsigned long long s_red_sq[256];
+  __shared__ int s_red_id[256];
+  __shared__ double s_chunk[1024];
+  __shared__ int s_any_empty;
+  {
+    unsigned long long best = 0, sq = 0;
+    int best_id = 0;
+    bool have = false;
+    int empty = 0;
+    for (int k = tid; k < K; k += blockDim.x) {
       const uint32_t c = cnt[k];
       cs[k] = c;
-      const uint32_t lr = last_row[(size_t)b * K + k];
-      if (c > max_size || (c == max_size && c > 0 && lr < best_last)) {
-        max_size = c;
-        max_id = k;
-        best_last = lr;
-      }
+      sq += (unsigned long long)c * c;
+      empty |= (c == 0);
+      const uint32_t lr = c > 0 ? last_row[(size_t)b * K + k] : 0xffffffffu;
+      const unsigned long long key = ((unsigned long long)c << 32) | (uint32_t)(~lr);
+      // ties on (count, last_row) cannot happen for c > 0 (a row belongs to one cluster); for
+      // c == 0 everywhere the reference keeps id 0 -> prefer the lowest k on equal keys
+      if (!have || key > best) { best = key; best_id = k; have = true; }
     }
+    s_red_a[tid] = have ? best : 0ull;
+    s_red_id[tid] = have ? best_id : 0x7fffffff;
+    s_red_sq[tid] = sq;
+    const int any = __syncthreads_or(empty);
+    if (tid == 0) s_any_empty = any;
+    for (int off = 128; off >= 1; off >>= 1) {
+      if (tid < off) {
+        const unsigned long long o = s_red_a[tid + off];
+        const int oi = s_red_id[tid + off];
+        if (o > s_red_a[tid] || (o == s_red_a[tid] && oi < s_red_id[tid])) {
+          s_red_a[tid] = o;
+          s_red_id[tid] = oi;
+        }
+        s_red_sq[tid] += s_red_sq[tid + off];
+      }
+      __syncthreads();
+    }
+  }
+  // (2) the f64 loss sum is order dependent (kmeans.rs:693): staged through shared memory in
+  //     chunks, added sequentially by thread 0
+  double sum = 0.0;
+  for (int k0 = 0; k0 < K; k0 += 1024) {
+    for (int k = tid; k < 1024 && k0 + k < K; k += blockDim.x) s_chunk[k] = ls[k0 + k];
+    __syncthreads();
+    if (tid == 0) {
+      const int m = min(1024, K - k0);
+      for (int k = 0; k < m; ++k) sum += s_chunk[k];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int max_id = s_red_id[0] == 0x7fffffff ? 0 : s_red_id[0];
+    const uint64_t size_sq = s_red_sq[0];
     st.adjusted = __fdiv_rn(__fsub_rn(radius[(size_t)b * K + max_id],
                                       __fdiv_rn((float)ls[max_id], (float)cs[max_id])),
                             (float)n);
-    uint64_t size_sq = 0;
-    for (int k = 0; k < K; ++k) size_sq += cs[k] * cs[k];
     const float balance_loss =
         __fmul_rn(st.bf_cur, __fsub_rn((float)size_sq, __fdiv_rn((float)(n * n), (float)K)));
-    double sum = 0.0;
-    for (int k = 0; k < K; ++k) sum += ls[k];
     st.last_loss = sum + (double)balance_loss;
     st.iters = it;
   }
+  __syncthreads();
   // split_clusters: sequential over empty clusters, vector part by the whole block
   int next = 0;
-  for (;;) {
+  for (; s_any_empty;) {
     if (tid == 0) {
       int i = next;
       while (i < K && cs[i] != 0) ++i;
@@ -411,13 +451,14 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
     bias.zero();  // iteration 1: cluster sizes are all zero -> bias 0
   }
   MemberSort ms;
+  TcWorkspace tcws;
   sync_stream();
 
   for (int it = 1; it <= max_iters; ++it) {
     // ---- membership (kmeans.rs:317-369) --------------------------------------------------------
     if (!small) {
       assign_f32_ex(x, n, ds, centroids, K, metric, bias.p, /*bias_padded=*/true, ids.p, dists.p,
-                    valid.p, nullptr, active_d.p);
+                    valid.p, nullptr, active_d.p, &tcws);
     } else {
       small_d_assign_f32(x, n, ldx, B, ds, centroids, K, metric, nullptr, nullptr, nullptr, nullptr,
                          ids.p, dists.p, valid.p, active_d.p);

@@ -1,0 +1,446 @@
+// tc_assign.cu -- tensor-core FILTER for nearest-centroid assignment (sm_100a: tcgen05 + TMEM + TMA).
+//
+// Replaces the O(n*K*d) part of  compute_membership_and_dist  (lance-index/src/vector/kmeans.rs:317-369)
+// and  compute_partitions_with_dists (kmeans.rs:1275-1294)  WITHOUT changing a single output bit:
+//
+//   1. tc_filter_kernel: score(x, c) = x.c - (|c|^2 + bias_c)/2 for a 128-row x 256-centroid tile as a
+//      TF32 GEMM (tcgen05.mma kind::tf32, f32 operands straight from TMA-swizzled shared memory,
+//      f32 accumulators in TMEM, double buffered).  The epilogue (tcgen05.ld) keeps the top-3 scores
+//      of every row and classifies the row with a conservative error bound tau:
+//        flag 0: top1 - top2 > tau   -> top1 IS the reference's argmin (no other centroid can win)
+//        flag 1: top1 - top3 > tau   -> the winner is top1 or top2: decide with exact arithmetic
+//        flag 2: otherwise (or NaN)  -> the row goes through the exact kernel (assign.cu)
+//   2. rerank_kernel: for flag<=1 rows the reference-order f32 distance (exact.cuh) of the one or
+//      two candidates, the reference's strict-< / lowest-index rule, and the exact distance output.
+//   3. flag-2 rows are compacted and fed to assign_tile_kernel through a row-index list.
+//
+// Error bound: TF32 keeps 11 significant bits, so each operand carries a
+// relative error <= 2^-10 (truncation); |x.c - tf32(x).tf32(c)| <= 2^-9 * sum|x_i||c_i|
+// <= 2^-10 (|x|^2 + |c|^2).  Two scores are compared, index packing perturbs by 2^-15 |score|, the
+// f32 accumulation by far less: tau = 3 * 2^-10 * (|x|^2 + max_c |c|^2) covers 2x the bound with
+// 20% to spare.  Whatever tau is, results stay exact as long as the bound holds; a larger tau only
+// sends more rows to the exact paths.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "assign.cuh"
+#include "common.cuh"
+#include "exact.cuh"
+#include "tc_assign.cuh"
+
+namespace lb2 {
+
+namespace tc {
+
+constexpr int TM = 128;                  // rows per tile (UMMA M)
+constexpr int TN = 256;                  // centroids per tile (UMMA N)
+constexpr int KC = 32;                   // f32 per 128-byte swizzle row
+constexpr int A_STAGE_BYTES = TM * 128;  // 16 KB
+constexpr int B_CHUNK_BYTES = TN * 128;  // 32 KB
+constexpr int MAX_STAGES = 5;
+constexpr int NUM_THREADS = 256;         // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp:SmemDescriptor):
+// start>>4 [0,14), LBO>>4 [16,30) (unused for swizzled K-major, 1), SBO>>4 [32,46) = 1024 B (8 rows),
+// version=1 [46,48), layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor, kind::tf32 (InstrDescriptor): c_format F32=1 [4,6), a/b format TF32=2 [7,10)/[10,13),
+// K-major A and B (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+struct SmemLayout {
+  // offsets from the 1024-aligned base
+  uint32_t b_off, a_off, cnh_off, bar_off, tmem_ptr_off, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int nkc, int stages) {
+  SmemLayout L;
+  L.b_off = 0;
+  L.a_off = nkc * B_CHUNK_BYTES;
+  L.cnh_off = L.a_off + stages * A_STAGE_BYTES;
+  L.bar_off = L.cnh_off + TN * 4;
+  L.tmem_ptr_off = L.bar_off + (2 * MAX_STAGES + 1 + 4) * 8;
+  L.total = L.tmem_ptr_off + 16;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the filter kernel (persistent, one CTA per SM)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
+                 uint64_t n, int nkc, int stages, const float* __restrict__ cnh_g,
+                 const float* __restrict__ row_norm2, const float* __restrict__ cmax2_ptr,
+                 uint32_t* __restrict__ res, const uint8_t* __restrict__ active) {
+  if (active && !active[0]) return;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const SmemLayout L = smem_layout(nkc, stages);
+  float* cnh = reinterpret_cast<float*>(smem + L.cnh_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L.tmem_ptr_off);
+  const uint32_t sb = smem_u32(smem);
+  auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
+  auto empty_bar = [&](int s) { return smem_u32(&bars[MAX_STAGES + s]); };
+  const uint32_t b_full = smem_u32(&bars[2 * MAX_STAGES]);
+  auto tfull_bar = [&](int b) { return smem_u32(&bars[2 * MAX_STAGES + 1 + b]); };
+  auto tempty_bar = [&](int b) { return smem_u32(&bars[2 * MAX_STAGES + 3 + b]); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t num_tiles = (n + TM - 1) / TM;
+
+  for (int i = threadIdx.x; i < TN; i += NUM_THREADS) cnh[i] = cnh_g[i];
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(b_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr_smem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(b_full, (uint32_t)nkc * B_CHUNK_BYTES);
+      for (int kc = 0; kc < nkc; ++kc)
+        tma_load_2d(sb + L.b_off + kc * B_CHUNK_BYTES, &map_c, b_full, kc * KC, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < nkc; ++kc) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), A_STAGE_BYTES);
+          tma_load_2d(sb + L.a_off + s * A_STAGE_BYTES, &map_x, full_bar(s), kc * KC, (int)(tile * TM));
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      mbar_wait(b_full, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t it = 0;
+      for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + buf * TN;
+        for (int kc = 0; kc < nkc; ++kc) {
+          mbar_wait(full_bar(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_addr = sb + L.a_off + s * A_STAGE_BYTES;
+          const uint32_t b_addr = sb + L.b_off + kc * B_CHUNK_BYTES;
+#pragma unroll
+          for (int k8 = 0; k8 < 4; ++k8)  // 4 x (K = 8 tf32 = 32 bytes) per 128-byte swizzle row
+            umma_tf32(d_tmem, make_desc(a_addr + k8 * 32), make_desc(b_addr + k8 * 32),
+                      (kc | k8) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(s));  // frees the A stage once these MMAs have read it
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(tfull_bar(buf));  // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers, top-3 per row =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const float cmax2 = *cmax2_ptr;
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1;
+      mbar_wait(tfull_bar(buf), (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * TN;
+      float m1 = __int_as_float(0xff800000), m2 = m1, m3 = m1;
+#pragma unroll 1
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float f = __uint_as_float(v[j]) + cnh[c0 + j];
+          const float g = __uint_as_float((__float_as_uint(f) & 0xFFFFFF00u) | (uint32_t)(c0 + j));
+          const float t1 = fminf(m1, g);
+          m1 = fmaxf(m1, g);
+          const float t2 = fminf(m2, t1);
+          m2 = fmaxf(m2, t1);
+          m3 = fmaxf(m3, t2);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+      const uint64_t row = tile * TM + q * 32 + lane;
+      if (row < n) {
+        const float tau = 0.0029296875f * (row_norm2[row] + cmax2);  // 3 * 2^-10
+        uint32_t flag = 2;
+        if (m1 - m2 > tau) flag = 0;
+        else if (m1 - m3 > tau) flag = 1;
+        res[row] = (__float_as_uint(m1) & 0xFFu) | ((__float_as_uint(m2) & 0xFFu) << 12) | (flag << 30);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// preparation kernels
+// ------------------------------------------------------------------------------------------------
+// padded copy of the centroids [TN][d] (zero rows past K), cnh[k] = -(|c_k|^2 + bias_k)/2 (-3e38 pads),
+// cmax2 = max_k |c_k|^2 (plain f32; any rounding is inside the error budget)
+__global__ void prep_centroids_kernel(const float* __restrict__ c, int K, int d,
+                                      const float* __restrict__ bias, float* __restrict__ cpad,
+                                      float* __restrict__ cnh, float* __restrict__ cmax2) {
+  __shared__ float s_max[TN];
+  const int k = threadIdx.x;  // blockDim = TN
+  float n2 = 0.0f;
+  for (int e = 0; e < d; ++e) {
+    const float v = k < K ? c[(size_t)k * d + e] : 0.0f;
+    cpad[(size_t)k * d + e] = v;
+    n2 += v * v;
+  }
+  // pads: a huge negative FINITE score (an inf would turn into NaN when the index is packed in)
+  cnh[k] = k < K ? -0.5f * (n2 + (bias ? bias[k] : 0.0f)) : -3.0e38f;
+  s_max[k] = k < K ? n2 : 0.0f;
+  __syncthreads();
+  if (k == 0) {
+    float m = 0.0f;
+    for (int i = 0; i < TN; ++i) m = fmaxf(m, s_max[i]);
+    *cmax2 = m;
+  }
+}
+
+// |x|^2 per row, 16 lanes per row (plain f32, inside the error budget; NaN/Inf propagate -> flag 2)
+__global__ void row_norm_kernel(const float* __restrict__ x, uint64_t n, int d, float* __restrict__ out) {
+  const uint64_t hw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int l = threadIdx.x & 15;
+  if (hw >= n) return;  // whole half-warp exits together
+  const float* v = x + hw * d;
+  float s = 0.0f;
+  for (int e = l * 4; e < d; e += 64) {
+    const float4 f = *reinterpret_cast<const float4*>(v + e);
+    s += f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
+  }
+  const unsigned mask = 0xffffu << (16 * ((threadIdx.x >> 4) & 1));
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) s += __shfl_xor_sync(mask, s, off, 16);
+  if (l == 0) out[hw] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact re-rank of the one or two surviving candidates (16 lanes per row; lane l owns the
+// reference's lane-accumulator l, l2.rs:82-88), flag-2 rows are appended to the fallback list
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rerank_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __restrict__ cent,
+              const float* __restrict__ bias, const uint32_t* __restrict__ res, int need_dist,
+              uint32_t* __restrict__ part, float* __restrict__ dist, uint8_t* __restrict__ valid,
+              uint32_t* __restrict__ fb_rows, uint32_t* __restrict__ fb_count,
+              const uint8_t* __restrict__ active) {
+  if (active && !active[0]) return;
+  const uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int l = threadIdx.x & 15;
+  if (row >= n) return;
+  const unsigned mask = 0xffffu << (16 * ((threadIdx.x >> 4) & 1));
+  const uint32_t r = res[row];
+  const uint32_t flag = r >> 30;
+  const uint32_t i1 = r & 0xFFFu, i2 = (r >> 12) & 0xFFFu;
+  if (flag == 2) {
+    if (l == 0) fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)row;
+    return;
+  }
+  if (flag == 0 && !need_dist) {
+    if (l == 0) {
+      part[row] = i1;
+      if (valid) valid[row] = 1;
+    }
+    return;
+  }
+  const float* xv = x + row * d;
+  const int ncand = flag == 0 ? 1 : 2;
+  float best_key = __int_as_float(0x7f800000), best_val = best_key;
+  uint32_t best_idx = 0xffffffffu;
+  for (int c = 0; c < ncand; ++c) {
+    const uint32_t ci = c == 0 ? i1 : i2;
+    const float* cv = cent + (size_t)ci * d;
+    float acc = 0.0f;
+    for (int e = l; e < d; e += 16) acc = f_add(acc, sq_diff(xv[e], cv[e]));
+    float t = 0.0f;
+#pragma unroll
+    for (int qq = 0; qq < 16; ++qq) t = f_add(t, __shfl_sync(mask, acc, qq, 16));
+    const float v = f_add(0.0f, t);
+    const float key = bias ? f_add(v, bias[ci]) : v;
+    if (key < best_key || (key == best_key && ci < best_idx)) {
+      best_key = key; best_val = v; best_idx = ci;
+    }
+  }
+  if (l == 0) {
+    const bool ok = best_idx != 0xffffffffu;
+    part[row] = ok ? best_idx : 0u;
+    if (dist) dist[row] = ok ? best_val : __int_as_float(0x7fc00000);
+    if (valid) valid[row] = ok ? 1 : 0;
+  }
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult qres;
+    void* p = nullptr;
+    LB2_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (!p || qres != cudaDriverEntryPointSuccess) fail(LB2_CUDA_ERROR, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+static CUtensorMap make_map_2d(const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)tc::KC, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides,
+                               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(LB2_CUDA_ERROR, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return m;
+}
+
+bool tc_assign_supported(uint64_t n, int d, int K, int metric, const float* x) {
+  if (getenv("LB2_DISABLE_TC")) return false;
+  return metric == METRIC_L2 && d % tc::KC == 0 && d >= 32 && d <= 128 && K >= 2 && K <= tc::TN &&
+         n >= 1 && n < (1ull << 31) && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+}
+
+void tc_assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, const float* bias,
+                   uint32_t* part, float* dist, uint8_t* valid, const uint8_t* active,
+                   TcWorkspace* ws) {
+  using namespace tc;
+  const int nkc = d / KC;
+  int stages = MAX_STAGES;
+  SmemLayout L = smem_layout(nkc, stages);
+  while (stages > 2 && L.total + 1024 > ctx().smem_optin) L = smem_layout(nkc, --stages);
+  if (L.total + 1024 > ctx().smem_optin) fail(LB2_UNSUPPORTED, "tc_assign: shared memory");
+  TcWorkspace local;
+  if (!ws) ws = &local;
+  if (ws->cpad.n < (size_t)TN * d) ws->cpad.alloc((size_t)TN * d);
+  if (ws->cnh.n < TN + 1) ws->cnh.alloc(TN + 1);
+  if (ws->row_norm2.n < n || ws->norm_src != x || ws->norm_n != n) {
+    if (ws->row_norm2.n < n) ws->row_norm2.alloc(n);
+    LB2_LAUNCH("tc_row_norms", row_norm_kernel, cdiv(n * 16, 256), 256, 0, x, n, d, ws->row_norm2.p);
+    ws->norm_src = x;
+    ws->norm_n = n;
+  }
+  if (ws->res.n < n) ws->res.alloc(n);
+  if (ws->fb_rows.n < n) ws->fb_rows.alloc(n);
+  if (ws->fb_count.n < 1) ws->fb_count.alloc(1);
+  LB2_LAUNCH("tc_prep_centroids", prep_centroids_kernel, 1, TN, 0, cent, K, d, bias, ws->cpad.p,
+             ws->cnh.p, ws->cnh.p + TN);
+  LB2_CUDA(cudaMemsetAsync(ws->fb_count.p, 0, sizeof(uint32_t), ctx().stream));
+  const CUtensorMap map_x = make_map_2d(x, n, d, TM);
+  const CUtensorMap map_c = make_map_2d(ws->cpad.p, TN, d, TN);
+  const uint64_t tiles = (n + TM - 1) / TM;
+  const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)ctx().num_sms);
+  const size_t smem = L.total + 1024;
+  set_smem(tc_filter_kernel, smem);
+  LB2_LAUNCH("tc_filter", tc_filter_kernel, grid, NUM_THREADS, smem, map_x, map_c, n, nkc, stages,
+             ws->cnh.p, ws->row_norm2.p, ws->cnh.p + TN, ws->res.p, active);
+  LB2_LAUNCH("tc_rerank", rerank_kernel, cdiv(n * 16, 256), 256, 0, x, n, d, cent, bias, ws->res.p,
+             dist != nullptr ? 1 : 0, part, dist, valid, ws->fb_rows.p, ws->fb_count.p, active);
+  if (getenv("LB2_TC_STATS")) {  // diagnostics: how selective was the filter?
+    std::vector<uint32_t> h(n);
+    d2h(h.data(), ws->res.p, n);
+    sync_stream();
+    uint64_t f[4] = {0, 0, 0, 0};
+    for (uint64_t i = 0; i < n; ++i) f[h[i] >> 30]++;
+    fprintf(stderr, "[lb2 tc_filter] n=%llu K=%d d=%d: unique %.2f%%, two-candidate %.2f%%, exact-fallback %.2f%%\n",
+            (unsigned long long)n, K, d, 100.0 * f[0] / n, 100.0 * f[1] / n, 100.0 * f[2] / n);
+  }
+  // flag-2 rows: exact kernel over the compacted row list (grid sized for the worst case; CTAs
+  // beyond the device-side count exit immediately -> no host synchronisation)
+  assign_rows_f32(x, n, d, cent, K, METRIC_L2, bias, ws->fb_rows.p, ws->fb_count.p, part, dist, valid, active);
+}
+
+}  // namespace lb2

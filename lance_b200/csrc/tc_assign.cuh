@@ -1,0 +1,18 @@
+// tc_assign.cuh -- internal interface of the tcgen05 filter path (tc_assign.cu)
+#pragma once
+#include <stdint.h>
+
+#include "common.cuh"
+namespace lb2 {
+struct TcWorkspace {
+  DevBuf<float> cpad, cnh, row_norm2;
+  DevBuf<uint32_t> res, fb_rows, fb_count;
+  const float* norm_src = nullptr;  // row norms are cached per (pointer, n): valid inside one call
+  uint64_t norm_n = 0;
+};
+bool tc_assign_supported(uint64_t n, int d, int K, int metric, const float* x);
+// same contract as assign_f32_ex (bias must be padded to 256 floats or NULL); bit-identical outputs
+void tc_assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, const float* bias,
+                   uint32_t* part, float* dist, uint8_t* valid, const uint8_t* active,
+                   TcWorkspace* ws);
+}  // namespace lb2

@@ -298,3 +298,60 @@ def test_unsupported_is_surfaced_not_masked():
     assert e.value.status == 2
     with pytest.raises(lb.LanceB200Error):
         lb.train_kmeans(np.zeros((10, 8), np.float32), 8, 20)
+
+
+# ---- tensor-core filter path (tcgen05) must be bit-identical to the exact path -----------------
+def _both_paths(fn):
+    import os
+    os.environ.pop("LB2_DISABLE_TC", None)
+    a = fn()
+    os.environ["LB2_DISABLE_TC"] = "1"
+    try:
+        b = fn()
+    finally:
+        os.environ.pop("LB2_DISABLE_TC", None)
+    return a, b
+
+
+@pytest.mark.parametrize("n,d,k", [(256, 128, 256), (1000, 128, 256), (5000, 128, 100), (4097, 64, 256),
+                                   (3000, 96, 33), (129, 32, 2), (20000, 128, 255)])
+def test_tc_filter_equals_exact_path(n, d, k):
+    rng = np.random.default_rng(n * 7 + d + k)
+    cent = (rng.standard_normal((k, d)) * 3).astype(np.float32)
+    data = (cent[rng.integers(0, k, n)] + rng.standard_normal((n, d))).astype(np.float32)
+    (p1, d1, v1), (p2, d2, v2) = _both_paths(lambda: lb.compute_partitions(cent, data))
+    assert np.array_equal(p1, p2) and np.array_equal(d1, d2) and np.array_equal(v1, v2)
+    po, do, vo = ob.compute_membership(cent, data, nthreads=NT)
+    assert np.array_equal(p1, po) and np.array_equal(d1, do)
+
+
+def test_tc_filter_adversarial_near_ties():
+    # centroids in tight groups (differences far below the TF32 resolution), exact duplicates, and
+    # rows exactly half-way between two centroids: every row must still match the exact path
+    rng = np.random.default_rng(99)
+    d, k, n = 128, 256, 6000
+    base = (rng.standard_normal((32, d)) * 50).astype(np.float32)
+    cent = np.repeat(base, 8, axis=0)
+    cent += (rng.standard_normal((k, d)) * 1e-3).astype(np.float32)
+    cent[17] = cent[16]          # exact duplicate
+    cent[40:44] = cent[40]       # 4 identical -> top-3 all tied -> exact fallback
+    data = (cent[rng.integers(0, k, n)] + rng.standard_normal((n, d)) * 0.5).astype(np.float32)
+    data[:100] = ((cent[0] + cent[9]) * 0.5).astype(np.float32)
+    data[100] = np.nan
+    data[101, 5] = np.inf
+    (p1, d1, v1), (p2, d2, v2) = _both_paths(lambda: lb.compute_partitions(cent, data))
+    assert np.array_equal(v1, v2) and not v1[100] and not v1[101]
+    assert np.array_equal(p1[v1], p2[v2]) and np.array_equal(d1[v1], d2[v2])
+    po, do, vo = ob.compute_membership(cent, data, nthreads=NT)
+    assert np.array_equal(p1[v1], po[vo]) and np.array_equal(d1[v1], do[vo])
+
+
+def test_tc_filter_sift_shaped_and_training():
+    data = synth.sift_like(70000, 128, seed=31)
+    init = data[np.random.default_rng(2).choice(70000, 256, replace=False)].copy()
+    (k1, k2) = _both_paths(lambda: lb.train_kmeans(data, 128, 256, max_iters=12, centroids=init, balance_factor=1.0))
+    assert k1.iters == k2.iters and k1.loss == k2.loss and np.array_equal(k1.centroids, k2.centroids)
+    nn = 65536
+    co, loss_o, it_o = ob.kmeans_train(data[:nn], 256, max_iters=12, init_centroids=init,
+                                       balance_factor=float(np.float32(1.0) / np.float32(nn)), nthreads=NT)
+    assert k1.iters == it_o and np.array_equal(k1.centroids, co) and k1.loss == loss_o
