@@ -9,6 +9,7 @@
 #include "exact.cuh"
 #include "kmeans.cuh"
 #include "search.cuh"
+#include "tc_pq.cuh"
 
 namespace lb2 {
 
@@ -497,8 +498,7 @@ lb2_status lb2_pq_encode(const void* codebook, uint32_t num_sub_vectors, uint32_
     }
   }
   OutArg<uint8_t> o(codes_out, (size_t)n * M);
-  small_d_assign_f32(x.get(), n, d, M, ds, cb.get(), 256, m, c.get(), p.get(), nullptr, o.get(),
-                     nullptr, nullptr, nullptr, nullptr);
+  pq_encode_dev(x.get(), n, d, M, ds, cb.get(), m, c.get(), p.get(), nullptr, o.get());
   o.commit();
   sync_stream();
   LB2_API_END
@@ -577,9 +577,8 @@ lb2_status lb2_ivfpq_transform(const void* centroids, uint32_t k, const void* co
   }
   const int am = m == METRIC_DOT ? METRIC_DOT : METRIC_L2;
   assign_f32(xp, n, d, c.get(), k, am, nullptr, p.get(), nullptr, vp, nullptr);
-  small_d_assign_f32(xp, n, d, M, ds, cb.get(), 256, am, am == METRIC_DOT ? nullptr : c.get(),
-                     am == METRIC_DOT ? nullptr : p.get(), vp, co.get(), nullptr, nullptr, nullptr,
-                     nullptr);
+  pq_encode_dev(xp, n, d, M, ds, cb.get(), am, am == METRIC_DOT ? nullptr : c.get(),
+                am == METRIC_DOT ? nullptr : p.get(), vp, co.get());
   p.commit(); co.commit(); v.commit();
   sync_stream();
   LB2_API_END
@@ -766,10 +765,8 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
     DevBuf<uint8_t> codes((size_t)n * M), valid(n);
     TagScope* tg3 = new TagScope("transform");
     assign_f32(x, n, d, ix->centroids.p, K, am, nullptr, part.p, nullptr, valid.p, nullptr);
-    small_d_assign_f32(x, n, d, M, ds, ix->codebook.p, 256, am,
-                       am == METRIC_DOT ? nullptr : ix->centroids.p,
-                       am == METRIC_DOT ? nullptr : part.p, valid.p, codes.p, nullptr, nullptr,
-                       nullptr, nullptr);
+    pq_encode_dev(x, n, d, M, ds, ix->codebook.p, am, am == METRIC_DOT ? nullptr : ix->centroids.p,
+                  am == METRIC_DOT ? nullptr : part.p, valid.p, codes.p);
     delete tg3;
     LB2_CUDA(cudaEventRecord(ev[3], c.stream));
     TagScope tg4("group");

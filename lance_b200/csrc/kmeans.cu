@@ -22,6 +22,7 @@
 #include "exact.cuh"
 #include "kmeans.cuh"
 #include "tc_assign.cuh"
+#include "tc_pq.cuh"
 
 namespace lb2 {
 
@@ -452,6 +453,13 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
   }
   MemberSort ms;
   TcWorkspace tcws;
+  TcPqWorkspace pqws;
+  DevBuf<float> rn2;
+  const bool pq_tc = small && ldx == B * ds && tc_pq_supported(n, ldx, B, ds, K, metric, x);
+  if (pq_tc) {  // per-sub-space norms of the (fixed) training rows, once
+    rn2.alloc(n * B);
+    tc_pq_residual_norms(x, nullptr, nullptr, n, B, nullptr, rn2.p);
+  }
   sync_stream();
 
   for (int it = 1; it <= max_iters; ++it) {
@@ -459,6 +467,9 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
     if (!small) {
       assign_f32_ex(x, n, ds, centroids, K, metric, bias.p, /*bias_padded=*/true, ids.p, dists.p,
                     valid.p, nullptr, active_d.p, &tcws);
+    } else if (pq_tc) {
+      tc_pq_assign(x, rn2.p, n, ldx, B, centroids, nullptr, nullptr, ids.p, dists.p, valid.p,
+                   active_d.p, &pqws);
     } else {
       small_d_assign_f32(x, n, ldx, B, ds, centroids, K, metric, nullptr, nullptr, nullptr, nullptr,
                          ids.p, dists.p, valid.p, active_d.p);

@@ -1,0 +1,441 @@
+// tc_pq.cu -- tensor-core FILTER + in-epilogue exact re-rank for PQ code assignment (8-wide
+// sub-vectors, 256 codewords), sm_100a: tcgen05 kind::tf32 + TMEM + TMA.
+//
+// Replaces the inner loop of  ProductQuantizer::transform_impl  (lance-index/src/vector/pq.rs:116-191:
+// per row, per sub-vector, argmin over the codebook via compute_partition kmeans.rs:1350-1369) and of
+// the PQ training membership step (pq/builder.rs:89-157 -> kmeans.rs:317-369), bit for bit:
+//
+//   * B operand: the codebook as one K-major matrix Bm[c][m*8+t] = cb[m][c][t] (256 x d f32), resident
+//     in shared memory for the whole kernel (TMA, SWIZZLE_128B).
+//   * A operand: 128-row tiles of the (residual) vectors, TMA-streamed in 32-float chunks (= 4 sub-spaces).
+//   * one tcgen05.mma (M128 N256 K8, tf32) per (tile, sub-space) into a double-buffered TMEM
+//     accumulator; the epilogue keeps the top-3 of  r.c - |c|^2/2  per row and classifies the row
+//     against tau = 3*2^-10 (|r_m|^2 + max|c_m|^2) exactly like tc_assign.cu;
+//   * flag 0/1 rows are decided IN THE EPILOGUE with reference-order f32 arithmetic on the operands
+//     that are still in shared memory (sequential 8-term sum, l2.rs:69-79; strict-< / lowest index);
+//   * flag 2 (row, sub-space) pairs are appended to a list and finished by pq_fallback_kernel
+//     (half-warp per pair, exact scan of all 256 codewords).
+#include "assign.cuh"
+#include "common.cuh"
+#include "exact.cuh"
+#include "tc_common.cuh"
+#include "tc_pq.cuh"
+
+namespace lb2 {
+namespace tcpq {
+
+using namespace tc;
+
+constexpr int DS = 8;
+constexpr int STAGES = 4;
+constexpr int MAX_M = 16;  // d <= 128
+
+struct Layout {
+  uint32_t b_off, a_off, cnh_off, bar_off, misc_off, total;
+};
+__host__ __device__ inline Layout layout(int nkc, int M) {
+  Layout L;
+  L.b_off = 0;
+  L.a_off = nkc * B_CHUNK_BYTES;
+  L.cnh_off = L.a_off + STAGES * A_STAGE_BYTES;
+  L.bar_off = L.cnh_off + M * TN * 4;
+  L.misc_off = L.bar_off + (2 * STAGES + 1 + 4) * 8;
+  L.total = L.misc_off + 64;
+  return L;
+}
+
+// physical address of the 16-byte unit `u` (0..7) of row `r` inside a [rows x 128 B] SWIZZLE_128B tile
+__device__ __forceinline__ const float4* swz(const uint8_t* tile, int r, int u) {
+  return reinterpret_cast<const float4*>(tile + (r >> 3) * 1024 + (r & 7) * 128 + ((u ^ (r & 7)) << 4));
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_b,
+             uint64_t n, int M, const float* __restrict__ cnh_g, const float* __restrict__ cbmax2,
+             const float* __restrict__ rn2, const uint8_t* __restrict__ row_valid,
+             uint8_t* __restrict__ codes, uint32_t* __restrict__ ids, float* __restrict__ dists,
+             uint8_t* __restrict__ valid, uint32_t* __restrict__ fb_pairs,
+             uint32_t* __restrict__ fb_count, const uint8_t* __restrict__ active) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nkc = M / 4;
+  const Layout L = layout(nkc, M);
+  float* cnh = reinterpret_cast<float*>(smem + L.cnh_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L.misc_off);
+  uint32_t* act_mask_smem = tmem_ptr_smem + 1;
+  const uint32_t sb = smem_u32(smem);
+  auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
+  auto empty_bar = [&](int s) { return smem_u32(&bars[STAGES + s]); };
+  const uint32_t b_full = smem_u32(&bars[2 * STAGES]);
+  auto tfull_bar = [&](int b) { return smem_u32(&bars[2 * STAGES + 1 + b]); };
+  auto tempty_bar = [&](int b) { return smem_u32(&bars[2 * STAGES + 3 + b]); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t num_tiles = (n + TM - 1) / TM;
+
+  for (int i = threadIdx.x; i < M * TN; i += NUM_THREADS) cnh[i] = cnh_g[i];
+  if (threadIdx.x == 0) {
+    uint32_t mask = 0;
+    for (int m = 0; m < M; ++m)
+      if (!active || active[m]) mask |= 1u << m;
+    *act_mask_smem = mask;
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 5);  // MMA commit + 4 epilogue warps (they re-read the operands)
+    }
+    mbar_init(b_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr_smem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t act_mask = *act_mask_smem;
+  if (act_mask == 0) goto teardown;  // uniform
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(b_full, (uint32_t)nkc * B_CHUNK_BYTES);
+      for (int kc = 0; kc < nkc; ++kc)
+        tma_load_2d(sb + L.b_off + kc * B_CHUNK_BYTES, &map_b, b_full, kc * KC, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < nkc; ++kc) {
+          if (((act_mask >> (kc * 4)) & 0xF) == 0) continue;  // chunk with no active sub-space
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), A_STAGE_BYTES);
+          tma_load_2d(sb + L.a_off + s * A_STAGE_BYTES, &map_r, full_bar(s), kc * KC, (int)(tile * TM));
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      mbar_wait(b_full, 0);
+      int s = 0;
+      uint32_t ph = 0, it = 0;
+      for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < nkc; ++kc) {
+          const uint32_t cm = (act_mask >> (kc * 4)) & 0xF;
+          if (cm == 0) continue;
+          mbar_wait(full_bar(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_addr = sb + L.a_off + s * A_STAGE_BYTES;
+          const uint32_t b_addr = sb + L.b_off + kc * B_CHUNK_BYTES;
+          for (int j = 0; j < 4; ++j) {
+            if (!((cm >> j) & 1)) continue;
+            const uint32_t buf = it & 1;
+            mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            umma_tf32(tmem_base + buf * TN, make_desc(a_addr + j * 32), make_desc(b_addr + j * 32), 0u);
+            umma_commit(tfull_bar(buf));
+            ++it;
+          }
+          umma_commit(empty_bar(s));
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int q = warp & 3;
+    const uint8_t* btile = smem + L.b_off;
+    mbar_wait(b_full, 0);  // the codebook tile is re-read by the exact re-rank below
+    int s = 0;
+    uint32_t ph = 0, it = 0;
+    for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int rl = q * 32 + lane;  // row inside the tile == TMEM lane
+      const uint64_t row = tile * TM + rl;
+      for (int kc = 0; kc < nkc; ++kc) {
+        const uint32_t cm = (act_mask >> (kc * 4)) & 0xF;
+        if (cm == 0) continue;
+        mbar_wait(full_bar(s), ph);  // operands visible to this thread (re-read below)
+        const uint8_t* atile = smem + L.a_off + s * A_STAGE_BYTES;
+        for (int j = 0; j < 4; ++j) {
+          if (!((cm >> j) & 1)) continue;
+          const int m = kc * 4 + j;
+          const uint32_t buf = it & 1;
+          mbar_wait(tfull_bar(buf), (it >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * TN;
+          const float* cn = cnh + m * TN;
+          float m1 = __int_as_float(0xff800000), m2 = m1, m3 = m1;
+#pragma unroll 1
+          for (int c0 = 0; c0 < TN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c0, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              const float f = __uint_as_float(v[jj]) + cn[c0 + jj];
+              const float g = __uint_as_float((__float_as_uint(f) & 0xFFFFFF00u) | (uint32_t)(c0 + jj));
+              const float t1 = fminf(m1, g);
+              m1 = fmaxf(m1, g);
+              const float t2 = fminf(m2, t1);
+              m2 = fmaxf(m2, t1);
+              m3 = fmaxf(m3, t2);
+            }
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(buf));
+          ++it;
+          if (row < n) {
+            const float tau = 0.0029296875f * (rn2[row * M + m] + cbmax2[m]);
+            uint32_t flag = 2;
+            if (m1 - m2 > tau) flag = 0;
+            else if (m1 - m3 > tau) flag = 1;
+            const uint32_t i1 = __float_as_uint(m1) & 0xFFu, i2 = __float_as_uint(m2) & 0xFFu;
+            uint32_t best_idx = i1;
+            float best_val = 0.0f;
+            bool ok = true;
+            if (flag == 2) {
+              fb_pairs[atomicAdd(fb_count, 1u)] = (uint32_t)(row * M + m);
+            } else if (TRAIN || flag == 1) {
+              // exact, reference-order distance(s) from the operands still in shared memory
+              const float4 r0 = *swz(atile, rl, j * 2), r1 = *swz(atile, rl, j * 2 + 1);
+              const float rv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+              float bv = __int_as_float(0x7f800000);
+              uint32_t bi = 0xffffffffu;
+              const int ncand = flag == 0 ? 1 : 2;
+              for (int c = 0; c < ncand; ++c) {
+                const uint32_t ci = c == 0 ? i1 : i2;
+                const uint8_t* bt = btile + kc * B_CHUNK_BYTES;
+                const float4 c0v = *swz(bt, (int)ci, j * 2), c1v = *swz(bt, (int)ci, j * 2 + 1);
+                const float cv[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+                float sacc = 0.0f;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) sacc = f_add(sacc, sq_diff(rv[t], cv[t]));
+                const float vv = f_add(sacc, 0.0f);
+                if (vv < bv || (vv == bv && ci < bi)) { bv = vv; bi = ci; }
+              }
+              ok = bi != 0xffffffffu;
+              best_idx = ok ? bi : 0u;
+              best_val = bv;
+            }
+            if (flag != 2) {
+              if (TRAIN) {
+                ids[(uint64_t)m * n + row] = best_idx;
+                dists[(uint64_t)m * n + row] = ok ? best_val : __int_as_float(0x7fc00000);
+                valid[(uint64_t)m * n + row] = ok ? 1 : 0;
+              } else {
+                const bool rv_ok = row_valid ? row_valid[row] != 0 : true;
+                codes[row * (uint64_t)M + m] = (ok && rv_ok) ? (uint8_t)best_idx : (uint8_t)0;
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(s));  // this warp is done re-reading the stage
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  }
+teardown:
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// Bm[c][m*8+t] = cb[m][c][t];  cnh[m][c] = -|cb[m][c]|^2 / 2;  cbmax2[m] = max_c |cb[m][c]|^2
+__global__ void prep_codebook_kernel(const float* __restrict__ cb, int M, int d, float* __restrict__ bm,
+                                     float* __restrict__ cnh, float* __restrict__ cbmax2) {
+  __shared__ float s_n2[TN];
+  const int m = blockIdx.x, c = threadIdx.x;  // grid M, block 256
+  const float* src = cb + ((size_t)m * TN + c) * DS;
+  float n2 = 0.0f;
+#pragma unroll
+  for (int t = 0; t < DS; ++t) {
+    const float v = src[t];
+    bm[(size_t)c * d + m * DS + t] = v;
+    n2 += v * v;
+  }
+  cnh[m * TN + c] = -0.5f * n2;
+  s_n2[c] = n2;
+  __syncthreads();
+  if (c == 0) {
+    float mx = 0.0f;
+    for (int i = 0; i < TN; ++i) mx = fmaxf(mx, s_n2[i]);
+    cbmax2[m] = mx;
+  }
+}
+
+// (optional residual) + per-sub-space squared norms: one thread per (row, m)
+__global__ void residual_norms_kernel(const float* x, const float* __restrict__ cent,
+                                      const uint32_t* __restrict__ part, uint64_t n, int M,
+                                      float* r_out, float* __restrict__ rn2) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n * M) return;
+  const uint64_t row = g / M;
+  const int m = g % M;
+  const int d = M * DS;
+  const float4* xp = reinterpret_cast<const float4*>(x + row * d + m * DS);
+  float4 a = xp[0], b = xp[1];
+  if (cent) {
+    const float4* cp = reinterpret_cast<const float4*>(cent + (size_t)part[row] * d + m * DS);
+    const float4 ca = cp[0], cbv = cp[1];
+    a.x = __fsub_rn(a.x, ca.x); a.y = __fsub_rn(a.y, ca.y); a.z = __fsub_rn(a.z, ca.z); a.w = __fsub_rn(a.w, ca.w);
+    b.x = __fsub_rn(b.x, cbv.x); b.y = __fsub_rn(b.y, cbv.y); b.z = __fsub_rn(b.z, cbv.z); b.w = __fsub_rn(b.w, cbv.w);
+  }
+  if (r_out) {
+    float4* rp = reinterpret_cast<float4*>(r_out + row * d + m * DS);
+    rp[0] = a;
+    rp[1] = b;
+  }
+  rn2[g] = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+}
+
+// exact scan of all 256 codewords for the (row, sub-space) pairs the filter could not decide:
+// half-warp per pair, lane l scans codewords l, l+16, ... (ascending), lexicographic (value, index) min
+template <bool TRAIN>
+__global__ void __launch_bounds__(256)
+pq_fallback_kernel(const float* __restrict__ r, uint64_t n, int M, const float* __restrict__ cb,
+                   const uint32_t* __restrict__ pairs, const uint32_t* __restrict__ count,
+                   const uint8_t* __restrict__ row_valid, uint8_t* __restrict__ codes,
+                   uint32_t* __restrict__ ids, float* __restrict__ dists, uint8_t* __restrict__ valid) {
+  const uint32_t total = *count;
+  const int l = threadIdx.x & 15;
+  const unsigned mask = 0xffffu << (16 * ((threadIdx.x >> 4) & 1));
+  for (uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4; p < total;
+       p += ((uint64_t)gridDim.x * blockDim.x) >> 4) {
+    const uint32_t pr = pairs[p];
+    const uint64_t row = pr / M;
+    const int m = pr % M;
+    const float* rp = r + row * (uint64_t)(M * DS) + m * DS;
+    float rv[DS];
+#pragma unroll
+    for (int t = 0; t < DS; ++t) rv[t] = rp[t];
+    float bv = __int_as_float(0x7f800000);
+    uint32_t bi = 0xffffffffu;
+    for (int c = l; c < TN; c += 16) {
+      const float* cp = cb + ((size_t)m * TN + c) * DS;
+      float s = 0.0f;
+#pragma unroll
+      for (int t = 0; t < DS; ++t) s = f_add(s, sq_diff(rv[t], cp[t]));
+      const float v = f_add(s, 0.0f);
+      if (v < bv) { bv = v; bi = c; }
+    }
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {
+      const float ov = __shfl_xor_sync(mask, bv, off, 16);
+      const uint32_t oi = __shfl_xor_sync(mask, bi, off, 16);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (l == 0) {
+      const bool ok = bi != 0xffffffffu;
+      if (TRAIN) {
+        ids[(uint64_t)m * n + row] = ok ? bi : 0u;
+        dists[(uint64_t)m * n + row] = ok ? bv : __int_as_float(0x7fc00000);
+        valid[(uint64_t)m * n + row] = ok ? 1 : 0;
+      } else {
+        const bool rv_ok = row_valid ? row_valid[row] != 0 : true;
+        codes[row * (uint64_t)M + m] = (ok && rv_ok) ? (uint8_t)bi : (uint8_t)0;
+      }
+    }
+  }
+}
+
+}  // namespace tcpq
+
+bool tc_pq_supported(uint64_t n, int d, int M, int ds, int Kc, int metric, const float* x) {
+  if (getenv("LB2_DISABLE_TC") && *getenv("LB2_DISABLE_TC")) return false;
+  return metric == METRIC_L2 && ds == 8 && Kc == 256 && d == M * 8 && d % 32 == 0 && d <= 128 &&
+         n >= 256 && n * (uint64_t)M < (1ull << 32) && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+}
+
+void tc_pq_prepare(const float* codebook, int M, int d, TcPqWorkspace* ws) {
+  using namespace tcpq;
+  if (ws->bm.n < (size_t)tc::TN * d) ws->bm.alloc((size_t)tc::TN * d);
+  if (ws->cnh.n < (size_t)M * tc::TN + M) ws->cnh.alloc((size_t)M * tc::TN + M);
+  LB2_LAUNCH("tc_pq_prep_codebook", prep_codebook_kernel, M, tc::TN, 0, codebook, M, d, ws->bm.p,
+             ws->cnh.p, ws->cnh.p + (size_t)M * tc::TN);
+}
+
+// r: residual (or raw) vectors [n][d] with their per-sub-space norms rn2 [n][M] already computed
+void tc_pq_assign(const float* r, const float* rn2, uint64_t n, int d, int M, const float* codebook,
+                  const uint8_t* row_valid, uint8_t* codes, uint32_t* ids, float* dists,
+                  uint8_t* valid, const uint8_t* active, TcPqWorkspace* ws) {
+  using namespace tcpq;
+  const int nkc = M / 4;
+  const Layout L = layout(nkc, M);
+  const size_t smem = L.total + 1024;
+  if (smem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "tc_pq: shared memory");
+  tc_pq_prepare(codebook, M, d, ws);
+  if (ws->fb_pairs.n < n * M) ws->fb_pairs.alloc(n * M);
+  if (ws->fb_count.n < 1) ws->fb_count.alloc(1);
+  LB2_CUDA(cudaMemsetAsync(ws->fb_count.p, 0, sizeof(uint32_t), ctx().stream));
+  const CUtensorMap map_r = make_map_2d(r, n, d, tc::TM);
+  const CUtensorMap map_b = make_map_2d(ws->bm.p, tc::TN, d, tc::TN);
+  const uint64_t tiles = (n + tc::TM - 1) / tc::TM;
+  const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)ctx().num_sms);
+  const float* cnh = ws->cnh.p;
+  const float* cbmax2 = ws->cnh.p + (size_t)M * tc::TN;
+  const unsigned fb_grid = (unsigned)std::min<uint64_t>(cdiv(n * M * 16, 256), (uint64_t)ctx().num_sms * 8);
+  if (codes) {
+    set_smem(tc_pq_kernel<false>, smem);
+    LB2_LAUNCH("tc_pq_filter", tc_pq_kernel<false>, grid, tc::NUM_THREADS, smem, map_r, map_b, n, M, cnh,
+               cbmax2, rn2, row_valid, codes, ids, dists, valid, ws->fb_pairs.p, ws->fb_count.p, active);
+    LB2_LAUNCH("tc_pq_fallback", pq_fallback_kernel<false>, fb_grid, 256, 0, r, n, M, codebook,
+               ws->fb_pairs.p, ws->fb_count.p, row_valid, codes, ids, dists, valid);
+  } else {
+    set_smem(tc_pq_kernel<true>, smem);
+    LB2_LAUNCH("tc_pq_filter", tc_pq_kernel<true>, grid, tc::NUM_THREADS, smem, map_r, map_b, n, M, cnh,
+               cbmax2, rn2, row_valid, codes, ids, dists, valid, ws->fb_pairs.p, ws->fb_count.p, active);
+    LB2_LAUNCH("tc_pq_fallback", pq_fallback_kernel<true>, fb_grid, 256, 0, r, n, M, codebook,
+               ws->fb_pairs.p, ws->fb_count.p, row_valid, codes, ids, dists, valid);
+  }
+  if (getenv("LB2_TC_STATS") && *getenv("LB2_TC_STATS")) {
+    uint32_t c = 0;
+    d2h(&c, ws->fb_count.p, 1);
+    sync_stream();
+    fprintf(stderr, "[lb2 tc_pq] n=%llu M=%d: exact-fallback pairs %.2f%%\n", (unsigned long long)n, M,
+            100.0 * c / ((double)n * M));
+  }
+}
+
+void pq_encode_dev(const float* x, uint64_t n, int d, int M, int ds, const float* codebook, int metric,
+                   const float* cent, const uint32_t* part, const uint8_t* row_valid, uint8_t* codes) {
+  if (n == 0) return;
+  if (!tc_pq_supported(n, d, M, ds, 256, metric, x)) {
+    small_d_assign_f32(x, n, d, M, ds, codebook, 256, metric, cent, part, row_valid, codes, nullptr,
+                       nullptr, nullptr, nullptr);
+    return;
+  }
+  TcPqWorkspace ws;
+  const uint64_t chunk = 1ull << 21;  // 2M rows: 1 GB of residuals at d = 128
+  DevBuf<float> r, rn2(std::min(n, chunk) * M);
+  if (cent) r.alloc(std::min(n, chunk) * d);
+  for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
+    const uint64_t rows = std::min(chunk, n - r0);
+    const float* xs = x + r0 * d;
+    tc_pq_residual_norms(xs, cent, part ? part + r0 : nullptr, rows, M, cent ? r.p : nullptr, rn2.p);
+    tc_pq_assign(cent ? r.p : xs, rn2.p, rows, d, M, codebook, row_valid ? row_valid + r0 : nullptr,
+                 codes + r0 * M, nullptr, nullptr, nullptr, nullptr, &ws);
+  }
+}
+
+void tc_pq_residual_norms(const float* x, const float* cent, const uint32_t* part, uint64_t n, int M,
+                          float* r_out, float* rn2) {
+  LB2_LAUNCH("tc_pq_residual_norms", tcpq::residual_norms_kernel, cdiv(n * M, 256), 256, 0, x, cent,
+             part, n, M, r_out, rn2);
+}
+
+}  // namespace lb2

@@ -355,3 +355,36 @@ def test_tc_filter_sift_shaped_and_training():
     co, loss_o, it_o = ob.kmeans_train(data[:nn], 256, max_iters=12, init_centroids=init,
                                        balance_factor=float(np.float32(1.0) / np.float32(nn)), nthreads=NT)
     assert k1.iters == it_o and np.array_equal(k1.centroids, co) and k1.loss == loss_o
+
+
+@pytest.mark.parametrize("n,d,M", [(1500, 128, 16), (4097, 64, 8), (300, 32, 4), (20000, 128, 16)])
+def test_tc_pq_encode_equals_exact_path(n, d, M):
+    rng = np.random.default_rng(n + d)
+    cb = (rng.standard_normal((M, 256, 8)) * 2).astype(np.float32)
+    cb[0, 7] = cb[0, 3]            # duplicate codeword: index 3 must win
+    cb[1, 100:104] = cb[1, 100]    # 4-way tie -> exact fallback
+    vec = (rng.standard_normal((n, d)) * 2).astype(np.float32)
+    vec[5, :8] = cb[0, 3]          # exactly on a duplicated codeword
+    pq = lb.ProductQuantizer(M, 8, d, cb)
+    c1, c2 = _both_paths(lambda: pq.quantize(vec))
+    assert np.array_equal(c1, c2)
+    assert np.array_equal(c1, ob.pq_encode(cb, vec, nthreads=NT))
+    assert c1[5, 0] == 3
+
+
+def test_tc_pq_fused_residual_and_training_equal_exact_path():
+    rng = np.random.default_rng(123)
+    n, d, M, K = 30000, 128, 16, 64
+    data = synth.sift_like(n, d, seed=9)
+    cent = data[rng.choice(n, K, replace=False)].copy()
+    cb0 = (rng.standard_normal((M, 256, 8)) * 20).astype(np.float32)
+    (a1, a2) = _both_paths(lambda: lb.ivfpq_transform(cent, cb0, data))
+    assert np.array_equal(a1[0], a2[0]) and np.array_equal(a1[1], a2[1])
+    part, _, _ = ob.compute_membership(cent, data, nthreads=NT)
+    res = ob.compute_residual(cent, data, part, nthreads=NT)
+    assert np.array_equal(a1[1], ob.pq_encode(cb0, res, nthreads=NT))
+    init = np.stack([res[rng.choice(n, 256, replace=False)][:, m * 8:(m + 1) * 8] for m in range(M)])
+    (p1, p2) = _both_paths(lambda: lb.PQBuildParams(M, 8, max_iters=10, codebook=init).build(res))
+    assert np.array_equal(p1.train_iters, p2.train_iters) and np.array_equal(p1.codebook, p2.codebook)
+    cbo, iters_o = ob.pq_train(res, M, max_iters=10, init_codebook=init, nthreads=NT)
+    assert np.array_equal(p1.codebook, cbo) and np.array_equal(p1.train_iters.astype(np.int32), iters_o)
