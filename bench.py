@@ -226,6 +226,10 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 KERNEL_BYTES = {
     # algorithmic bytes per launch (DESIGN.md "kernels"): rows*d*4 read + outputs written
+    "ivf_train:tc_filter": lambda ns, n: ns * DIM * 4 + ns * 8,
+    "pq_train:tc_pq_filter": lambda ns, n: ns * DIM * 4 + ns * NUM_SUB_VECTORS * (4 + 9),
+    "transform:tc_filter": lambda ns, n: n * DIM * 4 + n * 8,
+    "transform:tc_pq_filter": lambda ns, n: n * DIM * 4 + n * NUM_SUB_VECTORS * 5,
     "ivf_train:assign_exact": lambda ns, n: ns * DIM * 4 + ns * 9,
     "pq_train:pq_assign_exact": lambda ns, n: ns * DIM * 4 + ns * NUM_SUB_VECTORS * 9,
     "pq_train:assign_exact": lambda ns, n: ns * DIM * 4 + ns * 4,
@@ -318,14 +322,8 @@ def main():
     # ---- kernel breakdown + roofline of the dominant kernel -------------------------------------
     hbm_peak, peak_src = peaks()
     fams = {}
-    for fam in ["ivf_train:assign_exact", "ivf_train:member_sort", "ivf_train:kmeans_update", "ivf_train:kmeans_stats",
-                "ivf_train:transpose_centroids", "pq_train:pq_assign_exact", "pq_train:member_sort",
-                "pq_train:kmeans_update", "pq_train:kmeans_stats", "pq_train:assign_exact", "transform:assign_exact",
-                "transform:pq_assign_exact", "group:member_sort", "group:group_by_partition"]:
-        cnt, ms = lb.profile.get(fam)
-        if cnt:
-            fams[fam] = {"launches_per_step": cnt / args.steps, "ms_per_step": ms / args.steps,
-                         "share": ms / ms_total}
+    for fam, (cnt, ms) in sorted(lb.profile.dump().items()):
+        fams[fam] = {"launches_per_step": cnt / args.steps, "ms_per_step": ms / args.steps, "share": ms / ms_total}
     dom = max((f for f in fams if f in KERNEL_BYTES), key=lambda f: fams[f]["ms_per_step"])
     per_launch_ms = fams[dom]["ms_per_step"] / fams[dom]["launches_per_step"]
     alg_bytes = KERNEL_BYTES[dom](65536, n)
@@ -333,8 +331,7 @@ def main():
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": per_launch_ms,
-                "note": "exact-order f32 kernels are FP32-pipe bound (3 non-fused ops per element pair), "
-                        "not HBM bound; see DESIGN.md"}
+                "note": "dominant kernel of the build step by measured time; see DESIGN.md section 5"}
 
     if args.only == "build":
         if rank == 0:

@@ -66,6 +66,8 @@ lb2_status lb2_launch_count(uint64_t* count, int reset);
 lb2_status lb2_profile_enable(int on);
 lb2_status lb2_profile_get(const char* name, uint64_t* launches, double* total_ms);
 lb2_status lb2_profile_reset(void);
+/* all entries as "name\tlaunches\ttotal_ms\n" lines; returns the full length (like snprintf) */
+size_t lb2_profile_dump(char* buf, size_t len);
 lb2_status lb2_timer_start(void);          /* CUDA event on the library's stream */
 lb2_status lb2_timer_stop(float* ms_out);  /* records, synchronises, returns elapsed ms */
 

@@ -65,6 +65,18 @@ class profile:
         check(lib().lb2_profile_reset())
 
     @staticmethod
+    def dump():
+        """{name: (launches, total_ms)} for every kernel family seen since the last reset"""
+        n = lib().lb2_profile_dump(None, 0)
+        buf = C.create_string_buffer(n + 1)
+        lib().lb2_profile_dump(buf, n + 1)
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split("\t")
+            out[name] = (int(cnt), float(ms))
+        return out
+
+    @staticmethod
     def get(name):
         n, ms = C.c_uint64(0), C.c_double(0)
         check(lib().lb2_profile_get(name.encode(), C.byref(n), C.byref(ms)))

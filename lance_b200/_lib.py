@@ -53,7 +53,7 @@ class BuildStats(C.Structure):
 EXPORTS = [
     "lb2_version", "lb2_last_error", "lb2_device_count", "lb2_set_device", "lb2_synchronize",
     "lb2_malloc", "lb2_free", "lb2_malloc_host", "lb2_free_host", "lb2_memcpy", "lb2_launch_count",
-    "lb2_profile_enable", "lb2_profile_get", "lb2_profile_reset", "lb2_timer_start", "lb2_timer_stop",
+    "lb2_profile_enable", "lb2_profile_get", "lb2_profile_reset", "lb2_profile_dump", "lb2_timer_start", "lb2_timer_stop",
     "lb2_distance_batch", "lb2_normalize", "lb2_kmeans_params_default", "lb2_kmeans_train",
     "lb2_compute_partitions", "lb2_find_partitions", "lb2_compute_residual", "lb2_pq_params_default",
     "lb2_pq_train", "lb2_pq_encode", "lb2_pq_build_lut", "lb2_pq_scan", "lb2_flat_topk",
@@ -77,8 +77,10 @@ def lib():
         L.lb2_last_error.restype = C.c_size_t
         L.lb2_last_error.argtypes = [C.c_char_p, C.c_size_t]
         L.lb2_device_count.restype = C.c_int
+        L.lb2_profile_dump.restype = C.c_size_t
+        L.lb2_profile_dump.argtypes = [C.c_char_p, C.c_size_t]
         for name in EXPORTS:
-            if name not in ("lb2_version", "lb2_last_error", "lb2_device_count",
+            if name not in ("lb2_version", "lb2_last_error", "lb2_device_count", "lb2_profile_dump",
                             "lb2_kmeans_params_default", "lb2_pq_params_default",
                             "lb2_ivfpq_build_params_default"):
                 getattr(L, name).restype = C.c_int

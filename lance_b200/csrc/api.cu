@@ -297,6 +297,25 @@ lb2_status lb2_profile_reset(void) {
   ctx().prof.clear();
   LB2_API_END
 }
+size_t lb2_profile_dump(char* buf, size_t len) {
+  std::string out;
+  try {
+    ctx().flush_profile();
+    for (auto& kv : ctx().prof) {
+      char line[256];
+      snprintf(line, sizeof(line), "%s\t%llu\t%.6f\n", kv.first.c_str(),
+               (unsigned long long)kv.second.launches, kv.second.total_ms);
+      out += line;
+    }
+  } catch (...) {
+  }
+  if (buf && len) {
+    size_t c = std::min(len - 1, out.size());
+    memcpy(buf, out.data(), c);
+    buf[c] = 0;
+  }
+  return out.size();
+}
 lb2_status lb2_timer_start(void) {
   LB2_API_BEGIN
   LB2_CUDA(cudaEventRecord(ctx().t0, ctx().stream));
