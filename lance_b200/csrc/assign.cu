@@ -32,7 +32,9 @@ __global__ void transpose_pad_kernel(const float* __restrict__ c, int K, int d, 
 // ------------------------------------------------------------------------------------------------
 // (a) tile kernel
 // ------------------------------------------------------------------------------------------------
-template <int METRIC, bool WRITE_ALL>
+// RT = rows per thread (4: 64-row tiles for bulk work; 1: 16-row tiles so that a short row list
+// -- the tensor-core filter's ambiguous rows -- still spreads over all SMs)
+template <int METRIC, bool WRITE_ALL, int RT>
 __global__ void __launch_bounds__(256)
 assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __restrict__ cT,
                    int K, int Kp, const float* __restrict__ bias, uint32_t* __restrict__ part,
@@ -45,13 +47,14 @@ assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* 
   if (row_list) n = *row_count;
   extern __shared__ float smem[];
   const int ld = d + 1;
-  float* xs = smem;            // [64][d+1]
-  float* cs = smem + 64 * ld;  // [d][64]
+  constexpr int ROWS = 16 * RT;
+  float* xs = smem;              // [ROWS][d+1]
+  float* cs = smem + ROWS * ld;  // [d][64]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const uint64_t row0 = (uint64_t)blockIdx.x * 64;
+  const uint64_t row0 = (uint64_t)blockIdx.x * ROWS;
   if (row0 >= n) return;
 
-  for (int idx = tid; idx < 16 * d; idx += 256) {  // 64*d/4 float4
+  for (int idx = tid; idx < ROWS * d / 4; idx += 256) {  // float4 granules
     int r = (idx * 4) / d, e = (idx * 4) % d;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row0 + r < n) {
@@ -61,16 +64,16 @@ assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* 
     float* dst = xs + r * ld + e;
     dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
   }
-  float best_key[4], best_val[4];
-  uint32_t best_idx[4];
+  float best_key[RT], best_val[RT];
+  uint32_t best_idx[RT];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < RT; ++i) {
     best_key[i] = __int_as_float(0x7f800000);
     best_val[i] = __int_as_float(0x7f800000);
     best_idx[i] = 0xffffffffu;
   }
   const int nchunk = d >> 4;
-  const float* xrow = xs + (ty * 4) * ld;
+  const float* xrow = xs + (ty * RT) * ld;
   for (int ct = 0; ct < Kp; ct += 64) {
     __syncthreads();
     for (int idx = tid; idx < d * 16; idx += 256) {
@@ -79,26 +82,26 @@ assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* 
           *reinterpret_cast<const float4*>(cT + (size_t)e * Kp + ct + q * 4);
     }
     __syncthreads();
-    float total[4][4];
+    float total[RT][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RT; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) total[i][j] = 0.0f;
     for (int l = 0; l < 16; ++l) {
-      float acc[4][4];
+      float acc[RT][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RT; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 #pragma unroll 2
       for (int c = 0; c < nchunk; ++c) {
         const int e = c * 16 + l;
         const float4 cv = *reinterpret_cast<const float4*>(cs + e * 64 + tx * 4);
-        float xv[4];
+        float xv[RT];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) xv[i] = xrow[i * ld + e];
+        for (int i = 0; i < RT; ++i) xv[i] = xrow[i * ld + e];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < RT; ++i) {
           acc[i][0] = f_add(acc[i][0], term<METRIC>(xv[i], cv.x));
           acc[i][1] = f_add(acc[i][1], term<METRIC>(xv[i], cv.y));
           acc[i][2] = f_add(acc[i][2], term<METRIC>(xv[i], cv.z));
@@ -106,18 +109,18 @@ assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* 
         }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RT; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) total[i][j] = f_add(total[i][j], acc[i][j]);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < RT; ++i) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t cidx = ct + tx * 4 + j;
         const float v = finish<METRIC>(total[i][j]);
         if (WRITE_ALL) {
-          const uint64_t r = row0 + ty * 4 + i;
+          const uint64_t r = row0 + ty * RT + i;
           if (r < n && cidx < (uint32_t)K) all_out[r * K + cidx] = v;
         } else {
           const float key = bias ? f_add(v, bias[cidx < (uint32_t)K ? cidx : 0]) : v;
@@ -132,7 +135,7 @@ assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* 
   }
   if (WRITE_ALL) return;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < RT; ++i) {
 #pragma unroll
     for (int off = 8; off >= 1; off >>= 1) {
       float ok = __shfl_xor_sync(0xffffffffu, best_key[i], off);
@@ -142,7 +145,7 @@ assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* 
         best_key[i] = ok; best_val[i] = ov; best_idx[i] = oi;
       }
     }
-    const uint64_t rr = row0 + ty * 4 + i;
+    const uint64_t rr = row0 + ty * RT + i;
     if (tx == 0 && rr < n) {
       const uint64_t r = row_list ? row_list[rr] : rr;
       const bool ok = best_idx[i] != 0xffffffffu;
@@ -363,12 +366,12 @@ static void assign_dispatch(const float* x, uint64_t n, int d, const float* cent
     const size_t smem = sizeof(float) * (64 * (d + 1) + (size_t)d * 64);
     const unsigned grid = cdiv(n, 64);
     if (all_out) {
-      set_smem(assign_tile_kernel<METRIC, true>, smem);
-      LB2_LAUNCH("assign_exact", (assign_tile_kernel<METRIC, true>), grid, 256, smem, x, n, d,
+      set_smem(assign_tile_kernel<METRIC, true, 4>, smem);
+      LB2_LAUNCH("assign_exact", (assign_tile_kernel<METRIC, true, 4>), grid, 256, smem, x, n, d,
                  cT.get(), K, Kp, bp, part, dist, valid, all_out, active, nullptr, nullptr);
     } else {
-      set_smem(assign_tile_kernel<METRIC, false>, smem);
-      LB2_LAUNCH("assign_exact", (assign_tile_kernel<METRIC, false>), grid, 256, smem, x, n, d,
+      set_smem(assign_tile_kernel<METRIC, false, 4>, smem);
+      LB2_LAUNCH("assign_exact", (assign_tile_kernel<METRIC, false, 4>), grid, 256, smem, x, n, d,
                  cT.get(), K, Kp, bp, part, dist, valid, all_out, active, nullptr, nullptr);
     }
     return;
@@ -397,9 +400,9 @@ void assign_rows_f32(const float* x, uint64_t n_max, int d, const float* cent, i
   DevBuf<float> cT((size_t)d * Kp);
   LB2_LAUNCH("transpose_centroids", transpose_pad_kernel, cdiv((uint64_t)d * Kp, 256), 256, 0, cent,
              K, d, Kp, cT.get());
-  const size_t smem = sizeof(float) * (64 * (d + 1) + (size_t)d * 64);
-  set_smem(assign_tile_kernel<METRIC_L2, false>, smem);
-  LB2_LAUNCH("assign_exact_fallback", (assign_tile_kernel<METRIC_L2, false>), cdiv(n_max, 64), 256,
+  const size_t smem = sizeof(float) * (16 * (d + 1) + (size_t)d * 64);
+  set_smem(assign_tile_kernel<METRIC_L2, false, 1>, smem);
+  LB2_LAUNCH("assign_exact_fallback", (assign_tile_kernel<METRIC_L2, false, 1>), cdiv(n_max, 16), 256,
              smem, x, n_max, d, cT.get(), K, Kp, bias_padded, part, dist, valid, nullptr, active,
              row_list, row_count);
 }

@@ -132,12 +132,12 @@ __global__ void update_kernel(const float* __restrict__ x, int ldx, int ds, int 
   const float* col = x + (size_t)b * ds + t;
   float acc = 0.0f;
   uint32_t j = s;
-  for (; j + 8 <= e; j += 8) {
-    float v[8];
+  for (; j + 16 <= e; j += 16) {
+    float v[16];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = col[(size_t)mem[j + q] * ldx];
+    for (int q = 0; q < 16; ++q) v[q] = col[(size_t)mem[j + q] * ldx];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc = f_add(acc, v[q]);
+    for (int q = 0; q < 16; ++q) acc = f_add(acc, v[q]);
   }
   for (; j < e; ++j) acc = f_add(acc, col[(size_t)mem[j] * ldx]);
   const uint32_t cnt = e - s;
@@ -207,8 +207,11 @@ __global__ void gather_init_kernel(const float* __restrict__ x, int ldx, int ds,
 void MemberSort::run(const uint32_t* ids, const uint8_t* valid, uint64_t n, int K, int B,
                      const uint8_t* active) {
   // chunk size: keep the per-chunk histogram table below ~256 MB
-  int chunk_rows = 2048;
-  while ((double)B * (double)cdiv(n, chunk_rows) * K * 4.0 > 256e6) chunk_rows *= 2;
+  // one warp scatters one chunk sequentially (32 rows per step): keep chunks short so that the
+  // grid is wide, but bound the per-chunk histogram table (B * nchunks * K counters) to ~64 MB
+  int chunk_rows = 256;
+  while ((uint64_t)chunk_rows * 1024 < n) chunk_rows *= 2;  // at most ~1024 chunks (scan is per chunk)
+  while ((double)B * (double)cdiv(n, chunk_rows) * K * 4.0 > 64e6) chunk_rows *= 2;
   const int nchunks = std::max(1u, cdiv(n, chunk_rows));
   if (chunk_hist.n < (size_t)B * nchunks * K) chunk_hist.alloc((size_t)B * nchunks * K);
   if (counts.n < (size_t)B * K) counts.alloc((size_t)B * K);

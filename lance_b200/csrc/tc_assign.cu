@@ -139,10 +139,12 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers, top-3 per row =====
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const uint32_t group = (warp >> 2) - 1;  // 0 or 1: owns TMEM buffer `group`
     const float cmax2 = *cmax2_ptr;
     uint32_t it = 0;
     for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1;
+      if (buf != group) continue;
       mbar_wait(tfull_bar(buf), (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * TN;
@@ -192,22 +194,21 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 __global__ void prep_centroids_kernel(const float* __restrict__ c, int K, int d,
                                       const float* __restrict__ bias, float* __restrict__ cpad,
                                       float* __restrict__ cnh, float* __restrict__ cmax2) {
-  __shared__ float s_max[TN];
-  const int k = threadIdx.x;  // blockDim = TN
+  // grid = TN/8 blocks of 256 threads: one warp per centroid row (coalesced), cmax2 by atomicMax on
+  // the bit pattern (norms are >= 0 so the integer order equals the float order)
+  const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   float n2 = 0.0f;
-  for (int e = 0; e < d; ++e) {
+  for (int e = lane; e < d; e += 32) {
     const float v = k < K ? c[(size_t)k * d + e] : 0.0f;
     cpad[(size_t)k * d + e] = v;
     n2 += v * v;
   }
-  // pads: a huge negative FINITE score (an inf would turn into NaN when the index is packed in)
-  cnh[k] = k < K ? -0.5f * (n2 + (bias ? bias[k] : 0.0f)) : -3.0e38f;
-  s_max[k] = k < K ? n2 : 0.0f;
-  __syncthreads();
-  if (k == 0) {
-    float m = 0.0f;
-    for (int i = 0; i < TN; ++i) m = fmaxf(m, s_max[i]);
-    *cmax2 = m;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+  if (lane == 0) {
+    // pads: a huge negative FINITE score (an inf would turn into NaN when the index is packed in)
+    cnh[k] = k < K ? -0.5f * (n2 + (bias ? bias[k] : 0.0f)) : -3.0e38f;
+    if (k < K && n2 == n2) atomicMax(reinterpret_cast<int*>(cmax2), __float_as_int(n2));
   }
 }
 
@@ -341,7 +342,8 @@ void tc_assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, 
   if (ws->res.n < n) ws->res.alloc(n);
   if (ws->fb_rows.n < n) ws->fb_rows.alloc(n);
   if (ws->fb_count.n < 1) ws->fb_count.alloc(1);
-  LB2_LAUNCH("tc_prep_centroids", prep_centroids_kernel, 1, TN, 0, cent, K, d, bias, ws->cpad.p,
+  LB2_CUDA(cudaMemsetAsync(ws->cnh.p + TN, 0, sizeof(float), ctx().stream));
+  LB2_LAUNCH("tc_prep_centroids", prep_centroids_kernel, TN / 8, 256, 0, cent, K, d, bias, ws->cpad.p,
              ws->cnh.p, ws->cnh.p + TN);
   LB2_CUDA(cudaMemsetAsync(ws->fb_count.p, 0, sizeof(uint32_t), ctx().stream));
   const CUtensorMap map_x = make_map_2d(x, n, d, TM);

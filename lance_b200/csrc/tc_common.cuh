@@ -17,7 +17,8 @@ constexpr int KC = 32;                   // f32 per 128-byte swizzle row
 constexpr int A_STAGE_BYTES = TM * 128;  // 16 KB
 constexpr int B_CHUNK_BYTES = TN * 128;  // 32 KB
 constexpr int MAX_STAGES = 5;
-constexpr int NUM_THREADS = 256;         // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
+constexpr int NUM_THREADS = 384;         // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 / 8-11: two epilogue groups
+                                         // (group g drains TMEM buffer g, so a tcgen05.ld stall of one group is hidden by the other)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -85,7 +85,7 @@ tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 5);  // MMA commit + 4 epilogue warps (they re-read the operands)
+      mbar_init(empty_bar(s), 9);  // MMA commit + 8 epilogue warps (they re-read the operands)
     }
     mbar_init(b_full, 1);
     for (int b = 0; b < 2; ++b) {
@@ -154,6 +154,7 @@ tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ 
   } else if (warp >= 4) {
     // ===== epilogue =====
     const int q = warp & 3;
+    const uint32_t group = (warp >> 2) - 1;  // 0 or 1: owns TMEM buffer `group`
     const uint8_t* btile = smem + L.b_off;
     mbar_wait(b_full, 0);  // the codebook tile is re-read by the exact re-rank below
     int s = 0;
@@ -170,6 +171,7 @@ tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ 
           if (!((cm >> j) & 1)) continue;
           const int m = kc * 4 + j;
           const uint32_t buf = it & 1;
+          if (buf != group) { ++it; continue; }
           mbar_wait(tfull_bar(buf), (it >> 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * TN;
