@@ -346,11 +346,14 @@ generic_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __re
 template <int METRIC>
 static void assign_dispatch(const float* x, uint64_t n, int d, const float* cent, int K,
                             const float* bias, bool bias_padded, uint32_t* part, float* dist,
-                            uint8_t* valid, float* all_out, const uint8_t* active) {
+                            uint8_t* valid, float* all_out, const uint8_t* active, TcWorkspace* ws) {
   if (n == 0) return;
   if (d % 16 == 0 && d <= 256) {
     const int Kp = (K + 63) / 64 * 64;
-    DevBuf<float> cT((size_t)d * Kp);
+    TcWorkspace local;
+    if (!ws) ws = &local;
+    DevBuf<float>& cT = ws->cT;  // no allocation per call inside a training loop / CUDA graph
+    if (cT.n < (size_t)d * Kp) cT.alloc((size_t)d * Kp);
     LB2_LAUNCH("transpose_centroids", transpose_pad_kernel, cdiv((uint64_t)d * Kp, 256), 256, 0,
                cent, K, d, Kp, cT.get());
     DevBuf<float> biasp;
@@ -393,11 +396,15 @@ static void assign_dispatch(const float* x, uint64_t n, int d, const float* cent
 // exact tile kernel over a device-side row list (count read on the device: no host sync)
 void assign_rows_f32(const float* x, uint64_t n_max, int d, const float* cent, int K, int metric,
                      const float* bias_padded, const uint32_t* row_list, const uint32_t* row_count,
-                     uint32_t* part, float* dist, uint8_t* valid, const uint8_t* active) {
+                     uint32_t* part, float* dist, uint8_t* valid, const uint8_t* active,
+                     TcWorkspace* ws) {
   if (!(d % 16 == 0 && d <= 256) || metric != METRIC_L2)
     fail(LB2_UNSUPPORTED, "assign_rows_f32: shape not supported");
   const int Kp = (K + 63) / 64 * 64;
-  DevBuf<float> cT((size_t)d * Kp);
+  TcWorkspace local;
+  if (!ws) ws = &local;
+  DevBuf<float>& cT = ws->cT;
+  if (cT.n < (size_t)d * Kp) cT.alloc((size_t)d * Kp);
   LB2_LAUNCH("transpose_centroids", transpose_pad_kernel, cdiv((uint64_t)d * Kp, 256), 256, 0, cent,
              K, d, Kp, cT.get());
   const size_t smem = sizeof(float) * (16 * (d + 1) + (size_t)d * 64);
@@ -424,9 +431,9 @@ void assign_f32_ex(const float* x, uint64_t n, int d, const float* cent, int K, 
     return;
   }
   if (metric == METRIC_DOT)
-    assign_dispatch<METRIC_DOT>(x, n, d, cent, K, bias, bias_padded, part, dist, valid, all_out, active);
+    assign_dispatch<METRIC_DOT>(x, n, d, cent, K, bias, bias_padded, part, dist, valid, all_out, active, ws);
   else
-    assign_dispatch<METRIC_L2>(x, n, d, cent, K, bias, bias_padded, part, dist, valid, all_out, active);
+    assign_dispatch<METRIC_L2>(x, n, d, cent, K, bias, bias_padded, part, dist, valid, all_out, active, ws);
 }
 void assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, int metric,
                 const float* bias, uint32_t* part, float* dist, uint8_t* valid, float* all_out) {

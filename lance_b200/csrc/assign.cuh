@@ -15,7 +15,8 @@ void assign_f32_ex(const float* x, uint64_t n, int d, const float* cent, int K, 
 // exact tile kernel restricted to row_list[0 .. *row_count) (both on the device)
 void assign_rows_f32(const float* x, uint64_t n_max, int d, const float* cent, int K, int metric,
                      const float* bias_padded, const uint32_t* row_list, const uint32_t* row_count,
-                     uint32_t* part, float* dist, uint8_t* valid, const uint8_t* active);
+                     uint32_t* part, float* dist, uint8_t* valid, const uint8_t* active,
+                     TcWorkspace* ws);
 // d < 16 path, batched over M sub-spaces; x row stride ldx, sub-space m reads columns [m*ds,(m+1)*ds).
 // codes != NULL -> u8 [n][M] out (PQ encode), else ids/dists/valid [M][n] (PQ training).
 bool small_d_supported(int ds);

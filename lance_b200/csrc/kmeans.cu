@@ -251,7 +251,7 @@ __device__ __forceinline__ uint64_t sm64_next(uint64_t& s) {
 }
 
 __global__ void __launch_bounds__(256)
-epilogue_kernel(int K, int ds, uint64_t n, float bf_param, double tolerance, uint32_t it,
+epilogue_kernel(int K, int ds, uint64_t n, float bf_param, double tolerance,
                 const uint32_t* __restrict__ counts, const double* __restrict__ losses,
                 const float* __restrict__ radius, const uint32_t* __restrict__ last_row,
                 uint64_t* __restrict__ cluster_sizes, float* __restrict__ bias, int bias_ld,
@@ -327,7 +327,7 @@ epilogue_kernel(int K, int ds, uint64_t n, float bf_param, double tolerance, uin
     const float balance_loss =
         __fmul_rn(st.bf_cur, __fsub_rn((float)size_sq, __fdiv_rn((float)(n * n), (float)K)));
     st.last_loss = sum + (double)balance_loss;
-    st.iters = it;
+    st.iters += 1;
   }
   __syncthreads();
   // split_clusters: sequential over empty clusters, vector part by the whole block
@@ -465,8 +465,8 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
   }
   sync_stream();
 
-  for (int it = 1; it <= max_iters; ++it) {
-    // ---- membership (kmeans.rs:317-369) --------------------------------------------------------
+  // one Lloyd iteration = ~18 short kernels: membership, member sort, stats, update, scalar epilogue
+  auto iteration = [&]() {
     if (!small) {
       assign_f32_ex(x, n, ds, centroids, K, metric, bias.p, /*bias_padded=*/true, ids.p, dists.p,
                     valid.p, nullptr, active_d.p, &tcws);
@@ -477,23 +477,59 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
       small_d_assign_f32(x, n, ldx, B, ds, centroids, K, metric, nullptr, nullptr, nullptr, nullptr,
                          ids.p, dists.p, valid.p, active_d.p);
     }
-    // ---- member lists, stats, update, scalar epilogue ------------------------------------------
     ms.run(ids.p, valid.p, n, K, B, active_d.p);
     LB2_LAUNCH("kmeans_stats", stats_kernel, cdiv((uint64_t)BK * 32, 256), 256, 0, dists.p, n, K, B,
                ms.members.p, ms.offsets.p, losses.p, radius.p, last_row.p, active_d.p);
     LB2_LAUNCH("kmeans_update", update_kernel, cdiv(BK * ds, 128), 128, 0, x, ldx, ds, K, B, n,
                ms.members.p, ms.offsets.p, centroids, active_d.p, 1);
     LB2_LAUNCH("kmeans_epilogue", epilogue_kernel, B, 256, 0, K, ds, n, balance_factor_param,
-               tolerance, (uint32_t)it, ms.counts.p, losses.p, radius.p, last_row.p,
-               cluster_sizes.p, small ? nullptr : bias.p, Kp, centroids, states.p, active_d.p);
-    if ((it & 3) == 0 || it == max_iters) {  // poll convergence every 4 iterations
-      d2h(active.data(), active_d.p, B);
-      sync_stream();
-      bool any = false;
-      for (int b = 0; b < B; ++b) any = any || active[b];
-      if (!any) break;
+               tolerance, ms.counts.p, losses.p, radius.p, last_row.p, cluster_sizes.p,
+               small ? nullptr : bias.p, Kp, centroids, states.p, active_d.p);
+  };
+  // The first iteration runs eagerly (allocates every workspace, sets kernel attributes); the
+  // iteration is then captured ONCE into a CUDA graph and replayed, so that the loop is not bound
+  // by ~18 host launches per iteration.  (Event profiling and LB2_TC_STATS need eager launches.)
+  const bool stats_env = getenv("LB2_TC_STATS") && *getenv("LB2_TC_STATS");
+  const bool use_graph = max_iters > 1 && !ctx().profiling && !stats_env &&
+                         !(getenv("LB2_NO_GRAPH") && *getenv("LB2_NO_GRAPH"));
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  uint64_t graph_nodes = 0;
+  auto poll_done = [&]() {
+    d2h(active.data(), active_d.p, B);
+    sync_stream();
+    for (int b = 0; b < B; ++b)
+      if (active[b]) return false;
+    return true;
+  };
+  iteration();
+  bool done = max_iters == 1;
+  if (!done && use_graph) {
+    const uint64_t l0 = ctx().launches;
+    LB2_CUDA(cudaStreamBeginCapture(ctx().stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      iteration();
+    } catch (...) {
+      cudaStreamEndCapture(ctx().stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
     }
+    LB2_CUDA(cudaStreamEndCapture(ctx().stream, &graph));
+    graph_nodes = ctx().launches - l0;
+    ctx().launches = l0;
+    LB2_CUDA(cudaGraphInstantiate(&exec, graph, 0));
   }
+  for (int it = 2; it <= max_iters && !done; ++it) {
+    if (exec) {
+      LB2_CUDA(cudaGraphLaunch(exec, ctx().stream));
+      ctx().launches += graph_nodes;
+    } else {
+      iteration();
+    }
+    if ((it & 3) == 0 || it == max_iters) done = poll_done();  // poll convergence every 4 iterations
+  }
+  if (exec) cudaGraphExecDestroy(exec);
+  if (graph) cudaGraphDestroy(graph);
   d2h(h_states.data(), states.p, B);
   sync_stream();
   if (loss_out) {

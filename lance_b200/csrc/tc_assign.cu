@@ -367,7 +367,7 @@ void tc_assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, 
   }
   // flag-2 rows: exact kernel over the compacted row list (grid sized for the worst case; CTAs
   // beyond the device-side count exit immediately -> no host synchronisation)
-  assign_rows_f32(x, n, d, cent, K, METRIC_L2, bias, ws->fb_rows.p, ws->fb_count.p, part, dist, valid, active);
+  assign_rows_f32(x, n, d, cent, K, METRIC_L2, bias, ws->fb_rows.p, ws->fb_count.p, part, dist, valid, active, ws);
 }
 
 }  // namespace lb2
