@@ -401,14 +401,18 @@ class IvfPqIndex:
         return dict(num_partitions=k.value, dimension=d.value, num_sub_vectors=M.value,
                     num_bits=nb.value, num_rows=n.value)
 
-    def export(self):
+    def export(self, out=None):
+        """lb2_index_export; `out` = dict of preallocated arrays (same keys) to write into."""
         i = self.info()
         K, d, M, n = i["num_partitions"], i["dimension"], i["num_sub_vectors"], i["num_rows"]
-        cent = np.empty((K, d), np.float32)
-        cb = np.empty((M, 256, d // M), np.float32)
-        off = np.empty(K + 1, np.uint64)
-        codes = np.empty((n, M), np.uint8)
-        rid = np.empty(n, np.uint64)
+        if out is not None:
+            cent, cb, off, codes, rid = (out[k] for k in ("centroids", "codebook", "part_offsets", "codes", "row_ids"))
+        else:
+            cent = np.empty((K, d), np.float32)
+            cb = np.empty((M, 256, d // M), np.float32)
+            off = np.empty(K + 1, np.uint64)
+            codes = np.empty((n, M), np.uint8)
+            rid = np.empty(n, np.uint64)
         check(lib().lb2_index_export(self._h, C.c_void_p(cent.ctypes.data), C.c_void_p(cb.ctypes.data),
                                      C.c_void_p(off.ctypes.data), C.c_void_p(codes.ctypes.data),
                                      C.c_void_p(rid.ctypes.data)))

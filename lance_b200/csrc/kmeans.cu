@@ -114,6 +114,84 @@ __global__ void scatter_kernel(const uint32_t* __restrict__ ids, const uint8_t* 
   }
 }
 
+// Small problems (K <= 1024): the whole stable counting sort of one problem in ONE CTA of 32 warps,
+// per-warp histograms and running counters in shared memory (one launch instead of four, no
+// global-memory round trips inside the sequential scatter).
+__global__ void __launch_bounds__(1024)
+block_sort_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ valid, uint64_t n,
+                  int K, uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
+                  uint32_t* __restrict__ members, const uint8_t* __restrict__ active) {
+  const int b = blockIdx.x;
+  if (active && !active[b]) return;
+  extern __shared__ uint32_t sm[];
+  uint32_t* wh = sm;             // [32][K]
+  uint32_t* off = sm + 32 * K;   // [K]
+  __shared__ uint32_t wsum[32];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const uint32_t* idb = ids + (size_t)b * n;
+  const uint8_t* vb = valid ? valid + (size_t)b * n : nullptr;
+  for (int i = tid; i < 32 * K; i += 1024) wh[i] = 0;
+  __syncthreads();
+  const uint64_t chunk = ((n + 31) / 32 + 31) / 32 * 32;  // rows per warp, multiple of 32
+  const uint64_t r0 = (uint64_t)w * chunk, r1 = min(n, r0 + chunk);
+  for (uint64_t r = r0 + lane; r < r1; r += 32)
+    if (!vb || vb[r]) atomicAdd(&wh[w * K + idb[r]], 1u);
+  __syncthreads();
+  // per key: exclusive scan over the 32 warps; per-key totals -> counts; then offsets over keys
+  uint32_t total = 0;
+  if (tid < K) {
+    uint32_t run = 0;
+    for (int ww = 0; ww < 32; ++ww) {
+      const uint32_t t = wh[ww * K + tid];
+      wh[ww * K + tid] = run;
+      run += t;
+    }
+    total = run;
+    counts[(size_t)b * K + tid] = run;
+  }
+  uint32_t incl = total;  // inclusive warp scan of the totals (K <= 1024 -> one key per thread)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t v = wsum[lane], inc2 = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc2, o);
+      if (lane >= o) inc2 += t;
+    }
+    wsum[lane] = inc2 - v;  // exclusive
+  }
+  __syncthreads();
+  const uint32_t excl = wsum[w] + incl - total;
+  if (tid < K) {
+    off[tid] = excl;
+    offsets[(size_t)b * (K + 1) + tid] = excl;
+    if (tid == K - 1) offsets[(size_t)b * (K + 1) + K] = excl + total;
+  }
+  __syncthreads();
+  uint32_t* mem = members + (size_t)b * n;
+  for (uint64_t base = r0; base < r1; base += 32) {
+    const uint64_t r = base + lane;
+    const bool ok = r < r1 && (!vb || vb[r]);
+    const unsigned act = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const uint32_t key = idb[r];
+      const unsigned grp = __match_any_sync(act, key);
+      const int rank = __popc(grp & ((1u << lane) - 1));
+      const uint32_t start = wh[w * K + key];
+      mem[off[key] + start + rank] = (uint32_t)r;
+      __syncwarp(act);
+      if (rank == 0) wh[w * K + key] = start + __popc(grp);
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // ordered centroid update (kmeans.rs:388-418): one thread per (b, cluster, t)
 // ------------------------------------------------------------------------------------------------
@@ -206,6 +284,16 @@ __global__ void gather_init_kernel(const float* __restrict__ x, int ldx, int ds,
 // ------------------------------------------------------------------------------------------------
 void MemberSort::run(const uint32_t* ids, const uint8_t* valid, uint64_t n, int K, int B,
                      const uint8_t* active) {
+  if (K <= 1024 && n <= (1ull << 21) && n >= 1) {
+    if (counts.n < (size_t)B * K) counts.alloc((size_t)B * K);
+    if (offsets.n < (size_t)B * (K + 1)) offsets.alloc((size_t)B * (K + 1));
+    if (members.n < (size_t)B * n) members.alloc((size_t)B * n);
+    const size_t smem = sizeof(uint32_t) * (33 * (size_t)K);
+    set_smem(block_sort_kernel, smem);
+    LB2_LAUNCH("member_sort_block", block_sort_kernel, B, 1024, smem, ids, valid, n, K, counts.p,
+               offsets.p, members.p, active);
+    return;
+  }
   // chunk size: keep the per-chunk histogram table below ~256 MB
   // one warp scatters one chunk sequentially (32 rows per step): keep chunks short so that the
   // grid is wide, but bound the per-chunk histogram table (B * nchunks * K counters) to ~64 MB

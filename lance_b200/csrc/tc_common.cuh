@@ -86,6 +86,49 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 }
 
 
+// tcgen05.wait::ld that also names the destination registers of the load it completes, so the
+// compiler cannot schedule their consumers above the wait
+__device__ __forceinline__ void tmem_wait_ld(uint32_t* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+
+// top-3 (values carry their column index in the low 8 mantissa bits) of one 32-column chunk
+__device__ __forceinline__ void top3_chunk(const uint32_t* v, const float* cn, int c0, float& m1, float& m2,
+                                           float& m3) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float f = __uint_as_float(v[j]) + cn[c0 + j];
+    const float g = __uint_as_float((__float_as_uint(f) & 0xFFFFFF00u) | (uint32_t)(c0 + j));
+    const float t1 = fminf(m1, g);
+    m1 = fmaxf(m1, g);
+    const float t2 = fminf(m2, t1);
+    m2 = fmaxf(m2, t1);
+    m3 = fmaxf(m3, t2);
+  }
+}
+
+// top-3 of a 256-column accumulator row; the TMEM loads are software pipelined (the load of chunk
+// c+1 is in flight while chunk c is reduced)
+__device__ __forceinline__ void top3_row256(uint32_t taddr, const float* cn, float& m1, float& m2, float& m3) {
+  uint32_t va[32], vb[32];
+  tmem_ld32(taddr, va);
+#pragma unroll 1
+  for (int c0 = 0; c0 < TN; c0 += 64) {
+    tmem_wait_ld(va);
+    tmem_ld32(taddr + c0 + 32, vb);
+    top3_chunk(va, cn, c0, m1, m2, m3);
+    tmem_wait_ld(vb);
+    if (c0 + 64 < TN) tmem_ld32(taddr + c0 + 64, va);
+    top3_chunk(vb, cn, c0 + 32, m1, m2, m3);
+  }
+}
+
 }  // namespace tc
 
 // host: 2-D f32 tensor map, box = [32 floats (128 B, SWIZZLE_128B)] x box_rows

@@ -177,22 +177,7 @@ tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ 
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * TN;
           const float* cn = cnh + m * TN;
           float m1 = __int_as_float(0xff800000), m2 = m1, m3 = m1;
-#pragma unroll 1
-          for (int c0 = 0; c0 < TN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(taddr + c0, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-              const float f = __uint_as_float(v[jj]) + cn[c0 + jj];
-              const float g = __uint_as_float((__float_as_uint(f) & 0xFFFFFF00u) | (uint32_t)(c0 + jj));
-              const float t1 = fminf(m1, g);
-              m1 = fmaxf(m1, g);
-              const float t2 = fminf(m2, t1);
-              m2 = fmaxf(m2, t1);
-              m3 = fmaxf(m3, t2);
-            }
-          }
+top3_row256(taddr, cn, m1, m2, m3);
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(buf));
