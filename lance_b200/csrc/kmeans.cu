@@ -134,8 +134,18 @@ block_sort_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ 
   __syncthreads();
   const uint64_t chunk = ((n + 31) / 32 + 31) / 32 * 32;  // rows per warp, multiple of 32
   const uint64_t r0 = (uint64_t)w * chunk, r1 = min(n, r0 + chunk);
-  for (uint64_t r = r0 + lane; r < r1; r += 32)
-    if (!vb || vb[r]) atomicAdd(&wh[w * K + idb[r]], 1u);
+  constexpr uint32_t NONE = 0xffffffffu;
+  for (uint64_t base = r0; base < r1; base += 32 * 8) {  // 8 independent loads in flight per lane
+    uint32_t key[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint64_t r = base + u * 32 + lane;
+      key[u] = (r < r1 && (!vb || vb[r])) ? idb[r] : NONE;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (key[u] != NONE) atomicAdd(&wh[w * K + key[u]], 1u);
+  }
   __syncthreads();
   // per key: exclusive scan over the 32 warps; per-key totals -> counts; then offsets over keys
   uint32_t total = 0;
@@ -175,20 +185,29 @@ block_sort_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ 
   }
   __syncthreads();
   uint32_t* mem = members + (size_t)b * n;
-  for (uint64_t base = r0; base < r1; base += 32) {
-    const uint64_t r = base + lane;
-    const bool ok = r < r1 && (!vb || vb[r]);
-    const unsigned act = __ballot_sync(0xffffffffu, ok);
-    if (ok) {
-      const uint32_t key = idb[r];
-      const unsigned grp = __match_any_sync(act, key);
-      const int rank = __popc(grp & ((1u << lane) - 1));
-      const uint32_t start = wh[w * K + key];
-      mem[off[key] + start + rank] = (uint32_t)r;
-      __syncwarp(act);
-      if (rank == 0) wh[w * K + key] = start + __popc(grp);
+  for (uint64_t base0 = r0; base0 < r1; base0 += 32 * 8) {
+    uint32_t keys[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint64_t r = base0 + u * 32 + lane;
+      keys[u] = (r < r1 && (!vb || vb[r])) ? idb[r] : NONE;
     }
-    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint64_t r = base0 + u * 32 + lane;
+      const uint32_t key = keys[u];
+      const bool ok = key != NONE;
+      const unsigned act = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const unsigned grp = __match_any_sync(act, key);
+        const int rank = __popc(grp & ((1u << lane) - 1));
+        const uint32_t start = wh[w * K + key];
+        mem[off[key] + start + rank] = (uint32_t)r;
+        __syncwarp(act);
+        if (rank == 0) wh[w * K + key] = start + __popc(grp);
+      }
+      __syncwarp();
+    }
   }
 }
 

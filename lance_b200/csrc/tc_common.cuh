@@ -98,18 +98,25 @@ __device__ __forceinline__ void tmem_wait_ld(uint32_t* v) {
                : "memory");
 }
 
-// top-3 (values carry their column index in the low 8 mantissa bits) of one 32-column chunk
-__device__ __forceinline__ void top3_chunk(const uint32_t* v, const float* cn, int c0, float& m1, float& m2,
-                                           float& m3) {
+// insert g into the sorted triple (m1 >= m2 >= m3)
+__device__ __forceinline__ void top3_insert(float g, float& m1, float& m2, float& m3) {
+  const float t1 = fminf(m1, g);
+  m1 = fmaxf(m1, g);
+  const float t2 = fminf(m2, t1);
+  m2 = fmaxf(m2, t1);
+  m3 = fmaxf(m3, t2);
+}
+// top-3 (values carry their column index in the low 8 mantissa bits) of one 32-column chunk,
+// two independent triples (even / odd columns) to halve the dependent FMNMX chains
+__device__ __forceinline__ void top3_chunk(const uint32_t* v, const float* cn, int c0, float* a, float* b) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float f = __uint_as_float(v[j]) + cn[c0 + j];
-    const float g = __uint_as_float((__float_as_uint(f) & 0xFFFFFF00u) | (uint32_t)(c0 + j));
-    const float t1 = fminf(m1, g);
-    m1 = fmaxf(m1, g);
-    const float t2 = fminf(m2, t1);
-    m2 = fmaxf(m2, t1);
-    m3 = fmaxf(m3, t2);
+  for (int j = 0; j < 32; j += 2) {
+    const float f0 = __uint_as_float(v[j]) + cn[c0 + j];
+    const float f1 = __uint_as_float(v[j + 1]) + cn[c0 + j + 1];
+    const float g0 = __uint_as_float((__float_as_uint(f0) & 0xFFFFFF00u) | (uint32_t)(c0 + j));
+    const float g1 = __uint_as_float((__float_as_uint(f1) & 0xFFFFFF00u) | (uint32_t)(c0 + j + 1));
+    top3_insert(g0, a[0], a[1], a[2]);
+    top3_insert(g1, b[0], b[1], b[2]);
   }
 }
 
@@ -117,16 +124,22 @@ __device__ __forceinline__ void top3_chunk(const uint32_t* v, const float* cn, i
 // c+1 is in flight while chunk c is reduced)
 __device__ __forceinline__ void top3_row256(uint32_t taddr, const float* cn, float& m1, float& m2, float& m3) {
   uint32_t va[32], vb[32];
+  const float ninf = __int_as_float(0xff800000);
+  float a[3] = {ninf, ninf, ninf}, b[3] = {ninf, ninf, ninf};
   tmem_ld32(taddr, va);
 #pragma unroll 1
   for (int c0 = 0; c0 < TN; c0 += 64) {
     tmem_wait_ld(va);
     tmem_ld32(taddr + c0 + 32, vb);
-    top3_chunk(va, cn, c0, m1, m2, m3);
+    top3_chunk(va, cn, c0, a, b);
     tmem_wait_ld(vb);
     if (c0 + 64 < TN) tmem_ld32(taddr + c0 + 64, va);
-    top3_chunk(vb, cn, c0 + 32, m1, m2, m3);
+    top3_chunk(vb, cn, c0 + 32, a, b);
   }
+  m1 = a[0]; m2 = a[1]; m3 = a[2];
+  top3_insert(b[0], m1, m2, m3);
+  top3_insert(b[1], m1, m2, m3);
+  top3_insert(b[2], m1, m2, m3);
 }
 
 }  // namespace tc
