@@ -397,7 +397,7 @@ static void assign_dispatch(const float* x, uint64_t n, int d, const float* cent
 void assign_rows_f32(const float* x, uint64_t n_max, int d, const float* cent, int K, int metric,
                      const float* bias_padded, const uint32_t* row_list, const uint32_t* row_count,
                      uint32_t* part, float* dist, uint8_t* valid, const uint8_t* active,
-                     TcWorkspace* ws) {
+                     TcWorkspace* ws, bool cT_ready) {
   if (!(d % 16 == 0 && d <= 256) || metric != METRIC_L2)
     fail(LB2_UNSUPPORTED, "assign_rows_f32: shape not supported");
   const int Kp = (K + 63) / 64 * 64;
@@ -405,8 +405,9 @@ void assign_rows_f32(const float* x, uint64_t n_max, int d, const float* cent, i
   if (!ws) ws = &local;
   DevBuf<float>& cT = ws->cT;
   if (cT.n < (size_t)d * Kp) cT.alloc((size_t)d * Kp);
-  LB2_LAUNCH("transpose_centroids", transpose_pad_kernel, cdiv((uint64_t)d * Kp, 256), 256, 0, cent,
-             K, d, Kp, cT.get());
+  if (!cT_ready)
+    LB2_LAUNCH("transpose_centroids", transpose_pad_kernel, cdiv((uint64_t)d * Kp, 256), 256, 0, cent,
+               K, d, Kp, cT.get());
   const size_t smem = sizeof(float) * (16 * (d + 1) + (size_t)d * 64);
   set_smem(assign_tile_kernel<METRIC_L2, false, 1>, smem);
   LB2_LAUNCH("assign_exact_fallback", (assign_tile_kernel<METRIC_L2, false, 1>), cdiv(n_max, 16), 256,

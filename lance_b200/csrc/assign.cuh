@@ -16,7 +16,7 @@ void assign_f32_ex(const float* x, uint64_t n, int d, const float* cent, int K, 
 void assign_rows_f32(const float* x, uint64_t n_max, int d, const float* cent, int K, int metric,
                      const float* bias_padded, const uint32_t* row_list, const uint32_t* row_count,
                      uint32_t* part, float* dist, uint8_t* valid, const uint8_t* active,
-                     TcWorkspace* ws);
+                     TcWorkspace* ws, bool cT_ready = false);
 // d < 16 path, batched over M sub-spaces; x row stride ldx, sub-space m reads columns [m*ds,(m+1)*ds).
 // codes != NULL -> u8 [n][M] out (PQ encode), else ids/dists/valid [M][n] (PQ training).
 bool small_d_supported(int ds);

@@ -214,11 +214,10 @@ block_sort_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // ordered centroid update (kmeans.rs:388-418): one thread per (b, cluster, t)
 // ------------------------------------------------------------------------------------------------
-__global__ void update_kernel(const float* __restrict__ x, int ldx, int ds, int K, int B, uint64_t n,
+__device__ __forceinline__ void update_body(size_t g, const float* __restrict__ x, int ldx, int ds, int K, int B, uint64_t n,
                               const uint32_t* __restrict__ members,
                               const uint32_t* __restrict__ offsets, float* __restrict__ centroids,
                               const uint8_t* __restrict__ active, int scale) {
-  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (size_t)B * K * ds) return;
   const int b = g / ((size_t)K * ds);
   if (active && !active[b]) return;
@@ -243,12 +242,11 @@ __global__ void update_kernel(const float* __restrict__ x, int ldx, int ds, int 
 }
 
 // per (b, cluster): f64 loss in row order, radius (max), last member row (kmeans.rs:266-280)
-__global__ void stats_kernel(const float* __restrict__ dists, uint64_t n, int K, int B,
+__device__ __forceinline__ void stats_body(int w, const float* __restrict__ dists, uint64_t n, int K, int B,
                              const uint32_t* __restrict__ members,
                              const uint32_t* __restrict__ offsets, double* __restrict__ losses,
                              float* __restrict__ radius, uint32_t* __restrict__ last_row,
                              const uint8_t* __restrict__ active) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= B * K) return;
   const int b = w / K, k = w % K;
@@ -273,6 +271,22 @@ __global__ void stats_kernel(const float* __restrict__ dists, uint64_t n, int K,
     losses[w] = loss;
     radius[w] = rad;
     last_row[w] = e > s ? mem[e - 1] : 0xffffffffu;
+  }
+}
+
+// one launch for both: the first `update_blocks` blocks (128 threads each) run the ordered centroid
+// update, the remaining blocks the per-cluster f64 loss / radius / last-member statistics
+__global__ void __launch_bounds__(128)
+update_stats_kernel(unsigned update_blocks, const float* __restrict__ x, int ldx, int ds, int K, int B,
+                    uint64_t n, const uint32_t* __restrict__ members, const uint32_t* __restrict__ offsets,
+                    float* __restrict__ centroids, const float* __restrict__ dists,
+                    double* __restrict__ losses, float* __restrict__ radius,
+                    uint32_t* __restrict__ last_row, const uint8_t* __restrict__ active) {
+  if (blockIdx.x < update_blocks) {
+    update_body((size_t)blockIdx.x * 128 + threadIdx.x, x, ldx, ds, K, B, n, members, offsets, centroids, active, 1);
+  } else {
+    stats_body((int)(((size_t)(blockIdx.x - update_blocks) * 128 + threadIdx.x) >> 5), dists, n, K, B,
+               members, offsets, losses, radius, last_row, active);
   }
 }
 
@@ -585,10 +599,9 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
                          ids.p, dists.p, valid.p, active_d.p);
     }
     ms.run(ids.p, valid.p, n, K, B, active_d.p);
-    LB2_LAUNCH("kmeans_stats", stats_kernel, cdiv((uint64_t)BK * 32, 256), 256, 0, dists.p, n, K, B,
-               ms.members.p, ms.offsets.p, losses.p, radius.p, last_row.p, active_d.p);
-    LB2_LAUNCH("kmeans_update", update_kernel, cdiv(BK * ds, 128), 128, 0, x, ldx, ds, K, B, n,
-               ms.members.p, ms.offsets.p, centroids, active_d.p, 1);
+    const unsigned ub = cdiv(BK * ds, 128), sb = cdiv((uint64_t)BK * 32, 128);
+    LB2_LAUNCH("kmeans_update_stats", update_stats_kernel, ub + sb, 128, 0, ub, x, ldx, ds, K, B, n,
+               ms.members.p, ms.offsets.p, centroids, dists.p, losses.p, radius.p, last_row.p, active_d.p);
     LB2_LAUNCH("kmeans_epilogue", epilogue_kernel, B, 256, 0, K, ds, n, balance_factor_param,
                tolerance, ms.counts.p, losses.p, radius.p, last_row.p, cluster_sizes.p,
                small ? nullptr : bias.p, Kp, centroids, states.p, active_d.p);

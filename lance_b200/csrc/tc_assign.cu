@@ -51,7 +51,7 @@ __host__ __device__ inline SmemLayout smem_layout(int nkc, int stages) {
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
                  uint64_t n, int nkc, int stages, const float* __restrict__ cnh_g,
-                 const float* __restrict__ row_norm2, const float* __restrict__ cmax2_ptr,
+                 const float* __restrict__ row_norm2, const float* __restrict__ cn2_g,
                  uint32_t* __restrict__ res, const uint8_t* __restrict__ active) {
   if (active && !active[0]) return;
   extern __shared__ uint8_t smem_raw[];
@@ -70,7 +70,15 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t num_tiles = (n + TM - 1) / TM;
 
+  __shared__ float s_cmax2;
   for (int i = threadIdx.x; i < TN; i += NUM_THREADS) cnh[i] = cnh_g[i];
+  if (warp == 3) {  // max_c |c|^2 (the spare warp)
+    float m = 0.0f;
+    for (int i = lane; i < TN; i += 32) m = fmaxf(m, cn2_g[i]);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (lane == 0) s_cmax2 = m;
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar(s), 1);
@@ -102,7 +110,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       uint32_t ph = 0;
       for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int kc = 0; kc < nkc; ++kc) {
-          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_wait_relaxed(empty_bar(s), ph ^ 1);
           mbar_expect_tx(full_bar(s), A_STAGE_BYTES);
           tma_load_2d(sb + L.a_off + s * A_STAGE_BYTES, &map_x, full_bar(s), kc * KC, (int)(tile * TM));
           if (++s == stages) { s = 0; ph ^= 1; }
@@ -122,7 +130,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + buf * TN;
         for (int kc = 0; kc < nkc; ++kc) {
-          mbar_wait(full_bar(s), ph);
+          mbar_wait_relaxed(full_bar(s), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_addr = sb + L.a_off + s * A_STAGE_BYTES;
           const uint32_t b_addr = sb + L.b_off + kc * B_CHUNK_BYTES;
@@ -140,7 +148,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     // ===== epilogue: TMEM -> registers, top-3 per row =====
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const uint32_t group = (warp >> 2) - 1;  // 0 or 1: owns TMEM buffer `group`
-    const float cmax2 = *cmax2_ptr;
+    const float cmax2 = s_cmax2;
     uint32_t it = 0;
     for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1;
@@ -178,14 +186,18 @@ top3_row256(taddr, cnh, m1, m2, m3);
 // cmax2 = max_k |c_k|^2 (plain f32; any rounding is inside the error budget)
 __global__ void prep_centroids_kernel(const float* __restrict__ c, int K, int d,
                                       const float* __restrict__ bias, float* __restrict__ cpad,
-                                      float* __restrict__ cnh, float* __restrict__ cmax2) {
-  // grid = TN/8 blocks of 256 threads: one warp per centroid row (coalesced), cmax2 by atomicMax on
-  // the bit pattern (norms are >= 0 so the integer order equals the float order)
+                                      float* __restrict__ cnh, float* __restrict__ cn2,
+                                      float* __restrict__ cT, int Kp, uint32_t* __restrict__ fb_count) {
+  // grid = TN/8 blocks of 256 threads: one warp per (padded) centroid row.  Also writes the
+  // transposed NaN-padded copy cT[e][Kp] used by the exact fallback kernel and resets the
+  // fallback-row counter, so one launch prepares everything the iteration needs.
   const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *fb_count = 0;
   float n2 = 0.0f;
   for (int e = lane; e < d; e += 32) {
     const float v = k < K ? c[(size_t)k * d + e] : 0.0f;
     cpad[(size_t)k * d + e] = v;
+    if (k < Kp) cT[(size_t)e * Kp + k] = k < K ? v : __int_as_float(0x7fc00000);
     n2 += v * v;
   }
 #pragma unroll
@@ -193,7 +205,7 @@ __global__ void prep_centroids_kernel(const float* __restrict__ c, int K, int d,
   if (lane == 0) {
     // pads: a huge negative FINITE score (an inf would turn into NaN when the index is packed in)
     cnh[k] = k < K ? -0.5f * (n2 + (bias ? bias[k] : 0.0f)) : -3.0e38f;
-    if (k < K && n2 == n2) atomicMax(reinterpret_cast<int*>(cmax2), __float_as_int(n2));
+    cn2[k] = (k < K && n2 == n2) ? n2 : 0.0f;
   }
 }
 
@@ -317,7 +329,9 @@ void tc_assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, 
   TcWorkspace local;
   if (!ws) ws = &local;
   if (ws->cpad.n < (size_t)TN * d) ws->cpad.alloc((size_t)TN * d);
-  if (ws->cnh.n < TN + 1) ws->cnh.alloc(TN + 1);
+  if (ws->cnh.n < 2 * TN) ws->cnh.alloc(2 * TN);
+  const int Kp = (K + 63) / 64 * 64;
+  if (ws->cT.n < (size_t)d * Kp) ws->cT.alloc((size_t)d * Kp);
   if (ws->row_norm2.n < n || ws->norm_src != x || ws->norm_n != n) {
     if (ws->row_norm2.n < n) ws->row_norm2.alloc(n);
     LB2_LAUNCH("tc_row_norms", row_norm_kernel, cdiv(n * 16, 256), 256, 0, x, n, d, ws->row_norm2.p);
@@ -327,10 +341,8 @@ void tc_assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, 
   if (ws->res.n < n) ws->res.alloc(n);
   if (ws->fb_rows.n < n) ws->fb_rows.alloc(n);
   if (ws->fb_count.n < 1) ws->fb_count.alloc(1);
-  LB2_CUDA(cudaMemsetAsync(ws->cnh.p + TN, 0, sizeof(float), ctx().stream));
   LB2_LAUNCH("tc_prep_centroids", prep_centroids_kernel, TN / 8, 256, 0, cent, K, d, bias, ws->cpad.p,
-             ws->cnh.p, ws->cnh.p + TN);
-  LB2_CUDA(cudaMemsetAsync(ws->fb_count.p, 0, sizeof(uint32_t), ctx().stream));
+             ws->cnh.p, ws->cnh.p + TN, ws->cT.p, Kp, ws->fb_count.p);
   const CUtensorMap map_x = make_map_2d(x, n, d, TM);
   const CUtensorMap map_c = make_map_2d(ws->cpad.p, TN, d, TN);
   const uint64_t tiles = (n + TM - 1) / TM;
@@ -352,7 +364,8 @@ void tc_assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, 
   }
   // flag-2 rows: exact kernel over the compacted row list (grid sized for the worst case; CTAs
   // beyond the device-side count exit immediately -> no host synchronisation)
-  assign_rows_f32(x, n, d, cent, K, METRIC_L2, bias, ws->fb_rows.p, ws->fb_count.p, part, dist, valid, active, ws);
+  assign_rows_f32(x, n, d, cent, K, METRIC_L2, bias, ws->fb_rows.p, ws->fb_count.p, part, dist, valid, active, ws,
+                  /*cT_ready=*/true);
 }
 
 }  // namespace lb2

@@ -44,6 +44,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+// same, for the single-thread producer / issuer roles: back off between polls so that the spin
+// loop does not steal issue slots from the epilogue warps sharing the scheduler
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(40);
+  }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
                                             int c0, int c1) {
   asm volatile(
@@ -106,36 +122,54 @@ __device__ __forceinline__ void top3_insert(float g, float& m1, float& m2, float
   m2 = fmaxf(m2, t1);
   m3 = fmaxf(m3, t2);
 }
-// top-3 (values carry their column index in the low 8 mantissa bits) of one 32-column chunk,
-// two independent triples (even / odd columns) to halve the dependent FMNMX chains
-__device__ __forceinline__ void top3_chunk(const uint32_t* v, const float* cn, int c0, float* a, float* b) {
+// insert TWO values into the triple with 9 min/max ops (FMNMX / FMNMX3 run on the half-rate ALU
+// pipe, which is what bounds this epilogue): sort the pair, then merge (hi >= lo) into (m1,m2,m3)
+__device__ __forceinline__ void top3_insert2(float g0, float g1, float& m1, float& m2, float& m3) {
+  const float hi = fmaxf(g0, g1), lo = fminf(g0, g1);
+  const float a = fminf(m1, hi);          // loser of the top comparison
+  const float bq = fmaxf(m2, lo);
+  const float c = fminf(m2, lo);
+  m1 = fmaxf(m1, hi);
+  m2 = fmaxf(a, bq);
+  m3 = fmaxf(fmaxf(m3, fminf(a, bq)), c);  // -> FMNMX3
+}
+// top-3 (values carry their column index in the low 8 mantissa bits) of one 32-column chunk.
+// C0 is a compile-time constant so that the index OR-ed into the mantissa is an immediate.
+template <int C0>
+__device__ __forceinline__ void top3_chunk(const uint32_t* v, const float* cn, float* a, float* b) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    const float f0 = __uint_as_float(v[j]) + cn[c0 + j];
-    const float f1 = __uint_as_float(v[j + 1]) + cn[c0 + j + 1];
-    const float g0 = __uint_as_float((__float_as_uint(f0) & 0xFFFFFF00u) | (uint32_t)(c0 + j));
-    const float g1 = __uint_as_float((__float_as_uint(f1) & 0xFFFFFF00u) | (uint32_t)(c0 + j + 1));
-    top3_insert(g0, a[0], a[1], a[2]);
-    top3_insert(g1, b[0], b[1], b[2]);
+  for (int j = 0; j < 32; j += 4) {
+    float g[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float f = __uint_as_float(v[j + u]) + cn[C0 + j + u];
+      // replace the low mantissa byte by the column index: one PRMT (byte permute) with an immediate
+      g[u] = __uint_as_float(__byte_perm(__float_as_uint(f), (uint32_t)(C0 + j + u), 0x3214));
+    }
+    top3_insert2(g[0], g[1], a[0], a[1], a[2]);  // two independent triples -> shorter dependent chains
+    top3_insert2(g[2], g[3], b[0], b[1], b[2]);
   }
 }
 
 // top-3 of a 256-column accumulator row; the TMEM loads are software pipelined (the load of chunk
-// c+1 is in flight while chunk c is reduced)
+// c+1 is in flight while chunk c is reduced); fully unrolled over the 8 chunks
 __device__ __forceinline__ void top3_row256(uint32_t taddr, const float* cn, float& m1, float& m2, float& m3) {
   uint32_t va[32], vb[32];
   const float ninf = __int_as_float(0xff800000);
   float a[3] = {ninf, ninf, ninf}, b[3] = {ninf, ninf, ninf};
   tmem_ld32(taddr, va);
-#pragma unroll 1
-  for (int c0 = 0; c0 < TN; c0 += 64) {
-    tmem_wait_ld(va);
-    tmem_ld32(taddr + c0 + 32, vb);
-    top3_chunk(va, cn, c0, a, b);
-    tmem_wait_ld(vb);
-    if (c0 + 64 < TN) tmem_ld32(taddr + c0 + 64, va);
-    top3_chunk(vb, cn, c0 + 32, a, b);
-  }
+#define LB2_TOP3_STEP(C)                                   \
+  tmem_wait_ld(va);                                        \
+  tmem_ld32(taddr + (C) + 32, vb);                         \
+  top3_chunk<(C)>(va, cn, a, b);                           \
+  tmem_wait_ld(vb);                                        \
+  if ((C) + 64 < TN) tmem_ld32(taddr + (C) + 64, va);      \
+  top3_chunk<(C) + 32>(vb, cn, a, b);
+  LB2_TOP3_STEP(0)
+  LB2_TOP3_STEP(64)
+  LB2_TOP3_STEP(128)
+  LB2_TOP3_STEP(192)
+#undef LB2_TOP3_STEP
   m1 = a[0]; m2 = a[1]; m3 = a[2];
   top3_insert(b[0], m1, m2, m3);
   top3_insert(b[1], m1, m2, m3);

@@ -116,7 +116,7 @@ tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ 
       for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int kc = 0; kc < nkc; ++kc) {
           if (((act_mask >> (kc * 4)) & 0xF) == 0) continue;  // chunk with no active sub-space
-          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_wait_relaxed(empty_bar(s), ph ^ 1);
           mbar_expect_tx(full_bar(s), A_STAGE_BYTES);
           tma_load_2d(sb + L.a_off + s * A_STAGE_BYTES, &map_r, full_bar(s), kc * KC, (int)(tile * TM));
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -133,7 +133,7 @@ tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ 
         for (int kc = 0; kc < nkc; ++kc) {
           const uint32_t cm = (act_mask >> (kc * 4)) & 0xF;
           if (cm == 0) continue;
-          mbar_wait(full_bar(s), ph);
+          mbar_wait_relaxed(full_bar(s), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_addr = sb + L.a_off + s * A_STAGE_BYTES;
           const uint32_t b_addr = sb + L.b_off + kc * B_CHUNK_BYTES;
@@ -244,9 +244,11 @@ teardown:
 
 // Bm[c][m*8+t] = cb[m][c][t];  cnh[m][c] = -|cb[m][c]|^2 / 2;  cbmax2[m] = max_c |cb[m][c]|^2
 __global__ void prep_codebook_kernel(const float* __restrict__ cb, int M, int d, float* __restrict__ bm,
-                                     float* __restrict__ cnh, float* __restrict__ cbmax2) {
+                                     float* __restrict__ cnh, float* __restrict__ cbmax2,
+                                     uint32_t* __restrict__ fb_count) {
   __shared__ float s_n2[TN];
   const int m = blockIdx.x, c = threadIdx.x;  // grid M, block 256
+  if (m == 0 && c == 0) *fb_count = 0;
   const float* src = cb + ((size_t)m * TN + c) * DS;
   float n2 = 0.0f;
 #pragma unroll
@@ -352,8 +354,9 @@ void tc_pq_prepare(const float* codebook, int M, int d, TcPqWorkspace* ws) {
   using namespace tcpq;
   if (ws->bm.n < (size_t)tc::TN * d) ws->bm.alloc((size_t)tc::TN * d);
   if (ws->cnh.n < (size_t)M * tc::TN + M) ws->cnh.alloc((size_t)M * tc::TN + M);
+  if (ws->fb_count.n < 1) ws->fb_count.alloc(1);
   LB2_LAUNCH("tc_pq_prep_codebook", prep_codebook_kernel, M, tc::TN, 0, codebook, M, d, ws->bm.p,
-             ws->cnh.p, ws->cnh.p + (size_t)M * tc::TN);
+             ws->cnh.p, ws->cnh.p + (size_t)M * tc::TN, ws->fb_count.p);
 }
 
 // r: residual (or raw) vectors [n][d] with their per-sub-space norms rn2 [n][M] already computed
@@ -365,10 +368,8 @@ void tc_pq_assign(const float* r, const float* rn2, uint64_t n, int d, int M, co
   const Layout L = layout(nkc, M);
   const size_t smem = L.total + 1024;
   if (smem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "tc_pq: shared memory");
-  tc_pq_prepare(codebook, M, d, ws);
+  tc_pq_prepare(codebook, M, d, ws);  // also resets the fallback-pair counter
   if (ws->fb_pairs.n < n * M) ws->fb_pairs.alloc(n * M);
-  if (ws->fb_count.n < 1) ws->fb_count.alloc(1);
-  LB2_CUDA(cudaMemsetAsync(ws->fb_count.p, 0, sizeof(uint32_t), ctx().stream));
   const CUtensorMap map_r = make_map_2d(r, n, d, tc::TM);
   const CUtensorMap map_b = make_map_2d(ws->bm.p, tc::TN, d, tc::TN);
   const uint64_t tiles = (n + tc::TM - 1) / tc::TM;
