@@ -85,6 +85,19 @@ __global__ void offsets_kernel(const uint32_t* __restrict__ counts, int K,
   }
 }
 
+// lanes of `act` that hold the same key as this lane.  (__match_any_sync gives the same mask but
+// the MATCH unit is slow -- ~100 cycles per warp-wide call and not pipelined across warps, measured
+// with ncu on the single-CTA sort -- while a ballot per key bit is a handful of cycles.)
+__device__ __forceinline__ unsigned same_key_mask(unsigned act, uint32_t key, int nbits) {
+  unsigned grp = act;
+  for (int bit = 0; bit < nbits; ++bit) {
+    const bool one = (key >> bit) & 1u;
+    const unsigned bal = __ballot_sync(act, one);
+    grp &= one ? bal : ~bal;
+  }
+  return grp;
+}
+
 // one warp per (chunk, b): rows in ascending order, rank inside a batch of 32 by match_any
 __global__ void scatter_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ valid,
                                uint64_t n, int K, int chunk_rows, uint32_t* __restrict__ chunk_hist,
@@ -93,6 +106,7 @@ __global__ void scatter_kernel(const uint32_t* __restrict__ ids, const uint8_t* 
   const int b = blockIdx.y;
   if (active && !active[b]) return;
   const int lane = threadIdx.x;
+  const int nbits = 32 - __clz(max(K - 1, 1));
   const uint64_t r0 = (uint64_t)blockIdx.x * chunk_rows;
   const uint64_t r1 = min(n, r0 + (uint64_t)chunk_rows);
   uint32_t* h = chunk_hist + ((size_t)b * gridDim.x + blockIdx.x) * K;
@@ -103,7 +117,7 @@ __global__ void scatter_kernel(const uint32_t* __restrict__ ids, const uint8_t* 
     const unsigned act = __ballot_sync(0xffffffffu, ok);
     if (ok) {
       const uint32_t key = ids[(size_t)b * n + r];
-      const unsigned grp = __match_any_sync(act, key);
+      const unsigned grp = same_key_mask(act, key, nbits);
       const int rank = __popc(grp & ((1u << lane) - 1));
       const uint32_t start = h[key];
       members[(size_t)b * n + off[key] + start + rank] = (uint32_t)r;
@@ -185,6 +199,7 @@ block_sort_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ 
   }
   __syncthreads();
   uint32_t* mem = members + (size_t)b * n;
+  const int nbits = 32 - __clz(max(K - 1, 1));
   for (uint64_t base0 = r0; base0 < r1; base0 += 32 * 8) {
     uint32_t keys[8];
 #pragma unroll
@@ -199,7 +214,7 @@ block_sort_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ 
       const bool ok = key != NONE;
       const unsigned act = __ballot_sync(0xffffffffu, ok);
       if (ok) {
-        const unsigned grp = __match_any_sync(act, key);
+        const unsigned grp = same_key_mask(act, key, nbits);
         const int rank = __popc(grp & ((1u << lane) - 1));
         const uint32_t start = wh[w * K + key];
         mem[off[key] + start + rank] = (uint32_t)r;
