@@ -13,6 +13,8 @@
 // and let one thread per (cluster, dimension) add its members in that order.  Given the same
 // initial centroids the trained model is therefore BIT-IDENTICAL to the reference loop (checked
 // against the oracle), at the cost of a sort of n 4-byte keys per iteration.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cmath>
 #include <limits>
@@ -128,27 +130,34 @@ __global__ void scatter_kernel(const uint32_t* __restrict__ ids, const uint8_t* 
   }
 }
 
-// Small problems (K <= 1024): the whole stable counting sort of one problem in ONE CTA of 32 warps,
-// per-warp histograms and running counters in shared memory (one launch instead of four, no
-// global-memory round trips inside the sequential scatter).
-__global__ void __launch_bounds__(1024)
-block_sort_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ valid, uint64_t n,
-                  int K, uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
-                  uint32_t* __restrict__ members, const uint8_t* __restrict__ active) {
-  const int b = blockIdx.x;
-  if (active && !active[b]) return;
+// Small problems (K <= 1024): the whole stable counting sort of one problem in ONE launch by a
+// thread-block CLUSTER of 8 CTAs x 32 warps: every warp owns a contiguous chunk of rows, per-warp
+// histograms and running counters live in shared memory, and the cross-CTA prefix is read through
+// distributed shared memory between two cluster barriers (no global-memory round trips, no MATCH).
+constexpr int SORT_CLUSTER = 8;
+__global__ void __cluster_dims__(SORT_CLUSTER, 1, 1) __launch_bounds__(1024)
+cluster_sort_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ valid, uint64_t n,
+                    int K, uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
+                    uint32_t* __restrict__ members, const uint8_t* __restrict__ active) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int b = blockIdx.y;
+  if (active && !active[b]) return;  // uniform over the cluster
+  const unsigned crank = cluster.block_rank();
   extern __shared__ uint32_t sm[];
-  uint32_t* wh = sm;             // [32][K]
-  uint32_t* off = sm + 32 * K;   // [K]
+  uint32_t* wh = sm;             // [32][K] per-warp histogram, then running counters
+  uint32_t* tot = sm + 32 * K;   // [K]     this CTA's per-key total (read by the other CTAs)
+  uint32_t* off = tot + K;       // [K]     first output slot of this CTA's rows, per key
   __shared__ uint32_t wsum[32];
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const uint32_t* idb = ids + (size_t)b * n;
   const uint8_t* vb = valid ? valid + (size_t)b * n : nullptr;
   for (int i = tid; i < 32 * K; i += 1024) wh[i] = 0;
   __syncthreads();
-  const uint64_t chunk = ((n + 31) / 32 + 31) / 32 * 32;  // rows per warp, multiple of 32
-  const uint64_t r0 = (uint64_t)w * chunk, r1 = min(n, r0 + chunk);
   constexpr uint32_t NONE = 0xffffffffu;
+  const uint64_t nwarps = 32ull * SORT_CLUSTER;
+  const uint64_t chunk = ((n + nwarps - 1) / nwarps + 31) / 32 * 32;  // rows per warp, multiple of 32
+  const uint64_t r0 = min(n, ((uint64_t)crank * 32 + w) * chunk), r1 = min(n, r0 + chunk);
   for (uint64_t base = r0; base < r1; base += 32 * 8) {  // 8 independent loads in flight per lane
     uint32_t key[8];
 #pragma unroll
@@ -161,19 +170,25 @@ block_sort_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ 
       if (key[u] != NONE) atomicAdd(&wh[w * K + key[u]], 1u);
   }
   __syncthreads();
-  // per key: exclusive scan over the 32 warps; per-key totals -> counts; then offsets over keys
-  uint32_t total = 0;
-  if (tid < K) {
+  if (tid < K) {  // exclusive scan over this CTA's 32 warps
     uint32_t run = 0;
     for (int ww = 0; ww < 32; ++ww) {
       const uint32_t t = wh[ww * K + tid];
       wh[ww * K + tid] = run;
       run += t;
     }
-    total = run;
-    counts[(size_t)b * K + tid] = run;
+    tot[tid] = run;
   }
-  uint32_t incl = total;  // inclusive warp scan of the totals (K <= 1024 -> one key per thread)
+  cluster.sync();
+  uint32_t total = 0, before = 0;  // over all CTAs / over the preceding CTAs, for key `tid`
+  if (tid < K) {
+    for (unsigned c = 0; c < SORT_CLUSTER; ++c) {
+      const uint32_t t = cluster.map_shared_rank(tot, c)[tid];
+      total += t;
+      if (c < crank) before += t;
+    }
+  }
+  uint32_t incl = total;  // inclusive scan of the per-key totals over the block (K <= 1024)
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -193,9 +208,12 @@ block_sort_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ 
   __syncthreads();
   const uint32_t excl = wsum[w] + incl - total;
   if (tid < K) {
-    off[tid] = excl;
-    offsets[(size_t)b * (K + 1) + tid] = excl;
-    if (tid == K - 1) offsets[(size_t)b * (K + 1) + K] = excl + total;
+    off[tid] = excl + before;
+    if (crank == 0) {
+      counts[(size_t)b * K + tid] = total;
+      offsets[(size_t)b * (K + 1) + tid] = excl;
+      if (tid == K - 1) offsets[(size_t)b * (K + 1) + K] = excl + total;
+    }
   }
   __syncthreads();
   uint32_t* mem = members + (size_t)b * n;
@@ -224,6 +242,7 @@ block_sort_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ 
       __syncwarp();
     }
   }
+  cluster.sync();  // nobody leaves while a neighbour may still read its `tot`
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -336,10 +355,10 @@ void MemberSort::run(const uint32_t* ids, const uint8_t* valid, uint64_t n, int 
     if (counts.n < (size_t)B * K) counts.alloc((size_t)B * K);
     if (offsets.n < (size_t)B * (K + 1)) offsets.alloc((size_t)B * (K + 1));
     if (members.n < (size_t)B * n) members.alloc((size_t)B * n);
-    const size_t smem = sizeof(uint32_t) * (33 * (size_t)K);
-    set_smem(block_sort_kernel, smem);
-    LB2_LAUNCH("member_sort_block", block_sort_kernel, B, 1024, smem, ids, valid, n, K, counts.p,
-               offsets.p, members.p, active);
+    const size_t smem = sizeof(uint32_t) * (34 * (size_t)K);
+    set_smem(cluster_sort_kernel, smem);
+    LB2_LAUNCH("member_sort_cluster", cluster_sort_kernel, dim3(SORT_CLUSTER, B), 1024, smem, ids,
+               valid, n, K, counts.p, offsets.p, members.p, active);
     return;
   }
   // chunk size: keep the per-chunk histogram table below ~256 MB
