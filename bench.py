@@ -93,7 +93,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # synthetic data on the device (same law as lance_b200/synth.py:sift_like)
 # ------------------------------------------------------------------------------------------------
-def device_dataset(torch, n, nq, seed, device):
+def device_dataset(torch, n, nq, seed, device, qseed=99):
     from lance_b200 import synth
     W, cm = synth.sift_model(DIM, 24, 1024, 1234)
     W, cm = torch.from_numpy(W).to(device), torch.from_numpy(cm).to(device)
@@ -111,7 +111,9 @@ def device_dataset(torch, n, nq, seed, device):
             out[s:e] = torch.clamp(torch.round(x), 0.0, 255.0)
         return out
 
-    return draw(n), draw(nq)
+    data = draw(n)
+    g.manual_seed(qseed)  # the same queries on every rank
+    return data, draw(nq)
 
 
 def ground_truth(torch, data, queries, k):
@@ -268,6 +270,8 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+        from lance_b200 import parallel
+        parallel.init_comm(dist)  # NCCL all-reduce of centroid sums inside the k-means loops
 
     def barrier():
         if world > 1:
@@ -285,12 +289,12 @@ def main():
     n = args.rows
     # each rank owns an independent shard of n rows (weak scaling: no data-path collective)
     data_t, queries_t = device_dataset(torch, n, NQ, 1000 + rank, device)
-    data_dev = lb.DeviceArray.__new__(lb.DeviceArray)
-    data_dev.shape, data_dev.dtype, data_dev.ptr, data_dev.nbytes = (n, DIM), np.dtype(np.float32), data_t.data_ptr(), n * DIM * 4
-    data_dev.free = lambda: None
-    q_dev = lb.DeviceArray.__new__(lb.DeviceArray)
-    q_dev.shape, q_dev.dtype, q_dev.ptr, q_dev.nbytes = (NQ, DIM), np.dtype(np.float32), queries_t.data_ptr(), NQ * DIM * 4
-    q_dev.free = lambda: None
+    def wrap(t, dtype):
+        a = lb.DeviceArray.__new__(lb.DeviceArray)
+        a.shape, a.dtype, a.ptr, a.nbytes = tuple(t.shape), np.dtype(dtype), t.data_ptr(), t.numel() * t.element_size()
+        a.free = lambda: None
+        return a
+    data_dev, q_dev = wrap(data_t, np.float32), wrap(queries_t, np.float32)
     params = lb.IvfBuildParams(num_partitions=NUM_PARTITIONS, num_sub_vectors=NUM_SUB_VECTORS, seed=7)
 
     # ---- resident build: W warm-up, K timed ----------------------------------------------------
@@ -375,17 +379,38 @@ def main():
 
     # ---- query: QPS @ recall@10 ------------------------------------------------------------------
     ix = lb.IvfPqIndex.build(data_dev, "l2", params)
-    ids_dev = lb.DeviceArray((NQ, TOPK), np.uint64)
-    d_dev = lb.DeviceArray((NQ, TOPK), np.float32)
-    for _ in range(max(args.warmup, 1)):
+    ids_t = torch.empty((NQ, TOPK), dtype=torch.int64, device=device)
+    d_t = torch.empty((NQ, TOPK), dtype=torch.float32, device=device)
+    ids_dev, d_dev = wrap(ids_t, np.uint64), wrap(d_t, np.float32)
+    row_base = rank * n  # global row id of this shard's first row
+
+    def sharded_search():
+        """every rank scans its shard for all queries; candidates are all-gathered and merged by
+        (distance, row id) like the reference's final SortExec"""
         ix.search(q_dev, TOPK, NPROBES, out=(ids_dev, d_dev))
+        if world == 1:
+            return ids_t, d_t
+        gi = [torch.empty_like(ids_t) for _ in range(world)]
+        gd = [torch.empty_like(d_t) for _ in range(world)]
+        dist.all_gather(gi, ids_t + row_base)
+        dist.all_gather(gd, d_t)
+        ai, ad = torch.cat(gi, 1), torch.cat(gd, 1)
+        o1 = torch.argsort(ai, dim=1, stable=True)
+        ai, ad = torch.gather(ai, 1, o1), torch.gather(ad, 1, o1)
+        o2 = torch.argsort(ad, dim=1, stable=True)[:, :TOPK]
+        return torch.gather(ai, 1, o2), torch.gather(ad, 1, o2)
+    for _ in range(max(args.warmup, 1)):
+        sharded_search()
     barrier()
     lb.profile.reset()
     lb.profile.enable(True)
     lb.timer_start()
+    tq0 = time.perf_counter()
     for _ in range(args.steps):
-        ix.search(q_dev, TOPK, NPROBES, out=(ids_dev, d_dev))
-    q_ms = max_over_ranks(lb.timer_stop() / args.steps)
+        merged_ids, merged_d = sharded_search()
+    q_ms_dev = lb.timer_stop() / args.steps
+    barrier()
+    q_ms = max_over_ranks(q_ms_dev if world == 1 else (time.perf_counter() - tq0) * 1e3 / args.steps)
     lb.profile.enable(False)
     scan_cnt, scan_ms = lb.profile.get("search:pq_scan")
     q_host = queries_t.cpu().numpy()
@@ -395,11 +420,15 @@ def main():
     for _ in range(args.steps):
         ids_h, d_h = ix.search(q_host, TOPK, NPROBES)
     q_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
-    gt = ground_truth(torch, data_t, queries_t[:1000], TOPK)
-    recall = float(np.mean([len(set(ids_h[i].tolist()) & set(gt[i].tolist())) / TOPK for i in range(1000)]))
+    if world == 1:
+        gt = ground_truth(torch, data_t, queries_t[:1000], TOPK)
+        recall = float(np.mean([len(set(ids_h[i].tolist()) & set(gt[i].tolist())) / TOPK for i in range(1000)]))
+    else:
+        recall = None  # the merged result spans world x n rows; recall is reported at N=1
     scan_bytes = NQ * NPROBES * (n / NUM_PARTITIONS) * NUM_SUB_VECTORS + NQ * DIM * 4
     scan_launch_ms = scan_ms / max(scan_cnt, 1)
-    query = {"qps": world * NQ / (q_ms * 1e-3), "e2e_qps": world * NQ / (q_e2e_ms * 1e-3), "recall_at_10": recall,
+    query = {"qps": NQ / (q_ms * 1e-3), "e2e_qps": NQ / (q_e2e_ms * 1e-3), "recall_at_10": recall,
+             "indexed_rows": world * n,
              "nprobes": NPROBES, "k": TOPK, "batch": NQ, "refine_factor": None, "ms_per_batch": q_ms,
              "roofline": {"kernel": "search:pq_scan", "bound": "hbm", "achieved": scan_bytes / (scan_launch_ms * 1e-3) / 1e9,
                           "peak": hbm_peak, "unit": "GB/s", "frac": scan_bytes / (scan_launch_ms * 1e-3) / 1e9 / hbm_peak,
@@ -427,7 +456,7 @@ def main():
             "metric": "ivf_pq_index_build_mvec_per_s", "value": value, "unit": "Mvec/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rows_per_gpu": n, "sharding": "independent index shard per GPU (no data-path collective)",
+            "config": {"workload": WORKLOAD, "rows_per_gpu": n, "sharding": "row shard per GPU; k-means sums all-reduced over NCCL each iteration (one global IVF/PQ model); transform + search local, candidates all-gathered",
                        "cache": "inputs (512 MB) larger than L2 (126 MB)", "k": TOPK, "nprobes": NPROBES},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "build_phases_ms": {"ivf_train": stats.ms_ivf_train, "pq_train": stats.ms_pq_train, "transform": stats.ms_transform,

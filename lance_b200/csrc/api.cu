@@ -2,9 +2,9 @@
 // context, the device-resident index handle and the whole-index builder.
 #include <algorithm>
 #include <cmath>
-#include <unordered_set>
 
 #include "assign.cuh"
+#include "comm.cuh"
 #include "common.cuh"
 #include "exact.cuh"
 #include "kmeans.cuh"
@@ -175,7 +175,9 @@ static void index_load_dev(lb2_index* ix, const uint32_t* part_ids, const uint8_
   sync_stream();
 }
 
-// s distinct rows out of n, ascending (Floyd's algorithm; our rng)
+// s distinct rows out of n, ascending: one uniformly random row from each of s equal strata
+// (the reference draws a random subset through Dataset::sample, rust/lance/src/index/vector/utils.rs:
+// 202-209, with an unseeded rng -> the selection is unpinned; ours is O(s), seeded, already sorted)
 static std::vector<uint64_t> sample_rows(uint64_t n, uint64_t s, uint64_t seed) {
   std::vector<uint64_t> out;
   if (s >= n) {
@@ -184,14 +186,11 @@ static std::vector<uint64_t> sample_rows(uint64_t n, uint64_t s, uint64_t seed) 
     return out;
   }
   SplitMix64 rng(seed);
-  std::unordered_set<uint64_t> chosen;
-  chosen.reserve(s * 2);
-  for (uint64_t j = n - s; j < n; ++j) {
-    uint64_t t = rng.next() % (j + 1);
-    if (!chosen.insert(t).second) chosen.insert(j);
+  out.resize(s);
+  for (uint64_t i = 0; i < s; ++i) {
+    const uint64_t lo = (unsigned __int128)i * n / s, hi = (unsigned __int128)(i + 1) * n / s;
+    out[i] = lo + rng.next() % (hi - lo);
   }
-  out.assign(chosen.begin(), chosen.end());
-  std::sort(out.begin(), out.end());
   return out;
 }
 
@@ -200,10 +199,12 @@ static void pq_train_dev(const float* data, uint64_t n, int d, int metric, const
   const int M = p->num_sub_vectors, K = 1 << p->num_bits;
   LB2_REQUIRE(M > 0 && d % M == 0, "num_sub_vectors must divide vector dimension %d, but got %d", d, M);
   if (p->num_bits != 8) fail(LB2_UNSUPPORTED, "num_bits %u is not implemented on the device", p->num_bits);
-  LB2_REQUIRE(n >= (uint64_t)K, "Not enough rows to train PQ. Requires %d rows but only %llu available",
+  LB2_REQUIRE(current_comm() || n >= (uint64_t)K, "Not enough rows to train PQ. Requires %d rows but only %llu available",
               K, (unsigned long long)n);
-  // free fn train_kmeans (kmeans.rs:1328-1340): first sample_rate*k rows
-  const uint64_t rows = n > p->sample_rate * K ? p->sample_rate * K : n;
+  // free fn train_kmeans (kmeans.rs:1328-1340): first sample_rate*k rows (per-rank share when sharded)
+  const uint64_t nranks = current_comm() ? current_comm()->nranks : 1;
+  const uint64_t cap = (p->sample_rate * K + nranks - 1) / nranks;
+  const uint64_t rows = n > cap ? cap : n;
   InArg<float> init(p->codebook, (size_t)M * K * (d / M));
   lloyd_train(data, rows, d, M, d / M, K, metric == METRIC_DOT ? METRIC_DOT : METRIC_L2, 0.0f,
               (int)p->max_iters, 1e-4, p->seed, init.get(), codebook, nullptr, iters);
@@ -395,7 +396,7 @@ lb2_status lb2_kmeans_train(const void* data, uint64_t n, uint32_t d, lb2_dtype 
   const int m = metric_of(params->metric);
   if (m == METRIC_COSINE)
     fail(LB2_INVALID_ARG, "KMeans: cosine is trained as L2 on normalised vectors (normalise first)");
-  LB2_REQUIRE(n >= k, "KMeans: can not train %u centroids with %llu vectors, choose a smaller K (< %llu) instead",
+  LB2_REQUIRE(current_comm() || n >= k, "KMeans: can not train %u centroids with %llu vectors, choose a smaller K (< %llu) instead",
               k, (unsigned long long)n, (unsigned long long)n);
   // free fn train_kmeans (kmeans.rs:1328-1344)
   const uint64_t rows = n > params->sample_rate * k ? params->sample_rate * k : n;
@@ -404,7 +405,8 @@ lb2_status lb2_kmeans_train(const void* data, uint64_t n, uint32_t d, lb2_dtype 
   DevBuf<float> cent((size_t)k * d);
   std::vector<double> loss;
   std::vector<uint32_t> iters;
-  lloyd_train(x.get(), rows, d, 1, d, k, m, params->balance_factor / (float)rows,
+  const uint64_t kr = current_comm() ? current_comm()->nranks : 1;  // sharded: every rank passes its rows
+  lloyd_train(x.get(), rows, d, 1, d, k, m, params->balance_factor / (float)(rows * kr),
               (int)params->max_iters, params->tolerance, params->seed, init.get(), cent.p, &loss,
               &iters);
   OutArg<float> o(centroids_out, (size_t)k * d);
@@ -711,7 +713,8 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
   LB2_REQUIRE(data && params && out, "null argument");
   const int m = metric_of(metric);
   const int K = params->num_partitions, M = params->pq.num_sub_vectors;
-  LB2_REQUIRE(K > 0 && n >= (uint64_t)K, "KMeans: can not train %d centroids with %llu vectors", K,
+  const uint64_t nranks = current_comm() ? current_comm()->nranks : 1;  // sharded build: this rank's rows
+  LB2_REQUIRE(K > 0 && (nranks > 1 || n >= (uint64_t)K), "KMeans: can not train %d centroids with %llu vectors", K,
               (unsigned long long)n);
   LB2_REQUIRE(M > 0 && d % M == 0, "num_sub_vectors must divide vector dimension %u, but got %d", d, M);
   if (params->pq.num_bits != 8) fail(LB2_UNSUPPORTED, "num_bits %u is not implemented", params->pq.num_bits);
@@ -742,7 +745,7 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
     // 1. IVF: sample K*sample_rate rows (rust/lance/src/index/vector/ivf.rs:1237-1241)
     {
       TagScope tg("ivf_train");
-      const uint64_t s = std::min<uint64_t>(n, (uint64_t)K * params->ivf.sample_rate);
+      const uint64_t s = std::min<uint64_t>(n, ((uint64_t)K * params->ivf.sample_rate + nranks - 1) / nranks);
       const float* xs = x;
       DevBuf<float> sample;
       if (s < n) {
@@ -755,7 +758,7 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
         xs = sample.p;
       }
       InArg<float> init(params->ivf.init_centroids, (size_t)K * d);
-      lloyd_train(xs, s, d, 1, d, K, am, params->ivf.balance_factor / (float)s,
+      lloyd_train(xs, s, d, 1, d, K, am, params->ivf.balance_factor / (float)(s * nranks),
                   (int)params->ivf.max_iters, params->ivf.tolerance, params->ivf.seed, init.get(),
                   ix->centroids.p, &ivf_loss, &ivf_iters);
     }
@@ -763,7 +766,7 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
     // 2. PQ: sample 256*2^nbits rows, residuals w.r.t. the IVF centroids (builder.rs:410-450)
     {
       TagScope tg("pq_train");
-      const uint64_t s = std::min<uint64_t>(n, params->pq.sample_rate * 256);
+      const uint64_t s = std::min<uint64_t>(n, (params->pq.sample_rate * 256 + nranks - 1) / nranks);
       std::vector<uint64_t> rows = sample_rows(n, s, params->seed + 1);
       DevBuf<uint64_t> rows_d(s);
       h2d(rows_d.p, rows.data(), s);
@@ -811,21 +814,6 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
   }
   for (auto& e : ev) cudaEventDestroy(e);
   *out = ix;
-  LB2_API_END
-}
-
-lb2_status lb2_comm_unique_id(void*) {
-  LB2_API_BEGIN
-  fail(LB2_UNSUPPORTED, "multi-GPU communicator is not built yet");
-  LB2_API_END
-}
-lb2_status lb2_comm_init(const void*, int, int) {
-  LB2_API_BEGIN
-  fail(LB2_UNSUPPORTED, "multi-GPU communicator is not built yet");
-  LB2_API_END
-}
-lb2_status lb2_comm_destroy(void) {
-  LB2_API_BEGIN
   LB2_API_END
 }
 

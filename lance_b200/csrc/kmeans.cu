@@ -18,8 +18,10 @@
 #include <algorithm>
 #include <cmath>
 #include <limits>
+#include <unordered_map>
 
 #include "assign.cuh"
+#include "comm.cuh"
 #include "common.cuh"
 #include "exact.cuh"
 #include "kmeans.cuh"
@@ -315,13 +317,31 @@ update_stats_kernel(unsigned update_blocks, const float* __restrict__ x, int ldx
                     uint64_t n, const uint32_t* __restrict__ members, const uint32_t* __restrict__ offsets,
                     float* __restrict__ centroids, const float* __restrict__ dists,
                     double* __restrict__ losses, float* __restrict__ radius,
-                    uint32_t* __restrict__ last_row, const uint8_t* __restrict__ active) {
+                    uint32_t* __restrict__ last_row, const uint8_t* __restrict__ active, int scale) {
   if (blockIdx.x < update_blocks) {
-    update_body((size_t)blockIdx.x * 128 + threadIdx.x, x, ldx, ds, K, B, n, members, offsets, centroids, active, 1);
+    update_body((size_t)blockIdx.x * 128 + threadIdx.x, x, ldx, ds, K, B, n, members, offsets, centroids, active, scale);
   } else {
     stats_body((int)(((size_t)(blockIdx.x - update_blocks) * 128 + threadIdx.x) >> 5), dists, n, K, B,
                members, offsets, losses, radius, last_row, active);
   }
+}
+
+// multi-GPU: the per-rank partial results are all-reduced between these two small kernels
+__global__ void encode_last_row_kernel(uint32_t* __restrict__ last_row, size_t BK, uint32_t row_offset) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < BK) last_row[g] = last_row[g] == 0xffffffffu ? 0u : last_row[g] + row_offset + 1u;  // MAX-reducible
+}
+__global__ void finish_reduce_kernel(const float* __restrict__ sums, float* __restrict__ centroids,
+                                     const uint32_t* __restrict__ counts,
+                                     uint32_t* __restrict__ last_row, size_t BK, int ds,
+                                     const uint8_t* __restrict__ active, int K) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= BK * ds) return;
+  const size_t ck = g / ds;
+  if (active && !active[ck / K]) return;
+  const uint32_t cnt = counts[ck];
+  centroids[g] = cnt > 0 ? __fmul_rn(sums[g], __fdiv_rn(1.0f, (float)cnt)) : sums[g];  // kmeans.rs:414-416
+  if (g % ds == 0) last_row[ck] = last_row[ck] == 0u ? 0xffffffffu : last_row[ck] - 1u;
 }
 
 __global__ void split_kernel(float* __restrict__ c, int i, int j, int ds) {
@@ -552,11 +572,32 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
                  float balance_factor_param, int max_iters, double tolerance, uint64_t seed,
                  const float* init_dev, float* centroids, std::vector<double>* loss_out,
                  std::vector<uint32_t>* iters_out) {
-  LB2_REQUIRE(n_in >= (uint64_t)K, "KMeans: can not train %d centroids with %llu vectors", K,
+  LB2_REQUIRE(current_comm() || n_in >= (uint64_t)K, "KMeans: can not train %d centroids with %llu vectors", K,
               (unsigned long long)n_in);
   // kmeans.rs:623-627: only the first 512*k rows are used
-  const uint64_t n = n_in >= (uint64_t)K * 512 ? (uint64_t)K * 512 : n_in;
-  LB2_REQUIRE(n < 0xffffffffull, "training sample too large");
+  Comm* cm = current_comm();
+  const bool dist = cm && cm->nranks > 1;
+  uint64_t n = n_in >= (uint64_t)K * 512 ? (uint64_t)K * 512 : n_in;
+  uint64_t n_global = n, row_offset = 0;
+  if (dist) {
+    // every rank holds a row shard of the sample; rows are ordered rank-major
+    n = std::min<uint64_t>(n_in, ((uint64_t)K * 512 + cm->nranks - 1) / cm->nranks);
+    std::vector<uint32_t> all(cm->nranks, 0);
+    all[cm->rank] = (uint32_t)n;
+    DevBuf<uint32_t> all_d(cm->nranks);
+    h2d(all_d.p, all.data(), cm->nranks);
+    comm_allreduce_u32(all_d.p, cm->nranks, RedOp::Sum);
+    d2h(all.data(), all_d.p, cm->nranks);
+    sync_stream();
+    n_global = 0;
+    for (int r = 0; r < cm->nranks; ++r) {
+      if (r < cm->rank) row_offset += all[r];
+      n_global += all[r];
+    }
+    LB2_REQUIRE(n_global >= (uint64_t)K, "KMeans: can not train %d centroids with %llu vectors", K,
+                (unsigned long long)n_global);
+  }
+  LB2_REQUIRE(n_global < 0xfffffffeull, "training sample too large");
   const size_t BK = (size_t)B * K;
   const bool small = B > 1;
   if (small && !small_d_supported(ds))
@@ -576,21 +617,33 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
     if (init_dev != centroids) d2d(centroids, init_dev, BK * ds);
     for (int b = 0; b < B; ++b) h_states[b].rng = seed + b;
   } else {
-    std::vector<uint32_t> rows(BK), idx(n);
+    // partial Fisher-Yates over the virtual array idx[i] = i, kept sparse (only touched slots are
+    // stored): identical picks to the dense version, O(K) instead of O(n) host work per problem
+    std::vector<uint32_t> rows(BK);
+    std::unordered_map<uint64_t, uint32_t> moved;
     for (int b = 0; b < B; ++b) {
       SplitMix64 rng(seed + b);
-      for (uint64_t i = 0; i < n; ++i) idx[i] = (uint32_t)i;
+      moved.clear();
+      LB2_REQUIRE(n >= (uint64_t)K, "KMeans: the seeding rank needs at least k rows");
+      auto at = [&](uint64_t i) {
+        auto it = moved.find(i);
+        return it == moved.end() ? (uint32_t)i : it->second;
+      };
       for (int i = 0; i < K; ++i) {
-        uint64_t j = i + rng.next() % (n - i);
-        std::swap(idx[i], idx[j]);
-        rows[(size_t)b * K + i] = idx[i];
+        const uint64_t j = i + rng.next() % (n - i);
+        const uint32_t vi = at(i), vj = at(j);
+        moved[i] = vj;
+        moved[j] = vi;
+        rows[(size_t)b * K + i] = vj;
       }
       h_states[b].rng = rng.s;  // split_clusters continues the same stream
     }
     DevBuf<uint32_t> rows_d(BK);
     h2d(rows_d.p, rows.data(), BK);
-    LB2_LAUNCH("kmeans_init", gather_init_kernel, cdiv(BK * ds, 256), 256, 0, x, ldx, ds, K, B,
-               rows_d.p, centroids);
+    if (!dist || cm->rank == 0)  // multi-GPU: rank 0 seeds from its shard and broadcasts
+      LB2_LAUNCH("kmeans_init", gather_init_kernel, cdiv(BK * ds, 256), 256, 0, x, ldx, ds, K, B,
+                 rows_d.p, centroids);
+    if (dist) comm_broadcast_bytes(centroids, BK * ds * sizeof(float), 0);
     sync_stream();  // rows (host vector) must outlive the copy
   }
 
@@ -609,6 +662,8 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
     bias.alloc(Kp);
     bias.zero();  // iteration 1: cluster sizes are all zero -> bias 0
   }
+  DevBuf<float> sums;  // multi-GPU: per-rank partial centroid sums (all-reduced every iteration)
+  if (dist) sums.alloc(BK * ds);
   MemberSort ms;
   TcWorkspace tcws;
   TcPqWorkspace pqws;
@@ -635,8 +690,20 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
     ms.run(ids.p, valid.p, n, K, B, active_d.p);
     const unsigned ub = cdiv(BK * ds, 128), sb = cdiv((uint64_t)BK * 32, 128);
     LB2_LAUNCH("kmeans_update_stats", update_stats_kernel, ub + sb, 128, 0, ub, x, ldx, ds, K, B, n,
-               ms.members.p, ms.offsets.p, centroids, dists.p, losses.p, radius.p, last_row.p, active_d.p);
-    LB2_LAUNCH("kmeans_epilogue", epilogue_kernel, B, 256, 0, K, ds, n, balance_factor_param,
+               ms.members.p, ms.offsets.p, dist ? sums.p : centroids, dists.p, losses.p, radius.p,
+               last_row.p, active_d.p, dist ? 0 : 1);
+    if (dist) {  // one exchange step per iteration over NVLink
+      LB2_LAUNCH("kmeans_encode_last", encode_last_row_kernel, cdiv(BK, 256), 256, 0, last_row.p, BK,
+                 (uint32_t)row_offset);
+      comm_allreduce_f32(sums.p, BK * ds, RedOp::Sum);
+      comm_allreduce_u32(ms.counts.p, BK, RedOp::Sum);
+      comm_allreduce_f64(losses.p, BK, RedOp::Sum);
+      comm_allreduce_f32(radius.p, BK, RedOp::Max);
+      comm_allreduce_u32(last_row.p, BK, RedOp::Max);
+      LB2_LAUNCH("kmeans_finish_reduce", finish_reduce_kernel, cdiv(BK * ds, 256), 256, 0, sums.p,
+                 centroids, ms.counts.p, last_row.p, BK, ds, active_d.p, K);
+    }
+    LB2_LAUNCH("kmeans_epilogue", epilogue_kernel, B, 256, 0, K, ds, n_global, balance_factor_param,
                tolerance, ms.counts.p, losses.p, radius.p, last_row.p, cluster_sizes.p,
                small ? nullptr : bias.p, Kp, centroids, states.p, active_d.p);
   };
@@ -644,7 +711,7 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
   // iteration is then captured ONCE into a CUDA graph and replayed, so that the loop is not bound
   // by ~18 host launches per iteration.  (Event profiling and LB2_TC_STATS need eager launches.)
   const bool stats_env = getenv("LB2_TC_STATS") && *getenv("LB2_TC_STATS");
-  const bool use_graph = max_iters > 1 && !ctx().profiling && !stats_env &&
+  const bool use_graph = max_iters > 1 && !ctx().profiling && !stats_env && !dist &&
                          !(getenv("LB2_NO_GRAPH") && *getenv("LB2_NO_GRAPH"));
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
