@@ -398,8 +398,10 @@ lb2_status lb2_kmeans_train(const void* data, uint64_t n, uint32_t d, lb2_dtype 
     fail(LB2_INVALID_ARG, "KMeans: cosine is trained as L2 on normalised vectors (normalise first)");
   LB2_REQUIRE(current_comm() || n >= k, "KMeans: can not train %u centroids with %llu vectors, choose a smaller K (< %llu) instead",
               k, (unsigned long long)n, (unsigned long long)n);
-  // free fn train_kmeans (kmeans.rs:1328-1344)
-  const uint64_t rows = n > params->sample_rate * k ? params->sample_rate * k : n;
+  // free fn train_kmeans (kmeans.rs:1328-1344); sharded: every rank contributes its share of the cap
+  const uint64_t kr0 = current_comm() ? current_comm()->nranks : 1;
+  const uint64_t cap = (params->sample_rate * k + kr0 - 1) / kr0;
+  const uint64_t rows = n > cap ? cap : n;
   InArg<float> x(data, (size_t)rows * d);
   InArg<float> init(params->init_centroids, (size_t)k * d);
   DevBuf<float> cent((size_t)k * d);

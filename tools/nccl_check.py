@@ -13,7 +13,7 @@ rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
 lb.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
-n, d, K = 32768, 128, 64
+n, d, K = 16384, 128, 128  # n * world == sample_rate * K: both runs use exactly the same rows
 full = synth.sift_like(n * world, d, seed=11)
 init = full[np.random.default_rng(0).choice(n * world, K, replace=False)].copy()
 single = lb.train_kmeans(full, d, K, max_iters=10, centroids=init, balance_factor=1.0) if rank == 0 else None
@@ -36,6 +36,6 @@ if rank == 0:
     rel = abs(km.loss - single.loss) / single.loss
     print(f"identical centroids on all ranks: {bool(flags[0])}, identical PQ codebooks: {bool(flags[1])}; "
           f"sharded loss {km.loss:.6e} vs single-GPU {single.loss:.6e} (rel {rel:.2e}), iters {km.iters} vs {single.iters}")
-    assert bool(flags[0]) and bool(flags[1]) and rel < 1e-3
+    assert bool(flags[0]) and bool(flags[1]) and rel < 1e-5
 parallel.comm_destroy()
 dist.destroy_process_group()
