@@ -124,8 +124,14 @@ select_probes_kernel(const float* __restrict__ all_dists, int K, int nprobes,
 
 // ------------------------------------------------------------------------------------------------
 // the fused (residual query -> LUT -> code scan -> top-k) kernel
+//   distances of a chunk of <= SCAN_CHUNK rows go to shared memory; the k smallest (distance,
+//   position) pairs are then extracted by k rounds of "smallest key strictly greater than the
+//   previous winner" (no per-thread lists, no local memory).  Larger partitions are processed
+//   chunk by chunk, the previous winners joining the next chunk's candidate pool.
 // ------------------------------------------------------------------------------------------------
-template <int METRIC, int KMAX>
+constexpr int SCAN_CHUNK = 4096;
+
+template <int METRIC>
 __global__ void __launch_bounds__(256)
 ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restrict__ centroids,
                   const float* __restrict__ codebook, int M, int ds,
@@ -134,11 +140,17 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
                   const uint64_t* __restrict__ row_ids, int k, float* __restrict__ cand_d,
                   uint64_t* __restrict__ cand_id, uint32_t* __restrict__ cand_cnt) {
   extern __shared__ float smem[];
-  float* lut = smem;           // [M*256]
-  float* qr = smem + M * 256;  // [d]
+  float* lut = smem;                         // [M*256]
+  float* qr = lut + M * 256;                 // [d]
+  float* cd = qr + d;                        // [SCAN_CHUNK + k] candidate distances
+  uint32_t* cp = reinterpret_cast<uint32_t*>(cd + SCAN_CHUNK + k);  // [k] positions of carried winners
+  float* wd = reinterpret_cast<float*>(cp + k);                     // [k] new winners
+  uint32_t* wp = reinterpret_cast<uint32_t*>(wd + k);               // [k]
   __shared__ int32_t s_key[8];
   __shared__ uint64_t s_tie[8];
   __shared__ int s_tid[9];
+  __shared__ int32_t prev_key;
+  __shared__ uint32_t prev_pos;
   const int tid = threadIdx.x;
   const int pi = blockIdx.x;
   const size_t qi = blockIdx.y;
@@ -160,50 +172,78 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
   }
   __syncthreads();
 
-  ThreadTopK<KMAX> top;
   const uint8_t* pc = codes + off * M;
   const float dot_fix = (float)M - 1.0f;
-  if ((M & 15) == 0) {
-    for (uint32_t j = tid; j < n_p; j += 256) {
-      const uint4* rp = reinterpret_cast<const uint4*>(pc + (size_t)j * M);
-      float dist = 0.0f;
-      for (int c16 = 0; c16 < M / 16; ++c16) {
-        const uint4 v = __ldg(rp + c16);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        const float* l0 = lut + c16 * 16 * 256;
+  uint32_t nw = 0;  // winners carried from the previous chunks (uniform)
+  for (uint32_t c0 = 0; c0 < n_p; c0 += SCAN_CHUNK) {
+    const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
+    // ---- ADC distances of the chunk: dist = ((0 + LUT[0][c0]) + LUT[1][c1]) + ... (pq/distance.rs:125-141)
+    if ((M & 15) == 0) {
+      for (uint32_t j = tid; j < clen; j += 256) {
+        const uint4* rp = reinterpret_cast<const uint4*>(pc + (size_t)(c0 + j) * M);
+        float dist = 0.0f;
+        for (int c16 = 0; c16 < M / 16; ++c16) {
+          const uint4 v = __ldg(rp + c16);
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+          const float* l0 = lut + c16 * 16 * 256;
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+          for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int b = 0; b < 4; ++b)
-            dist = f_add(dist, l0[(a * 4 + b) * 256 + ((w[a] >> (8 * b)) & 0xff)]);
+            for (int b = 0; b < 4; ++b)
+              dist = f_add(dist, l0[(a * 4 + b) * 256 + ((w[a] >> (8 * b)) & 0xff)]);
+        }
+        if (METRIC == METRIC_DOT) dist = __fsub_rn(dist, dot_fix);  // pq/storage.rs:957-958
+        cd[j] = dist;
       }
-      if (METRIC == METRIC_DOT) dist = __fsub_rn(dist, dot_fix);  // pq/storage.rs:957-958
-      top.push(dist, j, k);
+    } else {
+      for (uint32_t j = tid; j < clen; j += 256) {
+        const uint8_t* rp = pc + (size_t)(c0 + j) * M;
+        float dist = 0.0f;
+        for (int m = 0; m < M; ++m) dist = f_add(dist, lut[m * 256 + rp[m]]);
+        if (METRIC == METRIC_DOT) dist = __fsub_rn(dist, dot_fix);
+        cd[j] = dist;
+      }
     }
-  } else {
-    for (uint32_t j = tid; j < n_p; j += 256) {
-      const uint8_t* rp = pc + (size_t)j * M;
-      float dist = 0.0f;
-      for (int m = 0; m < M; ++m) dist = f_add(dist, lut[m * 256 + rp[m]]);
-      if (METRIC == METRIC_DOT) dist = __fsub_rn(dist, dot_fix);
-      top.push(dist, j, k);
+    __syncthreads();
+    // ---- k rounds over the pool = chunk rows (positions c0 + j) + carried winners (positions cp[])
+    const uint32_t pool = clen + nw;
+    const uint32_t rounds = pool < (uint32_t)k ? pool : (uint32_t)k;
+    bool first = true;
+    for (uint32_t r = 0; r < rounds; ++r) {
+      int32_t bk = 0;
+      uint32_t bpos = 0, bslot = 0;
+      bool has = false;
+      const int32_t pk = first ? 0 : prev_key;
+      const uint32_t pp = first ? 0 : prev_pos;
+      for (uint32_t i = tid; i < pool; i += 256) {
+        const int32_t key = total_order_key(cd[i < clen ? i : SCAN_CHUNK + (i - clen)]);
+        const uint32_t pos = i < clen ? c0 + i : cp[i - clen];
+        if (!first && !ki_less(pk, pp, key, pos)) continue;  // already emitted
+        if (!has || ki_less(key, pos, bk, bpos)) { bk = key; bpos = pos; bslot = i; has = true; }
+      }
+      const int w = block_argmin<256>(has, bk, bpos, s_key, s_tie, s_tid);
+      if (tid == w) {
+        prev_key = bk;
+        prev_pos = bpos;
+        wd[r] = cd[bslot < clen ? bslot : SCAN_CHUNK + (bslot - clen)];
+        wp[r] = bpos;
+      }
+      __syncthreads();
+      first = false;
     }
+    // the winners become the carried candidates of the next chunk
+    for (uint32_t i = tid; i < rounds; i += 256) {
+      cd[SCAN_CHUNK + i] = wd[i];
+      cp[i] = wp[i];
+    }
+    nw = rounds;
+    __syncthreads();
   }
-  // block merge: k rounds of argmin over the threads' list heads
-  int head = 0;
-  const uint32_t rounds = n_p < (uint32_t)k ? n_p : (uint32_t)k;
-  for (uint32_t r = 0; r < rounds; ++r) {
-    const bool has = head < top.cnt;
-    const int32_t key = has ? total_order_key(top.d[head]) : 0;
-    const uint64_t tie = has ? top.j[head] : 0;
-    const int w = block_argmin<256>(has, key, tie, s_key, s_tie, s_tid);
-    if (tid == w) {
-      cand_d[slot * k + r] = top.d[head];
-      cand_id[slot * k + r] = row_ids[off + top.j[head]];
-      ++head;
-    }
+  for (uint32_t i = tid; i < nw; i += 256) {
+    cand_d[slot * k + i] = cd[SCAN_CHUNK + i];
+    cand_id[slot * k + i] = row_ids[off + cp[i]];
   }
-  if (tid == 0) cand_cnt[slot] = rounds;
+  if (tid == 0) cand_cnt[slot] = nw;
 }
 
 // global merge per query: ascending (distance, row id), first k
@@ -324,17 +364,9 @@ static void scan_launch(int kmax, dim3 grid, size_t smem, const float* queries, 
                         const uint32_t* probe_ids, int np, const uint64_t* part_offsets,
                         const uint8_t* codes, const uint64_t* row_ids, int k, float* cand_d,
                         uint64_t* cand_id, uint32_t* cand_cnt) {
-#define LB2_SCAN(KM)                                                                              \
-  {                                                                                               \
-    set_smem(ivfpq_scan_kernel<METRIC, KM>, smem);                                                \
-    LB2_LAUNCH("pq_scan", (ivfpq_scan_kernel<METRIC, KM>), grid, 256, smem, queries, d, centroids, \
-               codebook, M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id,  \
-               cand_cnt);                                                                         \
-  }
-  if (kmax <= 16) LB2_SCAN(16)
-  else if (kmax <= 128) LB2_SCAN(128)
-  else LB2_SCAN(1024)
-#undef LB2_SCAN
+  set_smem(ivfpq_scan_kernel<METRIC>, smem);
+  LB2_LAUNCH("pq_scan", (ivfpq_scan_kernel<METRIC>), grid, 256, smem, queries, d, centroids, codebook,
+             M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt);
 }
 
 void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const float* codebook, int M,
@@ -351,7 +383,7 @@ void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const fl
   DevBuf<float> pd((size_t)nq * np), cand_d((size_t)nq * np * k);
   DevBuf<uint64_t> cand_id((size_t)nq * np * k);
   find_partitions_f32(centroids, K, d, cmetric, queries, nq, np, pids.p, pd.p);
-  const size_t smem = sizeof(float) * ((size_t)M * 256 + d);
+  const size_t smem = sizeof(float) * ((size_t)M * 256 + d + SCAN_CHUNK + 4 * (size_t)k);
   if (smem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "LUT of %zu bytes exceeds shared memory", smem);
   dim3 grid(np, (unsigned)nq);
   if (nq > 65535) {
