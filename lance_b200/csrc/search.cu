@@ -133,7 +133,7 @@ constexpr int SCAN_CHUNK = 4096;
 
 template <int METRIC>
 __global__ void __launch_bounds__(256)
-ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restrict__ centroids,
+ivfpq_scan_rounds_kernel(const float* __restrict__ queries, int d, const float* __restrict__ centroids,
                   const float* __restrict__ codebook, int M, int ds,
                   const uint32_t* __restrict__ probe_ids, int np,
                   const uint64_t* __restrict__ part_offsets, const uint8_t* __restrict__ codes,
@@ -242,6 +242,190 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
   for (uint32_t i = tid; i < nw; i += 256) {
     cand_d[slot * k + i] = cd[SCAN_CHUNK + i];
     cand_id[slot * k + i] = row_ids[off + cp[i]];
+  }
+  if (tid == 0) cand_cnt[slot] = nw;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small-k (k <= 32) variant: a thread keeps its <= 16 chunk distances in registers.
+//   T  = k-th smallest of the 256 per-thread minima  (an upper bound of the k-th smallest overall)
+//   C  = { elements <= T } : at most (k-1)*16 + 1 of them, compacted into shared memory
+//   the k smallest of C (+ the winners carried from earlier chunks) are then selected by ONE warp
+//   with shuffle-only argmin rounds.  All comparisons are on (total-order key, position).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float key_to_float(int32_t key) {
+  return __int_as_float(key ^ (int32_t)((uint32_t)(key >> 31) >> 1));
+}
+// one warp: `rounds` smallest (key,pos) among the PER-per-lane register values, ascending; the r-th
+// winner is handed to emit(r, key, pos) by every lane (uniform)
+template <int PER, class Emit>
+__device__ __forceinline__ void warp_select(const int32_t (&key)[PER], const uint32_t (&pos)[PER],
+                                            const bool (&ok)[PER], int rounds, Emit emit) {
+  int32_t pk = 0;
+  uint32_t pp = 0;
+  for (int r = 0; r < rounds; ++r) {
+    int32_t bk = 0x7fffffff;
+    uint32_t bp = 0xffffffffu;
+    bool has = false;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const bool elig = ok[u] && (r == 0 || ki_less(pk, pp, key[u], pos[u]));
+      if (elig && (!has || ki_less(key[u], pos[u], bk, bp))) { bk = key[u]; bp = pos[u]; has = true; }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const int32_t ok2 = __shfl_xor_sync(0xffffffffu, bk, off);
+      const uint32_t op = __shfl_xor_sync(0xffffffffu, bp, off);
+      const int oh = __shfl_xor_sync(0xffffffffu, (int)has, off);
+      if (oh && (!has || ki_less(ok2, op, bk, bp))) { bk = ok2; bp = op; has = true; }
+    }
+    if (!has) break;  // uniform
+    pk = bk;
+    pp = bp;
+    emit(r, bk, bp);
+  }
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(256)
+ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restrict__ centroids,
+                  const float* __restrict__ codebook, int M, int ds,
+                  const uint32_t* __restrict__ probe_ids, int np,
+                  const uint64_t* __restrict__ part_offsets, const uint8_t* __restrict__ codes,
+                  const uint64_t* __restrict__ row_ids, int k, float* __restrict__ cand_d,
+                  uint64_t* __restrict__ cand_id, uint32_t* __restrict__ cand_cnt) {
+  constexpr int RPT = SCAN_CHUNK / 256;  // rows per thread and chunk (16)
+  constexpr int PER = 18;                // list entries per lane of the selecting warp: 32*18 >= 32*16+32+1
+  extern __shared__ float smem[];
+  float* lut = smem;          // [M*256]
+  float* qr = lut + M * 256;  // [d]
+  __shared__ int32_t tmin_key[256];
+  __shared__ uint32_t tmin_pos[256];
+  __shared__ int32_t list_key[32 * PER];
+  __shared__ uint32_t list_pos[32 * PER];
+  __shared__ int32_t car_key[32];   // winners carried across chunks
+  __shared__ uint32_t car_pos[32];
+  __shared__ int32_t s_tkey;
+  __shared__ uint32_t s_tpos, s_count, s_nw;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pi = blockIdx.x;
+  const size_t qi = blockIdx.y;
+  const uint32_t p = probe_ids[qi * np + pi];
+  const uint64_t off = part_offsets[p];
+  const uint32_t n_p = (uint32_t)(part_offsets[p + 1] - off);
+  const size_t slot = qi * np + pi;
+  if (n_p == 0) {
+    if (tid == 0) cand_cnt[slot] = 0;
+    return;
+  }
+  const float* q = queries + qi * d;
+  for (int t = tid; t < d; t += 256)
+    qr[t] = METRIC == METRIC_DOT ? q[t] : __fsub_rn(q[t], centroids[(size_t)p * d + t]);  // v2.rs:316-332
+  if (tid == 0) s_nw = 0;
+  __syncthreads();
+  for (int idx = tid; idx < M * 256; idx += 256) {  // pq/distance.rs:38-56
+    const int m = idx >> 8;
+    lut[idx] = dist_exact_thread<METRIC>(qr + m * ds, codebook + (size_t)idx * ds, ds);
+  }
+  __syncthreads();
+
+  const uint8_t* pc = codes + off * M;
+  const float dot_fix = (float)M - 1.0f;
+  for (uint32_t c0 = 0; c0 < n_p; c0 += SCAN_CHUNK) {
+    const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
+    int32_t key[RPT];
+    int32_t mk = 0x7fffffff;
+    uint32_t mp = 0xffffffffu;
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+      const uint32_t j = tid + 256 * u;
+      key[u] = 0x7fffffff;
+      if (j < clen) {
+        float dist = 0.0f;
+        if ((M & 15) == 0) {
+          const uint4* rp = reinterpret_cast<const uint4*>(pc + (size_t)(c0 + j) * M);
+          for (int c16 = 0; c16 < M / 16; ++c16) {
+            const uint4 v = __ldg(rp + c16);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            const float* l0 = lut + c16 * 16 * 256;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 4; ++b)
+                dist = f_add(dist, l0[(a * 4 + b) * 256 + ((w[a] >> (8 * b)) & 0xff)]);
+          }
+        } else {
+          const uint8_t* rp = pc + (size_t)(c0 + j) * M;
+          for (int m = 0; m < M; ++m) dist = f_add(dist, lut[m * 256 + rp[m]]);
+        }
+        if (METRIC == METRIC_DOT) dist = __fsub_rn(dist, dot_fix);  // pq/storage.rs:957-958
+        key[u] = total_order_key(dist);
+        if (key[u] < mk) { mk = key[u]; mp = c0 + j; }  // ascending position: first minimum wins
+      }
+    }
+    tmin_key[tid] = mk;
+    tmin_pos[tid] = mp;  // 0xffffffff = this thread has no row in the chunk
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    if (warp == 0) {  // T = k-th smallest thread minimum (or "everything" if fewer than k threads have rows)
+      int32_t tk[8];
+      uint32_t tp[8];
+      bool ok[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        tk[u] = tmin_key[lane + 32 * u];
+        tp[u] = tmin_pos[lane + 32 * u];
+        ok[u] = tp[u] != 0xffffffffu;
+      }
+      int32_t lk = 0x7fffffff;
+      uint32_t lp = 0xffffffffu;
+      int got = 0;
+      warp_select<8>(tk, tp, ok, k, [&](int r, int32_t kk, uint32_t pp) { lk = kk; lp = pp; got = r + 1; });
+      if (lane == 0) {
+        if (got < k) { lk = 0x7fffffff; lp = 0xffffffffu; }
+        s_tkey = lk;
+        s_tpos = lp;
+      }
+    }
+    __syncthreads();
+    const int32_t tkey = s_tkey;
+    const uint32_t tpos = s_tpos;
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+      const uint32_t j = tid + 256 * u;
+      if (j < clen && !ki_less(tkey, tpos, key[u], c0 + j)) {  // (key,pos) <= T
+        const uint32_t at = atomicAdd(&s_count, 1u);
+        list_key[at] = key[u];
+        list_pos[at] = c0 + j;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {  // k smallest of (carried winners + compacted list); order of the list is irrelevant
+      const uint32_t cnt = s_count, nw = s_nw;
+      int32_t vk[PER];
+      uint32_t vp[PER];
+      bool ok[PER];
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const uint32_t i = lane + 32 * u;
+        ok[u] = i < cnt + nw;
+        vk[u] = !ok[u] ? 0x7fffffff : (i < cnt ? list_key[i] : car_key[i - cnt]);
+        vp[u] = !ok[u] ? 0xffffffffu : (i < cnt ? list_pos[i] : car_pos[i - cnt]);
+      }
+      __syncwarp();
+      int got = 0;
+      warp_select<PER>(vk, vp, ok, k, [&](int r, int32_t kk, uint32_t pp) {
+        if (lane == 0) { car_key[r] = kk; car_pos[r] = pp; }
+        got = r + 1;
+      });
+      if (lane == 0) s_nw = got;
+    }
+    __syncthreads();
+  }
+  const uint32_t nw = s_nw;
+  for (uint32_t i = tid; i < nw; i += 256) {
+    cand_d[slot * k + i] = key_to_float(car_key[i]);
+    cand_id[slot * k + i] = row_ids[off + car_pos[i]];
   }
   if (tid == 0) cand_cnt[slot] = nw;
 }
@@ -364,8 +548,15 @@ static void scan_launch(int kmax, dim3 grid, size_t smem, const float* queries, 
                         const uint32_t* probe_ids, int np, const uint64_t* part_offsets,
                         const uint8_t* codes, const uint64_t* row_ids, int k, float* cand_d,
                         uint64_t* cand_id, uint32_t* cand_cnt) {
-  set_smem(ivfpq_scan_kernel<METRIC>, smem);
-  LB2_LAUNCH("pq_scan", (ivfpq_scan_kernel<METRIC>), grid, 256, smem, queries, d, centroids, codebook,
+  if (k <= 32) {
+    const size_t smem_fast = sizeof(float) * ((size_t)M * 256 + d);
+    set_smem(ivfpq_scan_kernel<METRIC>, smem_fast);
+    LB2_LAUNCH("pq_scan", (ivfpq_scan_kernel<METRIC>), grid, 256, smem_fast, queries, d, centroids,
+               codebook, M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt);
+    return;
+  }
+  set_smem(ivfpq_scan_rounds_kernel<METRIC>, smem);
+  LB2_LAUNCH("pq_scan", (ivfpq_scan_rounds_kernel<METRIC>), grid, 256, smem, queries, d, centroids, codebook,
              M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt);
 }
 
