@@ -727,13 +727,50 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
   for (auto& e : ev) LB2_CUDA(cudaEventCreate(&e));
   LB2_CUDA(cudaEventRecord(ev[0], c.stream));
 
-  InArg<float> xin(data, (size_t)n * d);
-  const float* x = xin.get();
+  // Staging.  Device pointer: used in place.  PINNED host pointer (L2 / dot): the bulk H2D copy runs
+  // on a second stream (copy engine) while both training phases gather their <= 65 536-row samples
+  // straight out of the pinned buffer (zero-copy reads over PCIe), so the 0.5 GB copy hides behind
+  // training; the transform waits on the copy.  Pageable host pointer: plain staged copy first.
+  InArg<float> xin;
+  DevBuf<float> xbulk;
+  const float* x = nullptr;         // complete device copy (valid after `copied`)
+  const float* x_sample = nullptr;  // what the training samples are gathered from
+  cudaEvent_t copied = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  {
+    cudaPointerAttributes pa;
+    const bool attr_ok = cudaPointerGetAttributes(&pa, data) == cudaSuccess;
+    if (!attr_ok) cudaGetLastError();
+    if (attr_ok && pa.type == cudaMemoryTypeHost && pa.devicePointer && m != METRIC_COSINE) {
+      xbulk.alloc((size_t)n * d);
+      LB2_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+      LB2_CUDA(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+      // the pool allocation above is ordered on c.stream: make the copy stream wait for it
+      LB2_CUDA(cudaEventRecord(copied, c.stream));
+      LB2_CUDA(cudaStreamWaitEvent(copy_stream, copied, 0));
+      LB2_CUDA(cudaMemcpyAsync(xbulk.p, data, sizeof(float) * (size_t)n * d, cudaMemcpyHostToDevice, copy_stream));
+      LB2_CUDA(cudaEventRecord(copied, copy_stream));
+      x = xbulk.p;
+      x_sample = static_cast<const float*>(pa.devicePointer);
+    } else {
+      xin.set(data, (size_t)n * d);
+      x = xin.get();
+      x_sample = x;
+    }
+  }
+  struct CopyGuard {  // never leave the copy stream / event behind, also on errors
+    cudaStream_t& s; cudaEvent_t& e;
+    ~CopyGuard() {
+      if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+      if (e) cudaEventDestroy(e);
+    }
+  } copy_guard{copy_stream, copied};
   DevBuf<float> xnorm;
   if (m == METRIC_COSINE) {  // normalise once; the reference normalises samples and every batch
     xnorm.alloc((size_t)n * d);
     LB2_LAUNCH("normalize", normalize_kernel, cdiv(n, 128), 128, 0, x, n, (int)d, xnorm.p);
     x = xnorm.p;
+    x_sample = x;
   }
   const int am = m == METRIC_DOT ? METRIC_DOT : METRIC_L2;
 
@@ -748,14 +785,14 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
     {
       TagScope tg("ivf_train");
       const uint64_t s = std::min<uint64_t>(n, ((uint64_t)K * params->ivf.sample_rate + nranks - 1) / nranks);
-      const float* xs = x;
+      const float* xs = x_sample;
       DevBuf<float> sample;
-      if (s < n) {
+      if (s < n || x_sample != x) {
         std::vector<uint64_t> rows = sample_rows(n, s, params->seed);
         DevBuf<uint64_t> rows_d(s);
         h2d(rows_d.p, rows.data(), s);
         sample.alloc((size_t)s * d);
-        LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(s * d, 256), 256, 0, x, rows_d.p, s, (int)d, sample.p);
+        LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(s * d, 256), 256, 0, x_sample, rows_d.p, s, (int)d, sample.p);
         sync_stream();
         xs = sample.p;
       }
@@ -773,7 +810,7 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
       DevBuf<uint64_t> rows_d(s);
       h2d(rows_d.p, rows.data(), s);
       DevBuf<float> sample((size_t)s * d);
-      LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(s * d, 256), 256, 0, x, rows_d.p, s, (int)d, sample.p);
+      LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(s * d, 256), 256, 0, x_sample, rows_d.p, s, (int)d, sample.p);
       sync_stream();
       if (am == METRIC_L2) {
         DevBuf<uint32_t> part(s);
@@ -787,6 +824,7 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
     // 3. transform every row (lance-index/src/vector/ivf.rs:357: partition -> residual -> PQ)
     DevBuf<uint32_t> part(n);
     DevBuf<uint8_t> codes((size_t)n * M), valid(n);
+    if (copied) LB2_CUDA(cudaStreamWaitEvent(c.stream, copied, 0));  // the bulk copy must have landed
     TagScope* tg3 = new TagScope("transform");
     assign_f32(x, n, d, ix->centroids.p, K, am, nullptr, part.p, nullptr, valid.p, nullptr);
     pq_encode_dev(x, n, d, M, ds, ix->codebook.p, am, am == METRIC_DOT ? nullptr : ix->centroids.p,

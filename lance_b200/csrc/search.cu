@@ -122,6 +122,48 @@ select_probes_kernel(const float* __restrict__ all_dists, int K, int nprobes,
   }
 }
 
+// LUT[m][c] = dist(q_m, cb[m][c])  (pq/distance.rs:38-56).  For the common sub-vector widths the
+// codeword is fetched with 128-bit loads and the reference-order sum is fully unrolled.
+template <int METRIC, int DS>
+__device__ __forceinline__ float lut_entry_fixed(const float* __restrict__ qm, const float* __restrict__ cw) {
+  float qv[DS], cv[DS];
+#pragma unroll
+  for (int t = 0; t < DS; t += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(qm + t);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(cw + t));
+    qv[t] = a.x; qv[t + 1] = a.y; qv[t + 2] = a.z; qv[t + 3] = a.w;
+    cv[t] = b.x; cv[t + 1] = b.y; cv[t + 2] = b.z; cv[t + 3] = b.w;
+  }
+  if (DS < 16) {  // tail-only path (l2.rs:69-79): plain left-to-right sum
+    float s = 0.0f;
+#pragma unroll
+    for (int t = 0; t < DS; ++t) s = f_add(s, term<METRIC>(qv[t], cv[t]));
+    return finish<METRIC>(f_add(s, 0.0f));
+  } else {        // DS == 16: one chunk of 16 lanes, summed lane 0..15
+    float t0 = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) t0 = f_add(t0, f_add(0.0f, term<METRIC>(qv[t], cv[t])));
+    return finish<METRIC>(f_add(0.0f, t0));
+  }
+}
+template <int METRIC>
+__device__ __forceinline__ void build_lut_smem(float* lut, const float* qr, const float* __restrict__ codebook,
+                                               int M, int ds, int tid) {
+  if (ds == 8) {
+    for (int idx = tid; idx < M * 256; idx += 256)
+      lut[idx] = lut_entry_fixed<METRIC, 8>(qr + (idx >> 8) * 8, codebook + (size_t)idx * 8);
+  } else if (ds == 4) {
+    for (int idx = tid; idx < M * 256; idx += 256)
+      lut[idx] = lut_entry_fixed<METRIC, 4>(qr + (idx >> 8) * 4, codebook + (size_t)idx * 4);
+  } else if (ds == 16) {
+    for (int idx = tid; idx < M * 256; idx += 256)
+      lut[idx] = lut_entry_fixed<METRIC, 16>(qr + (idx >> 8) * 16, codebook + (size_t)idx * 16);
+  } else {
+    for (int idx = tid; idx < M * 256; idx += 256)
+      lut[idx] = dist_exact_thread<METRIC>(qr + (idx >> 8) * ds, codebook + (size_t)idx * ds, ds);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the fused (residual query -> LUT -> code scan -> top-k) kernel
 //   distances of a chunk of <= SCAN_CHUNK rows go to shared memory; the k smallest (distance,
@@ -166,10 +208,7 @@ ivfpq_scan_rounds_kernel(const float* __restrict__ queries, int d, const float* 
   for (int t = tid; t < d; t += 256)
     qr[t] = METRIC == METRIC_DOT ? q[t] : __fsub_rn(q[t], centroids[(size_t)p * d + t]);  // v2.rs:316-332
   __syncthreads();
-  for (int idx = tid; idx < M * 256; idx += 256) {  // pq/distance.rs:38-56
-    const int m = idx >> 8;
-    lut[idx] = dist_exact_thread<METRIC>(qr + m * ds, codebook + (size_t)idx * ds, ds);
-  }
+  build_lut_smem<METRIC>(lut, qr, codebook, M, ds, tid);
   __syncthreads();
 
   const uint8_t* pc = codes + off * M;
@@ -323,10 +362,7 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
     qr[t] = METRIC == METRIC_DOT ? q[t] : __fsub_rn(q[t], centroids[(size_t)p * d + t]);  // v2.rs:316-332
   if (tid == 0) s_nw = 0;
   __syncthreads();
-  for (int idx = tid; idx < M * 256; idx += 256) {  // pq/distance.rs:38-56
-    const int m = idx >> 8;
-    lut[idx] = dist_exact_thread<METRIC>(qr + m * ds, codebook + (size_t)idx * ds, ds);
-  }
+  build_lut_smem<METRIC>(lut, qr, codebook, M, ds, tid);
   __syncthreads();
 
   const uint8_t* pc = codes + off * M;
