@@ -745,12 +745,8 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
       xbulk.alloc((size_t)n * d);
       LB2_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
       LB2_CUDA(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
-      // the pool allocation above is ordered on c.stream: make the copy stream wait for it
-      LB2_CUDA(cudaEventRecord(copied, c.stream));
-      LB2_CUDA(cudaStreamWaitEvent(copy_stream, copied, 0));
-      LB2_CUDA(cudaMemcpyAsync(xbulk.p, data, sizeof(float) * (size_t)n * d, cudaMemcpyHostToDevice, copy_stream));
-      LB2_CUDA(cudaEventRecord(copied, copy_stream));
-      x = xbulk.p;
+      x = xbulk.p;  // the copy itself is issued after the two sample gathers (start_bulk_copy below):
+                    // zero-copy reads get no PCIe bandwidth while the copy engine is streaming
       x_sample = static_cast<const float*>(pa.devicePointer);
     } else {
       xin.set(data, (size_t)n * d);
@@ -765,6 +761,14 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
       if (e) cudaEventDestroy(e);
     }
   } copy_guard{copy_stream, copied};
+  auto start_bulk_copy = [&]() {
+    if (!copy_stream) return;
+    // ordered after everything issued so far on c.stream (pool allocation, sample gathers)
+    LB2_CUDA(cudaEventRecord(copied, c.stream));
+    LB2_CUDA(cudaStreamWaitEvent(copy_stream, copied, 0));
+    LB2_CUDA(cudaMemcpyAsync(xbulk.p, data, sizeof(float) * (size_t)n * d, cudaMemcpyHostToDevice, copy_stream));
+    LB2_CUDA(cudaEventRecord(copied, copy_stream));
+  };
   DevBuf<float> xnorm;
   if (m == METRIC_COSINE) {  // normalise once; the reference normalises samples and every batch
     xnorm.alloc((size_t)n * d);
@@ -781,37 +785,45 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
   std::vector<double> ivf_loss;
   std::vector<uint32_t> ivf_iters, pq_iters;
   try {
-    // 1. IVF: sample K*sample_rate rows (rust/lance/src/index/vector/ivf.rs:1237-1241)
+    // 0. both training samples are gathered first (IVF: K*sample_rate rows, rust/lance/src/index/
+    //    vector/ivf.rs:1237-1241; PQ: 256*2^nbits rows, builder.rs:410-421), then the bulk copy starts
+    const uint64_t s_ivf = std::min<uint64_t>(n, ((uint64_t)K * params->ivf.sample_rate + nranks - 1) / nranks);
+    const uint64_t s_pq = std::min<uint64_t>(n, (params->pq.sample_rate * 256 + nranks - 1) / nranks);
+    DevBuf<float> sample_ivf, sample_pq((size_t)s_pq * d);
+    const float* xs_ivf = x_sample;
+    {
+      if (s_ivf < n || x_sample != x) {
+        std::vector<uint64_t> rows = sample_rows(n, s_ivf, params->seed);
+        DevBuf<uint64_t> rows_d(s_ivf);
+        h2d(rows_d.p, rows.data(), s_ivf);
+        sample_ivf.alloc((size_t)s_ivf * d);
+        LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(s_ivf * d, 256), 256, 0, x_sample, rows_d.p, s_ivf, (int)d, sample_ivf.p);
+        sync_stream();
+        xs_ivf = sample_ivf.p;
+      }
+      std::vector<uint64_t> rows = sample_rows(n, s_pq, params->seed + 1);
+      DevBuf<uint64_t> rows_d(s_pq);
+      h2d(rows_d.p, rows.data(), s_pq);
+      LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(s_pq * d, 256), 256, 0, x_sample, rows_d.p, s_pq, (int)d, sample_pq.p);
+      sync_stream();
+    }
+    start_bulk_copy();
+    // 1. IVF
     {
       TagScope tg("ivf_train");
-      const uint64_t s = std::min<uint64_t>(n, ((uint64_t)K * params->ivf.sample_rate + nranks - 1) / nranks);
-      const float* xs = x_sample;
-      DevBuf<float> sample;
-      if (s < n || x_sample != x) {
-        std::vector<uint64_t> rows = sample_rows(n, s, params->seed);
-        DevBuf<uint64_t> rows_d(s);
-        h2d(rows_d.p, rows.data(), s);
-        sample.alloc((size_t)s * d);
-        LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(s * d, 256), 256, 0, x_sample, rows_d.p, s, (int)d, sample.p);
-        sync_stream();
-        xs = sample.p;
-      }
+      const uint64_t s = s_ivf;
+      const float* xs = xs_ivf;
       InArg<float> init(params->ivf.init_centroids, (size_t)K * d);
       lloyd_train(xs, s, d, 1, d, K, am, params->ivf.balance_factor / (float)(s * nranks),
                   (int)params->ivf.max_iters, params->ivf.tolerance, params->ivf.seed, init.get(),
                   ix->centroids.p, &ivf_loss, &ivf_iters);
     }
     LB2_CUDA(cudaEventRecord(ev[1], c.stream));
-    // 2. PQ: sample 256*2^nbits rows, residuals w.r.t. the IVF centroids (builder.rs:410-450)
+    // 2. PQ: residuals of its sample w.r.t. the IVF centroids (builder.rs:439-450)
     {
       TagScope tg("pq_train");
-      const uint64_t s = std::min<uint64_t>(n, (params->pq.sample_rate * 256 + nranks - 1) / nranks);
-      std::vector<uint64_t> rows = sample_rows(n, s, params->seed + 1);
-      DevBuf<uint64_t> rows_d(s);
-      h2d(rows_d.p, rows.data(), s);
-      DevBuf<float> sample((size_t)s * d);
-      LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(s * d, 256), 256, 0, x_sample, rows_d.p, s, (int)d, sample.p);
-      sync_stream();
+      const uint64_t s = s_pq;
+      DevBuf<float>& sample = sample_pq;
       if (am == METRIC_L2) {
         DevBuf<uint32_t> part(s);
         assign_f32(sample.p, s, d, ix->centroids.p, K, METRIC_L2, nullptr, part.p, nullptr, nullptr, nullptr);

@@ -325,6 +325,44 @@ __device__ __forceinline__ void warp_select(const int32_t (&key)[PER], const uin
   }
 }
 
+// one warp, values in SHARED memory (cnt of them, strided over the lanes): the `rounds` smallest
+// (key,pos), ascending, handed to emit(r, key, pos) on every lane
+template <class Emit>
+__device__ __forceinline__ void warp_select_smem(const int32_t* keys, const uint32_t* poss, uint32_t cnt,
+                                                 int rounds, int lane, Emit emit) {
+  int32_t pk = 0;
+  uint32_t pp = 0;
+  for (int r = 0; r < rounds; ++r) {
+    int32_t bk = 0x7fffffff;
+    uint32_t bp = 0xffffffffu;
+    bool has = false;
+    for (uint32_t i = lane; i < cnt; i += 32) {
+      const int32_t kk = keys[i];
+      const uint32_t ps = poss[i];
+      if ((r == 0 || ki_less(pk, pp, kk, ps)) && (!has || ki_less(kk, ps, bk, bp))) { bk = kk; bp = ps; has = true; }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const int32_t ok2 = __shfl_xor_sync(0xffffffffu, bk, off);
+      const uint32_t op = __shfl_xor_sync(0xffffffffu, bp, off);
+      const int oh = __shfl_xor_sync(0xffffffffu, (int)has, off);
+      if (oh && (!has || ki_less(ok2, op, bk, bp))) { bk = ok2; bp = op; has = true; }
+    }
+    if (!has) break;  // uniform
+    pk = bk;
+    pp = bp;
+    emit(r, bk, bp);
+  }
+}
+
+// k <= 16.  Per chunk of 4096 rows every WARP works on its own 512 rows without block barriers:
+//   Tw = k-th smallest of its 32 lane minima (an upper bound of the warp's k-th smallest element),
+//   the <= (k-1)*16+1 elements <= Tw are compacted into the warp's shared-memory list, its k smallest
+//   are selected; then warp 0 merges the 8 x k warp winners with the winners carried from earlier
+//   chunks.  All comparisons are on (total-order key, position): ties keep the earlier rows.
+constexpr int SCAN_KFAST = 16;
+constexpr int SCAN_WLIST = (SCAN_KFAST - 1) * 16 + 1;  // 241
+
 template <int METRIC>
 __global__ void __launch_bounds__(256)
 ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restrict__ centroids,
@@ -334,18 +372,17 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
                   const uint64_t* __restrict__ row_ids, int k, float* __restrict__ cand_d,
                   uint64_t* __restrict__ cand_id, uint32_t* __restrict__ cand_cnt) {
   constexpr int RPT = SCAN_CHUNK / 256;  // rows per thread and chunk (16)
-  constexpr int PER = 18;                // list entries per lane of the selecting warp: 32*18 >= 32*16+32+1
   extern __shared__ float smem[];
   float* lut = smem;          // [M*256]
   float* qr = lut + M * 256;  // [d]
-  __shared__ int32_t tmin_key[256];
-  __shared__ uint32_t tmin_pos[256];
-  __shared__ int32_t list_key[32 * PER];
-  __shared__ uint32_t list_pos[32 * PER];
-  __shared__ int32_t car_key[32];   // winners carried across chunks
-  __shared__ uint32_t car_pos[32];
-  __shared__ int32_t s_tkey;
-  __shared__ uint32_t s_tpos, s_count, s_nw;
+  __shared__ int32_t wl_key[8][SCAN_WLIST];   // per-warp compacted candidates
+  __shared__ uint32_t wl_pos[8][SCAN_WLIST];
+  __shared__ int32_t fin_key[8 * SCAN_KFAST + SCAN_KFAST];  // 8 x k warp winners + carried winners
+  __shared__ uint32_t fin_pos[8 * SCAN_KFAST + SCAN_KFAST];
+  __shared__ uint32_t fin_cnt;
+  __shared__ int32_t car_key[SCAN_KFAST];
+  __shared__ uint32_t car_pos[SCAN_KFAST];
+  __shared__ uint32_t s_nw;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pi = blockIdx.x;
   const size_t qi = blockIdx.y;
@@ -372,9 +409,11 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
     int32_t key[RPT];
     int32_t mk = 0x7fffffff;
     uint32_t mp = 0xffffffffu;
+    // rows of warp w in this chunk: c0 + w*512 + lane + 32*u  (a warp owns a contiguous 512-row slab)
+    const uint32_t wbase = warp * (RPT * 32);
 #pragma unroll
     for (int u = 0; u < RPT; ++u) {
-      const uint32_t j = tid + 256 * u;
+      const uint32_t j = wbase + lane + 32 * u;
       key[u] = 0x7fffffff;
       if (j < clen) {
         float dist = 0.0f;
@@ -399,59 +438,83 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
         if (key[u] < mk) { mk = key[u]; mp = c0 + j; }  // ascending position: first minimum wins
       }
     }
-    tmin_key[tid] = mk;
-    tmin_pos[tid] = mp;  // 0xffffffff = this thread has no row in the chunk
-    if (tid == 0) s_count = 0;
-    __syncthreads();
-    if (warp == 0) {  // T = k-th smallest thread minimum (or "everything" if fewer than k threads have rows)
-      int32_t tk[8];
-      uint32_t tp[8];
-      bool ok[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        tk[u] = tmin_key[lane + 32 * u];
-        tp[u] = tmin_pos[lane + 32 * u];
-        ok[u] = tp[u] != 0xffffffffu;
-      }
-      int32_t lk = 0x7fffffff;
-      uint32_t lp = 0xffffffffu;
+    // ---- warp-local: Tw = k-th smallest lane minimum (or "everything" if < k lanes have rows)
+    int32_t tk = 0x7fffffff;
+    uint32_t tp = 0xffffffffu;
+    {
+      int32_t pk = 0;
+      uint32_t pp = 0;
       int got = 0;
-      warp_select<8>(tk, tp, ok, k, [&](int r, int32_t kk, uint32_t pp) { lk = kk; lp = pp; got = r + 1; });
-      if (lane == 0) {
-        if (got < k) { lk = 0x7fffffff; lp = 0xffffffffu; }
-        s_tkey = lk;
-        s_tpos = lp;
+      for (int r = 0; r < k; ++r) {
+        const bool elig = mp != 0xffffffffu && (r == 0 || ki_less(pk, pp, mk, mp));
+        int32_t bk = elig ? mk : 0x7fffffff;
+        uint32_t bp = elig ? mp : 0xffffffffu;
+        bool has = elig;
+#pragma unroll
+        for (int off2 = 16; off2 >= 1; off2 >>= 1) {
+          const int32_t ok2 = __shfl_xor_sync(0xffffffffu, bk, off2);
+          const uint32_t op = __shfl_xor_sync(0xffffffffu, bp, off2);
+          const int oh = __shfl_xor_sync(0xffffffffu, (int)has, off2);
+          if (oh && (!has || ki_less(ok2, op, bk, bp))) { bk = ok2; bp = op; has = true; }
+        }
+        if (!has) break;
+        pk = bk; pp = bp; got = r + 1;
       }
+      if (got == k) { tk = pk; tp = pp; }
     }
-    __syncthreads();
-    const int32_t tkey = s_tkey;
-    const uint32_t tpos = s_tpos;
+    // ---- compact the warp's elements <= Tw (ballot-ranked: deterministic order, no atomics)
+    uint32_t wcnt = 0;
 #pragma unroll
     for (int u = 0; u < RPT; ++u) {
-      const uint32_t j = tid + 256 * u;
-      if (j < clen && !ki_less(tkey, tpos, key[u], c0 + j)) {  // (key,pos) <= T
-        const uint32_t at = atomicAdd(&s_count, 1u);
-        list_key[at] = key[u];
-        list_pos[at] = c0 + j;
+      const uint32_t j = wbase + lane + 32 * u;
+      const bool take = j < clen && !ki_less(tk, tp, key[u], c0 + j);
+      const unsigned bal = __ballot_sync(0xffffffffu, take);
+      if (take) {
+        const uint32_t at = wcnt + __popc(bal & ((1u << lane) - 1));
+        wl_key[warp][at] = key[u];
+        wl_pos[warp][at] = c0 + j;
       }
+      wcnt += __popc(bal);
+    }
+    __syncwarp();
+    // ---- the warp's k smallest -> block list
+    warp_select_smem(wl_key[warp], wl_pos[warp], wcnt, k, lane, [&](int r, int32_t kk, uint32_t pp2) {
+      if (lane == 0) { fin_key[warp * SCAN_KFAST + r] = kk; fin_pos[warp * SCAN_KFAST + r] = pp2; }
+    });
+    if (lane == 0) {
+      const int got = (int)min(wcnt, (uint32_t)k);
+      for (int r = got; r < k; ++r) fin_pos[warp * SCAN_KFAST + r] = 0xffffffffu;  // unused slots
     }
     __syncthreads();
-    if (warp == 0) {  // k smallest of (carried winners + compacted list); order of the list is irrelevant
-      const uint32_t cnt = s_count, nw = s_nw;
-      int32_t vk[PER];
-      uint32_t vp[PER];
-      bool ok[PER];
-#pragma unroll
-      for (int u = 0; u < PER; ++u) {
-        const uint32_t i = lane + 32 * u;
-        ok[u] = i < cnt + nw;
-        vk[u] = !ok[u] ? 0x7fffffff : (i < cnt ? list_key[i] : car_key[i - cnt]);
-        vp[u] = !ok[u] ? 0xffffffffu : (i < cnt ? list_pos[i] : car_pos[i - cnt]);
+    if (warp == 0) {  // merge: 8 x k warp winners + carried winners -> k block winners
+      const uint32_t nw = s_nw;
+      // compact valid entries into a dense list in place (lane-parallel, order irrelevant)
+      uint32_t cnt = 0;
+      for (int base = 0; base < 8 * SCAN_KFAST; base += 32) {
+        const int i = base + lane;
+        const int w2 = i / SCAN_KFAST, r2 = i % SCAN_KFAST;
+        const bool ok = r2 < k && fin_pos[i] != 0xffffffffu;
+        const int32_t kk = fin_key[i];
+        const uint32_t ps = fin_pos[i];
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        __syncwarp();
+        if (ok) {
+          const uint32_t at = cnt + __popc(bal & ((1u << lane) - 1));
+          wl_key[0][at] = kk;  // warp 0's own list is free again
+          wl_pos[0][at] = ps;
+        }
+        cnt += __popc(bal);
+        (void)w2;
       }
+      if (lane < (int)nw) {
+        wl_key[0][cnt + lane] = car_key[lane];
+        wl_pos[0][cnt + lane] = car_pos[lane];
+      }
+      cnt += nw;
       __syncwarp();
       int got = 0;
-      warp_select<PER>(vk, vp, ok, k, [&](int r, int32_t kk, uint32_t pp) {
-        if (lane == 0) { car_key[r] = kk; car_pos[r] = pp; }
+      warp_select_smem(wl_key[0], wl_pos[0], cnt, k, lane, [&](int r, int32_t kk, uint32_t pp2) {
+        if (lane == 0) { car_key[r] = kk; car_pos[r] = pp2; }
         got = r + 1;
       });
       if (lane == 0) s_nw = got;
@@ -464,6 +527,7 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
     cand_id[slot * k + i] = row_ids[off + car_pos[i]];
   }
   if (tid == 0) cand_cnt[slot] = nw;
+  (void)fin_cnt;
 }
 
 // global merge per query: ascending (distance, row id), first k
@@ -584,7 +648,7 @@ static void scan_launch(int kmax, dim3 grid, size_t smem, const float* queries, 
                         const uint32_t* probe_ids, int np, const uint64_t* part_offsets,
                         const uint8_t* codes, const uint64_t* row_ids, int k, float* cand_d,
                         uint64_t* cand_id, uint32_t* cand_cnt) {
-  if (k <= 32) {
+  if (k <= SCAN_KFAST) {
     const size_t smem_fast = sizeof(float) * ((size_t)M * 256 + d);
     set_smem(ivfpq_scan_kernel<METRIC>, smem_fast);
     LB2_LAUNCH("pq_scan", (ivfpq_scan_kernel<METRIC>), grid, 256, smem_fast, queries, d, centroids,
