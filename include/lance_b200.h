@@ -211,6 +211,30 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
                            const uint64_t* row_ids /* NULL = 0..n */, lb2_index** out,
                            lb2_build_stats* stats /* nullable */);
 
+/* ---- IVF_FLAT: IVFIndex<FlatIndex, FlatQuantizer> (lance-index/src/vector/flat/{index,storage}.rs) --
+ * The partitions hold the raw f32 vectors (normalised first when the metric is cosine, as
+ * IvfTransformer::new_flat does, lance-index/src/vector/ivf.rs:149-185); search scores every row of
+ * the probed partitions exactly (FlatDistanceCal::distance_all, flat/storage.rs:397-403) and keeps
+ * the k smallest (FlatIndex::search, flat/index.rs:82-177).  lb2_index_search / _info / _destroy
+ * work on both index kinds. */
+typedef struct {
+  uint32_t num_partitions;
+  lb2_kmeans_params ivf;
+  uint64_t seed;
+} lb2_ivfflat_build_params;
+void lb2_ivfflat_build_params_default(lb2_ivfflat_build_params* p);
+lb2_status lb2_ivfflat_build(const void* data, uint64_t n, uint32_t d, lb2_dtype dtype,
+                             lb2_metric metric, const lb2_ivfflat_build_params* params,
+                             const uint64_t* row_ids, lb2_index** out, lb2_build_stats* stats);
+lb2_status lb2_index_create_flat(const void* centroids, uint32_t k, uint32_t d, lb2_dtype dtype,
+                                 lb2_metric metric, lb2_index** out);
+/* vectors [n][d] (already normalised for cosine), grouped by partition on the device (stable) */
+lb2_status lb2_index_load_flat(lb2_index* index, const uint32_t* part_ids, const void* vectors,
+                               const uint64_t* row_ids, uint64_t n);
+lb2_status lb2_index_export_flat(const lb2_index* index, void* centroids_out,
+                                 uint64_t* part_offsets_out, void* vectors_out,
+                                 uint64_t* row_ids_out);
+
 /* ---- multi-GPU (one process per GPU; NCCL all-reduce of centroid sums during training) ------- */
 /* unique_id is the 128-byte ncclUniqueId produced by rank 0 (lb2_comm_unique_id) and broadcast by
  * the host runtime (torch.distributed / MPI / the Rust side). */

@@ -11,7 +11,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import (BF16, COSINE, DOT, F16, F32, L2, METRICS, U8, BuildParams, BuildStats,
+from ._lib import (BF16, COSINE, DOT, F16, F32, L2, METRICS, U8, BuildParams, BuildStats, FlatBuildParams,
                    DeviceArray, KMeansParams as _CKMeansParams, LanceB200Error, PinnedArray,
                    PQParams as _CPQParams, as_ptr, check, device_count, lib)
 
@@ -19,7 +19,7 @@ __all__ = ["device_count", "DeviceArray", "PinnedArray", "LanceB200Error", "trai
            "compute_partitions", "kmeans_find_partitions", "compute_residual", "normalize_fsl",
            "l2_distance_batch", "dot_distance_batch", "PQBuildParams", "ProductQuantizer",
            "build_distance_table_l2", "compute_pq_distance", "flat_topk", "IvfPqIndex",
-           "IvfBuildParams", "launch_count", "profile"]
+           "IvfBuildParams", "IvfFlatIndex", "launch_count", "profile"]
 
 
 def _metric(m):
@@ -37,6 +37,25 @@ def _f32(a):
         assert a.dtype == np.float32
         return a
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+_DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float16): F16, np.dtype(np.uint8): U8}
+
+
+def _typed(a, bf16=False):
+    """(array, lb2_dtype): f32 / f16 / u8 buffers are passed as they are (bf16 = uint16 + bf16=True)."""
+    if bf16:
+        return np.ascontiguousarray(a, dtype=np.uint16), BF16
+    if isinstance(a, (DeviceArray, PinnedArray)):
+        return a, _DTYPES[np.dtype(a.dtype)]
+    a = np.asarray(a)
+    if a.dtype not in _DTYPES:
+        a = a.astype(np.float32)
+    return np.ascontiguousarray(a), _DTYPES[a.dtype]
+
+
+def _model_np(dt):
+    return {F32: np.float32, F16: np.float16, BF16: np.uint16, U8: np.float32}[dt]
 
 
 def set_device(i):
@@ -138,19 +157,19 @@ class KMeans:
 def train_kmeans(array, dimension, k, max_iters=50, redos=1, distance_type="l2", sample_rate=256,
                  balance_factor=0.0, tolerance=1e-4, seed=0, centroids=None):
     """lance_index::vector::kmeans::train_kmeans (kmeans.rs:1309-1347)."""
-    array = _f32(array)
+    array, dt = _typed(array)
     n = int(np.prod(array.shape)) // dimension
     p = _CKMeansParams()
     lib().lb2_kmeans_params_default(C.byref(p))
     p.max_iters, p.redos, p.sample_rate, p.seed = max_iters, redos, sample_rate, seed
     p.balance_factor, p.tolerance, p.metric = balance_factor, tolerance, _metric(distance_type)
-    init = None if centroids is None else _f32(centroids)
+    init = None if centroids is None else np.ascontiguousarray(centroids, dtype=_model_np(dt))
     ip, _k0 = as_ptr(init)
     p.init_centroids = ip.value if ip is not None else None
-    out = np.empty((k, dimension), np.float32)
+    out = np.empty((k, dimension), _model_np(dt))
     loss, iters = C.c_double(0), C.c_uint32(0)
     ap, _k1 = as_ptr(array)
-    check(lib().lb2_kmeans_train(ap, C.c_uint64(n), C.c_uint32(dimension), C.c_int(F32),
+    check(lib().lb2_kmeans_train(ap, C.c_uint64(n), C.c_uint32(dimension), C.c_int(dt),
                                  C.c_uint32(k), C.byref(p), C.c_void_p(out.ctypes.data),
                                  C.byref(loss), C.byref(iters)))
     return KMeans(out, dimension, distance_type, loss.value, iters.value)
@@ -159,7 +178,8 @@ def train_kmeans(array, dimension, k, max_iters=50, redos=1, distance_type="l2",
 def compute_partitions(centroids, vectors, distance_type="l2"):
     """compute_partitions_arrow_array (kmeans.rs:1187-1246) ->
     (part_ids u32[n], dists f32[n], valid bool[n]); valid False == the reference's None."""
-    centroids, vectors = _f32(centroids), _f32(vectors)
+    vectors, dt = _typed(vectors)
+    centroids = np.ascontiguousarray(centroids, dtype=_model_np(dt))
     k, d = centroids.shape
     n = vectors.shape[0]
     part = np.empty(n, np.uint32)
@@ -167,7 +187,7 @@ def compute_partitions(centroids, vectors, distance_type="l2"):
     valid = np.empty(n, np.uint8)
     cp, _k1 = as_ptr(centroids)
     vp, _k2 = as_ptr(vectors)
-    check(lib().lb2_compute_partitions(cp, C.c_uint32(k), C.c_uint32(d), C.c_int(F32),
+    check(lib().lb2_compute_partitions(cp, C.c_uint32(k), C.c_uint32(d), C.c_int(dt),
                                        C.c_int(_metric(distance_type)), vp, C.c_uint64(n),
                                        C.c_void_p(part.ctypes.data), C.c_void_p(dist.ctypes.data),
                                        C.c_void_p(valid.ctypes.data)))
@@ -345,7 +365,7 @@ class IvfPqIndex:
     def build(cls, data, distance_type="l2", params=None, row_ids=None):
         """IvfIndexBuilder::build (builder.rs:236): create_index("IVF_PQ")."""
         params = params or IvfBuildParams()
-        data = _f32(data)
+        data, dt = _typed(data)
         n, d = data.shape
         bp = BuildParams()
         lib().lb2_ivfpq_build_params_default(C.byref(bp))
@@ -369,10 +389,12 @@ class IvfPqIndex:
         st = BuildStats()
         dp, _k1 = as_ptr(data)
         rp, _k2 = as_ptr(rid)
-        check(lib().lb2_ivfpq_build(dp, C.c_uint64(n), C.c_uint32(d), C.c_int(F32),
+        check(lib().lb2_ivfpq_build(dp, C.c_uint64(n), C.c_uint32(d), C.c_int(dt),
                                     C.c_int(_metric(distance_type)), C.byref(bp), rp, C.byref(h),
                                     C.byref(st)))
-        return cls(h, st)
+        ix = cls(h, st)
+        ix._dt = dt
+        return ix
 
     @classmethod
     def from_parts(cls, centroids, codebook, part_ids, codes, row_ids=None, distance_type="l2", num_bits=8):
@@ -422,7 +444,11 @@ class IvfPqIndex:
         """to_table(nearest={q,k,nprobes}) for a batch of queries: IVFIndex::find_partitions +
         search_in_partition + global merge (v2.rs:455-500, scanner.rs:3450-3466).
         `out` = optional (row_ids, dists) arrays (numpy/Pinned/Device) to write into."""
-        queries = _f32(queries)
+        dt = getattr(self, "_dt", F32)
+        if isinstance(queries, (DeviceArray, PinnedArray)):
+            assert _DTYPES[np.dtype(queries.dtype)] == dt
+        else:
+            queries = np.ascontiguousarray(queries, dtype={F32: np.float32, F16: np.float16, U8: np.uint8, BF16: np.uint16}[dt])
         nq = queries.shape[0]
         if out is None:
             ids, dists = np.empty((nq, k), np.uint64), np.empty((nq, k), np.float32)
@@ -445,3 +471,58 @@ class IvfPqIndex:
             self.close()
         except Exception:
             pass
+
+
+class IvfFlatIndex(IvfPqIndex):
+    """Device-resident IVFIndex<FlatIndex, FlatQuantizer> (IVF_FLAT): exact distances inside the
+    probed partitions (lance-index/src/vector/flat/{index,storage}.rs)."""
+
+    @classmethod
+    def build(cls, data, distance_type="l2", num_partitions=256, max_iters=50, sample_rate=256, seed=0,
+              centroids=None, row_ids=None):
+        data, dt = _typed(data)
+        n, d = data.shape
+        bp = FlatBuildParams()
+        lib().lb2_ivfflat_build_params_default(C.byref(bp))
+        bp.num_partitions = num_partitions
+        bp.ivf.max_iters, bp.ivf.sample_rate, bp.ivf.seed, bp.seed = max_iters, sample_rate, seed, seed
+        keep = None
+        if centroids is not None:
+            keep = _f32(centroids)
+            bp.ivf.init_centroids = as_ptr(keep)[0].value
+        rid = None if row_ids is None else np.ascontiguousarray(row_ids, dtype=np.uint64)
+        h = C.c_void_p()
+        st = BuildStats()
+        dp, _k1 = as_ptr(data)
+        rp, _k2 = as_ptr(rid)
+        check(lib().lb2_ivfflat_build(dp, C.c_uint64(n), C.c_uint32(d), C.c_int(dt),
+                                      C.c_int(_metric(distance_type)), C.byref(bp), rp, C.byref(h), C.byref(st)))
+        ix = cls(h, st)
+        ix._dt = dt
+        return ix
+
+    @classmethod
+    def from_parts(cls, centroids, part_ids, vectors, row_ids=None, distance_type="l2"):
+        centroids, vectors = _f32(centroids), _f32(vectors)
+        k, d = centroids.shape
+        h = C.c_void_p()
+        check(lib().lb2_index_create_flat(C.c_void_p(centroids.ctypes.data), C.c_uint32(k), C.c_uint32(d),
+                                          C.c_int(F32), C.c_int(_metric(distance_type)), C.byref(h)))
+        ix = cls(h)
+        part_ids = np.ascontiguousarray(part_ids, dtype=np.uint32)
+        rid = None if row_ids is None else np.ascontiguousarray(row_ids, dtype=np.uint64)
+        rp, _k = as_ptr(rid)
+        vp, _k2 = as_ptr(vectors)
+        check(lib().lb2_index_load_flat(h, C.c_void_p(part_ids.ctypes.data), vp, rp, C.c_uint64(part_ids.size)))
+        return ix
+
+    def export(self):
+        i = self.info()
+        K, d, n = i["num_partitions"], i["dimension"], i["num_rows"]
+        cent = np.empty((K, d), np.float32)
+        off = np.empty(K + 1, np.uint64)
+        vec = np.empty((n, d), np.float32)
+        rid = np.empty(n, np.uint64)
+        check(lib().lb2_index_export_flat(self._h, C.c_void_p(cent.ctypes.data), C.c_void_p(off.ctypes.data),
+                                          C.c_void_p(vec.ctypes.data), C.c_void_p(rid.ctypes.data)))
+        return dict(centroids=cent, part_offsets=off, vectors=vec, row_ids=rid)

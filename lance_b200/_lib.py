@@ -43,6 +43,10 @@ class BuildParams(C.Structure):
                 ("seed", C.c_uint64)]
 
 
+class FlatBuildParams(C.Structure):
+    _fields_ = [("num_partitions", C.c_uint32), ("ivf", KMeansParams), ("seed", C.c_uint64)]
+
+
 class BuildStats(C.Structure):
     _fields_ = [("ms_ivf_train", C.c_float), ("ms_pq_train", C.c_float), ("ms_transform", C.c_float),
                 ("ms_group", C.c_float), ("ms_total", C.c_float), ("ivf_iters", C.c_uint32),
@@ -59,7 +63,8 @@ EXPORTS = [
     "lb2_pq_train", "lb2_pq_encode", "lb2_pq_build_lut", "lb2_pq_scan", "lb2_flat_topk",
     "lb2_ivfpq_transform", "lb2_index_create", "lb2_index_load", "lb2_index_search",
     "lb2_index_info", "lb2_index_export", "lb2_index_destroy", "lb2_ivfpq_build_params_default",
-    "lb2_ivfpq_build", "lb2_comm_unique_id", "lb2_comm_init", "lb2_comm_destroy",
+    "lb2_ivfpq_build", "lb2_ivfflat_build_params_default", "lb2_ivfflat_build", "lb2_index_create_flat",
+    "lb2_index_load_flat", "lb2_index_export_flat", "lb2_comm_unique_id", "lb2_comm_init", "lb2_comm_destroy",
 ]
 
 _lib = None
@@ -82,7 +87,7 @@ def lib():
         for name in EXPORTS:
             if name not in ("lb2_version", "lb2_last_error", "lb2_device_count", "lb2_profile_dump",
                             "lb2_kmeans_params_default", "lb2_pq_params_default",
-                            "lb2_ivfpq_build_params_default"):
+                            "lb2_ivfpq_build_params_default", "lb2_ivfflat_build_params_default"):
                 getattr(L, name).restype = C.c_int
         _lib = L
     return _lib

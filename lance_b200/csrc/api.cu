@@ -1,5 +1,8 @@
 // api.cu -- the extern "C" surface declared in include/lance_b200.h, the per-thread runtime
 // context, the device-resident index handle and the whole-index builder.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cmath>
 
@@ -123,11 +126,90 @@ __global__ void group_kernel(const uint32_t* __restrict__ members, uint64_t n, i
   for (int m = 0; m < M; ++m) codes_out[g * M + m] = codes[(size_t)src * M + m];
 }
 
+__global__ void group_vectors_kernel(const uint32_t* __restrict__ members, uint64_t n, int d,
+                                     const float* __restrict__ vectors, const uint64_t* __restrict__ row_ids,
+                                     float* __restrict__ vectors_out, uint64_t* __restrict__ row_ids_out) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 per thread
+  const int d4 = d >> 2;
+  if (g >= n * d4) return;
+  const uint64_t r = g / d4;
+  const int c = g % d4;
+  const uint32_t src = members[r];
+  reinterpret_cast<float4*>(vectors_out)[g] = reinterpret_cast<const float4*>(vectors)[(uint64_t)src * d4 + c];
+  if (c == 0) row_ids_out[r] = row_ids ? row_ids[src] : (uint64_t)src;
+}
+
 __global__ void widen_offsets_kernel(const uint32_t* __restrict__ off32, int K,
                                      uint64_t* __restrict__ off64) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i <= K) off64[i] = off32[i];
 }
+
+// ---- element types ---------------------------------------------------------------------------------
+// f16 / bf16 / u8 buffers are converted to f32 on the device at the boundary and every loop runs
+// with the reference's f32 semantics (what the reference itself does for Int8 vectors,
+// rust/lance/src/index/vector/ivf.rs:1917-1929; its f16 paths accumulate in f16 / use a -ffast-math
+// C kernel, so for f16 inputs parity with the reference is by tolerance).
+// Model outputs (centroids, codebook, residuals, normalised vectors) use the input's element type,
+// except for u8 inputs, whose model is f32.
+static size_t dtype_size(lb2_dtype dt) { return dt == LB2_F32 ? 4 : (dt == LB2_U8 ? 1 : 2); }
+static lb2_dtype model_dtype(lb2_dtype dt) { return dt == LB2_U8 ? LB2_F32 : dt; }
+
+__global__ void to_f32_kernel(const void* __restrict__ in, int dt, size_t count, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  if (dt == LB2_F16) out[i] = __half2float(reinterpret_cast<const __half*>(in)[i]);
+  else if (dt == LB2_BF16) out[i] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in)[i]);
+  else out[i] = (float)reinterpret_cast<const uint8_t*>(in)[i];
+}
+__global__ void from_f32_kernel(const float* __restrict__ in, int dt, size_t count, void* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  if (dt == LB2_F16) reinterpret_cast<__half*>(out)[i] = __float2half_rn(in[i]);
+  else reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(in[i]);
+}
+
+// typed input: device f32 view of a (host or device) buffer of `dt` elements
+struct VecIn {
+  InArg<float> f32;
+  InArg<uint8_t> raw;
+  DevBuf<float> conv;
+  const float* p = nullptr;
+  VecIn() = default;
+  VecIn(const void* ptr, size_t count, lb2_dtype dt) { set(ptr, count, dt); }
+  void set(const void* ptr, size_t count, lb2_dtype dt) {
+    if (!ptr || !count) { p = nullptr; return; }
+    if (dt == LB2_F32) { f32.set(ptr, count); p = f32.get(); return; }
+    raw.set(ptr, count * dtype_size(dt));
+    conv.alloc(count);
+    LB2_LAUNCH("convert_to_f32", to_f32_kernel, cdiv(count, 256), 256, 0, raw.get(), (int)dt, count, conv.p);
+    p = conv.p;
+  }
+  const float* get() const { return p; }
+};
+// typed output: kernels write f32; commit() converts to `dt` and copies to the caller's buffer
+struct VecOut {
+  OutArg<float> f32;
+  OutArg<uint8_t> raw;
+  DevBuf<float> tmp;
+  lb2_dtype dt = LB2_F32;
+  size_t count = 0;
+  float* p = nullptr;
+  VecOut(void* ptr, size_t cnt, lb2_dtype d) : dt(d), count(cnt) {
+    if (!ptr || !cnt) return;
+    if (dt == LB2_F32) { f32.set(ptr, cnt); p = f32.get(); return; }
+    raw.set(ptr, cnt * dtype_size(dt));
+    tmp.alloc(cnt);
+    p = tmp.p;
+  }
+  float* get() const { return p; }
+  void commit() {
+    if (!p) return;
+    if (dt == LB2_F32) { f32.commit(); return; }
+    LB2_LAUNCH("convert_from_f32", from_f32_kernel, cdiv(count, 256), 256, 0, tmp.p, (int)dt, count, raw.get());
+    raw.commit();
+  }
+};
 
 static void require_f32(lb2_dtype dt, const char* what) {
   if (dt != LB2_F32)
@@ -149,6 +231,9 @@ using namespace lb2;
 
 // the handle
 struct lb2_index {
+  int kind = 0;  // 0 = IVF_PQ, 1 = IVF_FLAT
+  lb2_dtype dtype = LB2_F32;  // element type of the vectors / queries the caller passes
+  DevBuf<float> vectors;  // IVF_FLAT: raw (normalised for cosine) vectors in partition order
   int K = 0, d = 0, M = 0, nbits = 8, metric = 0;
   uint64_t n = 0;
   DevBuf<float> centroids, codebook;
@@ -171,6 +256,24 @@ static void index_load_dev(lb2_index* ix, const uint32_t* part_ids, const uint8_
   if (n)
     LB2_LAUNCH("group_by_partition", group_kernel, cdiv(n, 256), 256, 0, ms.members.p, n, ix->M,
                codes, row_ids, ix->codes.p, ix->row_ids.p);
+  ix->n = n;
+  sync_stream();
+}
+
+static void index_load_flat_dev(lb2_index* ix, const uint32_t* part_ids, const float* vectors,
+                                const uint64_t* row_ids, uint64_t n) {
+  LB2_REQUIRE(n < 0xffffffffull, "more than 2^32-1 rows per index shard");
+  LB2_REQUIRE(ix->d % 4 == 0, "IVF_FLAT needs a dimension that is a multiple of 4");
+  MemberSort ms;
+  ms.run(part_ids, nullptr, n, ix->K, 1, nullptr);
+  ix->part_offsets.alloc(ix->K + 1);
+  LB2_LAUNCH("widen_offsets", widen_offsets_kernel, cdiv(ix->K + 1, 256), 256, 0, ms.offsets.p,
+             ix->K, ix->part_offsets.p);
+  ix->vectors.alloc(std::max<uint64_t>(1, n * ix->d));
+  ix->row_ids.alloc(std::max<uint64_t>(1, n));
+  if (n)
+    LB2_LAUNCH("group_vectors", group_vectors_kernel, cdiv(n * (ix->d / 4), 256), 256, 0, ms.members.p, n,
+               ix->d, vectors, row_ids, ix->vectors.p, ix->row_ids.p);
   ix->n = n;
   sync_stream();
 }
@@ -363,12 +466,11 @@ void lb2_ivfpq_build_params_default(lb2_ivfpq_build_params* p) {
 lb2_status lb2_distance_batch(const void* from, const void* to, uint64_t n, uint32_t d,
                               lb2_dtype dtype, lb2_metric metric, float* out) {
   LB2_API_BEGIN
-  require_f32(dtype, "distance_batch");
   const int m = metric_of(metric);
   if (m == METRIC_COSINE) fail(LB2_UNSUPPORTED, "cosine_distance_batch is not implemented yet");
   LB2_REQUIRE(d > 0, "dimension must be positive");
   LB2_REQUIRE(n < (1ull << 31), "too many rows");
-  InArg<float> f(from, d), t(to, (size_t)n * d);
+  VecIn f(from, d, dtype), t(to, (size_t)n * d, dtype);
   OutArg<float> o(out, n);
   assign_f32(f.get(), 1, d, t.get(), (int)n, m, nullptr, nullptr, nullptr, nullptr, o.get());
   o.commit();
@@ -378,9 +480,8 @@ lb2_status lb2_distance_batch(const void* from, const void* to, uint64_t n, uint
 
 lb2_status lb2_normalize(const void* vectors, uint64_t n, uint32_t d, lb2_dtype dtype, void* out) {
   LB2_API_BEGIN
-  require_f32(dtype, "normalize");
-  InArg<float> x(vectors, (size_t)n * d);
-  OutArg<float> o(out, (size_t)n * d);
+  VecIn x(vectors, (size_t)n * d, dtype);
+  VecOut o(out, (size_t)n * d, model_dtype(dtype));
   if (n) LB2_LAUNCH("normalize", normalize_kernel, cdiv(n, 128), 128, 0, x.get(), n, (int)d, o.get());
   o.commit();
   sync_stream();
@@ -391,7 +492,6 @@ lb2_status lb2_kmeans_train(const void* data, uint64_t n, uint32_t d, lb2_dtype 
                             const lb2_kmeans_params* params, void* centroids_out, double* loss_out,
                             uint32_t* iters_out) {
   LB2_API_BEGIN
-  require_f32(dtype, "kmeans_train");
   LB2_REQUIRE(params && data && centroids_out, "null argument");
   const int m = metric_of(params->metric);
   if (m == METRIC_COSINE)
@@ -402,8 +502,8 @@ lb2_status lb2_kmeans_train(const void* data, uint64_t n, uint32_t d, lb2_dtype 
   const uint64_t kr0 = current_comm() ? current_comm()->nranks : 1;
   const uint64_t cap = (params->sample_rate * k + kr0 - 1) / kr0;
   const uint64_t rows = n > cap ? cap : n;
-  InArg<float> x(data, (size_t)rows * d);
-  InArg<float> init(params->init_centroids, (size_t)k * d);
+  VecIn x(data, (size_t)rows * d, dtype);
+  VecIn init(params->init_centroids, (size_t)k * d, model_dtype(dtype));
   DevBuf<float> cent((size_t)k * d);
   std::vector<double> loss;
   std::vector<uint32_t> iters;
@@ -411,7 +511,7 @@ lb2_status lb2_kmeans_train(const void* data, uint64_t n, uint32_t d, lb2_dtype 
   lloyd_train(x.get(), rows, d, 1, d, k, m, params->balance_factor / (float)(rows * kr),
               (int)params->max_iters, params->tolerance, params->seed, init.get(), cent.p, &loss,
               &iters);
-  OutArg<float> o(centroids_out, (size_t)k * d);
+  VecOut o(centroids_out, (size_t)k * d, model_dtype(dtype));
   d2d(o.get(), cent.p, (size_t)k * d);
   o.commit();
   sync_stream();
@@ -424,10 +524,9 @@ lb2_status lb2_compute_partitions(const void* centroids, uint32_t k, uint32_t d,
                                   lb2_metric metric, const void* vectors, uint64_t n,
                                   uint32_t* part_out, float* dist_out, uint8_t* valid_out) {
   LB2_API_BEGIN
-  require_f32(dtype, "compute_partitions");
   const int m = metric_of(metric);
   if (m == METRIC_COSINE) fail(LB2_INVALID_ARG, "compute_partitions: normalise and use L2 for cosine");
-  InArg<float> c(centroids, (size_t)k * d), x(vectors, (size_t)n * d);
+  VecIn c(centroids, (size_t)k * d, model_dtype(dtype)), x(vectors, (size_t)n * d, dtype);
   OutArg<uint32_t> p(part_out, n);
   OutArg<float> dd(dist_out, n);
   OutArg<uint8_t> v(valid_out, n);
@@ -441,12 +540,12 @@ lb2_status lb2_find_partitions(const void* centroids, uint32_t k, uint32_t d, lb
                                lb2_metric metric, const void* queries, uint64_t nq,
                                uint32_t nprobes, uint32_t* ids_out, float* dists_out) {
   LB2_API_BEGIN
-  require_f32(dtype, "find_partitions");
+
   const int m = metric_of(metric);
   if (m == METRIC_COSINE) fail(LB2_INVALID_ARG, "find_partitions: normalise and use L2 for cosine");
   const uint32_t np = std::min(nprobes, k);
   LB2_REQUIRE(np == nprobes, "nprobes %u exceeds the number of partitions %u", nprobes, k);
-  InArg<float> c(centroids, (size_t)k * d), q(queries, (size_t)nq * d);
+  VecIn c(centroids, (size_t)k * d, model_dtype(dtype)), q(queries, (size_t)nq * d, dtype);
   OutArg<uint32_t> ids(ids_out, (size_t)nq * np);
   OutArg<float> dd(dists_out, (size_t)nq * np);
   find_partitions_f32(c.get(), k, d, m, q.get(), nq, np, ids.get(), dd.get());
@@ -459,10 +558,9 @@ lb2_status lb2_compute_residual(const void* centroids, uint32_t k, uint32_t d, l
                                 const void* vectors, uint64_t n, const uint32_t* part_ids,
                                 void* out) {
   LB2_API_BEGIN
-  require_f32(dtype, "compute_residual");
-  InArg<float> c(centroids, (size_t)k * d), x(vectors, (size_t)n * d);
+  VecIn c(centroids, (size_t)k * d, model_dtype(dtype)), x(vectors, (size_t)n * d, dtype);
   InArg<uint32_t> p(part_ids, n);
-  OutArg<float> o(out, (size_t)n * d);
+  VecOut o(out, (size_t)n * d, model_dtype(dtype));
   if (n)
     LB2_LAUNCH("residual", residual_kernel, cdiv(n * d, 256), 256, 0, x.get(), c.get(), p.get(), n,
                (int)d, o.get());
@@ -475,16 +573,18 @@ lb2_status lb2_pq_train(const void* data, uint64_t n, uint32_t d, lb2_dtype dtyp
                         lb2_metric metric, const lb2_pq_params* params, void* codebook_out,
                         uint32_t* iters_out) {
   LB2_API_BEGIN
-  require_f32(dtype, "pq_train");
   LB2_REQUIRE(params && data && codebook_out, "null argument");
   const int m = metric_of(metric);
   if (m == METRIC_COSINE) fail(LB2_INVALID_ARG, "PQ code does not support cosine");  // pq/builder.rs:98-102
-  InArg<float> x(data, (size_t)n * d);
+  VecIn x(data, (size_t)n * d, dtype);
   const size_t cb = (size_t)(1u << params->num_bits) * d;
   DevBuf<float> codebook(cb);
   std::vector<uint32_t> iters;
-  pq_train_dev(x.get(), n, d, m, params, codebook.p, &iters);
-  OutArg<float> o(codebook_out, cb);
+  VecIn cb_init(params->codebook, cb, model_dtype(dtype));
+  lb2_pq_params pp = *params;
+  pp.codebook = cb_init.get();  // device f32 view of the user codebook (or NULL)
+  pq_train_dev(x.get(), n, d, m, &pp, codebook.p, &iters);
+  VecOut o(codebook_out, cb, model_dtype(dtype));
   d2d(o.get(), codebook.p, cb);
   o.commit();
   sync_stream();
@@ -498,7 +598,6 @@ lb2_status lb2_pq_encode(const void* codebook, uint32_t num_sub_vectors, uint32_
                          const uint32_t* part_ids, const void* vectors, uint64_t n,
                          uint8_t* codes_out) {
   LB2_API_BEGIN
-  require_f32(dtype, "pq_encode");
   if (num_bits != 8) fail(LB2_UNSUPPORTED, "num_bits %u is not implemented on the device", num_bits);
   const int M = num_sub_vectors, ds = d / M;
   LB2_REQUIRE(M > 0 && d % M == 0, "num_sub_vectors must divide vector dimension %u, but got %d", d, M);
@@ -506,18 +605,20 @@ lb2_status lb2_pq_encode(const void* codebook, uint32_t num_sub_vectors, uint32_
               "centroids and part_ids must be given together");
   const int m = metric_of(metric) == METRIC_DOT ? METRIC_DOT : METRIC_L2;
   if (!small_d_supported(ds)) fail(LB2_UNSUPPORTED, "PQ sub-vector width %d not supported yet", ds);
-  InArg<float> cb(codebook, (size_t)256 * d), x(vectors, (size_t)n * d);
+  VecIn cb(codebook, (size_t)256 * d, model_dtype(dtype)), x(vectors, (size_t)n * d, dtype);
   uint64_t kmax = 0;
-  InArg<float> c;
+  VecIn c;
   InArg<uint32_t> p(part_ids, n);
   if (centroids) {
     // the number of IVF centroids is implied by part_ids; stage what the caller holds
     if (is_device_ptr(centroids)) {
-      c.dev = (const float*)centroids;
+      if (model_dtype(dtype) != LB2_F32)
+        fail(LB2_UNSUPPORTED, "pq_encode: device-resident non-f32 centroids need their count; use lb2_ivfpq_transform");
+      c.p = (const float*)centroids;
     } else {
       for (uint64_t i = 0; i < n && !is_device_ptr(part_ids); ++i) kmax = std::max<uint64_t>(kmax, part_ids[i]);
       if (is_device_ptr(part_ids)) fail(LB2_INVALID_ARG, "host centroids with device part_ids");
-      c.set(centroids, (size_t)(kmax + 1) * d);
+      c.set(centroids, (size_t)(kmax + 1) * d, model_dtype(dtype));
     }
   }
   OutArg<uint8_t> o(codes_out, (size_t)n * M);
@@ -579,13 +680,14 @@ lb2_status lb2_ivfpq_transform(const void* centroids, uint32_t k, const void* co
                                lb2_dtype dtype, lb2_metric metric, const void* vectors, uint64_t n,
                                uint32_t* part_out, uint8_t* codes_out, uint8_t* valid_out) {
   LB2_API_BEGIN
-  require_f32(dtype, "ivfpq_transform");
+
   if (num_bits != 8) fail(LB2_UNSUPPORTED, "num_bits %u is not implemented on the device", num_bits);
   const int M = num_sub_vectors, ds = d / M;
   LB2_REQUIRE(M > 0 && d % M == 0, "num_sub_vectors must divide vector dimension %u, but got %d", d, M);
   if (!small_d_supported(ds)) fail(LB2_UNSUPPORTED, "PQ sub-vector width %d not supported yet", ds);
   const int m = metric_of(metric);
-  InArg<float> c(centroids, (size_t)k * d), cb(codebook, (size_t)256 * d), x(vectors, (size_t)n * d);
+  VecIn c(centroids, (size_t)k * d, model_dtype(dtype)), cb(codebook, (size_t)256 * d, model_dtype(dtype)),
+      x(vectors, (size_t)n * d, dtype);
   OutArg<uint32_t> p(part_out, n);
   OutArg<uint8_t> co(codes_out, (size_t)n * M), v(valid_out, n);
   DevBuf<uint8_t> vtmp;
@@ -611,17 +713,21 @@ lb2_status lb2_index_create(const void* centroids, uint32_t k, uint32_t d, lb2_d
                             lb2_metric metric, const void* codebook, uint32_t num_sub_vectors,
                             uint32_t num_bits, lb2_index** out) {
   LB2_API_BEGIN
-  require_f32(dtype, "index_create");
   LB2_REQUIRE(out && centroids && codebook, "null argument");
   LB2_REQUIRE(num_sub_vectors > 0 && d % num_sub_vectors == 0, "num_sub_vectors must divide d");
   if (num_bits != 8) fail(LB2_UNSUPPORTED, "num_bits %u is not implemented on the device", num_bits);
   ctx();
   lb2_index* ix = new lb2_index();
   ix->K = k; ix->d = d; ix->M = num_sub_vectors; ix->nbits = num_bits; ix->metric = metric_of(metric);
+  ix->dtype = dtype;
   ix->centroids.alloc((size_t)k * d);
   ix->codebook.alloc((size_t)256 * d);
-  LB2_CUDA(cudaMemcpyAsync(ix->centroids.p, centroids, sizeof(float) * k * d, cudaMemcpyDefault, ctx().stream));
-  LB2_CUDA(cudaMemcpyAsync(ix->codebook.p, codebook, sizeof(float) * 256 * d, cudaMemcpyDefault, ctx().stream));
+  {
+    VecIn c(centroids, (size_t)k * d, model_dtype(dtype)), cb(codebook, (size_t)256 * d, model_dtype(dtype));
+    d2d(ix->centroids.p, c.get(), (size_t)k * d);
+    d2d(ix->codebook.p, cb.get(), (size_t)256 * d);
+    sync_stream();
+  }
   ix->part_offsets.alloc(k + 1);
   ix->part_offsets.zero();
   sync_stream();
@@ -632,7 +738,7 @@ lb2_status lb2_index_create(const void* centroids, uint32_t k, uint32_t d, lb2_d
 lb2_status lb2_index_load(lb2_index* index, const uint32_t* part_ids, const uint8_t* codes,
                           const uint64_t* row_ids, uint64_t n) {
   LB2_API_BEGIN
-  LB2_REQUIRE(index, "null index");
+  LB2_REQUIRE(index && index->kind == 0, "not an IVF_PQ index");
   InArg<uint32_t> p(part_ids, n);
   InArg<uint8_t> c(codes, (size_t)n * index->M);
   InArg<uint64_t> r(row_ids, n);
@@ -646,7 +752,7 @@ lb2_status lb2_index_search(lb2_index* index, const void* queries, uint64_t nq, 
   LB2_API_BEGIN
   LB2_REQUIRE(index && k > 0 && nprobes > 0, "bad argument");
   const int d = index->d;
-  InArg<float> q(queries, (size_t)nq * d);
+  VecIn q(queries, (size_t)nq * d, index->dtype);
   const float* qp = q.get();
   DevBuf<float> qn;
   if (index->metric == METRIC_COSINE) {  // knn.rs:497-499
@@ -658,6 +764,13 @@ lb2_status lb2_index_search(lb2_index* index, const void* queries, uint64_t nq, 
   OutArg<float> od(dists_out, (size_t)nq * k);
   OutArg<uint32_t> oc(counts_out, nq);
   TagScope tg("search");
+  if (index->kind == 1) {
+    ivfflat_search_f32(index->centroids.p, index->K, d, index->metric, index->part_offsets.p,
+                       index->vectors.p, index->row_ids.p, qp, nq, k, nprobes, oi.get(), od.get(), oc.get());
+    oi.commit(); od.commit(); oc.commit();
+    sync_stream();
+    return LB2_OK;
+  }
   ivfpq_search_f32(index->centroids.p, index->K, d, index->metric, index->codebook.p, index->M,
                    index->nbits, index->part_offsets.p, index->codes.p, index->row_ids.p, qp, nq, k,
                    nprobes, oi.get(), od.get(), oc.get());
@@ -681,7 +794,7 @@ lb2_status lb2_index_info(const lb2_index* index, uint32_t* k, uint32_t* d, uint
 lb2_status lb2_index_export(const lb2_index* index, void* centroids_out, void* codebook_out,
                             uint64_t* part_offsets_out, uint8_t* codes_out, uint64_t* row_ids_out) {
   LB2_API_BEGIN
-  LB2_REQUIRE(index, "null index");
+  LB2_REQUIRE(index && index->kind == 0, "not an IVF_PQ index");
   cudaStream_t s = ctx().stream;
   if (centroids_out)
     LB2_CUDA(cudaMemcpyAsync(centroids_out, index->centroids.p, sizeof(float) * index->K * index->d, cudaMemcpyDefault, s));
@@ -694,6 +807,143 @@ lb2_status lb2_index_export(const lb2_index* index, void* centroids_out, void* c
   if (row_ids_out && index->n)
     LB2_CUDA(cudaMemcpyAsync(row_ids_out, index->row_ids.p, sizeof(uint64_t) * index->n, cudaMemcpyDefault, s));
   sync_stream();
+  LB2_API_END
+}
+
+void lb2_ivfflat_build_params_default(lb2_ivfflat_build_params* p) {
+  p->num_partitions = 256;
+  lb2_kmeans_params_default(&p->ivf);
+  p->ivf.balance_factor = 1.0f;
+  p->seed = 0;
+}
+
+lb2_status lb2_index_create_flat(const void* centroids, uint32_t k, uint32_t d, lb2_dtype dtype,
+                                 lb2_metric metric, lb2_index** out) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(out && centroids, "null argument");
+  ctx();
+  lb2_index* ix = new lb2_index();
+  ix->kind = 1; ix->K = k; ix->d = d; ix->M = 0; ix->nbits = 0; ix->metric = metric_of(metric);
+  ix->dtype = dtype;
+  ix->centroids.alloc((size_t)k * d);
+  {
+    VecIn c(centroids, (size_t)k * d, model_dtype(dtype));
+    d2d(ix->centroids.p, c.get(), (size_t)k * d);
+    sync_stream();
+  }
+  ix->part_offsets.alloc(k + 1);
+  ix->part_offsets.zero();
+  sync_stream();
+  *out = ix;
+  LB2_API_END
+}
+
+lb2_status lb2_index_load_flat(lb2_index* index, const uint32_t* part_ids, const void* vectors,
+                               const uint64_t* row_ids, uint64_t n) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(index && index->kind == 1, "not an IVF_FLAT index");
+  InArg<uint32_t> p(part_ids, n);
+  VecIn v(vectors, (size_t)n * index->d, index->dtype);
+  InArg<uint64_t> r(row_ids, n);
+  index_load_flat_dev(index, p.get(), v.get(), r.get(), n);
+  LB2_API_END
+}
+
+lb2_status lb2_index_export_flat(const lb2_index* index, void* centroids_out,
+                                 uint64_t* part_offsets_out, void* vectors_out,
+                                 uint64_t* row_ids_out) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(index && index->kind == 1, "not an IVF_FLAT index");
+  cudaStream_t s = ctx().stream;
+  if (centroids_out)
+    LB2_CUDA(cudaMemcpyAsync(centroids_out, index->centroids.p, sizeof(float) * index->K * index->d, cudaMemcpyDefault, s));
+  if (part_offsets_out)
+    LB2_CUDA(cudaMemcpyAsync(part_offsets_out, index->part_offsets.p, sizeof(uint64_t) * (index->K + 1), cudaMemcpyDefault, s));
+  if (vectors_out && index->n)
+    LB2_CUDA(cudaMemcpyAsync(vectors_out, index->vectors.p, sizeof(float) * index->n * index->d, cudaMemcpyDefault, s));
+  if (row_ids_out && index->n)
+    LB2_CUDA(cudaMemcpyAsync(row_ids_out, index->row_ids.p, sizeof(uint64_t) * index->n, cudaMemcpyDefault, s));
+  sync_stream();
+  LB2_API_END
+}
+
+lb2_status lb2_ivfflat_build(const void* data, uint64_t n, uint32_t d, lb2_dtype dtype,
+                             lb2_metric metric, const lb2_ivfflat_build_params* params,
+                             const uint64_t* row_ids, lb2_index** out, lb2_build_stats* stats) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(data && params && out, "null argument");
+  const int m = metric_of(metric);
+  const int K = params->num_partitions;
+  const uint64_t nranks = current_comm() ? current_comm()->nranks : 1;
+  LB2_REQUIRE(K > 0 && (nranks > 1 || n >= (uint64_t)K), "KMeans: can not train %d centroids with %llu vectors", K,
+              (unsigned long long)n);
+  Ctx& c = ctx();
+  cudaEvent_t ev[4];
+  for (auto& e : ev) LB2_CUDA(cudaEventCreate(&e));
+  LB2_CUDA(cudaEventRecord(ev[0], c.stream));
+  VecIn xin(data, (size_t)n * d, dtype);
+  const float* x = xin.get();
+  DevBuf<float> xnorm;
+  if (m == METRIC_COSINE) {  // NormalizeTransformer first (ivf.rs:158-166); stored vectors are normalised
+    xnorm.alloc((size_t)n * d);
+    LB2_LAUNCH("normalize", normalize_kernel, cdiv(n, 128), 128, 0, x, n, (int)d, xnorm.p);
+    x = xnorm.p;
+  }
+  const int am = m == METRIC_DOT ? METRIC_DOT : METRIC_L2;
+  lb2_index* ix = new lb2_index();
+  ix->kind = 1; ix->K = K; ix->d = d; ix->M = 0; ix->nbits = 0; ix->metric = m; ix->dtype = dtype;
+  ix->centroids.alloc((size_t)K * d);
+  std::vector<double> loss;
+  std::vector<uint32_t> iters;
+  try {
+    {
+      TagScope tg("ivf_train");
+      const uint64_t s = std::min<uint64_t>(n, ((uint64_t)K * params->ivf.sample_rate + nranks - 1) / nranks);
+      const float* xs = x;
+      DevBuf<float> sample;
+      if (s < n) {
+        std::vector<uint64_t> rows = sample_rows(n, s, params->seed);
+        DevBuf<uint64_t> rows_d(s);
+        h2d(rows_d.p, rows.data(), s);
+        sample.alloc((size_t)s * d);
+        LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(s * d, 256), 256, 0, x, rows_d.p, s, (int)d, sample.p);
+        sync_stream();
+        xs = sample.p;
+      }
+      VecIn init(params->ivf.init_centroids, (size_t)K * d, model_dtype(dtype));
+      lloyd_train(xs, s, d, 1, d, K, am, params->ivf.balance_factor / (float)(s * nranks),
+                  (int)params->ivf.max_iters, params->ivf.tolerance, params->ivf.seed, init.get(),
+                  ix->centroids.p, &loss, &iters);
+    }
+    LB2_CUDA(cudaEventRecord(ev[1], c.stream));
+    DevBuf<uint32_t> part(n);
+    {
+      TagScope tg("transform");
+      assign_f32(x, n, d, ix->centroids.p, K, am, nullptr, part.p, nullptr, nullptr, nullptr);
+    }
+    LB2_CUDA(cudaEventRecord(ev[2], c.stream));
+    InArg<uint64_t> rid(row_ids, n);
+    {
+      TagScope tg("group");
+      index_load_flat_dev(ix, part.p, x, rid.get(), n);
+    }
+    LB2_CUDA(cudaEventRecord(ev[3], c.stream));
+    sync_stream();
+  } catch (...) {
+    delete ix;
+    throw;
+  }
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    cudaEventElapsedTime(&stats->ms_ivf_train, ev[0], ev[1]);
+    cudaEventElapsedTime(&stats->ms_transform, ev[1], ev[2]);
+    cudaEventElapsedTime(&stats->ms_group, ev[2], ev[3]);
+    cudaEventElapsedTime(&stats->ms_total, ev[0], ev[3]);
+    stats->ivf_iters = iters.empty() ? 0 : iters[0];
+    stats->ivf_loss = loss.empty() ? 0.0 : loss[0];
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  *out = ix;
   LB2_API_END
 }
 
@@ -711,7 +961,6 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
                            lb2_metric metric, const lb2_ivfpq_build_params* params,
                            const uint64_t* row_ids, lb2_index** out, lb2_build_stats* stats) {
   LB2_API_BEGIN
-  require_f32(dtype, "ivfpq_build");
   LB2_REQUIRE(data && params && out, "null argument");
   const int m = metric_of(metric);
   const int K = params->num_partitions, M = params->pq.num_sub_vectors;
@@ -731,7 +980,7 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
   // on a second stream (copy engine) while both training phases gather their <= 65 536-row samples
   // straight out of the pinned buffer (zero-copy reads over PCIe), so the 0.5 GB copy hides behind
   // training; the transform waits on the copy.  Pageable host pointer: plain staged copy first.
-  InArg<float> xin;
+  VecIn xin;
   DevBuf<float> xbulk;
   const float* x = nullptr;         // complete device copy (valid after `copied`)
   const float* x_sample = nullptr;  // what the training samples are gathered from
@@ -741,7 +990,7 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
     cudaPointerAttributes pa;
     const bool attr_ok = cudaPointerGetAttributes(&pa, data) == cudaSuccess;
     if (!attr_ok) cudaGetLastError();
-    if (attr_ok && pa.type == cudaMemoryTypeHost && pa.devicePointer && m != METRIC_COSINE) {
+    if (attr_ok && pa.type == cudaMemoryTypeHost && pa.devicePointer && m != METRIC_COSINE && dtype == LB2_F32) {
       xbulk.alloc((size_t)n * d);
       LB2_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
       LB2_CUDA(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
@@ -749,7 +998,7 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
                     // zero-copy reads get no PCIe bandwidth while the copy engine is streaming
       x_sample = static_cast<const float*>(pa.devicePointer);
     } else {
-      xin.set(data, (size_t)n * d);
+      xin.set(data, (size_t)n * d, dtype);
       x = xin.get();
       x_sample = x;
     }
@@ -779,7 +1028,7 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
   const int am = m == METRIC_DOT ? METRIC_DOT : METRIC_L2;
 
   lb2_index* ix = new lb2_index();
-  ix->K = K; ix->d = d; ix->M = M; ix->nbits = 8; ix->metric = m;
+  ix->K = K; ix->d = d; ix->M = M; ix->nbits = 8; ix->metric = m; ix->dtype = dtype;
   ix->centroids.alloc((size_t)K * d);
   ix->codebook.alloc((size_t)256 * d);
   std::vector<double> ivf_loss;
@@ -813,7 +1062,7 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
       TagScope tg("ivf_train");
       const uint64_t s = s_ivf;
       const float* xs = xs_ivf;
-      InArg<float> init(params->ivf.init_centroids, (size_t)K * d);
+      VecIn init(params->ivf.init_centroids, (size_t)K * d, model_dtype(dtype));
       lloyd_train(xs, s, d, 1, d, K, am, params->ivf.balance_factor / (float)(s * nranks),
                   (int)params->ivf.max_iters, params->ivf.tolerance, params->ivf.seed, init.get(),
                   ix->centroids.p, &ivf_loss, &ivf_iters);
@@ -830,7 +1079,10 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
         LB2_LAUNCH("residual", residual_kernel, cdiv(s * d, 256), 256, 0, sample.p, ix->centroids.p,
                    part.p, s, (int)d, sample.p);
       }
-      pq_train_dev(sample.p, s, d, am, &params->pq, ix->codebook.p, &pq_iters);
+      VecIn cb_init(params->pq.codebook, (size_t)256 * d, model_dtype(dtype));
+      lb2_pq_params pqp = params->pq;
+      pqp.codebook = cb_init.get();
+      pq_train_dev(sample.p, s, d, am, &pqp, ix->codebook.p, &pq_iters);
     }
     LB2_CUDA(cudaEventRecord(ev[2], c.stream));
     // 3. transform every row (lance-index/src/vector/ivf.rs:357: partition -> residual -> PQ)

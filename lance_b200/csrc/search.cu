@@ -530,6 +530,130 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
   (void)fin_cnt;
 }
 
+// ------------------------------------------------------------------------------------------------
+// IVF_FLAT: exact distances of the query to every row of a probed partition
+// (FlatDistanceCal::distance_all, lance-index/src/vector/flat/storage.rs:397-403) + top-k.
+// 16 lanes per row: lane l owns the reference's lane-accumulator l (elements 16c + l), so the L2 /
+// dot results are bit-identical to l2.rs:57-91 / dot.rs:30-58; cosine follows cosine.rs:143-174 in
+// structure (f32 FMA lanes) and is checked to the reference's own tolerance.
+// ------------------------------------------------------------------------------------------------
+template <int METRIC>
+__device__ __forceinline__ float flat_row_distance(const float* __restrict__ q, const float* __restrict__ v,
+                                                   int d, int l, unsigned mask, float q_norm) {
+  const int n16 = d & ~15;
+  if (METRIC == METRIC_COSINE) {
+    float xy = 0.0f, yy = 0.0f;
+    for (int e = l; e < d; e += 16) {
+      const float y = v[e];
+      xy = fmaf(q[e], y, xy);
+      yy = fmaf(y, y, yy);
+    }
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {
+      xy += __shfl_xor_sync(mask, xy, off, 16);
+      yy += __shfl_xor_sync(mask, yy, off, 16);
+    }
+    return 1.0f - xy / q_norm / sqrtf(yy);
+  }
+  float acc = 0.0f;
+  for (int e = l; e < n16; e += 16) acc = f_add(acc, term<METRIC>(q[e], v[e]));
+  float s = 0.0f;  // sequential tail, every lane redundantly (l2.rs:69-79)
+  for (int e = n16; e < d; ++e) s = f_add(s, term<METRIC>(q[e], v[e]));
+  float t = 0.0f;
+#pragma unroll
+  for (int qq = 0; qq < 16; ++qq) t = f_add(t, __shfl_sync(mask, acc, qq, 16));
+  return finish<METRIC>(f_add(s, t));
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(256)
+ivfflat_scan_kernel(const float* __restrict__ queries, int d, const uint32_t* __restrict__ probe_ids,
+                    int np, const uint64_t* __restrict__ part_offsets,
+                    const float* __restrict__ vectors, const uint64_t* __restrict__ row_ids, int k,
+                    float* __restrict__ cand_d, uint64_t* __restrict__ cand_id,
+                    uint32_t* __restrict__ cand_cnt) {
+  extern __shared__ float smem[];
+  float* qs = smem;                          // [d]
+  float* cd = qs + d;                        // [SCAN_CHUNK + k]
+  uint32_t* cp = reinterpret_cast<uint32_t*>(cd + SCAN_CHUNK + k);
+  float* wd = reinterpret_cast<float*>(cp + k);
+  uint32_t* wp = reinterpret_cast<uint32_t*>(wd + k);
+  __shared__ int32_t s_key[8];
+  __shared__ uint64_t s_tie[8];
+  __shared__ int s_tid[9];
+  __shared__ int32_t prev_key;
+  __shared__ uint32_t prev_pos;
+  __shared__ float s_qnorm;
+  const int tid = threadIdx.x, l = tid & 15;
+  const unsigned hmask = 0xffffu << (16 * ((tid >> 4) & 1));
+  const int pi = blockIdx.x;
+  const size_t qi = blockIdx.y;
+  const uint32_t p = probe_ids[qi * np + pi];
+  const uint64_t off = part_offsets[p];
+  const uint32_t n_p = (uint32_t)(part_offsets[p + 1] - off);
+  const size_t slot = qi * np + pi;
+  if (n_p == 0) {
+    if (tid == 0) cand_cnt[slot] = 0;
+    return;
+  }
+  for (int t = tid; t < d; t += 256) qs[t] = queries[qi * d + t];
+  __syncthreads();
+  if (METRIC == METRIC_COSINE && tid < 32) {  // norm_l2(query): 16 lanes + sqrt (norm_l2.rs:106-130)
+    float a = 0.0f;
+    for (int e = (tid & 15); e < d; e += 16) a = fmaf(qs[e], qs[e], a);
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o, 16);
+    if (tid == 0) s_qnorm = sqrtf(a);
+  }
+  __syncthreads();
+  const float qn = METRIC == METRIC_COSINE ? s_qnorm : 0.0f;
+  uint32_t nw = 0;
+  for (uint32_t c0 = 0; c0 < n_p; c0 += SCAN_CHUNK) {
+    const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
+    for (uint32_t j = tid >> 4; j < clen; j += 16) {  // 16 rows per pass, 16 lanes each
+      const float dist = flat_row_distance<METRIC>(qs, vectors + (off + c0 + j) * (uint64_t)d, d, l, hmask, qn);
+      if (l == 0) cd[j] = dist;
+    }
+    __syncthreads();
+    const uint32_t pool = clen + nw;
+    const uint32_t rounds = pool < (uint32_t)k ? pool : (uint32_t)k;
+    bool first = true;
+    for (uint32_t r = 0; r < rounds; ++r) {
+      int32_t bk = 0;
+      uint32_t bpos = 0, bslot = 0;
+      bool has = false;
+      const int32_t pk = first ? 0 : prev_key;
+      const uint32_t pp = first ? 0 : prev_pos;
+      for (uint32_t i = tid; i < pool; i += 256) {
+        const int32_t key = total_order_key(cd[i < clen ? i : SCAN_CHUNK + (i - clen)]);
+        const uint32_t pos = i < clen ? c0 + i : cp[i - clen];
+        if (!first && !ki_less(pk, pp, key, pos)) continue;
+        if (!has || ki_less(key, pos, bk, bpos)) { bk = key; bpos = pos; bslot = i; has = true; }
+      }
+      const int w = block_argmin<256>(has, bk, bpos, s_key, s_tie, s_tid);
+      if (tid == w) {
+        prev_key = bk;
+        prev_pos = bpos;
+        wd[r] = cd[bslot < clen ? bslot : SCAN_CHUNK + (bslot - clen)];
+        wp[r] = bpos;
+      }
+      __syncthreads();
+      first = false;
+    }
+    for (uint32_t i = tid; i < rounds; i += 256) {
+      cd[SCAN_CHUNK + i] = wd[i];
+      cp[i] = wp[i];
+    }
+    nw = rounds;
+    __syncthreads();
+  }
+  for (uint32_t i = tid; i < nw; i += 256) {
+    cand_d[slot * k + i] = cd[SCAN_CHUNK + i];
+    cand_id[slot * k + i] = row_ids[off + cp[i]];
+  }
+  if (tid == 0) cand_cnt[slot] = nw;
+}
+
 // global merge per query: ascending (distance, row id), first k
 __global__ void __launch_bounds__(128)
 merge_kernel(const float* __restrict__ cand_d, const uint64_t* __restrict__ cand_id,
@@ -697,6 +821,39 @@ void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const fl
   } else {
     scan_launch<METRIC_L2>(k, grid, smem, queries, d, centroids, codebook, M, ds, pids.p, np,
                            part_offsets, codes, row_ids, k, cand_d.p, cand_id.p, cand_cnt.p);
+  }
+  LB2_LAUNCH("merge_topk", merge_kernel, (unsigned)nq, 128, 0, cand_d.p, cand_id.p, cand_cnt.p, np,
+             k, out_ids, out_dists, out_counts);
+}
+
+void ivfflat_search_f32(const float* centroids, int K, int d, int metric, const uint64_t* part_offsets,
+                        const float* vectors, const uint64_t* row_ids, const float* queries, uint64_t nq,
+                        int k, int nprobes, uint64_t* out_ids, float* out_dists, uint32_t* out_counts) {
+  if (nq == 0 || k == 0) return;
+  if (k > 1024) fail(LB2_UNSUPPORTED, "k (incl. refine factor) > 1024 is not implemented");
+  const int np = nprobes < K ? nprobes : K;
+  // partitions are found with L2 on the (normalised) vectors for cosine (ivf.rs:149-185)
+  const int cmetric = metric == METRIC_DOT ? METRIC_DOT : METRIC_L2;
+  DevBuf<uint32_t> pids((size_t)nq * np), cand_cnt((size_t)nq * np);
+  DevBuf<float> pd((size_t)nq * np), cand_d((size_t)nq * np * k);
+  DevBuf<uint64_t> cand_id((size_t)nq * np * k);
+  find_partitions_f32(centroids, K, d, cmetric, queries, nq, np, pids.p, pd.p);
+  const size_t smem = sizeof(float) * ((size_t)d + SCAN_CHUNK + 4 * (size_t)k);
+  if (smem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "dimension %d too large for the flat scan", d);
+  for (uint64_t q0 = 0; q0 < nq; q0 += 32768) {
+    const uint64_t qn = std::min<uint64_t>(32768, nq - q0);
+    dim3 g(np, (unsigned)qn);
+#define LB2_FLAT(MET)                                                                                   \
+    {                                                                                                   \
+      set_smem(ivfflat_scan_kernel<MET>, smem);                                                         \
+      LB2_LAUNCH("flat_scan", (ivfflat_scan_kernel<MET>), g, 256, smem, queries + q0 * d, d,             \
+                 pids.p + q0 * np, np, part_offsets, vectors, row_ids, k, cand_d.p + q0 * np * k,        \
+                 cand_id.p + q0 * np * k, cand_cnt.p + q0 * np);                                         \
+    }
+    if (metric == METRIC_DOT) LB2_FLAT(METRIC_DOT)
+    else if (metric == METRIC_COSINE) LB2_FLAT(METRIC_COSINE)
+    else LB2_FLAT(METRIC_L2)
+#undef LB2_FLAT
   }
   LB2_LAUNCH("merge_topk", merge_kernel, (unsigned)nq, 128, 0, cand_d.p, cand_id.p, cand_cnt.p, np,
              k, out_ids, out_dists, out_counts);

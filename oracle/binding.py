@@ -274,3 +274,19 @@ def brute_force_topk(data, queries, k, metric="l2", nthreads=1):
                               C.c_uint64(k), _p(oi, C.c_uint64), _p(od, C.c_float),
                               C.c_int(nthreads))
     return oi, od
+
+
+def ivfflat_search(centroids, part_offsets, vectors, row_ids, queries, k, nprobes, metric="l2", nthreads=1):
+    centroids, vectors, queries = _f32(centroids), _f32(vectors), _f32(queries)
+    K, d = centroids.shape
+    po = np.ascontiguousarray(part_offsets, dtype=np.uint64)
+    rid = np.ascontiguousarray(row_ids, dtype=np.uint64)
+    nq = queries.shape[0]
+    oi = np.empty((nq, k), np.uint64)
+    od = np.empty((nq, k), np.float32)
+    oc = np.empty(nq, np.uint32)
+    lib().lo_ivfflat_search(_p(centroids, C.c_float), C.c_uint64(K), C.c_uint64(d), C.c_int(METRIC[metric]),
+                            _p(po, C.c_uint64), _p(vectors, C.c_float), _p(rid, C.c_uint64),
+                            _p(queries, C.c_float), C.c_uint64(nq), C.c_uint64(k), C.c_uint64(nprobes),
+                            _p(oi, C.c_uint64), _p(od, C.c_float), _p(oc, C.c_uint32), C.c_int(nthreads))
+    return oi, od, oc

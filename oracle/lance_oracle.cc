@@ -676,6 +676,59 @@ void lo_ivfpq_search(const float* centroids, uint64_t K, uint64_t d, int metric,
   });
 }
 
+// IVF_FLAT query (lance-index/src/vector/flat/index.rs:82-177 over FlatFloatStorage,
+// flat/storage.rs:345-403): partitions found with L2 on the normalised query for cosine
+// (ivf.rs:149-185), every row of the probed partitions scored with the index's metric.
+// `vectors` are the STORED vectors (normalised for cosine) in partition order.
+void lo_ivfflat_search(const float* centroids, uint64_t K, uint64_t d, int metric,
+                       const uint64_t* part_offsets, const float* vectors, const uint64_t* row_ids,
+                       const float* queries, uint64_t nq, uint64_t k, uint64_t nprobes,
+                       uint64_t* out_ids, float* out_dists, uint32_t* out_counts, int nthreads) {
+  uint64_t max_part = 0;
+  for (uint64_t p = 0; p < K; ++p) max_part = std::max(max_part, part_offsets[p + 1] - part_offsets[p]);
+  const int cmetric = metric == 2 ? 2 : 0;
+  parallel_for(nq, nthreads, [&](size_t b, size_t e) {
+    std::vector<uint32_t> pids(nprobes);
+    std::vector<float> pd(nprobes), q(d), dist(max_part);
+    std::vector<uint64_t> hid(k);
+    std::vector<float> hd(k);
+    std::vector<Node> cand;
+    for (size_t qi = b; qi < e; ++qi) {
+      const float* qin = queries + qi * d;
+      if (metric == 1)
+        lo_normalize_f32(qin, d, q.data());
+      else
+        std::memcpy(q.data(), qin, sizeof(float) * d);
+      uint64_t np = std::min(nprobes, K);
+      lo_find_partitions(centroids, K, d, q.data(), np, cmetric, pids.data(), pd.data());
+      cand.clear();
+      for (uint64_t pi = 0; pi < np; ++pi) {
+        uint64_t p = pids[pi];
+        uint64_t n = part_offsets[p + 1] - part_offsets[p];
+        if (n == 0) continue;
+        lo_flat_distance_all(q.data(), vectors + part_offsets[p] * d, n, d, metric, dist.data(), 1);
+        uint64_t got = lo_flat_topk(dist.data(), row_ids + part_offsets[p], n, k, 0, 0, 0, hid.data(), hd.data());
+        for (uint64_t i = 0; i < got; ++i) cand.push_back({hid[i], hd[i]});
+      }
+      std::sort(cand.begin(), cand.end(), [](const Node& a, const Node& c) {
+        int32_t ka = total_key(a.dist), kc = total_key(c.dist);
+        if (ka != kc) return ka < kc;
+        return a.id < c.id;
+      });
+      uint64_t got = std::min<uint64_t>(k, cand.size());
+      for (uint64_t i = 0; i < got; ++i) {
+        out_ids[qi * k + i] = cand[i].id;
+        out_dists[qi * k + i] = cand[i].dist;
+      }
+      for (uint64_t i = got; i < k; ++i) {
+        out_ids[qi * k + i] = ~uint64_t(0);
+        out_dists[qi * k + i] = std::numeric_limits<float>::infinity();
+      }
+      out_counts[qi] = uint32_t(got);
+    }
+  });
+}
+
 // exact brute-force ground truth (rust/lance/src/index/vector/ivf/v2.rs:959-983 `ground_truth`)
 void lo_brute_force_topk(const float* data, uint64_t n, uint64_t d, int metric,
                          const float* queries, uint64_t nq, uint64_t k, uint64_t* out_ids,

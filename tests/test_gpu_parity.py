@@ -388,3 +388,65 @@ def test_tc_pq_fused_residual_and_training_equal_exact_path():
     assert np.array_equal(p1.train_iters, p2.train_iters) and np.array_equal(p1.codebook, p2.codebook)
     cbo, iters_o = ob.pq_train(res, M, max_iters=10, init_codebook=init, nthreads=NT)
     assert np.array_equal(p1.codebook, cbo) and np.array_equal(p1.train_iters.astype(np.int32), iters_o)
+
+
+# ---- IVF_FLAT (flat/index.rs, flat/storage.rs; recall floor 1.0 in v2.rs:1310-1332) ------------
+@pytest.mark.parametrize("metric", ["l2", "dot", "cosine"])
+def test_ivf_flat_matches_oracle_and_full_probe_recall_is_one(metric):
+    n, d, K = 20000, 64, 32
+    data = synth.gaussian_mixture(n, d, n_components=K, seed=41)
+    if metric == "dot":
+        data /= np.linalg.norm(data, axis=1, keepdims=True)
+    ix = lb.IvfFlatIndex.build(data, metric, num_partitions=K, max_iters=10)
+    parts = ix.export()
+    assert parts["part_offsets"][-1] == n and sorted(parts["row_ids"].tolist()) == list(range(n))
+    stored = ob.normalize_rows(data, nthreads=NT) if metric == "cosine" else data
+    assert np.array_equal(parts["vectors"], stored[parts["row_ids"].astype(np.int64)])
+    q = synth.gaussian_mixture(40, d, n_components=K, seed=42)
+    for k, nprobes in ((10, 1), (10, 5), (64, 3)):
+        ids, dists = ix.search(q, k=k, nprobes=nprobes)
+        oi, od, oc = ob.ivfflat_search(parts["centroids"], parts["part_offsets"], parts["vectors"],
+                                       parts["row_ids"], q, k, nprobes, metric=metric, nthreads=NT)
+        for i in range(len(q)):
+            c = int(oc[i])
+            if metric == "cosine":  # FMA lane order differs from the reference's SIMD: tolerance parity
+                assert np.allclose(np.sort(dists[i, :c]), np.sort(od[i, :c]), rtol=1e-5, atol=1e-6)
+            else:
+                _check_topk(ids[i, :c], dists[i, :c], oi[i, :c], od[i, :c], k)
+    gt, _ = ob.brute_force_topk(stored if metric == "cosine" else data, q if metric != "cosine" else ob.normalize_rows(q), 10,
+                                metric="l2" if metric == "cosine" else metric, nthreads=NT)
+    ids, _ = ix.search(q, k=10, nprobes=K)
+    recall = np.mean([len(set(ids[i].tolist()) & set(gt[i].tolist())) / 10 for i in range(len(q))])
+    assert recall >= 0.999, recall
+
+
+# ---- element types: f16 / u8 buffers are converted to f32 on the device, then f32 semantics -----
+def test_f16_and_u8_inputs_equal_f32_path_on_converted_values():
+    rng = np.random.default_rng(77)
+    n, d, K = 5000, 128, 64
+    x8 = rng.integers(0, 256, size=(n, d), dtype=np.uint8)
+    cent = x8[:K].astype(np.float32) + 0.25
+    p8, d8, _ = lb.compute_partitions(cent, x8)
+    pf, df, _ = lb.compute_partitions(cent, x8.astype(np.float32))
+    assert np.array_equal(p8, pf) and np.array_equal(d8, df)
+    x16 = (rng.standard_normal((n, d)) * 4).astype(np.float16)
+    c16 = x16[:K].copy()
+    p16, d16, _ = lb.compute_partitions(c16, x16)
+    pr, dr, _ = lb.compute_partitions(c16.astype(np.float32), x16.astype(np.float32))
+    assert np.array_equal(p16, pr) and np.array_equal(d16, dr)
+    # the oracle's f16 scalar path (convert each element to f32, 16 lanes: l2.rs:100-106,156)
+    for i in range(0, 50, 7):
+        assert d16[i] == np.float32(ob.l2_f16(x16[i], c16[p16[i]]))
+    # trained model comes back in the input's element type
+    km = lb.train_kmeans(x16, d, 16, max_iters=4, centroids=c16[:16])
+    assert km.centroids.dtype == np.float16
+    kf = lb.train_kmeans(x16.astype(np.float32), d, 16, max_iters=4, centroids=c16[:16].astype(np.float32))
+    assert np.array_equal(km.centroids, kf.centroids.astype(np.float16))
+    # whole index from u8 vectors == index from the same values as f32
+    i8 = lb.IvfPqIndex.build(x8, "l2", lb.IvfBuildParams(num_partitions=16, num_sub_vectors=16, max_iters=5, pq_max_iters=4))
+    i32 = lb.IvfPqIndex.build(x8.astype(np.float32), "l2", lb.IvfBuildParams(num_partitions=16, num_sub_vectors=16, max_iters=5, pq_max_iters=4))
+    e8, e32 = i8.export(), i32.export()
+    assert np.array_equal(e8["codes"], e32["codes"]) and np.array_equal(e8["part_offsets"], e32["part_offsets"])
+    r8 = i8.search(x8[:20], k=5, nprobes=4)
+    r32 = i32.search(x8[:20].astype(np.float32), k=5, nprobes=4)
+    assert np.array_equal(r8[0], r32[0]) and np.array_equal(r8[1], r32[1])
