@@ -450,3 +450,52 @@ def test_f16_and_u8_inputs_equal_f32_path_on_converted_values():
     r8 = i8.search(x8[:20], k=5, nprobes=4)
     r32 = i32.search(x8[:20].astype(np.float32), k=5, nprobes=4)
     assert np.array_equal(r8[0], r32[0]) and np.array_equal(r8[1], r32[1])
+
+
+# ---- full-size (BASELINE config 1: 1M x 128, IVF_PQ 256/16) size-independent properties ----------
+def test_full_size_sift1m_properties():
+    import ctypes as C
+    n, d, K, M = 1_000_000, 128, 256, 16
+    pin = lb.PinnedArray((n, d), np.float32)
+    rng = np.random.default_rng(5)
+    W, cm = synth.sift_model(d)
+    for s in range(0, n, 1 << 16):  # generate in place (host allocations are slow on these VMs)
+        e = min(n, s + (1 << 16))
+        z = cm[rng.integers(0, cm.shape[0], e - s)] + rng.standard_normal((e - s, 24), dtype=np.float32)
+        x = np.maximum(z @ W * 12.0 + 20.0, 0.0) + rng.standard_normal((e - s, d), dtype=np.float32) * 3.0
+        pin.array[s:e] = np.clip(np.rint(x), 0, 255)
+    data = pin.array
+    ix = lb.IvfPqIndex.build(pin, "l2", lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, seed=3))
+    parts = ix.export()
+    off, rid, codes = parts["part_offsets"].astype(np.int64), parts["row_ids"].astype(np.int64), parts["codes"]
+    # every row exactly once; rows inside a partition in input order; offsets monotone
+    assert off[0] == 0 and off[-1] == n and np.all(np.diff(off) >= 0)
+    assert np.array_equal(np.sort(rid), np.arange(n))
+    part_of_pos = np.repeat(np.arange(K), np.diff(off))
+    same = part_of_pos[1:] == part_of_pos[:-1]
+    assert np.all(np.diff(rid)[same] > 0)
+    # idempotence: re-assigning with the trained model reproduces the stored partition of every row,
+    # and re-encoding reproduces every code (tensor-core path == stored result of the same path)
+    p2, c2, v2 = lb.ivfpq_transform(parts["centroids"], parts["codebook"], data[:200000])
+    part_of_row = np.empty(n, np.int64)
+    part_of_row[rid] = part_of_pos
+    code_of_row = np.empty((n, M), np.uint8)
+    code_of_row[rid] = codes
+    assert np.array_equal(p2, part_of_row[:200000]) and np.array_equal(c2, code_of_row[:200000]) and v2.all()
+    # a sample of rows against the oracle (exactness at full size)
+    sel = rng.choice(n, 4000, replace=False)
+    po, _, _ = ob.compute_membership(parts["centroids"], data[sel], nthreads=NT)
+    assert np.array_equal(po, part_of_row[sel])
+    res = ob.compute_residual(parts["centroids"], data[sel], po, nthreads=NT)
+    assert np.array_equal(ob.pq_encode(parts["codebook"], res, nthreads=NT), code_of_row[sel])
+    # reconstruction: decode(code) + centroid is closer to the row than the bare centroid (PQ helps)
+    recon = parts["centroids"][po] + np.concatenate([parts["codebook"][m][code_of_row[sel][:, m]] for m in range(M)], axis=1)
+    assert ((data[sel] - recon) ** 2).sum(1).mean() < 0.6 * ((data[sel] - parts["centroids"][po]) ** 2).sum(1).mean()
+    # search: distances ascending, ids unique, counts full, and equal to the oracle on a few queries
+    q = data[rng.choice(n, 64, replace=False)] + rng.integers(-2, 3, size=(64, d)).astype(np.float32)
+    ids, dd = ix.search(q, k=10, nprobes=16)
+    assert np.all(np.diff(dd, axis=1) >= 0) and all(len(set(r.tolist())) == 10 for r in ids)
+    oi, od, _ = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], codes,
+                                parts["row_ids"], q[:8], 10, 16, nthreads=NT)
+    assert np.array_equal(np.sort(dd[:8], axis=1), np.sort(od, axis=1))
+    pin.free()
