@@ -425,6 +425,22 @@ def main():
         recall = float(np.mean([len(set(ids_h[i].tolist()) & set(gt[i].tolist())) / TOPK for i in range(1000)]))
     else:
         recall = None  # the merged result spans world x n rows; recall is reported at N=1
+    # refine operating point (the reference's published curve uses refine_factor 5..10):
+    # k*refine PQ candidates re-ranked with exact distances from the resident raw vectors
+    query_refine = None
+    if world == 1:
+        REFINE = 10
+        for _ in range(2):
+            ix.search_refine(data_dev, q_dev, TOPK, NPROBES, REFINE, out=(ids_dev, d_dev))
+        barrier()
+        lb.timer_start()
+        for _ in range(args.steps):
+            ix.search_refine(data_dev, q_dev, TOPK, NPROBES, REFINE, out=(ids_dev, d_dev))
+        r_ms = lb.timer_stop() / args.steps
+        ids_r = ids_t[:1000].cpu().numpy()
+        rec_r = float(np.mean([len(set(ids_r[i].tolist()) & set(gt[i].tolist())) / TOPK for i in range(1000)]))
+        query_refine = {"qps": NQ / (r_ms * 1e-3), "recall_at_10": rec_r, "nprobes": NPROBES, "k": TOPK,
+                        "refine_factor": REFINE, "batch": NQ, "ms_per_batch": r_ms}
     scan_bytes = NQ * NPROBES * (n / NUM_PARTITIONS) * NUM_SUB_VECTORS + NQ * DIM * 4
     scan_launch_ms = scan_ms / max(scan_cnt, 1)
     query = {"qps": NQ / (q_ms * 1e-3), "e2e_qps": NQ / (q_e2e_ms * 1e-3), "recall_at_10": recall,
@@ -461,7 +477,8 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "build_phases_ms": {"ivf_train": stats.ms_ivf_train, "pq_train": stats.ms_pq_train, "transform": stats.ms_transform,
                                 "group": stats.ms_group, "ivf_iters": stats.ivf_iters, "pq_iters_max": stats.pq_iters_max},
-            "kernels": fams, "roofline": roofline, "query": query, "cpu_baseline": cpu_baseline,
+            "kernels": fams, "roofline": roofline, "query": query, "query_refine": query_refine,
+            "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
     if world > 1:

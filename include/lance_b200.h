@@ -184,6 +184,16 @@ lb2_status lb2_index_load(lb2_index* index, const uint32_t* part_ids, const uint
 lb2_status lb2_index_search(lb2_index* index, const void* queries, uint64_t nq, uint32_t k,
                             uint32_t nprobes, uint64_t* row_ids_out, float* dists_out,
                             uint32_t* counts_out);
+/* The same, followed by the refine step of the reference's plan (Take vectors + flat KNN re-rank,
+ * rust/lance/src/dataset/scanner.rs:2884-2905; lance-index/src/vector/flat.rs:95-148): the index
+ * returns k * refine_factor candidates, their EXACT distances to the query are recomputed from the
+ * raw column `vectors` ([>= max row id + 1][d], element type = the index's dtype, row id = row
+ * number; device-resident for speed) with the index's true metric, and the k best by
+ * (distance, row id) are returned.  k * refine_factor <= 1024. */
+lb2_status lb2_index_search_refine(lb2_index* index, const void* vectors, uint64_t num_vectors,
+                                   const void* queries, uint64_t nq, uint32_t k, uint32_t nprobes,
+                                   uint32_t refine_factor, uint64_t* row_ids_out, float* dists_out,
+                                   uint32_t* counts_out);
 lb2_status lb2_index_info(const lb2_index* index, uint32_t* k, uint32_t* d, uint32_t* num_sub_vectors,
                           uint32_t* num_bits, uint64_t* num_rows);
 /* export for the host to write index files: any pointer may be NULL.

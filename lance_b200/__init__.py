@@ -461,6 +461,29 @@ class IvfPqIndex:
                                      ip, dp, None))
         return ids, dists
 
+    def search_refine(self, vectors, queries, k=10, nprobes=1, refine_factor=1, out=None):
+        """to_table(nearest={..., refine_factor}): PQ candidates re-ranked with exact distances from
+        the raw column (scanner.rs:2884-2905).  `vectors` = the indexed column (row id = row number)."""
+        dt = getattr(self, "_dt", F32)
+        npdt = {F32: np.float32, F16: np.float16, U8: np.uint8, BF16: np.uint16}[dt]
+        if not isinstance(queries, (DeviceArray, PinnedArray)):
+            queries = np.ascontiguousarray(queries, dtype=npdt)
+        if not isinstance(vectors, (DeviceArray, PinnedArray)):
+            vectors = np.ascontiguousarray(vectors, dtype=npdt)
+        nq = queries.shape[0]
+        if out is None:
+            ids, dists = np.empty((nq, k), np.uint64), np.empty((nq, k), np.float32)
+        else:
+            ids, dists = out
+        qp, _k1 = as_ptr(queries)
+        vp, _k0 = as_ptr(vectors)
+        ip, _k2 = as_ptr(ids)
+        dp, _k3 = as_ptr(dists)
+        check(lib().lb2_index_search_refine(self._h, vp, C.c_uint64(vectors.shape[0]), qp, C.c_uint64(nq),
+                                            C.c_uint32(k), C.c_uint32(nprobes), C.c_uint32(refine_factor),
+                                            ip, dp, None))
+        return ids, dists
+
     def close(self):
         if self._h:
             lib().lb2_index_destroy(self._h)

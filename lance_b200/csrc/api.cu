@@ -779,6 +779,46 @@ lb2_status lb2_index_search(lb2_index* index, const void* queries, uint64_t nq, 
   LB2_API_END
 }
 
+lb2_status lb2_index_search_refine(lb2_index* index, const void* vectors, uint64_t num_vectors,
+                                   const void* queries, uint64_t nq, uint32_t k, uint32_t nprobes,
+                                   uint32_t refine_factor, uint64_t* row_ids_out, float* dists_out,
+                                   uint32_t* counts_out) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(index && vectors && k > 0 && nprobes > 0 && refine_factor > 0, "bad argument");
+  const uint64_t kc = (uint64_t)k * refine_factor;
+  if (kc > 1024) fail(LB2_UNSUPPORTED, "k * refine_factor = %llu > 1024 is not implemented", (unsigned long long)kc);
+  const int d = index->d;
+  VecIn q(queries, (size_t)nq * d, index->dtype);
+  VecIn v(vectors, (size_t)num_vectors * d, index->dtype);
+  const float* qp = q.get();
+  DevBuf<float> qn;
+  if (index->metric == METRIC_COSINE) {
+    qn.alloc((size_t)nq * d);
+    if (nq) LB2_LAUNCH("normalize", normalize_kernel, cdiv(nq, 128), 128, 0, qp, nq, d, qn.p);
+    qp = qn.p;
+  }
+  DevBuf<uint64_t> cid((size_t)nq * kc);
+  DevBuf<float> cdist((size_t)nq * kc);
+  DevBuf<uint32_t> ccnt(nq);
+  OutArg<uint64_t> oi(row_ids_out, (size_t)nq * k);
+  OutArg<float> od(dists_out, (size_t)nq * k);
+  OutArg<uint32_t> oc(counts_out, nq);
+  TagScope tg("search");
+  if (index->kind == 1)
+    ivfflat_search_f32(index->centroids.p, index->K, d, index->metric, index->part_offsets.p,
+                       index->vectors.p, index->row_ids.p, qp, nq, (int)kc, nprobes, cid.p, cdist.p, ccnt.p);
+  else
+    ivfpq_search_f32(index->centroids.p, index->K, d, index->metric, index->codebook.p, index->M,
+                     index->nbits, index->part_offsets.p, index->codes.p, index->row_ids.p, qp, nq, (int)kc,
+                     nprobes, cid.p, cdist.p, ccnt.p);
+  // exact re-rank with the true metric on the ORIGINAL (un-normalised) query, as flat_knn does
+  refine_f32(q.get(), nq, d, index->metric, v.get(), num_vectors, cid.p, ccnt.p, (int)kc, (int)k, oi.get(),
+             od.get(), oc.get());
+  oi.commit(); od.commit(); oc.commit();
+  sync_stream();
+  LB2_API_END
+}
+
 lb2_status lb2_index_info(const lb2_index* index, uint32_t* k, uint32_t* d, uint32_t* num_sub_vectors,
                           uint32_t* num_bits, uint64_t* num_rows) {
   LB2_API_BEGIN

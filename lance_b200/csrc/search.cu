@@ -285,6 +285,166 @@ ivfpq_scan_rounds_kernel(const float* __restrict__ queries, int d, const float* 
   if (tid == 0) cand_cnt[slot] = nw;
 }
 
+__device__ __forceinline__ float key_to_float(int32_t key) {
+  return __int_as_float(key ^ (int32_t)((uint32_t)(key >> 31) >> 1));
+}
+
+// ------------------------------------------------------------------------------------------------
+// general k (16 < k <= 1024, e.g. k * refine_factor): per chunk the k-th smallest key is found by a
+// 4-pass MSB radix select over shared-memory keys (256-bin histograms), everything below it is
+// kept, ties AT the k-th key are resolved by position (earliest rows survive).
+// ------------------------------------------------------------------------------------------------
+template <int METRIC>
+__global__ void __launch_bounds__(256)
+ivfpq_scan_radix_kernel(const float* __restrict__ queries, int d, const float* __restrict__ centroids,
+                        const float* __restrict__ codebook, int M, int ds,
+                        const uint32_t* __restrict__ probe_ids, int np,
+                        const uint64_t* __restrict__ part_offsets, const uint8_t* __restrict__ codes,
+                        const uint64_t* __restrict__ row_ids, int k, float* __restrict__ cand_d,
+                        uint64_t* __restrict__ cand_id, uint32_t* __restrict__ cand_cnt) {
+  extern __shared__ float smem[];
+  float* lut = smem;                                                   // [M*256]
+  float* qr = lut + M * 256;                                           // [d]
+  uint32_t* ukey = reinterpret_cast<uint32_t*>(qr + d);                // [SCAN_CHUNK + k] order-preserving keys
+  uint32_t* cpos = ukey + SCAN_CHUNK + k;                              // [k] positions of carried winners
+  uint32_t* nkey = cpos + k;                                           // [k] next winners
+  uint32_t* npos = nkey + k;                                           // [k]
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t s_prefix, s_need, s_eq, s_out;
+  __shared__ int32_t s_key[8];
+  __shared__ uint64_t s_tie[8];
+  __shared__ int s_tid[9];
+  __shared__ uint32_t prev_pos;
+  const int tid = threadIdx.x;
+  const int pi = blockIdx.x;
+  const size_t qi = blockIdx.y;
+  const uint32_t p = probe_ids[qi * np + pi];
+  const uint64_t off = part_offsets[p];
+  const uint32_t n_p = (uint32_t)(part_offsets[p + 1] - off);
+  const size_t slot = qi * np + pi;
+  if (n_p == 0) {
+    if (tid == 0) cand_cnt[slot] = 0;
+    return;
+  }
+  const float* q = queries + qi * d;
+  for (int t = tid; t < d; t += 256)
+    qr[t] = METRIC == METRIC_DOT ? q[t] : __fsub_rn(q[t], centroids[(size_t)p * d + t]);  // v2.rs:316-332
+  __syncthreads();
+  build_lut_smem<METRIC>(lut, qr, codebook, M, ds, tid);
+  __syncthreads();
+  const uint8_t* pc = codes + off * M;
+  const float dot_fix = (float)M - 1.0f;
+  uint32_t nw = 0;
+  for (uint32_t c0 = 0; c0 < n_p; c0 += SCAN_CHUNK) {
+    const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
+    for (uint32_t j = tid; j < clen; j += 256) {
+      float dist = 0.0f;
+      if ((M & 15) == 0) {
+        const uint4* rp = reinterpret_cast<const uint4*>(pc + (size_t)(c0 + j) * M);
+        for (int c16 = 0; c16 < M / 16; ++c16) {
+          const uint4 v = __ldg(rp + c16);
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+          const float* l0 = lut + c16 * 16 * 256;
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              dist = f_add(dist, l0[(a * 4 + b) * 256 + ((w[a] >> (8 * b)) & 0xff)]);
+        }
+      } else {
+        const uint8_t* rp = pc + (size_t)(c0 + j) * M;
+        for (int m = 0; m < M; ++m) dist = f_add(dist, lut[m * 256 + rp[m]]);
+      }
+      if (METRIC == METRIC_DOT) dist = __fsub_rn(dist, dot_fix);
+      ukey[j] = (uint32_t)total_order_key(dist) ^ 0x80000000u;  // unsigned order == total order
+    }
+    // carried winners sit at ukey[SCAN_CHUNK ..); pool element i: i < clen -> (ukey[i], c0+i), else carried
+    __syncthreads();
+    const uint32_t pool = clen + nw;
+    auto key_at = [&](uint32_t i) { return i < clen ? ukey[i] : ukey[SCAN_CHUNK + (i - clen)]; };
+    auto pos_at = [&](uint32_t i) { return i < clen ? c0 + i : cpos[i - clen]; };
+    if (pool <= (uint32_t)k) {
+      for (uint32_t i = tid; i < pool; i += 256) { nkey[i] = key_at(i); npos[i] = pos_at(i); }
+      __syncthreads();
+      for (uint32_t i = tid; i < pool; i += 256) { ukey[SCAN_CHUNK + i] = nkey[i]; cpos[i] = npos[i]; }
+      nw = pool;
+      __syncthreads();
+      continue;
+    }
+    if (tid == 0) { s_prefix = 0; s_need = (uint32_t)k; }
+    uint32_t mask = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      hist[tid] = 0;
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+      for (uint32_t i = tid; i < pool; i += 256) {
+        const uint32_t kk = key_at(i);
+        if ((kk & mask) == prefix) atomicAdd(&hist[(kk >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t need = s_need, cum = 0;
+        int b = 0;
+        for (; b < 256; ++b) {
+          if (cum + hist[b] >= need) break;
+          cum += hist[b];
+        }
+        s_need = need - cum;
+        s_prefix = prefix | ((uint32_t)b << shift);
+        s_eq = hist[b];
+      }
+      mask |= 0xffu << shift;
+      __syncthreads();
+    }
+    const uint32_t T = s_prefix, need = s_need, eq = s_eq;  // take all keys < T and `need` of the `eq` keys == T
+    if (tid == 0) s_out = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < pool; i += 256) {
+      const uint32_t kk = key_at(i);
+      if (kk < T || (kk == T && eq == need)) {
+        const uint32_t at = atomicAdd(&s_out, 1u);
+        nkey[at] = kk;
+        npos[at] = pos_at(i);
+      }
+    }
+    __syncthreads();
+    if (eq != need) {  // ties at the k-th key: the `need` smallest positions survive (rare)
+      bool first = true;
+      for (uint32_t r = 0; r < need; ++r) {
+        uint32_t bp = 0xffffffffu;
+        bool has = false;
+        const uint32_t pp = first ? 0 : prev_pos;
+        for (uint32_t i = tid; i < pool; i += 256) {
+          if (key_at(i) != T) continue;
+          const uint32_t ps = pos_at(i);
+          if (!first && ps <= pp) continue;
+          if (!has || ps < bp) { bp = ps; has = true; }
+        }
+        const int w = block_argmin<256>(has, 0, bp, s_key, s_tie, s_tid);
+        if (tid == w) {
+          prev_pos = bp;
+          const uint32_t at = s_out;
+          nkey[at] = T;
+          npos[at] = bp;
+          s_out = at + 1;
+        }
+        __syncthreads();
+        first = false;
+      }
+    }
+    const uint32_t got = s_out;  // == k
+    __syncthreads();
+    for (uint32_t i = tid; i < got; i += 256) { ukey[SCAN_CHUNK + i] = nkey[i]; cpos[i] = npos[i]; }
+    nw = got;
+    __syncthreads();
+  }
+  for (uint32_t i = tid; i < nw; i += 256) {
+    cand_d[slot * k + i] = key_to_float((int32_t)(ukey[SCAN_CHUNK + i] ^ 0x80000000u));
+    cand_id[slot * k + i] = row_ids[off + cpos[i]];
+  }
+  if (tid == 0) cand_cnt[slot] = nw;
+}
+
 // ------------------------------------------------------------------------------------------------
 // small-k (k <= 32) variant: a thread keeps its <= 16 chunk distances in registers.
 //   T  = k-th smallest of the 256 per-thread minima  (an upper bound of the k-th smallest overall)
@@ -292,9 +452,6 @@ ivfpq_scan_rounds_kernel(const float* __restrict__ queries, int d, const float* 
 //   the k smallest of C (+ the winners carried from earlier chunks) are then selected by ONE warp
 //   with shuffle-only argmin rounds.  All comparisons are on (total-order key, position).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float key_to_float(int32_t key) {
-  return __int_as_float(key ^ (int32_t)((uint32_t)(key >> 31) >> 1));
-}
 // one warp: `rounds` smallest (key,pos) among the PER-per-lane register values, ascending; the r-th
 // winner is handed to emit(r, key, pos) by every lane (uniform)
 template <int PER, class Emit>
@@ -779,8 +936,8 @@ static void scan_launch(int kmax, dim3 grid, size_t smem, const float* queries, 
                codebook, M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt);
     return;
   }
-  set_smem(ivfpq_scan_rounds_kernel<METRIC>, smem);
-  LB2_LAUNCH("pq_scan", (ivfpq_scan_rounds_kernel<METRIC>), grid, 256, smem, queries, d, centroids, codebook,
+  set_smem(ivfpq_scan_radix_kernel<METRIC>, smem);
+  LB2_LAUNCH("pq_scan", (ivfpq_scan_radix_kernel<METRIC>), grid, 256, smem, queries, d, centroids, codebook,
              M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt);
 }
 
@@ -857,6 +1014,99 @@ void ivfflat_search_f32(const float* centroids, int K, int d, int metric, const 
   }
   LB2_LAUNCH("merge_topk", merge_kernel, (unsigned)nq, 128, 0, cand_d.p, cand_id.p, cand_cnt.p, np,
              k, out_ids, out_dists, out_counts);
+}
+
+// ------------------------------------------------------------------------------------------------
+// refine: exact distances of k' = k * refine_factor candidates from the raw vectors, then the k
+// best by (distance, row id)  (scanner.rs:2884-2905, flat.rs:95-148)
+// ------------------------------------------------------------------------------------------------
+template <int METRIC>
+__global__ void __launch_bounds__(256)
+refine_kernel(const float* __restrict__ queries, int d, const float* __restrict__ vectors,
+              uint64_t num_vectors, const uint64_t* __restrict__ cand_id, const uint32_t* __restrict__ cand_cnt,
+              int kc, int k, uint64_t* __restrict__ out_id, float* __restrict__ out_d,
+              uint32_t* __restrict__ out_cnt) {
+  extern __shared__ float smem[];
+  float* qs = smem;       // [d]
+  float* cd = qs + d;     // [kc]
+  __shared__ int32_t s_key[8];
+  __shared__ uint64_t s_tie[8];
+  __shared__ int s_tid[9];
+  __shared__ int32_t prev_key;
+  __shared__ uint64_t prev_id;
+  __shared__ float s_qnorm;
+  const size_t qi = blockIdx.x;
+  const int tid = threadIdx.x, l = tid & 15;
+  const unsigned hmask = 0xffffu << (16 * ((tid >> 4) & 1));
+  const uint32_t cnt = min(cand_cnt[qi], (uint32_t)kc);
+  for (int t = tid; t < d; t += 256) qs[t] = queries[qi * d + t];
+  __syncthreads();
+  if (METRIC == METRIC_COSINE && tid < 32) {
+    float a = 0.0f;
+    for (int e = (tid & 15); e < d; e += 16) a = fmaf(qs[e], qs[e], a);
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o, 16);
+    if (tid == 0) s_qnorm = sqrtf(a);
+  }
+  __syncthreads();
+  const float qn = METRIC == METRIC_COSINE ? s_qnorm : 0.0f;
+  const uint64_t* ids = cand_id + qi * kc;
+  for (uint32_t c = tid >> 4; c < cnt; c += 16) {
+    const uint64_t id = ids[c];
+    float dist = __int_as_float(0x7fc00000);
+    if (id < num_vectors) dist = flat_row_distance<METRIC>(qs, vectors + id * (uint64_t)d, d, l, hmask, qn);
+    if (l == 0) cd[c] = dist;
+  }
+  __syncthreads();
+  bool first = true;
+  uint32_t r = 0;
+  const uint32_t rounds = cnt < (uint32_t)k ? cnt : (uint32_t)k;
+  for (; r < rounds; ++r) {
+    int32_t bk = 0;
+    uint64_t bi = 0;
+    uint32_t bslot = 0;
+    bool has = false;
+    const int32_t pk = first ? 0 : prev_key;
+    const uint64_t pid = first ? 0 : prev_id;
+    for (uint32_t c = tid; c < cnt; c += 256) {
+      const int32_t key = total_order_key(cd[c]);
+      const uint64_t id = ids[c];
+      if (!first && !ki_less(pk, pid, key, id)) continue;
+      if (!has || ki_less(key, id, bk, bi)) { bk = key; bi = id; bslot = c; has = true; }
+    }
+    const int w = block_argmin<256>(has, bk, bi, s_key, s_tie, s_tid);
+    if (w < 0) break;
+    if (tid == w) {
+      prev_key = bk;
+      prev_id = bi;
+      out_id[qi * k + r] = bi;
+      out_d[qi * k + r] = cd[bslot];
+    }
+    __syncthreads();
+    first = false;
+  }
+  for (uint32_t e = r + tid; e < (uint32_t)k; e += 256) {
+    out_id[qi * k + e] = ~0ull;
+    out_d[qi * k + e] = __int_as_float(0x7f800000);
+  }
+  if (tid == 0 && out_cnt) out_cnt[qi] = r;
+}
+
+void refine_f32(const float* queries, uint64_t nq, int d, int metric, const float* vectors,
+                uint64_t num_vectors, const uint64_t* cand_id, const uint32_t* cand_cnt, int kc, int k,
+                uint64_t* out_id, float* out_d, uint32_t* out_cnt) {
+  if (nq == 0) return;
+  const size_t smem = sizeof(float) * ((size_t)d + kc);
+#define LB2_REF(MET)                                                                                  \
+  {                                                                                                   \
+    set_smem(refine_kernel<MET>, smem);                                                               \
+    LB2_LAUNCH("refine", (refine_kernel<MET>), (unsigned)nq, 256, smem, queries, d, vectors,           \
+               num_vectors, cand_id, cand_cnt, kc, k, out_id, out_d, out_cnt);                         \
+  }
+  if (metric == METRIC_DOT) LB2_REF(METRIC_DOT)
+  else if (metric == METRIC_COSINE) LB2_REF(METRIC_COSINE)
+  else LB2_REF(METRIC_L2)
+#undef LB2_REF
 }
 
 void build_lut_f32(const float* codebook, int M, int nbits, int d, int metric, const float* query,

@@ -11,6 +11,9 @@ void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const fl
 void ivfflat_search_f32(const float* centroids, int K, int d, int metric, const uint64_t* part_offsets,
                         const float* vectors, const uint64_t* row_ids, const float* queries, uint64_t nq,
                         int k, int nprobes, uint64_t* out_ids, float* out_dists, uint32_t* out_counts);
+void refine_f32(const float* queries, uint64_t nq, int d, int metric, const float* vectors,
+                uint64_t num_vectors, const uint64_t* cand_id, const uint32_t* cand_cnt, int kc, int k,
+                uint64_t* out_id, float* out_d, uint32_t* out_cnt);
 void build_lut_f32(const float* codebook, int M, int nbits, int d, int metric, const float* query,
                    float* lut);
 void pq_scan_transposed_f32(const float* lut, int M, int metric, const uint8_t* codes_t, uint64_t n,

@@ -499,3 +499,26 @@ def test_full_size_sift1m_properties():
                                 parts["row_ids"], q[:8], 10, 16, nthreads=NT)
     assert np.array_equal(np.sort(dd[:8], axis=1), np.sort(od, axis=1))
     pin.free()
+
+
+def test_search_with_refine_matches_exact_rerank_of_oracle_candidates():
+    n, d, K, M = 40000, 128, 32, 16
+    data = synth.sift_like(n, d, seed=61)
+    q = synth.sift_like_queries(60, d, seed=61)
+    ix = lb.IvfPqIndex.build(data, "l2", lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, max_iters=10, pq_max_iters=8))
+    parts = ix.export()
+    k, nprobes, rf = 10, 8, 10
+    ids, dists = ix.search_refine(data, q, k=k, nprobes=nprobes, refine_factor=rf)
+    oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
+                                 parts["row_ids"], q, k * rf, nprobes, nthreads=NT)
+    for i in range(len(q)):
+        cand = oi[i, :oc[i]].astype(np.int64)
+        ex = np.array([ob.l2(q[i], data[c]) for c in cand], np.float32)
+        order = np.lexsort((cand, ex))[:k]
+        # candidate SETS can differ only through ties at the k*rf-th PQ distance (see _check_topk)
+        assert np.array_equal(np.sort(dists[i]), np.sort(ex[order])), i
+    gt, _ = ob.brute_force_topk(data, q, 10, nthreads=NT)
+    recall = np.mean([len(set(ids[i].tolist()) & set(gt[i].tolist())) / 10 for i in range(len(q))])
+    plain, _ = ix.search(q, k=10, nprobes=nprobes)
+    r0 = np.mean([len(set(plain[i].tolist()) & set(gt[i].tolist())) / 10 for i in range(len(q))])
+    assert recall > r0 + 0.1 and recall >= 0.85, (recall, r0)
