@@ -87,8 +87,8 @@ typedef struct {
   uint32_t redos;          /* 1 */
   float balance_factor;    /* BEFORE the division by n that train_kmeans applies (kmeans.rs:1344);
                               IVF training passes 1.0 (rust/lance/src/index/vector/ivf.rs:1858) */
-  uint32_t hierarchical_k; /* 16; hierarchical training for k > 256 is not implemented on the
-                              device yet: flat Lloyd is used for every k */
+  uint32_t hierarchical_k; /* 16: for k > 256 (and no init_centroids) the reference's hierarchical
+                              scheme is used (kmeans.rs:746-1003, 1027); 0/1 = flat Lloyd for every k */
   uint64_t sample_rate;    /* 256: only the first sample_rate*k rows are used (kmeans.rs:1328-1340) */
   uint64_t seed;           /* the reference is unseeded (kmeans.rs:645); we are reproducible */
   const void* init_centroids; /* KMeanInit::Incremental (k x d, same dtype) or NULL = random rows */

@@ -508,9 +508,16 @@ lb2_status lb2_kmeans_train(const void* data, uint64_t n, uint32_t d, lb2_dtype 
   std::vector<double> loss;
   std::vector<uint32_t> iters;
   const uint64_t kr = current_comm() ? current_comm()->nranks : 1;  // sharded: every rank passes its rows
-  lloyd_train(x.get(), rows, d, 1, d, k, m, params->balance_factor / (float)(rows * kr),
-              (int)params->max_iters, params->tolerance, params->seed, init.get(), cent.p, &loss,
-              &iters);
+  if (k > 256 && params->hierarchical_k > 1 && !params->init_centroids) {  // kmeans.rs:1027
+    hierarchical_train(x.get(), rows, d, k, m, params->balance_factor / (float)(rows * kr),
+                       (int)params->max_iters, params->tolerance, (int)params->hierarchical_k, params->seed, cent.p);
+    loss.assign(1, 0.0);
+    iters.assign(1, 0);
+  } else {
+    lloyd_train(x.get(), rows, d, 1, d, k, m, params->balance_factor / (float)(rows * kr),
+                (int)params->max_iters, params->tolerance, params->seed, init.get(), cent.p, &loss,
+                &iters);
+  }
   VecOut o(centroids_out, (size_t)k * d, model_dtype(dtype));
   d2d(o.get(), cent.p, (size_t)k * d);
   o.commit();
@@ -951,9 +958,16 @@ lb2_status lb2_ivfflat_build(const void* data, uint64_t n, uint32_t d, lb2_dtype
         xs = sample.p;
       }
       VecIn init(params->ivf.init_centroids, (size_t)K * d, model_dtype(dtype));
-      lloyd_train(xs, s, d, 1, d, K, am, params->ivf.balance_factor / (float)(s * nranks),
-                  (int)params->ivf.max_iters, params->ivf.tolerance, params->ivf.seed, init.get(),
-                  ix->centroids.p, &loss, &iters);
+      if (K > 256 && params->ivf.hierarchical_k > 1 && !params->ivf.init_centroids && nranks == 1) {
+        hierarchical_train(xs, s, d, K, am, params->ivf.balance_factor / (float)s, (int)params->ivf.max_iters,
+                           params->ivf.tolerance, (int)params->ivf.hierarchical_k, params->ivf.seed, ix->centroids.p);
+        loss.assign(1, 0.0);
+        iters.assign(1, 0);
+      } else {
+        lloyd_train(xs, s, d, 1, d, K, am, params->ivf.balance_factor / (float)(s * nranks),
+                    (int)params->ivf.max_iters, params->ivf.tolerance, params->ivf.seed, init.get(),
+                    ix->centroids.p, &loss, &iters);
+      }
     }
     LB2_CUDA(cudaEventRecord(ev[1], c.stream));
     DevBuf<uint32_t> part(n);
@@ -1103,9 +1117,16 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
       const uint64_t s = s_ivf;
       const float* xs = xs_ivf;
       VecIn init(params->ivf.init_centroids, (size_t)K * d, model_dtype(dtype));
-      lloyd_train(xs, s, d, 1, d, K, am, params->ivf.balance_factor / (float)(s * nranks),
-                  (int)params->ivf.max_iters, params->ivf.tolerance, params->ivf.seed, init.get(),
-                  ix->centroids.p, &ivf_loss, &ivf_iters);
+      if (K > 256 && params->ivf.hierarchical_k > 1 && !params->ivf.init_centroids && nranks == 1) {
+        hierarchical_train(xs, s, d, K, am, params->ivf.balance_factor / (float)s, (int)params->ivf.max_iters,
+                           params->ivf.tolerance, (int)params->ivf.hierarchical_k, params->ivf.seed, ix->centroids.p);
+        ivf_loss.assign(1, 0.0);
+        ivf_iters.assign(1, 0);
+      } else {
+        lloyd_train(xs, s, d, 1, d, K, am, params->ivf.balance_factor / (float)(s * nranks),
+                    (int)params->ivf.max_iters, params->ivf.tolerance, params->ivf.seed, init.get(),
+                    ix->centroids.p, &ivf_loss, &ivf_iters);
+      }
     }
     LB2_CUDA(cudaEventRecord(ev[1], c.stream));
     // 2. PQ: residuals of its sample w.r.t. the IVF centroids (builder.rs:439-450)

@@ -763,4 +763,159 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// hierarchical k-means for k > 256 (kmeans.rs:746-1003): top level with k0 = min(16, k, n), then the
+// largest cluster is repeatedly split by a small k-means (k' <= 16) on its rows until k clusters
+// exist.  The heap is Rust's BinaryHeap restated (push = sift_up, pop = swap + sift_down_to_bottom +
+// sift_up; library/alloc/src/collections/binary_heap) ordered by (not finalized, size); the j-th
+// training call uses seed + j (the reference is unseeded).  Row index lists stay on the device.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct HCluster {
+  uint32_t id;
+  uint32_t off, len;  // segment of the device index array
+  bool finalized;
+};
+inline bool hc_le(const HCluster& a, const HCluster& b) {  // a <= b in the reference's Ord
+  if (a.finalized != b.finalized) return a.finalized;  // finalized < not finalized
+  return a.len <= b.len;
+}
+struct RustHeap {
+  std::vector<HCluster> data;
+  void sift_up(size_t start, size_t pos) {
+    HCluster elt = data[pos];
+    while (pos > start) {
+      size_t parent = (pos - 1) / 2;
+      if (hc_le(elt, data[parent])) break;
+      data[pos] = data[parent];
+      pos = parent;
+    }
+    data[pos] = elt;
+  }
+  void push(const HCluster& c) {
+    data.push_back(c);
+    sift_up(0, data.size() - 1);
+  }
+  HCluster pop() {
+    HCluster item = data.back();
+    data.pop_back();
+    if (!data.empty()) {
+      std::swap(item, data[0]);
+      size_t end = data.size(), pos = 0;
+      HCluster elt = data[0];
+      size_t child = 1;
+      while (child + 1 < end) {
+        if (hc_le(data[child], data[child + 1])) child += 1;
+        data[pos] = data[child];
+        pos = child;
+        child = 2 * pos + 1;
+      }
+      if (child + 1 == end) {
+        data[pos] = data[child];
+        pos = child;
+      }
+      data[pos] = elt;
+      sift_up(0, pos);
+    }
+    return item;
+  }
+};
+__global__ void gather_rows_u32_kernel(const float* __restrict__ x, const uint32_t* __restrict__ rows,
+                                       uint64_t s, int d, float* __restrict__ out) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= s * d) return;
+  out[g] = x[(uint64_t)rows[g / d] * d + g % d];
+}
+__global__ void compose_index_kernel(const uint32_t* __restrict__ parent, const uint32_t* __restrict__ members,
+                                     uint32_t cnt, uint32_t* __restrict__ out) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < cnt) out[g] = parent[members[g]];
+}
+__global__ void iota_kernel(uint32_t* p, uint32_t n) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) p[g] = g;
+}
+}  // namespace
+
+void hierarchical_train(const float* x, uint64_t n, int d, int K, int metric, float balance_factor,
+                        int max_iters, double tolerance, int hk, uint64_t seed, float* centroids_out) {
+  LB2_REQUIRE(n >= (uint64_t)K && n < 0xffffffffull, "KMeans: can not train %d centroids with %llu vectors", K,
+              (unsigned long long)n);
+  if (current_comm() && current_comm()->nranks > 1)
+    fail(LB2_UNSUPPORTED, "hierarchical k-means is not sharded yet: use k <= 256 per call on multiple GPUs");
+  const int k0 = (int)std::min<uint64_t>(std::min(hk, K), n);
+  DevBuf<float> top((size_t)k0 * d), sub((size_t)n * d), subc((size_t)hk * d), store((size_t)2 * K * d + (size_t)k0 * d);
+  DevBuf<uint32_t> ids(n), idx(n), tmp(n), ident(n);
+  DevBuf<uint8_t> valid(n);
+  uint64_t call = 0;
+  lloyd_train(x, n, d, 1, d, k0, metric, balance_factor, max_iters, tolerance, seed + call++, nullptr, top.p,
+              nullptr, nullptr);
+  assign_f32(x, n, d, top.p, k0, metric, nullptr, ids.p, nullptr, valid.p, nullptr);
+  MemberSort ms;
+  ms.run(ids.p, valid.p, n, k0, 1, nullptr);
+  std::vector<uint32_t> counts(std::max(k0, hk)), offs(std::max(k0, hk) + 1);
+  d2h(counts.data(), ms.counts.p, k0);
+  d2h(offs.data(), ms.offsets.p, k0 + 1);
+  d2d(idx.p, ms.members.p, n);
+  LB2_LAUNCH("iota", iota_kernel, cdiv(n, 256), 256, 0, ident.p, (uint32_t)n);
+  sync_stream();
+  RustHeap heap;
+  uint32_t next_id = 0;
+  const size_t store_slots = (size_t)2 * K + k0;
+  for (int i = 0; i < k0; ++i) {
+    if (counts[i] == 0) continue;
+    d2d(store.p + (size_t)next_id * d, top.p + (size_t)i * d, d);
+    heap.push(HCluster{next_id++, offs[i], counts[i], false});
+  }
+  while ((int)heap.data.size() < K) {
+    LB2_REQUIRE(!heap.data.empty(), "No cluster can be further split");
+    HCluster big = heap.pop();
+    if (big.finalized || big.len <= 1) {  // kmeans.rs:868-881: stop splitting
+      heap.push(big);
+      break;
+    }
+    const int remaining = K - (int)heap.data.size();
+    int ck;
+    if ((int)big.len <= hk)
+      ck = std::min(std::min(2, remaining), (int)big.len);
+    else
+      ck = std::max(2, std::min(std::min((int)(big.len / hk), remaining), hk));
+    LB2_LAUNCH("gather_rows", gather_rows_u32_kernel, cdiv((uint64_t)big.len * d, 256), 256, 0, x,
+               idx.p + big.off, (uint64_t)big.len, d, sub.p);
+    lloyd_train(sub.p, big.len, d, 1, d, ck, metric, balance_factor, max_iters, tolerance, seed + call++,
+                nullptr, subc.p, nullptr, nullptr);
+    assign_f32(sub.p, big.len, d, subc.p, ck, metric, nullptr, ids.p, nullptr, valid.p, nullptr);
+    ms.run(ids.p, valid.p, big.len, ck, 1, nullptr);
+    d2h(counts.data(), ms.counts.p, ck);
+    d2h(offs.data(), ms.offsets.p, ck + 1);
+    sync_stream();
+    int nonzero = 0;
+    for (int i = 0; i < ck; ++i) nonzero += counts[i] > 0;
+    if (nonzero <= 1) {  // ineffective split: finalise the original cluster (kmeans.rs:957-962)
+      big.finalized = true;
+      heap.push(big);
+      continue;
+    }
+    // children's row lists = parent's list re-ordered by (child, position): stable, rows dropped as
+    // None by the membership step leave the lists
+    const uint32_t kept = offs[ck];
+    LB2_LAUNCH("compose_index", compose_index_kernel, cdiv(kept, 256), 256, 0, idx.p + big.off,
+               ms.members.p, kept, tmp.p);
+    d2d(idx.p + big.off, tmp.p, kept);
+    for (int i = 0; i < ck; ++i) {
+      if (counts[i] == 0) continue;
+      LB2_REQUIRE(next_id < store_slots, "hierarchical k-means: centroid store exhausted");
+      d2d(store.p + (size_t)next_id * d, subc.p + (size_t)i * d, d);
+      heap.push(HCluster{next_id++, big.off + offs[i], counts[i], false});
+    }
+  }
+  if ((int)heap.data.size() != K)
+    fail(LB2_INVALID_ARG, "hierarchical k-means produced %zu of %d clusters (no cluster can be further split)",
+         heap.data.size(), K);
+  std::vector<HCluster> all = heap.data;
+  std::sort(all.begin(), all.end(), [](const HCluster& a, const HCluster& b) { return a.id < b.id; });
+  for (int i = 0; i < K; ++i) d2d(centroids_out + (size_t)i * d, store.p + (size_t)all[i].id * d, d);
+  sync_stream();
+}
+
 }  // namespace lb2

@@ -21,4 +21,7 @@ void lloyd_train(const float* x, uint64_t n, int ldx, int B, int ds, int K, int 
                  float balance_factor, int max_iters, double tolerance, uint64_t seed,
                  const float* init_dev, float* centroids, std::vector<double>* loss_out,
                  std::vector<uint32_t>* iters_out);
+// k > 256: the reference's hierarchical scheme (kmeans.rs:746-1003); the loss is not meaningful (0)
+void hierarchical_train(const float* x, uint64_t n, int d, int K, int metric, float balance_factor,
+                        int max_iters, double tolerance, int hk, uint64_t seed, float* centroids_out);
 }  // namespace lb2

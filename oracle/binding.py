@@ -290,3 +290,14 @@ def ivfflat_search(centroids, part_offsets, vectors, row_ids, queries, k, nprobe
                             _p(queries, C.c_float), C.c_uint64(nq), C.c_uint64(k), C.c_uint64(nprobes),
                             _p(oi, C.c_uint64), _p(od, C.c_float), _p(oc, C.c_uint32), C.c_int(nthreads))
     return oi, od, oc
+
+
+def hierarchical_kmeans(data, k, max_iters=50, tolerance=1e-4, balance_factor=0.0, metric="l2", hk=16, seed=0, nthreads=1):
+    data = _f32(data)
+    n, d = data.shape
+    out = np.zeros((k, d), np.float32)
+    got = lib().lo_hierarchical_kmeans(_p(data, C.c_float), C.c_uint64(n), C.c_uint64(d), C.c_uint64(k),
+                                       C.c_int(max_iters), C.c_double(tolerance), C.c_float(balance_factor),
+                                       C.c_int(METRIC[metric]), C.c_uint64(hk), C.c_uint64(seed),
+                                       _p(out, C.c_float), C.c_int(nthreads))
+    return out, got

@@ -450,6 +450,130 @@ int lo_kmeans_train(const float* data_in, uint64_t n_in, uint64_t d, uint64_t k,
 }
 
 // ---------------------------------------------------------------------------------------------
+// A6  hierarchical k-means for k > 256 (kmeans.rs:746-1003).  Heap = Rust BinaryHeap restated,
+// ordered by (not finalized, size); the j-th training call uses seed + j (reference unseeded).
+// Returns the number of clusters produced (== k unless no cluster can be split further).
+// ---------------------------------------------------------------------------------------------
+int lo_hierarchical_kmeans(const float* data, uint64_t n, uint64_t d, uint64_t target_k, int max_iters,
+                           double tolerance, float balance_factor, int metric, uint64_t hk, uint64_t seed,
+                           float* centroids_out, int nthreads) {
+  struct Cl {
+    uint32_t id;
+    std::vector<uint32_t> idx;
+    std::vector<float> c;
+    bool fin;
+  };
+  auto le = [](const Cl& a, const Cl& b) {
+    if (a.fin != b.fin) return a.fin;
+    return a.idx.size() <= b.idx.size();
+  };
+  std::vector<Cl> heap;
+  auto sift_up = [&](size_t start, size_t pos) {
+    Cl elt = std::move(heap[pos]);
+    while (pos > start) {
+      size_t parent = (pos - 1) / 2;
+      if (le(elt, heap[parent])) break;
+      heap[pos] = std::move(heap[parent]);
+      pos = parent;
+    }
+    heap[pos] = std::move(elt);
+  };
+  auto push = [&](Cl c) {
+    heap.push_back(std::move(c));
+    sift_up(0, heap.size() - 1);
+  };
+  auto pop = [&]() {
+    Cl item = std::move(heap.back());
+    heap.pop_back();
+    if (!heap.empty()) {
+      std::swap(item, heap[0]);
+      size_t end = heap.size(), pos = 0;
+      Cl elt = std::move(heap[0]);
+      size_t child = 1;
+      while (child + 1 < end) {
+        if (le(heap[child], heap[child + 1])) child += 1;
+        heap[pos] = std::move(heap[child]);
+        pos = child;
+        child = 2 * pos + 1;
+      }
+      if (child + 1 == end) {
+        heap[pos] = std::move(heap[child]);
+        pos = child;
+      }
+      heap[pos] = std::move(elt);
+      sift_up(0, pos);
+    }
+    return item;
+  };
+  const uint64_t k0 = std::min(std::min(hk, target_k), n);
+  std::vector<float> top(k0 * d);
+  double loss;
+  uint64_t call = 0;
+  lo_kmeans_train(data, n, d, k0, max_iters, tolerance, balance_factor, metric, seed + call++, nullptr,
+                  top.data(), &loss, nthreads);
+  std::vector<uint32_t> ids(n);
+  std::vector<uint8_t> valid(n);
+  lo_compute_membership(top.data(), k0, d, data, n, metric, 0.0f, nullptr, ids.data(), nullptr, valid.data(), nthreads);
+  uint32_t next_id = 0;
+  for (uint64_t i = 0; i < k0; ++i) {
+    Cl c;
+    for (uint64_t r = 0; r < n; ++r)
+      if (valid[r] && ids[r] == i) c.idx.push_back(uint32_t(r));
+    if (c.idx.empty()) continue;
+    c.id = next_id++;
+    c.c.assign(top.begin() + i * d, top.begin() + (i + 1) * d);
+    c.fin = false;
+    push(std::move(c));
+  }
+  std::vector<float> sub, subc(hk * d);
+  while (heap.size() < target_k) {
+    if (heap.empty()) break;
+    Cl big = pop();
+    if (big.fin || big.idx.size() <= 1) {
+      push(std::move(big));
+      break;
+    }
+    const uint64_t size = big.idx.size(), remaining = target_k - heap.size();
+    uint64_t ck;
+    if (size <= hk)
+      ck = std::min<uint64_t>(std::min<uint64_t>(2, remaining), size);
+    else
+      ck = std::max<uint64_t>(2, std::min(std::min(size / hk, remaining), hk));
+    sub.resize(size * d);
+    for (uint64_t r = 0; r < size; ++r) std::memcpy(&sub[r * d], data + uint64_t(big.idx[r]) * d, sizeof(float) * d);
+    lo_kmeans_train(sub.data(), size, d, ck, max_iters, tolerance, balance_factor, metric, seed + call++, nullptr,
+                    subc.data(), &loss, nthreads);
+    ids.resize(size);
+    valid.resize(size);
+    lo_compute_membership(subc.data(), ck, d, sub.data(), size, metric, 0.0f, nullptr, ids.data(), nullptr,
+                          valid.data(), nthreads);
+    std::vector<std::vector<uint32_t>> ch(ck);
+    for (uint64_t r = 0; r < size; ++r)
+      if (valid[r]) ch[ids[r]].push_back(big.idx[r]);
+    int nonzero = 0;
+    for (auto& v : ch) nonzero += !v.empty();
+    if (nonzero <= 1) {
+      big.fin = true;
+      push(std::move(big));
+      continue;
+    }
+    for (uint64_t i = 0; i < ck; ++i) {
+      if (ch[i].empty()) continue;
+      Cl c;
+      c.id = next_id++;
+      c.idx = std::move(ch[i]);
+      c.c.assign(subc.begin() + i * d, subc.begin() + (i + 1) * d);
+      c.fin = false;
+      push(std::move(c));
+    }
+  }
+  std::sort(heap.begin(), heap.end(), [](const Cl& a, const Cl& b) { return a.id < b.id; });
+  for (size_t i = 0; i < heap.size() && i < target_k; ++i)
+    std::memcpy(centroids_out + i * d, heap[i].c.data(), sizeof(float) * d);
+  return int(heap.size());
+}
+
+// ---------------------------------------------------------------------------------------------
 // a12  kmeans_find_partitions (kmeans.rs:1134-1158): all K distances, ascending partial sort.
 //   tie order among equal distances: arrow-ord is unpinned -> ascending (dist, id); NaN last.
 // ---------------------------------------------------------------------------------------------

@@ -522,3 +522,20 @@ def test_search_with_refine_matches_exact_rerank_of_oracle_candidates():
     plain, _ = ix.search(q, k=10, nprobes=nprobes)
     r0 = np.mean([len(set(plain[i].tolist()) & set(gt[i].tolist())) / 10 for i in range(len(q))])
     assert recall > r0 + 0.1 and recall >= 0.85, (recall, r0)
+
+
+def test_hierarchical_kmeans_for_k_above_256_matches_oracle():
+    # kmeans.rs:1511-1537 (k = 257 produces K finite centroids) + bit parity with the restated scheme
+    n, d, k = 30000, 32, 300
+    data = synth.gaussian_mixture(n, d, n_components=400, seed=71)
+    km = lb.train_kmeans(data, d, k, max_iters=10, seed=9, balance_factor=1.0)
+    assert km.centroids.shape == (k, d) and np.isfinite(km.centroids).all()
+    co, got = ob.hierarchical_kmeans(data, k, max_iters=10, seed=9,
+                                     balance_factor=float(np.float32(1.0) / np.float32(n)), nthreads=NT)
+    assert got == k
+    assert np.array_equal(km.centroids, co)
+    # quality: not worse than a flat Lloyd run of the same budget by more than 15 %
+    _, d_h, _ = ob.compute_membership(km.centroids, data, nthreads=NT)
+    flat, _, _ = ob.kmeans_train(data, k, max_iters=10, seed=9, nthreads=NT)
+    _, d_f, _ = ob.compute_membership(flat, data, nthreads=NT)
+    assert d_h.sum() <= 1.15 * d_f.sum()
