@@ -539,3 +539,64 @@ def test_hierarchical_kmeans_for_k_above_256_matches_oracle():
     flat, _, _ = ob.kmeans_train(data, k, max_iters=10, seed=9, nthreads=NT)
     _, d_f, _ = ob.compute_membership(flat, data, nthreads=NT)
     assert d_h.sum() <= 1.15 * d_f.sum()
+
+
+# ---- scaled-down shapes of the other BASELINE.json configs (parity cases, not bench lines) ------
+def test_config2_shape_768d_k300_m96():
+    # C2: 768-d f32, K > 256 (hierarchical training), M = 96 (8-wide sub-vectors, 98 KB LUT)
+    n, d, K, M = 12000, 768, 300, 96
+    data = synth.gaussian_mixture(n, d, n_components=64, seed=81)
+    ix = lb.IvfPqIndex.build(data, "l2", lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, max_iters=4, pq_max_iters=3))
+    parts = ix.export()
+    order = np.argsort(parts["row_ids"])
+    p_ref, _, _ = ob.compute_membership(parts["centroids"], data, nthreads=NT)
+    sizes = np.diff(parts["part_offsets"]).astype(np.int64)
+    assert np.array_equal(np.repeat(np.arange(K, dtype=np.uint32), sizes)[order], p_ref)
+    res = ob.compute_residual(parts["centroids"], data, p_ref, nthreads=NT)
+    assert np.array_equal(parts["codes"][order], ob.pq_encode(parts["codebook"], res, nthreads=NT))
+    q = synth.gaussian_mixture(10, d, n_components=64, seed=82)
+    ids, dists = ix.search(q, k=10, nprobes=6)
+    oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
+                                 parts["row_ids"], q, 10, 6, nthreads=NT)
+    for i in range(len(q)):
+        _check_topk(ids[i, :oc[i]], dists[i, :oc[i]], oi[i, :oc[i]], od[i, :oc[i]], 10)
+
+
+def test_config3_shape_f16_cosine():
+    # C3: f16 vectors, cosine (normalise, then L2): same results as the f32 path on the converted values
+    n, d, K, M = 20000, 128, 64, 16
+    data16 = (synth.gaussian_mixture(n, d, n_components=K, seed=83) * 0.25).astype(np.float16)
+    p = lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, max_iters=6, pq_max_iters=4)
+    i16 = lb.IvfPqIndex.build(data16, "cosine", p)
+    i32 = lb.IvfPqIndex.build(data16.astype(np.float32), "cosine", p)
+    e16, e32 = i16.export(), i32.export()
+    assert np.array_equal(e16["codes"], e32["codes"]) and np.array_equal(e16["row_ids"], e32["row_ids"])
+    q16 = data16[:30]
+    r16, r32 = i16.search(q16, k=10, nprobes=5), i32.search(q16.astype(np.float32), k=10, nprobes=5)
+    assert np.array_equal(r16[0], r32[0]) and np.array_equal(r16[1], r32[1])
+    # and against the oracle (cosine index = L2 on unit vectors, _distance = squared L2 of unit vectors)
+    oi, od, oc = ob.ivfpq_search(e32["centroids"], e32["codebook"], e32["part_offsets"], e32["codes"],
+                                 e32["row_ids"], q16.astype(np.float32), 10, 5, metric="cosine", nthreads=NT)
+    for i in range(30):
+        _check_topk(r32[0][i, :oc[i]], r32[1][i, :oc[i]], oi[i, :oc[i]], od[i, :oc[i]], 10)
+
+
+def test_config5_shape_u8_m32():
+    # C5: u8 vectors, M = 32 (4-wide sub-vectors -> exact small-d kernel), many partitions
+    rng = np.random.default_rng(85)
+    n, d, K, M = 30000, 128, 200, 32
+    data8 = np.clip(synth.sift_like(n, d, seed=85), 0, 255).astype(np.uint8)
+    ix = lb.IvfPqIndex.build(data8, "l2", lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, max_iters=6, pq_max_iters=4))
+    parts = ix.export()
+    f = data8.astype(np.float32)
+    order = np.argsort(parts["row_ids"])
+    p_ref, _, _ = ob.compute_membership(parts["centroids"], f, nthreads=NT)
+    sizes = np.diff(parts["part_offsets"]).astype(np.int64)
+    assert np.array_equal(np.repeat(np.arange(K, dtype=np.uint32), sizes)[order], p_ref)
+    res = ob.compute_residual(parts["centroids"], f, p_ref, nthreads=NT)
+    assert np.array_equal(parts["codes"][order], ob.pq_encode(parts["codebook"], res, nthreads=NT))
+    ids, dists = ix.search(data8[:16], k=10, nprobes=8)
+    oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
+                                 parts["row_ids"], f[:16], 10, 8, nthreads=NT)
+    for i in range(16):
+        _check_topk(ids[i, :oc[i]], dists[i, :oc[i]], oi[i, :oc[i]], od[i, :oc[i]], 10)
