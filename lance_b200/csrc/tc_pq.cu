@@ -113,8 +113,12 @@ tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ 
         tma_load_2d(sb + L.b_off + kc * B_CHUNK_BYTES, &map_b, b_full, kc * KC, 0);
       int s = 0;
       uint32_t ph = 0;
-      for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int kc = 0; kc < nkc; ++kc) {
+      // work item = (row tile, 32-float chunk = 4 sub-spaces): finer than whole tiles so that the
+      // 148 persistent CTAs stay balanced on short inputs (65 536-row training calls: 512 tiles)
+      for (uint64_t item = blockIdx.x; item < num_tiles * nkc; item += gridDim.x) {
+        const uint64_t tile = item / nkc;
+        {
+          const int kc = (int)(item % nkc);
           if (((act_mask >> (kc * 4)) & 0xF) == 0) continue;  // chunk with no active sub-space
           mbar_wait_relaxed(empty_bar(s), ph ^ 1);
           mbar_expect_tx(full_bar(s), A_STAGE_BYTES);
@@ -129,8 +133,9 @@ tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ 
       mbar_wait(b_full, 0);
       int s = 0;
       uint32_t ph = 0, it = 0;
-      for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int kc = 0; kc < nkc; ++kc) {
+      for (uint64_t item = blockIdx.x; item < num_tiles * nkc; item += gridDim.x) {
+        {
+          const int kc = (int)(item % nkc);
           const uint32_t cm = (act_mask >> (kc * 4)) & 0xF;
           if (cm == 0) continue;
           mbar_wait_relaxed(full_bar(s), ph);
@@ -159,10 +164,12 @@ tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ 
     mbar_wait(b_full, 0);  // the codebook tile is re-read by the exact re-rank below
     int s = 0;
     uint32_t ph = 0, it = 0;
-    for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (uint64_t item = blockIdx.x; item < num_tiles * nkc; item += gridDim.x) {
+      const uint64_t tile = item / nkc;
       const int rl = q * 32 + lane;  // row inside the tile == TMEM lane
       const uint64_t row = tile * TM + rl;
-      for (int kc = 0; kc < nkc; ++kc) {
+      {
+        const int kc = (int)(item % nkc);
         const uint32_t cm = (act_mask >> (kc * 4)) & 0xF;
         if (cm == 0) continue;
         mbar_wait(full_bar(s), ph);  // operands visible to this thread (re-read below)
@@ -373,7 +380,7 @@ void tc_pq_assign(const float* r, const float* rn2, uint64_t n, int d, int M, co
   const CUtensorMap map_r = make_map_2d(r, n, d, tc::TM);
   const CUtensorMap map_b = make_map_2d(ws->bm.p, tc::TN, d, tc::TN);
   const uint64_t tiles = (n + tc::TM - 1) / tc::TM;
-  const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)ctx().num_sms);
+  const unsigned grid = (unsigned)std::min<uint64_t>(tiles * nkc, (uint64_t)ctx().num_sms);
   const float* cnh = ws->cnh.p;
   const float* cbmax2 = ws->cnh.p + (size_t)M * tc::TN;
   const unsigned fb_grid = (unsigned)std::min<uint64_t>(cdiv(n * M * 16, 256), (uint64_t)ctx().num_sms * 8);
