@@ -270,8 +270,10 @@ __global__ void __launch_bounds__(256)
 generic_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __restrict__ cent, int K,
                const float* __restrict__ bias, uint32_t* __restrict__ part, float* __restrict__ dist,
                uint8_t* __restrict__ valid, float* __restrict__ all_out,
-               const uint8_t* __restrict__ active) {
+               const uint8_t* __restrict__ active, const uint32_t* __restrict__ row_list,
+               const uint32_t* __restrict__ row_count) {
   if (active && !active[0]) return;
+  if (row_list) n = *row_count;  // same indirection as the tile kernel
   extern __shared__ float smem[];
   constexpr int R = 8;
   float* xs = smem;  // [R][d]
@@ -280,9 +282,11 @@ generic_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __re
   __shared__ uint32_t red_idx[16][R];
   const int tid = threadIdx.x, hw = tid >> 4, l = tid & 15;
   const uint64_t row0 = (uint64_t)blockIdx.x * R;
+  if (row0 >= n) return;
   for (int idx = tid; idx < R * d; idx += 256) {
     int r = idx / d, e = idx % d;
-    xs[idx] = (row0 + r < n) ? x[(row0 + r) * d + e] : 0.0f;
+    const uint64_t src = row0 + r < n ? (row_list ? (uint64_t)row_list[row0 + r] : row0 + r) : 0;
+    xs[idx] = (row0 + r < n) ? x[src * d + e] : 0.0f;
   }
   __syncthreads();
   const int n16 = d & ~15;
@@ -330,8 +334,9 @@ generic_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __re
       if (better(red_key[h][tid], red_idx[h][tid], k0, i0)) {
         k0 = red_key[h][tid]; v0 = red_val[h][tid]; i0 = red_idx[h][tid];
       }
-    const uint64_t r = row0 + tid;
+    uint64_t r = row0 + tid;
     if (r < n) {
+      if (row_list) r = row_list[r];
       const bool ok = i0 != 0xffffffffu;
       part[r] = ok ? i0 : 0u;
       if (dist) dist[r] = ok ? v0 : __int_as_float(0x7fc00000);
@@ -385,11 +390,11 @@ static void assign_dispatch(const float* x, uint64_t n, int d, const float* cent
   if (all_out) {
     set_smem(generic_kernel<METRIC, true>, smem);
     LB2_LAUNCH("assign_exact_generic", (generic_kernel<METRIC, true>), grid, 256, smem, x, n, d,
-               cent, K, bias, part, dist, valid, all_out, active);
+               cent, K, bias, part, dist, valid, all_out, active, nullptr, nullptr);
   } else {
     set_smem(generic_kernel<METRIC, false>, smem);
     LB2_LAUNCH("assign_exact_generic", (generic_kernel<METRIC, false>), grid, 256, smem, x, n, d,
-               cent, K, bias, part, dist, valid, all_out, active);
+               cent, K, bias, part, dist, valid, all_out, active, nullptr, nullptr);
   }
 }
 
@@ -398,8 +403,15 @@ void assign_rows_f32(const float* x, uint64_t n_max, int d, const float* cent, i
                      const float* bias_padded, const uint32_t* row_list, const uint32_t* row_count,
                      uint32_t* part, float* dist, uint8_t* valid, const uint8_t* active,
                      TcWorkspace* ws, bool cT_ready) {
-  if (!(d % 16 == 0 && d <= 256) || metric != METRIC_L2)
-    fail(LB2_UNSUPPORTED, "assign_rows_f32: shape not supported");
+  if (metric != METRIC_L2) fail(LB2_UNSUPPORTED, "assign_rows_f32: metric not supported");
+  if (!(d % 16 == 0 && d <= 256)) {
+    const size_t gsmem = sizeof(float) * 8 * (size_t)d;
+    if (gsmem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "dimension %d too large for the exact kernel", d);
+    set_smem(generic_kernel<METRIC_L2, false>, gsmem);
+    LB2_LAUNCH("assign_exact_fallback", (generic_kernel<METRIC_L2, false>), cdiv(n_max, 8), 256, gsmem, x,
+               n_max, d, cent, K, bias_padded, part, dist, valid, nullptr, active, row_list, row_count);
+    return;
+  }
   const int Kp = (K + 63) / 64 * 64;
   TcWorkspace local;
   if (!ws) ws = &local;
@@ -423,7 +435,8 @@ void assign_f32_ex(const float* x, uint64_t n, int d, const float* cent, int K, 
     DevBuf<float> biasp;
     const float* bp = bias;
     if (bias && !bias_padded) {
-      biasp.alloc(256);
+      const int Kp256 = (K + 255) / 256 * 256;
+      biasp.alloc(Kp256);
       biasp.zero();
       d2d(biasp.get(), bias, K);
       bp = biasp.get();

@@ -180,6 +180,248 @@ top3_row256(taddr, cnh, m1, m2, m3);
 }
 
 // ------------------------------------------------------------------------------------------------
+// general shapes: any d % 32 == 0 and any K.  The centroid matrix no longer fits in shared memory,
+// so A (128 rows x 32 floats) AND B (256 centroids x 32 floats) chunks are streamed together through
+// the TMA ring (48 KB per stage), centroid tiles of 256 are visited one after the other with the
+// running top-3 (now with full indices) kept in registers by the epilogue group that owns the row tile.
+// ------------------------------------------------------------------------------------------------
+constexpr int GEN_STAGES = 4;
+constexpr int GEN_STAGE_BYTES = A_STAGE_BYTES + B_CHUNK_BYTES;  // 48 KB
+
+struct GenLayout {
+  uint32_t stage_off, cnh_off, hand_off, bar_off, tmem_ptr_off, total;
+};
+__host__ __device__ inline GenLayout gen_layout() {
+  GenLayout L;
+  L.stage_off = 0;
+  L.cnh_off = GEN_STAGES * GEN_STAGE_BYTES;
+  L.hand_off = L.cnh_off + 2 * TN * 4;
+  L.bar_off = L.hand_off + 2 * 6 * 128 * 4;
+  L.tmem_ptr_off = L.bar_off + (2 * GEN_STAGES + 4) * 8;
+  L.total = L.tmem_ptr_off + 16;
+  return L;
+}
+
+// insert (v, i) into the descending triple (g, gi)
+__device__ __forceinline__ void top3_insert_idx(float v, uint32_t i, float* g, uint32_t* gi) {
+  if (v > g[0]) {
+    g[2] = g[1]; gi[2] = gi[1];
+    g[1] = g[0]; gi[1] = gi[0];
+    g[0] = v; gi[0] = i;
+  } else if (v > g[1]) {
+    g[2] = g[1]; gi[2] = gi[1];
+    g[1] = v; gi[1] = i;
+  } else if (v > g[2]) {
+    g[2] = v; gi[2] = i;
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_filter_general_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
+                         uint64_t n, int nkc, int ntiles, const float* __restrict__ cnh_g,
+                         const float* __restrict__ row_norm2, const float* __restrict__ cmax2_ptr,
+                         uint32_t* __restrict__ res, uint32_t* __restrict__ res_hi,
+                         const uint8_t* __restrict__ active) {
+  if (active && !active[0]) return;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const GenLayout L = gen_layout();
+  float* cnh_s = reinterpret_cast<float*>(smem + L.cnh_off);  // [2][TN], one slice per epilogue group
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L.tmem_ptr_off);
+  const uint32_t sb = smem_u32(smem);
+  auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
+  auto empty_bar = [&](int s) { return smem_u32(&bars[GEN_STAGES + s]); };
+  auto tfull_bar = [&](int b) { return smem_u32(&bars[2 * GEN_STAGES + b]); };
+  auto tempty_bar = [&](int b) { return smem_u32(&bars[2 * GEN_STAGES + 2 + b]); };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t num_tiles = (n + TM - 1) / TM;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < GEN_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr_smem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer: A and B chunk of every (row tile, centroid tile, k chunk)
+      int s = 0;
+      uint32_t ph = 0;
+      for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+        for (int nt = 0; nt < ntiles; ++nt)
+          for (int kc = 0; kc < nkc; ++kc) {
+            mbar_wait_relaxed(empty_bar(s), ph ^ 1);
+            mbar_expect_tx(full_bar(s), GEN_STAGE_BYTES);
+            const uint32_t st = sb + L.stage_off + s * GEN_STAGE_BYTES;
+            tma_load_2d(st, &map_x, full_bar(s), kc * KC, (int)(tile * TM));
+            tma_load_2d(st + A_STAGE_BYTES, &map_c, full_bar(s), kc * KC, nt * TN);
+            if (++s == GEN_STAGES) { s = 0; ph ^= 1; }
+          }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer
+      int s = 0;
+      uint32_t ph = 0, it = 0;
+      for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+        for (int nt = 0; nt < ntiles; ++nt, ++it) {
+          const uint32_t buf = it & 1;
+          mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t d_tmem = tmem_base + buf * TN;
+          for (int kc = 0; kc < nkc; ++kc) {
+            mbar_wait_relaxed(full_bar(s), ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_addr = sb + L.stage_off + s * GEN_STAGE_BYTES;
+            const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8)
+              umma_tf32(d_tmem, make_desc(a_addr + k8 * 32), make_desc(b_addr + k8 * 32), (kc | k8) != 0 ? 1u : 0u);
+            umma_commit(empty_bar(s));
+            if (++s == GEN_STAGES) { s = 0; ph ^= 1; }
+          }
+          umma_commit(tfull_bar(buf));
+        }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: the two groups alternate over the global (row tile, centroid tile) counter so
+    // both stay busy; the group that drains a row tile's LAST centroid tile merges the other group's
+    // partial top-3 (handed over through shared memory) and writes the row's verdict.
+    const int q = warp & 3;
+    const uint32_t group = (warp >> 2) - 1;
+    const int gt = threadIdx.x - 128 - group * 128;  // 0..127 inside the group == row inside the tile
+    float* cn = cnh_s + group * TN;
+    uint32_t* hand = reinterpret_cast<uint32_t*>(smem + L.hand_off);  // [2][6][128]
+    const float cmax2 = *cmax2_ptr;
+    uint32_t mt = 0;
+    for (uint64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++mt) {
+      const uint32_t it0 = mt * (uint32_t)ntiles;
+      const float ninf = __int_as_float(0xff800000);
+      float g[3] = {ninf, ninf, ninf};
+      uint32_t gi[3] = {0, 0, 0};
+      float hv[3] = {ninf, ninf, ninf};
+      uint32_t hi[3] = {0, 0, 0};
+      uint32_t* h = hand + (mt & 1) * 6 * 128;
+      const int bar_id = 3 + (int)(mt & 1);
+      for (int nt = 0; nt < ntiles; ++nt) {
+        const uint32_t it = it0 + nt;
+        const uint32_t buf = it & 1;
+        if (buf != group) continue;
+        // this tile's -(|c|^2+bias)/2 slice (the group's own 128 threads, then a group barrier)
+        cn[gt] = cnh_g[(size_t)nt * TN + gt];
+        cn[gt + 128] = cnh_g[(size_t)nt * TN + gt + 128];
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)group) : "memory");
+        mbar_wait(tfull_bar(buf), (it >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * TN;
+        float m1 = ninf, m2 = ninf, m3 = ninf;
+        top3_row256(taddr, cn, m1, m2, m3);
+        if (ntiles > 1 && nt == ntiles - 1) {
+          // finisher: take the other group's partial BEFORE releasing this TMEM buffer -- the release is
+          // what lets the pipeline (and with it the other group) run on to the row tile that reuses the
+          // hand-over slot and the named barrier
+          asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            hv[j] = __uint_as_float(h[j * 128 + gt]);
+            hi[j] = h[(3 + j) * 128 + gt];
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(buf));
+        const uint32_t base = (uint32_t)nt * TN;
+        top3_insert_idx(m1, base + (__float_as_uint(m1) & 0xFFu), g, gi);
+        top3_insert_idx(m2, base + (__float_as_uint(m2) & 0xFFu), g, gi);
+        top3_insert_idx(m3, base + (__float_as_uint(m3) & 0xFFu), g, gi);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)group) : "memory");  // cn is rewritten next tile
+      }
+      const uint32_t fin = (it0 + (uint32_t)ntiles - 1) & 1;
+      if (group != fin) {
+        if (ntiles > 1) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            h[j * 128 + gt] = __float_as_uint(g[j]);
+            h[(3 + j) * 128 + gt] = gi[j];
+          }
+          __threadfence_block();
+          asm volatile("bar.arrive %0, 256;" ::"r"(bar_id) : "memory");
+        }
+        continue;
+      }
+      if (ntiles > 1) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) top3_insert_idx(hv[j], hi[j], g, gi);
+      }
+      const uint64_t row = tile * TM + q * 32 + lane;
+      if (row < n) {
+        const float tau = 0.0029296875f * (row_norm2[row] + cmax2);  // 3 * 2^-10
+        uint32_t flag = 2;
+        if (g[0] - g[1] > tau) flag = 0;
+        else if (g[0] - g[2] > tau) flag = 1;
+        res[row] = gi[0] | (flag << 30);
+        res_hi[row] = gi[1];
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// padded copy [Kp][d] (Kp multiple of 256), cnh, |c|^2 for any K: one warp per centroid
+__global__ void prep_centroids_general_kernel(const float* __restrict__ c, int K, int Kp, int d,
+                                              const float* __restrict__ bias, float* __restrict__ cpad,
+                                              float* __restrict__ cnh, float* __restrict__ cn2,
+                                              uint32_t* __restrict__ fb_count) {
+  const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *fb_count = 0;
+  if (k >= Kp) return;
+  float n2 = 0.0f;
+  for (int e = lane; e < d; e += 32) {
+    const float v = k < K ? c[(size_t)k * d + e] : 0.0f;
+    cpad[(size_t)k * d + e] = v;
+    n2 += v * v;
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+  if (lane == 0) {
+    cnh[k] = k < K ? -0.5f * (n2 + (bias ? bias[k] : 0.0f)) : -3.0e38f;
+    cn2[k] = (k < K && n2 == n2) ? n2 : 0.0f;
+  }
+}
+__global__ void max_reduce_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  __shared__ float s[32];
+  float m = 0.0f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, v[i]);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = 0.0f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r = fmaxf(r, s[i]);
+    *out = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // preparation kernels
 // ------------------------------------------------------------------------------------------------
 // padded copy of the centroids [TN][d] (zero rows past K), cnh[k] = -(|c_k|^2 + bias_k)/2 (-3e38 pads),
@@ -232,7 +474,8 @@ __global__ void row_norm_kernel(const float* __restrict__ x, uint64_t n, int d, 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 rerank_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __restrict__ cent,
-              const float* __restrict__ bias, const uint32_t* __restrict__ res, int need_dist,
+              const float* __restrict__ bias, const uint32_t* __restrict__ res,
+              const uint32_t* __restrict__ res_hi, int need_dist,
               uint32_t* __restrict__ part, float* __restrict__ dist, uint8_t* __restrict__ valid,
               uint32_t* __restrict__ fb_rows, uint32_t* __restrict__ fb_count,
               const uint8_t* __restrict__ active) {
@@ -243,7 +486,8 @@ rerank_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __res
   const unsigned mask = 0xffffu << (16 * ((threadIdx.x >> 4) & 1));
   const uint32_t r = res[row];
   const uint32_t flag = r >> 30;
-  const uint32_t i1 = r & 0xFFFu, i2 = (r >> 12) & 0xFFFu;
+  const uint32_t i1 = res_hi ? (r & 0x3FFFFFFFu) : (r & 0xFFFu);
+  const uint32_t i2 = res_hi ? res_hi[row] : ((r >> 12) & 0xFFFu);
   if (flag == 2) {
     if (l == 0) fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)row;
     return;
@@ -311,16 +555,73 @@ CUtensorMap make_map_2d(const float* base, uint64_t rows, uint64_t cols, uint32_
   return m;
 }
 
+static bool tc_resident_shape(int d, int K) { return d <= 128 && K <= tc::TN; }
+
 bool tc_assign_supported(uint64_t n, int d, int K, int metric, const float* x) {
   if (getenv("LB2_DISABLE_TC") && *getenv("LB2_DISABLE_TC")) return false;
-  return metric == METRIC_L2 && d % tc::KC == 0 && d >= 32 && d <= 128 && K >= 2 && K <= tc::TN &&
+  return metric == METRIC_L2 && d % tc::KC == 0 && d >= 32 && d <= 4096 && K >= 2 && K < (1 << 28) &&
          n >= 1 && n < (1ull << 31) && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+}
+
+// general shapes (centroid tiles streamed): same contract as tc_assign_f32
+static void tc_assign_general_f32(const float* x, uint64_t n, int d, const float* cent, int K, const float* bias,
+                                  uint32_t* part, float* dist, uint8_t* valid, const uint8_t* active,
+                                  TcWorkspace* ws) {
+  using namespace tc;
+  const int nkc = d / KC, ntiles = (K + TN - 1) / TN, Kp = ntiles * TN;
+  const GenLayout L = gen_layout();
+  const size_t smem = L.total + 1024;
+  if (smem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "tc_assign: shared memory");
+  if (ws->cpad.n < (size_t)Kp * d) ws->cpad.alloc((size_t)Kp * d);
+  if (ws->cnh.n < (size_t)2 * Kp + 1) ws->cnh.alloc((size_t)2 * Kp + 1);
+  if (ws->row_norm2.n < n || ws->norm_src != x || ws->norm_n != n) {
+    if (ws->row_norm2.n < n) ws->row_norm2.alloc(n);
+    LB2_LAUNCH("tc_row_norms", row_norm_kernel, cdiv(n * 16, 256), 256, 0, x, n, d, ws->row_norm2.p);
+    ws->norm_src = x;
+    ws->norm_n = n;
+  }
+  if (ws->res.n < 2 * n) ws->res.alloc(2 * n);
+  if (ws->fb_rows.n < n) ws->fb_rows.alloc(n);
+  if (ws->fb_count.n < 1) ws->fb_count.alloc(1);
+  float* cnh = ws->cnh.p;
+  float* cn2 = ws->cnh.p + Kp;
+  float* cmax2 = ws->cnh.p + 2 * (size_t)Kp;
+  LB2_LAUNCH("tc_prep_centroids", prep_centroids_general_kernel, cdiv(Kp, 8), 256, 0, cent, K, Kp, d, bias,
+             ws->cpad.p, cnh, cn2, ws->fb_count.p);
+  LB2_LAUNCH("tc_prep_centroids", max_reduce_kernel, 1, 1024, 0, cn2, Kp, cmax2);
+  const CUtensorMap map_x = make_map_2d(x, n, d, TM);
+  const CUtensorMap map_c = make_map_2d(ws->cpad.p, Kp, d, TN);
+  const uint64_t tiles = (n + TM - 1) / TM;
+  const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)ctx().num_sms);
+  set_smem(tc_filter_general_kernel, smem);
+  LB2_LAUNCH("tc_filter_general", tc_filter_general_kernel, grid, NUM_THREADS, smem, map_x, map_c, n, nkc,
+             ntiles, cnh, ws->row_norm2.p, cmax2, ws->res.p, ws->res.p + n, active);
+  LB2_LAUNCH("tc_rerank", rerank_kernel, cdiv(n * 16, 256), 256, 0, x, n, d, cent, bias, ws->res.p,
+             (const uint32_t*)(ws->res.p + n), dist != nullptr ? 1 : 0, part, dist, valid, ws->fb_rows.p,
+             ws->fb_count.p, active);
+  if (getenv("LB2_TC_STATS") && *getenv("LB2_TC_STATS")) {
+    std::vector<uint32_t> h(n);
+    d2h(h.data(), ws->res.p, n);
+    sync_stream();
+    uint64_t f[4] = {0, 0, 0, 0};
+    for (uint64_t i = 0; i < n; ++i) f[h[i] >> 30]++;
+    fprintf(stderr, "[lb2 tc_filter_general] n=%llu K=%d d=%d: unique %.2f%%, two-candidate %.2f%%, exact-fallback %.2f%%\n",
+            (unsigned long long)n, K, d, 100.0 * f[0] / n, 100.0 * f[1] / n, 100.0 * f[2] / n);
+  }
+  assign_rows_f32(x, n, d, cent, K, METRIC_L2, bias, ws->fb_rows.p, ws->fb_count.p, part, dist, valid, active, ws,
+                  /*cT_ready=*/false);
 }
 
 void tc_assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, const float* bias,
                    uint32_t* part, float* dist, uint8_t* valid, const uint8_t* active,
                    TcWorkspace* ws) {
   using namespace tc;
+  TcWorkspace local0;
+  if (!ws) ws = &local0;
+  if (!tc_resident_shape(d, K)) {
+    tc_assign_general_f32(x, n, d, cent, K, bias, part, dist, valid, active, ws);
+    return;
+  }
   const int nkc = d / KC;
   int stages = MAX_STAGES;
   SmemLayout L = smem_layout(nkc, stages);
@@ -352,7 +653,8 @@ void tc_assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, 
   LB2_LAUNCH("tc_filter", tc_filter_kernel, grid, NUM_THREADS, smem, map_x, map_c, n, nkc, stages,
              ws->cnh.p, ws->row_norm2.p, ws->cnh.p + TN, ws->res.p, active);
   LB2_LAUNCH("tc_rerank", rerank_kernel, cdiv(n * 16, 256), 256, 0, x, n, d, cent, bias, ws->res.p,
-             dist != nullptr ? 1 : 0, part, dist, valid, ws->fb_rows.p, ws->fb_count.p, active);
+             (const uint32_t*)nullptr, dist != nullptr ? 1 : 0, part, dist, valid, ws->fb_rows.p,
+             ws->fb_count.p, active);
   if (getenv("LB2_TC_STATS") && *getenv("LB2_TC_STATS")) {  // diagnostics: how selective was the filter?
     std::vector<uint32_t> h(n);
     d2h(h.data(), ws->res.p, n);

@@ -325,6 +325,32 @@ def test_tc_filter_equals_exact_path(n, d, k):
     assert np.array_equal(p1, po) and np.array_equal(d1, do)
 
 
+@pytest.mark.parametrize("n,d,k", [(3000, 768, 300), (2000, 768, 1000), (5000, 64, 1000), (2500, 128, 4096),
+                                   (700, 256, 256), (1500, 1536, 64), (4000, 160, 513), (300, 32, 257)])
+def test_tc_filter_general_shapes_equal_exact_path(n, d, k):
+    # d > 128 and/or K > 256: centroid tiles streamed through the TMA ring, running top-3 across tiles
+    rng = np.random.default_rng(n * 3 + d + k)
+    cent = (rng.standard_normal((k, d)) * 3).astype(np.float32)
+    cent[k - 1] = cent[0]       # duplicate in the LAST centroid tile: index 0 must win
+    data = (cent[rng.integers(0, k, n)] + rng.standard_normal((n, d))).astype(np.float32)
+    data[7] = np.nan
+    data[11] = ((cent[1] + cent[k - 2]) * 0.5).astype(np.float32)   # half-way across tiles
+    (p1, d1, v1), (p2, d2, v2) = _both_paths(lambda: lb.compute_partitions(cent, data))
+    assert np.array_equal(v1, v2) and not v1[7]
+    assert np.array_equal(p1[v1], p2[v2]) and np.array_equal(d1[v1], d2[v2])
+    po, do, vo = ob.compute_membership(cent, data, nthreads=NT)
+    assert np.array_equal(p1[v1], po[vo]) and np.array_equal(d1[v1], do[vo])
+
+
+def test_tc_filter_general_training_with_balance_bias():
+    # direct Lloyd at K > 256 (hierarchical off): the bias/balance term goes through the streamed path
+    data = synth.sift_like(40000, 64, seed=77)
+    init = data[np.random.default_rng(5).choice(40000, 320, replace=False)].copy()
+    (k1, k2) = _both_paths(lambda: lb.train_kmeans(data, 64, 320, max_iters=6, centroids=init,
+                                                   balance_factor=1.0))
+    assert k1.iters == k2.iters and k1.loss == k2.loss and np.array_equal(k1.centroids, k2.centroids)
+
+
 def test_tc_filter_adversarial_near_ties():
     # centroids in tight groups (differences far below the TF32 resolution), exact duplicates, and
     # rows exactly half-way between two centroids: every row must still match the exact path
