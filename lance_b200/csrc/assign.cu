@@ -40,11 +40,16 @@ assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* 
                    int K, int Kp, const float* __restrict__ bias, uint32_t* __restrict__ part,
                    float* __restrict__ dist, uint8_t* __restrict__ valid,
                    float* __restrict__ all_out, const uint8_t* __restrict__ active,
-                   const uint32_t* __restrict__ row_list, const uint32_t* __restrict__ row_count) {
+                   const uint32_t* __restrict__ row_list, const uint32_t* __restrict__ row_count,
+                   uint32_t cnt_lo, uint32_t cnt_hi) {
   if (active && !active[0]) return;
   // optional indirection: process only rows row_list[0 .. *row_count) (the tensor-core filter's
-  // ambiguous rows); outputs are written at the ORIGINAL row positions
-  if (row_list) n = *row_count;
+  // ambiguous rows); outputs are written at the ORIGINAL row positions.  [cnt_lo, cnt_hi) selects
+  // the list lengths this instantiation serves (short lists: 16-row tiles, long lists: 64-row tiles)
+  if (row_list) {
+    n = *row_count;
+    if (n < cnt_lo || n >= cnt_hi) return;
+  }
   extern __shared__ float smem[];
   const int ld = d + 1;
   constexpr int ROWS = 16 * RT;
@@ -265,7 +270,7 @@ small_d_kernel(const float* __restrict__ x, uint64_t n, int ldx, const float* __
 // (c) generic kernel: 8 rows per CTA in smem, 16 half-warps stride over the centroids, lane l of a
 // half-warp owns lane-accumulator l (elements 16c+l) -> coalesced 64-byte centroid reads.
 // ------------------------------------------------------------------------------------------------
-template <int METRIC, bool WRITE_ALL>
+template <int METRIC, bool WRITE_ALL, int R>
 __global__ void __launch_bounds__(256)
 generic_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __restrict__ cent, int K,
                const float* __restrict__ bias, uint32_t* __restrict__ part, float* __restrict__ dist,
@@ -275,7 +280,6 @@ generic_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __re
   if (active && !active[0]) return;
   if (row_list) n = *row_count;  // same indirection as the tile kernel
   extern __shared__ float smem[];
-  constexpr int R = 8;
   float* xs = smem;  // [R][d]
   __shared__ float red_key[16][R];
   __shared__ float red_val[16][R];
@@ -291,7 +295,7 @@ generic_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __re
   __syncthreads();
   const int n16 = d & ~15;
   float bkey = __int_as_float(0x7f800000), bval = __int_as_float(0x7f800000);
-  uint32_t bidx = 0xffffffffu;  // lane (l & 7) tracks row (l & 7)
+  uint32_t bidx = 0xffffffffu;  // lane l tracks row (l & (R - 1)); R is 8 or 16
   const unsigned hmask = 0xffffu << (16 * ((tid >> 4) & 1));
   for (int c = hw; c < K; c += 16) {
     const float* cp = cent + (size_t)c * d;
@@ -315,7 +319,7 @@ generic_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __re
       const float v = finish<METRIC>(f_add(s, t));
       if (WRITE_ALL) {
         if (l == r && row0 + r < n) all_out[(row0 + r) * K + c] = v;
-      } else if ((l & 7) == r) {
+      } else if ((l & (R - 1)) == r) {
         mine = v;
       }
     }
@@ -376,26 +380,31 @@ static void assign_dispatch(const float* x, uint64_t n, int d, const float* cent
     if (all_out) {
       set_smem(assign_tile_kernel<METRIC, true, 4>, smem);
       LB2_LAUNCH("assign_exact", (assign_tile_kernel<METRIC, true, 4>), grid, 256, smem, x, n, d,
-                 cT.get(), K, Kp, bp, part, dist, valid, all_out, active, nullptr, nullptr);
+                 cT.get(), K, Kp, bp, part, dist, valid, all_out, active, nullptr, nullptr, 0u, 0xffffffffu);
     } else {
       set_smem(assign_tile_kernel<METRIC, false, 4>, smem);
       LB2_LAUNCH("assign_exact", (assign_tile_kernel<METRIC, false, 4>), grid, 256, smem, x, n, d,
-                 cT.get(), K, Kp, bp, part, dist, valid, all_out, active, nullptr, nullptr);
+                 cT.get(), K, Kp, bp, part, dist, valid, all_out, active, nullptr, nullptr, 0u, 0xffffffffu);
     }
     return;
   }
-  const size_t smem = sizeof(float) * 8 * (size_t)d;
+  // 16 rows per CTA halve the centroid re-reads from L2; wide vectors fall back to 8 rows
+  const bool r16 = sizeof(float) * 16 * (size_t)d <= 96 * 1024;
+  const size_t smem = sizeof(float) * (r16 ? 16 : 8) * (size_t)d;
   if (smem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "dimension %d too large for the exact kernel", d);
-  const unsigned grid = cdiv(n, 8);
+  const unsigned grid = cdiv(n, r16 ? 16 : 8);
+#define LB2_GENERIC(WA, RR)                                                                        \
+  do {                                                                                             \
+    set_smem(generic_kernel<METRIC, WA, RR>, smem);                                                \
+    LB2_LAUNCH("assign_exact_generic", (generic_kernel<METRIC, WA, RR>), grid, 256, smem, x, n, d, \
+               cent, K, bias, part, dist, valid, all_out, active, nullptr, nullptr);               \
+  } while (0)
   if (all_out) {
-    set_smem(generic_kernel<METRIC, true>, smem);
-    LB2_LAUNCH("assign_exact_generic", (generic_kernel<METRIC, true>), grid, 256, smem, x, n, d,
-               cent, K, bias, part, dist, valid, all_out, active, nullptr, nullptr);
+    if (r16) LB2_GENERIC(true, 16); else LB2_GENERIC(true, 8);
   } else {
-    set_smem(generic_kernel<METRIC, false>, smem);
-    LB2_LAUNCH("assign_exact_generic", (generic_kernel<METRIC, false>), grid, 256, smem, x, n, d,
-               cent, K, bias, part, dist, valid, all_out, active, nullptr, nullptr);
+    if (r16) LB2_GENERIC(false, 16); else LB2_GENERIC(false, 8);
   }
+#undef LB2_GENERIC
 }
 
 // exact tile kernel over a device-side row list (count read on the device: no host sync)
@@ -405,11 +414,18 @@ void assign_rows_f32(const float* x, uint64_t n_max, int d, const float* cent, i
                      TcWorkspace* ws, bool cT_ready) {
   if (metric != METRIC_L2) fail(LB2_UNSUPPORTED, "assign_rows_f32: metric not supported");
   if (!(d % 16 == 0 && d <= 256)) {
-    const size_t gsmem = sizeof(float) * 8 * (size_t)d;
+    const bool r16 = sizeof(float) * 16 * (size_t)d <= 96 * 1024;
+    const size_t gsmem = sizeof(float) * (r16 ? 16 : 8) * (size_t)d;
     if (gsmem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "dimension %d too large for the exact kernel", d);
-    set_smem(generic_kernel<METRIC_L2, false>, gsmem);
-    LB2_LAUNCH("assign_exact_fallback", (generic_kernel<METRIC_L2, false>), cdiv(n_max, 8), 256, gsmem, x,
-               n_max, d, cent, K, bias_padded, part, dist, valid, nullptr, active, row_list, row_count);
+    if (r16) {
+      set_smem(generic_kernel<METRIC_L2, false, 16>, gsmem);
+      LB2_LAUNCH("assign_exact_fallback", (generic_kernel<METRIC_L2, false, 16>), cdiv(n_max, 16), 256, gsmem,
+                 x, n_max, d, cent, K, bias_padded, part, dist, valid, nullptr, active, row_list, row_count);
+    } else {
+      set_smem(generic_kernel<METRIC_L2, false, 8>, gsmem);
+      LB2_LAUNCH("assign_exact_fallback", (generic_kernel<METRIC_L2, false, 8>), cdiv(n_max, 8), 256, gsmem,
+                 x, n_max, d, cent, K, bias_padded, part, dist, valid, nullptr, active, row_list, row_count);
+    }
     return;
   }
   const int Kp = (K + 63) / 64 * 64;
@@ -420,11 +436,23 @@ void assign_rows_f32(const float* x, uint64_t n_max, int d, const float* cent, i
   if (!cT_ready)
     LB2_LAUNCH("transpose_centroids", transpose_pad_kernel, cdiv((uint64_t)d * Kp, 256), 256, 0, cent,
                K, d, Kp, cT.get());
+  // short lists: 16-row tiles so that the work still spreads over all SMs; long lists: 64-row tiles
+  // (4x fewer passes over the centroids).  The count lives on the device, so both are launched and
+  // the one whose range does not hold the count exits at once.
+  // (only worth a second launch when the centroid matrix is large: K > 256)
+  const uint32_t split = K > 256 ? 64u * 2u * (uint32_t)ctx().num_sms : 0xffffffffu;
   const size_t smem = sizeof(float) * (16 * (d + 1) + (size_t)d * 64);
   set_smem(assign_tile_kernel<METRIC_L2, false, 1>, smem);
-  LB2_LAUNCH("assign_exact_fallback", (assign_tile_kernel<METRIC_L2, false, 1>), cdiv(n_max, 16), 256,
-             smem, x, n_max, d, cT.get(), K, Kp, bias_padded, part, dist, valid, nullptr, active,
-             row_list, row_count);
+  LB2_LAUNCH("assign_exact_fallback", (assign_tile_kernel<METRIC_L2, false, 1>),
+             cdiv(std::min<uint64_t>(n_max, split), 16), 256, smem, x, n_max, d, cT.get(), K, Kp, bias_padded,
+             part, dist, valid, nullptr, active, row_list, row_count, 0u, split);
+  if (n_max >= split) {
+    const size_t smem4 = sizeof(float) * (64 * (d + 1) + (size_t)d * 64);
+    set_smem(assign_tile_kernel<METRIC_L2, false, 4>, smem4);
+    LB2_LAUNCH("assign_exact_fallback", (assign_tile_kernel<METRIC_L2, false, 4>), cdiv(n_max, 64), 256, smem4,
+               x, n_max, d, cT.get(), K, Kp, bias_padded, part, dist, valid, nullptr, active, row_list,
+               row_count, split, 0xffffffffu);
+  }
 }
 
 void assign_f32_ex(const float* x, uint64_t n, int d, const float* cent, int K, int metric,

@@ -122,7 +122,7 @@ struct LaunchScope {
 
 template <class K>
 inline void set_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024)
+  if (bytes > 32 * 1024)  // static shared memory counts against the 48 KB default as well
     LB2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
 

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "common.cuh"
 
@@ -32,32 +33,61 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Watchdog: a wait that spins for more than ~4 s of SM clocks is a protocol bug, never a slow kernel.
+// It reports which barrier starved and traps (the launch fails with an error instead of hanging the
+// GPU).  With -DLB2_TC_WATCHDOG_SOFT the first starved wait only raises a flag that makes every
+// later wait fall through, so the kernel ends and the printf buffer reaches the host.
+#ifdef LB2_TC_WATCHDOG_SOFT
+static __device__ int g_wd_abort = 0;
+#endif
+static __device__ __noinline__ void mbar_watchdog_report(uint32_t bar, uint32_t parity) {
+  printf("[lb2 watchdog] block %d thread %d: mbarrier smem+0x%x parity %u starved\n", (int)blockIdx.x,
+         (int)threadIdx.x, bar, parity);
+#ifdef LB2_TC_WATCHDOG_SOFT
+  g_wd_abort = 1;
+  __threadfence();
+#else
+  __trap();
+#endif
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  for (uint32_t spins = 1;; ++spins) {
+    if (mbar_try(bar, parity)) return;
+    if ((spins & 0xFFFu) == 0) {
+#ifdef LB2_TC_WATCHDOG_SOFT
+      if (*(volatile int*)&g_wd_abort) return;
+#endif
+      if (clock64() - t0 > 8000000000ll) { mbar_watchdog_report(bar, parity); return; }
+    }
+  }
 }
 // same, for the single-thread producer / issuer roles: back off between polls so that the spin
 // loop does not steal issue slots from the epilogue warps sharing the scheduler
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  for (;;) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) break;
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  for (uint32_t spins = 1;; ++spins) {
+    if (mbar_try(bar, parity)) return;
     __nanosleep(40);
+    if ((spins & 0xFFu) == 0) {
+#ifdef LB2_TC_WATCHDOG_SOFT
+      if (*(volatile int*)&g_wd_abort) return;
+#endif
+      if (clock64() - t0 > 8000000000ll) { mbar_watchdog_report(bar, parity); return; }
+    }
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,

@@ -21,7 +21,9 @@ for n, d, K in ((200000, 768, 1024), (500000, 128, 4096), (500000, 256, 256), (1
     dx.free = lambda: None
     torch.cuda.synchronize()
     os.environ.pop("LB2_DISABLE_TC", None)
+    print("shape", n, d, K, "tc warm-up call", flush=True)
     lb.compute_partitions(cent, dx)
+    print("  done", flush=True)
     lb.profile.reset(); lb.profile.enable(True)
     p1, d1, v1 = lb.compute_partitions(cent, dx)
     lb.profile.enable(False)
