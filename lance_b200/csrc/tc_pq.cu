@@ -28,20 +28,42 @@ using namespace tc;
 
 constexpr int DS = 8;
 constexpr int STAGES = 4;
-constexpr int MAX_M = 16;  // d <= 128
+constexpr int MAX_M_RESIDENT = 16;  // d <= 128: the whole codebook matrix stays in shared memory
+constexpr int MAX_M = 256;          // d <= 2048: codebook chunk + its -|c|^2/2 slice streamed per work item
+constexpr int CNH_CHUNK_BYTES = 4 * TN * 4;                                       // 4 sub-spaces
+constexpr int STREAM_STAGE_BYTES = A_STAGE_BYTES + B_CHUNK_BYTES + CNH_CHUNK_BYTES;  // 52 KB
 
+// RESIDENT: [B: nkc x 32 KB][A ring: STAGES x 16 KB][cnh: M x 1 KB]
+// STREAM:   [ring: STAGES x (A 16 KB | B chunk 32 KB | cnh slice 4 KB)]
 struct Layout {
   uint32_t b_off, a_off, cnh_off, bar_off, misc_off, total;
+  uint32_t stage_bytes;  // distance between two A stages
 };
-__host__ __device__ inline Layout layout(int nkc, int M) {
+__host__ __device__ inline Layout layout(int nkc, int M, bool stream) {
   Layout L;
-  L.b_off = 0;
-  L.a_off = nkc * B_CHUNK_BYTES;
-  L.cnh_off = L.a_off + STAGES * A_STAGE_BYTES;
-  L.bar_off = L.cnh_off + M * TN * 4;
+  if (stream) {
+    L.b_off = A_STAGE_BYTES;                  // + s * stage_bytes
+    L.a_off = 0;                              // + s * stage_bytes
+    L.cnh_off = A_STAGE_BYTES + B_CHUNK_BYTES;  // + s * stage_bytes
+    L.stage_bytes = STREAM_STAGE_BYTES;
+    L.bar_off = STAGES * STREAM_STAGE_BYTES;
+  } else {
+    L.b_off = 0;
+    L.a_off = nkc * B_CHUNK_BYTES;
+    L.cnh_off = L.a_off + STAGES * A_STAGE_BYTES;
+    L.stage_bytes = A_STAGE_BYTES;
+    L.bar_off = L.cnh_off + M * TN * 4;
+  }
   L.misc_off = L.bar_off + (2 * STAGES + 1 + 4) * 8;
-  L.total = L.misc_off + 64;
+  L.total = L.misc_off + 64 + MAX_M;  // tmem pointer, then one "active" byte per sub-space
   return L;
+}
+
+// 1-D bulk copy global -> shared with mbarrier completion (the streamed -|c|^2/2 slice)
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
 }
 
 // physical address of the 16-byte unit `u` (0..7) of row `r` inside a [rows x 128 B] SWIZZLE_128B tile
@@ -49,7 +71,7 @@ __device__ __forceinline__ const float4* swz(const uint8_t* tile, int r, int u) 
   return reinterpret_cast<const float4*>(tile + (r >> 3) * 1024 + (r & 7) * 128 + ((u ^ (r & 7)) << 4));
 }
 
-template <bool TRAIN>
+template <bool TRAIN, bool STREAM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_b,
              uint64_t n, int M, const float* __restrict__ cnh_g, const float* __restrict__ cbmax2,
@@ -60,11 +82,10 @@ tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nkc = M / 4;
-  const Layout L = layout(nkc, M);
-  float* cnh = reinterpret_cast<float*>(smem + L.cnh_off);
+  const Layout L = layout(nkc, M, STREAM);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L.misc_off);
-  uint32_t* act_mask_smem = tmem_ptr_smem + 1;
+  uint8_t* act_s = smem + L.misc_off + 64;  // [M] 0/1 (M % 4 == 0: read as one word per chunk)
   const uint32_t sb = smem_u32(smem);
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
   auto empty_bar = [&](int s) { return smem_u32(&bars[STAGES + s]); };
@@ -75,12 +96,15 @@ tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t num_tiles = (n + TM - 1) / TM;
 
-  for (int i = threadIdx.x; i < M * TN; i += NUM_THREADS) cnh[i] = cnh_g[i];
-  if (threadIdx.x == 0) {
-    uint32_t mask = 0;
-    for (int m = 0; m < M; ++m)
-      if (!active || active[m]) mask |= 1u << m;
-    *act_mask_smem = mask;
+  if (!STREAM) {
+    float* cnh = reinterpret_cast<float*>(smem + L.cnh_off);
+    for (int i = threadIdx.x; i < M * TN; i += NUM_THREADS) cnh[i] = cnh_g[i];
+  }
+  int any_active = 0;
+  for (int m = threadIdx.x; m < M; m += NUM_THREADS) {
+    const uint8_t a = (!active || active[m]) ? 1 : 0;
+    act_s[m] = a;
+    any_active |= a;
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -99,18 +123,24 @@ tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  any_active = __syncthreads_or(any_active);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t act_mask = *act_mask_smem;
-  if (act_mask == 0) goto teardown;  // uniform
+  // bit j of chunk_mask(kc) = sub-space 4*kc + j still active
+  auto chunk_mask = [&](int kc) -> uint32_t {
+    const uint32_t w = reinterpret_cast<const uint32_t*>(act_s)[kc];
+    return (w | (w >> 7) | (w >> 14) | (w >> 21)) & 0xFu;
+  };
+  if (!any_active) goto teardown;  // uniform
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      mbar_expect_tx(b_full, (uint32_t)nkc * B_CHUNK_BYTES);
-      for (int kc = 0; kc < nkc; ++kc)
-        tma_load_2d(sb + L.b_off + kc * B_CHUNK_BYTES, &map_b, b_full, kc * KC, 0);
+      if (!STREAM) {
+        mbar_expect_tx(b_full, (uint32_t)nkc * B_CHUNK_BYTES);
+        for (int kc = 0; kc < nkc; ++kc)
+          tma_load_2d(sb + L.b_off + kc * B_CHUNK_BYTES, &map_b, b_full, kc * KC, 0);
+      }
       int s = 0;
       uint32_t ph = 0;
       // work item = (row tile, 32-float chunk = 4 sub-spaces): finer than whole tiles so that the
@@ -119,10 +149,15 @@ tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ 
         const uint64_t tile = item / nkc;
         {
           const int kc = (int)(item % nkc);
-          if (((act_mask >> (kc * 4)) & 0xF) == 0) continue;  // chunk with no active sub-space
+          if (chunk_mask(kc) == 0) continue;  // chunk with no active sub-space
           mbar_wait_relaxed(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), A_STAGE_BYTES);
-          tma_load_2d(sb + L.a_off + s * A_STAGE_BYTES, &map_r, full_bar(s), kc * KC, (int)(tile * TM));
+          mbar_expect_tx(full_bar(s), STREAM ? STREAM_STAGE_BYTES : A_STAGE_BYTES);
+          tma_load_2d(sb + L.a_off + s * L.stage_bytes, &map_r, full_bar(s), kc * KC, (int)(tile * TM));
+          if (STREAM) {
+            tma_load_2d(sb + L.b_off + s * L.stage_bytes, &map_b, full_bar(s), kc * KC, 0);
+            bulk_load_1d(sb + L.cnh_off + s * L.stage_bytes, cnh_g + (size_t)kc * 4 * TN, CNH_CHUNK_BYTES,
+                         full_bar(s));
+          }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -130,18 +165,18 @@ tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ 
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      mbar_wait(b_full, 0);
+      if (!STREAM) mbar_wait(b_full, 0);
       int s = 0;
       uint32_t ph = 0, it = 0;
       for (uint64_t item = blockIdx.x; item < num_tiles * nkc; item += gridDim.x) {
         {
           const int kc = (int)(item % nkc);
-          const uint32_t cm = (act_mask >> (kc * 4)) & 0xF;
+          const uint32_t cm = chunk_mask(kc);
           if (cm == 0) continue;
           mbar_wait_relaxed(full_bar(s), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_addr = sb + L.a_off + s * A_STAGE_BYTES;
-          const uint32_t b_addr = sb + L.b_off + kc * B_CHUNK_BYTES;
+          const uint32_t a_addr = sb + L.a_off + s * L.stage_bytes;
+          const uint32_t b_addr = sb + L.b_off + (STREAM ? s * L.stage_bytes : kc * B_CHUNK_BYTES);
           for (int j = 0; j < 4; ++j) {
             if (!((cm >> j) & 1)) continue;
             const uint32_t buf = it & 1;
@@ -160,8 +195,7 @@ tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ 
     // ===== epilogue =====
     const int q = warp & 3;
     const uint32_t group = (warp >> 2) - 1;  // 0 or 1: owns TMEM buffer `group`
-    const uint8_t* btile = smem + L.b_off;
-    mbar_wait(b_full, 0);  // the codebook tile is re-read by the exact re-rank below
+    if (!STREAM) mbar_wait(b_full, 0);  // the codebook tile is re-read by the exact re-rank below
     int s = 0;
     uint32_t ph = 0, it = 0;
     for (uint64_t item = blockIdx.x; item < num_tiles * nkc; item += gridDim.x) {
@@ -170,10 +204,12 @@ tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ 
       const uint64_t row = tile * TM + rl;
       {
         const int kc = (int)(item % nkc);
-        const uint32_t cm = (act_mask >> (kc * 4)) & 0xF;
+        const uint32_t cm = chunk_mask(kc);
         if (cm == 0) continue;
         mbar_wait(full_bar(s), ph);  // operands visible to this thread (re-read below)
-        const uint8_t* atile = smem + L.a_off + s * A_STAGE_BYTES;
+        const uint8_t* atile = smem + L.a_off + s * L.stage_bytes;
+        const uint8_t* bt = smem + L.b_off + (STREAM ? s * L.stage_bytes : kc * B_CHUNK_BYTES);
+        const float* cn4 = reinterpret_cast<const float*>(smem + L.cnh_off + (STREAM ? s * L.stage_bytes : kc * CNH_CHUNK_BYTES));
         for (int j = 0; j < 4; ++j) {
           if (!((cm >> j) & 1)) continue;
           const int m = kc * 4 + j;
@@ -182,7 +218,7 @@ tc_pq_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ 
           mbar_wait(tfull_bar(buf), (it >> 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * TN;
-          const float* cn = cnh + m * TN;
+          const float* cn = cn4 + j * TN;
           float m1 = __int_as_float(0xff800000), m2 = m1, m3 = m1;
 top3_row256(taddr, cn, m1, m2, m3);
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -209,7 +245,6 @@ top3_row256(taddr, cn, m1, m2, m3);
               const int ncand = flag == 0 ? 1 : 2;
               for (int c = 0; c < ncand; ++c) {
                 const uint32_t ci = c == 0 ? i1 : i2;
-                const uint8_t* bt = btile + kc * B_CHUNK_BYTES;
                 const float4 c0v = *swz(bt, (int)ci, j * 2), c1v = *swz(bt, (int)ci, j * 2 + 1);
                 const float cv[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
                 float sacc = 0.0f;
@@ -353,7 +388,7 @@ pq_fallback_kernel(const float* __restrict__ r, uint64_t n, int M, const float* 
 
 bool tc_pq_supported(uint64_t n, int d, int M, int ds, int Kc, int metric, const float* x) {
   if (getenv("LB2_DISABLE_TC") && *getenv("LB2_DISABLE_TC")) return false;
-  return metric == METRIC_L2 && ds == 8 && Kc == 256 && d == M * 8 && d % 32 == 0 && d <= 128 &&
+  return metric == METRIC_L2 && ds == 8 && Kc == 256 && d == M * 8 && d % 32 == 0 && M <= tcpq::MAX_M &&
          n >= 256 && n * (uint64_t)M < (1ull << 32) && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
 }
 
@@ -372,7 +407,8 @@ void tc_pq_assign(const float* r, const float* rn2, uint64_t n, int d, int M, co
                   uint8_t* valid, const uint8_t* active, TcPqWorkspace* ws) {
   using namespace tcpq;
   const int nkc = M / 4;
-  const Layout L = layout(nkc, M);
+  const bool stream = M > MAX_M_RESIDENT;
+  const Layout L = layout(nkc, M, stream);
   const size_t smem = L.total + 1024;
   if (smem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "tc_pq: shared memory");
   tc_pq_prepare(codebook, M, d, ws);  // also resets the fallback-pair counter
@@ -384,19 +420,23 @@ void tc_pq_assign(const float* r, const float* rn2, uint64_t n, int d, int M, co
   const float* cnh = ws->cnh.p;
   const float* cbmax2 = ws->cnh.p + (size_t)M * tc::TN;
   const unsigned fb_grid = (unsigned)std::min<uint64_t>(cdiv(n * M * 16, 256), (uint64_t)ctx().num_sms * 8);
+#define LB2_PQ_FILTER(TRAINV, STREAMV)                                                                      \
+  do {                                                                                                      \
+    set_smem(tc_pq_kernel<TRAINV, STREAMV>, smem);                                                          \
+    LB2_LAUNCH("tc_pq_filter", (tc_pq_kernel<TRAINV, STREAMV>), grid, tc::NUM_THREADS, smem, map_r, map_b, \
+               n, M, cnh, cbmax2, rn2, row_valid, codes, ids, dists, valid, ws->fb_pairs.p,                 \
+               ws->fb_count.p, active);                                                                     \
+  } while (0)
   if (codes) {
-    set_smem(tc_pq_kernel<false>, smem);
-    LB2_LAUNCH("tc_pq_filter", tc_pq_kernel<false>, grid, tc::NUM_THREADS, smem, map_r, map_b, n, M, cnh,
-               cbmax2, rn2, row_valid, codes, ids, dists, valid, ws->fb_pairs.p, ws->fb_count.p, active);
+    if (stream) LB2_PQ_FILTER(false, true); else LB2_PQ_FILTER(false, false);
     LB2_LAUNCH("tc_pq_fallback", pq_fallback_kernel<false>, fb_grid, 256, 0, r, n, M, codebook,
                ws->fb_pairs.p, ws->fb_count.p, row_valid, codes, ids, dists, valid);
   } else {
-    set_smem(tc_pq_kernel<true>, smem);
-    LB2_LAUNCH("tc_pq_filter", tc_pq_kernel<true>, grid, tc::NUM_THREADS, smem, map_r, map_b, n, M, cnh,
-               cbmax2, rn2, row_valid, codes, ids, dists, valid, ws->fb_pairs.p, ws->fb_count.p, active);
+    if (stream) LB2_PQ_FILTER(true, true); else LB2_PQ_FILTER(true, false);
     LB2_LAUNCH("tc_pq_fallback", pq_fallback_kernel<true>, fb_grid, 256, 0, r, n, M, codebook,
                ws->fb_pairs.p, ws->fb_count.p, row_valid, codes, ids, dists, valid);
   }
+#undef LB2_PQ_FILTER
   if (getenv("LB2_TC_STATS") && *getenv("LB2_TC_STATS")) {
     uint32_t c = 0;
     d2h(&c, ws->fb_count.p, 1);
@@ -415,7 +455,7 @@ void pq_encode_dev(const float* x, uint64_t n, int d, int M, int ds, const float
     return;
   }
   TcPqWorkspace ws;
-  const uint64_t chunk = 1ull << 21;  // 2M rows: 1 GB of residuals at d = 128
+  const uint64_t chunk = std::max<uint64_t>(1ull << 16, (1ull << 28) / (uint64_t)d);  // <= 1 GB of residuals
   DevBuf<float> r, rn2(std::min(n, chunk) * M);
   if (cent) r.alloc(std::min(n, chunk) * d);
   for (uint64_t r0 = 0; r0 < n; r0 += chunk) {

@@ -383,7 +383,8 @@ def test_tc_filter_sift_shaped_and_training():
     assert k1.iters == it_o and np.array_equal(k1.centroids, co) and k1.loss == loss_o
 
 
-@pytest.mark.parametrize("n,d,M", [(1500, 128, 16), (4097, 64, 8), (300, 32, 4), (20000, 128, 16)])
+@pytest.mark.parametrize("n,d,M", [(1500, 128, 16), (4097, 64, 8), (300, 32, 4), (20000, 128, 16),
+                                   (3000, 768, 96), (1000, 256, 32), (700, 1536, 192), (40000, 160, 20)])
 def test_tc_pq_encode_equals_exact_path(n, d, M):
     rng = np.random.default_rng(n + d)
     cb = (rng.standard_normal((M, 256, 8)) * 2).astype(np.float32)
@@ -413,6 +414,19 @@ def test_tc_pq_fused_residual_and_training_equal_exact_path():
     (p1, p2) = _both_paths(lambda: lb.PQBuildParams(M, 8, max_iters=10, codebook=init).build(res))
     assert np.array_equal(p1.train_iters, p2.train_iters) and np.array_equal(p1.codebook, p2.codebook)
     cbo, iters_o = ob.pq_train(res, M, max_iters=10, init_codebook=init, nthreads=NT)
+    assert np.array_equal(p1.codebook, cbo) and np.array_equal(p1.train_iters.astype(np.int32), iters_o)
+
+
+def test_tc_pq_streamed_codebook_training_equals_exact_path():
+    # M > 16: codebook chunks are streamed; sub-spaces converge at different iterations (active flags)
+    rng = np.random.default_rng(321)
+    n, d, M = 20000, 384, 48
+    res = (rng.standard_normal((n, d)) * np.linspace(0.5, 4.0, d)).astype(np.float32)
+    res[:, :8] = np.round(res[:, :8])          # a coarse sub-space: converges early, many exact ties
+    init = np.stack([res[rng.choice(n, 256, replace=False)][:, m * 8:(m + 1) * 8] for m in range(M)])
+    (p1, p2) = _both_paths(lambda: lb.PQBuildParams(M, 8, max_iters=8, codebook=init).build(res))
+    assert np.array_equal(p1.train_iters, p2.train_iters) and np.array_equal(p1.codebook, p2.codebook)
+    cbo, iters_o = ob.pq_train(res, M, max_iters=8, init_codebook=init, nthreads=NT)
     assert np.array_equal(p1.codebook, cbo) and np.array_equal(p1.train_iters.astype(np.int32), iters_o)
 
 
