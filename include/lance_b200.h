@@ -194,6 +194,31 @@ lb2_status lb2_index_search_refine(lb2_index* index, const void* vectors, uint64
                                    const void* queries, uint64_t nq, uint32_t k, uint32_t nprobes,
                                    uint32_t refine_factor, uint64_t* row_ids_out, float* dists_out,
                                    uint32_t* counts_out);
+/* Extended search: prefilter and refine in one call.
+ * Prefilter = the reference's PreFilter / RowIdMask (lance-index/src/prefilter.rs:27-51): when the
+ * mask is not empty FlatIndex::search visits the partition row by row and skips rows for which
+ * RowIdMask::selected(row_id) is false BEFORE they can enter the heap (flat/index.rs:129-165).
+ * Here the mask is a bitmap over STORAGE positions (the order of lb2_index_export's row_ids, i.e.
+ * partition-local offset + part_offsets[p]); bit i (word i/64, bit i%64) set = row may be returned.
+ * lb2_index_row_mask builds it on the device from the RowIdMask's allow / block lists.
+ * allow_bitmap NULL = the fast unfiltered path. Host or device pointer, (num_rows+63)/64 words. */
+typedef struct {
+  uint32_t k;
+  uint32_t nprobes;
+  uint32_t refine_factor;       /* 0 = no refine step */
+  const void* refine_vectors;   /* raw column, see lb2_index_search_refine; required when refine_factor > 0 */
+  uint64_t num_vectors;
+  const uint64_t* allow_bitmap; /* nullable */
+} lb2_search_params;
+lb2_status lb2_index_search_ex(lb2_index* index, const void* queries, uint64_t nq,
+                               const lb2_search_params* params, uint64_t* row_ids_out, float* dists_out,
+                               uint32_t* counts_out);
+/* bitmap_out[(num_rows+63)/64]: bit i = RowIdMask::selected(row id stored at position i)
+ * (lance-core/src/utils/mask.rs:84-93: in the allow list if there is one, and not in the block
+ * list if there is one). Lists are sorted ascending (RoaringTreemap order); has_* = list present. */
+lb2_status lb2_index_row_mask(const lb2_index* index, const uint64_t* allow_ids, uint64_t n_allow,
+                              int has_allow, const uint64_t* block_ids, uint64_t n_block, int has_block,
+                              uint64_t* bitmap_out);
 lb2_status lb2_index_info(const lb2_index* index, uint32_t* k, uint32_t* d, uint32_t* num_sub_vectors,
                           uint32_t* num_bits, uint64_t* num_rows);
 /* export for the host to write index files: any pointer may be NULL.

@@ -484,6 +484,46 @@ class IvfPqIndex:
                                             ip, dp, None))
         return ids, dists
 
+    def row_mask(self, allow_row_ids=None, block_row_ids=None):
+        """RowIdMask (lance-core/src/utils/mask.rs:84-93) -> bitmap over storage positions
+        (uint64 words), built on the device by lb2_index_row_mask."""
+        from ._lib import lib as _l
+        n = self.info()["num_rows"]
+        bm = np.zeros((n + 63) // 64, np.uint64)
+        a = None if allow_row_ids is None else np.ascontiguousarray(np.sort(np.asarray(allow_row_ids, dtype=np.uint64)))
+        b = None if block_row_ids is None else np.ascontiguousarray(np.sort(np.asarray(block_row_ids, dtype=np.uint64)))
+        check(_l().lb2_index_row_mask(self._h,
+                                      C.c_void_p(a.ctypes.data) if a is not None and a.size else None,
+                                      C.c_uint64(0 if a is None else a.size), C.c_int(a is not None),
+                                      C.c_void_p(b.ctypes.data) if b is not None and b.size else None,
+                                      C.c_uint64(0 if b is None else b.size), C.c_int(b is not None),
+                                      C.c_void_p(bm.ctypes.data)))
+        return bm
+
+    def search_ex(self, queries, k=10, nprobes=1, allow_bitmap=None, refine_factor=0, vectors=None, out=None):
+        """lb2_index_search_ex: prefilter (bitmap from row_mask) and/or refine in one call."""
+        from ._lib import SearchParams
+        dt = getattr(self, "_dt", F32)
+        npdt = {F32: np.float32, F16: np.float16, U8: np.uint8, BF16: np.uint16}[dt]
+        if not isinstance(queries, (DeviceArray, PinnedArray)):
+            queries = np.ascontiguousarray(queries, dtype=npdt)
+        if vectors is not None and not isinstance(vectors, (DeviceArray, PinnedArray)):
+            vectors = np.ascontiguousarray(vectors, dtype=npdt)
+        nq = queries.shape[0]
+        if out is None:
+            ids, dists = np.empty((nq, k), np.uint64), np.empty((nq, k), np.float32)
+        else:
+            ids, dists = out
+        qp, _k1 = as_ptr(queries)
+        vp, _k0 = as_ptr(vectors)
+        bp, _k4 = as_ptr(None if allow_bitmap is None else (allow_bitmap if isinstance(allow_bitmap, (DeviceArray, PinnedArray)) else np.ascontiguousarray(allow_bitmap, dtype=np.uint64)))
+        ip, _k2 = as_ptr(ids)
+        dp, _k3 = as_ptr(dists)
+        sp = SearchParams(k, nprobes, refine_factor, vp.value if vp is not None else None,
+                          0 if vectors is None else vectors.shape[0], bp.value if bp is not None else None)
+        check(lib().lb2_index_search_ex(self._h, qp, C.c_uint64(nq), C.byref(sp), ip, dp, None))
+        return ids, dists
+
     def close(self):
         if self._h:
             lib().lb2_index_destroy(self._h)

@@ -753,11 +753,15 @@ lb2_status lb2_index_load(lb2_index* index, const uint32_t* part_ids, const uint
   LB2_API_END
 }
 
-lb2_status lb2_index_search(lb2_index* index, const void* queries, uint64_t nq, uint32_t k,
-                            uint32_t nprobes, uint64_t* row_ids_out, float* dists_out,
-                            uint32_t* counts_out) {
-  LB2_API_BEGIN
+// one implementation behind lb2_index_search / _search_refine / _search_ex
+static void index_search_impl(lb2_index* index, const void* queries, uint64_t nq, uint32_t k, uint32_t nprobes,
+                              uint32_t refine_factor, const void* vectors, uint64_t num_vectors,
+                              const uint64_t* allow_bitmap, uint64_t* row_ids_out, float* dists_out,
+                              uint32_t* counts_out) {
   LB2_REQUIRE(index && k > 0 && nprobes > 0, "bad argument");
+  const bool refine = refine_factor > 0 && vectors != nullptr;
+  const uint64_t kc = refine ? (uint64_t)k * refine_factor : k;
+  if (kc > 1024) fail(LB2_UNSUPPORTED, "k * refine_factor = %llu > 1024 is not implemented", (unsigned long long)kc);
   const int d = index->d;
   VecIn q(queries, (size_t)nq * d, index->dtype);
   const float* qp = q.get();
@@ -767,22 +771,47 @@ lb2_status lb2_index_search(lb2_index* index, const void* queries, uint64_t nq, 
     if (nq) LB2_LAUNCH("normalize", normalize_kernel, cdiv(nq, 128), 128, 0, qp, nq, d, qn.p);
     qp = qn.p;
   }
+  InArg<uint64_t> allow(allow_bitmap, allow_bitmap ? (size_t)((index->n + 63) / 64) : 0);
   OutArg<uint64_t> oi(row_ids_out, (size_t)nq * k);
   OutArg<float> od(dists_out, (size_t)nq * k);
   OutArg<uint32_t> oc(counts_out, nq);
+  DevBuf<uint64_t> cid;
+  DevBuf<float> cdist;
+  DevBuf<uint32_t> ccnt;
+  if (refine) {
+    cid.alloc((size_t)nq * kc);
+    cdist.alloc((size_t)nq * kc);
+    ccnt.alloc(nq);
+  }
+  uint64_t* si = refine ? cid.p : oi.get();
+  float* sd = refine ? cdist.p : od.get();
+  uint32_t* sc = refine ? ccnt.p : oc.get();
   TagScope tg("search");
-  if (index->kind == 1) {
-    ivfflat_search_f32(index->centroids.p, index->K, d, index->metric, index->part_offsets.p,
-                       index->vectors.p, index->row_ids.p, qp, nq, k, nprobes, oi.get(), od.get(), oc.get());
+  if (index->kind == 1)
+    ivfflat_search_f32(index->centroids.p, index->K, d, index->metric, index->part_offsets.p, index->vectors.p,
+                       index->row_ids.p, qp, nq, (int)kc, nprobes, si, sd, sc, allow_bitmap ? allow.get() : nullptr);
+  else
+    ivfpq_search_f32(index->centroids.p, index->K, d, index->metric, index->codebook.p, index->M, index->nbits,
+                     index->part_offsets.p, index->codes.p, index->row_ids.p, qp, nq, (int)kc, nprobes, si, sd,
+                     sc, allow_bitmap ? allow.get() : nullptr);
+  if (refine) {
+    // exact re-rank with the true metric on the ORIGINAL (un-normalised) query, as flat_knn does
+    VecIn v(vectors, (size_t)num_vectors * d, index->dtype);
+    refine_f32(q.get(), nq, d, index->metric, v.get(), num_vectors, cid.p, ccnt.p, (int)kc, (int)k, oi.get(),
+               od.get(), oc.get());
     oi.commit(); od.commit(); oc.commit();
     sync_stream();
-    return LB2_OK;
+    return;
   }
-  ivfpq_search_f32(index->centroids.p, index->K, d, index->metric, index->codebook.p, index->M,
-                   index->nbits, index->part_offsets.p, index->codes.p, index->row_ids.p, qp, nq, k,
-                   nprobes, oi.get(), od.get(), oc.get());
   oi.commit(); od.commit(); oc.commit();
   sync_stream();
+}
+
+lb2_status lb2_index_search(lb2_index* index, const void* queries, uint64_t nq, uint32_t k,
+                            uint32_t nprobes, uint64_t* row_ids_out, float* dists_out,
+                            uint32_t* counts_out) {
+  LB2_API_BEGIN
+  index_search_impl(index, queries, nq, k, nprobes, 0, nullptr, 0, nullptr, row_ids_out, dists_out, counts_out);
   LB2_API_END
 }
 
@@ -791,37 +820,34 @@ lb2_status lb2_index_search_refine(lb2_index* index, const void* vectors, uint64
                                    uint32_t refine_factor, uint64_t* row_ids_out, float* dists_out,
                                    uint32_t* counts_out) {
   LB2_API_BEGIN
-  LB2_REQUIRE(index && vectors && k > 0 && nprobes > 0 && refine_factor > 0, "bad argument");
-  const uint64_t kc = (uint64_t)k * refine_factor;
-  if (kc > 1024) fail(LB2_UNSUPPORTED, "k * refine_factor = %llu > 1024 is not implemented", (unsigned long long)kc);
-  const int d = index->d;
-  VecIn q(queries, (size_t)nq * d, index->dtype);
-  VecIn v(vectors, (size_t)num_vectors * d, index->dtype);
-  const float* qp = q.get();
-  DevBuf<float> qn;
-  if (index->metric == METRIC_COSINE) {
-    qn.alloc((size_t)nq * d);
-    if (nq) LB2_LAUNCH("normalize", normalize_kernel, cdiv(nq, 128), 128, 0, qp, nq, d, qn.p);
-    qp = qn.p;
-  }
-  DevBuf<uint64_t> cid((size_t)nq * kc);
-  DevBuf<float> cdist((size_t)nq * kc);
-  DevBuf<uint32_t> ccnt(nq);
-  OutArg<uint64_t> oi(row_ids_out, (size_t)nq * k);
-  OutArg<float> od(dists_out, (size_t)nq * k);
-  OutArg<uint32_t> oc(counts_out, nq);
-  TagScope tg("search");
-  if (index->kind == 1)
-    ivfflat_search_f32(index->centroids.p, index->K, d, index->metric, index->part_offsets.p,
-                       index->vectors.p, index->row_ids.p, qp, nq, (int)kc, nprobes, cid.p, cdist.p, ccnt.p);
-  else
-    ivfpq_search_f32(index->centroids.p, index->K, d, index->metric, index->codebook.p, index->M,
-                     index->nbits, index->part_offsets.p, index->codes.p, index->row_ids.p, qp, nq, (int)kc,
-                     nprobes, cid.p, cdist.p, ccnt.p);
-  // exact re-rank with the true metric on the ORIGINAL (un-normalised) query, as flat_knn does
-  refine_f32(q.get(), nq, d, index->metric, v.get(), num_vectors, cid.p, ccnt.p, (int)kc, (int)k, oi.get(),
-             od.get(), oc.get());
-  oi.commit(); od.commit(); oc.commit();
+  LB2_REQUIRE(vectors && refine_factor > 0, "bad argument");
+  index_search_impl(index, queries, nq, k, nprobes, refine_factor, vectors, num_vectors, nullptr, row_ids_out,
+                    dists_out, counts_out);
+  LB2_API_END
+}
+
+lb2_status lb2_index_search_ex(lb2_index* index, const void* queries, uint64_t nq,
+                               const lb2_search_params* sp, uint64_t* row_ids_out, float* dists_out,
+                               uint32_t* counts_out) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(sp, "null search params");
+  LB2_REQUIRE(sp->refine_factor == 0 || sp->refine_vectors, "refine_factor > 0 needs refine_vectors");
+  index_search_impl(index, queries, nq, sp->k, sp->nprobes, sp->refine_factor, sp->refine_vectors,
+                    sp->num_vectors, sp->allow_bitmap, row_ids_out, dists_out, counts_out);
+  LB2_API_END
+}
+
+lb2_status lb2_index_row_mask(const lb2_index* index, const uint64_t* allow_ids, uint64_t n_allow,
+                              int has_allow, const uint64_t* block_ids, uint64_t n_block, int has_block,
+                              uint64_t* bitmap_out) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(index && bitmap_out, "bad argument");
+  LB2_REQUIRE((!has_allow || n_allow == 0 || allow_ids) && (!has_block || n_block == 0 || block_ids), "null id list");
+  InArg<uint64_t> a(allow_ids, has_allow ? (size_t)n_allow : 0), b(block_ids, has_block ? (size_t)n_block : 0);
+  OutArg<uint64_t> bm(bitmap_out, (size_t)((index->n + 63) / 64));
+  row_mask_f32(index->row_ids.p, index->n, a.get(), n_allow, has_allow != 0, b.get(), n_block, has_block != 0,
+               bm.get());
+  bm.commit();
   sync_stream();
   LB2_API_END
 }

@@ -18,6 +18,15 @@
 
 namespace lb2 {
 
+// prefilter (PreFilter::mask, lance-index/src/prefilter.rs:27-51; FlatIndex::search :129-165): one bit
+// per STORAGE position (partition-sorted order); a cleared bit removes the row from the scan.  Filtered
+// rows get the maximal key, so they can only surface when fewer than k allowed rows exist, and the
+// output stage drops them by re-testing the bit.
+__device__ __forceinline__ bool row_allowed(const uint64_t* __restrict__ allow, uint64_t pos) {
+  return allow == nullptr || ((allow[pos >> 6] >> (pos & 63)) & 1ull) != 0;
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // block-level helpers
 // ------------------------------------------------------------------------------------------------
@@ -165,125 +174,11 @@ __device__ __forceinline__ void build_lut_smem(float* lut, const float* qr, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// the fused (residual query -> LUT -> code scan -> top-k) kernel
-//   distances of a chunk of <= SCAN_CHUNK rows go to shared memory; the k smallest (distance,
-//   position) pairs are then extracted by k rounds of "smallest key strictly greater than the
-//   previous winner" (no per-thread lists, no local memory).  Larger partitions are processed
-//   chunk by chunk, the previous winners joining the next chunk's candidate pool.
+// the fused (residual query -> LUT -> code scan -> top-k) kernels: one CTA per (query, probed
+// partition).  Partitions are processed in chunks of <= SCAN_CHUNK rows, the winners of a chunk
+// joining the next chunk's candidate pool.
 // ------------------------------------------------------------------------------------------------
 constexpr int SCAN_CHUNK = 4096;
-
-template <int METRIC>
-__global__ void __launch_bounds__(256)
-ivfpq_scan_rounds_kernel(const float* __restrict__ queries, int d, const float* __restrict__ centroids,
-                  const float* __restrict__ codebook, int M, int ds,
-                  const uint32_t* __restrict__ probe_ids, int np,
-                  const uint64_t* __restrict__ part_offsets, const uint8_t* __restrict__ codes,
-                  const uint64_t* __restrict__ row_ids, int k, float* __restrict__ cand_d,
-                  uint64_t* __restrict__ cand_id, uint32_t* __restrict__ cand_cnt) {
-  extern __shared__ float smem[];
-  float* lut = smem;                         // [M*256]
-  float* qr = lut + M * 256;                 // [d]
-  float* cd = qr + d;                        // [SCAN_CHUNK + k] candidate distances
-  uint32_t* cp = reinterpret_cast<uint32_t*>(cd + SCAN_CHUNK + k);  // [k] positions of carried winners
-  float* wd = reinterpret_cast<float*>(cp + k);                     // [k] new winners
-  uint32_t* wp = reinterpret_cast<uint32_t*>(wd + k);               // [k]
-  __shared__ int32_t s_key[8];
-  __shared__ uint64_t s_tie[8];
-  __shared__ int s_tid[9];
-  __shared__ int32_t prev_key;
-  __shared__ uint32_t prev_pos;
-  const int tid = threadIdx.x;
-  const int pi = blockIdx.x;
-  const size_t qi = blockIdx.y;
-  const uint32_t p = probe_ids[qi * np + pi];
-  const uint64_t off = part_offsets[p];
-  const uint32_t n_p = (uint32_t)(part_offsets[p + 1] - off);
-  const size_t slot = qi * np + pi;
-  if (n_p == 0) {
-    if (tid == 0) cand_cnt[slot] = 0;
-    return;
-  }
-  const float* q = queries + qi * d;
-  for (int t = tid; t < d; t += 256)
-    qr[t] = METRIC == METRIC_DOT ? q[t] : __fsub_rn(q[t], centroids[(size_t)p * d + t]);  // v2.rs:316-332
-  __syncthreads();
-  build_lut_smem<METRIC>(lut, qr, codebook, M, ds, tid);
-  __syncthreads();
-
-  const uint8_t* pc = codes + off * M;
-  const float dot_fix = (float)M - 1.0f;
-  uint32_t nw = 0;  // winners carried from the previous chunks (uniform)
-  for (uint32_t c0 = 0; c0 < n_p; c0 += SCAN_CHUNK) {
-    const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
-    // ---- ADC distances of the chunk: dist = ((0 + LUT[0][c0]) + LUT[1][c1]) + ... (pq/distance.rs:125-141)
-    if ((M & 15) == 0) {
-      for (uint32_t j = tid; j < clen; j += 256) {
-        const uint4* rp = reinterpret_cast<const uint4*>(pc + (size_t)(c0 + j) * M);
-        float dist = 0.0f;
-        for (int c16 = 0; c16 < M / 16; ++c16) {
-          const uint4 v = __ldg(rp + c16);
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-          const float* l0 = lut + c16 * 16 * 256;
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-              dist = f_add(dist, l0[(a * 4 + b) * 256 + ((w[a] >> (8 * b)) & 0xff)]);
-        }
-        if (METRIC == METRIC_DOT) dist = __fsub_rn(dist, dot_fix);  // pq/storage.rs:957-958
-        cd[j] = dist;
-      }
-    } else {
-      for (uint32_t j = tid; j < clen; j += 256) {
-        const uint8_t* rp = pc + (size_t)(c0 + j) * M;
-        float dist = 0.0f;
-        for (int m = 0; m < M; ++m) dist = f_add(dist, lut[m * 256 + rp[m]]);
-        if (METRIC == METRIC_DOT) dist = __fsub_rn(dist, dot_fix);
-        cd[j] = dist;
-      }
-    }
-    __syncthreads();
-    // ---- k rounds over the pool = chunk rows (positions c0 + j) + carried winners (positions cp[])
-    const uint32_t pool = clen + nw;
-    const uint32_t rounds = pool < (uint32_t)k ? pool : (uint32_t)k;
-    bool first = true;
-    for (uint32_t r = 0; r < rounds; ++r) {
-      int32_t bk = 0;
-      uint32_t bpos = 0, bslot = 0;
-      bool has = false;
-      const int32_t pk = first ? 0 : prev_key;
-      const uint32_t pp = first ? 0 : prev_pos;
-      for (uint32_t i = tid; i < pool; i += 256) {
-        const int32_t key = total_order_key(cd[i < clen ? i : SCAN_CHUNK + (i - clen)]);
-        const uint32_t pos = i < clen ? c0 + i : cp[i - clen];
-        if (!first && !ki_less(pk, pp, key, pos)) continue;  // already emitted
-        if (!has || ki_less(key, pos, bk, bpos)) { bk = key; bpos = pos; bslot = i; has = true; }
-      }
-      const int w = block_argmin<256>(has, bk, bpos, s_key, s_tie, s_tid);
-      if (tid == w) {
-        prev_key = bk;
-        prev_pos = bpos;
-        wd[r] = cd[bslot < clen ? bslot : SCAN_CHUNK + (bslot - clen)];
-        wp[r] = bpos;
-      }
-      __syncthreads();
-      first = false;
-    }
-    // the winners become the carried candidates of the next chunk
-    for (uint32_t i = tid; i < rounds; i += 256) {
-      cd[SCAN_CHUNK + i] = wd[i];
-      cp[i] = wp[i];
-    }
-    nw = rounds;
-    __syncthreads();
-  }
-  for (uint32_t i = tid; i < nw; i += 256) {
-    cand_d[slot * k + i] = cd[SCAN_CHUNK + i];
-    cand_id[slot * k + i] = row_ids[off + cp[i]];
-  }
-  if (tid == 0) cand_cnt[slot] = nw;
-}
 
 __device__ __forceinline__ float key_to_float(int32_t key) {
   return __int_as_float(key ^ (int32_t)((uint32_t)(key >> 31) >> 1));
@@ -301,7 +196,8 @@ ivfpq_scan_radix_kernel(const float* __restrict__ queries, int d, const float* _
                         const uint32_t* __restrict__ probe_ids, int np,
                         const uint64_t* __restrict__ part_offsets, const uint8_t* __restrict__ codes,
                         const uint64_t* __restrict__ row_ids, int k, float* __restrict__ cand_d,
-                        uint64_t* __restrict__ cand_id, uint32_t* __restrict__ cand_cnt) {
+                        uint64_t* __restrict__ cand_id, uint32_t* __restrict__ cand_cnt,
+                        const uint64_t* __restrict__ allow) {
   extern __shared__ float smem[];
   float* lut = smem;                                                   // [M*256]
   float* qr = lut + M * 256;                                           // [d]
@@ -338,6 +234,10 @@ ivfpq_scan_radix_kernel(const float* __restrict__ queries, int d, const float* _
   for (uint32_t c0 = 0; c0 < n_p; c0 += SCAN_CHUNK) {
     const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
     for (uint32_t j = tid; j < clen; j += 256) {
+      if (!row_allowed(allow, off + c0 + j)) {
+        ukey[j] = 0xffffffffu;
+        continue;
+      }
       float dist = 0.0f;
       if ((M & 15) == 0) {
         const uint4* rp = reinterpret_cast<const uint4*>(pc + (size_t)(c0 + j) * M);
@@ -438,6 +338,19 @@ ivfpq_scan_radix_kernel(const float* __restrict__ queries, int d, const float* _
     nw = got;
     __syncthreads();
   }
+  if (allow) {  // drop filtered rows (order inside a candidate list is irrelevant: the merge sorts)
+    if (tid == 0) s_out = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < nw; i += 256)
+      if (row_allowed(allow, off + cpos[i])) {
+        const uint32_t at = atomicAdd(&s_out, 1u);
+        cand_d[slot * k + at] = key_to_float((int32_t)(ukey[SCAN_CHUNK + i] ^ 0x80000000u));
+        cand_id[slot * k + at] = row_ids[off + cpos[i]];
+      }
+    __syncthreads();
+    if (tid == 0) cand_cnt[slot] = s_out;
+    return;
+  }
   for (uint32_t i = tid; i < nw; i += 256) {
     cand_d[slot * k + i] = key_to_float((int32_t)(ukey[SCAN_CHUNK + i] ^ 0x80000000u));
     cand_id[slot * k + i] = row_ids[off + cpos[i]];
@@ -527,7 +440,8 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
                   const uint32_t* __restrict__ probe_ids, int np,
                   const uint64_t* __restrict__ part_offsets, const uint8_t* __restrict__ codes,
                   const uint64_t* __restrict__ row_ids, int k, float* __restrict__ cand_d,
-                  uint64_t* __restrict__ cand_id, uint32_t* __restrict__ cand_cnt) {
+                  uint64_t* __restrict__ cand_id, uint32_t* __restrict__ cand_cnt,
+                  const uint64_t* __restrict__ allow) {
   constexpr int RPT = SCAN_CHUNK / 256;  // rows per thread and chunk (16)
   extern __shared__ float smem[];
   float* lut = smem;          // [M*256]
@@ -572,7 +486,7 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
     for (int u = 0; u < RPT; ++u) {
       const uint32_t j = wbase + lane + 32 * u;
       key[u] = 0x7fffffff;
-      if (j < clen) {
+      if (j < clen && row_allowed(allow, off + c0 + j)) {
         float dist = 0.0f;
         if ((M & 15) == 0) {
           const uint4* rp = reinterpret_cast<const uint4*>(pc + (size_t)(c0 + j) * M);
@@ -679,6 +593,19 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
     __syncthreads();
   }
   const uint32_t nw = s_nw;
+  if (allow) {  // drop filtered rows that surfaced because fewer than k allowed rows exist (nw <= 16)
+    if (tid == 0) {
+      uint32_t c = 0;
+      for (uint32_t i = 0; i < nw; ++i)
+        if (row_allowed(allow, off + car_pos[i])) {
+          cand_d[slot * k + c] = key_to_float(car_key[i]);
+          cand_id[slot * k + c] = row_ids[off + car_pos[i]];
+          ++c;
+        }
+      cand_cnt[slot] = c;
+    }
+    return;
+  }
   for (uint32_t i = tid; i < nw; i += 256) {
     cand_d[slot * k + i] = key_to_float(car_key[i]);
     cand_id[slot * k + i] = row_ids[off + car_pos[i]];
@@ -728,8 +655,9 @@ ivfflat_scan_kernel(const float* __restrict__ queries, int d, const uint32_t* __
                     int np, const uint64_t* __restrict__ part_offsets,
                     const float* __restrict__ vectors, const uint64_t* __restrict__ row_ids, int k,
                     float* __restrict__ cand_d, uint64_t* __restrict__ cand_id,
-                    uint32_t* __restrict__ cand_cnt) {
+                    uint32_t* __restrict__ cand_cnt, const uint64_t* __restrict__ allow) {
   extern __shared__ float smem[];
+  __shared__ uint32_t s_outc;
   float* qs = smem;                          // [d]
   float* cd = qs + d;                        // [SCAN_CHUNK + k]
   uint32_t* cp = reinterpret_cast<uint32_t*>(cd + SCAN_CHUNK + k);
@@ -768,6 +696,10 @@ ivfflat_scan_kernel(const float* __restrict__ queries, int d, const uint32_t* __
   for (uint32_t c0 = 0; c0 < n_p; c0 += SCAN_CHUNK) {
     const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
     for (uint32_t j = tid >> 4; j < clen; j += 16) {  // 16 rows per pass, 16 lanes each
+      if (!row_allowed(allow, off + c0 + j)) {  // uniform per half-warp
+        if (l == 0) cd[j] = __int_as_float(0x7fffffff);  // maximal key of the total order
+        continue;
+      }
       const float dist = flat_row_distance<METRIC>(qs, vectors + (off + c0 + j) * (uint64_t)d, d, l, hmask, qn);
       if (l == 0) cd[j] = dist;
     }
@@ -803,6 +735,19 @@ ivfflat_scan_kernel(const float* __restrict__ queries, int d, const uint32_t* __
     }
     nw = rounds;
     __syncthreads();
+  }
+  if (allow) {
+    if (tid == 0) s_outc = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < nw; i += 256)
+      if (row_allowed(allow, off + cp[i])) {
+        const uint32_t at = atomicAdd(&s_outc, 1u);
+        cand_d[slot * k + at] = cd[SCAN_CHUNK + i];
+        cand_id[slot * k + at] = row_ids[off + cp[i]];
+      }
+    __syncthreads();
+    if (tid == 0) cand_cnt[slot] = s_outc;
+    return;
   }
   for (uint32_t i = tid; i < nw; i += 256) {
     cand_d[slot * k + i] = cd[SCAN_CHUNK + i];
@@ -928,23 +873,23 @@ static void scan_launch(int kmax, dim3 grid, size_t smem, const float* queries, 
                         const float* centroids, const float* codebook, int M, int ds,
                         const uint32_t* probe_ids, int np, const uint64_t* part_offsets,
                         const uint8_t* codes, const uint64_t* row_ids, int k, float* cand_d,
-                        uint64_t* cand_id, uint32_t* cand_cnt) {
+                        uint64_t* cand_id, uint32_t* cand_cnt, const uint64_t* allow) {
   if (k <= SCAN_KFAST) {
     const size_t smem_fast = sizeof(float) * ((size_t)M * 256 + d);
     set_smem(ivfpq_scan_kernel<METRIC>, smem_fast);
     LB2_LAUNCH("pq_scan", (ivfpq_scan_kernel<METRIC>), grid, 256, smem_fast, queries, d, centroids,
-               codebook, M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt);
+               codebook, M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt, allow);
     return;
   }
   set_smem(ivfpq_scan_radix_kernel<METRIC>, smem);
   LB2_LAUNCH("pq_scan", (ivfpq_scan_radix_kernel<METRIC>), grid, 256, smem, queries, d, centroids, codebook,
-             M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt);
+             M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt, allow);
 }
 
 void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const float* codebook, int M,
                       int nbits, const uint64_t* part_offsets, const uint8_t* codes,
                       const uint64_t* row_ids, const float* queries, uint64_t nq, int k, int nprobes,
-                      uint64_t* out_ids, float* out_dists, uint32_t* out_counts) {
+                      uint64_t* out_ids, float* out_dists, uint32_t* out_counts, const uint64_t* allow) {
   if (nq == 0 || k == 0) return;
   if (nbits != 8) fail(LB2_UNSUPPORTED, "only 8-bit PQ is implemented on the device");
   if (k > 1024) fail(LB2_UNSUPPORTED, "k (incl. refine factor) > 1024 is not implemented");
@@ -966,26 +911,56 @@ void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const fl
       if (cmetric == METRIC_DOT)
         scan_launch<METRIC_DOT>(k, g, smem, queries + q0 * d, d, centroids, codebook, M, ds,
                                 pids.p + q0 * np, np, part_offsets, codes, row_ids, k,
-                                cand_d.p + q0 * np * k, cand_id.p + q0 * np * k, cand_cnt.p + q0 * np);
+                                cand_d.p + q0 * np * k, cand_id.p + q0 * np * k, cand_cnt.p + q0 * np, allow);
       else
         scan_launch<METRIC_L2>(k, g, smem, queries + q0 * d, d, centroids, codebook, M, ds,
                                pids.p + q0 * np, np, part_offsets, codes, row_ids, k,
-                               cand_d.p + q0 * np * k, cand_id.p + q0 * np * k, cand_cnt.p + q0 * np);
+                               cand_d.p + q0 * np * k, cand_id.p + q0 * np * k, cand_cnt.p + q0 * np, allow);
     }
   } else if (cmetric == METRIC_DOT) {
     scan_launch<METRIC_DOT>(k, grid, smem, queries, d, centroids, codebook, M, ds, pids.p, np,
-                            part_offsets, codes, row_ids, k, cand_d.p, cand_id.p, cand_cnt.p);
+                            part_offsets, codes, row_ids, k, cand_d.p, cand_id.p, cand_cnt.p, allow);
   } else {
     scan_launch<METRIC_L2>(k, grid, smem, queries, d, centroids, codebook, M, ds, pids.p, np,
-                           part_offsets, codes, row_ids, k, cand_d.p, cand_id.p, cand_cnt.p);
+                           part_offsets, codes, row_ids, k, cand_d.p, cand_id.p, cand_cnt.p, allow);
   }
   LB2_LAUNCH("merge_topk", merge_kernel, (unsigned)nq, 128, 0, cand_d.p, cand_id.p, cand_cnt.p, np,
              k, out_ids, out_dists, out_counts);
 }
 
+__device__ __forceinline__ bool sorted_contains(const uint64_t* __restrict__ a, uint64_t n, uint64_t v) {
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo < n && a[lo] == v;
+}
+__global__ void row_mask_kernel(const uint64_t* __restrict__ row_ids, uint64_t n,
+                                const uint64_t* __restrict__ allow, uint64_t n_allow, int has_allow,
+                                const uint64_t* __restrict__ block, uint64_t n_block, int has_block,
+                                uint32_t* __restrict__ bitmap32) {
+  const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // n padded to 64 by the grid
+  bool sel = false;
+  if (pos < n) {
+    const uint64_t id = row_ids[pos];
+    sel = (!has_allow || sorted_contains(allow, n_allow, id)) && !(has_block && sorted_contains(block, n_block, id));
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, sel);
+  if ((threadIdx.x & 31) == 0) bitmap32[pos >> 5] = bal;
+}
+void row_mask_f32(const uint64_t* row_ids, uint64_t n, const uint64_t* allow, uint64_t n_allow, bool has_allow,
+                  const uint64_t* block, uint64_t n_block, bool has_block, uint64_t* bitmap) {
+  const uint64_t padded = (n + 63) / 64 * 64;
+  if (padded == 0) return;
+  LB2_LAUNCH("row_mask", row_mask_kernel, cdiv(padded, 256), 256, 0, row_ids, n, allow, n_allow,
+             has_allow ? 1 : 0, block, n_block, has_block ? 1 : 0, reinterpret_cast<uint32_t*>(bitmap));
+}
+
 void ivfflat_search_f32(const float* centroids, int K, int d, int metric, const uint64_t* part_offsets,
                         const float* vectors, const uint64_t* row_ids, const float* queries, uint64_t nq,
-                        int k, int nprobes, uint64_t* out_ids, float* out_dists, uint32_t* out_counts) {
+                        int k, int nprobes, uint64_t* out_ids, float* out_dists, uint32_t* out_counts,
+                        const uint64_t* allow) {
   if (nq == 0 || k == 0) return;
   if (k > 1024) fail(LB2_UNSUPPORTED, "k (incl. refine factor) > 1024 is not implemented");
   const int np = nprobes < K ? nprobes : K;
@@ -1005,7 +980,7 @@ void ivfflat_search_f32(const float* centroids, int K, int d, int metric, const 
       set_smem(ivfflat_scan_kernel<MET>, smem);                                                         \
       LB2_LAUNCH("flat_scan", (ivfflat_scan_kernel<MET>), g, 256, smem, queries + q0 * d, d,             \
                  pids.p + q0 * np, np, part_offsets, vectors, row_ids, k, cand_d.p + q0 * np * k,        \
-                 cand_id.p + q0 * np * k, cand_cnt.p + q0 * np);                                         \
+                 cand_id.p + q0 * np * k, cand_cnt.p + q0 * np, allow);                                  \
     }
     if (metric == METRIC_DOT) LB2_FLAT(METRIC_DOT)
     else if (metric == METRIC_COSINE) LB2_FLAT(METRIC_COSINE)

@@ -7,10 +7,15 @@ void find_partitions_f32(const float* centroids, int K, int d, int metric, const
 void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const float* codebook, int M,
                       int nbits, const uint64_t* part_offsets, const uint8_t* codes,
                       const uint64_t* row_ids, const float* queries, uint64_t nq, int k, int nprobes,
-                      uint64_t* out_ids, float* out_dists, uint32_t* out_counts);
+                      uint64_t* out_ids, float* out_dists, uint32_t* out_counts,
+                      const uint64_t* allow = nullptr);
 void ivfflat_search_f32(const float* centroids, int K, int d, int metric, const uint64_t* part_offsets,
                         const float* vectors, const uint64_t* row_ids, const float* queries, uint64_t nq,
-                        int k, int nprobes, uint64_t* out_ids, float* out_dists, uint32_t* out_counts);
+                        int k, int nprobes, uint64_t* out_ids, float* out_dists, uint32_t* out_counts,
+                        const uint64_t* allow = nullptr);
+// bit i of bitmap = RowIdMask::selected(row_ids[i]) (lance-core/src/utils/mask.rs:84-93); lists sorted
+void row_mask_f32(const uint64_t* row_ids, uint64_t n, const uint64_t* allow, uint64_t n_allow, bool has_allow,
+                  const uint64_t* block, uint64_t n_block, bool has_block, uint64_t* bitmap);
 void refine_f32(const float* queries, uint64_t nq, int d, int metric, const float* vectors,
                 uint64_t num_vectors, const uint64_t* cand_id, const uint32_t* cand_cnt, int kc, int k,
                 uint64_t* out_id, float* out_d, uint32_t* out_cnt);

@@ -242,8 +242,18 @@ def flat_distance_all(query, vectors, metric="l2", nthreads=1):
     return out
 
 
+def _mask_args(allow, block):
+    a = None if allow is None else np.ascontiguousarray(np.sort(np.asarray(allow, dtype=np.uint64)))
+    b = None if block is None else np.ascontiguousarray(np.sort(np.asarray(block, dtype=np.uint64)))
+    keep = (a, b)
+    return keep, [(_p(a, C.c_uint64) if a is not None and a.size else None), C.c_uint64(0 if a is None else a.size),
+                  C.c_int(a is not None),
+                  (_p(b, C.c_uint64) if b is not None and b.size else None), C.c_uint64(0 if b is None else b.size),
+                  C.c_int(b is not None)]
+
+
 def ivfpq_search(centroids, codebook, part_offsets, codes, row_ids, queries, k, nprobes,
-                 metric="l2", nbits=8, nthreads=1):
+                 metric="l2", nbits=8, nthreads=1, allow=None, block=None):
     centroids, codebook, queries = _f32(centroids), _f32(codebook), _f32(queries)
     K, d = centroids.shape
     M = codebook.shape[0]
@@ -254,6 +264,15 @@ def ivfpq_search(centroids, codebook, part_offsets, codes, row_ids, queries, k, 
     oi = np.empty((nq, k), np.uint64)
     od = np.empty((nq, k), np.float32)
     oc = np.empty(nq, np.uint32)
+    if allow is not None or block is not None:  # prefilter path (flat/index.rs:129-165)
+        keep, margs = _mask_args(allow, block)
+        lib().lo_ivfpq_search_masked(_p(centroids, C.c_float), C.c_uint64(K), C.c_uint64(d),
+                                     C.c_int(METRIC[metric]), _p(codebook, C.c_float), C.c_uint64(M),
+                                     C.c_int(nbits), _p(po, C.c_uint64), _p(codes, C.c_uint8),
+                                     _p(rid, C.c_uint64), _p(queries, C.c_float), C.c_uint64(nq),
+                                     C.c_uint64(k), C.c_uint64(nprobes), *margs, _p(oi, C.c_uint64),
+                                     _p(od, C.c_float), _p(oc, C.c_uint32), C.c_int(nthreads))
+        return oi, od, oc
     lib().lo_ivfpq_search(_p(centroids, C.c_float), C.c_uint64(K), C.c_uint64(d),
                           C.c_int(METRIC[metric]), _p(codebook, C.c_float), C.c_uint64(M),
                           C.c_int(nbits), _p(po, C.c_uint64), _p(codes, C.c_uint8),
@@ -276,7 +295,8 @@ def brute_force_topk(data, queries, k, metric="l2", nthreads=1):
     return oi, od
 
 
-def ivfflat_search(centroids, part_offsets, vectors, row_ids, queries, k, nprobes, metric="l2", nthreads=1):
+def ivfflat_search(centroids, part_offsets, vectors, row_ids, queries, k, nprobes, metric="l2", nthreads=1,
+                   allow=None, block=None):
     centroids, vectors, queries = _f32(centroids), _f32(vectors), _f32(queries)
     K, d = centroids.shape
     po = np.ascontiguousarray(part_offsets, dtype=np.uint64)
@@ -285,6 +305,14 @@ def ivfflat_search(centroids, part_offsets, vectors, row_ids, queries, k, nprobe
     oi = np.empty((nq, k), np.uint64)
     od = np.empty((nq, k), np.float32)
     oc = np.empty(nq, np.uint32)
+    if allow is not None or block is not None:
+        keep, margs = _mask_args(allow, block)
+        lib().lo_ivfflat_search_masked(_p(centroids, C.c_float), C.c_uint64(K), C.c_uint64(d), C.c_int(METRIC[metric]),
+                                       _p(po, C.c_uint64), _p(vectors, C.c_float), _p(rid, C.c_uint64),
+                                       _p(queries, C.c_float), C.c_uint64(nq), C.c_uint64(k), C.c_uint64(nprobes),
+                                       *margs, _p(oi, C.c_uint64), _p(od, C.c_float), _p(oc, C.c_uint32),
+                                       C.c_int(nthreads))
+        return oi, od, oc
     lib().lo_ivfflat_search(_p(centroids, C.c_float), C.c_uint64(K), C.c_uint64(d), C.c_int(METRIC[metric]),
                             _p(po, C.c_uint64), _p(vectors, C.c_float), _p(rid, C.c_uint64),
                             _p(queries, C.c_float), C.c_uint64(nq), C.c_uint64(k), C.c_uint64(nprobes),

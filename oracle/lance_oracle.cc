@@ -715,6 +715,42 @@ uint64_t lo_flat_topk(const float* dists, const uint64_t* row_ids, uint64_t n, u
   return h.data.size();
 }
 
+// RowIdMask::selected (lance-core/src/utils/mask.rs:84-93): allow list AND NOT block list; either
+// list may be absent (NULL).  Lists are sorted ascending (RoaringTreemap iteration order).
+struct RowMask {
+  const uint64_t* allow; uint64_t n_allow; int has_allow;
+  const uint64_t* block; uint64_t n_block; int has_block;
+  bool empty() const { return !has_allow && !has_block; }
+  bool selected(uint64_t id) const {
+    if (has_allow && !std::binary_search(allow, allow + n_allow, id)) return false;
+    if (has_block && std::binary_search(block, block + n_block, id)) return false;
+    return true;
+  }
+};
+
+// a16  FlatIndex::search prefilter path (flat/index.rs:129-165): rows are visited in storage order,
+//   unselected rows are skipped BEFORE the distance is looked at, then the same heap rule.
+static uint64_t flat_topk_masked(const float* dists, const uint64_t* row_ids, uint64_t n, uint64_t k,
+                                 const RowMask& mask, uint64_t* out_ids, float* out_dists) {
+  RustMaxHeap h;
+  if (k == 0) return 0;
+  for (uint64_t j = 0; j < n; ++j) {
+    if (!mask.selected(row_ids[j])) continue;
+    float dist = dists[j];
+    if (h.data.size() < k) {
+      h.push({row_ids[j], dist});
+    } else if (gt(h.data[0].dist, dist)) {
+      h.pop();
+      h.push({row_ids[j], dist});
+    }
+  }
+  for (size_t i = 0; i < h.data.size(); ++i) {
+    out_ids[i] = h.data[i].id;
+    out_dists[i] = h.data[i].dist;
+  }
+  return h.data.size();
+}
+
 // a17  FlatDistanceCal::distance_all (flat/storage.rs:397-403): exact distances to every row
 void lo_flat_distance_all(const float* query, const float* vectors, uint64_t n, uint64_t d,
                           int metric, float* out, int nthreads) {
@@ -736,10 +772,10 @@ void lo_flat_distance_all(const float* query, const float* vectors, uint64_t n, 
 // parallel; results are independent of that schedule).
 // out arrays are [nq][k]; out_counts[nq].
 // ---------------------------------------------------------------------------------------------
-void lo_ivfpq_search(const float* centroids, uint64_t K, uint64_t d, int metric,
+static void ivfpq_search_impl(const float* centroids, uint64_t K, uint64_t d, int metric,
                      const float* codebook, uint64_t M, int nbits, const uint64_t* part_offsets,
                      const uint8_t* codes, const uint64_t* row_ids, const float* queries,
-                     uint64_t nq, uint64_t k, uint64_t nprobes, uint64_t* out_ids,
+                     uint64_t nq, uint64_t k, uint64_t nprobes, const RowMask& mask, uint64_t* out_ids,
                      float* out_dists, uint32_t* out_counts, int nthreads) {
   const uint64_t ncode = uint64_t(1) << nbits;
   uint64_t max_part = 0;
@@ -777,8 +813,9 @@ void lo_ivfpq_search(const float* centroids, uint64_t K, uint64_t d, int metric,
         }
         lo_build_lut(codebook, nbits, M, d, cmetric, qq, lut.data());
         lo_pq_scan(lut.data(), M, codes_t.data() + part_offsets[p] * M, n, cmetric, dist.data());
-        uint64_t got = lo_flat_topk(dist.data(), row_ids + part_offsets[p], n, k, 0, 0, 0,
-                                    hid.data(), hd.data());
+        uint64_t got = mask.empty()
+                           ? lo_flat_topk(dist.data(), row_ids + part_offsets[p], n, k, 0, 0, 0, hid.data(), hd.data())
+                           : flat_topk_masked(dist.data(), row_ids + part_offsets[p], n, k, mask, hid.data(), hd.data());
         for (uint64_t i = 0; i < got; ++i) cand.push_back({hid[i], hd[i]});
       }
       std::sort(cand.begin(), cand.end(), [](const Node& a, const Node& c) {
@@ -800,13 +837,35 @@ void lo_ivfpq_search(const float* centroids, uint64_t K, uint64_t d, int metric,
   });
 }
 
+void lo_ivfpq_search(const float* centroids, uint64_t K, uint64_t d, int metric,
+                     const float* codebook, uint64_t M, int nbits, const uint64_t* part_offsets,
+                     const uint8_t* codes, const uint64_t* row_ids, const float* queries,
+                     uint64_t nq, uint64_t k, uint64_t nprobes, uint64_t* out_ids,
+                     float* out_dists, uint32_t* out_counts, int nthreads) {
+  const RowMask none{nullptr, 0, 0, nullptr, 0, 0};
+  ivfpq_search_impl(centroids, K, d, metric, codebook, M, nbits, part_offsets, codes, row_ids, queries, nq, k,
+                    nprobes, none, out_ids, out_dists, out_counts, nthreads);
+}
+// the same with a prefilter (PreFilter::mask -> RowIdMask, lance-index/src/prefilter.rs:27-51)
+void lo_ivfpq_search_masked(const float* centroids, uint64_t K, uint64_t d, int metric,
+                            const float* codebook, uint64_t M, int nbits, const uint64_t* part_offsets,
+                            const uint8_t* codes, const uint64_t* row_ids, const float* queries,
+                            uint64_t nq, uint64_t k, uint64_t nprobes, const uint64_t* allow,
+                            uint64_t n_allow, int has_allow, const uint64_t* block, uint64_t n_block,
+                            int has_block, uint64_t* out_ids, float* out_dists, uint32_t* out_counts,
+                            int nthreads) {
+  const RowMask mask{allow, n_allow, has_allow, block, n_block, has_block};
+  ivfpq_search_impl(centroids, K, d, metric, codebook, M, nbits, part_offsets, codes, row_ids, queries, nq, k,
+                    nprobes, mask, out_ids, out_dists, out_counts, nthreads);
+}
+
 // IVF_FLAT query (lance-index/src/vector/flat/index.rs:82-177 over FlatFloatStorage,
 // flat/storage.rs:345-403): partitions found with L2 on the normalised query for cosine
 // (ivf.rs:149-185), every row of the probed partitions scored with the index's metric.
 // `vectors` are the STORED vectors (normalised for cosine) in partition order.
-void lo_ivfflat_search(const float* centroids, uint64_t K, uint64_t d, int metric,
+static void ivfflat_search_impl(const float* centroids, uint64_t K, uint64_t d, int metric,
                        const uint64_t* part_offsets, const float* vectors, const uint64_t* row_ids,
-                       const float* queries, uint64_t nq, uint64_t k, uint64_t nprobes,
+                       const float* queries, uint64_t nq, uint64_t k, uint64_t nprobes, const RowMask& mask,
                        uint64_t* out_ids, float* out_dists, uint32_t* out_counts, int nthreads) {
   uint64_t max_part = 0;
   for (uint64_t p = 0; p < K; ++p) max_part = std::max(max_part, part_offsets[p + 1] - part_offsets[p]);
@@ -831,7 +890,9 @@ void lo_ivfflat_search(const float* centroids, uint64_t K, uint64_t d, int metri
         uint64_t n = part_offsets[p + 1] - part_offsets[p];
         if (n == 0) continue;
         lo_flat_distance_all(q.data(), vectors + part_offsets[p] * d, n, d, metric, dist.data(), 1);
-        uint64_t got = lo_flat_topk(dist.data(), row_ids + part_offsets[p], n, k, 0, 0, 0, hid.data(), hd.data());
+        uint64_t got = mask.empty()
+                           ? lo_flat_topk(dist.data(), row_ids + part_offsets[p], n, k, 0, 0, 0, hid.data(), hd.data())
+                           : flat_topk_masked(dist.data(), row_ids + part_offsets[p], n, k, mask, hid.data(), hd.data());
         for (uint64_t i = 0; i < got; ++i) cand.push_back({hid[i], hd[i]});
       }
       std::sort(cand.begin(), cand.end(), [](const Node& a, const Node& c) {
@@ -851,6 +912,25 @@ void lo_ivfflat_search(const float* centroids, uint64_t K, uint64_t d, int metri
       out_counts[qi] = uint32_t(got);
     }
   });
+}
+
+void lo_ivfflat_search(const float* centroids, uint64_t K, uint64_t d, int metric,
+                       const uint64_t* part_offsets, const float* vectors, const uint64_t* row_ids,
+                       const float* queries, uint64_t nq, uint64_t k, uint64_t nprobes,
+                       uint64_t* out_ids, float* out_dists, uint32_t* out_counts, int nthreads) {
+  const RowMask none{nullptr, 0, 0, nullptr, 0, 0};
+  ivfflat_search_impl(centroids, K, d, metric, part_offsets, vectors, row_ids, queries, nq, k, nprobes, none,
+                      out_ids, out_dists, out_counts, nthreads);
+}
+void lo_ivfflat_search_masked(const float* centroids, uint64_t K, uint64_t d, int metric,
+                              const uint64_t* part_offsets, const float* vectors, const uint64_t* row_ids,
+                              const float* queries, uint64_t nq, uint64_t k, uint64_t nprobes,
+                              const uint64_t* allow, uint64_t n_allow, int has_allow, const uint64_t* block,
+                              uint64_t n_block, int has_block, uint64_t* out_ids, float* out_dists,
+                              uint32_t* out_counts, int nthreads) {
+  const RowMask mask{allow, n_allow, has_allow, block, n_block, has_block};
+  ivfflat_search_impl(centroids, K, d, metric, part_offsets, vectors, row_ids, queries, nq, k, nprobes, mask,
+                      out_ids, out_dists, out_counts, nthreads);
 }
 
 // exact brute-force ground truth (rust/lance/src/index/vector/ivf/v2.rs:959-983 `ground_truth`)

@@ -255,6 +255,52 @@ def test_index_search_matches_oracle(metric):
             assert np.all(np.diff(dists[i, :c]) >= 0)
 
 
+# ---- prefilter: PreFilter / RowIdMask (prefilter.rs:27-51, flat/index.rs:129-165) --------------
+@pytest.mark.parametrize("kind", ["pq", "flat"])
+def test_index_search_with_row_mask_matches_oracle(kind):
+    rng = np.random.default_rng(115)
+    n, d, K, M = 24000, 64, 24, 8
+    data = synth.gaussian_mixture(n, d, n_components=K, seed=115)
+    rid = (rng.permutation(n).astype(np.uint64) * 3 + 7)          # sparse, shuffled row ids
+    if kind == "pq":
+        ix = lb.IvfPqIndex.build(data, "l2", lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, max_iters=8,
+                                                               pq_max_iters=6), row_ids=rid)
+    else:
+        ix = lb.IvfFlatIndex.build(data, "l2", num_partitions=K, max_iters=8, row_ids=rid)
+    parts = ix.export()
+    q = synth.gaussian_mixture(24, d, n_components=K, seed=116)
+    allow = rng.choice(rid, n // 3, replace=False)
+    block = rng.choice(rid, n // 2, replace=False)
+    few = rng.choice(rid, 25, replace=False)                       # fewer allowed rows than k in most probes
+    cases = [(allow, None), (None, block), (allow, block), (few, None), (np.zeros(0, np.uint64), None)]
+    for a, b in cases:
+        bm = ix.row_mask(a, b)
+        sel = np.ones(n, bool) if a is None else np.isin(parts["row_ids"], a)
+        if b is not None:
+            sel &= ~np.isin(parts["row_ids"], b)
+        bits = np.unpackbits(bm.view(np.uint8), bitorder="little")[:n].astype(bool)
+        assert np.array_equal(bits, sel)                           # lb2_index_row_mask == RowIdMask::selected
+        for k, nprobes in ((10, 4), (40, 6)):
+            ids, dists = ix.search_ex(q, k=k, nprobes=nprobes, allow_bitmap=bm)
+            if kind == "pq":
+                oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"],
+                                             parts["codes"], parts["row_ids"], q, k, nprobes, nthreads=NT,
+                                             allow=a, block=b)
+            else:
+                oi, od, oc = ob.ivfflat_search(parts["centroids"], parts["part_offsets"], parts["vectors"],
+                                               parts["row_ids"], q, k, nprobes, nthreads=NT, allow=a, block=b)
+            for i in range(len(q)):
+                c = int(oc[i])
+                assert np.isinf(dists[i, c:]).all() and (ids[i, c:] == np.uint64(2**64 - 1)).all()
+                _check_topk(ids[i, :c], dists[i, :c], oi[i, :c], od[i, :c], k)
+                assert sel[np.searchsorted(np.sort(parts["row_ids"]), ids[i, :c])].shape[0] == c
+                assert np.isin(ids[i, :c], parts["row_ids"][sel]).all()
+    # no mask == plain search; mask + refine composes
+    i0, d0 = ix.search(q, k=10, nprobes=4)
+    i1, d1 = ix.search_ex(q, k=10, nprobes=4)
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+
+
 def test_build_transform_equals_oracle_and_recall():
     # v2.rs:1310-1384: IVF_PQ recall floor on random data; here against exact brute force
     n, d, K, M = 50000, 128, 64, 16

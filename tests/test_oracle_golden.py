@@ -197,3 +197,31 @@ def test_find_partitions_sorted():
     dd = ob.l2_batch(q, cent, 24)
     order = np.lexsort((np.arange(64), dd))[:10]
     assert np.array_equal(ids, order.astype(np.uint32)) and np.array_equal(dists, dd[order])
+
+
+def test_masked_search_follows_row_id_mask_semantics():
+    """flat/index.rs:129-165 + mask.rs:84-93: unselected rows never enter the heap; allow-all == no mask."""
+    rng = np.random.default_rng(8)
+    n, d, K, M = 3000, 16, 8, 4
+    data = rng.standard_normal((n, d)).astype(np.float32)
+    cent, _, _ = ob.kmeans_train(data, K, max_iters=5, seed=1)
+    part, _, _ = ob.compute_membership(cent, data)
+    res = ob.compute_residual(cent, data, part)
+    cb, _ = ob.pq_train(res, M, max_iters=4, seed=2)
+    codes = ob.pq_encode(cb, res)
+    order = np.argsort(part, kind="stable")
+    offs = np.concatenate([[0], np.cumsum(np.bincount(part, minlength=K))]).astype(np.uint64)
+    rid = (order.astype(np.uint64) * 5 + 1)
+    q = rng.standard_normal((6, d)).astype(np.float32)
+    base = ob.ivfpq_search(cent, cb, offs, codes[order], rid, q, 10, 3)
+    same = ob.ivfpq_search(cent, cb, offs, codes[order], rid, q, 10, 3, allow=rid)
+    assert all(np.array_equal(a, b) for a, b in zip(base, same))
+    block = rid[rng.choice(n, n // 2, replace=False)]
+    oi, od, oc = ob.ivfpq_search(cent, cb, offs, codes[order], rid, q, 10, 3, block=block)
+    for i in range(len(q)):
+        c = int(oc[i])
+        assert not np.isin(oi[i, :c], block).any()
+        keep = ~np.isin(base[0][i, :int(base[2][i])], block)      # surviving unmasked winners stay winners
+        assert np.isin(base[0][i, :int(base[2][i])][keep], oi[i, :c]).all()
+    none = ob.ivfpq_search(cent, cb, offs, codes[order], rid, q, 10, 3, allow=np.zeros(0, np.uint64))
+    assert (none[2] == 0).all()
