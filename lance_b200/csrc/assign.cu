@@ -414,18 +414,12 @@ void assign_rows_f32(const float* x, uint64_t n_max, int d, const float* cent, i
                      TcWorkspace* ws, bool cT_ready) {
   if (metric != METRIC_L2) fail(LB2_UNSUPPORTED, "assign_rows_f32: metric not supported");
   if (!(d % 16 == 0 && d <= 256)) {
-    const bool r16 = sizeof(float) * 16 * (size_t)d <= 96 * 1024;
-    const size_t gsmem = sizeof(float) * (r16 ? 16 : 8) * (size_t)d;
+    // 8 rows per CTA: the list is short, more CTAs beat fewer centroid re-reads (measured)
+    const size_t gsmem = sizeof(float) * 8 * (size_t)d;
     if (gsmem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "dimension %d too large for the exact kernel", d);
-    if (r16) {
-      set_smem(generic_kernel<METRIC_L2, false, 16>, gsmem);
-      LB2_LAUNCH("assign_exact_fallback", (generic_kernel<METRIC_L2, false, 16>), cdiv(n_max, 16), 256, gsmem,
-                 x, n_max, d, cent, K, bias_padded, part, dist, valid, nullptr, active, row_list, row_count);
-    } else {
-      set_smem(generic_kernel<METRIC_L2, false, 8>, gsmem);
-      LB2_LAUNCH("assign_exact_fallback", (generic_kernel<METRIC_L2, false, 8>), cdiv(n_max, 8), 256, gsmem,
-                 x, n_max, d, cent, K, bias_padded, part, dist, valid, nullptr, active, row_list, row_count);
-    }
+    set_smem(generic_kernel<METRIC_L2, false, 8>, gsmem);
+    LB2_LAUNCH("assign_exact_fallback", (generic_kernel<METRIC_L2, false, 8>), cdiv(n_max, 8), 256, gsmem, x,
+               n_max, d, cent, K, bias_padded, part, dist, valid, nullptr, active, row_list, row_count);
     return;
   }
   const int Kp = (K + 63) / 64 * 64;

@@ -9,8 +9,9 @@
 //
 // One CTA per (query, probed partition): the residual query and its M x 256 f32 lookup table are
 // built in shared memory (never written to HBM), the partition's codes are streamed once with
-// 128-bit loads, each row's distance is the reference's m-ascending f32 sum (bit-exact), and a
-// per-thread sorted list + block argmin rounds produce the k smallest (distance, position) pairs.
+// 128-bit loads, each row's distance is the reference's m-ascending f32 sum (bit-exact), and
+// warp-level sorting networks (k <= 16) or a block radix select produce the k smallest (distance,
+// position) pairs.
 #include "assign.cuh"
 #include "common.cuh"
 #include "exact.cuh"
@@ -358,83 +359,61 @@ ivfpq_scan_radix_kernel(const float* __restrict__ queries, int d, const float* _
   if (tid == 0) cand_cnt[slot] = nw;
 }
 
-// ------------------------------------------------------------------------------------------------
-// small-k (k <= 32) variant: a thread keeps its <= 16 chunk distances in registers.
-//   T  = k-th smallest of the 256 per-thread minima  (an upper bound of the k-th smallest overall)
-//   C  = { elements <= T } : at most (k-1)*16 + 1 of them, compacted into shared memory
-//   the k smallest of C (+ the winners carried from earlier chunks) are then selected by ONE warp
-//   with shuffle-only argmin rounds.  All comparisons are on (total-order key, position).
-// ------------------------------------------------------------------------------------------------
-// one warp: `rounds` smallest (key,pos) among the PER-per-lane register values, ascending; the r-th
-// winner is handed to emit(r, key, pos) by every lane (uniform)
-template <int PER, class Emit>
-__device__ __forceinline__ void warp_select(const int32_t (&key)[PER], const uint32_t (&pos)[PER],
-                                            const bool (&ok)[PER], int rounds, Emit emit) {
-  int32_t pk = 0;
-  uint32_t pp = 0;
-  for (int r = 0; r < rounds; ++r) {
-    int32_t bk = 0x7fffffff;
-    uint32_t bp = 0xffffffffu;
-    bool has = false;
-#pragma unroll
-    for (int u = 0; u < PER; ++u) {
-      const bool elig = ok[u] && (r == 0 || ki_less(pk, pp, key[u], pos[u]));
-      if (elig && (!has || ki_less(key[u], pos[u], bk, bp))) { bk = key[u]; bp = pos[u]; has = true; }
-    }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      const int32_t ok2 = __shfl_xor_sync(0xffffffffu, bk, off);
-      const uint32_t op = __shfl_xor_sync(0xffffffffu, bp, off);
-      const int oh = __shfl_xor_sync(0xffffffffu, (int)has, off);
-      if (oh && (!has || ki_less(ok2, op, bk, bp))) { bk = ok2; bp = op; has = true; }
-    }
-    if (!has) break;  // uniform
-    pk = bk;
-    pp = bp;
-    emit(r, bk, bp);
-  }
+// ---- warp-wide sorting network on packed (key, position) words -------------------------------------
+// A candidate is one u64: (order-preserving u32 of the distance) << 32 | position inside the partition,
+// so an unsigned compare IS the (distance, position) order every selection step needs ("ties keep the
+// earlier row").  PACK_INF (no candidate) sorts last.
+constexpr uint64_t PACK_INF = ~0ull;
+__device__ __forceinline__ uint64_t pack_cand(int32_t key, uint32_t pos) {
+  return ((uint64_t)((uint32_t)key ^ 0x80000000u) << 32) | pos;
 }
+__device__ __forceinline__ int32_t cand_key(uint64_t c) { return (int32_t)((uint32_t)(c >> 32) ^ 0x80000000u); }
+__device__ __forceinline__ uint32_t cand_pos(uint64_t c) { return (uint32_t)c; }
 
-// one warp, values in SHARED memory (cnt of them, strided over the lanes): the `rounds` smallest
-// (key,pos), ascending, handed to emit(r, key, pos) on every lane
-template <class Emit>
-__device__ __forceinline__ void warp_select_smem(const int32_t* keys, const uint32_t* poss, uint32_t cnt,
-                                                 int rounds, int lane, Emit emit) {
-  int32_t pk = 0;
-  uint32_t pp = 0;
-  for (int r = 0; r < rounds; ++r) {
-    int32_t bk = 0x7fffffff;
-    uint32_t bp = 0xffffffffu;
-    bool has = false;
-    for (uint32_t i = lane; i < cnt; i += 32) {
-      const int32_t kk = keys[i];
-      const uint32_t ps = poss[i];
-      if ((r == 0 || ki_less(pk, pp, kk, ps)) && (!has || ki_less(kk, ps, bk, bp))) { bk = kk; bp = ps; has = true; }
-    }
+// bitonic merge of a 32-lane bitonic sequence into ascending order (5 compare-exchange steps)
+__device__ __forceinline__ uint64_t warp_bitonic_merge32(uint64_t v, int lane) {
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      const int32_t ok2 = __shfl_xor_sync(0xffffffffu, bk, off);
-      const uint32_t op = __shfl_xor_sync(0xffffffffu, bp, off);
-      const int oh = __shfl_xor_sync(0xffffffffu, (int)has, off);
-      if (oh && (!has || ki_less(ok2, op, bk, bp))) { bk = ok2; bp = op; has = true; }
-    }
-    if (!has) break;  // uniform
-    pk = bk;
-    pp = bp;
-    emit(r, bk, bp);
+  for (int j = 16; j >= 1; j >>= 1) {
+    const uint64_t o = __shfl_xor_sync(0xffffffffu, v, j);
+    const bool keep_min = (lane & j) == 0;
+    v = (keep_min == (o < v)) ? o : v;
   }
+  return v;
+}
+// full ascending sort of one value per lane (15 compare-exchange steps)
+__device__ __forceinline__ uint64_t warp_sort32(uint64_t v, int lane) {
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+    for (int j = k2 >> 1; j >= 1; j >>= 1) {
+      const uint64_t o = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool keep_min = ((lane & j) == 0) == ((lane & k2) == 0);
+      v = (keep_min == (o < v)) ? o : v;
+    }
+  }
+  return v;
+}
+// the 32 smallest of a shared-memory list, ascending, one per lane (lane r = r-th smallest)
+__device__ __forceinline__ uint64_t warp_smallest32(const uint64_t* list, uint32_t cnt, int lane) {
+  uint64_t best = warp_sort32(lane < (int)cnt ? list[lane] : PACK_INF, lane);
+  for (uint32_t base = 32; base < cnt; base += 32) {
+    uint64_t v = warp_sort32(base + lane < cnt ? list[base + lane] : PACK_INF, lane);
+    v = __shfl_sync(0xffffffffu, v, 31 - lane);  // descending: min(best, v) is bitonic
+    best = warp_bitonic_merge32(v < best ? v : best, lane);
+  }
+  return best;
 }
 
 // k <= 16.  Per chunk of 4096 rows every WARP works on its own 512 rows without block barriers:
-//   Tw = k-th smallest of its 32 lane minima (an upper bound of the warp's k-th smallest element),
-//   the <= (k-1)*16+1 elements <= Tw are compacted into the warp's shared-memory list, its k smallest
-//   are selected; then warp 0 merges the 8 x k warp winners with the winners carried from earlier
-//   chunks.  All comparisons are on (total-order key, position): ties keep the earlier rows.
+//   Tw = k-th smallest of its 32 lane minima (one 32-lane sort; an upper bound of the warp's k-th
+//   smallest element), the <= (k-1)*16+1 elements <= Tw are compacted into the warp's shared-memory
+//   list and sorted 32 at a time; then warp 0 merges the 8 x k warp winners with the winners carried
+//   from earlier chunks the same way.  All comparisons are on packed (key, position) words.
 constexpr int SCAN_KFAST = 16;
 constexpr int SCAN_WLIST = (SCAN_KFAST - 1) * 16 + 1;  // 241
 
-template <int METRIC>
-__global__ void __launch_bounds__(256)
+template <int METRIC, bool FILTER>
+__global__ void __launch_bounds__(256, 6)
 ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restrict__ centroids,
                   const float* __restrict__ codebook, int M, int ds,
                   const uint32_t* __restrict__ probe_ids, int np,
@@ -446,13 +425,9 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
   extern __shared__ float smem[];
   float* lut = smem;          // [M*256]
   float* qr = lut + M * 256;  // [d]
-  __shared__ int32_t wl_key[8][SCAN_WLIST];   // per-warp compacted candidates
-  __shared__ uint32_t wl_pos[8][SCAN_WLIST];
-  __shared__ int32_t fin_key[8 * SCAN_KFAST + SCAN_KFAST];  // 8 x k warp winners + carried winners
-  __shared__ uint32_t fin_pos[8 * SCAN_KFAST + SCAN_KFAST];
-  __shared__ uint32_t fin_cnt;
-  __shared__ int32_t car_key[SCAN_KFAST];
-  __shared__ uint32_t car_pos[SCAN_KFAST];
+  __shared__ uint64_t wl[8][SCAN_WLIST];                 // per-warp compacted candidates
+  __shared__ uint64_t fin[8 * SCAN_KFAST + SCAN_KFAST];  // 8 x k warp winners, then the carried winners
+  __shared__ uint64_t car[SCAN_KFAST];
   __shared__ uint32_t s_nw;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pi = blockIdx.x;
@@ -478,15 +453,16 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
   for (uint32_t c0 = 0; c0 < n_p; c0 += SCAN_CHUNK) {
     const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
     int32_t key[RPT];
-    int32_t mk = 0x7fffffff;
-    uint32_t mp = 0xffffffffu;
+    uint64_t mine = PACK_INF;  // this lane's smallest candidate
+    uint32_t livemask = 0;     // FILTER: bit u = row u of this thread passed the prefilter
     // rows of warp w in this chunk: c0 + w*512 + lane + 32*u  (a warp owns a contiguous 512-row slab)
     const uint32_t wbase = warp * (RPT * 32);
 #pragma unroll
     for (int u = 0; u < RPT; ++u) {
       const uint32_t j = wbase + lane + 32 * u;
       key[u] = 0x7fffffff;
-      if (j < clen && row_allowed(allow, off + c0 + j)) {
+      if (j < clen && (!FILTER || row_allowed(allow, off + c0 + j))) {
+        if (FILTER) livemask |= 1u << u;
         float dist = 0.0f;
         if ((M & 15) == 0) {
           const uint4* rp = reinterpret_cast<const uint4*>(pc + (size_t)(c0 + j) * M);
@@ -506,112 +482,60 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
         }
         if (METRIC == METRIC_DOT) dist = __fsub_rn(dist, dot_fix);  // pq/storage.rs:957-958
         key[u] = total_order_key(dist);
-        if (key[u] < mk) { mk = key[u]; mp = c0 + j; }  // ascending position: first minimum wins
+        const uint64_t c = pack_cand(key[u], c0 + j);
+        mine = c < mine ? c : mine;
       }
     }
-    // ---- warp-local: Tw = k-th smallest lane minimum (or "everything" if < k lanes have rows)
-    int32_t tk = 0x7fffffff;
-    uint32_t tp = 0xffffffffu;
-    {
-      int32_t pk = 0;
-      uint32_t pp = 0;
-      int got = 0;
-      for (int r = 0; r < k; ++r) {
-        const bool elig = mp != 0xffffffffu && (r == 0 || ki_less(pk, pp, mk, mp));
-        int32_t bk = elig ? mk : 0x7fffffff;
-        uint32_t bp = elig ? mp : 0xffffffffu;
-        bool has = elig;
-#pragma unroll
-        for (int off2 = 16; off2 >= 1; off2 >>= 1) {
-          const int32_t ok2 = __shfl_xor_sync(0xffffffffu, bk, off2);
-          const uint32_t op = __shfl_xor_sync(0xffffffffu, bp, off2);
-          const int oh = __shfl_xor_sync(0xffffffffu, (int)has, off2);
-          if (oh && (!has || ki_less(ok2, op, bk, bp))) { bk = ok2; bp = op; has = true; }
-        }
-        if (!has) break;
-        pk = bk; pp = bp; got = r + 1;
-      }
-      if (got == k) { tk = pk; tp = pp; }
-    }
+    // ---- warp-local threshold: Tw = k-th smallest lane minimum (PACK_INF if < k lanes have rows)
+    const uint64_t tw = __shfl_sync(0xffffffffu, warp_sort32(mine, lane), k - 1);
     // ---- compact the warp's elements <= Tw (ballot-ranked: deterministic order, no atomics)
     uint32_t wcnt = 0;
 #pragma unroll
     for (int u = 0; u < RPT; ++u) {
       const uint32_t j = wbase + lane + 32 * u;
-      const bool take = j < clen && !ki_less(tk, tp, key[u], c0 + j);
+      const bool live = FILTER ? ((livemask >> u) & 1u) != 0 : j < clen;
+      const uint64_t c = pack_cand(key[u], c0 + j);
+      const bool take = live && c <= tw;
       const unsigned bal = __ballot_sync(0xffffffffu, take);
-      if (take) {
-        const uint32_t at = wcnt + __popc(bal & ((1u << lane) - 1));
-        wl_key[warp][at] = key[u];
-        wl_pos[warp][at] = c0 + j;
-      }
+      if (take) wl[warp][wcnt + __popc(bal & ((1u << lane) - 1))] = c;
       wcnt += __popc(bal);
     }
     __syncwarp();
-    // ---- the warp's k smallest -> block list
-    warp_select_smem(wl_key[warp], wl_pos[warp], wcnt, k, lane, [&](int r, int32_t kk, uint32_t pp2) {
-      if (lane == 0) { fin_key[warp * SCAN_KFAST + r] = kk; fin_pos[warp * SCAN_KFAST + r] = pp2; }
-    });
-    if (lane == 0) {
-      const int got = (int)min(wcnt, (uint32_t)k);
-      for (int r = got; r < k; ++r) fin_pos[warp * SCAN_KFAST + r] = 0xffffffffu;  // unused slots
+    // ---- the warp's k smallest -> block list (lane r holds the r-th smallest; PACK_INF = none)
+    {
+      const uint64_t best = warp_smallest32(wl[warp], wcnt, lane);
+      if (lane < k) fin[warp * SCAN_KFAST + lane] = best;
     }
     __syncthreads();
     if (warp == 0) {  // merge: 8 x k warp winners + carried winners -> k block winners
       const uint32_t nw = s_nw;
-      // compact valid entries into a dense list in place (lane-parallel, order irrelevant)
-      uint32_t cnt = 0;
-      for (int base = 0; base < 8 * SCAN_KFAST; base += 32) {
-        const int i = base + lane;
-        const int w2 = i / SCAN_KFAST, r2 = i % SCAN_KFAST;
-        const bool ok = r2 < k && fin_pos[i] != 0xffffffffu;
-        const int32_t kk = fin_key[i];
-        const uint32_t ps = fin_pos[i];
-        const unsigned bal = __ballot_sync(0xffffffffu, ok);
-        __syncwarp();
-        if (ok) {
-          const uint32_t at = cnt + __popc(bal & ((1u << lane) - 1));
-          wl_key[0][at] = kk;  // warp 0's own list is free again
-          wl_pos[0][at] = ps;
-        }
-        cnt += __popc(bal);
-        (void)w2;
-      }
-      if (lane < (int)nw) {
-        wl_key[0][cnt + lane] = car_key[lane];
-        wl_pos[0][cnt + lane] = car_pos[lane];
-      }
-      cnt += nw;
+      if (lane < k) fin[8 * SCAN_KFAST + lane] = lane < (int)nw ? car[lane] : PACK_INF;
       __syncwarp();
-      int got = 0;
-      warp_select_smem(wl_key[0], wl_pos[0], cnt, k, lane, [&](int r, int32_t kk, uint32_t pp2) {
-        if (lane == 0) { car_key[r] = kk; car_pos[r] = pp2; }
-        got = r + 1;
-      });
-      if (lane == 0) s_nw = got;
+      // the winners sit at fin[w * 16 + r], r < k: visit them 32 at a time (2 warps' slots per pass)
+      uint64_t best = PACK_INF;
+      for (int base = 0; base < 9 * SCAN_KFAST; base += 32) {
+        const int i = base + lane;
+        uint64_t v = (i < 9 * SCAN_KFAST && (i % SCAN_KFAST) < k) ? fin[i] : PACK_INF;
+        v = warp_sort32(v, lane);
+        if (base == 0) {
+          best = v;
+        } else {
+          v = __shfl_sync(0xffffffffu, v, 31 - lane);
+          best = warp_bitonic_merge32(v < best ? v : best, lane);
+        }
+      }
+      if (lane < k) car[lane] = best;
+      const unsigned got = __ballot_sync(0xffffffffu, lane < k && best != PACK_INF);
+      if (lane == 0) s_nw = __popc(got);
     }
     __syncthreads();
   }
   const uint32_t nw = s_nw;
-  if (allow) {  // drop filtered rows that surfaced because fewer than k allowed rows exist (nw <= 16)
-    if (tid == 0) {
-      uint32_t c = 0;
-      for (uint32_t i = 0; i < nw; ++i)
-        if (row_allowed(allow, off + car_pos[i])) {
-          cand_d[slot * k + c] = key_to_float(car_key[i]);
-          cand_id[slot * k + c] = row_ids[off + car_pos[i]];
-          ++c;
-        }
-      cand_cnt[slot] = c;
-    }
-    return;
-  }
   for (uint32_t i = tid; i < nw; i += 256) {
-    cand_d[slot * k + i] = key_to_float(car_key[i]);
-    cand_id[slot * k + i] = row_ids[off + car_pos[i]];
+    cand_d[slot * k + i] = key_to_float(cand_key(car[i]));
+    cand_id[slot * k + i] = row_ids[off + cand_pos(car[i])];
   }
   if (tid == 0) cand_cnt[slot] = nw;
-  (void)fin_cnt;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -876,9 +800,15 @@ static void scan_launch(int kmax, dim3 grid, size_t smem, const float* queries, 
                         uint64_t* cand_id, uint32_t* cand_cnt, const uint64_t* allow) {
   if (k <= SCAN_KFAST) {
     const size_t smem_fast = sizeof(float) * ((size_t)M * 256 + d);
-    set_smem(ivfpq_scan_kernel<METRIC>, smem_fast);
-    LB2_LAUNCH("pq_scan", (ivfpq_scan_kernel<METRIC>), grid, 256, smem_fast, queries, d, centroids,
-               codebook, M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt, allow);
+    if (allow) {  // filtered rows never enter the candidate lists
+      set_smem(ivfpq_scan_kernel<METRIC, true>, smem_fast);
+      LB2_LAUNCH("pq_scan", (ivfpq_scan_kernel<METRIC, true>), grid, 256, smem_fast, queries, d, centroids,
+                 codebook, M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt, allow);
+    } else {
+      set_smem(ivfpq_scan_kernel<METRIC, false>, smem_fast);
+      LB2_LAUNCH("pq_scan", (ivfpq_scan_kernel<METRIC, false>), grid, 256, smem_fast, queries, d, centroids,
+                 codebook, M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt, allow);
+    }
     return;
   }
   set_smem(ivfpq_scan_radix_kernel<METRIC>, smem);
