@@ -441,6 +441,20 @@ def main():
         rec_r = float(np.mean([len(set(ids_r[i].tolist()) & set(gt[i].tolist())) / TOPK for i in range(1000)]))
         query_refine = {"qps": NQ / (r_ms * 1e-3), "recall_at_10": rec_r, "nprobes": NPROBES, "k": TOPK,
                         "refine_factor": REFINE, "batch": NQ, "ms_per_batch": r_ms}
+    # small batches (batch sizes 1 / 64 / 10 000): host queries in, host results out
+    query_batches = None
+    if world == 1:
+        query_batches = []
+        for bsz in (1, 64):
+            reps = 200 if bsz == 1 else 100
+            for r in range(5):
+                ix.search(q_host[r * bsz:(r + 1) * bsz], TOPK, NPROBES)
+            t0 = time.perf_counter()
+            for r in range(reps):
+                o = (r * bsz) % (NQ - bsz)
+                ix.search(q_host[o:o + bsz], TOPK, NPROBES)
+            dt = (time.perf_counter() - t0) / reps
+            query_batches.append({"batch": bsz, "e2e_qps": bsz / dt, "latency_ms": dt * 1e3})
     scan_bytes = NQ * NPROBES * (n / NUM_PARTITIONS) * NUM_SUB_VECTORS + NQ * DIM * 4
     scan_launch_ms = scan_ms / max(scan_cnt, 1)
     query = {"qps": NQ / (q_ms * 1e-3), "e2e_qps": NQ / (q_e2e_ms * 1e-3), "recall_at_10": recall,
@@ -477,7 +491,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "build_phases_ms": {"ivf_train": stats.ms_ivf_train, "pq_train": stats.ms_pq_train, "transform": stats.ms_transform,
                                 "group": stats.ms_group, "ivf_iters": stats.ivf_iters, "pq_iters_max": stats.pq_iters_max},
-            "kernels": fams, "roofline": roofline, "query": query, "query_refine": query_refine,
+            "kernels": fams, "roofline": roofline, "query": query, "query_refine": query_refine, "query_batches": query_batches,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
