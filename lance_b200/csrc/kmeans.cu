@@ -277,6 +277,65 @@ __device__ __forceinline__ void update_body(size_t g, const float* __restrict__ 
   centroids[g] = acc;
 }
 
+// The same update for ds % 8 == 0, one WARP per (b, cluster, 8-dim chunk): the 32 lanes fetch 128 member
+// rows at a time (index load + 32-byte gather, all independent -> one memory round trip per 128
+// members instead of one per 16), park them in shared memory, then lanes 0..7 add their dimension in
+// member order.  The f32 sums are the same sequential sums as update_body's.
+constexpr int UPD_TILE = 128;
+__device__ __forceinline__ void update_body_warp(size_t w, float* tile, const float* __restrict__ x, int ldx, int ds,
+                                                 int K, int B, uint64_t n, const uint32_t* __restrict__ members,
+                                                 const uint32_t* __restrict__ offsets,
+                                                 float* __restrict__ centroids,
+                                                 const uint8_t* __restrict__ active, int scale) {
+  const int lane = threadIdx.x & 31;
+  const int nch = ds >> 3;
+  if (w >= (size_t)B * K * nch) return;
+  const int b = (int)(w / ((size_t)K * nch));
+  if (active && !active[b]) return;
+  const int k = (int)((w / nch) % K), c = (int)(w % nch);
+  const uint32_t* off = offsets + (size_t)b * (K + 1);
+  const uint32_t s = off[k], e = off[k + 1];
+  const uint32_t* mem = members + (size_t)b * n;
+  const float* col = x + (size_t)b * ds + c * 8;
+  float acc = 0.0f;
+  for (uint32_t base = s; base < e; base += UPD_TILE) {
+    const uint32_t cnt = min((uint32_t)UPD_TILE, e - base);
+    uint32_t r[UPD_TILE / 32];
+#pragma unroll
+    for (int u = 0; u < UPD_TILE / 32; ++u) {
+      const uint32_t j = base + u * 32 + lane;
+      r[u] = j < e ? mem[j] : 0xffffffffu;
+    }
+#pragma unroll
+    for (int u = 0; u < UPD_TILE / 32; ++u) {
+      if (r[u] != 0xffffffffu) {
+        const float4* src = reinterpret_cast<const float4*>(col + (size_t)r[u] * ldx);
+        float4* dst = reinterpret_cast<float4*>(tile + (u * 32 + lane) * 8);
+        dst[0] = src[0];
+        dst[1] = src[1];
+      }
+    }
+    __syncwarp();
+    if (lane < 8) {
+      uint32_t q = 0;
+      for (; q + 8 <= cnt; q += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = tile[(q + i) * 8 + lane];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = f_add(acc, v[i]);
+      }
+      for (; q < cnt; ++q) acc = f_add(acc, tile[q * 8 + lane]);
+    }
+    __syncwarp();
+  }
+  if (lane < 8) {
+    const uint32_t cnt = e - s;
+    if (scale && cnt > 0) acc = __fmul_rn(acc, __fdiv_rn(1.0f, (float)cnt));  // kmeans.rs:414-416
+    centroids[((size_t)b * K + k) * ds + c * 8 + lane] = acc;
+  }
+}
+
 // per (b, cluster): f64 loss in row order, radius (max), last member row (kmeans.rs:266-280)
 __device__ __forceinline__ void stats_body(int w, const float* __restrict__ dists, uint64_t n, int K, int B,
                              const uint32_t* __restrict__ members,
@@ -317,9 +376,15 @@ update_stats_kernel(unsigned update_blocks, const float* __restrict__ x, int ldx
                     uint64_t n, const uint32_t* __restrict__ members, const uint32_t* __restrict__ offsets,
                     float* __restrict__ centroids, const float* __restrict__ dists,
                     double* __restrict__ losses, float* __restrict__ radius,
-                    uint32_t* __restrict__ last_row, const uint8_t* __restrict__ active, int scale) {
+                    uint32_t* __restrict__ last_row, const uint8_t* __restrict__ active, int scale,
+                    int warp_update) {
+  __shared__ __align__(16) float tiles[4][UPD_TILE * 8];
   if (blockIdx.x < update_blocks) {
-    update_body((size_t)blockIdx.x * 128 + threadIdx.x, x, ldx, ds, K, B, n, members, offsets, centroids, active, scale);
+    if (warp_update)
+      update_body_warp((size_t)blockIdx.x * 4 + (threadIdx.x >> 5), tiles[threadIdx.x >> 5], x, ldx, ds, K, B, n,
+                       members, offsets, centroids, active, scale);
+    else
+      update_body((size_t)blockIdx.x * 128 + threadIdx.x, x, ldx, ds, K, B, n, members, offsets, centroids, active, scale);
   } else {
     stats_body((int)(((size_t)(blockIdx.x - update_blocks) * 128 + threadIdx.x) >> 5), dists, n, K, B,
                members, offsets, losses, radius, last_row, active);
@@ -688,10 +753,13 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
                          ids.p, dists.p, valid.p, active_d.p);
     }
     ms.run(ids.p, valid.p, n, K, B, active_d.p);
-    const unsigned ub = cdiv(BK * ds, 128), sb = cdiv((uint64_t)BK * 32, 128);
+    // ds % 8 == 0 (and 16-byte aligned rows): warp-cooperative update, one warp per (b, cluster, 8 dims)
+    const int warp_update = (ds % 8 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
+    const unsigned ub = warp_update ? cdiv(BK * (uint64_t)(ds / 8), 4) : cdiv(BK * ds, 128);
+    const unsigned sb = cdiv((uint64_t)BK * 32, 128);
     LB2_LAUNCH("kmeans_update_stats", update_stats_kernel, ub + sb, 128, 0, ub, x, ldx, ds, K, B, n,
                ms.members.p, ms.offsets.p, dist ? sums.p : centroids, dists.p, losses.p, radius.p,
-               last_row.p, active_d.p, dist ? 0 : 1);
+               last_row.p, active_d.p, dist ? 0 : 1, warp_update);
     if (dist) {  // one exchange step per iteration over NVLink
       LB2_LAUNCH("kmeans_encode_last", encode_last_row_kernel, cdiv(BK, 256), 256, 0, last_row.p, BK,
                  (uint32_t)row_offset);

@@ -61,33 +61,32 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// slow path of a wait (kept out of line so the hot loops stay small): called every few thousand failed
+// polls; the first call records the start time, later calls compare against it
+static __device__ __noinline__ bool mbar_watchdog_tick(uint32_t bar, uint32_t parity, long long* t0) {
+#ifdef LB2_TC_WATCHDOG_SOFT
+  if (*(volatile int*)&g_wd_abort) return true;
+#endif
+  const long long now = clock64();
+  if (*t0 == 0) { *t0 = now; return false; }
+  if (now - *t0 > 8000000000ll) { mbar_watchdog_report(bar, parity); return true; }
+  return false;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try(bar, parity)) return;
-  const long long t0 = clock64();
+  long long t0 = 0;
   for (uint32_t spins = 1;; ++spins) {
     if (mbar_try(bar, parity)) return;
-    if ((spins & 0xFFFu) == 0) {
-#ifdef LB2_TC_WATCHDOG_SOFT
-      if (*(volatile int*)&g_wd_abort) return;
-#endif
-      if (clock64() - t0 > 8000000000ll) { mbar_watchdog_report(bar, parity); return; }
-    }
+    if ((spins & 0x3FFFu) == 0 && mbar_watchdog_tick(bar, parity, &t0)) return;
   }
 }
 // same, for the single-thread producer / issuer roles: back off between polls so that the spin
 // loop does not steal issue slots from the epilogue warps sharing the scheduler
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-  if (mbar_try(bar, parity)) return;
-  const long long t0 = clock64();
+  long long t0 = 0;
   for (uint32_t spins = 1;; ++spins) {
     if (mbar_try(bar, parity)) return;
     __nanosleep(40);
-    if ((spins & 0xFFu) == 0) {
-#ifdef LB2_TC_WATCHDOG_SOFT
-      if (*(volatile int*)&g_wd_abort) return;
-#endif
-      if (clock64() - t0 > 8000000000ll) { mbar_watchdog_report(bar, parity); return; }
-    }
+    if ((spins & 0x3FFu) == 0 && mbar_watchdog_tick(bar, parity, &t0)) return;
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
@@ -152,33 +151,49 @@ __device__ __forceinline__ void top3_insert(float g, float& m1, float& m2, float
   m2 = fmaxf(m2, t1);
   m3 = fmaxf(m3, t2);
 }
-// insert TWO values into the triple with 9 min/max ops (FMNMX / FMNMX3 run on the half-rate ALU
-// pipe, which is what bounds this epilogue): sort the pair, then merge (hi >= lo) into (m1,m2,m3)
-__device__ __forceinline__ void top3_insert2(float g0, float g1, float& m1, float& m2, float& m3) {
-  const float hi = fmaxf(g0, g1), lo = fminf(g0, g1);
-  const float a = fminf(m1, hi);          // loser of the top comparison
-  const float bq = fmaxf(m2, lo);
-  const float c = fminf(m2, lo);
-  m1 = fmaxf(m1, hi);
-  m2 = fmaxf(a, bq);
-  m3 = fmaxf(fmaxf(m3, fminf(a, bq)), c);  // -> FMNMX3
-}
-// top-3 (values carry their column index in the low 8 mantissa bits) of one 32-column chunk.
-// C0 is a compile-time constant so that the index OR-ed into the mantissa is an immediate.
+// ---- top-3 of a 256-column accumulator row by TOURNAMENT ------------------------------------------
+// The epilogue is bound by the half-rate ALU pipe (FMNMX / FMNMX3 / PRMT), so what counts is min/max
+// instructions per column.  Pair the values: the winners (max) go on, and of the losers (min) only the
+// LARGEST can be among the row's top 3 -- a loser is beaten by its own partner, so two losers in the top
+// 3 would need four distinct values ahead of the smaller one.  (All values are distinct: each carries
+// its column index in the low mantissa byte.)  Applying this at every level,
+//     top3(row) = top3( top3(last-level winners)  U  { largest loser of each level } ),
+// i.e. per level one running FMNMX3 maximum over the losers plus one exact top-3 tracker fed by a single
+// value per 32-column chunk: 83 min/max instructions per chunk instead of 128.
+constexpr int TOUR_LEVELS = 5;
+
+// one 32-column chunk.  C0 is a compile-time constant so that the index OR-ed into the mantissa is an
+// immediate.  T = exact top-3 of the chunk winners so far, L[j] = largest level-j loser so far.
 template <int C0>
-__device__ __forceinline__ void top3_chunk(const uint32_t* v, const float* cn, float* a, float* b) {
+__device__ __forceinline__ void tour_chunk(const uint32_t* v, const float* cn, float* T, float* L) {
+  float g[32];
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    float g[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float f = __uint_as_float(v[j + u]) + cn[C0 + j + u];
-      // replace the low mantissa byte by the column index: one PRMT (byte permute) with an immediate
-      g[u] = __uint_as_float(__byte_perm(__float_as_uint(f), (uint32_t)(C0 + j + u), 0x3214));
-    }
-    top3_insert2(g[0], g[1], a[0], a[1], a[2]);  // two independent triples -> shorter dependent chains
-    top3_insert2(g[2], g[3], b[0], b[1], b[2]);
+  for (int u = 0; u < 32; ++u) {
+    const float f = __uint_as_float(v[u]) + cn[C0 + u];
+    // replace the low mantissa byte by the column index: one PRMT (byte permute) with an immediate
+    g[u] = __uint_as_float(__byte_perm(__float_as_uint(f), (uint32_t)(C0 + u), 0x3214));
   }
+#pragma unroll
+  for (int lvl = 0, cnt = 32; lvl < TOUR_LEVELS; ++lvl, cnt >>= 1) {
+    // cnt values in g[0..cnt) -> cnt/2 winners in g[0..cnt/2), losers folded into L[lvl]
+    float lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < cnt / 2) {
+        const float x = g[2 * i], y = g[2 * i + 1];
+        g[i] = fmaxf(x, y);
+        lo[i] = fminf(x, y);
+      }
+    }
+    if (cnt / 2 >= 2) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 2)
+        if (i < cnt / 2) L[lvl] = fmaxf(fmaxf(L[lvl], lo[i]), lo[i + 1]);  // -> FMNMX3
+    } else {
+      L[lvl] = fmaxf(L[lvl], lo[0]);
+    }
+  }
+  top3_insert(g[0], T[0], T[1], T[2]);
 }
 
 // top-3 of a 256-column accumulator row; the TMEM loads are software pipelined (the load of chunk
@@ -186,24 +201,26 @@ __device__ __forceinline__ void top3_chunk(const uint32_t* v, const float* cn, f
 __device__ __forceinline__ void top3_row256(uint32_t taddr, const float* cn, float& m1, float& m2, float& m3) {
   uint32_t va[32], vb[32];
   const float ninf = __int_as_float(0xff800000);
-  float a[3] = {ninf, ninf, ninf}, b[3] = {ninf, ninf, ninf};
+  float T[3] = {ninf, ninf, ninf};
+  float L[TOUR_LEVELS];
+#pragma unroll
+  for (int j = 0; j < TOUR_LEVELS; ++j) L[j] = ninf;
   tmem_ld32(taddr, va);
 #define LB2_TOP3_STEP(C)                                   \
   tmem_wait_ld(va);                                        \
   tmem_ld32(taddr + (C) + 32, vb);                         \
-  top3_chunk<(C)>(va, cn, a, b);                           \
+  tour_chunk<(C)>(va, cn, T, L);                           \
   tmem_wait_ld(vb);                                        \
   if ((C) + 64 < TN) tmem_ld32(taddr + (C) + 64, va);      \
-  top3_chunk<(C) + 32>(vb, cn, a, b);
+  tour_chunk<(C) + 32>(vb, cn, T, L);
   LB2_TOP3_STEP(0)
   LB2_TOP3_STEP(64)
   LB2_TOP3_STEP(128)
   LB2_TOP3_STEP(192)
 #undef LB2_TOP3_STEP
-  m1 = a[0]; m2 = a[1]; m3 = a[2];
-  top3_insert(b[0], m1, m2, m3);
-  top3_insert(b[1], m1, m2, m3);
-  top3_insert(b[2], m1, m2, m3);
+  m1 = T[0]; m2 = T[1]; m3 = T[2];
+#pragma unroll
+  for (int j = 0; j < TOUR_LEVELS; ++j) top3_insert(L[j], m1, m2, m3);
 }
 
 }  // namespace tc

@@ -235,7 +235,7 @@ top3_row256(taddr, cn, m1, m2, m3);
             float best_val = 0.0f;
             bool ok = true;
             if (flag == 2) {
-              fb_pairs[atomicAdd(fb_count, 1u)] = (uint32_t)(row * M + m);
+              fb_pairs[(size_t)m * n + atomicAdd(fb_count + m, 1u)] = (uint32_t)row;  // per-sub-space list
             } else if (TRAIN || flag == 1) {
               // exact, reference-order distance(s) from the operands still in shared memory
               const float4 r0 = *swz(atile, rl, j * 2), r1 = *swz(atile, rl, j * 2 + 1);
@@ -290,7 +290,7 @@ __global__ void prep_codebook_kernel(const float* __restrict__ cb, int M, int d,
                                      uint32_t* __restrict__ fb_count) {
   __shared__ float s_n2[TN];
   const int m = blockIdx.x, c = threadIdx.x;  // grid M, block 256
-  if (m == 0 && c == 0) *fb_count = 0;
+  if (c == 0) fb_count[m] = 0;  // one undecided-row list per sub-space
   const float* src = cb + ((size_t)m * TN + c) * DS;
   float n2 = 0.0f;
 #pragma unroll
@@ -334,33 +334,44 @@ __global__ void residual_norms_kernel(const float* x, const float* __restrict__ 
   rn2[g] = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
 }
 
-// exact scan of all 256 codewords for the (row, sub-space) pairs the filter could not decide:
-// half-warp per pair, lane l scans codewords l, l+16, ... (ascending), lexicographic (value, index) min
+// exact scan of all 256 codewords for the (row, sub-space) pairs the filter could not decide.  The
+// filter appends the rows to one list per sub-space, so a CTA stages that sub-space's codebook (8 KB)
+// in shared memory once and serves its share of the list from there: half-warp per pair, lane l scans
+// codewords l, l+16, ... (ascending), lexicographic (value, index) min.
 template <bool TRAIN>
 __global__ void __launch_bounds__(256)
 pq_fallback_kernel(const float* __restrict__ r, uint64_t n, int M, const float* __restrict__ cb,
                    const uint32_t* __restrict__ pairs, const uint32_t* __restrict__ count,
                    const uint8_t* __restrict__ row_valid, uint8_t* __restrict__ codes,
                    uint32_t* __restrict__ ids, float* __restrict__ dists, uint8_t* __restrict__ valid) {
-  const uint32_t total = *count;
+  __shared__ __align__(16) float cbs[TN * DS];
+  const int m = blockIdx.x;
+  const uint32_t total = count[m];
+  if (blockIdx.y * 16u >= total) return;  // uniform
+  {
+    const float4* src = reinterpret_cast<const float4*>(cb + (size_t)m * TN * DS);
+    float4* dst = reinterpret_cast<float4*>(cbs);
+    for (int i = threadIdx.x; i < TN * DS / 4; i += 256) dst[i] = src[i];
+  }
+  __syncthreads();
   const int l = threadIdx.x & 15;
   const unsigned mask = 0xffffu << (16 * ((threadIdx.x >> 4) & 1));
-  for (uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4; p < total;
-       p += ((uint64_t)gridDim.x * blockDim.x) >> 4) {
-    const uint32_t pr = pairs[p];
-    const uint64_t row = pr / M;
-    const int m = pr % M;
+  const uint32_t* list = pairs + (size_t)m * n;
+  for (uint32_t p = blockIdx.y * 16u + (threadIdx.x >> 4); p < total; p += gridDim.y * 16u) {
+    const uint64_t row = list[p];
     const float* rp = r + row * (uint64_t)(M * DS) + m * DS;
-    float rv[DS];
-#pragma unroll
-    for (int t = 0; t < DS; ++t) rv[t] = rp[t];
+    const float4 r0 = reinterpret_cast<const float4*>(rp)[0], r1 = reinterpret_cast<const float4*>(rp)[1];
+    const float rv[DS] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
     float bv = __int_as_float(0x7f800000);
     uint32_t bi = 0xffffffffu;
+#pragma unroll 4
     for (int c = l; c < TN; c += 16) {
-      const float* cp = cb + ((size_t)m * TN + c) * DS;
+      const float4 c0 = reinterpret_cast<const float4*>(cbs + c * DS)[0];
+      const float4 c1 = reinterpret_cast<const float4*>(cbs + c * DS)[1];
+      const float cv[DS] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
       float s = 0.0f;
 #pragma unroll
-      for (int t = 0; t < DS; ++t) s = f_add(s, sq_diff(rv[t], cp[t]));
+      for (int t = 0; t < DS; ++t) s = f_add(s, sq_diff(rv[t], cv[t]));
       const float v = f_add(s, 0.0f);
       if (v < bv) { bv = v; bi = c; }
     }
@@ -396,7 +407,7 @@ void tc_pq_prepare(const float* codebook, int M, int d, TcPqWorkspace* ws) {
   using namespace tcpq;
   if (ws->bm.n < (size_t)tc::TN * d) ws->bm.alloc((size_t)tc::TN * d);
   if (ws->cnh.n < (size_t)M * tc::TN + M) ws->cnh.alloc((size_t)M * tc::TN + M);
-  if (ws->fb_count.n < 1) ws->fb_count.alloc(1);
+  if (ws->fb_count.n < (size_t)M) ws->fb_count.alloc(M);
   LB2_LAUNCH("tc_pq_prep_codebook", prep_codebook_kernel, M, tc::TN, 0, codebook, M, d, ws->bm.p,
              ws->cnh.p, ws->cnh.p + (size_t)M * tc::TN, ws->fb_count.p);
 }
@@ -419,7 +430,8 @@ void tc_pq_assign(const float* r, const float* rn2, uint64_t n, int d, int M, co
   const unsigned grid = (unsigned)std::min<uint64_t>(tiles * nkc, (uint64_t)ctx().num_sms);
   const float* cnh = ws->cnh.p;
   const float* cbmax2 = ws->cnh.p + (size_t)M * tc::TN;
-  const unsigned fb_grid = (unsigned)std::min<uint64_t>(cdiv(n * M * 16, 256), (uint64_t)ctx().num_sms * 8);
+  // per sub-space: enough CTAs (16 pairs per pass each) for the worst case, capped; idle ones exit at once
+  const dim3 fb_grid((unsigned)M, (unsigned)std::min<uint64_t>(cdiv(n, 16), std::max(1, 8 * ctx().num_sms / M)));
 #define LB2_PQ_FILTER(TRAINV, STREAMV)                                                                      \
   do {                                                                                                      \
     set_smem(tc_pq_kernel<TRAINV, STREAMV>, smem);                                                          \
@@ -438,9 +450,11 @@ void tc_pq_assign(const float* r, const float* rn2, uint64_t n, int d, int M, co
   }
 #undef LB2_PQ_FILTER
   if (getenv("LB2_TC_STATS") && *getenv("LB2_TC_STATS")) {
-    uint32_t c = 0;
-    d2h(&c, ws->fb_count.p, 1);
+    std::vector<uint32_t> cm(M);
+    d2h(cm.data(), ws->fb_count.p, M);
     sync_stream();
+    uint64_t c = 0;
+    for (int m = 0; m < M; ++m) c += cm[m];
     fprintf(stderr, "[lb2 tc_pq] n=%llu M=%d: exact-fallback pairs %.2f%%\n", (unsigned long long)n, M,
             100.0 * c / ((double)n * M));
   }
