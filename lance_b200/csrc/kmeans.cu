@@ -298,24 +298,35 @@ __device__ __forceinline__ void update_body_warp(size_t w, float* tile, const fl
   const uint32_t* mem = members + (size_t)b * n;
   const float* col = x + (size_t)b * ds + c * 8;
   float acc = 0.0f;
-  for (uint32_t base = s; base < e; base += UPD_TILE) {
-    const uint32_t cnt = min((uint32_t)UPD_TILE, e - base);
-    uint32_t r[UPD_TILE / 32];
+  constexpr int UU = UPD_TILE / 32;
+  float4 pa[UU], pb[UU];  // the next tile's rows, fetched while the current tile is being summed
+  auto fetch = [&](uint32_t base) {
+    uint32_t r[UU];
 #pragma unroll
-    for (int u = 0; u < UPD_TILE / 32; ++u) {
+    for (int u = 0; u < UU; ++u) {
       const uint32_t j = base + u * 32 + lane;
       r[u] = j < e ? mem[j] : 0xffffffffu;
     }
 #pragma unroll
-    for (int u = 0; u < UPD_TILE / 32; ++u) {
+    for (int u = 0; u < UU; ++u) {
       if (r[u] != 0xffffffffu) {
         const float4* src = reinterpret_cast<const float4*>(col + (size_t)r[u] * ldx);
-        float4* dst = reinterpret_cast<float4*>(tile + (u * 32 + lane) * 8);
-        dst[0] = src[0];
-        dst[1] = src[1];
+        pa[u] = src[0];
+        pb[u] = src[1];
       }
     }
+  };
+  if (s < e) fetch(s);
+  for (uint32_t base = s; base < e; base += UPD_TILE) {
+    const uint32_t cnt = min((uint32_t)UPD_TILE, e - base);
+#pragma unroll
+    for (int u = 0; u < UU; ++u) {
+      float4* dst = reinterpret_cast<float4*>(tile + (u * 32 + lane) * 8);
+      dst[0] = pa[u];
+      dst[1] = pb[u];
+    }
     __syncwarp();
+    if (base + UPD_TILE < e) fetch(base + UPD_TILE);
     if (lane < 8) {
       uint32_t q = 0;
       for (; q + 8 <= cnt; q += 8) {
@@ -352,15 +363,44 @@ __device__ __forceinline__ void stats_body(int w, const float* __restrict__ dist
   const float* dv = dists + (size_t)b * n;
   double loss = 0.0;
   float rad = 0.0f;
-  for (uint32_t base = s; base < e; base += 32) {
-    const uint32_t j = base + lane;
-    const float v = j < e ? dv[mem[j]] : 0.0f;
-    const int cnt = min(32u, e - base);
-    for (int q = 0; q < cnt; ++q) {
-      const float u = __shfl_sync(0xffffffffu, v, q);
-      loss += (double)u;
-      rad = fmaxf(rad, u);  // f32::max ignores NaN like fmaxf; dists of members are never NaN
+  // 256 members per round, the NEXT round's (index, distance) gathers in flight while this round's
+  // values are folded in member order: the only serial work left is the f64 add chain itself
+  constexpr int SU = 8;
+  float cur[SU], nxt[SU];
+#pragma unroll
+  for (int u = 0; u < SU; ++u) {
+    const uint32_t j = s + u * 32 + lane;
+    cur[u] = j < e ? dv[mem[j]] : 0.0f;
+  }
+  for (uint32_t base = s; base < e; base += SU * 32) {
+#pragma unroll
+    for (int u = 0; u < SU; ++u) {
+      const uint32_t j = base + (SU + u) * 32 + lane;
+      nxt[u] = j < e ? dv[mem[j]] : 0.0f;
     }
+#pragma unroll
+    for (int u = 0; u < SU; ++u) {
+      const uint32_t b0 = base + u * 32;
+      if (b0 < e) {  // uniform
+        const int cnt = min(32u, e - b0);
+        if (cnt == 32) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const float v = __shfl_sync(0xffffffffu, cur[u], q);
+            loss += (double)v;
+            rad = fmaxf(rad, v);  // f32::max ignores NaN like fmaxf; dists of members are never NaN
+          }
+        } else {
+          for (int q = 0; q < cnt; ++q) {
+            const float v = __shfl_sync(0xffffffffu, cur[u], q);
+            loss += (double)v;
+            rad = fmaxf(rad, v);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < SU; ++u) cur[u] = nxt[u];
   }
   if (lane == 0) {
     losses[w] = loss;
