@@ -277,16 +277,45 @@ __device__ __forceinline__ void update_body(size_t g, const float* __restrict__ 
   centroids[g] = acc;
 }
 
-// The same update for ds % 8 == 0, one WARP per (b, cluster, 8-dim chunk): the 32 lanes fetch 128 member
-// rows at a time (index load + 32-byte gather, all independent -> one memory round trip per 128
-// members instead of one per 16), park them in shared memory, then lanes 0..7 add their dimension in
-// member order.  The f32 sums are the same sequential sums as update_body's.
+// ---- order-independent sums -------------------------------------------------------------------
+// The reference adds a cluster's members one after the other (f32 centroid sums, f64 loss), and a
+// floating-point sum depends on that order -- unless no addition rounds.  If every term is an integer
+// multiple of 2^g and sum|term| < 2^(g+p) (p = 24 for f32, 53 for f64), every partial sum of ANY
+// association is such a multiple below 2^(g+p), hence exactly representable: all orders give the same
+// bits.  g = min over the non-zero terms of (unbiased exponent - 23 + trailing zeros of the 24-bit
+// significand).  The kernels below test this per cluster (with one bit of margin, the bound itself
+// being computed in floating point) and then reduce in parallel; otherwise they run the sequential
+// chain.  Integer-valued columns (SIFT, u8) pass for the centroid sums, distances nearly always
+// pass for the f64 loss; a per-problem hint stops retrying once a problem's data has failed.
+__device__ __forceinline__ int pow2_granule(float v, bool& bad) {
+  const uint32_t bits = __float_as_uint(v) & 0x7fffffffu;
+  if (bits == 0) return 0x7fffffff;  // zero is a multiple of everything
+  uint32_t ex = bits >> 23;
+  if (ex == 255) { bad = true; return 0x7fffffff; }
+  uint32_t mant = bits & 0x7fffffu;
+  if (ex) mant |= 0x800000u; else ex = 1;
+  return (int)ex - 150 + (__ffs((int)mant) - 1);
+}
+__device__ __forceinline__ double pow2_f64(int e) {  // 2^e, -1022 <= e <= 1023
+  return __longlong_as_double((long long)(e + 1023) << 52);
+}
+__device__ __forceinline__ float pow2_f32(int e) {  // 2^e clamped to the normal f32 range
+  e = max(-126, min(127, e));
+  return __int_as_float((e + 127) << 23);
+}
+
+// The centroid update for ds % 8 == 0, one WARP per (b, cluster, 8-dim chunk).
+//   fast path (see above): lanes stride the members, private f32 sums, one warp reduction;
+//   sequential path: the 32 lanes fetch 128 member rows at a time (index load + 32-byte gather, all
+//   independent -> one memory round trip per 128 members instead of one per 16), park them in shared
+//   memory, then lanes 0..7 add their dimension in member order -- update_body's sums exactly.
 constexpr int UPD_TILE = 128;
 __device__ __forceinline__ void update_body_warp(size_t w, float* tile, const float* __restrict__ x, int ldx, int ds,
                                                  int K, int B, uint64_t n, const uint32_t* __restrict__ members,
                                                  const uint32_t* __restrict__ offsets,
                                                  float* __restrict__ centroids,
-                                                 const uint8_t* __restrict__ active, int scale) {
+                                                 const uint8_t* __restrict__ active, int scale,
+                                                 uint8_t* __restrict__ exact_hint) {
   const int lane = threadIdx.x & 31;
   const int nch = ds >> 3;
   if (w >= (size_t)B * K * nch) return;
@@ -297,6 +326,70 @@ __device__ __forceinline__ void update_body_warp(size_t w, float* tile, const fl
   const uint32_t s = off[k], e = off[k + 1];
   const uint32_t* mem = members + (size_t)b * n;
   const float* col = x + (size_t)b * ds + c * 8;
+  float* out = centroids + ((size_t)b * K + k) * ds + c * 8;
+  const float inv = (scale && e > s) ? __fdiv_rn(1.0f, (float)(e - s)) : 1.0f;  // kmeans.rs:414-416
+  const bool do_scale = scale && e > s;
+
+  if (e - s >= 64 && exact_hint[b]) {  // ---- fast path: only worth it for long chains
+    float sum[8], asum[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { sum[t] = 0.0f; asum[t] = 0.0f; }
+    int g = 0x7fffffff;
+    bool bad = false;
+    for (uint32_t j0 = s; j0 < e; j0 += 128) {
+      float4 va[4], vb[4];
+      bool have[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t j = j0 + u * 32 + lane;
+        have[u] = j < e;
+        if (have[u]) {
+          const float4* src = reinterpret_cast<const float4*>(col + (size_t)mem[j] * ldx);
+          va[u] = src[0];
+          vb[u] = src[1];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (have[u]) {
+          const float v[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            sum[t] += v[t];
+            asum[t] += fabsf(v[t]);
+            g = min(g, pow2_granule(v[t], bad));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        sum[t] += __shfl_xor_sync(0xffffffffu, sum[t], o);
+        asum[t] += __shfl_xor_sync(0xffffffffu, asum[t], o);
+      }
+      g = min(g, __shfl_xor_sync(0xffffffffu, g, o));
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    float amax = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) amax = fmaxf(amax, asum[t]);
+    // exact iff every sum|.| < 2^(g+24); one bit of margin; g + 23 must be a normal f32 exponent
+    const bool exact = !bad && (g == 0x7fffffff || (g + 23 >= -126 && g + 23 <= 127 && amax < pow2_f32(g + 23)));
+    if (exact) {
+      if (lane < 8) {
+        float r = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          if (lane == t) r = sum[t];
+        out[lane] = do_scale ? __fmul_rn(r, inv) : r;
+      }
+      return;
+    }
+    if (lane == 0) exact_hint[b] = 0;  // this problem's data is not of the exact kind: stop trying
+  }
+
   float acc = 0.0f;
   constexpr int UU = UPD_TILE / 32;
   float4 pa[UU], pb[UU];  // the next tile's rows, fetched while the current tile is being summed
@@ -329,22 +422,18 @@ __device__ __forceinline__ void update_body_warp(size_t w, float* tile, const fl
     if (base + UPD_TILE < e) fetch(base + UPD_TILE);
     if (lane < 8) {
       uint32_t q = 0;
-      for (; q + 8 <= cnt; q += 8) {
-        float v[8];
+      for (; q + 16 <= cnt; q += 16) {  // 16 loads ahead of a 4-cycle add chain
+        float v[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = tile[(q + i) * 8 + lane];
+        for (int i = 0; i < 16; ++i) v[i] = tile[(q + i) * 8 + lane];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc = f_add(acc, v[i]);
+        for (int i = 0; i < 16; ++i) acc = f_add(acc, v[i]);
       }
       for (; q < cnt; ++q) acc = f_add(acc, tile[q * 8 + lane]);
     }
     __syncwarp();
   }
-  if (lane < 8) {
-    const uint32_t cnt = e - s;
-    if (scale && cnt > 0) acc = __fmul_rn(acc, __fdiv_rn(1.0f, (float)cnt));  // kmeans.rs:414-416
-    centroids[((size_t)b * K + k) * ds + c * 8 + lane] = acc;
-  }
+  if (lane < 8) out[lane] = do_scale ? __fmul_rn(acc, inv) : acc;
 }
 
 // per (b, cluster): f64 loss in row order, radius (max), last member row (kmeans.rs:266-280)
@@ -352,7 +441,7 @@ __device__ __forceinline__ void stats_body(int w, const float* __restrict__ dist
                              const uint32_t* __restrict__ members,
                              const uint32_t* __restrict__ offsets, double* __restrict__ losses,
                              float* __restrict__ radius, uint32_t* __restrict__ last_row,
-                             const uint8_t* __restrict__ active) {
+                             const uint8_t* __restrict__ active, uint8_t* __restrict__ loss_hint) {
   const int lane = threadIdx.x & 31;
   if (w >= B * K) return;
   const int b = w / K, k = w % K;
@@ -363,6 +452,44 @@ __device__ __forceinline__ void stats_body(int w, const float* __restrict__ dist
   const float* dv = dists + (size_t)b * n;
   double loss = 0.0;
   float rad = 0.0f;
+  if (e - s >= 64 && loss_hint[b]) {  // ---- order-independent f64 sum (see "order-independent sums")
+    double sd = 0.0, ad = 0.0;
+    float rm = 0.0f;
+    int g = 0x7fffffff;
+    bool bad = false;
+    for (uint32_t j0 = s; j0 < e; j0 += 256) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t j = j0 + u * 32 + lane;
+        v[u] = j < e ? dv[mem[j]] : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        sd += (double)v[u];
+        ad += (double)fabsf(v[u]);
+        rm = fmaxf(rm, v[u]);
+        g = min(g, pow2_granule(v[u], bad));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      sd += __shfl_xor_sync(0xffffffffu, sd, o);
+      ad += __shfl_xor_sync(0xffffffffu, ad, o);
+      rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, o));
+      g = min(g, __shfl_xor_sync(0xffffffffu, g, o));
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (!bad && (g == 0x7fffffff || ad < pow2_f64(g + 52))) {  // exact iff sum|.| < 2^(g+53); 1 bit margin
+      if (lane == 0) {
+        losses[w] = sd;
+        radius[w] = rm;
+        last_row[w] = mem[e - 1];
+      }
+      return;
+    }
+    if (lane == 0) loss_hint[b] = 0;
+  }
   // 256 members per round, the NEXT round's (index, distance) gathers in flight while this round's
   // values are folded in member order: the only serial work left is the f64 add chain itself
   constexpr int SU = 8;
@@ -417,17 +544,17 @@ update_stats_kernel(unsigned update_blocks, const float* __restrict__ x, int ldx
                     float* __restrict__ centroids, const float* __restrict__ dists,
                     double* __restrict__ losses, float* __restrict__ radius,
                     uint32_t* __restrict__ last_row, const uint8_t* __restrict__ active, int scale,
-                    int warp_update) {
+                    int warp_update, uint8_t* __restrict__ hints /* [2][B]: exact-sum hints */) {
   __shared__ __align__(16) float tiles[4][UPD_TILE * 8];
   if (blockIdx.x < update_blocks) {
     if (warp_update)
       update_body_warp((size_t)blockIdx.x * 4 + (threadIdx.x >> 5), tiles[threadIdx.x >> 5], x, ldx, ds, K, B, n,
-                       members, offsets, centroids, active, scale);
+                       members, offsets, centroids, active, scale, hints);
     else
       update_body((size_t)blockIdx.x * 128 + threadIdx.x, x, ldx, ds, K, B, n, members, offsets, centroids, active, scale);
   } else {
     stats_body((int)(((size_t)(blockIdx.x - update_blocks) * 128 + threadIdx.x) >> 5), dists, n, K, B,
-               members, offsets, losses, radius, last_row, active);
+               members, offsets, losses, radius, last_row, active, hints + B);
   }
 }
 
@@ -769,6 +896,8 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
   }
   DevBuf<float> sums;  // multi-GPU: per-rank partial centroid sums (all-reduced every iteration)
   if (dist) sums.alloc(BK * ds);
+  DevBuf<uint8_t> hints((size_t)2 * B);  // order-independent-sum hints (update, loss) per problem
+  LB2_CUDA(cudaMemsetAsync(hints.p, 1, (size_t)2 * B, ctx().stream));
   MemberSort ms;
   TcWorkspace tcws;
   TcPqWorkspace pqws;
@@ -799,7 +928,7 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
     const unsigned sb = cdiv((uint64_t)BK * 32, 128);
     LB2_LAUNCH("kmeans_update_stats", update_stats_kernel, ub + sb, 128, 0, ub, x, ldx, ds, K, B, n,
                ms.members.p, ms.offsets.p, dist ? sums.p : centroids, dists.p, losses.p, radius.p,
-               last_row.p, active_d.p, dist ? 0 : 1, warp_update);
+               last_row.p, active_d.p, dist ? 0 : 1, warp_update, hints.p);
     if (dist) {  // one exchange step per iteration over NVLink
       LB2_LAUNCH("kmeans_encode_last", encode_last_row_kernel, cdiv(BK, 256), 256, 0, last_row.p, BK,
                  (uint32_t)row_offset);
