@@ -926,6 +926,15 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
     const int warp_update = (ds % 8 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
     const unsigned ub = warp_update ? cdiv(BK * (uint64_t)(ds / 8), 4) : cdiv(BK * ds, 128);
     const unsigned sb = cdiv((uint64_t)BK * 32, 128);
+    static const bool split_us = getenv("LB2_SPLIT_UPDATE_STATS") && *getenv("LB2_SPLIT_UPDATE_STATS");
+    if (split_us) {  // diagnostics: time the two halves of the fused launch separately
+      LB2_LAUNCH("kmeans_update_only", update_stats_kernel, ub, 128, 0, ub, x, ldx, ds, K, B, n,
+                 ms.members.p, ms.offsets.p, dist ? sums.p : centroids, dists.p, losses.p, radius.p,
+                 last_row.p, active_d.p, dist ? 0 : 1, warp_update, hints.p);
+      LB2_LAUNCH("kmeans_stats_only", update_stats_kernel, sb, 128, 0, 0u, x, ldx, ds, K, B, n,
+                 ms.members.p, ms.offsets.p, dist ? sums.p : centroids, dists.p, losses.p, radius.p,
+                 last_row.p, active_d.p, dist ? 0 : 1, warp_update, hints.p);
+    } else
     LB2_LAUNCH("kmeans_update_stats", update_stats_kernel, ub + sb, 128, 0, ub, x, ldx, ds, K, B, n,
                ms.members.p, ms.offsets.p, dist ? sums.p : centroids, dists.p, losses.p, radius.p,
                last_row.p, active_d.p, dist ? 0 : 1, warp_update, hints.p);
