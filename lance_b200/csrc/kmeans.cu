@@ -285,8 +285,9 @@ __device__ __forceinline__ void update_body(size_t g, const float* __restrict__ 
 // bits.  g = min over the non-zero terms of (unbiased exponent - 23 + trailing zeros of the 24-bit
 // significand).  The kernels below test this per cluster (with one bit of margin, the bound itself
 // being computed in floating point) and then reduce in parallel; otherwise they run the sequential
-// chain.  Integer-valued columns (SIFT, u8) pass for the centroid sums, distances nearly always
-// pass for the f64 loss; a per-problem hint stops retrying once a problem's data has failed.
+// chain.  The f64 loss uses the general test (distances nearly always pass); the f32 centroid sums use
+// the special case g = 0 (integer-valued columns: SIFT, u8, quantised data), which costs three adds per
+// term to check.  A per-problem hint stops retrying once a problem's data has failed.
 __device__ __forceinline__ int pow2_granule(float v, bool& bad) {
   const uint32_t bits = __float_as_uint(v) & 0x7fffffffu;
   if (bits == 0) return 0x7fffffff;  // zero is a multiple of everything
@@ -298,10 +299,6 @@ __device__ __forceinline__ int pow2_granule(float v, bool& bad) {
 }
 __device__ __forceinline__ double pow2_f64(int e) {  // 2^e, -1022 <= e <= 1023
   return __longlong_as_double((long long)(e + 1023) << 52);
-}
-__device__ __forceinline__ float pow2_f32(int e) {  // 2^e clamped to the normal f32 range
-  e = max(-126, min(127, e));
-  return __int_as_float((e + 127) << 23);
 }
 
 // The centroid update for ds % 8 == 0, one WARP per (b, cluster, 8-dim chunk).
@@ -331,11 +328,12 @@ __device__ __forceinline__ void update_body_warp(size_t w, float* tile, const fl
   const bool do_scale = scale && e > s;
 
   if (e - s >= 64 && exact_hint[b]) {  // ---- fast path: only worth it for long chains
+    // Centroid sums: the cheap special case g = 0 -- every term an INTEGER (SIFT / u8 / quantised
+    // columns) and sum|term| < 2^23.  (v + 1.5*2^23) - 1.5*2^23 == v  <=>  v is an integer, for |v| < 2^22.
     float sum[8], asum[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) { sum[t] = 0.0f; asum[t] = 0.0f; }
-    int g = 0x7fffffff;
-    bool bad = false;
+    float dev = 0.0f;  // max |v - round(v)|: 0 iff all terms are integers
     for (uint32_t j0 = s; j0 < e; j0 += 128) {
       float4 va[4], vb[4];
       bool have[4];
@@ -355,28 +353,26 @@ __device__ __forceinline__ void update_body_warp(size_t w, float* tile, const fl
           const float v[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
-            sum[t] += v[t];
-            asum[t] += fabsf(v[t]);
-            g = min(g, pow2_granule(v[t], bad));
+            sum[t] = __fadd_rn(sum[t], v[t]);
+            asum[t] = __fadd_rn(asum[t], fabsf(v[t]));
+            const float rt = __fadd_rn(__fadd_rn(v[t], 12582912.0f), -12582912.0f);
+            dev = fmaxf(dev, fabsf(__fadd_rn(rt, -v[t])));
           }
         }
       }
     }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        sum[t] += __shfl_xor_sync(0xffffffffu, sum[t], o);
-        asum[t] += __shfl_xor_sync(0xffffffffu, asum[t], o);
-      }
-      g = min(g, __shfl_xor_sync(0xffffffffu, g, o));
-    }
-    bad = __any_sync(0xffffffffu, bad);
+    // sum over the lanes of each lane's largest |.| sum bounds every dimension's sum|term| from above
     float amax = 0.0f;
 #pragma unroll
     for (int t = 0; t < 8; ++t) amax = fmaxf(amax, asum[t]);
-    // exact iff every sum|.| < 2^(g+24); one bit of margin; g + 23 must be a normal f32 exponent
-    const bool exact = !bad && (g == 0x7fffffff || (g + 23 >= -126 && g + 23 <= 127 && amax < pow2_f32(g + 23)));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) sum[t] = __fadd_rn(sum[t], __shfl_xor_sync(0xffffffffu, sum[t], o));
+      amax = __fadd_rn(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      dev = fmaxf(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+    }
+    const bool exact = dev == 0.0f && amax < 8388608.0f;  // NaN / Inf terms fail the comparison
     if (exact) {
       if (lane < 8) {
         float r = 0.0f;
