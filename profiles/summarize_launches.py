@@ -14,7 +14,7 @@ for r in rows[hdr + 1:]:
         continue
     name = r[cols["Kernel Name"]]
     name = re.sub(r"\(.*", "", name).replace("void ", "").strip()
-    ours = "lb2::" in name or name.split("<")[0] in ()
+    ours = "lb2::" in name or name.startswith(("tc::", "tcpq::"))  # ncu drops the outer namespace of nested ones
     key = ("ours " if ours else "other ") + name[:110]
     agg[key][0] += 1
     agg[key][1] += float(r[cols["Metric Value"]].replace(",", "")) / 1e6
