@@ -239,6 +239,14 @@ KERNEL_BYTES = {
     "transform:pq_assign_exact": lambda ns, n: n * DIM * 4 + n * 4 + n * NUM_SUB_VECTORS,
 }
 
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
+# `ncu --set full` captures of the same kernels on the same workload (profiles/ncu_r01_summary_v2.txt)
+NCU_TRAFFIC = {
+    "pq_train:tc_pq_filter": 37_954_304 + 27_904,
+    "transform:tc_filter": 516_604_672 + 7_315_200,
+    "ivf_train:tc_filter": None,
+}
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -337,9 +345,19 @@ def main():
     alg_bytes = KERNEL_BYTES[dom](65536, n)
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": per_launch_ms,
-                "note": "dominant kernel of the build step by measured time; see DESIGN.md section 5"}
+                "note": "dominant kernel of the build step by measured time; its epilogue is bound by the "
+                        "half-rate ALU pipe (62 % busy in ncu), not by HBM: see DESIGN.md section 5"}
+    # the same figure for every tensor-path kernel of the step (the 1M-row transform kernels are the
+    # HBM-streaming ones)
+    roofline_all = []
+    for fam in sorted(f for f in fams if f in KERNEL_BYTES):
+        pl = fams[fam]["ms_per_step"] / fams[fam]["launches_per_step"]
+        ab = KERNEL_BYTES[fam](65536, n)
+        roofline_all.append({"kernel": fam, "avg_launch_ms": pl, "algorithmic_bytes_per_launch": ab,
+                             "achieved": ab / (pl * 1e-3) / 1e9, "frac": ab / (pl * 1e-3) / 1e9 / hbm_peak,
+                             "traffic": NCU_TRAFFIC.get(fam)})
 
     if args.only == "build":
         if rank == 0:
@@ -491,7 +509,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "build_phases_ms": {"ivf_train": stats.ms_ivf_train, "pq_train": stats.ms_pq_train, "transform": stats.ms_transform,
                                 "group": stats.ms_group, "ivf_iters": stats.ivf_iters, "pq_iters_max": stats.pq_iters_max},
-            "kernels": fams, "roofline": roofline, "query": query, "query_refine": query_refine, "query_batches": query_batches,
+            "kernels": fams, "roofline": roofline, "roofline_all": roofline_all, "query": query, "query_refine": query_refine, "query_batches": query_batches,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
