@@ -139,7 +139,8 @@ lb2_status lb2_pq_train(const void* data, uint64_t n, uint32_t d, lb2_dtype dtyp
 
 /* ProductQuantizer::quantize / transform_impl (pq.rs:116-191,430).  When `centroids` and
  * `part_ids` are given the residual (residual.rs:161-205) is fused: codes of v - centroids[part].
- * codes_out is row-major [n][M] (8-bit). */
+ * codes_out is row-major [n][M] (8-bit) or [n][M/2] (4-bit: byte i = code[2i+1] << 4 | code[2i],
+ * pq.rs:168-173; 16 codewords per sub-space, M even). */
 lb2_status lb2_pq_encode(const void* codebook, uint32_t num_sub_vectors, uint32_t num_bits,
                          uint32_t d, lb2_dtype dtype, lb2_metric metric, const void* centroids,
                          const uint32_t* part_ids, const void* vectors, uint64_t n,
@@ -155,6 +156,15 @@ lb2_status lb2_pq_build_lut(const void* codebook, uint32_t num_sub_vectors, uint
 lb2_status lb2_pq_scan(const float* lut, uint32_t num_sub_vectors, uint32_t num_bits,
                        lb2_metric metric, const uint8_t* codes_transposed, uint64_t n,
                        float* dists_out);
+
+/* 4-bit PQ: compute_pq_distance_4bit (pq/distance.rs:147-242) with PQDistCalculator::distance_all's
+ * Dot correction.  lut = M x 16 f32 (lb2_pq_build_lut with num_bits = 4), codes_transposed = packed
+ * [M/2][n].  The first min(max(200, k_hint), n) rows and the last n % 16 rows are exact f32 sums; the
+ * rest is the reference's u8-quantised table with saturating u8 accumulation, dequantised.  k_hint =
+ * the k of the search (DistCalculator::distance_all(k_hint), flat/index.rs:99). */
+lb2_status lb2_pq_scan_4bit(const float* lut, uint32_t num_sub_vectors, lb2_metric metric,
+                            const uint8_t* codes_transposed, uint64_t n, uint64_t k_hint,
+                            float* dists_out);
 
 /* FlatIndex::search fast path over a distance array (flat/index.rs:97-127): the k smallest
  * (distance, position) pairs; out sorted ascending by (distance, row id).  *count_out <= k. */

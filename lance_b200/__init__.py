@@ -276,7 +276,7 @@ class ProductQuantizer:
         centroids+part_ids the residual transform (residual.rs:161-205) is fused in."""
         vectors = _f32(vectors)
         n, d = vectors.shape
-        out = np.empty((n, self.num_sub_vectors), np.uint8)
+        out = np.empty((n, self.num_sub_vectors // 2 if self.num_bits == 4 else self.num_sub_vectors), np.uint8)
         cent = None if centroids is None else _f32(centroids)
         parts = None if part_ids is None else np.ascontiguousarray(part_ids, dtype=np.uint32)
         vp, _k1 = as_ptr(vectors)
@@ -309,6 +309,18 @@ def compute_pq_distance(distance_table, num_bits, num_sub_vectors, code_transpos
     check(lib().lb2_pq_scan(C.c_void_p(lut.ctypes.data), C.c_uint32(num_sub_vectors),
                             C.c_uint32(num_bits), C.c_int(_metric(distance_type)),
                             C.c_void_p(code.ctypes.data), C.c_uint64(n), C.c_void_p(out.ctypes.data)))
+    return out
+
+
+def compute_pq_distance_4bit(distance_table, num_sub_vectors, code_transposed, k_hint, distance_type="l2"):
+    """pq/distance.rs:147-242 on transposed packed codes [M/2][n]; distance_table [M][16]."""
+    lut = _f32(distance_table)
+    code = np.ascontiguousarray(code_transposed, dtype=np.uint8)
+    n = code.size // (num_sub_vectors // 2)
+    out = np.empty(n, np.float32)
+    check(lib().lb2_pq_scan_4bit(C.c_void_p(lut.ctypes.data), C.c_uint32(num_sub_vectors),
+                                 C.c_int(_metric(distance_type)), C.c_void_p(code.ctypes.data), C.c_uint64(n),
+                                 C.c_uint64(k_hint), C.c_void_p(out.ctypes.data)))
     return out
 
 

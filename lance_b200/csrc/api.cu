@@ -301,7 +301,8 @@ static void pq_train_dev(const float* data, uint64_t n, int d, int metric, const
                          float* codebook, std::vector<uint32_t>* iters) {
   const int M = p->num_sub_vectors, K = 1 << p->num_bits;
   LB2_REQUIRE(M > 0 && d % M == 0, "num_sub_vectors must divide vector dimension %d, but got %d", d, M);
-  if (p->num_bits != 8) fail(LB2_UNSUPPORTED, "num_bits %u is not implemented on the device", p->num_bits);
+  if (p->num_bits != 8 && p->num_bits != 4)  // pq/builder.rs: only 4 and 8 exist in the reference
+    fail(LB2_INVALID_ARG, "PQ: num_bits must be 4 or 8, got %u", p->num_bits);
   LB2_REQUIRE(current_comm() || n >= (uint64_t)K, "Not enough rows to train PQ. Requires %d rows but only %llu available",
               K, (unsigned long long)n);
   // free fn train_kmeans (kmeans.rs:1328-1340): first sample_rate*k rows (per-rank share when sharded)
@@ -605,14 +606,16 @@ lb2_status lb2_pq_encode(const void* codebook, uint32_t num_sub_vectors, uint32_
                          const uint32_t* part_ids, const void* vectors, uint64_t n,
                          uint8_t* codes_out) {
   LB2_API_BEGIN
-  if (num_bits != 8) fail(LB2_UNSUPPORTED, "num_bits %u is not implemented on the device", num_bits);
+  if (num_bits != 8 && num_bits != 4) fail(LB2_INVALID_ARG, "PQ: num_bits must be 4 or 8, got %u", num_bits);
   const int M = num_sub_vectors, ds = d / M;
   LB2_REQUIRE(M > 0 && d % M == 0, "num_sub_vectors must divide vector dimension %u, but got %d", d, M);
+  LB2_REQUIRE(num_bits == 8 || M % 2 == 0, "PQ: num_sub_vectors must be divisible by 2 for num_bits=4, but got %d", M);
   LB2_REQUIRE((centroids == nullptr) == (part_ids == nullptr),
               "centroids and part_ids must be given together");
+  const int ncode = 1 << num_bits;
   const int m = metric_of(metric) == METRIC_DOT ? METRIC_DOT : METRIC_L2;
   if (!small_d_supported(ds)) fail(LB2_UNSUPPORTED, "PQ sub-vector width %d not supported yet", ds);
-  VecIn cb(codebook, (size_t)256 * d, model_dtype(dtype)), x(vectors, (size_t)n * d, dtype);
+  VecIn cb(codebook, (size_t)ncode * d, model_dtype(dtype)), x(vectors, (size_t)n * d, dtype);
   uint64_t kmax = 0;
   VecIn c;
   InArg<uint32_t> p(part_ids, n);
@@ -628,8 +631,32 @@ lb2_status lb2_pq_encode(const void* codebook, uint32_t num_sub_vectors, uint32_
       c.set(centroids, (size_t)(kmax + 1) * d, model_dtype(dtype));
     }
   }
+  if (num_bits == 4) {  // 16 codewords per sub-space, two codes per byte (pq.rs:168-173)
+    OutArg<uint8_t> o4(codes_out, (size_t)n * (M / 2));
+    DevBuf<uint8_t> wide((size_t)n * M);
+    small_d_assign_f32(x.get(), n, d, M, ds, cb.get(), 16, m, c.get(), p.get(), nullptr, wide.p, nullptr, nullptr,
+                       nullptr, nullptr);
+    pack_nibbles(wide.p, n, M, o4.get());
+    o4.commit();
+    sync_stream();
+    return LB2_OK;
+  }
   OutArg<uint8_t> o(codes_out, (size_t)n * M);
   pq_encode_dev(x.get(), n, d, M, ds, cb.get(), m, c.get(), p.get(), nullptr, o.get());
+  o.commit();
+  sync_stream();
+  LB2_API_END
+}
+
+lb2_status lb2_pq_scan_4bit(const float* lut, uint32_t num_sub_vectors, lb2_metric metric,
+                            const uint8_t* codes_transposed, uint64_t n, uint64_t k_hint, float* dists_out) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(num_sub_vectors > 0 && num_sub_vectors % 2 == 0,
+              "PQ: num_sub_vectors must be divisible by 2 for num_bits=4, but got %u", num_sub_vectors);
+  InArg<float> l(lut, (size_t)num_sub_vectors * 16);
+  InArg<uint8_t> c(codes_transposed, (size_t)n * (num_sub_vectors / 2));
+  OutArg<float> o(dists_out, n);
+  pq_scan_4bit_f32(l.get(), num_sub_vectors, metric_of(metric), c.get(), n, k_hint, o.get());
   o.commit();
   sync_stream();
   LB2_API_END

@@ -1035,6 +1035,111 @@ void pq_scan_transposed_f32(const float* lut, int M, int metric, const uint8_t* 
              codes_t, n, metric == METRIC_DOT ? 1 : 0, out);
 }
 
+// ------------------------------------------------------------------------------------------------
+// a19  4-bit PQ scan: compute_pq_distance_4bit (pq/distance.rs:147-242).  lut = M x 16 f32, codes_t =
+// transposed packed codes [M/2][n] (low nibble = sub-vector 2i, high nibble = 2i+1).
+//   rows [0, flat_num) and the last n % 16 rows: exact f32, two adds per byte in byte order;
+//   the others: saturating u8 sum of the table quantised with qmin = min(table), qmax = max of the
+//   flat rows (total order), then q * ((qmax - qmin) / 255) + qmin.
+// ------------------------------------------------------------------------------------------------
+__global__ void pq4_flat_kernel(const float* __restrict__ lut, int nb, const uint8_t* __restrict__ codes_t,
+                                uint64_t n, uint64_t off, uint64_t len, float* __restrict__ out) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= len) return;
+  const uint64_t j = off + t;
+  float dist = 0.0f;
+  for (int i = 0; i < nb; ++i) {
+    const uint8_t c = codes_t[(size_t)i * n + j];
+    dist = f_add(dist, lut[(2 * i) * 16 + (c & 0xF)]);
+    dist = f_add(dist, lut[(2 * i + 1) * 16 + (c >> 4)]);
+  }
+  out[j] = dist;
+}
+// one block: qmax over the flat rows (total order), qmin over the table (f32::min ignores NaN), the u8 table
+__global__ void pq4_quantize_kernel(const float* __restrict__ lut, int M, const float* __restrict__ flat,
+                                    uint64_t flat_num, uint8_t* __restrict__ qt, float* __restrict__ params) {
+  __shared__ int32_t s_max[256];
+  __shared__ float s_min[256];
+  const int tid = threadIdx.x;
+  int32_t mx = (int32_t)0x80000000;
+  for (uint64_t j = tid; j < flat_num; j += 256) mx = max(mx, total_order_key(flat[j]));
+  float mn = __int_as_float(0x7f800000);
+  for (int i = tid; i < M * 16; i += 256) mn = fminf(mn, lut[i]);
+  s_max[tid] = mx;
+  s_min[tid] = mn;
+  __syncthreads();
+  for (int o = 128; o >= 1; o >>= 1) {
+    if (tid < o) {
+      s_max[tid] = max(s_max[tid], s_max[tid + o]);
+      s_min[tid] = fminf(s_min[tid], s_min[tid + o]);
+    }
+    __syncthreads();
+  }
+  const float qmax = key_to_float(s_max[0]), qmin = s_min[0];
+  const float factor = __fdiv_rn(255.0f, __fsub_rn(qmax, qmin));
+  for (int i = tid; i < M * 16; i += 256) {
+    const float v = roundf(__fmul_rn(__fsub_rn(lut[i], qmin), factor));  // f32::round: half away from zero
+    qt[i] = (v != v) ? 0 : v <= 0.0f ? 0 : v >= 255.0f ? 255 : (uint8_t)v;  // `as u8`: saturating, NaN -> 0
+  }
+  if (tid == 0) {
+    params[0] = qmin;
+    params[1] = __fdiv_rn(__fsub_rn(qmax, qmin), 255.0f);
+  }
+}
+__global__ void pq4_quant_scan_kernel(const uint8_t* __restrict__ qt, int nb, const uint8_t* __restrict__ codes_t,
+                                      uint64_t n, uint64_t begin, uint64_t end,
+                                      const float* __restrict__ params, float* __restrict__ out) {
+  extern __shared__ uint8_t s_qt[];
+  for (int i = threadIdx.x; i < nb * 32; i += blockDim.x) s_qt[i] = qt[i];
+  __syncthreads();
+  const uint64_t j = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= end) return;
+  uint32_t q = 0;  // saturating u8 adds of non-negative terms == min(255, sum)
+  for (int i = 0; i < nb; ++i) {
+    const uint8_t c = codes_t[(size_t)i * n + j];
+    q += s_qt[(2 * i) * 16 + (c & 0xF)];
+    q += s_qt[(2 * i + 1) * 16 + (c >> 4)];
+  }
+  q = min(q, 255u);
+  out[j] = __fadd_rn(__fmul_rn((float)q, params[1]), params[0]);
+}
+__global__ void sub_scalar_kernel(float* __restrict__ v, uint64_t n, float s) {
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) v[j] = __fsub_rn(v[j], s);
+}
+void pq_scan_4bit_f32(const float* lut, int M, int metric, const uint8_t* codes_t, uint64_t n, uint64_t k_hint,
+                      float* out) {
+  if (n == 0) return;
+  const int nb = M / 2;
+  k_hint = std::min<uint64_t>(k_hint, n);
+  const uint64_t flat_num = std::min<uint64_t>(std::max<uint64_t>(200, k_hint), n);  // FLAT_NUM_4BIT_PQ = 200
+  const uint64_t rem = n % 16;
+  LB2_LAUNCH("pq4_flat", pq4_flat_kernel, cdiv(flat_num, 256), 256, 0, lut, nb, codes_t, n, (uint64_t)0, flat_num, out);
+  DevBuf<uint8_t> qt((size_t)M * 16);
+  DevBuf<float> params(2);
+  LB2_LAUNCH("pq4_quantize", pq4_quantize_kernel, 1, 256, 0, lut, M, (const float*)out, flat_num, qt.p, params.p);
+  if (n - rem > flat_num)
+    LB2_LAUNCH("pq4_scan", pq4_quant_scan_kernel, cdiv(n - rem - flat_num, 256), 256, (size_t)M * 16, qt.p, nb,
+               codes_t, n, flat_num, n - rem, params.p, out);
+  if (rem > 0) {
+    const uint64_t off = std::max(n - rem, flat_num);
+    if (n > off) LB2_LAUNCH("pq4_flat", pq4_flat_kernel, cdiv(n - off, 256), 256, 0, lut, nb, codes_t, n, off, n - off, out);
+  }
+  if (metric == METRIC_DOT)
+    LB2_LAUNCH("pq4_dot_fix", sub_scalar_kernel, cdiv(n, 256), 256, 0, out, n, (float)M - 1.0f);
+  sync_stream();  // qt / params are freed on return
+}
+
+// two 4-bit codes per byte: (v[1] << 4) | v[0]  (pq.rs:168-173)
+__global__ void pack_nibbles_kernel(const uint8_t* __restrict__ codes, uint64_t total_bytes, uint8_t* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total_bytes) out[i] = (uint8_t)((codes[2 * i + 1] << 4) | (codes[2 * i] & 0xF));
+}
+void pack_nibbles(const uint8_t* codes, uint64_t n, int M, uint8_t* out) {
+  const uint64_t total = n * (uint64_t)(M / 2);
+  if (total) LB2_LAUNCH("pack_nibbles", pack_nibbles_kernel, cdiv(total, 256), 256, 0, codes, total, out);
+}
+
 void flat_topk_f32(const float* dists, const uint64_t* row_ids, uint64_t n, int k, uint64_t* out_id,
                    float* out_d, uint32_t* out_cnt) {
   if (k > 1024) fail(LB2_UNSUPPORTED, "k > 1024 is not implemented");

@@ -23,6 +23,9 @@ void build_lut_f32(const float* codebook, int M, int nbits, int d, int metric, c
                    float* lut);
 void pq_scan_transposed_f32(const float* lut, int M, int metric, const uint8_t* codes_t, uint64_t n,
                             float* out);
+void pq_scan_4bit_f32(const float* lut, int M, int metric, const uint8_t* codes_t, uint64_t n, uint64_t k_hint,
+                      float* out);
+void pack_nibbles(const uint8_t* codes, uint64_t n, int M, uint8_t* out);
 void flat_topk_f32(const float* dists, const uint64_t* row_ids, uint64_t n, int k, uint64_t* out_id,
                    float* out_d, uint32_t* out_cnt);
 }  // namespace lb2

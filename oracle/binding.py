@@ -282,6 +282,17 @@ def ivfpq_search(centroids, codebook, part_offsets, codes, row_ids, queries, k, 
     return oi, od, oc
 
 
+def pq_scan_4bit(lut, codes_t, n, k_hint, metric="l2"):
+    """compute_pq_distance_4bit (pq/distance.rs:147-242): lut [M][16] f32, codes_t [M/2][n] packed u8."""
+    lut = _f32(lut)
+    M = lut.size // 16
+    codes_t = np.ascontiguousarray(codes_t, dtype=np.uint8)
+    out = np.empty(n, np.float32)
+    lib().lo_pq_scan_4bit(_p(lut, C.c_float), C.c_uint64(M), _p(codes_t, C.c_uint8), C.c_uint64(n),
+                          C.c_uint64(k_hint), C.c_int(METRIC[metric]), _p(out, C.c_float))
+    return out
+
+
 def brute_force_topk(data, queries, k, metric="l2", nthreads=1):
     data, queries = _f32(data), _f32(queries)
     n, d = data.shape

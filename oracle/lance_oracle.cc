@@ -689,6 +689,69 @@ void lo_pq_scan(const float* lut, uint64_t M, const uint8_t* codes_t, uint64_t n
     for (uint64_t j = 0; j < n; ++j) dists[j] -= float(M) - 1.0f;
 }
 
+// a19  compute_pq_distance_4bit (pq/distance.rs:147-242) + quantize_distance_table (:284-295) +
+//   PQDistCalculator::distance_all's Dot fix-up (pq/storage.rs:957-958).
+//   lut: M x 16 f32; codes_t: TRANSPOSED packed codes [M/2][n], low nibble = sub-vector 2i, high nibble =
+//   sub-vector 2i+1 (pq.rs:168-173).  The first flat_num = min(max(200, k_hint), n) rows and the last
+//   n % 16 rows are exact f32 sums (two adds per byte, byte order); every other row is the SATURATING u8
+//   sum (u8x16 `+=` is _mm_adds_epu8, lance-linalg/src/simd/u8.rs:303-321) of the table quantised to
+//   u8 with qmin = min(table), qmax = max(first flat_num distances) (total order), dequantised as
+//   q * ((qmax - qmin) / 255) + qmin.
+void lo_pq_scan_4bit(const float* lut, uint64_t M, const uint8_t* codes_t, uint64_t n, uint64_t k_hint,
+                     int metric, float* dists) {
+  const uint64_t nb = M / 2;
+  for (uint64_t j = 0; j < n; ++j) dists[j] = 0.0f;
+  if (n == 0) return;
+  auto flat = [&](uint64_t off, uint64_t len) {
+    for (uint64_t i = 0; i < nb; ++i) {
+      const float* t0 = lut + (2 * i) * 16;
+      const float* t1 = lut + (2 * i + 1) * 16;
+      const uint8_t* c = codes_t + i * n;
+      for (uint64_t j = off; j < off + len; ++j) {
+        dists[j] += t0[c[j] & 0xF];
+        dists[j] += t1[c[j] >> 4];
+      }
+    }
+  };
+  k_hint = std::min<uint64_t>(k_hint, n);
+  const uint64_t flat_num = std::min<uint64_t>(std::max<uint64_t>(200, k_hint), n);
+  flat(0, flat_num);
+  float qmax = dists[0];
+  for (uint64_t j = 1; j < flat_num; ++j)  // max_by(total_cmp): the LAST maximum wins, same value either way
+    if (total_key(dists[j]) >= total_key(qmax)) qmax = dists[j];
+  float qmin = std::numeric_limits<float>::infinity();
+  for (uint64_t i = 0; i < M * 16; ++i) qmin = std::fmin(qmin, lut[i]);  // f32::min ignores NaN
+  const float factor = 255.0f / (qmax - qmin);
+  std::vector<uint8_t> qt(M * 16);
+  for (uint64_t i = 0; i < M * 16; ++i) {
+    const float v = std::round((lut[i] - qmin) * factor);  // f32::round: half away from zero
+    qt[i] = std::isnan(v) ? 0 : v <= 0.0f ? 0 : v >= 255.0f ? 255 : uint8_t(v);  // `as u8` saturates, NaN -> 0
+  }
+  const uint64_t rem = n % 16;
+  std::vector<uint8_t> q(n, 0);
+  for (uint64_t i = 0; i < nb; ++i) {
+    const uint8_t* t0 = qt.data() + (2 * i) * 16;
+    const uint8_t* t1 = qt.data() + (2 * i + 1) * 16;
+    const uint8_t* c = codes_t + i * n;
+    for (uint64_t j = 0; j < n - rem; ++j) {
+      unsigned a = q[j] + t0[c[j] & 0xF];
+      a = a > 255 ? 255 : a;
+      a += t1[c[j] >> 4];
+      q[j] = uint8_t(a > 255 ? 255 : a);
+    }
+  }
+  if (rem > 0) {
+    const uint64_t off = std::max(n - rem, flat_num);
+    flat(off, n - off);
+  }
+  const float range = (qmax - qmin) / 255.0f;
+  for (uint64_t j = flat_num; j < n - rem; ++j) dists[j] = float(q[j]) * range + qmin;
+  if (metric == 2) {
+    const float diff = float(M) - 1.0f;
+    for (uint64_t j = 0; j < n; ++j) dists[j] = dists[j] - diff;
+  }
+}
+
 // a16  FlatIndex::search fast path (flat/index.rs:97-127): size-k Rust BinaryHeap, push while
 //   len<k else replace the root iff root.dist > dist (total_cmp).  Output = heap's internal
 //   vector order (`into_iter`), unsorted.  Optional [lower, upper) range (flat/index.rs:101-115).

@@ -255,6 +255,35 @@ def test_index_search_matches_oracle(metric):
             assert np.all(np.diff(dists[i, :c]) >= 0)
 
 
+# ---- 4-bit PQ (a19): 16 codewords per sub-space, packed codes, u8-quantised table scan -----------
+@pytest.mark.parametrize("metric", ["l2", "dot"])
+def test_pq_4bit_train_encode_lut_scan_bit_exact(metric):
+    rng = np.random.default_rng(404)
+    n, d, M = 6000, 64, 16
+    data = synth.gaussian_mixture(n, d, n_components=32, seed=404)
+    if metric == "dot":
+        data /= np.linalg.norm(data, axis=1, keepdims=True)
+    init = np.stack([data[rng.choice(n, 16, replace=False)][:, m * 4:(m + 1) * 4] for m in range(M)])
+    pq = lb.PQBuildParams(M, 4, max_iters=12, codebook=init).build(data, metric)
+    cbo, iters_o = ob.pq_train(data, M, nbits=4, max_iters=12, init_codebook=init, metric=metric, nthreads=NT)
+    assert pq.codebook.shape == (M, 16, 4)
+    assert np.array_equal(pq.codebook, cbo) and np.array_equal(pq.train_iters.astype(np.int32), iters_o)
+    codes = pq.quantize(data)
+    assert codes.shape == (n, M // 2)
+    assert np.array_equal(codes, ob.pq_encode(cbo, data, nbits=4, metric=metric, nthreads=NT))
+    q = data[17] + 0.01
+    lut = lb.build_distance_table_l2(pq.codebook, 4, M, q, metric)
+    assert np.array_equal(lut, ob.build_lut(cbo, q, nbits=4, metric=metric))
+    for rows in (1, 50, 199, 200, 216, 1000, 4099):          # < 200: all flat; n % 16 != 0: exact remainder rows
+        ct = np.ascontiguousarray(codes[:rows].T)
+        for k_hint in (10, 300):
+            got = lb.compute_pq_distance_4bit(lut, M, ct, k_hint, metric)
+            want = ob.pq_scan_4bit(lut, ct, rows, k_hint, metric)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (rows, k_hint)
+    with pytest.raises(lb.LanceB200Error, match="divisible by 2"):
+        lb.ProductQuantizer(3, 4, 12, np.zeros((3, 16, 4), np.float32)).quantize(np.zeros((4, 12), np.float32))
+
+
 # ---- prefilter: PreFilter / RowIdMask (prefilter.rs:27-51, flat/index.rs:129-165) --------------
 @pytest.mark.parametrize("kind", ["pq", "flat"])
 def test_index_search_with_row_mask_matches_oracle(kind):
@@ -344,6 +373,48 @@ def test_unsupported_is_surfaced_not_masked():
     assert e.value.status == 2
     with pytest.raises(lb.LanceB200Error):
         lb.train_kmeans(np.zeros((10, 8), np.float32), 8, 20)
+
+
+def test_edge_cases_empty_ragged_and_error_messages():
+    rng = np.random.default_rng(77)
+    cent = rng.standard_normal((7, 24)).astype(np.float32)
+    # empty batch (transform.rs: empty record batches pass through)
+    p, dd, v = lb.compute_partitions(cent, np.zeros((0, 24), np.float32))
+    assert p.shape == (0,) and dd.shape == (0,) and v.shape == (0,)
+    # one row, K not a multiple of anything, d not a multiple of 16 (sequential tail of l2.rs:69-79)
+    x = rng.standard_normal((1, 24)).astype(np.float32)
+    p, dd, v = lb.compute_partitions(cent, x)
+    po, do, vo = ob.compute_membership(cent, x)
+    assert np.array_equal(p, po) and np.array_equal(dd, do)
+    # tiny index: more partitions than rows -> empty partitions; k larger than the probed rows
+    n, d, K, M = 40, 16, 8, 4
+    data = rng.standard_normal((n, d)).astype(np.float32)
+    cb = rng.standard_normal((M, 256, d // M)).astype(np.float32)
+    cents = data[:K].copy()
+    part, codes = lb.ivfpq_transform(cents, cb, data)[:2]
+    part = np.where(part == 3, 2, part).astype(np.uint32)      # partition 3 is empty
+    ix = lb.IvfPqIndex.from_parts(cents, cb, part, codes)
+    parts = ix.export()
+    assert parts["part_offsets"][4] == parts["part_offsets"][3]
+    q = rng.standard_normal((5, d)).astype(np.float32)
+    for k, nprobes in ((10, 1), (64, 8), (1, 3)):
+        ids, dists = ix.search(q, k=k, nprobes=nprobes)
+        oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
+                                     parts["row_ids"], q, k, nprobes)
+        for i in range(len(q)):
+            c = int(oc[i])
+            assert np.isinf(dists[i, c:]).all()
+            _check_topk(ids[i, :c], dists[i, :c], oi[i, :c], od[i, :c], k)
+    ids, dists = ix.search(np.zeros((0, d), np.float32), k=5, nprobes=2)   # empty query batch
+    assert ids.shape == (0, 5)
+    # the reference's error texts (kmeans.rs:1014-1022, pq/builder.rs:96-110) come back through lb2_last_error
+    with pytest.raises(lb.LanceB200Error, match="can not train 20 centroids with 10 vectors") as e:
+        lb.train_kmeans(np.zeros((10, 8), np.float32), 8, 20)
+    assert e.value.status == 1
+    with pytest.raises(lb.LanceB200Error, match="num_sub_vectors must divide vector dimension"):
+        lb.PQBuildParams(5, 8).build(np.zeros((300, 16), np.float32))
+    with pytest.raises(lb.LanceB200Error, match="nprobes"):
+        lb.kmeans_find_partitions(cent, x, 8)
 
 
 # ---- tensor-core filter path (tcgen05) must be bit-identical to the exact path -----------------

@@ -225,3 +225,35 @@ def test_masked_search_follows_row_id_mask_semantics():
         assert np.isin(base[0][i, :int(base[2][i])][keep], oi[i, :c]).all()
     none = ob.ivfpq_search(cent, cb, offs, codes[order], rid, q, 10, 3, allow=np.zeros(0, np.uint64))
     assert (none[2] == 0).all()
+
+
+def test_pq_scan_4bit_restatement_against_independent_numpy():
+    """compute_pq_distance_4bit (pq/distance.rs:147-242): flat rows exact, the rest through the
+    u8-quantised table with saturating adds (u8.rs:303-321) -- re-derived here in numpy."""
+    rng = np.random.default_rng(44)
+    M, n = 8, 1003
+    lut = (rng.random((M, 16)) * 50).astype(np.float32)
+    codes = rng.integers(0, 256, size=(n, M // 2), dtype=np.uint8)
+    ct = np.ascontiguousarray(codes.T)
+    lo, hi = codes & 0xF, codes >> 4
+    for k_hint in (10, 250):
+        got = ob.pq_scan_4bit(lut, ct, n, k_hint)
+        exact = np.zeros(n, np.float32)
+        for i in range(M // 2):
+            exact = (exact + lut[2 * i][lo[:, i]]).astype(np.float32)
+            exact = (exact + lut[2 * i + 1][hi[:, i]]).astype(np.float32)
+        flat_num = min(max(200, k_hint), n)
+        rem = n % 16
+        assert np.array_equal(got[:flat_num], exact[:flat_num]) and np.array_equal(got[n - rem:], exact[n - rem:])
+        qmax, qmin = exact[:flat_num].max(), lut.min()
+        factor = np.float32(255.0) / np.float32(qmax - qmin)
+        t = ((lut - qmin).astype(np.float32) * factor).astype(np.float32)
+        qt = np.clip(np.where(t >= 0, np.floor(t + np.float32(0.5)), 0), 0, 255).astype(np.int64)   # round half away
+        qsum = np.zeros(n, np.int64)
+        for i in range(M // 2):
+            qsum += qt[2 * i][lo[:, i]] + qt[2 * i + 1][hi[:, i]]
+        qsum = np.minimum(qsum, 255)
+        rng_ = np.float32(qmax - qmin) / np.float32(255.0)
+        want = (qsum.astype(np.float32) * rng_).astype(np.float32) + np.float32(qmin)
+        assert np.array_equal(got[flat_num:n - rem], want.astype(np.float32)[flat_num:n - rem])
+        assert (qsum[flat_num:n - rem] == 255).any()          # the saturating case is exercised
