@@ -368,9 +368,13 @@ def test_device_resident_inputs():
 
 
 def test_unsupported_is_surfaced_not_masked():
-    with pytest.raises(lb.LanceB200Error) as e:
-        lb.PQBuildParams(4, 4).build(np.zeros((300, 16), np.float32))
+    with pytest.raises(lb.LanceB200Error) as e:      # 4-bit PQ inside a device-resident index: not implemented
+        lb.IvfPqIndex.from_parts(np.zeros((2, 16), np.float32), np.zeros((4, 16, 4), np.float32),
+                                 np.zeros(4, np.uint32), np.zeros((4, 2), np.uint8), num_bits=4)
     assert e.value.status == 2
+    with pytest.raises(lb.LanceB200Error) as e:      # the reference only has 4 and 8 bits
+        lb.PQBuildParams(4, 6).build(np.zeros((300, 16), np.float32))
+    assert e.value.status == 1
     with pytest.raises(lb.LanceB200Error):
         lb.train_kmeans(np.zeros((10, 8), np.float32), 8, 20)
 
