@@ -877,7 +877,8 @@ __global__ void row_mask_kernel(const uint64_t* __restrict__ row_ids, uint64_t n
     sel = (!has_allow || sorted_contains(allow, n_allow, id)) && !(has_block && sorted_contains(block, n_block, id));
   }
   const unsigned bal = __ballot_sync(0xffffffffu, sel);
-  if ((threadIdx.x & 31) == 0) bitmap32[pos >> 5] = bal;
+  // the bitmap holds ceil(n / 64) u64 words; the last CTA may reach beyond it
+  if ((threadIdx.x & 31) == 0 && (pos >> 5) < ((n + 63) / 64) * 2) bitmap32[pos >> 5] = bal;
 }
 void row_mask_f32(const uint64_t* row_ids, uint64_t n, const uint64_t* allow, uint64_t n_allow, bool has_allow,
                   const uint64_t* block, uint64_t n_block, bool has_block, uint64_t* bitmap) {
