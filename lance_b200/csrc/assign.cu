@@ -56,9 +56,10 @@ assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* 
   float* xs = smem;              // [ROWS][d+1]
   float* cs = smem + ROWS * ld;  // [d][64]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const uint64_t row0 = (uint64_t)blockIdx.x * ROWS;
-  if (row0 >= n) return;
-
+  // grid-stride over row tiles: bulk launches give every CTA exactly one tile; row-list launches use a
+  // small persistent grid (the list length is only known on the device)
+  for (uint64_t row0 = (uint64_t)blockIdx.x * ROWS; row0 < n; row0 += (uint64_t)gridDim.x * ROWS) {
+  __syncthreads();  // the previous tile's readers are done with xs
   for (int idx = tid; idx < ROWS * d / 4; idx += 256) {  // float4 granules
     int r = (idx * 4) / d, e = (idx * 4) % d;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -138,7 +139,7 @@ assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* 
       }
     }
   }
-  if (WRITE_ALL) return;
+  if (WRITE_ALL) continue;
 #pragma unroll
   for (int i = 0; i < RT; ++i) {
 #pragma unroll
@@ -159,6 +160,7 @@ assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* 
       if (valid) valid[r] = ok ? 1 : 0;
     }
   }
+  }  // row tiles
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -285,8 +287,8 @@ generic_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __re
   __shared__ float red_val[16][R];
   __shared__ uint32_t red_idx[16][R];
   const int tid = threadIdx.x, hw = tid >> 4, l = tid & 15;
-  const uint64_t row0 = (uint64_t)blockIdx.x * R;
-  if (row0 >= n) return;
+  for (uint64_t row0 = (uint64_t)blockIdx.x * R; row0 < n; row0 += (uint64_t)gridDim.x * R) {  // see tile kernel
+  __syncthreads();
   for (int idx = tid; idx < R * d; idx += 256) {
     int r = idx / d, e = idx % d;
     const uint64_t src = row0 + r < n ? (row_list ? (uint64_t)row_list[row0 + r] : row0 + r) : 0;
@@ -328,7 +330,7 @@ generic_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __re
       if (key < bkey) { bkey = key; bval = mine; bidx = c; }
     }
   }
-  if (WRITE_ALL) return;
+  if (WRITE_ALL) continue;
   if (l < R) { red_key[hw][l] = bkey; red_val[hw][l] = bval; red_idx[hw][l] = bidx; }
   __syncthreads();
   if (tid < R) {
@@ -347,6 +349,7 @@ generic_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __re
       if (valid) valid[r] = ok ? 1 : 0;
     }
   }
+  }  // row groups
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -418,7 +421,8 @@ void assign_rows_f32(const float* x, uint64_t n_max, int d, const float* cent, i
     const size_t gsmem = sizeof(float) * 8 * (size_t)d;
     if (gsmem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "dimension %d too large for the exact kernel", d);
     set_smem(generic_kernel<METRIC_L2, false, 8>, gsmem);
-    LB2_LAUNCH("assign_exact_fallback", (generic_kernel<METRIC_L2, false, 8>), cdiv(n_max, 8), 256, gsmem, x,
+    LB2_LAUNCH("assign_exact_fallback", (generic_kernel<METRIC_L2, false, 8>),
+               (unsigned)std::min<uint64_t>(cdiv(n_max, 8), 8 * (uint64_t)ctx().num_sms), 256, gsmem, x,
                n_max, d, cent, K, bias_padded, part, dist, valid, nullptr, active, row_list, row_count);
     return;
   }
@@ -438,12 +442,14 @@ void assign_rows_f32(const float* x, uint64_t n_max, int d, const float* cent, i
   const size_t smem = sizeof(float) * (16 * (d + 1) + (size_t)d * 64);
   set_smem(assign_tile_kernel<METRIC_L2, false, 1>, smem);
   LB2_LAUNCH("assign_exact_fallback", (assign_tile_kernel<METRIC_L2, false, 1>),
-             cdiv(std::min<uint64_t>(n_max, split), 16), 256, smem, x, n_max, d, cT.get(), K, Kp, bias_padded,
+             (unsigned)std::min<uint64_t>(cdiv(std::min<uint64_t>(n_max, split), 16), 4 * (uint64_t)ctx().num_sms), 256,
+             smem, x, n_max, d, cT.get(), K, Kp, bias_padded,
              part, dist, valid, nullptr, active, row_list, row_count, 0u, split);
   if (n_max >= split) {
     const size_t smem4 = sizeof(float) * (64 * (d + 1) + (size_t)d * 64);
     set_smem(assign_tile_kernel<METRIC_L2, false, 4>, smem4);
-    LB2_LAUNCH("assign_exact_fallback", (assign_tile_kernel<METRIC_L2, false, 4>), cdiv(n_max, 64), 256, smem4,
+    LB2_LAUNCH("assign_exact_fallback", (assign_tile_kernel<METRIC_L2, false, 4>),
+               (unsigned)std::min<uint64_t>(cdiv(n_max, 64), 2 * (uint64_t)ctx().num_sms), 256, smem4,
                x, n_max, d, cT.get(), K, Kp, bias_padded, part, dist, valid, nullptr, active, row_list,
                row_count, split, 0xffffffffu);
   }

@@ -659,8 +659,9 @@ epilogue_kernel(int K, int ds, uint64_t n, float bf_param, double tolerance,
                 const float* __restrict__ radius, const uint32_t* __restrict__ last_row,
                 uint64_t* __restrict__ cluster_sizes, float* __restrict__ bias, int bias_ld,
                 float* __restrict__ centroids, LloydState* __restrict__ states,
-                uint8_t* __restrict__ active) {
+                uint8_t* __restrict__ active, TcPqPrepArgs pq_prep) {
   const int b = blockIdx.x, tid = threadIdx.x;
+  if (pq_prep.bm && tid == 0) pq_prep.fb_count[b] = 0;  // next iteration's undecided-row list (active or not)
   if (!active[b]) return;
   __shared__ int s_i, s_j;
   LloydState& st = states[b];
@@ -791,6 +792,11 @@ epilogue_kernel(int K, int ds, uint64_t n, float bf_param, double tolerance,
   if (bias)
     for (int k = tid; k < K; k += blockDim.x)
       bias[(size_t)b * bias_ld + k] = __fmul_rn(s_bf, (float)cs[k]);
+  if (pq_prep.bm) {  // PQ tensor path (K == 256 codewords x 8 dims, 256 threads): operands of the NEXT iteration
+    __shared__ float s_n2[256];
+    __syncthreads();  // the split above may have rewritten codewords
+    tc_pq_prep_block(cb, b, pq_prep, s_n2);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -899,9 +905,12 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
   TcPqWorkspace pqws;
   DevBuf<float> rn2;
   const bool pq_tc = small && ldx == B * ds && tc_pq_supported(n, ldx, B, ds, K, metric, x);
+  TcPqPrepArgs pq_prep;      // bm == nullptr unless the PQ tensor path is in use
+  bool pq_prepared = false;  // true once an epilogue has written the next iteration's operands
   if (pq_tc) {  // per-sub-space norms of the (fixed) training rows, once
     rn2.alloc(n * B);
     tc_pq_residual_norms(x, nullptr, nullptr, n, B, nullptr, rn2.p);
+    pq_prep = tc_pq_prep_args(B, ldx, &pqws);
   }
   sync_stream();
 
@@ -911,8 +920,11 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
       assign_f32_ex(x, n, ds, centroids, K, metric, bias.p, /*bias_padded=*/true, ids.p, dists.p,
                     valid.p, nullptr, active_d.p, &tcws);
     } else if (pq_tc) {
+      // the first call prepares the operands itself; afterwards the epilogue of iteration i has
+      // already written them for iteration i + 1
       tc_pq_assign(x, rn2.p, n, ldx, B, centroids, nullptr, nullptr, ids.p, dists.p, valid.p,
-                   active_d.p, &pqws);
+                   active_d.p, &pqws, /*prepared=*/pq_prepared);
+      pq_prepared = true;
     } else {
       small_d_assign_f32(x, n, ldx, B, ds, centroids, K, metric, nullptr, nullptr, nullptr, nullptr,
                          ids.p, dists.p, valid.p, active_d.p);
@@ -947,7 +959,7 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
     }
     LB2_LAUNCH("kmeans_epilogue", epilogue_kernel, B, 256, 0, K, ds, n_global, balance_factor_param,
                tolerance, ms.counts.p, losses.p, radius.p, last_row.p, cluster_sizes.p,
-               small ? nullptr : bias.p, Kp, centroids, states.p, active_d.p);
+               small ? nullptr : bias.p, Kp, centroids, states.p, active_d.p, pq_prep);
   };
   // The first iteration runs eagerly (allocates every workspace, sets kernel attributes); the
   // iteration is then captured ONCE into a CUDA graph and replayed, so that the loop is not bound

@@ -285,28 +285,12 @@ teardown:
 }
 
 // Bm[c][m*8+t] = cb[m][c][t];  cnh[m][c] = -|cb[m][c]|^2 / 2;  cbmax2[m] = max_c |cb[m][c]|^2
-__global__ void prep_codebook_kernel(const float* __restrict__ cb, int M, int d, float* __restrict__ bm,
-                                     float* __restrict__ cnh, float* __restrict__ cbmax2,
-                                     uint32_t* __restrict__ fb_count) {
+__global__ void __launch_bounds__(256)
+prep_codebook_kernel(const float* __restrict__ cb, TcPqPrepArgs a) {
   __shared__ float s_n2[TN];
-  const int m = blockIdx.x, c = threadIdx.x;  // grid M, block 256
-  if (c == 0) fb_count[m] = 0;  // one undecided-row list per sub-space
-  const float* src = cb + ((size_t)m * TN + c) * DS;
-  float n2 = 0.0f;
-#pragma unroll
-  for (int t = 0; t < DS; ++t) {
-    const float v = src[t];
-    bm[(size_t)c * d + m * DS + t] = v;
-    n2 += v * v;
-  }
-  cnh[m * TN + c] = -0.5f * n2;
-  s_n2[c] = n2;
-  __syncthreads();
-  if (c == 0) {
-    float mx = 0.0f;
-    for (int i = 0; i < TN; ++i) mx = fmaxf(mx, s_n2[i]);
-    cbmax2[m] = mx;
-  }
+  const int m = blockIdx.x;  // grid M, block 256
+  if (threadIdx.x == 0) a.fb_count[m] = 0;  // one undecided-row list per sub-space
+  tc_pq_prep_block(cb + (size_t)m * TN * DS, m, a, s_n2);
 }
 
 // (optional residual) + per-sub-space squared norms: one thread per (row, m)
@@ -403,26 +387,35 @@ bool tc_pq_supported(uint64_t n, int d, int M, int ds, int Kc, int metric, const
          n >= 256 && n * (uint64_t)M < (1ull << 32) && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
 }
 
-void tc_pq_prepare(const float* codebook, int M, int d, TcPqWorkspace* ws) {
-  using namespace tcpq;
+TcPqPrepArgs tc_pq_prep_args(int M, int d, TcPqWorkspace* ws) {
   if (ws->bm.n < (size_t)tc::TN * d) ws->bm.alloc((size_t)tc::TN * d);
   if (ws->cnh.n < (size_t)M * tc::TN + M) ws->cnh.alloc((size_t)M * tc::TN + M);
   if (ws->fb_count.n < (size_t)M) ws->fb_count.alloc(M);
-  LB2_LAUNCH("tc_pq_prep_codebook", prep_codebook_kernel, M, tc::TN, 0, codebook, M, d, ws->bm.p,
-             ws->cnh.p, ws->cnh.p + (size_t)M * tc::TN, ws->fb_count.p);
+  TcPqPrepArgs a;
+  a.bm = ws->bm.p;
+  a.cnh = ws->cnh.p;
+  a.cbmax2 = ws->cnh.p + (size_t)M * tc::TN;
+  a.fb_count = ws->fb_count.p;
+  a.d = d;
+  return a;
+}
+void tc_pq_prepare(const float* codebook, int M, int d, TcPqWorkspace* ws) {
+  using namespace tcpq;
+  const TcPqPrepArgs a = tc_pq_prep_args(M, d, ws);
+  LB2_LAUNCH("tc_pq_prep_codebook", prep_codebook_kernel, M, tc::TN, 0, codebook, a);
 }
 
 // r: residual (or raw) vectors [n][d] with their per-sub-space norms rn2 [n][M] already computed
 void tc_pq_assign(const float* r, const float* rn2, uint64_t n, int d, int M, const float* codebook,
                   const uint8_t* row_valid, uint8_t* codes, uint32_t* ids, float* dists,
-                  uint8_t* valid, const uint8_t* active, TcPqWorkspace* ws) {
+                  uint8_t* valid, const uint8_t* active, TcPqWorkspace* ws, bool prepared) {
   using namespace tcpq;
   const int nkc = M / 4;
   const bool stream = M > MAX_M_RESIDENT;
   const Layout L = layout(nkc, M, stream);
   const size_t smem = L.total + 1024;
   if (smem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "tc_pq: shared memory");
-  tc_pq_prepare(codebook, M, d, ws);  // also resets the fallback-pair counter
+  if (!prepared) tc_pq_prepare(codebook, M, d, ws);  // also resets the undecided-row lists
   if (ws->fb_pairs.n < n * M) ws->fb_pairs.alloc(n * M);
   const CUtensorMap map_r = make_map_2d(r, n, d, tc::TM);
   const CUtensorMap map_b = make_map_2d(ws->bm.p, tc::TN, d, tc::TN);
