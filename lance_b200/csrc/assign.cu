@@ -34,14 +34,17 @@ __global__ void transpose_pad_kernel(const float* __restrict__ c, int K, int d, 
 // ------------------------------------------------------------------------------------------------
 // RT = rows per thread (4: 64-row tiles for bulk work; 1: 16-row tiles so that a short row list
 // -- the tensor-core filter's ambiguous rows -- still spreads over all SMs)
-template <int METRIC, bool WRITE_ALL, int RT>
+// SPLIT (short row lists only): blockIdx.y selects ONE 64-centroid chunk, the partial (key, value, index)
+// of every row goes to split_out[(list position * gridDim.y + chunk) * 3 ..] and split_merge_kernel picks
+// the reference's winner -- the same work spread over gridDim.y times as many CTAs
+template <int METRIC, bool WRITE_ALL, int RT, bool SPLIT = false>
 __global__ void __launch_bounds__(256)
 assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __restrict__ cT,
                    int K, int Kp, const float* __restrict__ bias, uint32_t* __restrict__ part,
                    float* __restrict__ dist, uint8_t* __restrict__ valid,
                    float* __restrict__ all_out, const uint8_t* __restrict__ active,
                    const uint32_t* __restrict__ row_list, const uint32_t* __restrict__ row_count,
-                   uint32_t cnt_lo, uint32_t cnt_hi) {
+                   uint32_t cnt_lo, uint32_t cnt_hi, float* __restrict__ split_out = nullptr) {
   if (active && !active[0]) return;
   // optional indirection: process only rows row_list[0 .. *row_count) (the tensor-core filter's
   // ambiguous rows); outputs are written at the ORIGINAL row positions.  [cnt_lo, cnt_hi) selects
@@ -80,7 +83,8 @@ assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* 
   }
   const int nchunk = d >> 4;
   const float* xrow = xs + (ty * RT) * ld;
-  for (int ct = 0; ct < Kp; ct += 64) {
+  const int ct_begin = SPLIT ? (int)blockIdx.y * 64 : 0, ct_end = SPLIT ? ct_begin + 64 : Kp;
+  for (int ct = ct_begin; ct < ct_end; ct += 64) {
     __syncthreads();
     for (int idx = tid; idx < d * 16; idx += 256) {
       int e = idx >> 4, q = idx & 15;
@@ -152,6 +156,15 @@ assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* 
       }
     }
     const uint64_t rr = row0 + ty * RT + i;
+    if (SPLIT) {
+      if (tx == 0 && rr < n) {
+        float* o = split_out + (rr * gridDim.y + blockIdx.y) * 3;
+        o[0] = best_key[i];
+        o[1] = best_val[i];
+        o[2] = __uint_as_float(best_idx[i]);
+      }
+      continue;
+    }
     if (tx == 0 && rr < n) {
       const uint64_t r = row_list ? row_list[rr] : rr;
       const bool ok = best_idx[i] != 0xffffffffu;
@@ -161,6 +174,31 @@ assign_tile_kernel(const float* __restrict__ x, uint64_t n, int d, const float* 
     }
   }
   }  // row tiles
+}
+
+// winner over the chunk partials of a SPLIT launch: strict-< on the key, lowest index on ties (chunks are
+// visited in ascending centroid order, exactly like the un-split loop)
+__global__ void split_merge_kernel(const float* __restrict__ split_out, int nchunks,
+                                   const uint32_t* __restrict__ row_list, const uint32_t* __restrict__ row_count,
+                                   uint32_t cnt_hi, uint32_t* __restrict__ part, float* __restrict__ dist,
+                                   uint8_t* __restrict__ valid, const uint8_t* __restrict__ active) {
+  if (active && !active[0]) return;
+  const uint32_t n = *row_count;
+  if (n >= cnt_hi) return;
+  const uint32_t rr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rr >= n) return;
+  float bk = __int_as_float(0x7f800000), bv = bk;
+  uint32_t bi = 0xffffffffu;
+  for (int c = 0; c < nchunks; ++c) {
+    const float* o = split_out + ((size_t)rr * nchunks + c) * 3;
+    const uint32_t idx = __float_as_uint(o[2]);
+    if (idx != 0xffffffffu && o[0] < bk) { bk = o[0]; bv = o[1]; bi = idx; }
+  }
+  const uint32_t r = row_list[rr];
+  const bool ok = bi != 0xffffffffu;
+  part[r] = ok ? bi : 0u;
+  if (dist) dist[r] = ok ? bv : __int_as_float(0x7fc00000);
+  if (valid) valid[r] = ok ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -434,17 +472,29 @@ void assign_rows_f32(const float* x, uint64_t n_max, int d, const float* cent, i
   if (!cT_ready)
     LB2_LAUNCH("transpose_centroids", transpose_pad_kernel, cdiv((uint64_t)d * Kp, 256), 256, 0, cent,
                K, d, Kp, cT.get());
-  // short lists: 16-row tiles so that the work still spreads over all SMs; long lists: 64-row tiles
-  // (4x fewer passes over the centroids).  The count lives on the device, so both are launched and
-  // the one whose range does not hold the count exits at once.
-  // (only worth a second launch when the centroid matrix is large: K > 256)
+  // The list length lives on the device, so every regime is launched and the ones whose range does not
+  // hold the count exit at once:
+  //   very short lists (< 2048 rows): 16-row tiles x one CTA per 64-centroid chunk + a merge (latency);
+  //   short lists: 16-row tiles so that the work still spreads over all SMs;
+  //   long lists (only worth a launch when the centroid matrix is large, K > 256): 64-row tiles.
+  const int nchunks = Kp / 64;
+  const uint32_t tiny = (nchunks > 1 && nchunks <= 64) ? (uint32_t)std::min<uint64_t>(2048, n_max + 1) : 0u;
   const uint32_t split = K > 256 ? 64u * 2u * (uint32_t)ctx().num_sms : 0xffffffffu;
   const size_t smem = sizeof(float) * (16 * (d + 1) + (size_t)d * 64);
+  if (tiny) {
+    if (ws->split_scratch.n < (size_t)tiny * nchunks * 3) ws->split_scratch.alloc((size_t)tiny * nchunks * 3);
+    set_smem(assign_tile_kernel<METRIC_L2, false, 1, true>, smem);
+    LB2_LAUNCH("assign_exact_fallback", (assign_tile_kernel<METRIC_L2, false, 1, true>),
+               dim3((unsigned)cdiv(tiny, 16), (unsigned)nchunks), 256, smem, x, n_max, d, cT.get(), K, Kp, bias_padded,
+               part, dist, valid, nullptr, active, row_list, row_count, 0u, tiny, ws->split_scratch.p);
+    LB2_LAUNCH("assign_exact_fallback", split_merge_kernel, cdiv(tiny, 256), 256, 0, ws->split_scratch.p, nchunks,
+               row_list, row_count, tiny, part, dist, valid, active);
+  }
   set_smem(assign_tile_kernel<METRIC_L2, false, 1>, smem);
   LB2_LAUNCH("assign_exact_fallback", (assign_tile_kernel<METRIC_L2, false, 1>),
              (unsigned)std::min<uint64_t>(cdiv(std::min<uint64_t>(n_max, split), 16), 4 * (uint64_t)ctx().num_sms), 256,
              smem, x, n_max, d, cT.get(), K, Kp, bias_padded,
-             part, dist, valid, nullptr, active, row_list, row_count, 0u, split);
+             part, dist, valid, nullptr, active, row_list, row_count, tiny, split);
   if (n_max >= split) {
     const size_t smem4 = sizeof(float) * (64 * (d + 1) + (size_t)d * 64);
     set_smem(assign_tile_kernel<METRIC_L2, false, 4>, smem4);

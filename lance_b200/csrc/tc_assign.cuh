@@ -7,6 +7,7 @@ namespace lb2 {
 struct TcWorkspace {
   DevBuf<float> cpad, cnh, row_norm2, cT;  // cT: transposed centroids for the exact kernels
   DevBuf<uint32_t> res, fb_rows, fb_count;
+  DevBuf<float> split_scratch;  // short row lists: per (row, 64-centroid chunk) partial argmins (key, val, idx)
   const float* norm_src = nullptr;  // row norms are cached per (pointer, n): valid inside one call
   uint64_t norm_n = 0;
 };
