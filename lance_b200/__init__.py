@@ -554,8 +554,9 @@ class IvfFlatIndex(IvfPqIndex):
 
     @classmethod
     def build(cls, data, distance_type="l2", num_partitions=256, max_iters=50, sample_rate=256, seed=0,
-              centroids=None, row_ids=None):
-        data, dt = _typed(data)
+              centroids=None, row_ids=None, bf16=False):
+        """bf16=True: `data` is a uint16 array holding bfloat16 bit patterns (numpy has no bf16 dtype)."""
+        data, dt = _typed(data, bf16)
         n, d = data.shape
         bp = FlatBuildParams()
         lib().lb2_ivfflat_build_params_default(C.byref(bp))

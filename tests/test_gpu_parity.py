@@ -742,6 +742,29 @@ def test_config3_shape_f16_cosine():
         _check_topk(r32[0][i, :oc[i]], r32[1][i, :oc[i]], oi[i, :oc[i]], od[i, :oc[i]], 10)
 
 
+def test_config4_shape_bf16_ivf_flat_1536d():
+    # C4: 1536-d bf16 column, IVF_FLAT (no PQ): coarse assignment through the streamed tensor-core filter,
+    # exact partition scan; bf16 -> f32 is exact, so everything equals the f32 path on the converted values
+    n, d, K = 6000, 1536, 48
+    f = synth.gaussian_mixture(n, d, n_components=K, seed=87).astype(np.float32)
+    bits = (f.view(np.uint32) >> 16).astype(np.uint16)               # truncate to bf16
+    f = (bits.astype(np.uint32) << 16).view(np.float32)              # the exact f32 value of every element
+    ib = lb.IvfFlatIndex.build(bits, "l2", num_partitions=K, max_iters=6, bf16=True)
+    i32 = lb.IvfFlatIndex.build(f, "l2", num_partitions=K, max_iters=6)
+    eb, e32 = ib.export(), i32.export()
+    assert np.array_equal(eb["part_offsets"], e32["part_offsets"]) and np.array_equal(eb["row_ids"], e32["row_ids"])
+    assert np.array_equal(eb["vectors"], e32["vectors"])
+    p_ref, _, _ = ob.compute_membership(e32["centroids"], f, nthreads=NT)
+    sizes = np.diff(e32["part_offsets"]).astype(np.int64)
+    assert np.array_equal(np.repeat(np.arange(K, dtype=np.uint32), sizes)[np.argsort(e32["row_ids"])], p_ref)
+    q = f[:20]
+    ids, dists = ib.search(bits[:20], k=10, nprobes=4)
+    oi, od, oc = ob.ivfflat_search(e32["centroids"], e32["part_offsets"], e32["vectors"], e32["row_ids"], q, 10, 4,
+                                   nthreads=NT)
+    for i in range(20):
+        _check_topk(ids[i, :oc[i]], dists[i, :oc[i]], oi[i, :oc[i]], od[i, :oc[i]], 10)
+
+
 def test_config5_shape_u8_m32():
     # C5: u8 vectors, M = 32 (4-wide sub-vectors -> exact small-d kernel), many partitions
     rng = np.random.default_rng(85)
