@@ -184,7 +184,10 @@ lb2_status lb2_ivfpq_transform(const void* centroids, uint32_t k, const void* co
 lb2_status lb2_index_create(const void* centroids, uint32_t k, uint32_t d, lb2_dtype dtype,
                             lb2_metric metric, const void* codebook, uint32_t num_sub_vectors,
                             uint32_t num_bits, lb2_index** out);
-/* load the (row_id, __ivf_part_id, __pq_code) shuffle output (builder.rs:685-937): rows are grouped
+/* num_bits = 8 or 4 (4: 16 codewords per sub-space, codes are [n][M/2] packed bytes, M even; searches
+ * use compute_pq_distance_4bit's flat-rows + u8-quantised-table rule with k_hint = k, and exact
+ * row-by-row distances when a prefilter is given, as the reference does).
+ * load the (row_id, __ivf_part_id, __pq_code) shuffle output (builder.rs:685-937): rows are grouped
  * by partition on the device (stable, i.e. input order inside a partition). Replaces prior content. */
 lb2_status lb2_index_load(lb2_index* index, const uint32_t* part_ids, const uint8_t* codes,
                           const uint64_t* row_ids /* NULL = 0..n */, uint64_t n);

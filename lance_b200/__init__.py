@@ -343,7 +343,7 @@ def ivfpq_transform(centroids, codebook, vectors, distance_type="l2", num_bits=8
     k, d = centroids.shape
     M = codebook.shape[0]
     n = vectors.shape[0]
-    part, codes, valid = np.empty(n, np.uint32), np.empty((n, M), np.uint8), np.empty(n, np.uint8)
+    part, codes, valid = np.empty(n, np.uint32), np.empty((n, M // 2 if num_bits == 4 else M), np.uint8), np.empty(n, np.uint8)
     cp, _k1 = as_ptr(centroids)
     bp, _k2 = as_ptr(codebook)
     vp, _k3 = as_ptr(vectors)
@@ -443,9 +443,10 @@ class IvfPqIndex:
             cent, cb, off, codes, rid = (out[k] for k in ("centroids", "codebook", "part_offsets", "codes", "row_ids"))
         else:
             cent = np.empty((K, d), np.float32)
-            cb = np.empty((M, 256, d // M), np.float32)
+            nbits = i["num_bits"]
+            cb = np.empty((M, 1 << nbits, d // M), np.float32)
             off = np.empty(K + 1, np.uint64)
-            codes = np.empty((n, M), np.uint8)
+            codes = np.empty((n, M // 2 if nbits == 4 else M), np.uint8)   # 4-bit: two codes per byte
             rid = np.empty(n, np.uint64)
         check(lib().lb2_index_export(self._h, C.c_void_p(cent.ctypes.data), C.c_void_p(cb.ctypes.data),
                                      C.c_void_p(off.ctypes.data), C.c_void_p(codes.ctypes.data),

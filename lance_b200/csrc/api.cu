@@ -239,6 +239,8 @@ struct lb2_index {
   DevBuf<float> centroids, codebook;
   DevBuf<uint64_t> part_offsets, row_ids;
   DevBuf<uint8_t> codes;
+  int code_bytes() const { return nbits == 4 ? M / 2 : M; }  // bytes per row of `codes` (pq.rs:168-173)
+  size_t codebook_len() const { return ((size_t)1 << nbits) * d; }
 };
 
 namespace lb2 {
@@ -251,10 +253,10 @@ static void index_load_dev(lb2_index* ix, const uint32_t* part_ids, const uint8_
   ix->part_offsets.alloc(ix->K + 1);
   LB2_LAUNCH("widen_offsets", widen_offsets_kernel, cdiv(ix->K + 1, 256), 256, 0, ms.offsets.p,
              ix->K, ix->part_offsets.p);
-  ix->codes.alloc(std::max<uint64_t>(1, n * ix->M));
+  ix->codes.alloc(std::max<uint64_t>(1, n * ix->code_bytes()));
   ix->row_ids.alloc(std::max<uint64_t>(1, n));
   if (n)
-    LB2_LAUNCH("group_by_partition", group_kernel, cdiv(n, 256), 256, 0, ms.members.p, n, ix->M,
+    LB2_LAUNCH("group_by_partition", group_kernel, cdiv(n, 256), 256, 0, ms.members.p, n, ix->code_bytes(),
                codes, row_ids, ix->codes.p, ix->row_ids.p);
   ix->n = n;
   sync_stream();
@@ -295,6 +297,23 @@ static std::vector<uint64_t> sample_rows(uint64_t n, uint64_t s, uint64_t seed) 
     out[i] = lo + rng.next() % (hi - lo);
   }
   return out;
+}
+
+// ProductQuantizer::transform_impl for either code width (pq.rs:116-191): 8-bit -> [n][M] through the
+// tensor path where it applies; 4-bit -> 16 codewords per sub-space, exact kernel, two codes per byte
+static void pq_encode_any(const float* x, uint64_t n, int d, int M, int ds, const float* codebook, int metric,
+                          const float* cent, const uint32_t* part, const uint8_t* row_valid, int nbits,
+                          uint8_t* codes) {
+  if (nbits == 8) {
+    pq_encode_dev(x, n, d, M, ds, codebook, metric, cent, part, row_valid, codes);
+    return;
+  }
+  if (n == 0) return;
+  DevBuf<uint8_t> wide((size_t)n * M);
+  small_d_assign_f32(x, n, d, M, ds, codebook, 16, metric, cent, part, row_valid, wide.p, nullptr, nullptr,
+                     nullptr, nullptr);
+  pack_nibbles(wide.p, n, M, codes);
+  sync_stream();  // `wide` is freed on return
 }
 
 static void pq_train_dev(const float* data, uint64_t n, int d, int metric, const lb2_pq_params* p,
@@ -631,18 +650,8 @@ lb2_status lb2_pq_encode(const void* codebook, uint32_t num_sub_vectors, uint32_
       c.set(centroids, (size_t)(kmax + 1) * d, model_dtype(dtype));
     }
   }
-  if (num_bits == 4) {  // 16 codewords per sub-space, two codes per byte (pq.rs:168-173)
-    OutArg<uint8_t> o4(codes_out, (size_t)n * (M / 2));
-    DevBuf<uint8_t> wide((size_t)n * M);
-    small_d_assign_f32(x.get(), n, d, M, ds, cb.get(), 16, m, c.get(), p.get(), nullptr, wide.p, nullptr, nullptr,
-                       nullptr, nullptr);
-    pack_nibbles(wide.p, n, M, o4.get());
-    o4.commit();
-    sync_stream();
-    return LB2_OK;
-  }
-  OutArg<uint8_t> o(codes_out, (size_t)n * M);
-  pq_encode_dev(x.get(), n, d, M, ds, cb.get(), m, c.get(), p.get(), nullptr, o.get());
+  OutArg<uint8_t> o(codes_out, (size_t)n * (num_bits == 4 ? M / 2 : M));
+  pq_encode_any(x.get(), n, d, M, ds, cb.get(), m, c.get(), p.get(), nullptr, (int)num_bits, o.get());
   o.commit();
   sync_stream();
   LB2_API_END
@@ -715,15 +724,16 @@ lb2_status lb2_ivfpq_transform(const void* centroids, uint32_t k, const void* co
                                uint32_t* part_out, uint8_t* codes_out, uint8_t* valid_out) {
   LB2_API_BEGIN
 
-  if (num_bits != 8) fail(LB2_UNSUPPORTED, "num_bits %u is not implemented on the device", num_bits);
+  if (num_bits != 8 && num_bits != 4) fail(LB2_INVALID_ARG, "PQ: num_bits must be 4 or 8, got %u", num_bits);
   const int M = num_sub_vectors, ds = d / M;
   LB2_REQUIRE(M > 0 && d % M == 0, "num_sub_vectors must divide vector dimension %u, but got %d", d, M);
+  LB2_REQUIRE(num_bits == 8 || M % 2 == 0, "PQ: num_sub_vectors must be divisible by 2 for num_bits=4, but got %d", M);
   if (!small_d_supported(ds)) fail(LB2_UNSUPPORTED, "PQ sub-vector width %d not supported yet", ds);
   const int m = metric_of(metric);
-  VecIn c(centroids, (size_t)k * d, model_dtype(dtype)), cb(codebook, (size_t)256 * d, model_dtype(dtype)),
+  VecIn c(centroids, (size_t)k * d, model_dtype(dtype)), cb(codebook, ((size_t)1 << num_bits) * d, model_dtype(dtype)),
       x(vectors, (size_t)n * d, dtype);
   OutArg<uint32_t> p(part_out, n);
-  OutArg<uint8_t> co(codes_out, (size_t)n * M), v(valid_out, n);
+  OutArg<uint8_t> co(codes_out, (size_t)n * (num_bits == 4 ? M / 2 : M)), v(valid_out, n);
   DevBuf<uint8_t> vtmp;
   uint8_t* vp = v.get();
   if (!vp) { vtmp.alloc(std::max<uint64_t>(n, 1)); vp = vtmp.p; }
@@ -736,8 +746,8 @@ lb2_status lb2_ivfpq_transform(const void* centroids, uint32_t k, const void* co
   }
   const int am = m == METRIC_DOT ? METRIC_DOT : METRIC_L2;
   assign_f32(xp, n, d, c.get(), k, am, nullptr, p.get(), nullptr, vp, nullptr);
-  pq_encode_dev(xp, n, d, M, ds, cb.get(), am, am == METRIC_DOT ? nullptr : c.get(),
-                am == METRIC_DOT ? nullptr : p.get(), vp, co.get());
+  pq_encode_any(xp, n, d, M, ds, cb.get(), am, am == METRIC_DOT ? nullptr : c.get(),
+                am == METRIC_DOT ? nullptr : p.get(), vp, (int)num_bits, co.get());
   p.commit(); co.commit(); v.commit();
   sync_stream();
   LB2_API_END
@@ -749,17 +759,19 @@ lb2_status lb2_index_create(const void* centroids, uint32_t k, uint32_t d, lb2_d
   LB2_API_BEGIN
   LB2_REQUIRE(out && centroids && codebook, "null argument");
   LB2_REQUIRE(num_sub_vectors > 0 && d % num_sub_vectors == 0, "num_sub_vectors must divide d");
-  if (num_bits != 8) fail(LB2_UNSUPPORTED, "num_bits %u is not implemented on the device", num_bits);
+  if (num_bits != 8 && num_bits != 4) fail(LB2_INVALID_ARG, "PQ: num_bits must be 4 or 8, got %u", num_bits);
+  LB2_REQUIRE(num_bits == 8 || num_sub_vectors % 2 == 0,
+              "PQ: num_sub_vectors must be divisible by 2 for num_bits=4, but got %u", num_sub_vectors);
   ctx();
   lb2_index* ix = new lb2_index();
   ix->K = k; ix->d = d; ix->M = num_sub_vectors; ix->nbits = num_bits; ix->metric = metric_of(metric);
   ix->dtype = dtype;
   ix->centroids.alloc((size_t)k * d);
-  ix->codebook.alloc((size_t)256 * d);
+  ix->codebook.alloc(ix->codebook_len());
   {
-    VecIn c(centroids, (size_t)k * d, model_dtype(dtype)), cb(codebook, (size_t)256 * d, model_dtype(dtype));
+    VecIn c(centroids, (size_t)k * d, model_dtype(dtype)), cb(codebook, ix->codebook_len(), model_dtype(dtype));
     d2d(ix->centroids.p, c.get(), (size_t)k * d);
-    d2d(ix->codebook.p, cb.get(), (size_t)256 * d);
+    d2d(ix->codebook.p, cb.get(), ix->codebook_len());
     sync_stream();
   }
   ix->part_offsets.alloc(k + 1);
@@ -774,7 +786,7 @@ lb2_status lb2_index_load(lb2_index* index, const uint32_t* part_ids, const uint
   LB2_API_BEGIN
   LB2_REQUIRE(index && index->kind == 0, "not an IVF_PQ index");
   InArg<uint32_t> p(part_ids, n);
-  InArg<uint8_t> c(codes, (size_t)n * index->M);
+  InArg<uint8_t> c(codes, (size_t)n * index->code_bytes());
   InArg<uint64_t> r(row_ids, n);
   index_load_dev(index, p.get(), c.get(), r.get(), n);
   LB2_API_END
@@ -899,11 +911,11 @@ lb2_status lb2_index_export(const lb2_index* index, void* centroids_out, void* c
   if (centroids_out)
     LB2_CUDA(cudaMemcpyAsync(centroids_out, index->centroids.p, sizeof(float) * index->K * index->d, cudaMemcpyDefault, s));
   if (codebook_out)
-    LB2_CUDA(cudaMemcpyAsync(codebook_out, index->codebook.p, sizeof(float) * 256 * index->d, cudaMemcpyDefault, s));
+    LB2_CUDA(cudaMemcpyAsync(codebook_out, index->codebook.p, sizeof(float) * index->codebook_len(), cudaMemcpyDefault, s));
   if (part_offsets_out)
     LB2_CUDA(cudaMemcpyAsync(part_offsets_out, index->part_offsets.p, sizeof(uint64_t) * (index->K + 1), cudaMemcpyDefault, s));
   if (codes_out && index->n)
-    LB2_CUDA(cudaMemcpyAsync(codes_out, index->codes.p, index->n * index->M, cudaMemcpyDefault, s));
+    LB2_CUDA(cudaMemcpyAsync(codes_out, index->codes.p, index->n * index->code_bytes(), cudaMemcpyDefault, s));
   if (row_ids_out && index->n)
     LB2_CUDA(cudaMemcpyAsync(row_ids_out, index->row_ids.p, sizeof(uint64_t) * index->n, cudaMemcpyDefault, s));
   sync_stream();
@@ -1075,7 +1087,9 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
   LB2_REQUIRE(K > 0 && (nranks > 1 || n >= (uint64_t)K), "KMeans: can not train %d centroids with %llu vectors", K,
               (unsigned long long)n);
   LB2_REQUIRE(M > 0 && d % M == 0, "num_sub_vectors must divide vector dimension %u, but got %d", d, M);
-  if (params->pq.num_bits != 8) fail(LB2_UNSUPPORTED, "num_bits %u is not implemented", params->pq.num_bits);
+  const int nbits = (int)params->pq.num_bits;
+  if (nbits != 8 && nbits != 4) fail(LB2_INVALID_ARG, "PQ: num_bits must be 4 or 8, got %d", nbits);
+  LB2_REQUIRE(nbits == 8 || M % 2 == 0, "PQ: num_sub_vectors must be divisible by 2 for num_bits=4, but got %d", M);
   const int ds = d / M;
   if (!small_d_supported(ds)) fail(LB2_UNSUPPORTED, "PQ sub-vector width %d not supported yet", ds);
   Ctx& c = ctx();
@@ -1135,16 +1149,16 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
   const int am = m == METRIC_DOT ? METRIC_DOT : METRIC_L2;
 
   lb2_index* ix = new lb2_index();
-  ix->K = K; ix->d = d; ix->M = M; ix->nbits = 8; ix->metric = m; ix->dtype = dtype;
+  ix->K = K; ix->d = d; ix->M = M; ix->nbits = nbits; ix->metric = m; ix->dtype = dtype;
   ix->centroids.alloc((size_t)K * d);
-  ix->codebook.alloc((size_t)256 * d);
+  ix->codebook.alloc(ix->codebook_len());
   std::vector<double> ivf_loss;
   std::vector<uint32_t> ivf_iters, pq_iters;
   try {
     // 0. both training samples are gathered first (IVF: K*sample_rate rows, rust/lance/src/index/
     //    vector/ivf.rs:1237-1241; PQ: 256*2^nbits rows, builder.rs:410-421), then the bulk copy starts
     const uint64_t s_ivf = std::min<uint64_t>(n, ((uint64_t)K * params->ivf.sample_rate + nranks - 1) / nranks);
-    const uint64_t s_pq = std::min<uint64_t>(n, (params->pq.sample_rate * 256 + nranks - 1) / nranks);
+    const uint64_t s_pq = std::min<uint64_t>(n, (params->pq.sample_rate * ((uint64_t)1 << nbits) + nranks - 1) / nranks);
     DevBuf<float> sample_ivf, sample_pq((size_t)s_pq * d);
     const float* xs_ivf = x_sample;
     {
@@ -1193,7 +1207,7 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
         LB2_LAUNCH("residual", residual_kernel, cdiv(s * d, 256), 256, 0, sample.p, ix->centroids.p,
                    part.p, s, (int)d, sample.p);
       }
-      VecIn cb_init(params->pq.codebook, (size_t)256 * d, model_dtype(dtype));
+      VecIn cb_init(params->pq.codebook, ix->codebook_len(), model_dtype(dtype));
       lb2_pq_params pqp = params->pq;
       pqp.codebook = cb_init.get();
       pq_train_dev(sample.p, s, d, am, &pqp, ix->codebook.p, &pq_iters);
@@ -1201,12 +1215,12 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
     LB2_CUDA(cudaEventRecord(ev[2], c.stream));
     // 3. transform every row (lance-index/src/vector/ivf.rs:357: partition -> residual -> PQ)
     DevBuf<uint32_t> part(n);
-    DevBuf<uint8_t> codes((size_t)n * M), valid(n);
+    DevBuf<uint8_t> codes((size_t)n * ix->code_bytes()), valid(n);
     if (copied) LB2_CUDA(cudaStreamWaitEvent(c.stream, copied, 0));  // the bulk copy must have landed
     TagScope* tg3 = new TagScope("transform");
     assign_f32(x, n, d, ix->centroids.p, K, am, nullptr, part.p, nullptr, valid.p, nullptr);
-    pq_encode_dev(x, n, d, M, ds, ix->codebook.p, am, am == METRIC_DOT ? nullptr : ix->centroids.p,
-                  am == METRIC_DOT ? nullptr : part.p, valid.p, codes.p);
+    pq_encode_any(x, n, d, M, ds, ix->codebook.p, am, am == METRIC_DOT ? nullptr : ix->centroids.p,
+                  am == METRIC_DOT ? nullptr : part.p, valid.p, nbits, codes.p);
     delete tg3;
     LB2_CUDA(cudaEventRecord(ev[3], c.stream));
     TagScope tg4("group");

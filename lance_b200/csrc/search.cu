@@ -190,7 +190,7 @@ __device__ __forceinline__ float key_to_float(int32_t key) {
 // 4-pass MSB radix select over shared-memory keys (256-bin histograms), everything below it is
 // kept, ties AT the k-th key are resolved by position (earliest rows survive).
 // ------------------------------------------------------------------------------------------------
-template <int METRIC>
+template <int METRIC, int NBITS>
 __global__ void __launch_bounds__(256)
 ivfpq_scan_radix_kernel(const float* __restrict__ queries, int d, const float* __restrict__ centroids,
                         const float* __restrict__ codebook, int M, int ds,
@@ -200,7 +200,8 @@ ivfpq_scan_radix_kernel(const float* __restrict__ queries, int d, const float* _
                         uint64_t* __restrict__ cand_id, uint32_t* __restrict__ cand_cnt,
                         const uint64_t* __restrict__ allow) {
   extern __shared__ float smem[];
-  float* lut = smem;                                                   // [M*256]
+  constexpr int NCODE = 1 << NBITS;
+  float* lut = smem;                                                   // [M*NCODE] (8-bit: M*256)
   float* qr = lut + M * 256;                                           // [d]
   uint32_t* ukey = reinterpret_cast<uint32_t*>(qr + d);                // [SCAN_CHUNK + k] order-preserving keys
   uint32_t* cpos = ukey + SCAN_CHUNK + k;                              // [k] positions of carried winners
@@ -227,10 +228,66 @@ ivfpq_scan_radix_kernel(const float* __restrict__ queries, int d, const float* _
   for (int t = tid; t < d; t += 256)
     qr[t] = METRIC == METRIC_DOT ? q[t] : __fsub_rn(q[t], centroids[(size_t)p * d + t]);  // v2.rs:316-332
   __syncthreads();
-  build_lut_smem<METRIC>(lut, qr, codebook, M, ds, tid);
+  if (NBITS == 8) {
+    build_lut_smem<METRIC>(lut, qr, codebook, M, ds, tid);
+  } else {
+    for (int idx = tid; idx < M * NCODE; idx += 256)
+      lut[idx] = dist_exact_thread<METRIC>(qr + (idx / NCODE) * ds, codebook + (size_t)idx * ds, ds);
+  }
   __syncthreads();
-  const uint8_t* pc = codes + off * M;
+  constexpr int CW_DIV = NBITS == 4 ? 2 : 1;
+  const int cw = M / CW_DIV;  // code bytes per row
+  const uint8_t* pc = codes + off * cw;
   const float dot_fix = (float)M - 1.0f;
+  // ---- 4-bit (pq/distance.rs:147-242): rows [0, flat_num) and the last n_p % 16 rows are exact f32 sums;
+  // the others go through the table quantised to u8 with qmin = min(table), qmax = max(flat rows).
+  // With a prefilter the reference scores row by row with DistCalculator::distance (exact, pq/storage.rs:
+  // 895-916), so every row is exact then.
+  __shared__ uint8_t qt[NBITS == 4 ? 256 * 16 : 1];  // M <= 256 sub-vectors x 16 entries
+  __shared__ float s_q[2];                                // qmin, (qmax - qmin) / 255
+  const uint32_t flat_num = NBITS == 4 ? min((uint32_t)max(200, k), n_p) : 0;
+  const uint32_t rem16 = NBITS == 4 ? n_p % 16 : 0;
+  auto exact4 = [&](uint32_t j) -> float {  // two adds per byte, byte order
+    const uint8_t* rp = pc + (size_t)j * cw;
+    float dist = 0.0f;
+    for (int i = 0; i < cw; ++i) {
+      const uint8_t c = rp[i];
+      dist = f_add(dist, lut[(2 * i) * 16 + (c & 0xF)]);
+      dist = f_add(dist, lut[(2 * i + 1) * 16 + (c >> 4)]);
+    }
+    return dist;
+  };
+  if (NBITS == 4 && allow == nullptr) {
+    int32_t mx = (int32_t)0x80000000;
+    for (uint32_t j = tid; j < flat_num; j += 256) mx = max(mx, total_order_key(exact4(j)));
+    float mn = __int_as_float(0x7f800000);
+    for (int i = tid; i < M * 16; i += 256) mn = fminf(mn, lut[i]);
+    // block reduce through the (still unused) selection scratch
+    int32_t* r_mx = reinterpret_cast<int32_t*>(hist);
+    float* r_mn = reinterpret_cast<float*>(ukey);
+    r_mx[tid] = mx;
+    r_mn[tid] = mn;
+    __syncthreads();
+    for (int o = 128; o >= 1; o >>= 1) {
+      if (tid < o) {
+        r_mx[tid] = max(r_mx[tid], r_mx[tid + o]);
+        r_mn[tid] = fminf(r_mn[tid], r_mn[tid + o]);
+      }
+      __syncthreads();
+    }
+    const float qmax = key_to_float(r_mx[0]), qmin = r_mn[0];
+    __syncthreads();
+    const float factor = __fdiv_rn(255.0f, __fsub_rn(qmax, qmin));
+    for (int i = tid; i < M * 16; i += 256) {
+      const float v = roundf(__fmul_rn(__fsub_rn(lut[i], qmin), factor));
+      qt[i] = (v != v) ? 0 : v <= 0.0f ? 0 : v >= 255.0f ? 255 : (uint8_t)v;
+    }
+    if (tid == 0) {
+      s_q[0] = qmin;
+      s_q[1] = __fdiv_rn(__fsub_rn(qmax, qmin), 255.0f);
+    }
+    __syncthreads();
+  }
   uint32_t nw = 0;
   for (uint32_t c0 = 0; c0 < n_p; c0 += SCAN_CHUNK) {
     const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
@@ -240,7 +297,21 @@ ivfpq_scan_radix_kernel(const float* __restrict__ queries, int d, const float* _
         continue;
       }
       float dist = 0.0f;
-      if ((M & 15) == 0) {
+      if (NBITS == 4) {
+        const uint32_t row = c0 + j;
+        if (allow != nullptr || row < flat_num || row >= n_p - rem16) {
+          dist = exact4(row);
+        } else {
+          const uint8_t* rp = pc + (size_t)row * cw;
+          uint32_t q = 0;  // saturating u8 adds of non-negative terms == min(255, sum)
+          for (int i2 = 0; i2 < cw; ++i2) {
+            const uint8_t c = rp[i2];
+            q += qt[(2 * i2) * 16 + (c & 0xF)];
+            q += qt[(2 * i2 + 1) * 16 + (c >> 4)];
+          }
+          dist = __fadd_rn(__fmul_rn((float)min(q, 255u), s_q[1]), s_q[0]);
+        }
+      } else if ((M & 15) == 0) {
         const uint4* rp = reinterpret_cast<const uint4*>(pc + (size_t)(c0 + j) * M);
         for (int c16 = 0; c16 < M / 16; ++c16) {
           const uint4 v = __ldg(rp + c16);
@@ -793,12 +864,12 @@ void find_partitions_f32(const float* centroids, int K, int d, int metric, const
 }
 
 template <int METRIC>
-static void scan_launch(int kmax, dim3 grid, size_t smem, const float* queries, int d,
+static void scan_launch(int nbits, dim3 grid, size_t smem, const float* queries, int d,
                         const float* centroids, const float* codebook, int M, int ds,
                         const uint32_t* probe_ids, int np, const uint64_t* part_offsets,
                         const uint8_t* codes, const uint64_t* row_ids, int k, float* cand_d,
                         uint64_t* cand_id, uint32_t* cand_cnt, const uint64_t* allow) {
-  if (k <= SCAN_KFAST) {
+  if (nbits == 8 && k <= SCAN_KFAST) {
     const size_t smem_fast = sizeof(float) * ((size_t)M * 256 + d);
     if (allow) {  // filtered rows never enter the candidate lists
       set_smem(ivfpq_scan_kernel<METRIC, true>, smem_fast);
@@ -811,8 +882,14 @@ static void scan_launch(int kmax, dim3 grid, size_t smem, const float* queries, 
     }
     return;
   }
-  set_smem(ivfpq_scan_radix_kernel<METRIC>, smem);
-  LB2_LAUNCH("pq_scan", (ivfpq_scan_radix_kernel<METRIC>), grid, 256, smem, queries, d, centroids, codebook,
+  if (nbits == 4) {
+    set_smem((ivfpq_scan_radix_kernel<METRIC, 4>), smem);
+    LB2_LAUNCH("pq_scan", (ivfpq_scan_radix_kernel<METRIC, 4>), grid, 256, smem, queries, d, centroids, codebook,
+               M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt, allow);
+    return;
+  }
+  set_smem((ivfpq_scan_radix_kernel<METRIC, 8>), smem);
+  LB2_LAUNCH("pq_scan", (ivfpq_scan_radix_kernel<METRIC, 8>), grid, 256, smem, queries, d, centroids, codebook,
              M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt, allow);
 }
 
@@ -821,7 +898,8 @@ void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const fl
                       const uint64_t* row_ids, const float* queries, uint64_t nq, int k, int nprobes,
                       uint64_t* out_ids, float* out_dists, uint32_t* out_counts, const uint64_t* allow) {
   if (nq == 0 || k == 0) return;
-  if (nbits != 8) fail(LB2_UNSUPPORTED, "only 8-bit PQ is implemented on the device");
+  if (nbits != 8 && nbits != 4) fail(LB2_INVALID_ARG, "PQ: num_bits must be 4 or 8, got %d", nbits);
+  if (nbits == 4 && (M % 2 != 0 || M > 256)) fail(LB2_UNSUPPORTED, "4-bit PQ needs an even num_sub_vectors <= 256");
   if (k > 1024) fail(LB2_UNSUPPORTED, "k (incl. refine factor) > 1024 is not implemented");
   const int np = nprobes < K ? nprobes : K;
   const int ds = d / M;
@@ -839,19 +917,19 @@ void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const fl
       const uint64_t qn = std::min<uint64_t>(32768, nq - q0);
       dim3 g(np, (unsigned)qn);
       if (cmetric == METRIC_DOT)
-        scan_launch<METRIC_DOT>(k, g, smem, queries + q0 * d, d, centroids, codebook, M, ds,
+        scan_launch<METRIC_DOT>(nbits, g, smem, queries + q0 * d, d, centroids, codebook, M, ds,
                                 pids.p + q0 * np, np, part_offsets, codes, row_ids, k,
                                 cand_d.p + q0 * np * k, cand_id.p + q0 * np * k, cand_cnt.p + q0 * np, allow);
       else
-        scan_launch<METRIC_L2>(k, g, smem, queries + q0 * d, d, centroids, codebook, M, ds,
+        scan_launch<METRIC_L2>(nbits, g, smem, queries + q0 * d, d, centroids, codebook, M, ds,
                                pids.p + q0 * np, np, part_offsets, codes, row_ids, k,
                                cand_d.p + q0 * np * k, cand_id.p + q0 * np * k, cand_cnt.p + q0 * np, allow);
     }
   } else if (cmetric == METRIC_DOT) {
-    scan_launch<METRIC_DOT>(k, grid, smem, queries, d, centroids, codebook, M, ds, pids.p, np,
+    scan_launch<METRIC_DOT>(nbits, grid, smem, queries, d, centroids, codebook, M, ds, pids.p, np,
                             part_offsets, codes, row_ids, k, cand_d.p, cand_id.p, cand_cnt.p, allow);
   } else {
-    scan_launch<METRIC_L2>(k, grid, smem, queries, d, centroids, codebook, M, ds, pids.p, np,
+    scan_launch<METRIC_L2>(nbits, grid, smem, queries, d, centroids, codebook, M, ds, pids.p, np,
                            part_offsets, codes, row_ids, k, cand_d.p, cand_id.p, cand_cnt.p, allow);
   }
   LB2_LAUNCH("merge_topk", merge_kernel, (unsigned)nq, 128, 0, cand_d.p, cand_id.p, cand_cnt.p, np,

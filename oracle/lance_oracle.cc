@@ -843,11 +843,13 @@ static void ivfpq_search_impl(const float* centroids, uint64_t K, uint64_t d, in
   const uint64_t ncode = uint64_t(1) << nbits;
   uint64_t max_part = 0;
   for (uint64_t p = 0; p < K; ++p) max_part = std::max(max_part, part_offsets[p + 1] - part_offsets[p]);
-  // transposed copies per partition, built once (ProductQuantizationStorage::new transposes)
-  std::vector<uint8_t> codes_t(part_offsets[K] * M);
+  // transposed copies per partition, built once (ProductQuantizationStorage::new transposes);
+  // 4-bit: M/2 packed bytes per row (pq.rs:168-173), transposed byte-wise
+  const uint64_t cw = nbits == 4 ? M / 2 : M;
+  std::vector<uint8_t> codes_t(part_offsets[K] * cw);
   for (uint64_t p = 0; p < K; ++p) {
     uint64_t n = part_offsets[p + 1] - part_offsets[p];
-    lo_transpose_codes(codes + part_offsets[p] * M, n, M, codes_t.data() + part_offsets[p] * M);
+    lo_transpose_codes(codes + part_offsets[p] * cw, n, cw, codes_t.data() + part_offsets[p] * cw);
   }
   const int cmetric = metric == 1 ? 0 : metric;  // cosine -> L2 on normalised vectors
   parallel_for(nq, nthreads, [&](size_t b, size_t e) {
@@ -875,7 +877,13 @@ static void ivfpq_search_impl(const float* centroids, uint64_t K, uint64_t d, in
           qq = qr.data();
         }
         lo_build_lut(codebook, nbits, M, d, cmetric, qq, lut.data());
-        lo_pq_scan(lut.data(), M, codes_t.data() + part_offsets[p] * M, n, cmetric, dist.data());
+        if (nbits == 4)  // DistCalculator::distance_all(k_hint = k), flat/index.rs:99 -> pq/distance.rs:147;
+                         // with a prefilter the rows are scored one by one with the EXACT
+                         // DistCalculator::distance (flat/index.rs:152, pq/storage.rs:895-916): k_hint = n
+          lo_pq_scan_4bit(lut.data(), M, codes_t.data() + part_offsets[p] * cw, n, mask.empty() ? k : n, cmetric,
+                          dist.data());
+        else
+          lo_pq_scan(lut.data(), M, codes_t.data() + part_offsets[p] * M, n, cmetric, dist.data());
         uint64_t got = mask.empty()
                            ? lo_flat_topk(dist.data(), row_ids + part_offsets[p], n, k, 0, 0, 0, hid.data(), hd.data())
                            : flat_topk_masked(dist.data(), row_ids + part_offsets[p], n, k, mask, hid.data(), hd.data());

@@ -284,6 +284,49 @@ def test_pq_4bit_train_encode_lut_scan_bit_exact(metric):
         lb.ProductQuantizer(3, 4, 12, np.zeros((3, 16, 4), np.float32)).quantize(np.zeros((4, 12), np.float32))
 
 
+@pytest.mark.parametrize("metric", ["l2", "dot"])
+def test_index_4bit_build_search_matches_oracle(metric):
+    # create_index(IVF_PQ, num_bits=4): 16 codewords, packed codes, quantised-table scan inside the index
+    rng = np.random.default_rng(414)
+    n, d, K, M = 20000, 64, 16, 16
+    data = synth.gaussian_mixture(n, d, n_components=K, seed=414)
+    if metric == "dot":
+        data /= np.linalg.norm(data, axis=1, keepdims=True)
+    ix = lb.IvfPqIndex.build(data, metric, lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, num_bits=4,
+                                                             max_iters=8, pq_max_iters=6))
+    parts = ix.export()
+    assert parts["codebook"].shape == (M, 16, d // M) and parts["codes"].shape == (n, M // 2)
+    assert ix.info()["num_bits"] == 4
+    # the stored codes are the reference's codes for the stored model
+    order = np.argsort(parts["row_ids"])
+    p_ref, _, _ = ob.compute_membership(parts["centroids"], data, metric=metric, nthreads=NT)
+    res = data if metric == "dot" else ob.compute_residual(parts["centroids"], data, p_ref, nthreads=NT)
+    assert np.array_equal(parts["codes"][order], ob.pq_encode(parts["codebook"], res, nbits=4, metric=metric, nthreads=NT))
+    q = synth.gaussian_mixture(16, d, n_components=K, seed=415)
+    for k, nprobes in ((10, 3), (250, 2)):                    # k > 200 moves flat_num
+        ids, dists = ix.search(q, k=k, nprobes=nprobes)
+        oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
+                                     parts["row_ids"], q, k, nprobes, metric=metric, nbits=4, nthreads=NT)
+        for i in range(len(q)):
+            c = int(oc[i])
+            _check_topk(ids[i, :c], dists[i, :c], oi[i, :c], od[i, :c], k)
+    # prefilter: the reference scores the selected rows exactly (DistCalculator::distance)
+    allow = parts["row_ids"][rng.choice(n, n // 3, replace=False)]
+    bm = ix.row_mask(allow, None)
+    ids, dists = ix.search_ex(q, k=10, nprobes=3, allow_bitmap=bm)
+    oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
+                                 parts["row_ids"], q, 10, 3, metric=metric, nbits=4, nthreads=NT, allow=allow)
+    for i in range(len(q)):
+        c = int(oc[i])
+        _check_topk(ids[i, :c], dists[i, :c], oi[i, :c], od[i, :c], 10)
+    # from_parts with packed codes == build
+    i2 = lb.IvfPqIndex.from_parts(parts["centroids"], parts["codebook"],
+                                  np.repeat(np.arange(K, dtype=np.uint32), np.diff(parts["part_offsets"]).astype(np.int64)),
+                                  parts["codes"], parts["row_ids"], metric, num_bits=4)
+    a, b = ix.search(q, k=10, nprobes=3), i2.search(q, k=10, nprobes=3)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
 # ---- prefilter: PreFilter / RowIdMask (prefilter.rs:27-51, flat/index.rs:129-165) --------------
 @pytest.mark.parametrize("kind", ["pq", "flat"])
 def test_index_search_with_row_mask_matches_oracle(kind):
@@ -368,9 +411,10 @@ def test_device_resident_inputs():
 
 
 def test_unsupported_is_surfaced_not_masked():
-    with pytest.raises(lb.LanceB200Error) as e:      # 4-bit PQ inside a device-resident index: not implemented
-        lb.IvfPqIndex.from_parts(np.zeros((2, 16), np.float32), np.zeros((4, 16, 4), np.float32),
-                                 np.zeros(4, np.uint32), np.zeros((4, 2), np.uint8), num_bits=4)
+    ixs = lb.IvfPqIndex.from_parts(np.zeros((2, 16), np.float32), np.zeros((4, 256, 4), np.float32),
+                                   np.zeros(4, np.uint32), np.zeros((4, 4), np.uint8))
+    with pytest.raises(lb.LanceB200Error) as e:      # k beyond what the scan kernels select: surfaced
+        ixs.search(np.zeros((1, 16), np.float32), k=2000, nprobes=1)
     assert e.value.status == 2
     with pytest.raises(lb.LanceB200Error) as e:      # the reference only has 4 and 8 bits
         lb.PQBuildParams(4, 6).build(np.zeros((300, 16), np.float32))
