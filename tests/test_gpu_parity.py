@@ -465,6 +465,36 @@ def test_edge_cases_empty_ragged_and_error_messages():
         lb.kmeans_find_partitions(cent, x, 8)
 
 
+def test_concurrent_host_threads_share_an_index():
+    """SURVEY 8b threading: every symbol is re-entrant, each calling thread gets its own stream; the
+    reference searches partitions from many spawn_cpu threads at once (knn.rs:881, v2.rs:483)."""
+    import threading
+    n, d, K, M = 30000, 64, 32, 8
+    data = synth.gaussian_mixture(n, d, n_components=K, seed=501)
+    ix = lb.IvfPqIndex.build(data, "l2", lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, max_iters=6, pq_max_iters=4))
+    cent = ix.export()["centroids"]
+    qs = [synth.gaussian_mixture(200, d, n_components=K, seed=600 + t) for t in range(6)]
+    want = [(ix.search(q, k=10, nprobes=4), lb.compute_partitions(cent, q)) for q in qs]
+    got, errs = [None] * len(qs), []
+
+    def work(t):
+        try:
+            for _ in range(5):
+                got[t] = (ix.search(qs[t], k=10, nprobes=4), lb.compute_partitions(cent, qs[t]))
+        except Exception as e:  # noqa: BLE001 - reported below
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(len(qs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for (s1, p1), (s2, p2) in zip(want, got):
+        assert np.array_equal(s1[0], s2[0]) and np.array_equal(s1[1], s2[1])
+        assert all(np.array_equal(a, b) for a, b in zip(p1, p2))
+
+
 # ---- tensor-core filter path (tcgen05) must be bit-identical to the exact path -----------------
 def _both_paths(fn):
     import os
