@@ -187,12 +187,14 @@ def run_reference(args):
         return
     from oracle import binding as ob
     threads = ob.nthreads_default()
-    transform_rows = 200_000
-    data, queries = host_dataset_numpy(max(transform_rows, 65536 * 2), 2000)
+    # LB2_BENCH_REF_ROWS shrinks the CPU sample (tests/test_bench_contract.py runs this arm in seconds)
+    transform_rows = int(os.environ.get("LB2_BENCH_REF_ROWS", "200000"))
+    sample_rows = min(65536, transform_rows)
+    data, queries = host_dataset_numpy(max(transform_rows, sample_rows * 2), 2000)
     rng = np.random.default_rng(0)
     n = data.shape[0]
-    s_ivf = np.sort(rng.choice(n, 65536, replace=False))
-    s_pq = np.sort(rng.choice(n, 65536, replace=False))
+    s_ivf = np.sort(rng.choice(n, sample_rows, replace=False))
+    s_pq = np.sort(rng.choice(n, sample_rows, replace=False))
     times = []
     detail = None
     budget_s = 150.0
@@ -208,8 +210,8 @@ def run_reference(args):
     sec = float(np.mean(times))
     value = N_ROWS / sec / 1e6
     model = detail.pop("model")
-    qps = cpu_query_qps(ob, model, data[:transform_rows], queries, threads, 2000)
-    sample = (f"IVF + PQ training in full (2 x 65536-row samples, <=50 iters), transform on {transform_rows} of "
+    qps = cpu_query_qps(ob, model, data[:transform_rows], queries, threads, min(2000, queries.shape[0]))
+    sample = (f"IVF + PQ training in full (2 x {sample_rows}-row samples, <=50 iters), transform on {transform_rows} of "
               f"{N_ROWS} rows scaled linearly; {len(times)} timed steps")
     line = {
         "impl": "reference", "metric": "ivf_pq_index_build_mvec_per_s", "value": value, "unit": "Mvec/s",
