@@ -33,3 +33,23 @@ def test_reference_arm_prints_one_contract_line():
 
 def test_reference_arm_other_ranks_stay_silent():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
+
+
+def test_committed_bench_line_follows_the_contract():
+    """profiles/bench_r01_final.json is the line `python bench.py` printed on the B200 box."""
+    j = json.load(open(os.path.join(ROOT, "profiles", "bench_r01_final.json")))
+    base = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+            "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"}
+    assert base <= set(j)
+    assert j["n_gpus"] == 1 and j["warmup"] >= 3 and j["higher_is_better"] is True and j["scaling"] == "weak"
+    assert j["data"] == "synthetic" and j["dtype"] == "f32" and j["vs_baseline"] is None
+    assert abs(j["value"] - 1e6 / (j["ms_per_step"] * 1e-3) / 1e6) < 1e-6 * j["value"]      # 1M rows per step
+    r = j["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s")
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] is not None
+    e = j["e2e"]
+    assert e["h2d_bytes_per_step"] == 1_000_000 * 128 * 4 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < j["value"]
+    c = j["cpu_baseline"]
+    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    assert j["gpu_launches"] > 0 and not set(j["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(j["clocks"])
