@@ -173,6 +173,9 @@ lb2_status lb2_flat_topk(const float* dists, const uint64_t* row_ids, uint64_t n
 
 /* IvfTransformer::transform for IVF_PQ (lance-index/src/vector/ivf.rs:188-236,357): for a batch,
  * [normalise if cosine] -> partition id -> residual -> PQ code, in one pass over the vectors.
+ * `metric` is the index metric: it selects the partition assignment and whether residuals are taken
+ * (not for dot, PQBuildParams::use_residual); the PQ codes are L2 codes in every case, because the
+ * index builder trains its quantizer with DistanceType::L2 (rust/lance/src/index/vector/builder.rs:460).
  * valid_out[i] = 0 marks rows KeepFiniteVectors would drop (transform.rs:112-159). */
 lb2_status lb2_ivfpq_transform(const void* centroids, uint32_t k, const void* codebook,
                                uint32_t num_sub_vectors, uint32_t num_bits, uint32_t d,

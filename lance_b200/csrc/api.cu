@@ -746,7 +746,11 @@ lb2_status lb2_ivfpq_transform(const void* centroids, uint32_t k, const void* co
   }
   const int am = m == METRIC_DOT ? METRIC_DOT : METRIC_L2;
   assign_f32(xp, n, d, c.get(), k, am, nullptr, p.get(), nullptr, vp, nullptr);
-  pq_encode_any(xp, n, d, M, ds, cb.get(), am, am == METRIC_DOT ? nullptr : c.get(),
+  // The quantizer of an index build is trained -- and therefore encodes -- with L2 whatever the index
+  // metric is: Q::build(&training_data, DistanceType::L2, ..) (rust/lance/src/index/vector/builder.rs:460);
+  // the index metric only decides the partition assignment, whether residuals are taken (not for dot,
+  // PQBuildParams::use_residual) and the query-time lookup table.
+  pq_encode_any(xp, n, d, M, ds, cb.get(), METRIC_L2, am == METRIC_DOT ? nullptr : c.get(),
                 am == METRIC_DOT ? nullptr : p.get(), vp, (int)num_bits, co.get());
   p.commit(); co.commit(); v.commit();
   sync_stream();
@@ -1210,7 +1214,9 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
       VecIn cb_init(params->pq.codebook, ix->codebook_len(), model_dtype(dtype));
       lb2_pq_params pqp = params->pq;
       pqp.codebook = cb_init.get();
-      pq_train_dev(sample.p, s, d, am, &pqp, ix->codebook.p, &pq_iters);
+      // always L2 k-means (builder.rs:460: Q::build(&training_data, DistanceType::L2, ..)); for a dot index
+      // the sample is the raw vectors (no residual), for L2 / cosine the residuals computed above
+      pq_train_dev(sample.p, s, d, METRIC_L2, &pqp, ix->codebook.p, &pq_iters);
     }
     LB2_CUDA(cudaEventRecord(ev[2], c.stream));
     // 3. transform every row (lance-index/src/vector/ivf.rs:357: partition -> residual -> PQ)
@@ -1219,8 +1225,8 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
     if (copied) LB2_CUDA(cudaStreamWaitEvent(c.stream, copied, 0));  // the bulk copy must have landed
     TagScope* tg3 = new TagScope("transform");
     assign_f32(x, n, d, ix->centroids.p, K, am, nullptr, part.p, nullptr, valid.p, nullptr);
-    pq_encode_any(x, n, d, M, ds, ix->codebook.p, am, am == METRIC_DOT ? nullptr : ix->centroids.p,
-                  am == METRIC_DOT ? nullptr : part.p, valid.p, nbits, codes.p);
+    pq_encode_any(x, n, d, M, ds, ix->codebook.p, METRIC_L2, am == METRIC_DOT ? nullptr : ix->centroids.p,
+                  am == METRIC_DOT ? nullptr : part.p, valid.p, nbits, codes.p);  // L2 codes: see lb2_ivfpq_transform
     delete tg3;
     LB2_CUDA(cudaEventRecord(ev[3], c.stream));
     TagScope tg4("group");

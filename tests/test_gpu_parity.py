@@ -301,7 +301,8 @@ def test_index_4bit_build_search_matches_oracle(metric):
     order = np.argsort(parts["row_ids"])
     p_ref, _, _ = ob.compute_membership(parts["centroids"], data, metric=metric, nthreads=NT)
     res = data if metric == "dot" else ob.compute_residual(parts["centroids"], data, p_ref, nthreads=NT)
-    assert np.array_equal(parts["codes"][order], ob.pq_encode(parts["codebook"], res, nbits=4, metric=metric, nthreads=NT))
+    # codes are L2 codes whatever the index metric (builder.rs:460: the quantizer is built with DistanceType::L2)
+    assert np.array_equal(parts["codes"][order], ob.pq_encode(parts["codebook"], res, nbits=4, metric="l2", nthreads=NT))
     q = synth.gaussian_mixture(16, d, n_components=K, seed=415)
     for k, nprobes in ((10, 3), (250, 2)):                    # k > 200 moves flat_num
         ids, dists = ix.search(q, k=k, nprobes=nprobes)
