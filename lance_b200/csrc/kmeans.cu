@@ -10,9 +10,13 @@
 // Design: the reference sums each cluster's rows SEQUENTIALLY IN ROW ORDER in f32 and its losses in
 // f64, so the result depends on the order.  Instead of atomics (fast but order-free) we build, per
 // iteration, a stable counting sort of the rows by cluster (member lists in ascending row order)
-// and let one thread per (cluster, dimension) add its members in that order.  Given the same
-// initial centroids the trained model is therefore BIT-IDENTICAL to the reference loop (checked
-// against the oracle), at the cost of a sort of n 4-byte keys per iteration.
+// and add each cluster's members in that order: one warp per (cluster, 8-dimension chunk) gathers the
+// member rows 128 at a time and lanes 0..7 run the sequential f32 chains (update_body_warp), one warp
+// per cluster the f64 loss chain (stats_body).  Where no addition can round -- see "order-independent
+// sums" below -- the chain is replaced by a parallel reduction that returns the same bits.  Given the
+// same initial centroids the trained model is therefore BIT-IDENTICAL to the reference loop (checked
+// against the oracle), at the cost of a sort of n 4-byte keys per iteration.  The scalar bookkeeping
+// of an iteration runs in epilogue_kernel, and iterations 2.. replay one captured CUDA graph.
 #include <cooperative_groups.h>
 
 #include <algorithm>
