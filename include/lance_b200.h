@@ -84,7 +84,8 @@ lb2_status lb2_normalize(const void* vectors, uint64_t n, uint32_t d, lb2_dtype 
 typedef struct {
   uint32_t max_iters;      /* KMeansParams::max_iters, default 50 (kmeans.rs:92-103) */
   double tolerance;        /* 1e-4 */
-  uint32_t redos;          /* 1 */
+  uint32_t redos;          /* 1.  Every redo restarts from the same rng state (kmeans.rs:645-653), so without a
+                              balance bias redos > 1 equals one run; with a bias redos > 1 -> LB2_UNSUPPORTED */
   float balance_factor;    /* BEFORE the division by n that train_kmeans applies (kmeans.rs:1344);
                               IVF training passes 1.0 (rust/lance/src/index/vector/ivf.rs:1858) */
   uint32_t hierarchical_k; /* 16: for k > 256 (and no init_centroids) the reference's hierarchical
@@ -122,9 +123,9 @@ lb2_status lb2_compute_residual(const void* centroids, uint32_t k, uint32_t d, l
 /* ---- product quantisation (lance-index/src/vector/pq*.rs) ------------------------------------ */
 typedef struct {
   uint32_t num_sub_vectors; /* PQBuildParams (pq/builder.rs:27-59): 16 */
-  uint32_t num_bits;        /* 8 (4 is not implemented on the device yet -> LB2_UNSUPPORTED) */
+  uint32_t num_bits;        /* 8 or 4 */
   uint32_t max_iters;       /* 50 */
-  uint32_t kmeans_redos;    /* 1 */
+  uint32_t kmeans_redos;    /* 1 (PQ k-means has no balance bias: any value equals one run, see redos above) */
   uint64_t sample_rate;     /* 256 */
   const void* codebook;     /* user codebook to continue from, or NULL */
   uint64_t seed;
@@ -137,13 +138,14 @@ lb2_status lb2_pq_train(const void* data, uint64_t n, uint32_t d, lb2_dtype dtyp
                         lb2_metric metric, const lb2_pq_params* params, void* codebook_out,
                         uint32_t* iters_out);
 
-/* ProductQuantizer::quantize / transform_impl (pq.rs:116-191,430).  When `centroids` and
- * `part_ids` are given the residual (residual.rs:161-205) is fused: codes of v - centroids[part].
+/* ProductQuantizer::quantize / transform_impl (pq.rs:116-191,430).  When `centroids`
+ * ([num_centroids][d]) and `part_ids` are given the residual (residual.rs:161-205) is fused: codes of
+ * v - centroids[part]; a part id >= num_centroids is LB2_INVALID_ARG.
  * codes_out is row-major [n][M] (8-bit) or [n][M/2] (4-bit: byte i = code[2i+1] << 4 | code[2i],
  * pq.rs:168-173; 16 codewords per sub-space, M even). */
 lb2_status lb2_pq_encode(const void* codebook, uint32_t num_sub_vectors, uint32_t num_bits,
                          uint32_t d, lb2_dtype dtype, lb2_metric metric, const void* centroids,
-                         const uint32_t* part_ids, const void* vectors, uint64_t n,
+                         uint32_t num_centroids, const uint32_t* part_ids, const void* vectors, uint64_t n,
                          uint8_t* codes_out);
 
 /* build_distance_table_l2 / _dot (pq/distance.rs:24-92): lut_out[M * 2^nbits] f32 */
@@ -170,6 +172,13 @@ lb2_status lb2_pq_scan_4bit(const float* lut, uint32_t num_sub_vectors, lb2_metr
  * (distance, position) pairs; out sorted ascending by (distance, row id).  *count_out <= k. */
 lb2_status lb2_flat_topk(const float* dists, const uint64_t* row_ids, uint64_t n, uint32_t k,
                          uint64_t* ids_out, float* dists_out, uint32_t* count_out);
+/* The same with FlatIndex::search's range branch (flat/index.rs:100-115): only rows with
+ * lower <= dist < upper (f32::total_cmp order; an absent bound is f32::MIN / f32::MAX, as the reference
+ * unwraps it) are offered to the heap.  Both calls return exactly the SET the reference's BinaryHeap ends
+ * with -- also when more rows tie at the k-th distance than fit (the heap's sift order is restated). */
+lb2_status lb2_flat_topk_range(const float* dists, const uint64_t* row_ids, uint64_t n, uint32_t k,
+                               int has_lower, float lower, int has_upper, float upper,
+                               uint64_t* ids_out, float* dists_out, uint32_t* count_out);
 
 /* IvfTransformer::transform for IVF_PQ (lance-index/src/vector/ivf.rs:188-236,357): for a batch,
  * [normalise if cosine] -> partition id -> residual -> PQ code, in one pass over the vectors.
@@ -225,6 +234,11 @@ typedef struct {
   const void* refine_vectors;   /* raw column, see lb2_index_search_refine; required when refine_factor > 0 */
   uint64_t num_vectors;
   const uint64_t* allow_bitmap; /* nullable */
+  /* range query (Query::lower_bound / upper_bound, lance-index/src/vector.rs:83-86): inside a partition
+   * only rows with lower <= _distance < upper enter the top-k (flat/index.rs:100-115, index distances);
+   * with refine the plan filters the exact distances the same way afterwards (scanner.rs:3342-3377) */
+  uint32_t has_lower_bound, has_upper_bound;
+  float lower_bound, upper_bound;
 } lb2_search_params;
 lb2_status lb2_index_search_ex(lb2_index* index, const void* queries, uint64_t nq,
                                const lb2_search_params* params, uint64_t* row_ids_out, float* dists_out,

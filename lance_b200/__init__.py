@@ -17,7 +17,7 @@ from ._lib import (BF16, COSINE, DOT, F16, F32, L2, METRICS, U8, BuildParams, Bu
 
 __all__ = ["device_count", "DeviceArray", "PinnedArray", "LanceB200Error", "train_kmeans",
            "compute_partitions", "kmeans_find_partitions", "compute_residual", "normalize_fsl",
-           "l2_distance_batch", "dot_distance_batch", "PQBuildParams", "ProductQuantizer",
+           "l2_distance_batch", "dot_distance_batch", "cosine_distance_batch", "PQBuildParams", "ProductQuantizer",
            "build_distance_table_l2", "compute_pq_distance", "flat_topk", "IvfPqIndex",
            "IvfBuildParams", "IvfFlatIndex", "launch_count", "profile"]
 
@@ -123,13 +123,20 @@ def dot_distance_batch(frm, to, dimension):
     return _distance_batch(frm, to, dimension, DOT)
 
 
+def cosine_distance_batch(frm, to, dimension):
+    """lance_linalg::distance::cosine_distance_batch (cosine.rs:266-290)."""
+    return _distance_batch(frm, to, dimension, COSINE)
+
+
 def _distance_batch(frm, to, d, metric):
-    frm, to = _f32(frm), _f32(to)
+    """f32 / f16 / u8 inputs keep their element type (u8 L2 = the reference's integer sum, l2.rs:44-49)."""
+    to, dt = _typed(to)
+    frm = np.ascontiguousarray(frm, dtype=to.dtype) if not isinstance(frm, (DeviceArray, PinnedArray)) else frm
     n = int(np.prod(to.shape)) // d
     out = np.empty(n, np.float32)
     fp, _k1 = as_ptr(frm)
     tp, _k2 = as_ptr(to)
-    check(lib().lb2_distance_batch(fp, tp, C.c_uint64(n), C.c_uint32(d), C.c_int(F32),
+    check(lib().lb2_distance_batch(fp, tp, C.c_uint64(n), C.c_uint32(d), C.c_int(dt),
                                    C.c_int(metric), C.c_void_p(out.ctypes.data)))
     return out
 
@@ -284,7 +291,8 @@ class ProductQuantizer:
         pp, _k3 = as_ptr(parts)
         check(lib().lb2_pq_encode(C.c_void_p(self.codebook.ctypes.data), C.c_uint32(self.num_sub_vectors),
                                   C.c_uint32(self.num_bits), C.c_uint32(d), C.c_int(F32),
-                                  C.c_int(_metric(self.distance_type)), cp, pp, vp, C.c_uint64(n),
+                                  C.c_int(_metric(self.distance_type)), cp,
+                                  C.c_uint32(0 if cent is None else cent.shape[0]), pp, vp, C.c_uint64(n),
                                   C.c_void_p(out.ctypes.data)))
         return out
 
@@ -324,16 +332,19 @@ def compute_pq_distance_4bit(distance_table, num_sub_vectors, code_transposed, k
     return out
 
 
-def flat_topk(dists, row_ids, k):
-    """FlatIndex::search fast path (flat/index.rs:97-127) over a distance array."""
+def flat_topk(dists, row_ids, k, lower_bound=None, upper_bound=None):
+    """FlatIndex::search fast path (flat/index.rs:97-127) over a distance array, optionally with the
+    range branch (:100-115)."""
     dists = _f32(dists)
     n = dists.size
     rid = None if row_ids is None else np.ascontiguousarray(row_ids, dtype=np.uint64)
     oi, od, cnt = np.empty(k, np.uint64), np.empty(k, np.float32), np.zeros(1, np.uint32)
     rp, _k = as_ptr(rid)
-    check(lib().lb2_flat_topk(C.c_void_p(dists.ctypes.data), rp, C.c_uint64(n), C.c_uint32(k),
-                              C.c_void_p(oi.ctypes.data), C.c_void_p(od.ctypes.data),
-                              C.c_void_p(cnt.ctypes.data)))
+    check(lib().lb2_flat_topk_range(C.c_void_p(dists.ctypes.data), rp, C.c_uint64(n), C.c_uint32(k),
+                                    C.c_int(lower_bound is not None), C.c_float(lower_bound or 0.0),
+                                    C.c_int(upper_bound is not None), C.c_float(upper_bound or 0.0),
+                                    C.c_void_p(oi.ctypes.data), C.c_void_p(od.ctypes.data),
+                                    C.c_void_p(cnt.ctypes.data)))
     return oi[:cnt[0]], od[:cnt[0]]
 
 
@@ -513,8 +524,9 @@ class IvfPqIndex:
                                       C.c_void_p(bm.ctypes.data)))
         return bm
 
-    def search_ex(self, queries, k=10, nprobes=1, allow_bitmap=None, refine_factor=0, vectors=None, out=None):
-        """lb2_index_search_ex: prefilter (bitmap from row_mask) and/or refine in one call."""
+    def search_ex(self, queries, k=10, nprobes=1, allow_bitmap=None, refine_factor=0, vectors=None, out=None,
+                  lower_bound=None, upper_bound=None):
+        """lb2_index_search_ex: prefilter (bitmap from row_mask), range bounds and/or refine in one call."""
         from ._lib import SearchParams
         dt = getattr(self, "_dt", F32)
         npdt = {F32: np.float32, F16: np.float16, U8: np.uint8, BF16: np.uint16}[dt]
@@ -533,7 +545,9 @@ class IvfPqIndex:
         ip, _k2 = as_ptr(ids)
         dp, _k3 = as_ptr(dists)
         sp = SearchParams(k, nprobes, refine_factor, vp.value if vp is not None else None,
-                          0 if vectors is None else vectors.shape[0], bp.value if bp is not None else None)
+                          0 if vectors is None else vectors.shape[0], bp.value if bp is not None else None,
+                          int(lower_bound is not None), int(upper_bound is not None),
+                          float(lower_bound or 0.0), float(upper_bound or 0.0))
         check(lib().lb2_index_search_ex(self._h, qp, C.c_uint64(nq), C.byref(sp), ip, dp, None))
         return ids, dists
 

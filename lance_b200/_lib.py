@@ -60,7 +60,7 @@ EXPORTS = [
     "lb2_profile_enable", "lb2_profile_get", "lb2_profile_reset", "lb2_profile_dump", "lb2_timer_start", "lb2_timer_stop",
     "lb2_distance_batch", "lb2_normalize", "lb2_kmeans_params_default", "lb2_kmeans_train",
     "lb2_compute_partitions", "lb2_find_partitions", "lb2_compute_residual", "lb2_pq_params_default",
-    "lb2_pq_train", "lb2_pq_encode", "lb2_pq_build_lut", "lb2_pq_scan", "lb2_flat_topk",
+    "lb2_pq_train", "lb2_pq_encode", "lb2_pq_build_lut", "lb2_pq_scan", "lb2_flat_topk", "lb2_flat_topk_range",
     "lb2_ivfpq_transform", "lb2_index_create", "lb2_index_load", "lb2_index_search", "lb2_index_search_refine",
     "lb2_index_search_ex", "lb2_index_row_mask", "lb2_pq_scan_4bit",
     "lb2_index_info", "lb2_index_export", "lb2_index_destroy", "lb2_ivfpq_build_params_default",
@@ -108,7 +108,9 @@ def device_count():
 class SearchParams(C.Structure):
     """lb2_search_params (include/lance_b200.h)."""
     _fields_ = [("k", C.c_uint32), ("nprobes", C.c_uint32), ("refine_factor", C.c_uint32),
-                ("refine_vectors", C.c_void_p), ("num_vectors", C.c_uint64), ("allow_bitmap", C.c_void_p)]
+                ("refine_vectors", C.c_void_p), ("num_vectors", C.c_uint64), ("allow_bitmap", C.c_void_p),
+                ("has_lower_bound", C.c_uint32), ("has_upper_bound", C.c_uint32),
+                ("lower_bound", C.c_float), ("upper_bound", C.c_float)]
 
 
 class DeviceArray:

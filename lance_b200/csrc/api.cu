@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <memory>
 
 #include "assign.cuh"
 #include "comm.cuh"
@@ -145,6 +146,67 @@ __global__ void widen_offsets_kernel(const uint32_t* __restrict__ off32, int K,
   if (i <= K) off64[i] = off32[i];
 }
 
+// largest partition id of a caller-supplied id column (range check before it indexes device memory)
+__global__ void max_u32_kernel(const uint32_t* __restrict__ v, uint64_t n, uint32_t* __restrict__ out) {
+  uint32_t m = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    m = max(m, v[i]);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// KeepFiniteVectors (lance-index/src/vector/transform.rs:112-159) / the is_finite filter applied to the
+// training sample (rust/lance/src/index/vector/builder.rs:436): flag[r] = every element of row r is finite
+__global__ void finite_rows_kernel(const float* __restrict__ x, uint64_t n, int d, uint8_t* __restrict__ flag) {
+  const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  bool ok = true;
+  for (int e = lane; e < d; e += 32) ok &= isfinite(x[w * d + e]);
+  ok = __all_sync(0xffffffffu, ok);
+  if (lane == 0) flag[w] = ok ? 1 : 0;
+}
+
+// l2_distance_uint_scalar (lance-linalg/src/distance/l2.rs:44-49, impl L2 for u8 :93-98): sum of |x - y|^2 in
+// u32 (wrapping, like Rust's release-mode `sum::<u32>()`), then `as f32` (round to nearest even); warp per row
+__global__ void l2_u8_kernel(const uint8_t* __restrict__ from, const uint8_t* __restrict__ to, uint64_t n, int d,
+                             float* __restrict__ out) {
+  const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  uint32_t s = 0;
+  for (int e = lane; e < d; e += 32) {
+    const int df = (int)from[e] - (int)to[w * d + e];
+    s += (uint32_t)(df * df);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[w] = __uint2float_rn(s);
+}
+// cosine_distance_batch (cosine.rs:143-174,266-290): 1 - xy / |x| / sqrt(yy) with f32 FMA lanes; the
+// reference's own lane order is ISA specific, so parity is the reference's tolerance (cosine.rs:361-393)
+__global__ void cosine_f32_kernel(const float* __restrict__ from, const float* __restrict__ to, uint64_t n, int d,
+                                  float* __restrict__ out) {
+  const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  float xx = 0.0f, xy = 0.0f, yy = 0.0f;
+  for (int e = lane; e < d; e += 32) {
+    const float x = from[e], y = to[w * d + e];
+    xx = fmaf(x, x, xx);
+    xy = fmaf(x, y, xy);
+    yy = fmaf(y, y, yy);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    xx += __shfl_xor_sync(0xffffffffu, xx, o);
+    xy += __shfl_xor_sync(0xffffffffu, xy, o);
+    yy += __shfl_xor_sync(0xffffffffu, yy, o);
+  }
+  if (lane == 0) out[w] = 1.0f - xy / sqrtf(xx) / sqrtf(yy);
+}
+
 // ---- element types ---------------------------------------------------------------------------------
 // f16 / bf16 / u8 buffers are converted to f32 on the device at the boundary and every loop runs
 // with the reference's f32 semantics (what the reference itself does for Int8 vectors,
@@ -245,39 +307,90 @@ struct lb2_index {
 
 namespace lb2 {
 
-static void index_load_dev(lb2_index* ix, const uint32_t* part_ids, const uint8_t* codes,
-                           const uint64_t* row_ids, uint64_t n) {
+// a partition id >= K (a corrupted / mismatched shuffle file) would index device memory out of bounds
+static void check_part_ids(const uint32_t* part_ids, uint64_t n, uint32_t K, const char* what) {
+  if (n == 0) return;
+  DevBuf<uint32_t> mx(1);
+  mx.zero();
+  LB2_LAUNCH("check_part_ids", max_u32_kernel, (unsigned)std::min<uint64_t>(cdiv(n, 1024), 1024), 256, 0, part_ids, n, mx.p);
+  uint32_t h = 0;
+  d2h(&h, mx.p, 1);
+  sync_stream();
+  if (h >= K) fail(LB2_INVALID_ARG, "%s: partition id %u out of range (the index has %u partitions)", what, h, K);
+}
+
+// stable grouping of the kept rows by partition; rows with valid[r] == 0 (KeepFiniteVectors,
+// transform.rs:112-159: NaN / Inf rows, zero vectors under cosine) never enter the index
+static uint64_t member_sort_index(MemberSort& ms, lb2_index* ix, const uint32_t* part_ids, const uint8_t* valid,
+                                  uint64_t n) {
   LB2_REQUIRE(n < 0xffffffffull, "more than 2^32-1 rows per index shard");
-  MemberSort ms;
-  ms.run(part_ids, nullptr, n, ix->K, 1, nullptr);
+  ms.run(part_ids, valid, n, ix->K, 1, nullptr);
   ix->part_offsets.alloc(ix->K + 1);
+  if (n == 0) {
+    ix->part_offsets.zero();
+    return 0;
+  }
   LB2_LAUNCH("widen_offsets", widen_offsets_kernel, cdiv(ix->K + 1, 256), 256, 0, ms.offsets.p,
              ix->K, ix->part_offsets.p);
-  ix->codes.alloc(std::max<uint64_t>(1, n * ix->code_bytes()));
-  ix->row_ids.alloc(std::max<uint64_t>(1, n));
-  if (n)
-    LB2_LAUNCH("group_by_partition", group_kernel, cdiv(n, 256), 256, 0, ms.members.p, n, ix->code_bytes(),
+  uint32_t kept = 0;
+  d2h(&kept, ms.offsets.p + ix->K, 1);
+  sync_stream();
+  return kept;
+}
+
+static void index_load_dev(lb2_index* ix, const uint32_t* part_ids, const uint8_t* codes,
+                           const uint64_t* row_ids, uint64_t n, const uint8_t* valid = nullptr) {
+  MemberSort ms;
+  const uint64_t kept = member_sort_index(ms, ix, part_ids, valid, n);
+  ix->codes.alloc(std::max<uint64_t>(1, kept * ix->code_bytes()));
+  ix->row_ids.alloc(std::max<uint64_t>(1, kept));
+  if (kept)
+    LB2_LAUNCH("group_by_partition", group_kernel, cdiv(kept, 256), 256, 0, ms.members.p, kept, ix->code_bytes(),
                codes, row_ids, ix->codes.p, ix->row_ids.p);
-  ix->n = n;
+  ix->n = kept;
   sync_stream();
 }
 
 static void index_load_flat_dev(lb2_index* ix, const uint32_t* part_ids, const float* vectors,
-                                const uint64_t* row_ids, uint64_t n) {
-  LB2_REQUIRE(n < 0xffffffffull, "more than 2^32-1 rows per index shard");
+                                const uint64_t* row_ids, uint64_t n, const uint8_t* valid = nullptr) {
   LB2_REQUIRE(ix->d % 4 == 0, "IVF_FLAT needs a dimension that is a multiple of 4");
   MemberSort ms;
-  ms.run(part_ids, nullptr, n, ix->K, 1, nullptr);
-  ix->part_offsets.alloc(ix->K + 1);
-  LB2_LAUNCH("widen_offsets", widen_offsets_kernel, cdiv(ix->K + 1, 256), 256, 0, ms.offsets.p,
-             ix->K, ix->part_offsets.p);
-  ix->vectors.alloc(std::max<uint64_t>(1, n * ix->d));
-  ix->row_ids.alloc(std::max<uint64_t>(1, n));
-  if (n)
-    LB2_LAUNCH("group_vectors", group_vectors_kernel, cdiv(n * (ix->d / 4), 256), 256, 0, ms.members.p, n,
+  const uint64_t kept = member_sort_index(ms, ix, part_ids, valid, n);
+  ix->vectors.alloc(std::max<uint64_t>(1, kept * ix->d));
+  ix->row_ids.alloc(std::max<uint64_t>(1, kept));
+  if (kept)
+    LB2_LAUNCH("group_vectors", group_vectors_kernel, cdiv(kept * (ix->d / 4), 256), 256, 0, ms.members.p, kept,
                ix->d, vectors, row_ids, ix->vectors.p, ix->row_ids.p);
-  ix->n = n;
+  ix->n = kept;
   sync_stream();
+}
+
+// Training sample of a build: rows `rows` (ascending) of x, minus the rows that are not finite
+// (rust/lance/src/index/vector/builder.rs:436 keeps `is_finite` rows only; under cosine a zero vector
+// has become NaN by then).  Returns the number of rows kept in `out` ([rows.size()][d]).
+static uint64_t gather_finite_sample(const float* x, std::vector<uint64_t>& rows, int d, DevBuf<float>& out) {
+  uint64_t s = rows.size();
+  out.alloc(std::max<uint64_t>(1, s * d));
+  if (s == 0) return 0;
+  DevBuf<uint64_t> rows_d(s);
+  DevBuf<uint8_t> flag(s);
+  h2d(rows_d.p, rows.data(), s);
+  LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(s * d, 256), 256, 0, x, rows_d.p, s, d, out.p);
+  LB2_LAUNCH("finite_rows", finite_rows_kernel, cdiv(s * 32, 256), 256, 0, out.p, s, d, flag.p);
+  std::vector<uint8_t> hf(s);
+  d2h(hf.data(), flag.p, s);
+  sync_stream();
+  uint64_t kept = 0;
+  for (uint64_t i = 0; i < s; ++i)
+    if (hf[i]) rows[kept++] = rows[i];
+  if (kept == s) return s;
+  rows.resize(kept);  // rare: gather again without the dropped rows (order preserved)
+  if (kept) {
+    h2d(rows_d.p, rows.data(), kept);
+    LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(kept * d, 256), 256, 0, x, rows_d.p, kept, d, out.p);
+    sync_stream();
+  }
+  return kept;
 }
 
 // s distinct rows out of n, ascending: one uniformly random row from each of s equal strata
@@ -316,12 +429,24 @@ static void pq_encode_any(const float* x, uint64_t n, int d, int M, int ds, cons
   sync_stream();  // `wide` is freed on return
 }
 
+// KMeansParams::redos (kmeans.rs:643-716).  Every redo starts from `rng.clone()` of the same generator
+// (kmeans.rs:645-653), i.e. from the SAME initial centroids; the only state carried from one redo to the
+// next is cluster_sizes / adjusted_balance_factor, which only enter through the balance bias.  With
+// balance_factor == 0 (every PQ codebook, pq/builder.rs:100) all redos are therefore identical and
+// "best of redos" is the single run; with a balance bias the redo loop is not implemented -> UNSUPPORTED.
+static void check_redos(uint32_t redos, float balance_factor) {
+  if (redos == 0) fail(LB2_INVALID_ARG, "KMeans: redos must be at least 1");
+  if (redos > 1 && balance_factor != 0.0f)
+    fail(LB2_UNSUPPORTED, "KMeans: redos = %u with a balance factor is not implemented (redos = 1 only)", redos);
+}
+
 static void pq_train_dev(const float* data, uint64_t n, int d, int metric, const lb2_pq_params* p,
                          float* codebook, std::vector<uint32_t>* iters) {
   const int M = p->num_sub_vectors, K = 1 << p->num_bits;
   LB2_REQUIRE(M > 0 && d % M == 0, "num_sub_vectors must divide vector dimension %d, but got %d", d, M);
   if (p->num_bits != 8 && p->num_bits != 4)  // pq/builder.rs: only 4 and 8 exist in the reference
     fail(LB2_INVALID_ARG, "PQ: num_bits must be 4 or 8, got %u", p->num_bits);
+  check_redos(p->kmeans_redos, 0.0f);
   LB2_REQUIRE(current_comm() || n >= (uint64_t)K, "Not enough rows to train PQ. Requires %d rows but only %llu available",
               K, (unsigned long long)n);
   // free fn train_kmeans (kmeans.rs:1328-1340): first sample_rate*k rows (per-rank share when sharded)
@@ -487,11 +612,23 @@ lb2_status lb2_distance_batch(const void* from, const void* to, uint64_t n, uint
                               lb2_dtype dtype, lb2_metric metric, float* out) {
   LB2_API_BEGIN
   const int m = metric_of(metric);
-  if (m == METRIC_COSINE) fail(LB2_UNSUPPORTED, "cosine_distance_batch is not implemented yet");
   LB2_REQUIRE(d > 0, "dimension must be positive");
   LB2_REQUIRE(n < (1ull << 31), "too many rows");
-  VecIn f(from, d, dtype), t(to, (size_t)n * d, dtype);
   OutArg<float> o(out, n);
+  if (dtype == LB2_U8 && m == METRIC_L2) {  // integer arithmetic (l2.rs:44-49)
+    InArg<uint8_t> f8(from, d), t8(to, (size_t)n * d);
+    if (n) LB2_LAUNCH("l2_u8", l2_u8_kernel, cdiv(n * 32, 256), 256, 0, f8.get(), t8.get(), n, (int)d, o.get());
+    o.commit();
+    sync_stream();
+    return LB2_OK;
+  }
+  VecIn f(from, d, dtype), t(to, (size_t)n * d, dtype);
+  if (m == METRIC_COSINE) {
+    if (n) LB2_LAUNCH("cosine_batch", cosine_f32_kernel, cdiv(n * 32, 256), 256, 0, f.get(), t.get(), n, (int)d, o.get());
+    o.commit();
+    sync_stream();
+    return LB2_OK;
+  }
   assign_f32(f.get(), 1, d, t.get(), (int)n, m, nullptr, nullptr, nullptr, nullptr, o.get());
   o.commit();
   sync_stream();
@@ -513,6 +650,7 @@ lb2_status lb2_kmeans_train(const void* data, uint64_t n, uint32_t d, lb2_dtype 
                             uint32_t* iters_out) {
   LB2_API_BEGIN
   LB2_REQUIRE(params && data && centroids_out, "null argument");
+  check_redos(params->redos, params->balance_factor);
   const int m = metric_of(params->metric);
   if (m == METRIC_COSINE)
     fail(LB2_INVALID_ARG, "KMeans: cosine is trained as L2 on normalised vectors (normalise first)");
@@ -587,6 +725,7 @@ lb2_status lb2_compute_residual(const void* centroids, uint32_t k, uint32_t d, l
   LB2_API_BEGIN
   VecIn c(centroids, (size_t)k * d, model_dtype(dtype)), x(vectors, (size_t)n * d, dtype);
   InArg<uint32_t> p(part_ids, n);
+  check_part_ids(p.get(), n, k, "compute_residual");
   VecOut o(out, (size_t)n * d, model_dtype(dtype));
   if (n)
     LB2_LAUNCH("residual", residual_kernel, cdiv(n * d, 256), 256, 0, x.get(), c.get(), p.get(), n,
@@ -622,7 +761,7 @@ lb2_status lb2_pq_train(const void* data, uint64_t n, uint32_t d, lb2_dtype dtyp
 
 lb2_status lb2_pq_encode(const void* codebook, uint32_t num_sub_vectors, uint32_t num_bits,
                          uint32_t d, lb2_dtype dtype, lb2_metric metric, const void* centroids,
-                         const uint32_t* part_ids, const void* vectors, uint64_t n,
+                         uint32_t num_centroids, const uint32_t* part_ids, const void* vectors, uint64_t n,
                          uint8_t* codes_out) {
   LB2_API_BEGIN
   if (num_bits != 8 && num_bits != 4) fail(LB2_INVALID_ARG, "PQ: num_bits must be 4 or 8, got %u", num_bits);
@@ -631,25 +770,14 @@ lb2_status lb2_pq_encode(const void* codebook, uint32_t num_sub_vectors, uint32_
   LB2_REQUIRE(num_bits == 8 || M % 2 == 0, "PQ: num_sub_vectors must be divisible by 2 for num_bits=4, but got %d", M);
   LB2_REQUIRE((centroids == nullptr) == (part_ids == nullptr),
               "centroids and part_ids must be given together");
+  LB2_REQUIRE(centroids == nullptr || num_centroids > 0, "num_centroids must be given with centroids");
   const int ncode = 1 << num_bits;
   const int m = metric_of(metric) == METRIC_DOT ? METRIC_DOT : METRIC_L2;
   if (!small_d_supported(ds)) fail(LB2_UNSUPPORTED, "PQ sub-vector width %d not supported yet", ds);
   VecIn cb(codebook, (size_t)ncode * d, model_dtype(dtype)), x(vectors, (size_t)n * d, dtype);
-  uint64_t kmax = 0;
-  VecIn c;
+  VecIn c(centroids, (size_t)num_centroids * d, model_dtype(dtype));
   InArg<uint32_t> p(part_ids, n);
-  if (centroids) {
-    // the number of IVF centroids is implied by part_ids; stage what the caller holds
-    if (is_device_ptr(centroids)) {
-      if (model_dtype(dtype) != LB2_F32)
-        fail(LB2_UNSUPPORTED, "pq_encode: device-resident non-f32 centroids need their count; use lb2_ivfpq_transform");
-      c.p = (const float*)centroids;
-    } else {
-      for (uint64_t i = 0; i < n && !is_device_ptr(part_ids); ++i) kmax = std::max<uint64_t>(kmax, part_ids[i]);
-      if (is_device_ptr(part_ids)) fail(LB2_INVALID_ARG, "host centroids with device part_ids");
-      c.set(centroids, (size_t)(kmax + 1) * d, model_dtype(dtype));
-    }
-  }
+  if (centroids) check_part_ids(p.get(), n, num_centroids, "pq_encode");
   OutArg<uint8_t> o(codes_out, (size_t)n * (num_bits == 4 ? M / 2 : M));
   pq_encode_any(x.get(), n, d, M, ds, cb.get(), m, c.get(), p.get(), nullptr, (int)num_bits, o.get());
   o.commit();
@@ -699,8 +827,19 @@ lb2_status lb2_pq_scan(const float* lut, uint32_t num_sub_vectors, uint32_t num_
   LB2_API_END
 }
 
-lb2_status lb2_flat_topk(const float* dists, const uint64_t* row_ids, uint64_t n, uint32_t k,
-                         uint64_t* ids_out, float* dists_out, uint32_t* count_out) {
+static ScanFilter make_filter(const uint64_t* allow, int has_lower, float lower, int has_upper, float upper) {
+  ScanFilter f;
+  f.allow = allow;
+  f.range = (has_lower || has_upper) ? 1 : 0;
+  // flat/index.rs:101-102: lower_bound.unwrap_or(f32::MIN), upper_bound.unwrap_or(f32::MAX)
+  f.lo_key = host_total_key(has_lower ? lower : -3.40282347e+38f);
+  f.hi_key = host_total_key(has_upper ? upper : 3.40282347e+38f);
+  return f;
+}
+
+lb2_status lb2_flat_topk_range(const float* dists, const uint64_t* row_ids, uint64_t n, uint32_t k,
+                               int has_lower, float lower, int has_upper, float upper,
+                               uint64_t* ids_out, float* dists_out, uint32_t* count_out) {
   LB2_API_BEGIN
   LB2_REQUIRE(k > 0, "k must be positive");
   LB2_REQUIRE(n < 0xffffffffull, "too many rows");
@@ -712,10 +851,16 @@ lb2_status lb2_flat_topk(const float* dists, const uint64_t* row_ids, uint64_t n
   DevBuf<uint32_t> cnt_tmp;
   uint32_t* cp = oc.get();
   if (!cp) { cnt_tmp.alloc(1); cp = cnt_tmp.p; }
-  flat_topk_f32(dd.get(), r.get(), n, k, oi.get(), od.get(), cp);
+  flat_topk_f32(dd.get(), r.get(), n, k, make_filter(nullptr, has_lower, lower, has_upper, upper), oi.get(),
+                od.get(), cp);
   oi.commit(); od.commit(); oc.commit();
   sync_stream();
   LB2_API_END
+}
+
+lb2_status lb2_flat_topk(const float* dists, const uint64_t* row_ids, uint64_t n, uint32_t k,
+                         uint64_t* ids_out, float* dists_out, uint32_t* count_out) {
+  return lb2_flat_topk_range(dists, row_ids, n, k, 0, 0.0f, 0, 0.0f, ids_out, dists_out, count_out);
 }
 
 lb2_status lb2_ivfpq_transform(const void* centroids, uint32_t k, const void* codebook,
@@ -792,6 +937,7 @@ lb2_status lb2_index_load(lb2_index* index, const uint32_t* part_ids, const uint
   InArg<uint32_t> p(part_ids, n);
   InArg<uint8_t> c(codes, (size_t)n * index->code_bytes());
   InArg<uint64_t> r(row_ids, n);
+  check_part_ids(p.get(), n, (uint32_t)index->K, "index_load");
   index_load_dev(index, p.get(), c.get(), r.get(), n);
   LB2_API_END
 }
@@ -800,7 +946,8 @@ lb2_status lb2_index_load(lb2_index* index, const uint32_t* part_ids, const uint
 static void index_search_impl(lb2_index* index, const void* queries, uint64_t nq, uint32_t k, uint32_t nprobes,
                               uint32_t refine_factor, const void* vectors, uint64_t num_vectors,
                               const uint64_t* allow_bitmap, uint64_t* row_ids_out, float* dists_out,
-                              uint32_t* counts_out) {
+                              uint32_t* counts_out, int has_lower = 0, float lower = 0.0f, int has_upper = 0,
+                              float upper = 0.0f) {
   LB2_REQUIRE(index && k > 0 && nprobes > 0, "bad argument");
   const bool refine = refine_factor > 0 && vectors != nullptr;
   const uint64_t kc = refine ? (uint64_t)k * refine_factor : k;
@@ -830,18 +977,20 @@ static void index_search_impl(lb2_index* index, const void* queries, uint64_t nq
   float* sd = refine ? cdist.p : od.get();
   uint32_t* sc = refine ? ccnt.p : oc.get();
   TagScope tg("search");
+  const ScanFilter flt = make_filter(allow_bitmap ? allow.get() : nullptr, has_lower, lower, has_upper, upper);
   if (index->kind == 1)
     ivfflat_search_f32(index->centroids.p, index->K, d, index->metric, index->part_offsets.p, index->vectors.p,
-                       index->row_ids.p, qp, nq, (int)kc, nprobes, si, sd, sc, allow_bitmap ? allow.get() : nullptr);
+                       index->row_ids.p, qp, nq, (int)kc, nprobes, si, sd, sc, flt);
   else
     ivfpq_search_f32(index->centroids.p, index->K, d, index->metric, index->codebook.p, index->M, index->nbits,
                      index->part_offsets.p, index->codes.p, index->row_ids.p, qp, nq, (int)kc, nprobes, si, sd,
-                     sc, allow_bitmap ? allow.get() : nullptr);
+                     sc, flt);
   if (refine) {
-    // exact re-rank with the true metric on the ORIGINAL (un-normalised) query, as flat_knn does
+    // exact re-rank with the true metric on the ORIGINAL (un-normalised) query, as flat_knn does; the
+    // plan then filters `_distance >= lower AND _distance < upper` on the exact distances (scanner.rs:3342-3377)
     VecIn v(vectors, (size_t)num_vectors * d, index->dtype);
     refine_f32(q.get(), nq, d, index->metric, v.get(), num_vectors, cid.p, ccnt.p, (int)kc, (int)k, oi.get(),
-               od.get(), oc.get());
+               od.get(), oc.get(), has_lower, lower, has_upper, upper);
     oi.commit(); od.commit(); oc.commit();
     sync_stream();
     return;
@@ -876,7 +1025,8 @@ lb2_status lb2_index_search_ex(lb2_index* index, const void* queries, uint64_t n
   LB2_REQUIRE(sp, "null search params");
   LB2_REQUIRE(sp->refine_factor == 0 || sp->refine_vectors, "refine_factor > 0 needs refine_vectors");
   index_search_impl(index, queries, nq, sp->k, sp->nprobes, sp->refine_factor, sp->refine_vectors,
-                    sp->num_vectors, sp->allow_bitmap, row_ids_out, dists_out, counts_out);
+                    sp->num_vectors, sp->allow_bitmap, row_ids_out, dists_out, counts_out, sp->has_lower_bound != 0,
+                    sp->lower_bound, sp->has_upper_bound != 0, sp->upper_bound);
   LB2_API_END
 }
 
@@ -961,6 +1111,7 @@ lb2_status lb2_index_load_flat(lb2_index* index, const uint32_t* part_ids, const
   InArg<uint32_t> p(part_ids, n);
   VecIn v(vectors, (size_t)n * index->d, index->dtype);
   InArg<uint64_t> r(row_ids, n);
+  check_part_ids(p.get(), n, (uint32_t)index->K, "index_load_flat");
   index_load_flat_dev(index, p.get(), v.get(), r.get(), n);
   LB2_API_END
 }
@@ -983,6 +1134,40 @@ lb2_status lb2_index_export_flat(const lb2_index* index, void* centroids_out,
   LB2_API_END
 }
 
+namespace {
+// CUDA events of a build, destroyed on every path
+struct EventSet {
+  std::vector<cudaEvent_t> ev;
+  explicit EventSet(int n) : ev(n, nullptr) {
+    for (auto& e : ev) LB2_CUDA(cudaEventCreate(&e));
+  }
+  ~EventSet() {
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+  }
+  void record(int i) { LB2_CUDA(cudaEventRecord(ev[i], ctx().stream)); }
+  float ms(int i, int j) const {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, ev[i], ev[j]);
+    return t;
+  }
+};
+// KMeans::new_with_params (kmeans.rs:1008-1030): hierarchical for k > 256, flat Lloyd otherwise
+void train_ivf(const float* xs, uint64_t s, int d, int K, int am, const lb2_kmeans_params& kp, uint64_t nranks,
+               const float* init, float* centroids, std::vector<double>* loss, std::vector<uint32_t>* iters) {
+  check_redos(kp.redos, kp.balance_factor);
+  if (K > 256 && kp.hierarchical_k > 1 && !init) {
+    hierarchical_train(xs, s, d, K, am, kp.balance_factor / (float)(s * nranks), (int)kp.max_iters, kp.tolerance,
+                       (int)kp.hierarchical_k, kp.seed, centroids);
+    loss->assign(1, 0.0);
+    iters->assign(1, 0);
+  } else {
+    lloyd_train(xs, s, d, 1, d, K, am, kp.balance_factor / (float)(s * nranks), (int)kp.max_iters, kp.tolerance,
+                kp.seed, init, centroids, loss, iters);
+  }
+}
+}  // namespace
+
 lb2_status lb2_ivfflat_build(const void* data, uint64_t n, uint32_t d, lb2_dtype dtype,
                              lb2_metric metric, const lb2_ivfflat_build_params* params,
                              const uint64_t* row_ids, lb2_index** out, lb2_build_stats* stats) {
@@ -993,10 +1178,8 @@ lb2_status lb2_ivfflat_build(const void* data, uint64_t n, uint32_t d, lb2_dtype
   const uint64_t nranks = current_comm() ? current_comm()->nranks : 1;
   LB2_REQUIRE(K > 0 && (nranks > 1 || n >= (uint64_t)K), "KMeans: can not train %d centroids with %llu vectors", K,
               (unsigned long long)n);
-  Ctx& c = ctx();
-  cudaEvent_t ev[4];
-  for (auto& e : ev) LB2_CUDA(cudaEventCreate(&e));
-  LB2_CUDA(cudaEventRecord(ev[0], c.stream));
+  EventSet ev(4);
+  ev.record(0);
   VecIn xin(data, (size_t)n * d, dtype);
   const float* x = xin.get();
   DevBuf<float> xnorm;
@@ -1006,67 +1189,47 @@ lb2_status lb2_ivfflat_build(const void* data, uint64_t n, uint32_t d, lb2_dtype
     x = xnorm.p;
   }
   const int am = m == METRIC_DOT ? METRIC_DOT : METRIC_L2;
-  lb2_index* ix = new lb2_index();
+  std::unique_ptr<lb2_index> ix(new lb2_index());
   ix->kind = 1; ix->K = K; ix->d = d; ix->M = 0; ix->nbits = 0; ix->metric = m; ix->dtype = dtype;
   ix->centroids.alloc((size_t)K * d);
   std::vector<double> loss;
   std::vector<uint32_t> iters;
-  try {
-    {
-      TagScope tg("ivf_train");
-      const uint64_t s = std::min<uint64_t>(n, ((uint64_t)K * params->ivf.sample_rate + nranks - 1) / nranks);
-      const float* xs = x;
-      DevBuf<float> sample;
-      if (s < n) {
-        std::vector<uint64_t> rows = sample_rows(n, s, params->seed);
-        DevBuf<uint64_t> rows_d(s);
-        h2d(rows_d.p, rows.data(), s);
-        sample.alloc((size_t)s * d);
-        LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(s * d, 256), 256, 0, x, rows_d.p, s, (int)d, sample.p);
-        sync_stream();
-        xs = sample.p;
-      }
-      VecIn init(params->ivf.init_centroids, (size_t)K * d, model_dtype(dtype));
-      if (K > 256 && params->ivf.hierarchical_k > 1 && !params->ivf.init_centroids && nranks == 1) {
-        hierarchical_train(xs, s, d, K, am, params->ivf.balance_factor / (float)s, (int)params->ivf.max_iters,
-                           params->ivf.tolerance, (int)params->ivf.hierarchical_k, params->ivf.seed, ix->centroids.p);
-        loss.assign(1, 0.0);
-        iters.assign(1, 0);
-      } else {
-        lloyd_train(xs, s, d, 1, d, K, am, params->ivf.balance_factor / (float)(s * nranks),
-                    (int)params->ivf.max_iters, params->ivf.tolerance, params->ivf.seed, init.get(),
-                    ix->centroids.p, &loss, &iters);
-      }
-    }
-    LB2_CUDA(cudaEventRecord(ev[1], c.stream));
-    DevBuf<uint32_t> part(n);
-    {
-      TagScope tg("transform");
-      assign_f32(x, n, d, ix->centroids.p, K, am, nullptr, part.p, nullptr, nullptr, nullptr);
-    }
-    LB2_CUDA(cudaEventRecord(ev[2], c.stream));
-    InArg<uint64_t> rid(row_ids, n);
-    {
-      TagScope tg("group");
-      index_load_flat_dev(ix, part.p, x, rid.get(), n);
-    }
-    LB2_CUDA(cudaEventRecord(ev[3], c.stream));
-    sync_stream();
-  } catch (...) {
-    delete ix;
-    throw;
+  {
+    TagScope tg("ivf_train");
+    const uint64_t s0 = std::min<uint64_t>(n, ((uint64_t)K * params->ivf.sample_rate + nranks - 1) / nranks);
+    std::vector<uint64_t> rows = sample_rows(n, s0, params->seed);
+    DevBuf<float> sample;
+    const uint64_t s = gather_finite_sample(x, rows, (int)d, sample);
+    LB2_REQUIRE(nranks > 1 || s >= (uint64_t)K, "KMeans: can not train %d centroids with %llu finite vectors", K,
+                (unsigned long long)s);
+    VecIn init(params->ivf.init_centroids, (size_t)K * d, model_dtype(dtype));
+    train_ivf(sample.p, s, d, K, am, params->ivf, nranks, init.get(), ix->centroids.p, &loss, &iters);
   }
+  ev.record(1);
+  DevBuf<uint32_t> part(std::max<uint64_t>(n, 1));
+  DevBuf<uint8_t> valid(std::max<uint64_t>(n, 1));
+  {
+    TagScope tg("transform");
+    assign_f32(x, n, d, ix->centroids.p, K, am, nullptr, part.p, nullptr, valid.p, nullptr);
+  }
+  ev.record(2);
+  InArg<uint64_t> rid(row_ids, n);
+  {
+    TagScope tg("group");
+    index_load_flat_dev(ix.get(), part.p, x, rid.get(), n, valid.p);
+  }
+  ev.record(3);
+  sync_stream();
   if (stats) {
     memset(stats, 0, sizeof(*stats));
-    cudaEventElapsedTime(&stats->ms_ivf_train, ev[0], ev[1]);
-    cudaEventElapsedTime(&stats->ms_transform, ev[1], ev[2]);
-    cudaEventElapsedTime(&stats->ms_group, ev[2], ev[3]);
-    cudaEventElapsedTime(&stats->ms_total, ev[0], ev[3]);
+    stats->ms_ivf_train = ev.ms(0, 1);
+    stats->ms_transform = ev.ms(1, 2);
+    stats->ms_group = ev.ms(2, 3);
+    stats->ms_total = ev.ms(0, 3);
     stats->ivf_iters = iters.empty() ? 0 : iters[0];
     stats->ivf_loss = loss.empty() ? 0.0 : loss[0];
   }
-  for (auto& e : ev) cudaEventDestroy(e);
-  *out = ix;
+  *out = ix.release();
   LB2_API_END
 }
 
@@ -1097,9 +1260,8 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
   const int ds = d / M;
   if (!small_d_supported(ds)) fail(LB2_UNSUPPORTED, "PQ sub-vector width %d not supported yet", ds);
   Ctx& c = ctx();
-  cudaEvent_t ev[5];
-  for (auto& e : ev) LB2_CUDA(cudaEventCreate(&e));
-  LB2_CUDA(cudaEventRecord(ev[0], c.stream));
+  EventSet ev(5);
+  ev.record(0);
 
   // Staging.  Device pointer: used in place.  PINNED host pointer (L2 / dot): the bulk H2D copy runs
   // on a second stream (copy engine) while both training phases gather their <= 65 536-row samples
@@ -1152,106 +1314,84 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
   }
   const int am = m == METRIC_DOT ? METRIC_DOT : METRIC_L2;
 
-  lb2_index* ix = new lb2_index();
+  std::unique_ptr<lb2_index> ix(new lb2_index());
   ix->K = K; ix->d = d; ix->M = M; ix->nbits = nbits; ix->metric = m; ix->dtype = dtype;
   ix->centroids.alloc((size_t)K * d);
   ix->codebook.alloc(ix->codebook_len());
   std::vector<double> ivf_loss;
   std::vector<uint32_t> ivf_iters, pq_iters;
-  try {
-    // 0. both training samples are gathered first (IVF: K*sample_rate rows, rust/lance/src/index/
-    //    vector/ivf.rs:1237-1241; PQ: 256*2^nbits rows, builder.rs:410-421), then the bulk copy starts
-    const uint64_t s_ivf = std::min<uint64_t>(n, ((uint64_t)K * params->ivf.sample_rate + nranks - 1) / nranks);
-    const uint64_t s_pq = std::min<uint64_t>(n, (params->pq.sample_rate * ((uint64_t)1 << nbits) + nranks - 1) / nranks);
-    DevBuf<float> sample_ivf, sample_pq((size_t)s_pq * d);
-    const float* xs_ivf = x_sample;
-    {
-      if (s_ivf < n || x_sample != x) {
-        std::vector<uint64_t> rows = sample_rows(n, s_ivf, params->seed);
-        DevBuf<uint64_t> rows_d(s_ivf);
-        h2d(rows_d.p, rows.data(), s_ivf);
-        sample_ivf.alloc((size_t)s_ivf * d);
-        LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(s_ivf * d, 256), 256, 0, x_sample, rows_d.p, s_ivf, (int)d, sample_ivf.p);
-        sync_stream();
-        xs_ivf = sample_ivf.p;
-      }
-      std::vector<uint64_t> rows = sample_rows(n, s_pq, params->seed + 1);
-      DevBuf<uint64_t> rows_d(s_pq);
-      h2d(rows_d.p, rows.data(), s_pq);
-      LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(s_pq * d, 256), 256, 0, x_sample, rows_d.p, s_pq, (int)d, sample_pq.p);
-      sync_stream();
+  // 0. both training samples are gathered first (IVF: K*sample_rate rows, rust/lance/src/index/
+  //    vector/ivf.rs:1237-1241; PQ: 256*2^nbits rows, builder.rs:410-421), rows that are not finite are
+  //    dropped from them (builder.rs:436), then the bulk copy starts
+  const uint64_t s_ivf0 = std::min<uint64_t>(n, ((uint64_t)K * params->ivf.sample_rate + nranks - 1) / nranks);
+  const uint64_t s_pq0 = std::min<uint64_t>(n, (params->pq.sample_rate * ((uint64_t)1 << nbits) + nranks - 1) / nranks);
+  DevBuf<float> sample_ivf, sample_pq;
+  uint64_t s_ivf = 0, s_pq = 0;
+  {
+    std::vector<uint64_t> rows = sample_rows(n, s_ivf0, params->seed);
+    s_ivf = gather_finite_sample(x_sample, rows, (int)d, sample_ivf);
+    rows = sample_rows(n, s_pq0, params->seed + 1);
+    s_pq = gather_finite_sample(x_sample, rows, (int)d, sample_pq);
+  }
+  LB2_REQUIRE(nranks > 1 || s_ivf >= (uint64_t)K, "KMeans: can not train %d centroids with %llu finite vectors", K,
+              (unsigned long long)s_ivf);
+  start_bulk_copy();
+  // 1. IVF
+  {
+    TagScope tg("ivf_train");
+    VecIn init(params->ivf.init_centroids, (size_t)K * d, model_dtype(dtype));
+    train_ivf(sample_ivf.p, s_ivf, d, K, am, params->ivf, nranks, init.get(), ix->centroids.p, &ivf_loss, &ivf_iters);
+  }
+  ev.record(1);
+  // 2. PQ: residuals of its sample w.r.t. the IVF centroids (builder.rs:439-450)
+  {
+    TagScope tg("pq_train");
+    if (am == METRIC_L2 && s_pq) {
+      DevBuf<uint32_t> part(s_pq);
+      assign_f32(sample_pq.p, s_pq, d, ix->centroids.p, K, METRIC_L2, nullptr, part.p, nullptr, nullptr, nullptr);
+      LB2_LAUNCH("residual", residual_kernel, cdiv(s_pq * d, 256), 256, 0, sample_pq.p, ix->centroids.p,
+                 part.p, s_pq, (int)d, sample_pq.p);
     }
-    start_bulk_copy();
-    // 1. IVF
-    {
-      TagScope tg("ivf_train");
-      const uint64_t s = s_ivf;
-      const float* xs = xs_ivf;
-      VecIn init(params->ivf.init_centroids, (size_t)K * d, model_dtype(dtype));
-      if (K > 256 && params->ivf.hierarchical_k > 1 && !params->ivf.init_centroids && nranks == 1) {
-        hierarchical_train(xs, s, d, K, am, params->ivf.balance_factor / (float)s, (int)params->ivf.max_iters,
-                           params->ivf.tolerance, (int)params->ivf.hierarchical_k, params->ivf.seed, ix->centroids.p);
-        ivf_loss.assign(1, 0.0);
-        ivf_iters.assign(1, 0);
-      } else {
-        lloyd_train(xs, s, d, 1, d, K, am, params->ivf.balance_factor / (float)(s * nranks),
-                    (int)params->ivf.max_iters, params->ivf.tolerance, params->ivf.seed, init.get(),
-                    ix->centroids.p, &ivf_loss, &ivf_iters);
-      }
-    }
-    LB2_CUDA(cudaEventRecord(ev[1], c.stream));
-    // 2. PQ: residuals of its sample w.r.t. the IVF centroids (builder.rs:439-450)
-    {
-      TagScope tg("pq_train");
-      const uint64_t s = s_pq;
-      DevBuf<float>& sample = sample_pq;
-      if (am == METRIC_L2) {
-        DevBuf<uint32_t> part(s);
-        assign_f32(sample.p, s, d, ix->centroids.p, K, METRIC_L2, nullptr, part.p, nullptr, nullptr, nullptr);
-        LB2_LAUNCH("residual", residual_kernel, cdiv(s * d, 256), 256, 0, sample.p, ix->centroids.p,
-                   part.p, s, (int)d, sample.p);
-      }
-      VecIn cb_init(params->pq.codebook, ix->codebook_len(), model_dtype(dtype));
-      lb2_pq_params pqp = params->pq;
-      pqp.codebook = cb_init.get();
-      // always L2 k-means (builder.rs:460: Q::build(&training_data, DistanceType::L2, ..)); for a dot index
-      // the sample is the raw vectors (no residual), for L2 / cosine the residuals computed above
-      pq_train_dev(sample.p, s, d, METRIC_L2, &pqp, ix->codebook.p, &pq_iters);
-    }
-    LB2_CUDA(cudaEventRecord(ev[2], c.stream));
-    // 3. transform every row (lance-index/src/vector/ivf.rs:357: partition -> residual -> PQ)
-    DevBuf<uint32_t> part(n);
-    DevBuf<uint8_t> codes((size_t)n * ix->code_bytes()), valid(n);
-    if (copied) LB2_CUDA(cudaStreamWaitEvent(c.stream, copied, 0));  // the bulk copy must have landed
-    TagScope* tg3 = new TagScope("transform");
+    VecIn cb_init(params->pq.codebook, ix->codebook_len(), model_dtype(dtype));
+    lb2_pq_params pqp = params->pq;
+    pqp.codebook = cb_init.get();
+    // always L2 k-means (builder.rs:460: Q::build(&training_data, DistanceType::L2, ..)); for a dot index
+    // the sample is the raw vectors (no residual), for L2 / cosine the residuals computed above
+    pq_train_dev(sample_pq.p, s_pq, d, METRIC_L2, &pqp, ix->codebook.p, &pq_iters);
+  }
+  ev.record(2);
+  // 3. transform every row (lance-index/src/vector/ivf.rs:357: partition -> residual -> PQ)
+  DevBuf<uint32_t> part(std::max<uint64_t>(n, 1));
+  DevBuf<uint8_t> codes(std::max<uint64_t>(1, (size_t)n * ix->code_bytes())), valid(std::max<uint64_t>(n, 1));
+  if (copied) LB2_CUDA(cudaStreamWaitEvent(c.stream, copied, 0));  // the bulk copy must have landed
+  {
+    TagScope tg("transform");
     assign_f32(x, n, d, ix->centroids.p, K, am, nullptr, part.p, nullptr, valid.p, nullptr);
     pq_encode_any(x, n, d, M, ds, ix->codebook.p, METRIC_L2, am == METRIC_DOT ? nullptr : ix->centroids.p,
                   am == METRIC_DOT ? nullptr : part.p, valid.p, nbits, codes.p);  // L2 codes: see lb2_ivfpq_transform
-    delete tg3;
-    LB2_CUDA(cudaEventRecord(ev[3], c.stream));
-    TagScope tg4("group");
-    // 4. group rows by partition (shuffle + build_partitions, builder.rs:501-937)
-    InArg<uint64_t> rid(row_ids, n);
-    index_load_dev(ix, part.p, codes.p, rid.get(), n);
-    LB2_CUDA(cudaEventRecord(ev[4], c.stream));
-    sync_stream();
-  } catch (...) {
-    delete ix;
-    throw;
   }
+  ev.record(3);
+  {
+    // 4. group the kept rows by partition (shuffle + build_partitions, builder.rs:501-937); rows the
+    //    transform marked invalid are dropped, as KeepFiniteVectors does (transform.rs:112-159)
+    TagScope tg("group");
+    InArg<uint64_t> rid(row_ids, n);
+    index_load_dev(ix.get(), part.p, codes.p, rid.get(), n, valid.p);
+  }
+  ev.record(4);
+  sync_stream();
   if (stats) {
-    cudaEventElapsedTime(&stats->ms_ivf_train, ev[0], ev[1]);
-    cudaEventElapsedTime(&stats->ms_pq_train, ev[1], ev[2]);
-    cudaEventElapsedTime(&stats->ms_transform, ev[2], ev[3]);
-    cudaEventElapsedTime(&stats->ms_group, ev[3], ev[4]);
-    cudaEventElapsedTime(&stats->ms_total, ev[0], ev[4]);
+    stats->ms_ivf_train = ev.ms(0, 1);
+    stats->ms_pq_train = ev.ms(1, 2);
+    stats->ms_transform = ev.ms(2, 3);
+    stats->ms_group = ev.ms(3, 4);
+    stats->ms_total = ev.ms(0, 4);
     stats->ivf_iters = ivf_iters.empty() ? 0 : ivf_iters[0];
     stats->pq_iters_max = 0;
     for (auto v : pq_iters) stats->pq_iters_max = std::max(stats->pq_iters_max, v);
     stats->ivf_loss = ivf_loss.empty() ? 0.0 : ivf_loss[0];
   }
-  for (auto& e : ev) cudaEventDestroy(e);
-  *out = ix;
+  *out = ix.release();
   LB2_API_END
 }
 

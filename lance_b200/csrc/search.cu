@@ -26,6 +26,69 @@ namespace lb2 {
 __device__ __forceinline__ bool row_allowed(const uint64_t* __restrict__ allow, uint64_t pos) {
   return allow == nullptr || ((allow[pos >> 6] >> (pos & 63)) & 1ull) != 0;
 }
+// range query (flat/index.rs:100-115): a row enters the heap iff lower <= dist < upper in f32::total_cmp
+// order; an absent bound is f32::MIN / f32::MAX (NOT -inf / +inf), exactly as the reference unwraps them
+__device__ __forceinline__ bool key_in_range(const ScanFilter& f, int32_t key) {
+  return !f.range || (key >= f.lo_key && key < f.hi_key);
+}
+
+// ---- Rust std BinaryHeap<OrderedNode> restated (alloc::collections::binary_heap: push = sift_up,
+// pop = swap with the last + sift_down_to_bottom + sift_up) on (unsigned order key, position) pairs.
+// OrderedNode compares by distance only (graph.rs:117-121), so WHICH of several rows tied at the k-th
+// distance survives FlatIndex::search's `if root.dist > dist { pop; push }` loop (flat/index.rs:116-126)
+// depends on this exact sift order.  The parallel selections below return the k smallest (distance,
+// position) pairs, which is the same SET unless more rows tie at the k-th distance than fit; exactly
+// then (detected by selecting k + 1) the slot is replayed sequentially through this heap.
+__device__ __forceinline__ void rheap_sift_up(uint32_t* hk, uint32_t* hp, uint32_t pos) {
+  const uint32_t ek = hk[pos], ep = hp[pos];
+  while (pos > 0) {
+    const uint32_t parent = (pos - 1) >> 1;
+    if (ek <= hk[parent]) break;
+    hk[pos] = hk[parent];
+    hp[pos] = hp[parent];
+    pos = parent;
+  }
+  hk[pos] = ek;
+  hp[pos] = ep;
+}
+__device__ __forceinline__ void rheap_push(uint32_t* hk, uint32_t* hp, uint32_t& len, uint32_t key, uint32_t pos) {
+  hk[len] = key;
+  hp[len] = pos;
+  rheap_sift_up(hk, hp, len);
+  ++len;
+}
+__device__ __forceinline__ void rheap_pop(uint32_t* hk, uint32_t* hp, uint32_t& len) {
+  --len;
+  if (len == 0) return;
+  const uint32_t ek = hk[len], ep = hp[len];  // the last element moves to the root, then sinks to the bottom
+  uint32_t pos = 0, child = 1;
+  const uint32_t end = len;
+  while (child + 1 < end) {
+    if (hk[child] <= hk[child + 1]) child += 1;
+    hk[pos] = hk[child];
+    hp[pos] = hp[child];
+    pos = child;
+    child = 2 * pos + 1;
+  }
+  if (child + 1 == end) {
+    hk[pos] = hk[child];
+    hp[pos] = hp[child];
+    pos = child;
+  }
+  hk[pos] = ek;
+  hp[pos] = ep;
+  rheap_sift_up(hk, hp, pos);
+}
+// FlatIndex::search's insertion rule for one row (flat/index.rs:116-126); keys are unsigned order keys
+__device__ __forceinline__ void rheap_offer(uint32_t* hk, uint32_t* hp, uint32_t& len, uint32_t k, uint32_t key,
+                                            uint32_t pos) {
+  if (len < k) {
+    rheap_push(hk, hp, len, key, pos);
+  } else if (hk[0] > key) {
+    rheap_pop(hk, hp, len);
+    rheap_push(hk, hp, len, key, pos);
+  }
+}
 
 
 // ------------------------------------------------------------------------------------------------
@@ -190,54 +253,58 @@ __device__ __forceinline__ float key_to_float(int32_t key) {
 // 4-pass MSB radix select over shared-memory keys (256-bin histograms), everything below it is
 // kept, ties AT the k-th key are resolved by position (earliest rows survive).
 // ------------------------------------------------------------------------------------------------
+// arguments shared by the fused scan kernels (one slot = one (query, probed partition) pair)
+struct ScanArgs {
+  const float* queries; int d; const float* centroids; const float* codebook; int M, ds;
+  const uint32_t* probe_ids; int np; const uint64_t* part_offsets; const uint8_t* codes;
+  const uint64_t* row_ids; int k; float* cand_d; uint64_t* cand_id; uint32_t* cand_cnt;
+  ScanFilter flt;
+};
+
 template <int METRIC, int NBITS>
-__global__ void __launch_bounds__(256)
-ivfpq_scan_radix_kernel(const float* __restrict__ queries, int d, const float* __restrict__ centroids,
-                        const float* __restrict__ codebook, int M, int ds,
-                        const uint32_t* __restrict__ probe_ids, int np,
-                        const uint64_t* __restrict__ part_offsets, const uint8_t* __restrict__ codes,
-                        const uint64_t* __restrict__ row_ids, int k, float* __restrict__ cand_d,
-                        uint64_t* __restrict__ cand_id, uint32_t* __restrict__ cand_cnt,
-                        const uint64_t* __restrict__ allow) {
+__device__ void radix_slot(const ScanArgs& a, size_t slot, bool replay) {
   extern __shared__ float smem[];
   constexpr int NCODE = 1 << NBITS;
+  const int M = a.M, ds = a.ds, d = a.d, k = a.k, np = a.np;
+  const int kk = k + 1;  // one more than asked for: exposes ties that overflow the k-th place
+  const uint64_t* __restrict__ allow = a.flt.allow;
+  const bool filtering = allow != nullptr || a.flt.range;
   float* lut = smem;                                                   // [M*NCODE] (8-bit: M*256)
   float* qr = lut + M * 256;                                           // [d]
-  uint32_t* ukey = reinterpret_cast<uint32_t*>(qr + d);                // [SCAN_CHUNK + k] order-preserving keys
-  uint32_t* cpos = ukey + SCAN_CHUNK + k;                              // [k] positions of carried winners
-  uint32_t* nkey = cpos + k;                                           // [k] next winners
-  uint32_t* npos = nkey + k;                                           // [k]
+  uint32_t* ukey = reinterpret_cast<uint32_t*>(qr + d);                // [SCAN_CHUNK + kk] order-preserving keys
+  uint32_t* cpos = ukey + SCAN_CHUNK + kk;                             // [kk] positions of carried winners
+  uint32_t* nkey = cpos + kk;                                          // [kk] next winners / the replay heap
+  uint32_t* npos = nkey + kk;                                          // [kk]
   __shared__ uint32_t hist[256];
-  __shared__ uint32_t s_prefix, s_need, s_eq, s_out;
+  __shared__ uint32_t s_prefix, s_need, s_eq, s_out, s_max, s_maxcnt;
   __shared__ int32_t s_key[8];
   __shared__ uint64_t s_tie[8];
   __shared__ int s_tid[9];
   __shared__ uint32_t prev_pos;
   const int tid = threadIdx.x;
-  const int pi = blockIdx.x;
-  const size_t qi = blockIdx.y;
-  const uint32_t p = probe_ids[qi * np + pi];
-  const uint64_t off = part_offsets[p];
-  const uint32_t n_p = (uint32_t)(part_offsets[p + 1] - off);
-  const size_t slot = qi * np + pi;
+  const int pi = (int)(slot % np);
+  const size_t qi = slot / np;
+  const uint32_t p = a.probe_ids[qi * np + pi];
+  const uint64_t off = a.part_offsets[p];
+  const uint32_t n_p = (uint32_t)(a.part_offsets[p + 1] - off);
   if (n_p == 0) {
-    if (tid == 0) cand_cnt[slot] = 0;
+    if (tid == 0) a.cand_cnt[slot] = 0;
     return;
   }
-  const float* q = queries + qi * d;
+  const float* q = a.queries + qi * d;
   for (int t = tid; t < d; t += 256)
-    qr[t] = METRIC == METRIC_DOT ? q[t] : __fsub_rn(q[t], centroids[(size_t)p * d + t]);  // v2.rs:316-332
+    qr[t] = METRIC == METRIC_DOT ? q[t] : __fsub_rn(q[t], a.centroids[(size_t)p * d + t]);  // v2.rs:316-332
   __syncthreads();
   if (NBITS == 8) {
-    build_lut_smem<METRIC>(lut, qr, codebook, M, ds, tid);
+    build_lut_smem<METRIC>(lut, qr, a.codebook, M, ds, tid);
   } else {
     for (int idx = tid; idx < M * NCODE; idx += 256)
-      lut[idx] = dist_exact_thread<METRIC>(qr + (idx / NCODE) * ds, codebook + (size_t)idx * ds, ds);
+      lut[idx] = dist_exact_thread<METRIC>(qr + (idx / NCODE) * ds, a.codebook + (size_t)idx * ds, ds);
   }
   __syncthreads();
   constexpr int CW_DIV = NBITS == 4 ? 2 : 1;
   const int cw = M / CW_DIV;  // code bytes per row
-  const uint8_t* pc = codes + off * cw;
+  const uint8_t* pc = a.codes + off * cw;
   const float dot_fix = (float)M - 1.0f;
   // ---- 4-bit (pq/distance.rs:147-242): rows [0, flat_num) and the last n_p % 16 rows are exact f32 sums;
   // the others go through the table quantised to u8 with qmin = min(table), qmax = max(flat rows).
@@ -288,146 +355,218 @@ ivfpq_scan_radix_kernel(const float* __restrict__ queries, int d, const float* _
     }
     __syncthreads();
   }
+  // unsigned order key of row `row`'s distance (unsigned order == f32::total_cmp order)
+  auto row_key = [&](uint32_t row) -> uint32_t {
+    float dist = 0.0f;
+    if (NBITS == 4) {
+      if (allow != nullptr || row < flat_num || row >= n_p - rem16) {
+        dist = exact4(row);
+      } else {
+        const uint8_t* rp = pc + (size_t)row * cw;
+        uint32_t qs = 0;  // saturating u8 adds of non-negative terms == min(255, sum)
+        for (int i2 = 0; i2 < cw; ++i2) {
+          const uint8_t c = rp[i2];
+          qs += qt[(2 * i2) * 16 + (c & 0xF)];
+          qs += qt[(2 * i2 + 1) * 16 + (c >> 4)];
+        }
+        dist = __fadd_rn(__fmul_rn((float)min(qs, 255u), s_q[1]), s_q[0]);
+      }
+    } else if ((M & 15) == 0) {
+      const uint4* rp = reinterpret_cast<const uint4*>(pc + (size_t)row * M);
+      for (int c16 = 0; c16 < M / 16; ++c16) {
+        const uint4 v = __ldg(rp + c16);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const float* l0 = lut + c16 * 16 * 256;
+#pragma unroll
+        for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb)
+            dist = f_add(dist, l0[(aa * 4 + bb) * 256 + ((w[aa] >> (8 * bb)) & 0xff)]);
+      }
+    } else {
+      const uint8_t* rp = pc + (size_t)row * M;
+      for (int m = 0; m < M; ++m) dist = f_add(dist, lut[m * 256 + rp[m]]);
+    }
+    if (METRIC == METRIC_DOT) dist = __fsub_rn(dist, dot_fix);
+    return (uint32_t)total_order_key(dist) ^ 0x80000000u;
+  };
+  auto excluded = [&](uint32_t row, uint32_t key) -> bool {
+    return !row_allowed(allow, off + row) || !key_in_range(a.flt, (int32_t)(key ^ 0x80000000u));
+  };
+
   uint32_t nw = 0;
-  for (uint32_t c0 = 0; c0 < n_p; c0 += SCAN_CHUNK) {
-    const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
-    for (uint32_t j = tid; j < clen; j += 256) {
-      if (!row_allowed(allow, off + c0 + j)) {
-        ukey[j] = 0xffffffffu;
+  if (!replay) {
+    for (uint32_t c0 = 0; c0 < n_p; c0 += SCAN_CHUNK) {
+      const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
+      for (uint32_t j = tid; j < clen; j += 256) {
+        if (!row_allowed(allow, off + c0 + j)) {
+          ukey[j] = 0xffffffffu;
+          continue;
+        }
+        const uint32_t key = row_key(c0 + j);
+        ukey[j] = key_in_range(a.flt, (int32_t)(key ^ 0x80000000u)) ? key : 0xffffffffu;
+      }
+      // carried winners sit at ukey[SCAN_CHUNK ..); pool element i: i < clen -> (ukey[i], c0+i), else carried
+      __syncthreads();
+      const uint32_t pool = clen + nw;
+      auto key_at = [&](uint32_t i) { return i < clen ? ukey[i] : ukey[SCAN_CHUNK + (i - clen)]; };
+      auto pos_at = [&](uint32_t i) { return i < clen ? c0 + i : cpos[i - clen]; };
+      if (pool <= (uint32_t)kk) {
+        for (uint32_t i = tid; i < pool; i += 256) { nkey[i] = key_at(i); npos[i] = pos_at(i); }
+        __syncthreads();
+        for (uint32_t i = tid; i < pool; i += 256) { ukey[SCAN_CHUNK + i] = nkey[i]; cpos[i] = npos[i]; }
+        nw = pool;
+        __syncthreads();
         continue;
       }
-      float dist = 0.0f;
-      if (NBITS == 4) {
-        const uint32_t row = c0 + j;
-        if (allow != nullptr || row < flat_num || row >= n_p - rem16) {
-          dist = exact4(row);
-        } else {
-          const uint8_t* rp = pc + (size_t)row * cw;
-          uint32_t q = 0;  // saturating u8 adds of non-negative terms == min(255, sum)
-          for (int i2 = 0; i2 < cw; ++i2) {
-            const uint8_t c = rp[i2];
-            q += qt[(2 * i2) * 16 + (c & 0xF)];
-            q += qt[(2 * i2 + 1) * 16 + (c >> 4)];
-          }
-          dist = __fadd_rn(__fmul_rn((float)min(q, 255u), s_q[1]), s_q[0]);
-        }
-      } else if ((M & 15) == 0) {
-        const uint4* rp = reinterpret_cast<const uint4*>(pc + (size_t)(c0 + j) * M);
-        for (int c16 = 0; c16 < M / 16; ++c16) {
-          const uint4 v = __ldg(rp + c16);
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-          const float* l0 = lut + c16 * 16 * 256;
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-              dist = f_add(dist, l0[(a * 4 + b) * 256 + ((w[a] >> (8 * b)) & 0xff)]);
-        }
-      } else {
-        const uint8_t* rp = pc + (size_t)(c0 + j) * M;
-        for (int m = 0; m < M; ++m) dist = f_add(dist, lut[m * 256 + rp[m]]);
-      }
-      if (METRIC == METRIC_DOT) dist = __fsub_rn(dist, dot_fix);
-      ukey[j] = (uint32_t)total_order_key(dist) ^ 0x80000000u;  // unsigned order == total order
-    }
-    // carried winners sit at ukey[SCAN_CHUNK ..); pool element i: i < clen -> (ukey[i], c0+i), else carried
-    __syncthreads();
-    const uint32_t pool = clen + nw;
-    auto key_at = [&](uint32_t i) { return i < clen ? ukey[i] : ukey[SCAN_CHUNK + (i - clen)]; };
-    auto pos_at = [&](uint32_t i) { return i < clen ? c0 + i : cpos[i - clen]; };
-    if (pool <= (uint32_t)k) {
-      for (uint32_t i = tid; i < pool; i += 256) { nkey[i] = key_at(i); npos[i] = pos_at(i); }
-      __syncthreads();
-      for (uint32_t i = tid; i < pool; i += 256) { ukey[SCAN_CHUNK + i] = nkey[i]; cpos[i] = npos[i]; }
-      nw = pool;
-      __syncthreads();
-      continue;
-    }
-    if (tid == 0) { s_prefix = 0; s_need = (uint32_t)k; }
-    uint32_t mask = 0;
-    for (int shift = 24; shift >= 0; shift -= 8) {
-      hist[tid] = 0;
-      __syncthreads();
-      const uint32_t prefix = s_prefix;
-      for (uint32_t i = tid; i < pool; i += 256) {
-        const uint32_t kk = key_at(i);
-        if ((kk & mask) == prefix) atomicAdd(&hist[(kk >> shift) & 255u], 1u);
-      }
-      __syncthreads();
-      if (tid == 0) {
-        uint32_t need = s_need, cum = 0;
-        int b = 0;
-        for (; b < 256; ++b) {
-          if (cum + hist[b] >= need) break;
-          cum += hist[b];
-        }
-        s_need = need - cum;
-        s_prefix = prefix | ((uint32_t)b << shift);
-        s_eq = hist[b];
-      }
-      mask |= 0xffu << shift;
-      __syncthreads();
-    }
-    const uint32_t T = s_prefix, need = s_need, eq = s_eq;  // take all keys < T and `need` of the `eq` keys == T
-    if (tid == 0) s_out = 0;
-    __syncthreads();
-    for (uint32_t i = tid; i < pool; i += 256) {
-      const uint32_t kk = key_at(i);
-      if (kk < T || (kk == T && eq == need)) {
-        const uint32_t at = atomicAdd(&s_out, 1u);
-        nkey[at] = kk;
-        npos[at] = pos_at(i);
-      }
-    }
-    __syncthreads();
-    if (eq != need) {  // ties at the k-th key: the `need` smallest positions survive (rare)
-      bool first = true;
-      for (uint32_t r = 0; r < need; ++r) {
-        uint32_t bp = 0xffffffffu;
-        bool has = false;
-        const uint32_t pp = first ? 0 : prev_pos;
+      if (tid == 0) { s_prefix = 0; s_need = (uint32_t)kk; }
+      uint32_t mask = 0;
+      for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[tid] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
         for (uint32_t i = tid; i < pool; i += 256) {
-          if (key_at(i) != T) continue;
-          const uint32_t ps = pos_at(i);
-          if (!first && ps <= pp) continue;
-          if (!has || ps < bp) { bp = ps; has = true; }
-        }
-        const int w = block_argmin<256>(has, 0, bp, s_key, s_tie, s_tid);
-        if (tid == w) {
-          prev_pos = bp;
-          const uint32_t at = s_out;
-          nkey[at] = T;
-          npos[at] = bp;
-          s_out = at + 1;
+          const uint32_t kv = key_at(i);
+          if ((kv & mask) == prefix) atomicAdd(&hist[(kv >> shift) & 255u], 1u);
         }
         __syncthreads();
-        first = false;
+        if (tid == 0) {
+          uint32_t need = s_need, cum = 0;
+          int b = 0;
+          for (; b < 256; ++b) {
+            if (cum + hist[b] >= need) break;
+            cum += hist[b];
+          }
+          s_need = need - cum;
+          s_prefix = prefix | ((uint32_t)b << shift);
+          s_eq = hist[b];
+        }
+        mask |= 0xffu << shift;
+        __syncthreads();
+      }
+      const uint32_t T = s_prefix, need = s_need, eq = s_eq;  // take all keys < T and `need` of the `eq` keys == T
+      if (tid == 0) s_out = 0;
+      __syncthreads();
+      for (uint32_t i = tid; i < pool; i += 256) {
+        const uint32_t kv = key_at(i);
+        if (kv < T || (kv == T && eq == need)) {
+          const uint32_t at = atomicAdd(&s_out, 1u);
+          nkey[at] = kv;
+          npos[at] = pos_at(i);
+        }
+      }
+      __syncthreads();
+      if (eq != need) {  // ties at the last key: the `need` smallest positions survive (rare)
+        bool first = true;
+        for (uint32_t r = 0; r < need; ++r) {
+          uint32_t bp = 0xffffffffu;
+          bool has = false;
+          const uint32_t pp = first ? 0 : prev_pos;
+          for (uint32_t i = tid; i < pool; i += 256) {
+            if (key_at(i) != T) continue;
+            const uint32_t ps = pos_at(i);
+            if (!first && ps <= pp) continue;
+            if (!has || ps < bp) { bp = ps; has = true; }
+          }
+          const int w = block_argmin<256>(has, 0, bp, s_key, s_tie, s_tid);
+          if (tid == w) {
+            prev_pos = bp;
+            const uint32_t at = s_out;
+            nkey[at] = T;
+            npos[at] = bp;
+            s_out = at + 1;
+          }
+          __syncthreads();
+          first = false;
+        }
+      }
+      const uint32_t got = s_out;  // == kk
+      __syncthreads();
+      for (uint32_t i = tid; i < got; i += 256) { ukey[SCAN_CHUNK + i] = nkey[i]; cpos[i] = npos[i]; }
+      nw = got;
+      __syncthreads();
+    }
+    // ---- the kk = k + 1 smallest (key, position) pairs are in hand.  Excluded rows (prefilter / range)
+    // carry the maximal key and are dropped here; if the two largest survivors share a key, more rows tie
+    // at the k-th distance than fit and the reference's heap decides -> replay
+    if (tid == 0) { s_out = 0; s_max = 0; s_maxcnt = 0; }
+    __syncthreads();
+    for (uint32_t i = tid; i < nw; i += 256) {
+      const uint32_t key = ukey[SCAN_CHUNK + i], pos = cpos[i];
+      const bool keep = !filtering || (row_allowed(allow, off + pos) && !(a.flt.range && key == 0xffffffffu));
+      if (keep) {
+        const uint32_t at = atomicAdd(&s_out, 1u);
+        nkey[at] = key;
+        npos[at] = pos;
+        atomicMax(&s_max, key);
       }
     }
-    const uint32_t got = s_out;  // == k
     __syncthreads();
-    for (uint32_t i = tid; i < got; i += 256) { ukey[SCAN_CHUNK + i] = nkey[i]; cpos[i] = npos[i]; }
-    nw = got;
+    nw = s_out;
+    if (nw == (uint32_t)kk) {
+      for (uint32_t i = tid; i < nw; i += 256)
+        if (nkey[i] == s_max) atomicAdd(&s_maxcnt, 1u);
+      __syncthreads();
+      replay = s_maxcnt >= 2;  // block-uniform
+    }
+    if (!replay) {
+      const bool drop_max = nw == (uint32_t)kk;
+      const uint32_t mx = s_max;
+      __syncthreads();
+      if (tid == 0) s_out = 0;
+      __syncthreads();
+      for (uint32_t i = tid; i < nw; i += 256) {
+        if (drop_max && nkey[i] == mx) continue;
+        const uint32_t at = atomicAdd(&s_out, 1u);
+        a.cand_d[slot * k + at] = key_to_float((int32_t)(nkey[i] ^ 0x80000000u));
+        a.cand_id[slot * k + at] = a.row_ids[off + npos[i]];
+      }
+      __syncthreads();
+      if (tid == 0) a.cand_cnt[slot] = s_out;
+      return;
+    }
     __syncthreads();
   }
-  if (allow) {  // drop filtered rows (order inside a candidate list is irrelevant: the merge sorts)
-    if (tid == 0) s_out = 0;
+  // ---- replay: the reference's own loop (flat/index.rs:116-165), rows in storage order, distances
+  // computed in parallel one chunk ahead of the single thread that drives the heap
+  uint32_t len = 0;
+  for (uint32_t c0 = 0; c0 < n_p; c0 += SCAN_CHUNK) {
+    const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
+    for (uint32_t j = tid; j < clen; j += 256) ukey[j] = row_key(c0 + j);
     __syncthreads();
-    for (uint32_t i = tid; i < nw; i += 256)
-      if (row_allowed(allow, off + cpos[i])) {
-        const uint32_t at = atomicAdd(&s_out, 1u);
-        cand_d[slot * k + at] = key_to_float((int32_t)(ukey[SCAN_CHUNK + i] ^ 0x80000000u));
-        cand_id[slot * k + at] = row_ids[off + cpos[i]];
+    if (tid == 0) {
+      for (uint32_t j = 0; j < clen; ++j) {
+        const uint32_t key = ukey[j];
+        if (filtering && excluded(c0 + j, key)) continue;
+        rheap_offer(nkey, npos, len, (uint32_t)k, key, c0 + j);
       }
+    }
     __syncthreads();
-    if (tid == 0) cand_cnt[slot] = s_out;
+  }
+  if (tid == 0) s_out = len;
+  __syncthreads();
+  len = s_out;
+  for (uint32_t i = tid; i < len; i += 256) {
+    a.cand_d[slot * k + i] = key_to_float((int32_t)(nkey[i] ^ 0x80000000u));
+    a.cand_id[slot * k + i] = a.row_ids[off + npos[i]];
+  }
+  if (tid == 0) a.cand_cnt[slot] = len;
+}
+
+// grid (np, nq): one CTA per slot; or, with a replay list (slots the fast kernel could not settle because of
+// ties at the k-th distance), a small persistent grid that replays the listed slots
+template <int METRIC, int NBITS>
+__global__ void __launch_bounds__(256)
+ivfpq_scan_radix_kernel(const ScanArgs a, const uint32_t* __restrict__ rlist, const uint32_t* __restrict__ rcount) {
+  if (rlist) {
+    const uint32_t cnt = *rcount;
+    for (uint32_t i = blockIdx.x; i < cnt; i += gridDim.x) {
+      radix_slot<METRIC, NBITS>(a, rlist[i], true);
+      __syncthreads();
+    }
     return;
   }
-  for (uint32_t i = tid; i < nw; i += 256) {
-    cand_d[slot * k + i] = key_to_float((int32_t)(ukey[SCAN_CHUNK + i] ^ 0x80000000u));
-    cand_id[slot * k + i] = row_ids[off + cpos[i]];
-  }
-  if (tid == 0) cand_cnt[slot] = nw;
+  radix_slot<METRIC, NBITS>(a, (size_t)blockIdx.y * a.np + blockIdx.x, false);
 }
 
 // ---- warp-wide sorting network on packed (key, position) words -------------------------------------
@@ -485,47 +624,44 @@ constexpr int SCAN_WLIST = (SCAN_KFAST - 1) * 16 + 1;  // 241
 
 template <int METRIC, bool FILTER>
 __global__ void __launch_bounds__(256, 6)
-ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restrict__ centroids,
-                  const float* __restrict__ codebook, int M, int ds,
-                  const uint32_t* __restrict__ probe_ids, int np,
-                  const uint64_t* __restrict__ part_offsets, const uint8_t* __restrict__ codes,
-                  const uint64_t* __restrict__ row_ids, int k, float* __restrict__ cand_d,
-                  uint64_t* __restrict__ cand_id, uint32_t* __restrict__ cand_cnt,
-                  const uint64_t* __restrict__ allow) {
+ivfpq_scan_kernel(const ScanArgs a, uint32_t* __restrict__ rlist, uint32_t* __restrict__ rcount) {
   constexpr int RPT = SCAN_CHUNK / 256;  // rows per thread and chunk (16)
   extern __shared__ float smem[];
+  const int M = a.M, ds = a.ds, d = a.d, k = a.k, np = a.np;
+  const int kk = k + 1;  // <= SCAN_KFAST: one more than asked for, to expose ties that overflow the k-th place
+  const uint64_t* __restrict__ allow = a.flt.allow;
   float* lut = smem;          // [M*256]
   float* qr = lut + M * 256;  // [d]
   __shared__ uint64_t wl[8][SCAN_WLIST];                 // per-warp compacted candidates
-  __shared__ uint64_t fin[8 * SCAN_KFAST + SCAN_KFAST];  // 8 x k warp winners, then the carried winners
+  __shared__ uint64_t fin[8 * SCAN_KFAST + SCAN_KFAST];  // 8 x kk warp winners, then the carried winners
   __shared__ uint64_t car[SCAN_KFAST];
   __shared__ uint32_t s_nw;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pi = blockIdx.x;
   const size_t qi = blockIdx.y;
-  const uint32_t p = probe_ids[qi * np + pi];
-  const uint64_t off = part_offsets[p];
-  const uint32_t n_p = (uint32_t)(part_offsets[p + 1] - off);
+  const uint32_t p = a.probe_ids[qi * np + pi];
+  const uint64_t off = a.part_offsets[p];
+  const uint32_t n_p = (uint32_t)(a.part_offsets[p + 1] - off);
   const size_t slot = qi * np + pi;
   if (n_p == 0) {
-    if (tid == 0) cand_cnt[slot] = 0;
+    if (tid == 0) a.cand_cnt[slot] = 0;
     return;
   }
-  const float* q = queries + qi * d;
+  const float* q = a.queries + qi * d;
   for (int t = tid; t < d; t += 256)
-    qr[t] = METRIC == METRIC_DOT ? q[t] : __fsub_rn(q[t], centroids[(size_t)p * d + t]);  // v2.rs:316-332
+    qr[t] = METRIC == METRIC_DOT ? q[t] : __fsub_rn(q[t], a.centroids[(size_t)p * d + t]);  // v2.rs:316-332
   if (tid == 0) s_nw = 0;
   __syncthreads();
-  build_lut_smem<METRIC>(lut, qr, codebook, M, ds, tid);
+  build_lut_smem<METRIC>(lut, qr, a.codebook, M, ds, tid);
   __syncthreads();
 
-  const uint8_t* pc = codes + off * M;
+  const uint8_t* pc = a.codes + off * M;
   const float dot_fix = (float)M - 1.0f;
   for (uint32_t c0 = 0; c0 < n_p; c0 += SCAN_CHUNK) {
     const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
     int32_t key[RPT];
     uint64_t mine = PACK_INF;  // this lane's smallest candidate
-    uint32_t livemask = 0;     // FILTER: bit u = row u of this thread passed the prefilter
+    uint32_t livemask = 0;     // FILTER: bit u = row u of this thread passed the prefilter and the range
     // rows of warp w in this chunk: c0 + w*512 + lane + 32*u  (a warp owns a contiguous 512-row slab)
     const uint32_t wbase = warp * (RPT * 32);
 #pragma unroll
@@ -533,7 +669,6 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
       const uint32_t j = wbase + lane + 32 * u;
       key[u] = 0x7fffffff;
       if (j < clen && (!FILTER || row_allowed(allow, off + c0 + j))) {
-        if (FILTER) livemask |= 1u << u;
         float dist = 0.0f;
         if ((M & 15) == 0) {
           const uint4* rp = reinterpret_cast<const uint4*>(pc + (size_t)(c0 + j) * M);
@@ -542,23 +677,27 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
             const float* l0 = lut + c16 * 16 * 256;
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int aa = 0; aa < 4; ++aa)
 #pragma unroll
-              for (int b = 0; b < 4; ++b)
-                dist = f_add(dist, l0[(a * 4 + b) * 256 + ((w[a] >> (8 * b)) & 0xff)]);
+              for (int bb = 0; bb < 4; ++bb)
+                dist = f_add(dist, l0[(aa * 4 + bb) * 256 + ((w[aa] >> (8 * bb)) & 0xff)]);
           }
         } else {
           const uint8_t* rp = pc + (size_t)(c0 + j) * M;
           for (int m = 0; m < M; ++m) dist = f_add(dist, lut[m * 256 + rp[m]]);
         }
         if (METRIC == METRIC_DOT) dist = __fsub_rn(dist, dot_fix);  // pq/storage.rs:957-958
-        key[u] = total_order_key(dist);
-        const uint64_t c = pack_cand(key[u], c0 + j);
-        mine = c < mine ? c : mine;
+        const int32_t kv = total_order_key(dist);
+        if (!FILTER || key_in_range(a.flt, kv)) {
+          if (FILTER) livemask |= 1u << u;
+          key[u] = kv;
+          const uint64_t c = pack_cand(kv, c0 + j);
+          mine = c < mine ? c : mine;
+        }
       }
     }
-    // ---- warp-local threshold: Tw = k-th smallest lane minimum (PACK_INF if < k lanes have rows)
-    const uint64_t tw = __shfl_sync(0xffffffffu, warp_sort32(mine, lane), k - 1);
+    // ---- warp-local threshold: Tw = kk-th smallest lane minimum (PACK_INF if < kk lanes have rows)
+    const uint64_t tw = __shfl_sync(0xffffffffu, warp_sort32(mine, lane), kk - 1);
     // ---- compact the warp's elements <= Tw (ballot-ranked: deterministic order, no atomics)
     uint32_t wcnt = 0;
 #pragma unroll
@@ -572,21 +711,21 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
       wcnt += __popc(bal);
     }
     __syncwarp();
-    // ---- the warp's k smallest -> block list (lane r holds the r-th smallest; PACK_INF = none)
+    // ---- the warp's kk smallest -> block list (lane r holds the r-th smallest; PACK_INF = none)
     {
       const uint64_t best = warp_smallest32(wl[warp], wcnt, lane);
-      if (lane < k) fin[warp * SCAN_KFAST + lane] = best;
+      if (lane < kk) fin[warp * SCAN_KFAST + lane] = best;
     }
     __syncthreads();
-    if (warp == 0) {  // merge: 8 x k warp winners + carried winners -> k block winners
+    if (warp == 0) {  // merge: 8 x kk warp winners + carried winners -> kk block winners
       const uint32_t nw = s_nw;
-      if (lane < k) fin[8 * SCAN_KFAST + lane] = lane < (int)nw ? car[lane] : PACK_INF;
+      if (lane < kk) fin[8 * SCAN_KFAST + lane] = lane < (int)nw ? car[lane] : PACK_INF;
       __syncwarp();
-      // the winners sit at fin[w * 16 + r], r < k: visit them 32 at a time (2 warps' slots per pass)
+      // the winners sit at fin[w * 16 + r], r < kk: visit them 32 at a time (2 warps' slots per pass)
       uint64_t best = PACK_INF;
       for (int base = 0; base < 9 * SCAN_KFAST; base += 32) {
         const int i = base + lane;
-        uint64_t v = (i < 9 * SCAN_KFAST && (i % SCAN_KFAST) < k) ? fin[i] : PACK_INF;
+        uint64_t v = (i < 9 * SCAN_KFAST && (i % SCAN_KFAST) < kk) ? fin[i] : PACK_INF;
         v = warp_sort32(v, lane);
         if (base == 0) {
           best = v;
@@ -595,18 +734,31 @@ ivfpq_scan_kernel(const float* __restrict__ queries, int d, const float* __restr
           best = warp_bitonic_merge32(v < best ? v : best, lane);
         }
       }
-      if (lane < k) car[lane] = best;
-      const unsigned got = __ballot_sync(0xffffffffu, lane < k && best != PACK_INF);
+      if (lane < kk) car[lane] = best;
+      const unsigned got = __ballot_sync(0xffffffffu, lane < kk && best != PACK_INF);
       if (lane == 0) s_nw = __popc(got);
     }
     __syncthreads();
   }
-  const uint32_t nw = s_nw;
-  for (uint32_t i = tid; i < nw; i += 256) {
-    cand_d[slot * k + i] = key_to_float(cand_key(car[i]));
-    cand_id[slot * k + i] = row_ids[off + cand_pos(car[i])];
+  // car[0..nw) ascending by (key, position).  If the k-th and the (k+1)-th share a key, more rows tie at the
+  // k-th distance than fit: which of them the reference's BinaryHeap keeps depends on its sift order, so the
+  // slot goes on the replay list (ivfpq_scan_radix_kernel in list mode restates that loop).
+  uint32_t nw = s_nw;
+  if (nw == (uint32_t)kk) {
+    if (cand_key(car[k]) == cand_key(car[k - 1])) {
+      if (tid == 0) {
+        rlist[atomicAdd(rcount, 1u)] = (uint32_t)slot;
+        a.cand_cnt[slot] = 0;
+      }
+      return;
+    }
+    nw = k;
   }
-  if (tid == 0) cand_cnt[slot] = nw;
+  for (uint32_t i = tid; i < nw; i += 256) {
+    a.cand_d[slot * k + i] = key_to_float(cand_key(car[i]));
+    a.cand_id[slot * k + i] = a.row_ids[off + cand_pos(car[i])];
+  }
+  if (tid == 0) a.cand_cnt[slot] = nw;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -650,14 +802,17 @@ ivfflat_scan_kernel(const float* __restrict__ queries, int d, const uint32_t* __
                     int np, const uint64_t* __restrict__ part_offsets,
                     const float* __restrict__ vectors, const uint64_t* __restrict__ row_ids, int k,
                     float* __restrict__ cand_d, uint64_t* __restrict__ cand_id,
-                    uint32_t* __restrict__ cand_cnt, const uint64_t* __restrict__ allow) {
+                    uint32_t* __restrict__ cand_cnt, const ScanFilter flt) {
   extern __shared__ float smem[];
   __shared__ uint32_t s_outc;
+  const int kk = k + 1;  // see radix_slot: exposes ties that overflow the k-th place
+  const uint64_t* __restrict__ allow = flt.allow;
+  const bool filtering = allow != nullptr || flt.range;
   float* qs = smem;                          // [d]
-  float* cd = qs + d;                        // [SCAN_CHUNK + k]
-  uint32_t* cp = reinterpret_cast<uint32_t*>(cd + SCAN_CHUNK + k);
-  float* wd = reinterpret_cast<float*>(cp + k);
-  uint32_t* wp = reinterpret_cast<uint32_t*>(wd + k);
+  float* cd = qs + d;                        // [SCAN_CHUNK + kk]
+  uint32_t* cp = reinterpret_cast<uint32_t*>(cd + SCAN_CHUNK + kk);
+  float* wd = reinterpret_cast<float*>(cp + kk);
+  uint32_t* wp = reinterpret_cast<uint32_t*>(wd + kk);
   __shared__ int32_t s_key[8];
   __shared__ uint64_t s_tie[8];
   __shared__ int s_tid[9];
@@ -687,20 +842,21 @@ ivfflat_scan_kernel(const float* __restrict__ queries, int d, const uint32_t* __
   }
   __syncthreads();
   const float qn = METRIC == METRIC_COSINE ? s_qnorm : 0.0f;
+  const float excluded_key = __int_as_float(0x7fffffff);  // maximal key of the total order
   uint32_t nw = 0;
   for (uint32_t c0 = 0; c0 < n_p; c0 += SCAN_CHUNK) {
     const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
     for (uint32_t j = tid >> 4; j < clen; j += 16) {  // 16 rows per pass, 16 lanes each
       if (!row_allowed(allow, off + c0 + j)) {  // uniform per half-warp
-        if (l == 0) cd[j] = __int_as_float(0x7fffffff);  // maximal key of the total order
+        if (l == 0) cd[j] = excluded_key;
         continue;
       }
       const float dist = flat_row_distance<METRIC>(qs, vectors + (off + c0 + j) * (uint64_t)d, d, l, hmask, qn);
-      if (l == 0) cd[j] = dist;
+      if (l == 0) cd[j] = key_in_range(flt, total_order_key(dist)) ? dist : excluded_key;
     }
     __syncthreads();
     const uint32_t pool = clen + nw;
-    const uint32_t rounds = pool < (uint32_t)k ? pool : (uint32_t)k;
+    const uint32_t rounds = pool < (uint32_t)kk ? pool : (uint32_t)kk;
     bool first = true;
     for (uint32_t r = 0; r < rounds; ++r) {
       int32_t bk = 0;
@@ -731,24 +887,70 @@ ivfflat_scan_kernel(const float* __restrict__ queries, int d, const uint32_t* __
     nw = rounds;
     __syncthreads();
   }
-  if (allow) {
-    if (tid == 0) s_outc = 0;
-    __syncthreads();
-    for (uint32_t i = tid; i < nw; i += 256)
-      if (row_allowed(allow, off + cp[i])) {
-        const uint32_t at = atomicAdd(&s_outc, 1u);
-        cand_d[slot * k + at] = cd[SCAN_CHUNK + i];
-        cand_id[slot * k + at] = row_ids[off + cp[i]];
-      }
-    __syncthreads();
-    if (tid == 0) cand_cnt[slot] = s_outc;
+  // winners ascending by (key, position) in cd[SCAN_CHUNK ..), cp[]; excluded rows (maximal key) sort last
+  auto dropped = [&](uint32_t i) -> bool {
+    return !row_allowed(allow, off + cp[i]) || (flt.range && __float_as_int(cd[SCAN_CHUNK + i]) == 0x7fffffff);
+  };
+  if (filtering) {
+    uint32_t keep = nw;
+    while (keep > 0 && dropped(keep - 1)) --keep;
+    nw = keep;  // every thread computes the same value
+  }
+  bool replay = false;
+  if (nw == (uint32_t)kk) {
+    replay = total_order_key(cd[SCAN_CHUNK + k]) == total_order_key(cd[SCAN_CHUNK + k - 1]);
+    nw = k;
+  }
+  if (!replay) {
+    if (filtering) {  // (a NaN distance can leave a dropped row in front of the tail: re-test every entry)
+      if (tid == 0) s_outc = 0;
+      __syncthreads();
+      for (uint32_t i = tid; i < nw; i += 256)
+        if (!dropped(i)) {
+          const uint32_t at = atomicAdd(&s_outc, 1u);
+          cand_d[slot * k + at] = cd[SCAN_CHUNK + i];
+          cand_id[slot * k + at] = row_ids[off + cp[i]];
+        }
+      __syncthreads();
+      if (tid == 0) cand_cnt[slot] = s_outc;
+      return;
+    }
+    for (uint32_t i = tid; i < nw; i += 256) {
+      cand_d[slot * k + i] = cd[SCAN_CHUNK + i];
+      cand_id[slot * k + i] = row_ids[off + cp[i]];
+    }
+    if (tid == 0) cand_cnt[slot] = nw;
     return;
   }
-  for (uint32_t i = tid; i < nw; i += 256) {
-    cand_d[slot * k + i] = cd[SCAN_CHUNK + i];
-    cand_id[slot * k + i] = row_ids[off + cp[i]];
+  // ---- ties overflow the k-th place: the reference's heap loop (flat/index.rs:116-165), see radix_slot
+  __syncthreads();
+  uint32_t* hk = reinterpret_cast<uint32_t*>(wd);
+  uint32_t* hp = wp;
+  uint32_t len = 0;
+  for (uint32_t c0 = 0; c0 < n_p; c0 += SCAN_CHUNK) {
+    const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
+    for (uint32_t j = tid >> 4; j < clen; j += 16) {
+      const float dist = flat_row_distance<METRIC>(qs, vectors + (off + c0 + j) * (uint64_t)d, d, l, hmask, qn);
+      if (l == 0) cd[j] = dist;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (uint32_t j = 0; j < clen; ++j) {
+        const int32_t key = total_order_key(cd[j]);
+        if (filtering && (!row_allowed(allow, off + c0 + j) || !key_in_range(flt, key))) continue;
+        rheap_offer(hk, hp, len, (uint32_t)k, (uint32_t)key ^ 0x80000000u, c0 + j);
+      }
+    }
+    __syncthreads();
   }
-  if (tid == 0) cand_cnt[slot] = nw;
+  if (tid == 0) s_outc = len;
+  __syncthreads();
+  len = s_outc;
+  for (uint32_t i = tid; i < len; i += 256) {
+    cand_d[slot * k + i] = key_to_float((int32_t)(hk[i] ^ 0x80000000u));
+    cand_id[slot * k + i] = row_ids[off + hp[i]];
+  }
+  if (tid == 0) cand_cnt[slot] = len;
 }
 
 // global merge per query: ascending (distance, row id), first k
@@ -825,31 +1027,87 @@ __global__ void pq_scan_transposed_kernel(const float* __restrict__ lut, int M,
   out[j] = dist;
 }
 
+// FlatIndex::search over a distance array (flat/index.rs:97-127): the heap's final content, written
+// ascending by (distance, row id).  Selection of k + 1 by per-thread sorted lists; when rows tie at the
+// k-th distance beyond what fits, thread 0 replays the reference's loop through the Rust heap.
 template <int KMAX>
 __global__ void __launch_bounds__(256)
 flat_topk_kernel(const float* __restrict__ dists, const uint64_t* __restrict__ row_ids, uint64_t n,
-                 int k, uint64_t* __restrict__ out_id, float* __restrict__ out_d,
+                 int k, const ScanFilter flt, uint64_t* __restrict__ out_id, float* __restrict__ out_d,
                  uint32_t* __restrict__ out_cnt) {
   __shared__ int32_t s_key[8];
   __shared__ uint64_t s_tie[8];
   __shared__ int s_tid[9];
+  __shared__ uint32_t wk[KMAX], wpos[KMAX];  // winners: unsigned order key, position
+  __shared__ uint32_t s_len;
   const int tid = threadIdx.x;
+  const int kk = k + 1;
   ThreadTopK<KMAX> top;
-  for (uint64_t j = tid; j < n; j += 256) top.push(dists[j], (uint32_t)j, k);
+  for (uint64_t j = tid; j < n; j += 256) {
+    const float dv = dists[j];
+    if (key_in_range(flt, total_order_key(dv))) top.push(dv, (uint32_t)j, kk);
+  }
   int head = 0;
-  const uint32_t rounds = n < (uint64_t)k ? (uint32_t)n : (uint32_t)k;
-  for (uint32_t r = 0; r < rounds; ++r) {
+  uint32_t cnt = 0;
+  for (int r = 0; r < kk; ++r) {
     const bool has = head < top.cnt;
     const int32_t key = has ? total_order_key(top.d[head]) : 0;
     const uint64_t tie = has ? top.j[head] : 0;
     const int w = block_argmin<256>(has, key, tie, s_key, s_tie, s_tid);
+    if (w < 0) break;
     if (tid == w) {
-      out_d[r] = top.d[head];
-      out_id[r] = row_ids ? row_ids[top.j[head]] : (uint64_t)top.j[head];
+      wk[r] = (uint32_t)key ^ 0x80000000u;
+      wpos[r] = top.j[head];
       ++head;
     }
+    ++cnt;
   }
-  if (tid == 0) *out_cnt = rounds;
+  __syncthreads();
+  if (cnt == (uint32_t)kk) {
+    if (wk[k] == wk[k - 1]) {  // block-uniform: replay (see radix_slot)
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t len = 0;
+        for (uint64_t j = 0; j < n; ++j) {
+          const int32_t key = total_order_key(dists[j]);
+          if (!key_in_range(flt, key)) continue;
+          rheap_offer(wk, wpos, len, (uint32_t)k, (uint32_t)key ^ 0x80000000u, (uint32_t)j);
+        }
+        s_len = len;
+      }
+      __syncthreads();
+      cnt = s_len;
+    } else {
+      cnt = k;
+    }
+  }
+  // ascending (distance, row id) over the <= k survivors
+  __shared__ int32_t prev_key;
+  __shared__ uint64_t prev_id;
+  bool first = true;
+  for (uint32_t r = 0; r < cnt; ++r) {
+    int32_t bk = 0;
+    uint64_t bi = 0;
+    bool has = false;
+    const int32_t pk = first ? 0 : prev_key;
+    const uint64_t pid = first ? 0 : prev_id;
+    for (uint32_t i = tid; i < cnt; i += 256) {
+      const int32_t key = (int32_t)(wk[i] ^ 0x80000000u);
+      const uint64_t id = row_ids ? row_ids[wpos[i]] : (uint64_t)wpos[i];
+      if (!first && !ki_less(pk, pid, key, id)) continue;
+      if (!has || ki_less(key, id, bk, bi)) { bk = key; bi = id; has = true; }
+    }
+    const int w = block_argmin<256>(has, bk, bi, s_key, s_tie, s_tid);
+    if (tid == w) {
+      prev_key = bk;
+      prev_id = bi;
+      out_d[r] = key_to_float(bk);
+      out_id[r] = bi;
+    }
+    __syncthreads();
+    first = false;
+  }
+  if (tid == 0) *out_cnt = cnt;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -864,39 +1122,40 @@ void find_partitions_f32(const float* centroids, int K, int d, int metric, const
 }
 
 template <int METRIC>
-static void scan_launch(int nbits, dim3 grid, size_t smem, const float* queries, int d,
-                        const float* centroids, const float* codebook, int M, int ds,
-                        const uint32_t* probe_ids, int np, const uint64_t* part_offsets,
-                        const uint8_t* codes, const uint64_t* row_ids, int k, float* cand_d,
-                        uint64_t* cand_id, uint32_t* cand_cnt, const uint64_t* allow) {
-  if (nbits == 8 && k <= SCAN_KFAST) {
-    const size_t smem_fast = sizeof(float) * ((size_t)M * 256 + d);
-    if (allow) {  // filtered rows never enter the candidate lists
+static void scan_launch(int nbits, dim3 grid, size_t smem, const ScanArgs& a, uint32_t* rlist, uint32_t* rcount) {
+  const bool filtering = a.flt.allow != nullptr || a.flt.range;
+  if (nbits == 8 && a.k + 1 <= SCAN_KFAST) {
+    const size_t smem_fast = sizeof(float) * ((size_t)a.M * 256 + a.d);
+    LB2_CUDA(cudaMemsetAsync(rcount, 0, sizeof(uint32_t), ctx().stream));
+    if (filtering) {  // filtered rows never enter the candidate lists
       set_smem(ivfpq_scan_kernel<METRIC, true>, smem_fast);
-      LB2_LAUNCH("pq_scan", (ivfpq_scan_kernel<METRIC, true>), grid, 256, smem_fast, queries, d, centroids,
-                 codebook, M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt, allow);
+      LB2_LAUNCH("pq_scan", (ivfpq_scan_kernel<METRIC, true>), grid, 256, smem_fast, a, rlist, rcount);
     } else {
       set_smem(ivfpq_scan_kernel<METRIC, false>, smem_fast);
-      LB2_LAUNCH("pq_scan", (ivfpq_scan_kernel<METRIC, false>), grid, 256, smem_fast, queries, d, centroids,
-                 codebook, M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt, allow);
+      LB2_LAUNCH("pq_scan", (ivfpq_scan_kernel<METRIC, false>), grid, 256, smem_fast, a, rlist, rcount);
     }
+    // slots with ties beyond the k-th place (rare): the reference's heap loop, restated
+    set_smem((ivfpq_scan_radix_kernel<METRIC, 8>), smem);
+    const unsigned rgrid = (unsigned)std::min<uint64_t>((uint64_t)grid.x * grid.y, 4 * (uint64_t)ctx().num_sms);
+    LB2_LAUNCH("pq_scan_tie_replay", (ivfpq_scan_radix_kernel<METRIC, 8>), rgrid, 256, smem, a,
+               (const uint32_t*)rlist, (const uint32_t*)rcount);
     return;
   }
   if (nbits == 4) {
     set_smem((ivfpq_scan_radix_kernel<METRIC, 4>), smem);
-    LB2_LAUNCH("pq_scan", (ivfpq_scan_radix_kernel<METRIC, 4>), grid, 256, smem, queries, d, centroids, codebook,
-               M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt, allow);
+    LB2_LAUNCH("pq_scan", (ivfpq_scan_radix_kernel<METRIC, 4>), grid, 256, smem, a, (const uint32_t*)nullptr,
+               (const uint32_t*)nullptr);
     return;
   }
   set_smem((ivfpq_scan_radix_kernel<METRIC, 8>), smem);
-  LB2_LAUNCH("pq_scan", (ivfpq_scan_radix_kernel<METRIC, 8>), grid, 256, smem, queries, d, centroids, codebook,
-             M, ds, probe_ids, np, part_offsets, codes, row_ids, k, cand_d, cand_id, cand_cnt, allow);
+  LB2_LAUNCH("pq_scan", (ivfpq_scan_radix_kernel<METRIC, 8>), grid, 256, smem, a, (const uint32_t*)nullptr,
+             (const uint32_t*)nullptr);
 }
 
 void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const float* codebook, int M,
                       int nbits, const uint64_t* part_offsets, const uint8_t* codes,
                       const uint64_t* row_ids, const float* queries, uint64_t nq, int k, int nprobes,
-                      uint64_t* out_ids, float* out_dists, uint32_t* out_counts, const uint64_t* allow) {
+                      uint64_t* out_ids, float* out_dists, uint32_t* out_counts, const ScanFilter& flt) {
   if (nq == 0 || k == 0) return;
   if (nbits != 8 && nbits != 4) fail(LB2_INVALID_ARG, "PQ: num_bits must be 4 or 8, got %d", nbits);
   if (nbits == 4 && (M % 2 != 0 || M > 256)) fail(LB2_UNSUPPORTED, "4-bit PQ needs an even num_sub_vectors <= 256");
@@ -908,29 +1167,19 @@ void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const fl
   DevBuf<float> pd((size_t)nq * np), cand_d((size_t)nq * np * k);
   DevBuf<uint64_t> cand_id((size_t)nq * np * k);
   find_partitions_f32(centroids, K, d, cmetric, queries, nq, np, pids.p, pd.p);
-  const size_t smem = sizeof(float) * ((size_t)M * 256 + d + SCAN_CHUNK + 4 * (size_t)k);
+  const size_t smem = sizeof(float) * ((size_t)M * 256 + d + SCAN_CHUNK + 4 * (size_t)(k + 1));
   if (smem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "LUT of %zu bytes exceeds shared memory", smem);
-  dim3 grid(np, (unsigned)nq);
-  if (nq > 65535) {
-    // grid.y limit: process in slabs
-    for (uint64_t q0 = 0; q0 < nq; q0 += 32768) {
-      const uint64_t qn = std::min<uint64_t>(32768, nq - q0);
-      dim3 g(np, (unsigned)qn);
-      if (cmetric == METRIC_DOT)
-        scan_launch<METRIC_DOT>(nbits, g, smem, queries + q0 * d, d, centroids, codebook, M, ds,
-                                pids.p + q0 * np, np, part_offsets, codes, row_ids, k,
-                                cand_d.p + q0 * np * k, cand_id.p + q0 * np * k, cand_cnt.p + q0 * np, allow);
-      else
-        scan_launch<METRIC_L2>(nbits, g, smem, queries + q0 * d, d, centroids, codebook, M, ds,
-                               pids.p + q0 * np, np, part_offsets, codes, row_ids, k,
-                               cand_d.p + q0 * np * k, cand_id.p + q0 * np * k, cand_cnt.p + q0 * np, allow);
-    }
-  } else if (cmetric == METRIC_DOT) {
-    scan_launch<METRIC_DOT>(nbits, grid, smem, queries, d, centroids, codebook, M, ds, pids.p, np,
-                            part_offsets, codes, row_ids, k, cand_d.p, cand_id.p, cand_cnt.p, allow);
-  } else {
-    scan_launch<METRIC_L2>(nbits, grid, smem, queries, d, centroids, codebook, M, ds, pids.p, np,
-                           part_offsets, codes, row_ids, k, cand_d.p, cand_id.p, cand_cnt.p, allow);
+  const uint64_t slab = 32768;  // grid.y limit: queries are processed in slabs
+  DevBuf<uint32_t> rlist((size_t)std::min<uint64_t>(nq, slab) * np), rcount(1);
+  for (uint64_t q0 = 0; q0 < nq; q0 += slab) {
+    const uint64_t qn = std::min<uint64_t>(slab, nq - q0);
+    dim3 g(np, (unsigned)qn);
+    ScanArgs a{queries + q0 * d, d, centroids, codebook, M, ds, pids.p + q0 * np, np, part_offsets, codes, row_ids, k,
+               cand_d.p + q0 * np * k, cand_id.p + q0 * np * k, cand_cnt.p + q0 * np, flt};
+    if (cmetric == METRIC_DOT)
+      scan_launch<METRIC_DOT>(nbits, g, smem, a, rlist.p, rcount.p);
+    else
+      scan_launch<METRIC_L2>(nbits, g, smem, a, rlist.p, rcount.p);
   }
   LB2_LAUNCH("merge_topk", merge_kernel, (unsigned)nq, 128, 0, cand_d.p, cand_id.p, cand_cnt.p, np,
              k, out_ids, out_dists, out_counts);
@@ -969,7 +1218,7 @@ void row_mask_f32(const uint64_t* row_ids, uint64_t n, const uint64_t* allow, ui
 void ivfflat_search_f32(const float* centroids, int K, int d, int metric, const uint64_t* part_offsets,
                         const float* vectors, const uint64_t* row_ids, const float* queries, uint64_t nq,
                         int k, int nprobes, uint64_t* out_ids, float* out_dists, uint32_t* out_counts,
-                        const uint64_t* allow) {
+                        const ScanFilter& flt) {
   if (nq == 0 || k == 0) return;
   if (k > 1024) fail(LB2_UNSUPPORTED, "k (incl. refine factor) > 1024 is not implemented");
   const int np = nprobes < K ? nprobes : K;
@@ -979,7 +1228,7 @@ void ivfflat_search_f32(const float* centroids, int K, int d, int metric, const 
   DevBuf<float> pd((size_t)nq * np), cand_d((size_t)nq * np * k);
   DevBuf<uint64_t> cand_id((size_t)nq * np * k);
   find_partitions_f32(centroids, K, d, cmetric, queries, nq, np, pids.p, pd.p);
-  const size_t smem = sizeof(float) * ((size_t)d + SCAN_CHUNK + 4 * (size_t)k);
+  const size_t smem = sizeof(float) * ((size_t)d + SCAN_CHUNK + 4 * (size_t)(k + 1));
   if (smem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "dimension %d too large for the flat scan", d);
   for (uint64_t q0 = 0; q0 < nq; q0 += 32768) {
     const uint64_t qn = std::min<uint64_t>(32768, nq - q0);
@@ -989,7 +1238,7 @@ void ivfflat_search_f32(const float* centroids, int K, int d, int metric, const 
       set_smem(ivfflat_scan_kernel<MET>, smem);                                                         \
       LB2_LAUNCH("flat_scan", (ivfflat_scan_kernel<MET>), g, 256, smem, queries + q0 * d, d,             \
                  pids.p + q0 * np, np, part_offsets, vectors, row_ids, k, cand_d.p + q0 * np * k,        \
-                 cand_id.p + q0 * np * k, cand_cnt.p + q0 * np, allow);                                  \
+                 cand_id.p + q0 * np * k, cand_cnt.p + q0 * np, flt);                                    \
     }
     if (metric == METRIC_DOT) LB2_FLAT(METRIC_DOT)
     else if (metric == METRIC_COSINE) LB2_FLAT(METRIC_COSINE)
@@ -1009,7 +1258,7 @@ __global__ void __launch_bounds__(256)
 refine_kernel(const float* __restrict__ queries, int d, const float* __restrict__ vectors,
               uint64_t num_vectors, const uint64_t* __restrict__ cand_id, const uint32_t* __restrict__ cand_cnt,
               int kc, int k, uint64_t* __restrict__ out_id, float* __restrict__ out_d,
-              uint32_t* __restrict__ out_cnt) {
+              uint32_t* __restrict__ out_cnt, int has_lower, float lower, int has_upper, float upper) {
   extern __shared__ float smem[];
   float* qs = smem;       // [d]
   float* cd = qs + d;     // [kc]
@@ -1045,6 +1294,9 @@ refine_kernel(const float* __restrict__ queries, int d, const float* __restrict_
   bool first = true;
   uint32_t r = 0;
   const uint32_t rounds = cnt < (uint32_t)k ? cnt : (uint32_t)k;
+  auto passes = [&](float dv) {  // LanceFilterExec(_distance >= lower AND _distance < upper): SQL compares
+    return (!has_lower || dv >= lower) && (!has_upper || dv < upper);
+  };
   for (; r < rounds; ++r) {
     int32_t bk = 0;
     uint64_t bi = 0;
@@ -1053,6 +1305,7 @@ refine_kernel(const float* __restrict__ queries, int d, const float* __restrict_
     const int32_t pk = first ? 0 : prev_key;
     const uint64_t pid = first ? 0 : prev_id;
     for (uint32_t c = tid; c < cnt; c += 256) {
+      if (!passes(cd[c])) continue;
       const int32_t key = total_order_key(cd[c]);
       const uint64_t id = ids[c];
       if (!first && !ki_less(pk, pid, key, id)) continue;
@@ -1078,14 +1331,16 @@ refine_kernel(const float* __restrict__ queries, int d, const float* __restrict_
 
 void refine_f32(const float* queries, uint64_t nq, int d, int metric, const float* vectors,
                 uint64_t num_vectors, const uint64_t* cand_id, const uint32_t* cand_cnt, int kc, int k,
-                uint64_t* out_id, float* out_d, uint32_t* out_cnt) {
+                uint64_t* out_id, float* out_d, uint32_t* out_cnt, int has_lower, float lower, int has_upper,
+                float upper) {
   if (nq == 0) return;
   const size_t smem = sizeof(float) * ((size_t)d + kc);
 #define LB2_REF(MET)                                                                                  \
   {                                                                                                   \
     set_smem(refine_kernel<MET>, smem);                                                               \
     LB2_LAUNCH("refine", (refine_kernel<MET>), (unsigned)nq, 256, smem, queries, d, vectors,           \
-               num_vectors, cand_id, cand_cnt, kc, k, out_id, out_d, out_cnt);                         \
+               num_vectors, cand_id, cand_cnt, kc, k, out_id, out_d, out_cnt, has_lower, lower,        \
+               has_upper, upper);                                                                      \
   }
   if (metric == METRIC_DOT) LB2_REF(METRIC_DOT)
   else if (metric == METRIC_COSINE) LB2_REF(METRIC_COSINE)
@@ -1219,15 +1474,15 @@ void pack_nibbles(const uint8_t* codes, uint64_t n, int M, uint8_t* out) {
   if (total) LB2_LAUNCH("pack_nibbles", pack_nibbles_kernel, cdiv(total, 256), 256, 0, codes, total, out);
 }
 
-void flat_topk_f32(const float* dists, const uint64_t* row_ids, uint64_t n, int k, uint64_t* out_id,
-                   float* out_d, uint32_t* out_cnt) {
+void flat_topk_f32(const float* dists, const uint64_t* row_ids, uint64_t n, int k, const ScanFilter& flt,
+                   uint64_t* out_id, float* out_d, uint32_t* out_cnt) {
   if (k > 1024) fail(LB2_UNSUPPORTED, "k > 1024 is not implemented");
-  if (k <= 16)
-    LB2_LAUNCH("flat_topk", flat_topk_kernel<16>, 1, 256, 0, dists, row_ids, n, k, out_id, out_d, out_cnt);
-  else if (k <= 128)
-    LB2_LAUNCH("flat_topk", flat_topk_kernel<128>, 1, 256, 0, dists, row_ids, n, k, out_id, out_d, out_cnt);
+  if (k < 16)
+    LB2_LAUNCH("flat_topk", flat_topk_kernel<16>, 1, 256, 0, dists, row_ids, n, k, flt, out_id, out_d, out_cnt);
+  else if (k < 128)
+    LB2_LAUNCH("flat_topk", flat_topk_kernel<128>, 1, 256, 0, dists, row_ids, n, k, flt, out_id, out_d, out_cnt);
   else
-    LB2_LAUNCH("flat_topk", flat_topk_kernel<1024>, 1, 256, 0, dists, row_ids, n, k, out_id, out_d, out_cnt);
+    LB2_LAUNCH("flat_topk", flat_topk_kernel<1025>, 1, 256, 0, dists, row_ids, n, k, flt, out_id, out_d, out_cnt);
 }
 
 }  // namespace lb2

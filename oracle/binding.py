@@ -253,7 +253,7 @@ def _mask_args(allow, block):
 
 
 def ivfpq_search(centroids, codebook, part_offsets, codes, row_ids, queries, k, nprobes,
-                 metric="l2", nbits=8, nthreads=1, allow=None, block=None):
+                 metric="l2", nbits=8, nthreads=1, allow=None, block=None, lower=None, upper=None):
     centroids, codebook, queries = _f32(centroids), _f32(codebook), _f32(queries)
     K, d = centroids.shape
     M = codebook.shape[0]
@@ -264,6 +264,17 @@ def ivfpq_search(centroids, codebook, part_offsets, codes, row_ids, queries, k, 
     oi = np.empty((nq, k), np.uint64)
     od = np.empty((nq, k), np.float32)
     oc = np.empty(nq, np.uint32)
+    if lower is not None or upper is not None:  # range branch (flat/index.rs:100-115,131-148)
+        keep, margs = _mask_args(allow, block)
+        lib().lo_ivfpq_search_ex(_p(centroids, C.c_float), C.c_uint64(K), C.c_uint64(d),
+                                 C.c_int(METRIC[metric]), _p(codebook, C.c_float), C.c_uint64(M),
+                                 C.c_int(nbits), _p(po, C.c_uint64), _p(codes, C.c_uint8),
+                                 _p(rid, C.c_uint64), _p(queries, C.c_float), C.c_uint64(nq),
+                                 C.c_uint64(k), C.c_uint64(nprobes), *margs,
+                                 C.c_int(lower is not None), C.c_float(lower or 0.0),
+                                 C.c_int(upper is not None), C.c_float(upper or 0.0), _p(oi, C.c_uint64),
+                                 _p(od, C.c_float), _p(oc, C.c_uint32), C.c_int(nthreads))
+        return oi, od, oc
     if allow is not None or block is not None:  # prefilter path (flat/index.rs:129-165)
         keep, margs = _mask_args(allow, block)
         lib().lo_ivfpq_search_masked(_p(centroids, C.c_float), C.c_uint64(K), C.c_uint64(d),
@@ -280,6 +291,16 @@ def ivfpq_search(centroids, codebook, part_offsets, codes, row_ids, queries, k, 
                           C.c_uint64(k), C.c_uint64(nprobes), _p(oi, C.c_uint64),
                           _p(od, C.c_float), _p(oc, C.c_uint32), C.c_int(nthreads))
     return oi, od, oc
+
+
+def sum_4bit_dist_table(n, code_len, codes, dist_table):
+    """sum_4bit_dist_table_scalar (lance-linalg/src/simd/dist_table.rs:62-91) -> u16[n]."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    dist_table = np.ascontiguousarray(dist_table, dtype=np.uint8)
+    out = np.zeros(n, np.uint16)
+    lib().lo_sum_4bit_dist_table(C.c_uint64(n), C.c_uint64(code_len), _p(codes, C.c_uint8),
+                                 _p(dist_table, C.c_uint8), _p(out, C.c_uint16))
+    return out
 
 
 def pq_scan_4bit(lut, codes_t, n, k_hint, metric="l2"):
@@ -307,7 +328,7 @@ def brute_force_topk(data, queries, k, metric="l2", nthreads=1):
 
 
 def ivfflat_search(centroids, part_offsets, vectors, row_ids, queries, k, nprobes, metric="l2", nthreads=1,
-                   allow=None, block=None):
+                   allow=None, block=None, lower=None, upper=None):
     centroids, vectors, queries = _f32(centroids), _f32(vectors), _f32(queries)
     K, d = centroids.shape
     po = np.ascontiguousarray(part_offsets, dtype=np.uint64)
@@ -316,6 +337,15 @@ def ivfflat_search(centroids, part_offsets, vectors, row_ids, queries, k, nprobe
     oi = np.empty((nq, k), np.uint64)
     od = np.empty((nq, k), np.float32)
     oc = np.empty(nq, np.uint32)
+    if lower is not None or upper is not None:
+        keep, margs = _mask_args(allow, block)
+        lib().lo_ivfflat_search_ex(_p(centroids, C.c_float), C.c_uint64(K), C.c_uint64(d), C.c_int(METRIC[metric]),
+                                   _p(po, C.c_uint64), _p(vectors, C.c_float), _p(rid, C.c_uint64),
+                                   _p(queries, C.c_float), C.c_uint64(nq), C.c_uint64(k), C.c_uint64(nprobes),
+                                   *margs, C.c_int(lower is not None), C.c_float(lower or 0.0),
+                                   C.c_int(upper is not None), C.c_float(upper or 0.0), _p(oi, C.c_uint64),
+                                   _p(od, C.c_float), _p(oc, C.c_uint32), C.c_int(nthreads))
+        return oi, od, oc
     if allow is not None or block is not None:
         keep, margs = _mask_args(allow, block)
         lib().lo_ivfflat_search_masked(_p(centroids, C.c_float), C.c_uint64(K), C.c_uint64(d), C.c_int(METRIC[metric]),

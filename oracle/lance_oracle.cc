@@ -752,6 +752,30 @@ void lo_pq_scan_4bit(const float* lut, uint64_t M, const uint8_t* codes_t, uint6
   }
 }
 
+// a19  sum_4bit_dist_table_scalar (lance-linalg/src/simd/dist_table.rs:62-91): u8 table sums over 4-bit
+//   codes laid out in PERM0 order, 32 vectors per block, code_len bytes per vector; u16 saturating adds.
+//   (The IVF_PQ 4-bit path uses compute_pq_distance_4bit above; this kernel serves the reference's RabitQ
+//   storage, bq/storage.rs:333 -- restated because it carries the reference's only 4-bit literal,
+//   dist_table.rs:179-217, and its C twin dist_table.c:8 compiles into oracle/_ref.)
+void lo_sum_4bit_dist_table(uint64_t n, uint64_t code_len, const uint8_t* codes, const uint8_t* dist_table,
+                            uint16_t* dists) {
+  static const uint64_t PERM0[16] = {0, 8, 1, 9, 2, 10, 3, 11, 4, 12, 5, 13, 6, 14, 7, 15};
+  auto sat = [](uint16_t a, uint16_t b) { uint32_t s = uint32_t(a) + b; return uint16_t(s > 65535 ? 65535 : s); };
+  for (uint64_t vb = 0; vb * 32 < n; ++vb) {
+    const uint8_t* blocks = codes + vb * 32 * code_len;
+    for (uint64_t sv = 0; sv * 32 < 32 * code_len; ++sv) {
+      const uint8_t* block = blocks + sv * 32;
+      const uint8_t* cur = dist_table + sv * 2 * 16;
+      const uint8_t* nxt = dist_table + (sv * 2 + 1) * 16;
+      for (uint64_t j = 0; j < 16; ++j) {
+        const uint64_t lo_id = vb * 32 + PERM0[j], hi_id = lo_id + 16;
+        dists[lo_id] = sat(sat(dists[lo_id], cur[block[j] & 0x0F]), nxt[block[j + 16] & 0x0F]);
+        dists[hi_id] = sat(sat(dists[hi_id], cur[block[j] >> 4]), nxt[block[j + 16] >> 4]);
+      }
+    }
+  }
+}
+
 // a16  FlatIndex::search fast path (flat/index.rs:97-127): size-k Rust BinaryHeap, push while
 //   len<k else replace the root iff root.dist > dist (total_cmp).  Output = heap's internal
 //   vector order (`into_iter`), unsorted.  Optional [lower, upper) range (flat/index.rs:101-115).
@@ -793,13 +817,25 @@ struct RowMask {
 
 // a16  FlatIndex::search prefilter path (flat/index.rs:129-165): rows are visited in storage order,
 //   unselected rows are skipped BEFORE the distance is looked at, then the same heap rule.
+// flat/index.rs:101-102,132-133: lower_bound.unwrap_or(f32::MIN), upper_bound.unwrap_or(f32::MAX)
+struct Range {
+  int use; float lower, upper;
+  bool excludes(float dist) const {
+    return use && (total_key(dist) < total_key(lower) || total_key(dist) >= total_key(upper));
+  }
+};
+static Range make_range(int has_lower, float lower, int has_upper, float upper) {
+  return Range{has_lower || has_upper, has_lower ? lower : std::numeric_limits<float>::lowest(),
+               has_upper ? upper : std::numeric_limits<float>::max()};
+}
 static uint64_t flat_topk_masked(const float* dists, const uint64_t* row_ids, uint64_t n, uint64_t k,
-                                 const RowMask& mask, uint64_t* out_ids, float* out_dists) {
+                                 const RowMask& mask, const Range& range, uint64_t* out_ids, float* out_dists) {
   RustMaxHeap h;
   if (k == 0) return 0;
   for (uint64_t j = 0; j < n; ++j) {
     if (!mask.selected(row_ids[j])) continue;
     float dist = dists[j];
+    if (range.excludes(dist)) continue;
     if (h.data.size() < k) {
       h.push({row_ids[j], dist});
     } else if (gt(h.data[0].dist, dist)) {
@@ -838,8 +874,8 @@ void lo_flat_distance_all(const float* query, const float* vectors, uint64_t n, 
 static void ivfpq_search_impl(const float* centroids, uint64_t K, uint64_t d, int metric,
                      const float* codebook, uint64_t M, int nbits, const uint64_t* part_offsets,
                      const uint8_t* codes, const uint64_t* row_ids, const float* queries,
-                     uint64_t nq, uint64_t k, uint64_t nprobes, const RowMask& mask, uint64_t* out_ids,
-                     float* out_dists, uint32_t* out_counts, int nthreads) {
+                     uint64_t nq, uint64_t k, uint64_t nprobes, const RowMask& mask, const Range& range,
+                     uint64_t* out_ids, float* out_dists, uint32_t* out_counts, int nthreads) {
   const uint64_t ncode = uint64_t(1) << nbits;
   uint64_t max_part = 0;
   for (uint64_t p = 0; p < K; ++p) max_part = std::max(max_part, part_offsets[p + 1] - part_offsets[p]);
@@ -885,8 +921,10 @@ static void ivfpq_search_impl(const float* centroids, uint64_t K, uint64_t d, in
         else
           lo_pq_scan(lut.data(), M, codes_t.data() + part_offsets[p] * M, n, cmetric, dist.data());
         uint64_t got = mask.empty()
-                           ? lo_flat_topk(dist.data(), row_ids + part_offsets[p], n, k, 0, 0, 0, hid.data(), hd.data())
-                           : flat_topk_masked(dist.data(), row_ids + part_offsets[p], n, k, mask, hid.data(), hd.data());
+                           ? lo_flat_topk(dist.data(), row_ids + part_offsets[p], n, k, range.use, range.lower,
+                                          range.upper, hid.data(), hd.data())
+                           : flat_topk_masked(dist.data(), row_ids + part_offsets[p], n, k, mask, range, hid.data(),
+                                              hd.data());
         for (uint64_t i = 0; i < got; ++i) cand.push_back({hid[i], hd[i]});
       }
       std::sort(cand.begin(), cand.end(), [](const Node& a, const Node& c) {
@@ -915,7 +953,7 @@ void lo_ivfpq_search(const float* centroids, uint64_t K, uint64_t d, int metric,
                      float* out_dists, uint32_t* out_counts, int nthreads) {
   const RowMask none{nullptr, 0, 0, nullptr, 0, 0};
   ivfpq_search_impl(centroids, K, d, metric, codebook, M, nbits, part_offsets, codes, row_ids, queries, nq, k,
-                    nprobes, none, out_ids, out_dists, out_counts, nthreads);
+                    nprobes, none, Range{0, 0, 0}, out_ids, out_dists, out_counts, nthreads);
 }
 // the same with a prefilter (PreFilter::mask -> RowIdMask, lance-index/src/prefilter.rs:27-51)
 void lo_ivfpq_search_masked(const float* centroids, uint64_t K, uint64_t d, int metric,
@@ -927,7 +965,20 @@ void lo_ivfpq_search_masked(const float* centroids, uint64_t K, uint64_t d, int 
                             int nthreads) {
   const RowMask mask{allow, n_allow, has_allow, block, n_block, has_block};
   ivfpq_search_impl(centroids, K, d, metric, codebook, M, nbits, part_offsets, codes, row_ids, queries, nq, k,
-                    nprobes, mask, out_ids, out_dists, out_counts, nthreads);
+                    nprobes, mask, Range{0, 0, 0}, out_ids, out_dists, out_counts, nthreads);
+}
+// ... and with the range branch of FlatIndex::search (flat/index.rs:100-115,131-148)
+void lo_ivfpq_search_ex(const float* centroids, uint64_t K, uint64_t d, int metric,
+                        const float* codebook, uint64_t M, int nbits, const uint64_t* part_offsets,
+                        const uint8_t* codes, const uint64_t* row_ids, const float* queries,
+                        uint64_t nq, uint64_t k, uint64_t nprobes, const uint64_t* allow,
+                        uint64_t n_allow, int has_allow, const uint64_t* block, uint64_t n_block,
+                        int has_block, int has_lower, float lower, int has_upper, float upper,
+                        uint64_t* out_ids, float* out_dists, uint32_t* out_counts, int nthreads) {
+  const RowMask mask{allow, n_allow, has_allow, block, n_block, has_block};
+  ivfpq_search_impl(centroids, K, d, metric, codebook, M, nbits, part_offsets, codes, row_ids, queries, nq, k,
+                    nprobes, mask, make_range(has_lower, lower, has_upper, upper), out_ids, out_dists, out_counts,
+                    nthreads);
 }
 
 // IVF_FLAT query (lance-index/src/vector/flat/index.rs:82-177 over FlatFloatStorage,
@@ -937,7 +988,7 @@ void lo_ivfpq_search_masked(const float* centroids, uint64_t K, uint64_t d, int 
 static void ivfflat_search_impl(const float* centroids, uint64_t K, uint64_t d, int metric,
                        const uint64_t* part_offsets, const float* vectors, const uint64_t* row_ids,
                        const float* queries, uint64_t nq, uint64_t k, uint64_t nprobes, const RowMask& mask,
-                       uint64_t* out_ids, float* out_dists, uint32_t* out_counts, int nthreads) {
+                       const Range& range, uint64_t* out_ids, float* out_dists, uint32_t* out_counts, int nthreads) {
   uint64_t max_part = 0;
   for (uint64_t p = 0; p < K; ++p) max_part = std::max(max_part, part_offsets[p + 1] - part_offsets[p]);
   const int cmetric = metric == 2 ? 2 : 0;
@@ -962,8 +1013,10 @@ static void ivfflat_search_impl(const float* centroids, uint64_t K, uint64_t d, 
         if (n == 0) continue;
         lo_flat_distance_all(q.data(), vectors + part_offsets[p] * d, n, d, metric, dist.data(), 1);
         uint64_t got = mask.empty()
-                           ? lo_flat_topk(dist.data(), row_ids + part_offsets[p], n, k, 0, 0, 0, hid.data(), hd.data())
-                           : flat_topk_masked(dist.data(), row_ids + part_offsets[p], n, k, mask, hid.data(), hd.data());
+                           ? lo_flat_topk(dist.data(), row_ids + part_offsets[p], n, k, range.use, range.lower,
+                                          range.upper, hid.data(), hd.data())
+                           : flat_topk_masked(dist.data(), row_ids + part_offsets[p], n, k, mask, range, hid.data(),
+                                              hd.data());
         for (uint64_t i = 0; i < got; ++i) cand.push_back({hid[i], hd[i]});
       }
       std::sort(cand.begin(), cand.end(), [](const Node& a, const Node& c) {
@@ -991,7 +1044,7 @@ void lo_ivfflat_search(const float* centroids, uint64_t K, uint64_t d, int metri
                        uint64_t* out_ids, float* out_dists, uint32_t* out_counts, int nthreads) {
   const RowMask none{nullptr, 0, 0, nullptr, 0, 0};
   ivfflat_search_impl(centroids, K, d, metric, part_offsets, vectors, row_ids, queries, nq, k, nprobes, none,
-                      out_ids, out_dists, out_counts, nthreads);
+                      Range{0, 0, 0}, out_ids, out_dists, out_counts, nthreads);
 }
 void lo_ivfflat_search_masked(const float* centroids, uint64_t K, uint64_t d, int metric,
                               const uint64_t* part_offsets, const float* vectors, const uint64_t* row_ids,
@@ -1001,7 +1054,17 @@ void lo_ivfflat_search_masked(const float* centroids, uint64_t K, uint64_t d, in
                               uint32_t* out_counts, int nthreads) {
   const RowMask mask{allow, n_allow, has_allow, block, n_block, has_block};
   ivfflat_search_impl(centroids, K, d, metric, part_offsets, vectors, row_ids, queries, nq, k, nprobes, mask,
-                      out_ids, out_dists, out_counts, nthreads);
+                      Range{0, 0, 0}, out_ids, out_dists, out_counts, nthreads);
+}
+void lo_ivfflat_search_ex(const float* centroids, uint64_t K, uint64_t d, int metric,
+                          const uint64_t* part_offsets, const float* vectors, const uint64_t* row_ids,
+                          const float* queries, uint64_t nq, uint64_t k, uint64_t nprobes,
+                          const uint64_t* allow, uint64_t n_allow, int has_allow, const uint64_t* block,
+                          uint64_t n_block, int has_block, int has_lower, float lower, int has_upper, float upper,
+                          uint64_t* out_ids, float* out_dists, uint32_t* out_counts, int nthreads) {
+  const RowMask mask{allow, n_allow, has_allow, block, n_block, has_block};
+  ivfflat_search_impl(centroids, K, d, metric, part_offsets, vectors, row_ids, queries, nq, k, nprobes, mask,
+                      make_range(has_lower, lower, has_upper, upper), out_ids, out_dists, out_counts, nthreads);
 }
 
 // exact brute-force ground truth (rust/lance/src/index/vector/ivf/v2.rs:959-983 `ground_truth`)

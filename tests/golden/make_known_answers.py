@@ -61,6 +61,15 @@ cases.append(dict(name="cosine_not_aligned", ref="lance-linalg/src/distance/cosi
 cases.append(dict(name="pq_transposed_equals_rowmajor", ref="lance-index/src/vector/pq/distance.rs:337-365",
                   op="pq_scan_identity", num_vectors=100, num_sub_vectors=4, num_bits=8, dimension=16))
 
+# lance-linalg/src/simd/dist_table.rs:179-217 test_sum_4bit_dist_table_basic: 32 vectors, code_len 2,
+# the 32-byte code pattern repeated to n * code_len bytes, dist_table[i] = i % 16 + 1; the reference asserts
+# kernel == scalar and dists[1] == 38
+pattern = [0x12, 0x34, 0x56, 0x78, 0x9a, 0xbc, 0xde, 0xf0, 0x11, 0x22, 0x33, 0x44, 0x55, 0x66, 0x77, 0x88,
+           0x99, 0xaa, 0xbb, 0xcc, 0xdd, 0xee, 0xff, 0x00, 0x12, 0x34, 0x56, 0x78, 0x9a, 0xbc, 0xde, 0xf0]
+cases.append(dict(name="sum_4bit_dist_table_basic", ref="lance-linalg/src/simd/dist_table.rs:179-217",
+                  op="sum_4bit_dist_table", n=32, code_len=2, codes=pattern * (32 * 2 // len(pattern)),
+                  dist_table=[i % 16 + 1 for i in range(16 * 4)], expect_index=1, expect=38))
+
 out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_known_answers.json")
 with open(out, "w") as f:
     json.dump(cases, f, indent=1)

@@ -40,6 +40,15 @@ def test_reference_known_answers_on_gpu():
     import json, os
     cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_known_answers.json")))
     for c in cases:
+        if c["op"] == "l2_u8":      # l2.rs:431-447: the u8 kernel sums in u32
+            x, y = np.asarray(c["x"], np.uint8), np.asarray(c["y"], np.uint8)
+            assert float(lb.l2_distance_batch(x, y, x.size)[0]) == c["expect"] == float(lb.l2_distance_batch(y, x, x.size)[0])
+            continue
+        if c["op"] == "cosine":     # cosine.rs:361-393
+            got = float(lb.cosine_distance_batch(np.asarray(c["x"], np.float32), np.asarray(c["y"], np.float32), len(c["x"]))[0])
+            tol = c["abs"] if "abs" in c else c["rel"] * abs(c["expect"])
+            assert abs(got - c["expect"]) <= tol, c["name"]
+            continue
         if c["op"] != "l2_batch":
             continue
         got = lb.l2_distance_batch(c["frm"], c["to"], c["d"])
@@ -200,15 +209,12 @@ def test_pq_scan_reference_deterministic_case():
 
 
 def _check_topk(ids, dists, oi, od, k):
-    """distance multisets identical; ids identical strictly below the k-th distance (rows tied
-    at the boundary are implementation-defined in the reference's BinaryHeap)."""
-    assert np.array_equal(np.sort(dists), np.sort(od))
-    if len(od) == 0:
-        return
-    kth = np.sort(od)[-1]
-    a = set(ids[dists < kth].tolist())
-    b = set(oi[od < kth].tolist())
-    assert a == b
+    """the SET of (distance, row id) pairs equals the final content of the reference's BinaryHeap --
+    rows tied at the k-th distance included (which of them survive depends on the heap's sift order,
+    flat/index.rs:116-126; the product replays that loop whenever such ties overflow the k-th place)."""
+    got = sorted(zip(np.asarray(dists).view(np.uint32).tolist(), np.asarray(ids).tolist()))
+    exp = sorted(zip(np.asarray(od).view(np.uint32).tolist(), np.asarray(oi).tolist()))
+    assert got == exp
 
 
 def test_flat_topk_matches_heap_semantics():
@@ -253,6 +259,8 @@ def test_index_search_matches_oracle(metric):
             assert np.isinf(dists[i, c:]).all()
             _check_topk(ids[i, :c], dists[i, :c], oi[i, :c], od[i, :c], k)
             assert np.all(np.diff(dists[i, :c]) >= 0)
+        # the merged output is sorted by (_distance, _rowid) like the reference's SortExec: arrays are equal
+        assert np.array_equal(ids, oi) and np.array_equal(dists, od)
 
 
 # ---- 4-bit PQ (a19): 16 codewords per sub-space, packed codes, u8-quantised table scan -----------
@@ -751,8 +759,7 @@ def test_search_with_refine_matches_exact_rerank_of_oracle_candidates():
         cand = oi[i, :oc[i]].astype(np.int64)
         ex = np.array([ob.l2(q[i], data[c]) for c in cand], np.float32)
         order = np.lexsort((cand, ex))[:k]
-        # candidate SETS can differ only through ties at the k*rf-th PQ distance (see _check_topk)
-        assert np.array_equal(np.sort(dists[i]), np.sort(ex[order])), i
+        assert np.array_equal(dists[i], ex[order]) and np.array_equal(ids[i].astype(np.int64), cand[order]), i
     gt, _ = ob.brute_force_topk(data, q, 10, nthreads=NT)
     recall = np.mean([len(set(ids[i].tolist()) & set(gt[i].tolist())) / 10 for i in range(len(q))])
     plain, _ = ix.search(q, k=10, nprobes=nprobes)
@@ -859,3 +866,197 @@ def test_config5_shape_u8_m32():
                                  parts["row_ids"], f[:16], 10, 8, nthreads=NT)
     for i in range(16):
         _check_topk(ids[i, :oc[i]], dists[i, :oc[i]], oi[i, :oc[i]], od[i, :oc[i]], 10)
+
+
+# ---- round 2: parity loose ends -----------------------------------------------------------------------
+def test_flat_topk_ties_and_range_equal_reference_heap():
+    rng = np.random.default_rng(2001)
+    d = rng.integers(0, 12, size=5000).astype(np.float32)          # at most 12 distinct values: ties everywhere
+    rid = rng.permutation(5000).astype(np.uint64)
+    for k in (1, 2, 7, 15, 16, 17, 100, 127, 128, 500, 1024):
+        ids, dist = lb.flat_topk(d, rid, k)
+        oi, od = ob.flat_topk(d, rid, k)
+        _check_topk(ids, dist, oi, od, k)
+        assert np.all(np.diff(dist) >= 0)
+    for lo, hi in ((2.0, 7.0), (None, 3.0), (5.0, None), (3.0, 3.0), (11.0, 100.0)):
+        for k in (5, 40):
+            ids, dist = lb.flat_topk(d, rid, k, lower_bound=lo, upper_bound=hi)
+            oi, od = ob.flat_topk(d, rid, k, lower=lo, upper=hi)
+            _check_topk(ids, dist, oi, od, k)
+    x = np.array([np.inf, -np.inf, 1.0, 2.0], np.float32)          # an absent bound is f32::MIN / f32::MAX
+    assert lb.flat_topk(x, None, 4, upper_bound=5.0)[1].tolist() == [1.0, 2.0]
+    assert lb.flat_topk(x, None, 4, lower_bound=-5.0)[1].tolist() == [1.0, 2.0]
+
+
+@pytest.mark.parametrize("kind", ["pq", "flat", "pq4"])
+def test_index_search_boundary_ties_equal_reference_heap(kind):
+    """Duplicate rows -> identical codes / distances -> ties at the k-th place inside a partition: the
+    survivors must be the ones the reference's BinaryHeap keeps (flat/index.rs:116-126)."""
+    rng = np.random.default_rng(2002)
+    distinct, d, K, M = 220, 32, 6, 8
+    base = synth.gaussian_mixture(distinct, d, n_components=K, seed=2002)
+    n = 9000
+    data = base[rng.integers(0, distinct, n)]                       # every vector ~40 times
+    q = base[rng.integers(0, distinct, 40)] + 0.01
+    if kind == "flat":
+        ix = lb.IvfFlatIndex.build(data, "l2", num_partitions=K, max_iters=6)
+    else:
+        ix = lb.IvfPqIndex.build(data, "l2", lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, max_iters=6, pq_max_iters=5,
+                                                               num_bits=4 if kind == "pq4" else 8))
+    parts = ix.export()
+    for k, nprobes in ((1, 1), (5, 2), (10, 3), (15, 6), (16, 2), (60, 3), (300, 6)):
+        ids, dists = ix.search(q, k=k, nprobes=nprobes)
+        if kind == "flat":
+            oi, od, oc = ob.ivfflat_search(parts["centroids"], parts["part_offsets"], parts["vectors"],
+                                           parts["row_ids"], q, k, nprobes, nthreads=NT)
+        else:
+            oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
+                                         parts["row_ids"], q, k, nprobes, nbits=4 if kind == "pq4" else 8, nthreads=NT)
+        assert np.array_equal(ids, oi) and np.array_equal(dists, od), (kind, k, nprobes)
+    # ... and under a prefilter
+    allow = rng.choice(parts["row_ids"], n // 2, replace=False)
+    bm = ix.row_mask(allow, None)
+    ids, dists = ix.search_ex(q, k=10, nprobes=3, allow_bitmap=bm)
+    if kind == "flat":
+        oi, od, oc = ob.ivfflat_search(parts["centroids"], parts["part_offsets"], parts["vectors"], parts["row_ids"], q, 10, 3,
+                                       nthreads=NT, allow=allow)
+    else:
+        oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
+                                     parts["row_ids"], q, 10, 3, nbits=4 if kind == "pq4" else 8, nthreads=NT, allow=allow)
+    assert np.array_equal(ids, oi) and np.array_equal(dists, od)
+
+
+@pytest.mark.parametrize("kind", ["pq", "flat"])
+def test_index_search_range_query_matches_oracle(kind):
+    rng = np.random.default_rng(2003)
+    n, d, K, M = 20000, 64, 16, 8
+    data = synth.gaussian_mixture(n, d, n_components=K, seed=2003)
+    q = synth.gaussian_mixture(30, d, n_components=K, seed=2004)
+    if kind == "pq":
+        ix = lb.IvfPqIndex.build(data, "l2", lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, max_iters=8, pq_max_iters=6))
+    else:
+        ix = lb.IvfFlatIndex.build(data, "l2", num_partitions=K, max_iters=8)
+    parts = ix.export()
+    i0, d0 = ix.search(q, k=50, nprobes=4)
+    lo, hi = float(np.median(d0[:, 5])), float(np.median(d0[:, 30]))
+    allow = rng.choice(parts["row_ids"], n // 2, replace=False)
+    bm = ix.row_mask(allow, None)
+    for lower, upper, a in ((lo, hi, None), (None, hi, None), (lo, None, None), (lo, hi, allow), (hi, lo, None)):
+        for k in (10, 40):
+            ids, dists = ix.search_ex(q, k=k, nprobes=4, lower_bound=lower, upper_bound=upper,
+                                      allow_bitmap=None if a is None else bm)
+            if kind == "pq":
+                oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
+                                             parts["row_ids"], q, k, 4, nthreads=NT, allow=a, lower=lower, upper=upper)
+            else:
+                oi, od, oc = ob.ivfflat_search(parts["centroids"], parts["part_offsets"], parts["vectors"], parts["row_ids"],
+                                               q, k, 4, nthreads=NT, allow=a, lower=lower, upper=upper)
+            assert np.array_equal(ids, oi) and np.array_equal(dists, od), (kind, lower, upper, k)
+            fin = np.isfinite(dists)
+            if lower is not None:
+                assert np.all(dists[fin] >= lower)
+            if upper is not None:
+                assert np.all(dists[fin] < upper)
+    if kind == "pq":  # with refine the plan filters the EXACT distances afterwards (scanner.rs:3342-3377)
+        k, rf = 10, 5
+        ids, dists = ix.search_ex(q, k=k, nprobes=4, refine_factor=rf, vectors=data, lower_bound=lo, upper_bound=hi)
+        oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
+                                     parts["row_ids"], q, k * rf, 4, nthreads=NT, lower=lo, upper=hi)
+        for i in range(len(q)):
+            cand = oi[i, :oc[i]].astype(np.int64)
+            ex = np.array([ob.l2(q[i], data[c]) for c in cand], np.float32)
+            keep = (ex >= np.float32(lo)) & (ex < np.float32(hi))
+            cand, ex = cand[keep], ex[keep]
+            order = np.lexsort((cand, ex))[:k]
+            c = len(order)
+            assert np.array_equal(dists[i, :c], ex[order]) and np.array_equal(ids[i, :c].astype(np.int64), cand[order])
+            assert np.isinf(dists[i, c:]).all()
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_builds_drop_non_finite_rows_like_keep_finite_vectors(metric):
+    """transform.rs:112-159 (KeepFiniteVectors) and builder.rs:436 (is_finite filter on the sample): NaN / Inf
+    rows -- and zero vectors under cosine, which normalise to NaN -- never enter the index or the training."""
+    rng = np.random.default_rng(2005)
+    n, d, K, M = 6000, 32, 8, 8
+    data = synth.gaussian_mixture(n, d, n_components=K, seed=2005)
+    bad = np.sort(rng.choice(n, 40, replace=False))
+    data[bad[:15], 3] = np.nan
+    data[bad[15:30], 7] = np.inf
+    if metric == "cosine":
+        data[bad[30:]] = 0.0
+        dropped = set(bad.tolist())
+    else:
+        data[bad[30:], 0] = -np.inf
+        dropped = set(bad.tolist())
+    q = synth.gaussian_mixture(20, d, n_components=K, seed=2006)
+    # sample_rate large enough that the training sample is the whole dataset (bad rows included)
+    ix = lb.IvfPqIndex.build(data, metric, lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, max_iters=6, pq_max_iters=5,
+                                                            sample_rate=n))
+    info, parts = ix.info(), ix.export()
+    assert info["num_rows"] == n - len(dropped) == int(parts["part_offsets"][-1])
+    assert dropped.isdisjoint(parts["row_ids"].tolist())
+    assert np.isfinite(parts["centroids"]).all() and np.isfinite(parts["codebook"]).all()
+    ids, dists = ix.search(q, k=20, nprobes=K)
+    assert dropped.isdisjoint(ids.ravel().tolist()) and np.isfinite(dists).all()
+    fx = lb.IvfFlatIndex.build(data, metric, num_partitions=K, max_iters=6, sample_rate=n)
+    fparts = fx.export()
+    assert fx.info()["num_rows"] == n - len(dropped) and dropped.isdisjoint(fparts["row_ids"].tolist())
+    assert np.isfinite(fparts["vectors"]).all() and np.isfinite(fparts["centroids"]).all()
+    ids, dists = fx.search(q, k=20, nprobes=K)
+    assert dropped.isdisjoint(ids.ravel().tolist()) and np.isfinite(dists).all()
+    # rows the index holds are exactly the oracle's kept rows with the oracle's partition ids
+    src = ob.normalize_rows(data) if metric == "cosine" else data
+    keep = np.isfinite(src).all(axis=1)
+    assert np.array_equal(np.sort(fparts["row_ids"]), np.flatnonzero(keep).astype(np.uint64))
+    p_ref, _, _ = ob.compute_membership(fparts["centroids"], src[keep], nthreads=NT)
+    order = np.argsort(fparts["row_ids"])
+    sizes = np.diff(fparts["part_offsets"]).astype(np.int64)
+    assert np.array_equal(np.repeat(np.arange(K, dtype=np.uint32), sizes)[order], p_ref)
+
+
+def test_part_ids_out_of_range_are_rejected():
+    rng = np.random.default_rng(2007)
+    d, K, M, n = 16, 4, 4, 50
+    cent = rng.standard_normal((K, d)).astype(np.float32)
+    cb = rng.standard_normal((M, 256, d // M)).astype(np.float32)
+    data = rng.standard_normal((n, d)).astype(np.float32)
+    part = rng.integers(0, K, n).astype(np.uint32)
+    codes = rng.integers(0, 256, (n, M)).astype(np.uint8)
+    bad = part.copy()
+    bad[17] = K
+    with pytest.raises(lb.LanceB200Error, match="out of range") as e:
+        lb.IvfPqIndex.from_parts(cent, cb, bad, codes)
+    assert e.value.status == 1
+    with pytest.raises(lb.LanceB200Error, match="out of range"):
+        lb.IvfFlatIndex.from_parts(cent, bad, data)
+    with pytest.raises(lb.LanceB200Error, match="out of range"):
+        lb.compute_residual(cent, data, bad)
+    with pytest.raises(lb.LanceB200Error, match="out of range"):
+        lb.ProductQuantizer(M, 8, d, cb).quantize(data, centroids=cent, part_ids=bad)
+    lb.IvfPqIndex.from_parts(cent, cb, part, codes)                 # in range: fine
+
+
+def test_kmeans_redos_semantics():
+    """kmeans.rs:643-716: every redo restarts from rng.clone() -> identical runs without a balance bias (PQ);
+    with a bias redos > 1 is not implemented and says so."""
+    data = synth.gaussian_mixture(3000, 16, n_components=8, seed=2008)
+    a = lb.train_kmeans(data, 16, 8, max_iters=10, redos=1, seed=5)
+    b = lb.train_kmeans(data, 16, 8, max_iters=10, redos=3, seed=5)
+    assert np.array_equal(a.centroids, b.centroids) and a.loss == b.loss
+    with pytest.raises(lb.LanceB200Error) as e:
+        lb.train_kmeans(data, 16, 8, max_iters=10, redos=2, balance_factor=1.0, seed=5)
+    assert e.value.status == 2
+    p1 = lb.PQBuildParams(4, 8, max_iters=6, kmeans_redos=1, seed=3).build(data)
+    p2 = lb.PQBuildParams(4, 8, max_iters=6, kmeans_redos=4, seed=3).build(data)
+    assert np.array_equal(p1.codebook, p2.codebook)
+
+
+@pytest.mark.parametrize("d", [3, 8, 32, 100, 768])
+def test_normalize_fsl_bit_exact(d):
+    rng = np.random.default_rng(2009 + d)
+    x = rng.standard_normal((257, d)).astype(np.float32)
+    x[5] = 0.0                                                     # 0 / 0 -> NaN like the reference
+    got, exp = lb.normalize_fsl(x), ob.normalize_rows(x)
+    assert np.array_equal(got.view(np.uint32)[np.isfinite(exp)], exp.view(np.uint32)[np.isfinite(exp)])
+    assert np.isnan(got[5]).all() and np.isnan(exp[5]).all()

@@ -103,6 +103,60 @@ def test_f16_l2_against_reference_c_kernel():
         assert abs(r - o) <= 1e-5 * max(abs(r), 1e-6)
 
 
+@pytest.mark.parametrize("c", [c for c in CASES if c["op"] == "sum_4bit_dist_table"], ids=lambda c: c["name"])
+def test_sum_4bit_dist_table_known_answer(c):
+    # lance-linalg/src/simd/dist_table.rs:179-217: kernel == scalar and dists[1] == 38
+    got = ob.sum_4bit_dist_table(c["n"], c["code_len"], c["codes"], c["dist_table"])
+    assert int(got[c["expect_index"]]) == c["expect"]
+    # independent numpy derivation of the PERM0 layout (dist_table.rs:17-26)
+    perm0 = [0, 8, 1, 9, 2, 10, 3, 11, 4, 12, 5, 13, 6, 14, 7, 15]
+    codes, table = np.asarray(c["codes"], np.uint8), np.asarray(c["dist_table"], np.uint16)
+    exp = np.zeros(c["n"], np.uint16)
+    for sv in range(c["code_len"]):
+        block = codes[sv * 32:(sv + 1) * 32]
+        cur, nxt = table[sv * 32:sv * 32 + 16], table[sv * 32 + 16:sv * 32 + 32]
+        for j in range(16):
+            exp[perm0[j]] += cur[block[j] & 0xF] + nxt[block[j + 16] & 0xF]
+            exp[perm0[j] + 16] += cur[block[j] >> 4] + nxt[block[j + 16] >> 4]
+    assert np.array_equal(got, exp)
+
+
+def test_sum_4bit_dist_table_against_reference_c_kernel():
+    """oracle/_ref's dist_table.o is the reference's own AVX-512 kernel (dist_table.c:8): bit-equal to
+    the restatement on the reference literal and on random codes (integer arithmetic)."""
+    so = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libref_simd.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    flags = open("/proc/cpuinfo").read()
+    if "avx512bw" not in flags:
+        pytest.skip("host CPU has no AVX-512BW")
+    ref = C.CDLL(so)
+    ref.sum_4bit_dist_table_32bytes_batch_avx512.restype = None
+    ref.sum_4bit_dist_table_32bytes_batch_avx512.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(7)
+    cases = [(np.asarray(c["codes"], np.uint8), np.asarray(c["dist_table"], np.uint8), c["code_len"])
+             for c in CASES if c["op"] == "sum_4bit_dist_table"]
+    for code_len in (2, 4, 8, 16):  # the C kernel consumes 64 code bytes (= 2 sub-vector pairs) per step
+        cases.append((rng.integers(0, 256, 32 * code_len, dtype=np.uint8),
+                      rng.integers(0, 256 // (2 * code_len), 32 * code_len, dtype=np.uint8), code_len))
+    for codes, table, code_len in cases:
+        out = np.zeros(32, np.uint16)
+        ref.sum_4bit_dist_table_32bytes_batch_avx512(codes.ctypes.data, codes.size, table.ctypes.data, out.ctypes.data)
+        assert np.array_equal(out, ob.sum_4bit_dist_table(32, code_len, codes, table)), code_len
+
+
+def test_range_query_follows_flat_index_semantics():
+    # flat/index.rs:100-115: lower <= dist < upper in total order, absent bound = f32::MIN / f32::MAX
+    d = np.array([5, 1, 3, 3, 9, np.inf, -np.inf, 2, 3, 7], np.float32)
+    rid = np.arange(10, dtype=np.uint64) + 100
+    ids, dist = ob.flat_topk(d, rid, 10, lower=2.0, upper=7.0)
+    assert sorted(zip(dist.tolist(), ids.tolist())) == [(2.0, 107), (3.0, 102), (3.0, 103), (3.0, 108), (5.0, 100)]
+    ids, dist = ob.flat_topk(d, rid, 10, upper=3.0)            # lower = f32::MIN: -inf is NOT >= f32::MIN
+    assert sorted(dist.tolist()) == [1.0, 2.0]
+    ids, dist = ob.flat_topk(d, rid, 10, lower=7.0)            # upper = f32::MAX: +inf is not < f32::MAX
+    assert sorted(dist.tolist()) == [7.0, 9.0]
+
+
 def test_argmin_semantics():
     # kernels.rs:79-89: first minimum wins; NaN / inf rows -> None (kmeans.rs:1447-1486)
     cent = np.array([[0, 0], [1, 1], [0, 0]], np.float32)
