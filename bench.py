@@ -280,8 +280,8 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-        from lance_b200 import parallel
-        parallel.init_comm(dist)  # NCCL all-reduce of centroid sums inside the k-means loops
+        from tools import dist_util
+        dist_util.init_comm(dist)  # hands the NCCL unique id to lb2_comm_init on every rank
 
     def barrier():
         if world > 1:

@@ -300,12 +300,24 @@ lb2_status lb2_index_export_flat(const lb2_index* index, void* centroids_out,
                                  uint64_t* part_offsets_out, void* vectors_out,
                                  uint64_t* row_ids_out);
 
-/* ---- multi-GPU (one process per GPU; NCCL all-reduce of centroid sums during training) ------- */
+/* ---- multi-GPU (one process per GPU) -----------------------------------------------------------
+ * With a communicator every training / build call takes THIS RANK'S ROW SHARD: the k-means loops
+ * (flat and hierarchical) exchange their packed per-cluster partial results once per Lloyd iteration
+ * (one collective, reduced in rank order on every rank -> bit-identical models on all ranks), the
+ * transform and the index are local to the shard. */
 /* unique_id is the 128-byte ncclUniqueId produced by rank 0 (lb2_comm_unique_id) and broadcast by
  * the host runtime (torch.distributed / MPI / the Rust side). */
 lb2_status lb2_comm_unique_id(void* unique_id_128);
 lb2_status lb2_comm_init(const void* unique_id_128, int rank, int nranks);
 lb2_status lb2_comm_destroy(void);
+lb2_status lb2_comm_info(int* rank, int* nranks); /* (0, 1) without a communicator */
+/* Search of a ROW-SHARDED index (every rank built / loaded its own rows, row ids global): the local
+ * lb2_index_search_ex result of every rank is exchanged in one collective and merged by (_distance,
+ * _rowid) -- the reference's final SortExec.fetch(k) (rust/lance/src/dataset/scanner.rs:3450-3466) --
+ * so every rank returns the global top-k.  All ranks must call it with the same queries and params. */
+lb2_status lb2_index_search_sharded(lb2_index* index, const void* queries, uint64_t nq,
+                                    const lb2_search_params* params, uint64_t* row_ids_out, float* dists_out,
+                                    uint32_t* counts_out);
 
 #ifdef __cplusplus
 }

@@ -551,6 +551,26 @@ class IvfPqIndex:
         check(lib().lb2_index_search_ex(self._h, qp, C.c_uint64(nq), C.byref(sp), ip, dp, None))
         return ids, dists
 
+    def search_sharded(self, queries, k=10, nprobes=1, out=None):
+        """lb2_index_search_sharded: this index holds ONE RANK'S rows (global row ids); every rank calls with
+        the same queries and gets the global top-k (per-rank lists exchanged + merged in the library)."""
+        from ._lib import SearchParams
+        dt = getattr(self, "_dt", F32)
+        npdt = {F32: np.float32, F16: np.float16, U8: np.uint8, BF16: np.uint16}[dt]
+        if not isinstance(queries, (DeviceArray, PinnedArray)):
+            queries = np.ascontiguousarray(queries, dtype=npdt)
+        nq = queries.shape[0]
+        if out is None:
+            ids, dists = np.empty((nq, k), np.uint64), np.empty((nq, k), np.float32)
+        else:
+            ids, dists = out
+        qp, _k1 = as_ptr(queries)
+        ip, _k2 = as_ptr(ids)
+        dp, _k3 = as_ptr(dists)
+        sp = SearchParams(k, nprobes, 0, None, 0, None, 0, 0, 0.0, 0.0)
+        check(lib().lb2_index_search_sharded(self._h, qp, C.c_uint64(nq), C.byref(sp), ip, dp, None))
+        return ids, dists
+
     def close(self):
         if self._h:
             lib().lb2_index_destroy(self._h)

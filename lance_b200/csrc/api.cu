@@ -1030,6 +1030,39 @@ lb2_status lb2_index_search_ex(lb2_index* index, const void* queries, uint64_t n
   LB2_API_END
 }
 
+lb2_status lb2_index_search_sharded(lb2_index* index, const void* queries, uint64_t nq,
+                                    const lb2_search_params* sp, uint64_t* row_ids_out, float* dists_out,
+                                    uint32_t* counts_out) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(sp && index, "null argument");
+  LB2_REQUIRE(sp->refine_factor == 0 || sp->refine_vectors, "refine_factor > 0 needs refine_vectors");
+  const uint32_t k = sp->k;
+  DevBuf<uint64_t> li((size_t)std::max<uint64_t>(1, nq * k));
+  DevBuf<float> ld((size_t)std::max<uint64_t>(1, nq * k));
+  DevBuf<uint32_t> lc(std::max<uint64_t>(1, nq));
+  index_search_impl(index, queries, nq, k, sp->nprobes, sp->refine_factor, sp->refine_vectors, sp->num_vectors,
+                    sp->allow_bitmap, li.p, ld.p, lc.p, sp->has_lower_bound != 0, sp->lower_bound,
+                    sp->has_upper_bound != 0, sp->upper_bound);
+  OutArg<uint64_t> oi(row_ids_out, (size_t)nq * k);
+  OutArg<float> od(dists_out, (size_t)nq * k);
+  OutArg<uint32_t> oc(counts_out, nq);
+  DevBuf<uint32_t> ctmp;
+  uint32_t* cp = oc.get();
+  if (!cp) { ctmp.alloc(std::max<uint64_t>(1, nq)); cp = ctmp.p; }
+  if (nq) merge_sharded_topk(li.p, ld.p, lc.p, nq, (int)k, oi.get(), od.get(), cp);
+  oi.commit(); od.commit(); oc.commit();
+  sync_stream();
+  LB2_API_END
+}
+
+lb2_status lb2_comm_info(int* rank, int* nranks) {
+  LB2_API_BEGIN
+  Comm* c = current_comm();
+  if (rank) *rank = c ? c->rank : 0;
+  if (nranks) *nranks = c ? c->nranks : 1;
+  LB2_API_END
+}
+
 lb2_status lb2_index_row_mask(const lb2_index* index, const uint64_t* allow_ids, uint64_t n_allow,
                               int has_allow, const uint64_t* block_ids, uint64_t n_block, int has_block,
                               uint64_t* bitmap_out) {

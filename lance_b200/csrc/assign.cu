@@ -519,7 +519,20 @@ void assign_f32_ex(const float* x, uint64_t n, int d, const float* cent, int K, 
       d2d(biasp.get(), bias, K);
       bp = biasp.get();
     }
-    tc_assign_f32(x, n, d, cent, K, bp, part, dist, valid, active, ws);
+    // large inputs in chunks of <= 2^20 rows (<= 4 GB of vectors): bounds the per-call scratch (row norms,
+    // verdicts, the 3x-wide refinement rows) without changing any output
+    const uint64_t chunk = std::max<uint64_t>(1ull << 16, std::min<uint64_t>(1ull << 20, (1ull << 30) / (uint64_t)d));
+    if (n <= chunk + chunk / 2) {
+      tc_assign_f32(x, n, d, cent, K, bp, part, dist, valid, active, ws);
+      return;
+    }
+    TcWorkspace local;
+    if (!ws) ws = &local;
+    for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
+      const uint64_t rows = std::min(chunk, n - r0);
+      tc_assign_f32(x + r0 * d, rows, d, cent, K, bp, part + r0, dist ? dist + r0 : nullptr,
+                    valid ? valid + r0 : nullptr, active, ws);
+    }
     return;
   }
   if (metric == METRIC_DOT)

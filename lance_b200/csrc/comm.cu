@@ -24,6 +24,7 @@ struct Api {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 Api& api() {
@@ -41,9 +42,10 @@ Api& api() {
     a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
     a.AllReduce = (decltype(a.AllReduce))dlsym(a.lib, "ncclAllReduce");
     a.Broadcast = (decltype(a.Broadcast))dlsym(a.lib, "ncclBroadcast");
+    a.AllGather = (decltype(a.AllGather))dlsym(a.lib, "ncclAllGather");
     a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
   });
-  if (!a.lib || !a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.Broadcast)
+  if (!a.lib || !a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.Broadcast || !a.AllGather)
     fail(LB2_NCCL_ERROR, "NCCL (libnccl.so.2) could not be loaded: %s", dlerror() ? dlerror() : "missing symbols");
   return a;
 }
@@ -66,6 +68,16 @@ static void allreduce(void* buf, size_t count, int dtype, RedOp op) {
 void comm_allreduce_f32(float* buf, size_t count, RedOp op) { allreduce(buf, count, ncclFloat32, op); }
 void comm_allreduce_f64(double* buf, size_t count, RedOp op) { allreduce(buf, count, ncclFloat64, op); }
 void comm_allreduce_u32(uint32_t* buf, size_t count, RedOp op) { allreduce(buf, count, ncclUint32, op); }
+// out[r * bytes ..] = rank r's `in` (every rank ends with the same buffer, in rank order)
+void comm_allgather_bytes(const void* in, void* out, size_t bytes) {
+  Comm* c = g_comm;
+  if (!c || c->nranks <= 1 || bytes == 0) {
+    if (bytes && in != out) LB2_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, ctx().stream));
+    return;
+  }
+  nccl_check(api().AllGather(in, out, bytes, ncclUint8, (ncclComm_t)c->handle, ctx().stream), "ncclAllGather");
+  ctx().launches++;
+}
 void comm_broadcast_bytes(void* buf, size_t bytes, int root) {
   Comm* c = g_comm;
   if (!c || c->nranks <= 1 || bytes == 0) return;

@@ -16,4 +16,6 @@ void comm_allreduce_f32(float* buf, size_t count, RedOp op);
 void comm_allreduce_f64(double* buf, size_t count, RedOp op);
 void comm_allreduce_u32(uint32_t* buf, size_t count, RedOp op);
 void comm_broadcast_bytes(void* buf, size_t bytes, int root);
+// out[r * bytes ..] = rank r's `in`: one collective whose result every rank reduces in the same (rank) order
+void comm_allgather_bytes(const void* in, void* out, size_t bytes);
 }  // namespace lb2

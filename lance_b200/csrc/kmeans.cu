@@ -558,22 +558,80 @@ update_stats_kernel(unsigned update_blocks, const float* __restrict__ x, int ldx
   }
 }
 
-// multi-GPU: the per-rank partial results are all-reduced between these two small kernels
-__global__ void encode_last_row_kernel(uint32_t* __restrict__ last_row, size_t BK, uint32_t row_offset) {
-  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < BK) last_row[g] = last_row[g] == 0xffffffffu ? 0u : last_row[g] + row_offset + 1u;  // MAX-reducible
+// ---- multi-GPU: ONE exchange per Lloyd iteration ------------------------------------------
+// Every rank packs its partial results of the iteration into one blob
+//     [ sums f32 BK*ds | counts u32 BK | radius f32 BK | last member row u32 BK (global, +1; 0 = none) | loss f64 BK ]
+// (update_stats_kernel writes the sums straight into it), the blobs are all-gathered in ONE collective, and
+// every rank reduces the gathered blobs in RANK ORDER -- so all ranks hold bit-identical models whatever
+// algorithm the transport uses, and the whole iteration (collective included) replays from a CUDA graph.
+struct ExchangeLayout {
+  size_t off_counts, off_radius, off_last, off_loss, bytes;
+};
+static ExchangeLayout exchange_layout(size_t BK, int ds) {
+  ExchangeLayout L;
+  L.off_counts = (BK * ds * sizeof(float) + 15) / 16 * 16;
+  L.off_radius = L.off_counts + BK * 4;
+  L.off_last = L.off_radius + BK * 4;
+  L.off_loss = (L.off_last + BK * 4 + 7) / 8 * 8;
+  L.bytes = (L.off_loss + BK * 8 + 15) / 16 * 16;
+  return L;
 }
-__global__ void finish_reduce_kernel(const float* __restrict__ sums, float* __restrict__ centroids,
-                                     const uint32_t* __restrict__ counts,
-                                     uint32_t* __restrict__ last_row, size_t BK, int ds,
-                                     const uint8_t* __restrict__ active, int K) {
+__global__ void pack_partials_kernel(uint8_t* __restrict__ blob, ExchangeLayout L, size_t BK,
+                                     const uint32_t* __restrict__ counts, const float* __restrict__ radius,
+                                     const uint32_t* __restrict__ last_row, const double* __restrict__ losses,
+                                     uint32_t row_offset) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= BK) return;
+  reinterpret_cast<uint32_t*>(blob + L.off_counts)[g] = counts[g];
+  reinterpret_cast<float*>(blob + L.off_radius)[g] = radius[g];
+  reinterpret_cast<uint32_t*>(blob + L.off_last)[g] = last_row[g] == 0xffffffffu ? 0u : last_row[g] + row_offset + 1u;
+  reinterpret_cast<double*>(blob + L.off_loss)[g] = losses[g];
+}
+__global__ void reduce_partials_kernel(const uint8_t* __restrict__ gathered, int nranks, ExchangeLayout L, size_t BK,
+                                       int ds, int K, float* __restrict__ centroids, uint32_t* __restrict__ counts,
+                                       float* __restrict__ radius, uint32_t* __restrict__ last_row,
+                                       double* __restrict__ losses, const uint8_t* __restrict__ active) {
   const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= BK * ds) return;
   const size_t ck = g / ds;
   if (active && !active[ck / K]) return;
-  const uint32_t cnt = counts[ck];
-  centroids[g] = cnt > 0 ? __fmul_rn(sums[g], __fdiv_rn(1.0f, (float)cnt)) : sums[g];  // kmeans.rs:414-416
-  if (g % ds == 0) last_row[ck] = last_row[ck] == 0u ? 0xffffffffu : last_row[ck] - 1u;
+  float sum = 0.0f;
+  uint32_t cnt = 0;
+  for (int r = 0; r < nranks; ++r) {
+    const uint8_t* blob = gathered + (size_t)r * L.bytes;
+    sum = __fadd_rn(sum, reinterpret_cast<const float*>(blob)[g]);
+    cnt += reinterpret_cast<const uint32_t*>(blob + L.off_counts)[ck];
+  }
+  centroids[g] = cnt > 0 ? __fmul_rn(sum, __fdiv_rn(1.0f, (float)cnt)) : sum;  // kmeans.rs:414-416
+  if (g % ds == 0) {
+    float rad = 0.0f;
+    uint32_t last = 0;
+    double loss = 0.0;
+    for (int r = 0; r < nranks; ++r) {
+      const uint8_t* blob = gathered + (size_t)r * L.bytes;
+      rad = fmaxf(rad, reinterpret_cast<const float*>(blob + L.off_radius)[ck]);
+      last = max(last, reinterpret_cast<const uint32_t*>(blob + L.off_last)[ck]);
+      loss += reinterpret_cast<const double*>(blob + L.off_loss)[ck];
+    }
+    counts[ck] = cnt;
+    radius[ck] = rad;
+    last_row[ck] = last == 0u ? 0xffffffffu : last - 1u;
+    losses[ck] = loss;
+  }
+}
+
+// sharded initialisation: the k picked rows are GLOBAL row numbers (rank-major order); every rank copies
+// the rows it owns into a zeroed buffer and the buffers are summed (each row has exactly one owner, x + 0
+// is exact) -- the picks, and with them the model, do not depend on how the sample is sharded
+__global__ void gather_init_owned_kernel(const float* __restrict__ x, int ldx, int ds, int K, int B,
+                                         const uint32_t* __restrict__ rows, uint32_t row_offset, uint32_t n_local,
+                                         float* __restrict__ out) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (size_t)B * K * ds) return;
+  const int b = g / ((size_t)K * ds), k = (g / ds) % K, t = g % ds;
+  const uint32_t gr = rows[(size_t)b * K + k];
+  const bool mine = gr >= row_offset && gr - row_offset < n_local;
+  out[g] = mine ? x[(size_t)(gr - row_offset) * ldx + (size_t)b * ds + t] : 0.0f;
 }
 
 __global__ void split_kernel(float* __restrict__ c, int i, int j, int ds) {
@@ -856,19 +914,20 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
     for (int b = 0; b < B; ++b) h_states[b].rng = seed + b;
   } else {
     // partial Fisher-Yates over the virtual array idx[i] = i, kept sparse (only touched slots are
-    // stored): identical picks to the dense version, O(K) instead of O(n) host work per problem
+    // stored): identical picks to the dense version, O(K) instead of O(n) host work per problem.
+    // Sharded: the picks range over the GLOBAL rows (rank-major), see gather_init_owned_kernel.
     std::vector<uint32_t> rows(BK);
     std::unordered_map<uint64_t, uint32_t> moved;
+    const uint64_t n_pick = dist ? n_global : n;
     for (int b = 0; b < B; ++b) {
       SplitMix64 rng(seed + b);
       moved.clear();
-      LB2_REQUIRE(n >= (uint64_t)K, "KMeans: the seeding rank needs at least k rows");
       auto at = [&](uint64_t i) {
         auto it = moved.find(i);
         return it == moved.end() ? (uint32_t)i : it->second;
       };
       for (int i = 0; i < K; ++i) {
-        const uint64_t j = i + rng.next() % (n - i);
+        const uint64_t j = i + rng.next() % (n_pick - i);
         const uint32_t vi = at(i), vj = at(j);
         moved[i] = vj;
         moved[j] = vi;
@@ -878,10 +937,14 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
     }
     DevBuf<uint32_t> rows_d(BK);
     h2d(rows_d.p, rows.data(), BK);
-    if (!dist || cm->rank == 0)  // multi-GPU: rank 0 seeds from its shard and broadcasts
+    if (!dist) {
       LB2_LAUNCH("kmeans_init", gather_init_kernel, cdiv(BK * ds, 256), 256, 0, x, ldx, ds, K, B,
                  rows_d.p, centroids);
-    if (dist) comm_broadcast_bytes(centroids, BK * ds * sizeof(float), 0);
+    } else {
+      LB2_LAUNCH("kmeans_init", gather_init_owned_kernel, cdiv(BK * ds, 256), 256, 0, x, ldx, ds, K, B,
+                 rows_d.p, (uint32_t)row_offset, (uint32_t)n, centroids);
+      comm_allreduce_f32(centroids, BK * ds, RedOp::Sum);
+    }
     sync_stream();  // rows (host vector) must outlive the copy
   }
 
@@ -900,8 +963,14 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
     bias.alloc(Kp);
     bias.zero();  // iteration 1: cluster sizes are all zero -> bias 0
   }
-  DevBuf<float> sums;  // multi-GPU: per-rank partial centroid sums (all-reduced every iteration)
-  if (dist) sums.alloc(BK * ds);
+  // multi-GPU: this rank's packed partial results and the gathered blobs of all ranks (see "ONE exchange")
+  const ExchangeLayout xl = exchange_layout(BK, ds);
+  DevBuf<uint8_t> blob, gathered;
+  if (dist) {
+    blob.alloc(xl.bytes);
+    gathered.alloc(xl.bytes * (size_t)cm->nranks);
+  }
+  float* sums_p = dist ? reinterpret_cast<float*>(blob.p) : nullptr;
   DevBuf<uint8_t> hints((size_t)2 * B);  // order-independent-sum hints (update, loss) per problem
   LB2_CUDA(cudaMemsetAsync(hints.p, 1, (size_t)2 * B, ctx().stream));
   MemberSort ms;
@@ -941,25 +1010,21 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
     static const bool split_us = getenv("LB2_SPLIT_UPDATE_STATS") && *getenv("LB2_SPLIT_UPDATE_STATS");
     if (split_us) {  // diagnostics: time the two halves of the fused launch separately
       LB2_LAUNCH("kmeans_update_only", update_stats_kernel, ub, 128, 0, ub, x, ldx, ds, K, B, n,
-                 ms.members.p, ms.offsets.p, dist ? sums.p : centroids, dists.p, losses.p, radius.p,
+                 ms.members.p, ms.offsets.p, dist ? sums_p : centroids, dists.p, losses.p, radius.p,
                  last_row.p, active_d.p, dist ? 0 : 1, warp_update, hints.p);
       LB2_LAUNCH("kmeans_stats_only", update_stats_kernel, sb, 128, 0, 0u, x, ldx, ds, K, B, n,
-                 ms.members.p, ms.offsets.p, dist ? sums.p : centroids, dists.p, losses.p, radius.p,
+                 ms.members.p, ms.offsets.p, dist ? sums_p : centroids, dists.p, losses.p, radius.p,
                  last_row.p, active_d.p, dist ? 0 : 1, warp_update, hints.p);
     } else
     LB2_LAUNCH("kmeans_update_stats", update_stats_kernel, ub + sb, 128, 0, ub, x, ldx, ds, K, B, n,
-               ms.members.p, ms.offsets.p, dist ? sums.p : centroids, dists.p, losses.p, radius.p,
+               ms.members.p, ms.offsets.p, dist ? sums_p : centroids, dists.p, losses.p, radius.p,
                last_row.p, active_d.p, dist ? 0 : 1, warp_update, hints.p);
     if (dist) {  // one exchange step per iteration over NVLink
-      LB2_LAUNCH("kmeans_encode_last", encode_last_row_kernel, cdiv(BK, 256), 256, 0, last_row.p, BK,
-                 (uint32_t)row_offset);
-      comm_allreduce_f32(sums.p, BK * ds, RedOp::Sum);
-      comm_allreduce_u32(ms.counts.p, BK, RedOp::Sum);
-      comm_allreduce_f64(losses.p, BK, RedOp::Sum);
-      comm_allreduce_f32(radius.p, BK, RedOp::Max);
-      comm_allreduce_u32(last_row.p, BK, RedOp::Max);
-      LB2_LAUNCH("kmeans_finish_reduce", finish_reduce_kernel, cdiv(BK * ds, 256), 256, 0, sums.p,
-                 centroids, ms.counts.p, last_row.p, BK, ds, active_d.p, K);
+      LB2_LAUNCH("kmeans_pack_partials", pack_partials_kernel, cdiv(BK, 256), 256, 0, blob.p, xl, BK, ms.counts.p,
+                 radius.p, last_row.p, losses.p, (uint32_t)row_offset);
+      comm_allgather_bytes(blob.p, gathered.p, xl.bytes);
+      LB2_LAUNCH("kmeans_reduce_partials", reduce_partials_kernel, cdiv(BK * ds, 256), 256, 0, gathered.p, cm->nranks,
+                 xl, BK, ds, K, centroids, ms.counts.p, radius.p, last_row.p, losses.p, active_d.p);
     }
     LB2_LAUNCH("kmeans_epilogue", epilogue_kernel, B, 256, 0, K, ds, n_global, balance_factor_param,
                tolerance, ms.counts.p, losses.p, radius.p, last_row.p, cluster_sizes.p,
@@ -969,7 +1034,8 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
   // iteration is then captured ONCE into a CUDA graph and replayed, so that the loop is not bound
   // by ~18 host launches per iteration.  (Event profiling and LB2_TC_STATS need eager launches.)
   const bool stats_env = getenv("LB2_TC_STATS") && *getenv("LB2_TC_STATS");
-  const bool use_graph = max_iters > 1 && !ctx().profiling && !stats_env && !dist &&
+  // (NCCL collectives are capturable; the sharded iteration is replayed from the graph like the local one)
+  const bool use_graph = max_iters > 1 && !ctx().profiling && !stats_env &&
                          !(getenv("LB2_NO_GRAPH") && *getenv("LB2_NO_GRAPH"));
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
@@ -1031,7 +1097,8 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
 namespace {
 struct HCluster {
   uint32_t id;
-  uint32_t off, len;  // segment of the device index array
+  uint32_t off, loc;  // this rank's segment of the device index array (loc rows)
+  uint64_t len;       // rows of the cluster over ALL ranks: what the reference's heap orders by
   bool finalized;
 };
 inline bool hc_le(const HCluster& a, const HCluster& b) {  // a <= b in the reference's Ord
@@ -1095,16 +1162,44 @@ __global__ void iota_kernel(uint32_t* p, uint32_t n) {
 }
 }  // namespace
 
+// Sharded: every rank holds a row shard of the sample and runs the SAME split loop -- the heap is
+// ordered by the clusters' global sizes (one small all-reduce of <= 16 counters per split), each Lloyd run
+// exchanges its partial sums once per iteration (lloyd_train), the row index lists stay local to the rank.
 void hierarchical_train(const float* x, uint64_t n, int d, int K, int metric, float balance_factor,
                         int max_iters, double tolerance, int hk, uint64_t seed, float* centroids_out) {
-  LB2_REQUIRE(n >= (uint64_t)K && n < 0xffffffffull, "KMeans: can not train %d centroids with %llu vectors", K,
-              (unsigned long long)n);
-  if (current_comm() && current_comm()->nranks > 1)
-    fail(LB2_UNSUPPORTED, "hierarchical k-means is not sharded yet: use k <= 256 per call on multiple GPUs");
-  const int k0 = (int)std::min<uint64_t>(std::min(hk, K), n);
-  DevBuf<float> top((size_t)k0 * d), sub((size_t)n * d), subc((size_t)hk * d), store((size_t)2 * K * d + (size_t)k0 * d);
-  DevBuf<uint32_t> ids(n), idx(n), tmp(n), ident(n);
-  DevBuf<uint8_t> valid(n);
+  Comm* cm = current_comm();
+  const bool dist = cm && cm->nranks > 1;
+  LB2_REQUIRE(n < 0xffffffffull, "KMeans: too many vectors");
+  const int kmax = std::max(std::min(hk, K), hk);
+  DevBuf<uint32_t> cnt_d(kmax);
+  // local per-cluster counts -> global counts (identity on one GPU)
+  auto global_counts = [&](const std::vector<uint32_t>& local, int k, std::vector<uint64_t>& out) {
+    out.assign(k, 0);
+    if (!dist) {
+      for (int i = 0; i < k; ++i) out[i] = local[i];
+      return;
+    }
+    std::vector<uint32_t> tmp(local.begin(), local.begin() + k);
+    h2d(cnt_d.p, tmp.data(), k);
+    comm_allreduce_u32(cnt_d.p, k, RedOp::Sum);
+    d2h(tmp.data(), cnt_d.p, k);
+    sync_stream();
+    for (int i = 0; i < k; ++i) out[i] = tmp[i];
+  };
+  uint64_t n_global = n;
+  {
+    std::vector<uint32_t> one(1, (uint32_t)n);
+    std::vector<uint64_t> g;
+    global_counts(one, 1, g);
+    n_global = g[0];
+  }
+  LB2_REQUIRE(n_global >= (uint64_t)K, "KMeans: can not train %d centroids with %llu vectors", K,
+              (unsigned long long)n_global);
+  const int k0 = (int)std::min<uint64_t>(std::min(hk, K), n_global);
+  const uint64_t n1 = std::max<uint64_t>(n, 1);
+  DevBuf<float> top((size_t)k0 * d), sub(n1 * d), subc((size_t)hk * d), store((size_t)2 * K * d + (size_t)k0 * d);
+  DevBuf<uint32_t> ids(n1), idx(n1), tmp(n1), ident(n1);
+  DevBuf<uint8_t> valid(n1);
   uint64_t call = 0;
   lloyd_train(x, n, d, 1, d, k0, metric, balance_factor, max_iters, tolerance, seed + call++, nullptr, top.p,
               nullptr, nullptr);
@@ -1112,18 +1207,22 @@ void hierarchical_train(const float* x, uint64_t n, int d, int K, int metric, fl
   MemberSort ms;
   ms.run(ids.p, valid.p, n, k0, 1, nullptr);
   std::vector<uint32_t> counts(std::max(k0, hk)), offs(std::max(k0, hk) + 1);
+  std::vector<uint64_t> gcounts;
   d2h(counts.data(), ms.counts.p, k0);
   d2h(offs.data(), ms.offsets.p, k0 + 1);
-  d2d(idx.p, ms.members.p, n);
-  LB2_LAUNCH("iota", iota_kernel, cdiv(n, 256), 256, 0, ident.p, (uint32_t)n);
+  if (n) {
+    d2d(idx.p, ms.members.p, n);
+    LB2_LAUNCH("iota", iota_kernel, cdiv(n, 256), 256, 0, ident.p, (uint32_t)n);
+  }
   sync_stream();
+  global_counts(counts, k0, gcounts);
   RustHeap heap;
   uint32_t next_id = 0;
   const size_t store_slots = (size_t)2 * K + k0;
   for (int i = 0; i < k0; ++i) {
-    if (counts[i] == 0) continue;
+    if (gcounts[i] == 0) continue;
     d2d(store.p + (size_t)next_id * d, top.p + (size_t)i * d, d);
-    heap.push(HCluster{next_id++, offs[i], counts[i], false});
+    heap.push(HCluster{next_id++, offs[i], counts[i], gcounts[i], false});
   }
   while ((int)heap.data.size() < K) {
     LB2_REQUIRE(!heap.data.empty(), "No cluster can be further split");
@@ -1134,21 +1233,23 @@ void hierarchical_train(const float* x, uint64_t n, int d, int K, int metric, fl
     }
     const int remaining = K - (int)heap.data.size();
     int ck;
-    if ((int)big.len <= hk)
+    if (big.len <= (uint64_t)hk)
       ck = std::min(std::min(2, remaining), (int)big.len);
     else
-      ck = std::max(2, std::min(std::min((int)(big.len / hk), remaining), hk));
-    LB2_LAUNCH("gather_rows", gather_rows_u32_kernel, cdiv((uint64_t)big.len * d, 256), 256, 0, x,
-               idx.p + big.off, (uint64_t)big.len, d, sub.p);
-    lloyd_train(sub.p, big.len, d, 1, d, ck, metric, balance_factor, max_iters, tolerance, seed + call++,
+      ck = std::max(2, std::min(std::min((int)std::min<uint64_t>(big.len / hk, 1u << 30), remaining), hk));
+    if (big.loc)
+      LB2_LAUNCH("gather_rows", gather_rows_u32_kernel, cdiv((uint64_t)big.loc * d, 256), 256, 0, x,
+                 idx.p + big.off, (uint64_t)big.loc, d, sub.p);
+    lloyd_train(sub.p, big.loc, d, 1, d, ck, metric, balance_factor, max_iters, tolerance, seed + call++,
                 nullptr, subc.p, nullptr, nullptr);
-    assign_f32(sub.p, big.len, d, subc.p, ck, metric, nullptr, ids.p, nullptr, valid.p, nullptr);
-    ms.run(ids.p, valid.p, big.len, ck, 1, nullptr);
+    assign_f32(sub.p, big.loc, d, subc.p, ck, metric, nullptr, ids.p, nullptr, valid.p, nullptr);
+    ms.run(ids.p, valid.p, big.loc, ck, 1, nullptr);
     d2h(counts.data(), ms.counts.p, ck);
     d2h(offs.data(), ms.offsets.p, ck + 1);
     sync_stream();
+    global_counts(counts, ck, gcounts);
     int nonzero = 0;
-    for (int i = 0; i < ck; ++i) nonzero += counts[i] > 0;
+    for (int i = 0; i < ck; ++i) nonzero += gcounts[i] > 0;
     if (nonzero <= 1) {  // ineffective split: finalise the original cluster (kmeans.rs:957-962)
       big.finalized = true;
       heap.push(big);
@@ -1157,14 +1258,16 @@ void hierarchical_train(const float* x, uint64_t n, int d, int K, int metric, fl
     // children's row lists = parent's list re-ordered by (child, position): stable, rows dropped as
     // None by the membership step leave the lists
     const uint32_t kept = offs[ck];
-    LB2_LAUNCH("compose_index", compose_index_kernel, cdiv(kept, 256), 256, 0, idx.p + big.off,
-               ms.members.p, kept, tmp.p);
-    d2d(idx.p + big.off, tmp.p, kept);
+    if (kept) {
+      LB2_LAUNCH("compose_index", compose_index_kernel, cdiv(kept, 256), 256, 0, idx.p + big.off,
+                 ms.members.p, kept, tmp.p);
+      d2d(idx.p + big.off, tmp.p, kept);
+    }
     for (int i = 0; i < ck; ++i) {
-      if (counts[i] == 0) continue;
+      if (gcounts[i] == 0) continue;
       LB2_REQUIRE(next_id < store_slots, "hierarchical k-means: centroid store exhausted");
       d2d(store.p + (size_t)next_id * d, subc.p + (size_t)i * d, d);
-      heap.push(HCluster{next_id++, big.off + offs[i], counts[i], false});
+      heap.push(HCluster{next_id++, big.off + offs[i], counts[i], gcounts[i], false});
     }
   }
   if ((int)heap.data.size() != K)

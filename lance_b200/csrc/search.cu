@@ -13,6 +13,7 @@
 // warp-level sorting networks (k <= 16) or a block radix select produce the k smallest (distance,
 // position) pairs.
 #include "assign.cuh"
+#include "comm.cuh"
 #include "common.cuh"
 #include "exact.cuh"
 #include "search.cuh"
@@ -953,10 +954,13 @@ ivfflat_scan_kernel(const float* __restrict__ queries, int d, const uint32_t* __
   if (tid == 0) cand_cnt[slot] = len;
 }
 
-// global merge per query: ascending (distance, row id), first k
+// global merge per query: ascending (distance, row id), first k.  Candidate e of list pi of query qi sits
+// at cand[pi * stride_p + qi * stride_q + e] (per-partition lists of one GPU: stride_p = k, stride_q = np * k;
+// per-rank results gathered from a sharded index: stride_p = the rank stride, stride_q = k).
 __global__ void __launch_bounds__(128)
 merge_kernel(const float* __restrict__ cand_d, const uint64_t* __restrict__ cand_id,
-             const uint32_t* __restrict__ cand_cnt, int np, int k, uint64_t* __restrict__ out_id,
+             const uint32_t* __restrict__ cand_cnt, int np, int k, size_t stride_p_d, size_t stride_p_id,
+             size_t stride_q, size_t cnt_stride_p, size_t cnt_stride_q, uint64_t* __restrict__ out_id,
              float* __restrict__ out_d, uint32_t* __restrict__ out_cnt) {
   __shared__ int32_t s_key[4];
   __shared__ uint64_t s_tie[4];
@@ -976,12 +980,11 @@ merge_kernel(const float* __restrict__ cand_d, const uint64_t* __restrict__ cand
     const uint64_t pid = first ? 0 : prev_id;
     for (int c = tid; c < total; c += 128) {
       const int pi = c / k, e = c % k;
-      if ((uint32_t)e >= cand_cnt[qi * np + pi]) continue;
-      const size_t g = (qi * np + pi) * k + e;
-      const int32_t key = total_order_key(cand_d[g]);
-      const uint64_t id = cand_id[g];
+      if ((uint32_t)e >= cand_cnt[pi * cnt_stride_p + qi * cnt_stride_q]) continue;
+      const int32_t key = total_order_key(cand_d[pi * stride_p_d + qi * stride_q + e]);
+      const uint64_t id = cand_id[pi * stride_p_id + qi * stride_q + e];
       if (!first && !ki_less(pk, pid, key, id)) continue;
-      if (bslot < 0 || ki_less(key, id, bk, bi)) { bk = key; bi = id; bslot = (int)(g - qi * np * k); }
+      if (bslot < 0 || ki_less(key, id, bk, bi)) { bk = key; bi = id; bslot = c; }
     }
     const int w = block_argmin<128>(bslot >= 0, bk, bi, s_key, s_tie, s_tid);
     if (w < 0) break;
@@ -989,7 +992,7 @@ merge_kernel(const float* __restrict__ cand_d, const uint64_t* __restrict__ cand
       prev_key = bk;
       prev_id = bi;
       out_id[qi * k + r] = bi;
-      out_d[qi * k + r] = cand_d[qi * np * k + bslot];
+      out_d[qi * k + r] = cand_d[(bslot / k) * stride_p_d + qi * stride_q + (bslot % k)];
     }
     __syncthreads();
     first = false;
@@ -1182,7 +1185,29 @@ void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const fl
       scan_launch<METRIC_L2>(nbits, g, smem, a, rlist.p, rcount.p);
   }
   LB2_LAUNCH("merge_topk", merge_kernel, (unsigned)nq, 128, 0, cand_d.p, cand_id.p, cand_cnt.p, np,
-             k, out_ids, out_dists, out_counts);
+             k, (size_t)k, (size_t)k, (size_t)np * k, (size_t)1, (size_t)np, out_ids, out_dists, out_counts);
+}
+
+// Row-sharded index (SURVEY 8e search (ii)): every rank has searched its own shard; the per-rank top-k lists
+// are exchanged in ONE collective and merged on every rank by (_distance, _rowid), the order of the
+// reference's final SortExec (rust/lance/src/dataset/scanner.rs:3450-3466).  ids / dists / counts: this
+// rank's [nq][k] / [nq] results on the device; outputs likewise.
+void merge_sharded_topk(const uint64_t* ids, const float* dists, const uint32_t* counts, uint64_t nq, int k,
+                        uint64_t* out_ids, float* out_dists, uint32_t* out_counts) {
+  Comm* c = current_comm();
+  const int nr = c ? c->nranks : 1;
+  const size_t id_bytes = (size_t)nq * k * 8, d_bytes = ((size_t)nq * k * 4 + 7) / 8 * 8, c_bytes = ((size_t)nq * 4 + 7) / 8 * 8;
+  const size_t S = id_bytes + d_bytes + c_bytes;
+  DevBuf<uint8_t> blob(S), gathered(S * nr);
+  LB2_CUDA(cudaMemcpyAsync(blob.p, ids, (size_t)nq * k * 8, cudaMemcpyDeviceToDevice, ctx().stream));
+  LB2_CUDA(cudaMemcpyAsync(blob.p + id_bytes, dists, (size_t)nq * k * 4, cudaMemcpyDeviceToDevice, ctx().stream));
+  LB2_CUDA(cudaMemcpyAsync(blob.p + id_bytes + d_bytes, counts, (size_t)nq * 4, cudaMemcpyDeviceToDevice, ctx().stream));
+  comm_allgather_bytes(blob.p, gathered.p, S);
+  LB2_LAUNCH("merge_sharded_topk", merge_kernel, (unsigned)nq, 128, 0,
+             reinterpret_cast<const float*>(gathered.p + id_bytes), reinterpret_cast<const uint64_t*>(gathered.p),
+             reinterpret_cast<const uint32_t*>(gathered.p + id_bytes + d_bytes), nr, k, S / 4, S / 8, (size_t)k,
+             S / 4, (size_t)1, out_ids, out_dists, out_counts);
+  sync_stream();  // the exchange buffers are freed on return
 }
 
 __device__ __forceinline__ bool sorted_contains(const uint64_t* __restrict__ a, uint64_t n, uint64_t v) {
@@ -1246,7 +1271,7 @@ void ivfflat_search_f32(const float* centroids, int K, int d, int metric, const 
 #undef LB2_FLAT
   }
   LB2_LAUNCH("merge_topk", merge_kernel, (unsigned)nq, 128, 0, cand_d.p, cand_id.p, cand_cnt.p, np,
-             k, out_ids, out_dists, out_counts);
+             k, (size_t)k, (size_t)k, (size_t)np * k, (size_t)1, (size_t)np, out_ids, out_dists, out_counts);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -27,6 +27,9 @@ void ivfflat_search_f32(const float* centroids, int K, int d, int metric, const 
                         const float* vectors, const uint64_t* row_ids, const float* queries, uint64_t nq,
                         int k, int nprobes, uint64_t* out_ids, float* out_dists, uint32_t* out_counts,
                         const ScanFilter& flt = ScanFilter());
+// all ranks' [nq][k] results of a row-sharded index -> the global top-k by (distance, row id) on every rank
+void merge_sharded_topk(const uint64_t* ids, const float* dists, const uint32_t* counts, uint64_t nq, int k,
+                        uint64_t* out_ids, float* out_dists, uint32_t* out_counts);
 // bit i of bitmap = RowIdMask::selected(row_ids[i]) (lance-core/src/utils/mask.rs:84-93); lists sorted
 void row_mask_f32(const uint64_t* row_ids, uint64_t n, const uint64_t* allow, uint64_t n_allow, bool has_allow,
                   const uint64_t* block, uint64_t n_block, bool has_block, uint64_t* bitmap);

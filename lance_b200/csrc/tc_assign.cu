@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_filter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
                  uint64_t n, int nkc, int stages, const float* __restrict__ cnh_g,
                  const float* __restrict__ row_norm2, const float* __restrict__ cn2_g,
-                 uint32_t* __restrict__ res, const uint8_t* __restrict__ active) {
+                 uint32_t* __restrict__ res, const uint8_t* __restrict__ active, float tau_scale) {
   if (active && !active[0]) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -163,7 +163,7 @@ top3_row256(taddr, cnh, m1, m2, m3);
       if (lane == 0) mbar_arrive(tempty_bar(buf));
       const uint64_t row = tile * TM + q * 32 + lane;
       if (row < n) {
-        const float tau = 0.0029296875f * (row_norm2[row] + cmax2);  // 3 * 2^-10
+        const float tau = tau_scale * (row_norm2[row] + cmax2);
         uint32_t flag = 2;
         if (m1 - m2 > tau) flag = 0;
         else if (m1 - m3 > tau) flag = 1;
@@ -221,8 +221,11 @@ tc_filter_general_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
                          uint64_t n, int nkc, int ntiles, const float* __restrict__ cnh_g,
                          const float* __restrict__ row_norm2, const float* __restrict__ cmax2_ptr,
                          uint32_t* __restrict__ res, uint32_t* __restrict__ res_hi,
-                         const uint8_t* __restrict__ active) {
+                         const uint8_t* __restrict__ active, float tau_scale,
+                         const uint32_t* __restrict__ n_dev, uint32_t n_cap) {
   if (active && !active[0]) return;
+  if (n_dev) n = min(*n_dev, n_cap);  // refinement pass: the row count lives on the device
+  if (n == 0) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const GenLayout L = gen_layout();
@@ -368,7 +371,7 @@ tc_filter_general_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
       }
       const uint64_t row = tile * TM + q * 32 + lane;
       if (row < n) {
-        const float tau = 0.0029296875f * (row_norm2[row] + cmax2);  // 3 * 2^-10
+        const float tau = tau_scale * (row_norm2[row] + cmax2);
         uint32_t flag = 2;
         if (g[0] - g[1] > tau) flag = 0;
         else if (g[0] - g[2] > tau) flag = 1;
@@ -391,7 +394,7 @@ __global__ void prep_centroids_general_kernel(const float* __restrict__ c, int K
                                               float* __restrict__ cnh, float* __restrict__ cn2,
                                               uint32_t* __restrict__ fb_count) {
   const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *fb_count = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { fb_count[0] = 0; fb_count[1] = 0; }
   if (k >= Kp) return;
   float n2 = 0.0f;
   for (int e = lane; e < d; e += 32) {
@@ -434,7 +437,7 @@ __global__ void prep_centroids_kernel(const float* __restrict__ c, int K, int d,
   // transposed NaN-padded copy cT[e][Kp] used by the exact fallback kernel and resets the
   // fallback-row counter, so one launch prepares everything the iteration needs.
   const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *fb_count = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { fb_count[0] = 0; fb_count[1] = 0; }
   float n2 = 0.0f;
   for (int e = lane; e < d; e += 32) {
     const float v = k < K ? c[(size_t)k * d + e] : 0.0f;
@@ -472,57 +475,126 @@ __global__ void row_norm_kernel(const float* __restrict__ x, uint64_t n, int d, 
 // exact re-rank of the one or two surviving candidates (16 lanes per row; lane l owns the
 // reference's lane-accumulator l, l2.rs:82-88), flag-2 rows are appended to the fallback list
 // ------------------------------------------------------------------------------------------------
+// With `src_list` the kernel serves the refinement pass: entry i of res / res_hi belongs to row
+// src_list[i], i < min(*src_count, src_cap); list entries beyond src_cap (no room in the refinement
+// buffers) are forwarded to the fallback list untouched.
 __global__ void __launch_bounds__(256)
 rerank_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __restrict__ cent,
               const float* __restrict__ bias, const uint32_t* __restrict__ res,
               const uint32_t* __restrict__ res_hi, int need_dist,
               uint32_t* __restrict__ part, float* __restrict__ dist, uint8_t* __restrict__ valid,
               uint32_t* __restrict__ fb_rows, uint32_t* __restrict__ fb_count,
-              const uint8_t* __restrict__ active) {
+              const uint8_t* __restrict__ active, const uint32_t* __restrict__ src_list,
+              const uint32_t* __restrict__ src_count, uint32_t src_cap) {
   if (active && !active[0]) return;
-  const uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   const int l = threadIdx.x & 15;
-  if (row >= n) return;
   const unsigned mask = 0xffffu << (16 * ((threadIdx.x >> 4) & 1));
-  const uint32_t r = res[row];
-  const uint32_t flag = r >> 30;
-  const uint32_t i1 = res_hi ? (r & 0x3FFFFFFFu) : (r & 0xFFFu);
-  const uint32_t i2 = res_hi ? res_hi[row] : ((r >> 12) & 0xFFFu);
-  if (flag == 2) {
-    if (l == 0) fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)row;
-    return;
+  uint64_t total = n;
+  if (src_list) {
+    total = *src_count;
+    need_dist = 1;  // the first pass left these rows without any output
   }
-  if (flag == 0 && !need_dist) {
-    if (l == 0) {
-      part[row] = i1;
-      if (valid) valid[row] = 1;
+  for (uint64_t idx = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4; idx < total;
+       idx += ((uint64_t)gridDim.x * blockDim.x) >> 4) {
+    uint64_t row = idx;
+    if (src_list) {
+      row = src_list[idx];
+      if (idx >= src_cap) {  // overflow of the refinement buffers
+        if (l == 0) fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)row;
+        continue;
+      }
     }
-    return;
-  }
-  const float* xv = x + row * d;
-  const int ncand = flag == 0 ? 1 : 2;
-  float best_key = __int_as_float(0x7f800000), best_val = best_key;
-  uint32_t best_idx = 0xffffffffu;
-  for (int c = 0; c < ncand; ++c) {
-    const uint32_t ci = c == 0 ? i1 : i2;
-    const float* cv = cent + (size_t)ci * d;
-    float acc = 0.0f;
-    for (int e = l; e < d; e += 16) acc = f_add(acc, sq_diff(xv[e], cv[e]));
-    float t = 0.0f;
+    const uint32_t r = res[idx];
+    const uint32_t flag = r >> 30;
+    const uint32_t i1 = res_hi ? (r & 0x3FFFFFFFu) : (r & 0xFFFu);
+    const uint32_t i2 = res_hi ? res_hi[idx] : ((r >> 12) & 0xFFFu);
+    if (flag == 2) {
+      if (l == 0) fb_rows[atomicAdd(fb_count, 1u)] = (uint32_t)row;
+      continue;
+    }
+    if (flag == 0 && !need_dist) {
+      if (l == 0) {
+        part[row] = i1;
+        if (valid) valid[row] = 1;
+      }
+      continue;
+    }
+    const float* xv = x + row * d;
+    const int ncand = flag == 0 ? 1 : 2;
+    float best_key = __int_as_float(0x7f800000), best_val = best_key;
+    uint32_t best_idx = 0xffffffffu;
+    for (int c = 0; c < ncand; ++c) {
+      const uint32_t ci = c == 0 ? i1 : i2;
+      const float* cv = cent + (size_t)ci * d;
+      float acc = 0.0f;
+      for (int e = l; e < d; e += 16) acc = f_add(acc, sq_diff(xv[e], cv[e]));
+      float t = 0.0f;
 #pragma unroll
-    for (int qq = 0; qq < 16; ++qq) t = f_add(t, __shfl_sync(mask, acc, qq, 16));
-    const float v = f_add(0.0f, t);
-    const float key = bias ? f_add(v, bias[ci]) : v;
-    if (key < best_key || (key == best_key && ci < best_idx)) {
-      best_key = key; best_val = v; best_idx = ci;
+      for (int qq = 0; qq < 16; ++qq) t = f_add(t, __shfl_sync(mask, acc, qq, 16));
+      const float v = f_add(0.0f, t);
+      const float key = bias ? f_add(v, bias[ci]) : v;
+      if (key < best_key || (key == best_key && ci < best_idx)) {
+        best_key = key; best_val = v; best_idx = ci;
+      }
+    }
+    if (l == 0) {
+      const bool ok = best_idx != 0xffffffffu;
+      part[row] = ok ? best_idx : 0u;
+      if (dist) dist[row] = ok ? best_val : __int_as_float(0x7fc00000);
+      if (valid) valid[row] = ok ? 1 : 0;
     }
   }
-  if (l == 0) {
-    const bool ok = best_idx != 0xffffffffu;
-    part[row] = ok ? best_idx : 0u;
-    if (dist) dist[row] = ok ? best_val : __int_as_float(0x7fc00000);
-    if (valid) valid[row] = ok ? 1 : 0;
+}
+
+// ---- refinement of the rows the TF32 filter left undecided ------------------------------------------
+// A second tcgen05 pass over those rows only, with the operands split into TF32-exact pieces
+//     x = xh + xl (+ <= 2^-22 |x|),   c = ch + cl (+ <= 2^-22 |c|),     x.c ~ xh.ch + xh.cl + xl.ch,
+// i.e. the SAME filter kernel run on A' = [xh | xh | xl] (gathered, 3d wide) and B' = [ch | cl | ch]: every
+// product is exact in TF32, what is dropped is <= 1.51 * 2^-22 (|x|^2 + |c|^2), the f32 accumulation over
+// 3d/8 MMA steps <= 3d * 2^-26 (|x|^2 + |c|^2) (two ulps per step on the running magnitude), packing the
+// column index into the low mantissa byte 2^-16 (|x|^2 + 2|c|^2).  tau' = (2^-13 + 3d * 2^-25)(|x|^2 +
+// max|c|^2) covers twice their sum; it is ~1/20 .. 1/45 of the first pass's tau, so all but a sliver of the
+// undecided rows become unique / two-candidate rows and only true near-ties reach the full-K exact scan.
+__device__ __forceinline__ float rn_tf32(float v) {  // round to nearest-even TF32 (10 explicit mantissa bits)
+  uint32_t b = __float_as_uint(v);
+  if ((b & 0x7f800000u) == 0x7f800000u) return v;  // Inf / NaN
+  b += 0xFFFu + ((b >> 13) & 1u);
+  return __uint_as_float(b & 0xFFFFE000u);
+}
+__global__ void gather_split_kernel(const float* __restrict__ x, int d, const float* __restrict__ row_norm2,
+                                    const uint32_t* __restrict__ list, const uint32_t* __restrict__ count,
+                                    uint32_t cap, float* __restrict__ a3, float* __restrict__ rn2c,
+                                    const uint8_t* __restrict__ active) {
+  if (active && !active[0]) return;
+  const uint32_t cnt = min(*count, cap);
+  const int d4 = d >> 2;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < (uint64_t)cnt * d4;
+       g += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t i = (uint32_t)(g / d4);
+    const int e = (int)(g % d4) * 4;
+    const uint32_t row = list[i];
+    const float4 v = *reinterpret_cast<const float4*>(x + (size_t)row * d + e);
+    float4 h, lo;
+    h.x = rn_tf32(v.x); h.y = rn_tf32(v.y); h.z = rn_tf32(v.z); h.w = rn_tf32(v.w);
+    lo.x = rn_tf32(v.x - h.x); lo.y = rn_tf32(v.y - h.y); lo.z = rn_tf32(v.z - h.z); lo.w = rn_tf32(v.w - h.w);
+    float* o = a3 + (size_t)i * 3 * d + e;
+    *reinterpret_cast<float4*>(o) = h;
+    *reinterpret_cast<float4*>(o + d) = h;
+    *reinterpret_cast<float4*>(o + 2 * d) = lo;
+    if (e == 0) rn2c[i] = row_norm2[row];
   }
+}
+// B' = [ch | cl | ch] from the padded centroid copy [Kp][d] (pad rows are zero)
+__global__ void split_centroids_kernel(const float* __restrict__ cpad, size_t total, int d, float* __restrict__ b3) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const size_t k = g / d;
+  const int e = (int)(g % d);
+  const float v = cpad[g], h = rn_tf32(v), lo = rn_tf32(v - h);
+  float* o = b3 + k * 3 * d + e;
+  o[0] = h;
+  o[d] = lo;
+  o[2 * d] = h;
 }
 
 }  // namespace tc
@@ -556,6 +628,54 @@ CUtensorMap make_map_2d(const float* base, uint64_t rows, uint64_t cols, uint32_
 }
 
 static bool tc_resident_shape(int d, int K) { return d <= 128 && K <= tc::TN; }
+constexpr float TAU_TF32 = 0.0029296875f;  // 3 * 2^-10, see the header comment
+
+// rows the first pass left undecided (ws->fb_rows / fb_count[0]): refinement pass, exact re-rank of what it
+// settles, and the full-K exact kernel for the rest (ws->fb_rows2 / fb_count[1]).  `cpad` = zero-padded
+// centroids [Kp][d], cnh / cmax2 as prepared for the first pass.
+static void tc_refine_and_fallback(const float* x, uint64_t n, int d, const float* cent, int K, int Kp,
+                                   const float* bias, const float* cpad, const float* cnh, const float* cmax2,
+                                   uint32_t* part, float* dist, uint8_t* valid, const uint8_t* active,
+                                   TcWorkspace* ws, bool cT_ready) {
+  using namespace tc;
+  static const bool no_refine = getenv("LB2_NO_REFINE") && *getenv("LB2_NO_REFINE");
+  const int d3 = 3 * d;
+  // room for 1/8 of the rows, at most ~1.5 GB of 3x-wide rows (callers chunk large inputs, assign_f32_ex);
+  // list entries beyond the capacity go straight to the exact kernel
+  const uint32_t cap = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(n, std::max<uint64_t>(4096, n / 8)),
+                                                    std::max<uint64_t>(TM, ((size_t)3 << 29) / ((size_t)d3 * 4)));
+  const GenLayout L = gen_layout();
+  const size_t smem = L.total + 1024;
+  const bool refine = !no_refine && smem <= ctx().smem_optin;
+  if (!refine) {
+    assign_rows_f32(x, n, d, cent, K, METRIC_L2, bias, ws->fb_rows.p, ws->fb_count.p, part, dist, valid, active, ws,
+                    cT_ready);
+    return;
+  }
+  if (ws->a3.n < (size_t)cap * d3) ws->a3.alloc((size_t)cap * d3);
+  if (ws->b3.n < (size_t)Kp * d3) ws->b3.alloc((size_t)Kp * d3);
+  if (ws->rn2c.n < cap) ws->rn2c.alloc(cap);
+  if (ws->res2.n < (size_t)2 * cap) ws->res2.alloc((size_t)2 * cap);
+  if (ws->fb_rows2.n < n) ws->fb_rows2.alloc(n);
+  const unsigned sms = (unsigned)ctx().num_sms;
+  LB2_LAUNCH("tc_refine_gather", gather_split_kernel, (unsigned)std::min<uint64_t>(cdiv((uint64_t)cap * (d / 4), 256), 8 * sms),
+             256, 0, x, d, ws->row_norm2.p, ws->fb_rows.p, ws->fb_count.p, cap, ws->a3.p, ws->rn2c.p, active);
+  LB2_LAUNCH("tc_refine_gather", split_centroids_kernel, cdiv((uint64_t)Kp * d, 256), 256, 0, cpad, (size_t)Kp * d, d,
+             ws->b3.p);
+  const CUtensorMap map_a = make_map_2d(ws->a3.p, cap, d3, TM);
+  const CUtensorMap map_b = make_map_2d(ws->b3.p, Kp, d3, TN);
+  const float tau2 = 1.220703125e-4f + (float)d3 * 2.98023224e-8f;  // 2^-13 + 3d * 2^-25
+  const unsigned grid = (unsigned)std::min<uint64_t>(cdiv(cap, TM), (uint64_t)sms);
+  set_smem(tc_filter_general_kernel, smem);
+  LB2_LAUNCH("tc_refine_filter", tc_filter_general_kernel, grid, NUM_THREADS, smem, map_a, map_b, (uint64_t)cap, d3 / KC,
+             Kp / TN, cnh, ws->rn2c.p, cmax2, ws->res2.p, ws->res2.p + cap, active, tau2,
+             (const uint32_t*)ws->fb_count.p, cap);
+  LB2_LAUNCH("tc_refine_rerank", rerank_kernel, (unsigned)std::min<uint64_t>(cdiv((uint64_t)n * 16, 256), 8 * sms), 256, 0, x,
+             n, d, cent, bias, ws->res2.p, (const uint32_t*)(ws->res2.p + cap), 1, part, dist, valid, ws->fb_rows2.p,
+             ws->fb_count.p + 1, active, (const uint32_t*)ws->fb_rows.p, (const uint32_t*)ws->fb_count.p, cap);
+  assign_rows_f32(x, n, d, cent, K, METRIC_L2, bias, ws->fb_rows2.p, ws->fb_count.p + 1, part, dist, valid, active, ws,
+                  cT_ready);
+}
 
 bool tc_assign_supported(uint64_t n, int d, int K, int metric, const float* x) {
   if (getenv("LB2_DISABLE_TC") && *getenv("LB2_DISABLE_TC")) return false;
@@ -582,7 +702,7 @@ static void tc_assign_general_f32(const float* x, uint64_t n, int d, const float
   }
   if (ws->res.n < 2 * n) ws->res.alloc(2 * n);
   if (ws->fb_rows.n < n) ws->fb_rows.alloc(n);
-  if (ws->fb_count.n < 1) ws->fb_count.alloc(1);
+  if (ws->fb_count.n < 2) ws->fb_count.alloc(2);
   float* cnh = ws->cnh.p;
   float* cn2 = ws->cnh.p + Kp;
   float* cmax2 = ws->cnh.p + 2 * (size_t)Kp;
@@ -595,10 +715,11 @@ static void tc_assign_general_f32(const float* x, uint64_t n, int d, const float
   const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)ctx().num_sms);
   set_smem(tc_filter_general_kernel, smem);
   LB2_LAUNCH("tc_filter_general", tc_filter_general_kernel, grid, NUM_THREADS, smem, map_x, map_c, n, nkc,
-             ntiles, cnh, ws->row_norm2.p, cmax2, ws->res.p, ws->res.p + n, active);
+             ntiles, cnh, ws->row_norm2.p, cmax2, ws->res.p, ws->res.p + n, active, TAU_TF32,
+             (const uint32_t*)nullptr, 0u);
   LB2_LAUNCH("tc_rerank", rerank_kernel, cdiv(n * 16, 256), 256, 0, x, n, d, cent, bias, ws->res.p,
              (const uint32_t*)(ws->res.p + n), dist != nullptr ? 1 : 0, part, dist, valid, ws->fb_rows.p,
-             ws->fb_count.p, active);
+             ws->fb_count.p, active, (const uint32_t*)nullptr, (const uint32_t*)nullptr, 0u);
   if (getenv("LB2_TC_STATS") && *getenv("LB2_TC_STATS")) {
     std::vector<uint32_t> h(n);
     d2h(h.data(), ws->res.p, n);
@@ -608,8 +729,8 @@ static void tc_assign_general_f32(const float* x, uint64_t n, int d, const float
     fprintf(stderr, "[lb2 tc_filter_general] n=%llu K=%d d=%d: unique %.2f%%, two-candidate %.2f%%, exact-fallback %.2f%%\n",
             (unsigned long long)n, K, d, 100.0 * f[0] / n, 100.0 * f[1] / n, 100.0 * f[2] / n);
   }
-  assign_rows_f32(x, n, d, cent, K, METRIC_L2, bias, ws->fb_rows.p, ws->fb_count.p, part, dist, valid, active, ws,
-                  /*cT_ready=*/false);
+  tc_refine_and_fallback(x, n, d, cent, K, Kp, bias, ws->cpad.p, cnh, cmax2, part, dist, valid, active, ws,
+                         /*cT_ready=*/false);
 }
 
 void tc_assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, const float* bias,
@@ -630,7 +751,7 @@ void tc_assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, 
   TcWorkspace local;
   if (!ws) ws = &local;
   if (ws->cpad.n < (size_t)TN * d) ws->cpad.alloc((size_t)TN * d);
-  if (ws->cnh.n < 2 * TN) ws->cnh.alloc(2 * TN);
+  if (ws->cnh.n < 2 * TN + 1) ws->cnh.alloc(2 * TN + 1);
   const int Kp = (K + 63) / 64 * 64;
   if (ws->cT.n < (size_t)d * Kp) ws->cT.alloc((size_t)d * Kp);
   if (ws->row_norm2.n < n || ws->norm_src != x || ws->norm_n != n) {
@@ -641,9 +762,10 @@ void tc_assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, 
   }
   if (ws->res.n < n) ws->res.alloc(n);
   if (ws->fb_rows.n < n) ws->fb_rows.alloc(n);
-  if (ws->fb_count.n < 1) ws->fb_count.alloc(1);
+  if (ws->fb_count.n < 2) ws->fb_count.alloc(2);
   LB2_LAUNCH("tc_prep_centroids", prep_centroids_kernel, TN / 8, 256, 0, cent, K, d, bias, ws->cpad.p,
              ws->cnh.p, ws->cnh.p + TN, ws->cT.p, Kp, ws->fb_count.p);
+  LB2_LAUNCH("tc_prep_centroids", max_reduce_kernel, 1, 256, 0, ws->cnh.p + TN, TN, ws->cnh.p + 2 * TN);
   const CUtensorMap map_x = make_map_2d(x, n, d, TM);
   const CUtensorMap map_c = make_map_2d(ws->cpad.p, TN, d, TN);
   const uint64_t tiles = (n + TM - 1) / TM;
@@ -651,10 +773,10 @@ void tc_assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, 
   const size_t smem = L.total + 1024;
   set_smem(tc_filter_kernel, smem);
   LB2_LAUNCH("tc_filter", tc_filter_kernel, grid, NUM_THREADS, smem, map_x, map_c, n, nkc, stages,
-             ws->cnh.p, ws->row_norm2.p, ws->cnh.p + TN, ws->res.p, active);
+             ws->cnh.p, ws->row_norm2.p, ws->cnh.p + TN, ws->res.p, active, TAU_TF32);
   LB2_LAUNCH("tc_rerank", rerank_kernel, cdiv(n * 16, 256), 256, 0, x, n, d, cent, bias, ws->res.p,
              (const uint32_t*)nullptr, dist != nullptr ? 1 : 0, part, dist, valid, ws->fb_rows.p,
-             ws->fb_count.p, active);
+             ws->fb_count.p, active, (const uint32_t*)nullptr, (const uint32_t*)nullptr, 0u);
   if (getenv("LB2_TC_STATS") && *getenv("LB2_TC_STATS")) {  // diagnostics: how selective was the filter?
     std::vector<uint32_t> h(n);
     d2h(h.data(), ws->res.p, n);
@@ -666,8 +788,8 @@ void tc_assign_f32(const float* x, uint64_t n, int d, const float* cent, int K, 
   }
   // flag-2 rows: exact kernel over the compacted row list (grid sized for the worst case; CTAs
   // beyond the device-side count exit immediately -> no host synchronisation)
-  assign_rows_f32(x, n, d, cent, K, METRIC_L2, bias, ws->fb_rows.p, ws->fb_count.p, part, dist, valid, active, ws,
-                  /*cT_ready=*/true);
+  tc_refine_and_fallback(x, n, d, cent, K, TN, bias, ws->cpad.p, ws->cnh.p, ws->cnh.p + 2 * TN, part, dist, valid,
+                         active, ws, /*cT_ready=*/true);
 }
 
 }  // namespace lb2

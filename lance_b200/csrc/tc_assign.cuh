@@ -8,6 +8,9 @@ struct TcWorkspace {
   DevBuf<float> cpad, cnh, row_norm2, cT;  // cT: transposed centroids for the exact kernels
   DevBuf<uint32_t> res, fb_rows, fb_count;
   DevBuf<float> split_scratch;  // short row lists: per (row, 64-centroid chunk) partial argmins (key, val, idx)
+  // refinement pass over the rows the first pass left undecided (tc_assign.cu, "refinement")
+  DevBuf<float> a3, b3, rn2c;        // [cap][3d] split rows, [Kp][3d] split centroids, their |x|^2
+  DevBuf<uint32_t> res2, fb_rows2;   // verdicts of the refinement pass, rows that need the full-K exact scan
   const float* norm_src = nullptr;  // row norms are cached per (pointer, n): valid inside one call
   uint64_t norm_n = 0;
 };

@@ -1,13 +1,15 @@
-"""Multi-GPU host plumbing: one process per GPU (torch.distributed for rendezvous only).
+"""Multi-GPU host plumbing: one process per GPU, no framework dependency.
 
-* `init_comm(dist)`  -- rank 0 creates the NCCL unique id (lb2_comm_unique_id), it is broadcast with
-  torch.distributed (gloo or nccl object broadcast), every rank calls lb2_comm_init: from then on
-  lb2_kmeans_train / lb2_pq_train / lb2_ivfpq_build all-reduce the per-cluster sums over NVLink
-   and every rank ends with the SAME centroids / codebook and an index over its
-  own row shard.
-* `shard_rows` / `merge_topk` -- how a query is answered by a row-sharded index: every rank searches
-  its shard, the per-rank (row id, distance) lists are gathered and merged by (distance, row id),
-  exactly the ordering of the reference's final SortExec (rust/lance/src/dataset/scanner.rs:3450-3466).
+* `unique_id()` / `comm_init(uid, rank, world)` -- rank 0 creates the NCCL unique id (lb2_comm_unique_id),
+  the HOST RUNTIME (the Rust side, MPI, torch.distributed -- see tools/dist_util.py for the latter) hands
+  it to every rank, every rank calls lb2_comm_init: from then on lb2_kmeans_train / lb2_pq_train /
+  lb2_ivfpq_build / lb2_ivfflat_build take this rank's ROW SHARD, exchange the per-cluster partial results
+  once per Lloyd iteration over NVLink and every rank ends with the SAME centroids /
+  codebook and an index over its own rows; `IvfPqIndex.search_sharded` merges the per-rank results in the
+  library (lb2_index_search_sharded).
+* `shard_rows` -- contiguous row ranges per GPU; `merge_topk` -- the host-side statement of the merge rule
+  (ascending (distance, row id), the reference's final SortExec, rust/lance/src/dataset/scanner.rs:3450-3466),
+  used by the CPU tests.
 """
 import ctypes as C
 
@@ -38,13 +40,10 @@ def comm_destroy():
     check(lib().lb2_comm_destroy())
 
 
-def init_comm(dist):
-    """dist = torch.distributed (already initialised)."""
-    rank, world = dist.get_rank(), dist.get_world_size()
-    box = [unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(box, src=0)
-    comm_init(box[0], rank, world)
-    return rank, world
+def comm_info():
+    r, n = C.c_int(0), C.c_int(1)
+    check(lib().lb2_comm_info(C.byref(r), C.byref(n)))
+    return r.value, n.value
 
 
 def merge_topk(ids_list, dists_list, k):
@@ -60,15 +59,3 @@ def merge_topk(ids_list, dists_list, k):
         out_i[q, :len(keep)] = ids[q][keep]
         out_d[q, :len(keep)] = dists[q][keep]
     return out_i, out_d
-
-
-def gather_merge_topk(dist, ids, dists, k):
-    """all-gather the per-rank candidate lists (CPU tensors / numpy) and merge on every rank."""
-    import torch
-    world = dist.get_world_size()
-    ti, td = torch.from_numpy(ids.view(np.int64)), torch.from_numpy(dists)
-    gi = [torch.empty_like(ti) for _ in range(world)]
-    gd = [torch.empty_like(td) for _ in range(world)]
-    dist.all_gather(gi, ti)
-    dist.all_gather(gd, td)
-    return merge_topk([g.numpy().view(np.uint64) for g in gi], [g.numpy() for g in gd], k)

@@ -18,7 +18,10 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <limits>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -27,27 +30,104 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------
+// Persistent worker pool (the reference runs these loops on rayon's global pool: threads are created once
+// and parked between jobs, rust/lance-index/src/vector/kmeans.rs:335-356 `par_chunks`).  Workers spin
+// briefly for the next job before sleeping, like rayon's, so that the ~100 short parallel regions of a
+// k-means run do not each pay thread start-up.  Per-row results are independent of the schedule.
+class Pool {
+ public:
+  static Pool& get() {
+    static Pool p;
+    return p;
+  }
+  template <class F>
+  void run(size_t n, int nthreads, F&& f) {
+    std::lock_guard<std::mutex> run_lock(run_mu_);  // one job at a time (callers are not concurrent in practice)
+    const size_t nt = std::min<size_t>(size_t(nthreads), n);
+    ensure(nt - 1);
+    const size_t chunk = std::max<size_t>(1, n / (nt * 16));
+    std::atomic<size_t> next{0};
+    std::function<void()> body = [&] {
+      for (;;) {
+        const size_t b = next.fetch_add(chunk, std::memory_order_relaxed);
+        if (b >= n) break;
+        f(b, std::min(n, b + chunk));
+      }
+    };
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      job_ = &body;
+      want_ = nt - 1;
+      taken_ = 0;
+      done_ = 0;
+      ++gen_;
+    }
+    cv_.notify_all();
+    body();
+    // wait for the helpers that picked the job up
+    for (int spin = 0;; ++spin) {
+      if (done_.load(std::memory_order_acquire) == want_) break;
+      if (spin > 2000) std::this_thread::yield();
+    }
+    std::lock_guard<std::mutex> lk(mu_);
+    job_ = nullptr;
+  }
+
+ private:
+  Pool() = default;
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  void ensure(size_t helpers) {
+    while (th_.size() < helpers) th_.emplace_back([this, id = th_.size()] { worker(id); });
+  }
+  void worker(size_t id) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::function<void()>* job = nullptr;
+      {
+        // spin a little on the generation counter before blocking
+        for (int spin = 0; spin < 4000 && gen_relaxed() == seen; ++spin) {
+        }
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        if (job_ && id < want_) {
+          job = job_;
+          ++taken_;
+        }
+      }
+      if (job) {
+        (*job)();
+        done_.fetch_add(1, std::memory_order_release);
+      }
+    }
+  }
+  uint64_t gen_relaxed() { return gen_.load(std::memory_order_relaxed); }
+  std::mutex mu_, run_mu_;
+  std::condition_variable cv_;
+  std::vector<std::thread> th_;
+  std::function<void()>* job_ = nullptr;
+  size_t want_ = 0, taken_ = 0;
+  std::atomic<size_t> done_{0};
+  std::atomic<uint64_t> gen_{0};
+  bool stop_ = false;
+};
+
 template <class F>
 void parallel_for(size_t n, int nthreads, F f) {
   if (nthreads <= 1 || n < 2) {
     f(size_t(0), n);
     return;
   }
-  size_t nt = std::min<size_t>(size_t(nthreads), n);
-  std::atomic<size_t> next{0};
-  // dynamic chunks, like rayon's work stealing; per-row results are independent so scheduling
-  // cannot change any output.
-  size_t chunk = std::max<size_t>(1, n / (nt * 16));
-  std::vector<std::thread> th;
-  for (size_t t = 0; t < nt; ++t)
-    th.emplace_back([&] {
-      for (;;) {
-        size_t b = next.fetch_add(chunk);
-        if (b >= n) break;
-        f(b, std::min(n, b + chunk));
-      }
-    });
-  for (auto& x : th) x.join();
+  Pool::get().run(n, nthreads, f);
 }
 
 // splitmix64: OUR rng for init / split_clusters (reference uses an unseeded SmallRng,
@@ -398,13 +478,29 @@ int lo_kmeans_train(const float* data_in, uint64_t n_in, uint64_t d, uint64_t k,
     for (uint64_t c = 0; c < k; ++c) sum_losses += losses[c];
     last_loss = sum_losses + double(balance_loss);
     // to_kmeans (kmeans.rs:371-446): per-cluster sum in row order IN T, then *= 1/cnt
+    //   The reference splits the CENTROIDS into chunks, one rayon task each, and every task walks all rows
+    //   and adds the ones that belong to its chunk (kmeans.rs:383-408): per centroid the rows are still
+    //   added in row order, so the bits do not depend on the number of tasks.
     std::fill(cent.begin(), cent.end(), 0.0f);
-    for (uint64_t i = 0; i < n; ++i)
-      if (valid[i]) {
-        float* c = &cent[uint64_t(ids[i]) * d];
-        const float* v = data + i * d;
-        for (uint64_t j = 0; j < d; ++j) c[j] += v[j];
-      }
+    {
+      uint64_t ncpu = nthreads > 2 ? uint64_t(nthreads - 2) : 1;  // get_num_compute_intensive_cpus()
+      if (k < ncpu || k < 16) ncpu = 1;
+      const uint64_t chunk_size = k / ncpu;
+      const uint64_t nchunks = (k + chunk_size - 1) / chunk_size;
+      parallel_for(nchunks, nthreads, [&](size_t cb, size_t ce) {
+        for (size_t ch = cb; ch < ce; ++ch) {
+          const uint64_t start = ch * chunk_size, end = std::min<uint64_t>((ch + 1) * chunk_size, k);
+          for (uint64_t i = 0; i < n; ++i) {
+            const uint64_t cid = ids[i];
+            if (valid[i] && start <= cid && cid < end) {
+              float* c = &cent[cid * d];
+              const float* v = data + i * d;
+              for (uint64_t j = 0; j < d; ++j) c[j] += v[j];
+            }
+          }
+        }
+      });
+    }
     for (uint64_t c = 0; c < k; ++c)
       if (cluster_sizes[c] > 0) {
         float norm = 1.0f / float(cluster_sizes[c]);

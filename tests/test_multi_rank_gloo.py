@@ -49,7 +49,8 @@ def _worker(rank, world, port, q):
         off[1:] = np.cumsum(np.bincount(p_s, minlength=K))
         rid = (order + lo).astype(np.uint64)
         ids, dd, _ = ob.ivfpq_search(cent, cb, off, codes_s[order], rid, queries, k, nprobes)
-        gi, gd = parallel.gather_merge_topk(dist, ids, dd, k)
+        from tools import dist_util
+        gi, gd = dist_util.gather_merge_topk(dist, ids, dd, k)
         if rank == 0:
             # unsharded reference
             codes = ob.pq_encode(cb, res)

@@ -8,8 +8,9 @@ import lance_b200 as lb
 
 os.environ["LB2_TC_STATS"] = "1"
 lb.set_device(0)
-NAMES = ("tc_filter", "tc_filter_general", "tc_rerank", "assign_exact_fallback", "tc_row_norms",
-         "tc_prep_centroids", "assign_exact", "assign_exact_generic", "transpose_centroids")
+NAMES = ("tc_filter", "tc_filter_general", "tc_rerank", "tc_refine_gather", "tc_refine_filter", "tc_refine_rerank",
+         "assign_exact_fallback", "tc_row_norms", "tc_prep_centroids", "assign_exact", "assign_exact_generic",
+         "transpose_centroids")
 for n, d, K in ((200000, 768, 1024), (500000, 128, 4096), (500000, 256, 256), (100000, 1536, 512), (500000, 64, 1024)):
     g = torch.Generator(device="cuda").manual_seed(n + d + K)
     lat = torch.randn(n, 24, device="cuda", generator=g)
