@@ -45,6 +45,9 @@ _DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float16): F16, np.dtype(np.uin
 def _typed(a, bf16=False):
     """(array, lb2_dtype): f32 / f16 / u8 buffers are passed as they are (bf16 = uint16 + bf16=True)."""
     if bf16:
+        if isinstance(a, (DeviceArray, PinnedArray)):
+            assert np.dtype(a.dtype) == np.uint16
+            return a, BF16
         return np.ascontiguousarray(a, dtype=np.uint16), BF16
     if isinstance(a, (DeviceArray, PinnedArray)):
         return a, _DTYPES[np.dtype(a.dtype)]
@@ -470,7 +473,7 @@ class IvfPqIndex:
         `out` = optional (row_ids, dists) arrays (numpy/Pinned/Device) to write into."""
         dt = getattr(self, "_dt", F32)
         if isinstance(queries, (DeviceArray, PinnedArray)):
-            assert _DTYPES[np.dtype(queries.dtype)] == dt
+            assert np.dtype(queries.dtype).itemsize == {F32: 4, F16: 2, BF16: 2, U8: 1}[dt]
         else:
             queries = np.ascontiguousarray(queries, dtype={F32: np.float32, F16: np.float16, U8: np.uint8, BF16: np.uint16}[dt])
         nq = queries.shape[0]
@@ -601,7 +604,8 @@ class IvfFlatIndex(IvfPqIndex):
         if centroids is not None:
             keep = _f32(centroids)
             bp.ivf.init_centroids = as_ptr(keep)[0].value
-        rid = None if row_ids is None else np.ascontiguousarray(row_ids, dtype=np.uint64)
+        rid = None if row_ids is None else (row_ids if isinstance(row_ids, (DeviceArray, PinnedArray))
+                                            else np.ascontiguousarray(row_ids, dtype=np.uint64))
         h = C.c_void_p()
         st = BuildStats()
         dp, _k1 = as_ptr(data)
@@ -632,7 +636,8 @@ class IvfFlatIndex(IvfPqIndex):
         K, d, n = i["num_partitions"], i["dimension"], i["num_rows"]
         cent = np.empty((K, d), np.float32)
         off = np.empty(K + 1, np.uint64)
-        vec = np.empty((n, d), np.float32)
+        # the stored vectors keep the column's element type (bf16 as uint16 bit patterns; u8 columns are held as f32)
+        vec = np.empty((n, d), {F32: np.float32, F16: np.float16, BF16: np.uint16, U8: np.float32}[getattr(self, "_dt", F32)])
         rid = np.empty(n, np.uint64)
         check(lib().lb2_index_export_flat(self._h, C.c_void_p(cent.ctypes.data), C.c_void_p(off.ctypes.data),
                                           C.c_void_p(vec.ctypes.data), C.c_void_p(rid.ctypes.data)))

@@ -99,8 +99,8 @@ __global__ void residual_kernel(const float* x, const float* __restrict__ cent,
 }
 
 // kernels.rs:141-146: norm = sqrt(sum x^2) accumulated sequentially in f32, then x / norm
-__global__ void normalize_kernel(const float* __restrict__ x, uint64_t n, int d,
-                                 float* __restrict__ out) {
+// (x and out may be the same buffer: a row is read completely before it is written)
+__global__ void normalize_kernel(const float* x, uint64_t n, int d, float* out) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const float* v = x + r * d;
@@ -273,6 +273,184 @@ struct VecOut {
   }
 };
 
+// gather rows of a matrix of any element type into f32 (training samples, fallback rows)
+__global__ void gather_rows_typed_kernel(const void* __restrict__ x, int dt, const uint64_t* __restrict__ rows,
+                                         uint64_t s, int d, float* __restrict__ out) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= s * d) return;
+  const size_t src = (size_t)rows[g / d] * d + g % d;
+  float v;
+  if (dt == LB2_F32) v = reinterpret_cast<const float*>(x)[src];
+  else if (dt == LB2_F16) v = __half2float(reinterpret_cast<const __half*>(x)[src]);
+  else if (dt == LB2_BF16) v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[src]);
+  else v = (float)reinterpret_cast<const uint8_t*>(x)[src];
+  out[g] = v;
+}
+// values of an f32 buffer rounded to what element type `dt` can hold (f16 / bf16 models: the reference keeps
+// centroids and codebooks in the vectors' own type, kmeans.rs:405-418, pq/builder.rs:139-157)
+__global__ void round_to_dtype_kernel(float* __restrict__ v, size_t count, int dt) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  if (dt == LB2_F16) v[i] = __half2float(__float2half_rn(v[i]));
+  else if (dt == LB2_BF16) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+}
+static void round_model(float* v, size_t count, lb2_dtype dt) {
+  if ((dt == LB2_F16 || dt == LB2_BF16) && count)
+    LB2_LAUNCH("round_model", round_to_dtype_kernel, cdiv(count, 256), 256, 0, v, count, (int)dt);
+}
+
+// ---- a caller's n x d matrix, in its own element type, wherever it lives ----------------------------------
+// The kernels never see an f32 copy of the WHOLE matrix.  Device-resident rows are used where they are;
+// host rows are either copied once, in their native type, on a second stream while training runs (when they
+// fit the budget), or streamed chunk by chunk through two staging slots during the per-row pass.  f32 views
+// exist for one chunk of rows at a time (zero-copy when the rows already are f32 on the device).
+class Source {
+ public:
+  Source(const void* p, uint64_t n, int d, lb2_dtype dt) : host_(p), n_(n), d_(d), dt_(dt), es_(dtype_size(dt)) {
+    cudaPointerAttributes pa;
+    const bool ok = cudaPointerGetAttributes(&pa, p) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    if (ok && (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged)) {
+      dev_native_ = p;
+    } else if (ok && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
+      zero_copy_ = pa.devicePointer;  // pinned: the device can read it over PCIe
+    }
+  }
+  ~Source() {
+    if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
+    if (copied_) cudaEventDestroy(copied_);
+    for (auto& e : slot_ready_) if (e) cudaEventDestroy(e);
+    for (auto& e : slot_free_) if (e) cudaEventDestroy(e);
+  }
+  Source(const Source&) = delete;
+  uint64_t rows_per_chunk() const {  // <= 1 GB of f32 per chunk, 64 Ki .. 1 Mi rows
+    return std::max<uint64_t>(1ull << 16, std::min<uint64_t>(1ull << 20, (1ull << 28) / (uint64_t)d_));
+  }
+  // training sample: rows `rows` (ascending) as f32 [rows.size()][d] -- straight out of the caller's memory
+  void gather_f32(const std::vector<uint64_t>& rows, float* out) {
+    const uint64_t s = rows.size();
+    if (!s) return;
+    const void* src = dev_native_ ? dev_native_ : zero_copy_;
+    if (src) {
+      DevBuf<uint64_t> rows_d(s);
+      h2d(rows_d.p, rows.data(), s);
+      LB2_LAUNCH("gather_rows", gather_rows_typed_kernel, cdiv(s * d_, 256), 256, 0, src, (int)dt_, rows_d.p, s, d_, out);
+      sync_stream();
+      return;
+    }
+    // pageable host memory: pack the rows on the host, one copy, convert on the device
+    std::vector<uint8_t> pack((size_t)s * d_ * es_);
+    for (uint64_t i = 0; i < s; ++i)
+      memcpy(pack.data() + (size_t)i * d_ * es_, static_cast<const uint8_t*>(host_) + (size_t)rows[i] * d_ * es_, (size_t)d_ * es_);
+    if (dt_ == LB2_F32) {
+      LB2_CUDA(cudaMemcpyAsync(out, pack.data(), pack.size(), cudaMemcpyHostToDevice, ctx().stream));
+    } else {
+      DevBuf<uint8_t> raw(pack.size());
+      LB2_CUDA(cudaMemcpyAsync(raw.p, pack.data(), pack.size(), cudaMemcpyHostToDevice, ctx().stream));
+      LB2_LAUNCH("convert_to_f32", to_f32_kernel, cdiv((size_t)s * d_, 256), 256, 0, raw.p, (int)dt_, (size_t)s * d_, out);
+    }
+    sync_stream();
+  }
+  // Host rows that fit: one bulk copy in the NATIVE type on a second stream (call after the sample gathers --
+  // zero-copy reads get no PCIe bandwidth while the copy engine streams).  Otherwise chunks are staged on demand.
+  void start_resident_copy() {
+    if (dev_native_ || n_ == 0) return;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t bytes = (size_t)n_ * d_ * es_;
+    if (bytes > free_b / 2) return;  // streamed
+    bulk_.alloc(bytes);
+    LB2_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    LB2_CUDA(cudaEventCreateWithFlags(&copied_, cudaEventDisableTiming));
+    LB2_CUDA(cudaEventRecord(copied_, ctx().stream));  // after the pool allocation and the gathers
+    LB2_CUDA(cudaStreamWaitEvent(copy_stream_, copied_, 0));
+    LB2_CUDA(cudaMemcpyAsync(bulk_.p, host_, bytes, cudaMemcpyHostToDevice, copy_stream_));
+    LB2_CUDA(cudaEventRecord(copied_, copy_stream_));
+    bulk_pending_ = true;
+  }
+  // device pointer to ALL rows in their native type, or nullptr when the matrix is streamed
+  const void* native_device() {
+    if (dev_native_) return dev_native_;
+    if (bulk_.p) {
+      if (bulk_pending_) { LB2_CUDA(cudaStreamWaitEvent(ctx().stream, copied_, 0)); bulk_pending_ = false; }
+      return bulk_.p;
+    }
+    return nullptr;
+  }
+  // f32 view of rows [r0, r0 + rows) on the library's stream; valid until the second-next call (two slots)
+  const float* rows_f32(uint64_t r0, uint64_t rows) {
+    const void* nat = native_device();
+    const size_t off = (size_t)r0 * d_ * es_, cnt = (size_t)rows * d_;
+    if (nat && dt_ == LB2_F32) return reinterpret_cast<const float*>(static_cast<const uint8_t*>(nat) + off);
+    const int slot = (int)(calls_++ & 1);
+    if (nat) {
+      if (f32_[slot].n < cnt) f32_[slot].alloc(cnt);
+      LB2_LAUNCH("convert_to_f32", to_f32_kernel, cdiv(cnt, 256), 256, 0, static_cast<const uint8_t*>(nat) + off,
+                 (int)dt_, cnt, f32_[slot].p);
+      return f32_[slot].p;
+    }
+    // streamed from the host: the copy runs on the copy stream (issued by prefetch() while the previous chunk's
+    // kernels execute, or here), the conversion on the library's stream
+    if (!(staged_[slot] && staged_r0_[slot] == r0)) issue_copy(slot, r0, rows);
+    staged_[slot] = false;
+    LB2_CUDA(cudaStreamWaitEvent(ctx().stream, slot_ready_[slot], 0));
+    if (dt_ != LB2_F32)
+      LB2_LAUNCH("convert_to_f32", to_f32_kernel, cdiv(cnt, 256), 256, 0, raw_[slot].p, (int)dt_, cnt, f32_[slot].p);
+    return f32_[slot].p;
+  }
+  // start the host-to-device copy of the NEXT chunk; call right after rows_f32() of the current chunk and
+  // BEFORE launching the current chunk's kernels (the slot being refilled was last read by the chunk before it)
+  void prefetch(uint64_t r0, uint64_t rows) {
+    if (rows == 0 || native_device() != nullptr) return;
+    issue_copy((int)(calls_ & 1), r0, rows);
+  }
+
+ private:
+  void issue_copy(int slot, uint64_t r0, uint64_t rows) {
+    const size_t off = (size_t)r0 * d_ * es_, cnt = (size_t)rows * d_;
+    if (!copy_stream_) LB2_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    if (!slot_ready_[slot]) {
+      LB2_CUDA(cudaEventCreateWithFlags(&slot_ready_[slot], cudaEventDisableTiming));
+      LB2_CUDA(cudaEventCreateWithFlags(&slot_free_[slot], cudaEventDisableTiming));
+    }
+    if (f32_[slot].n < cnt) f32_[slot].alloc(cnt);
+    uint8_t* dst = reinterpret_cast<uint8_t*>(f32_[slot].p);
+    if (dt_ != LB2_F32) {
+      if (raw_[slot].n < cnt * es_) raw_[slot].alloc(cnt * es_);
+      dst = raw_[slot].p;
+    }
+    LB2_CUDA(cudaEventRecord(slot_free_[slot], ctx().stream));  // everything issued so far is done with the slot
+    LB2_CUDA(cudaStreamWaitEvent(copy_stream_, slot_free_[slot], 0));
+    LB2_CUDA(cudaMemcpyAsync(dst, static_cast<const uint8_t*>(host_) + off, cnt * es_, cudaMemcpyHostToDevice, copy_stream_));
+    LB2_CUDA(cudaEventRecord(slot_ready_[slot], copy_stream_));
+    staged_[slot] = true;
+    staged_r0_[slot] = r0;
+  }
+
+ public:
+  uint64_t n() const { return n_; }
+  int d() const { return d_; }
+  lb2_dtype dtype() const { return dt_; }
+  size_t row_bytes() const { return (size_t)d_ * es_; }
+
+ private:
+  bool staged_[2] = {false, false};
+  uint64_t staged_r0_[2] = {0, 0};
+  const void* host_;
+  uint64_t n_;
+  int d_;
+  lb2_dtype dt_;
+  size_t es_;
+  const void* dev_native_ = nullptr;
+  const void* zero_copy_ = nullptr;
+  DevBuf<uint8_t> bulk_, raw_[2];
+  DevBuf<float> f32_[2];
+  cudaStream_t copy_stream_ = nullptr;
+  cudaEvent_t copied_ = nullptr, slot_ready_[2] = {nullptr, nullptr}, slot_free_[2] = {nullptr, nullptr};
+  bool bulk_pending_ = false;
+  uint64_t calls_ = 0;
+};
+
 static void require_f32(lb2_dtype dt, const char* what) {
   if (dt != LB2_F32)
     fail(LB2_UNSUPPORTED, "%s: element type %d is not implemented on the device yet (f32 only)", what,
@@ -295,7 +473,11 @@ using namespace lb2;
 struct lb2_index {
   int kind = 0;  // 0 = IVF_PQ, 1 = IVF_FLAT
   lb2_dtype dtype = LB2_F32;  // element type of the vectors / queries the caller passes
-  DevBuf<float> vectors;  // IVF_FLAT: raw (normalised for cosine) vectors in partition order
+  // IVF_FLAT: the (normalised for cosine) vectors in partition order, in the vectors' own element type
+  // (f32 / f16 / bf16; u8 columns are held as f32, the reference's model type for them, ivf.rs:1917-1929)
+  DevBuf<uint8_t> vectors;
+  lb2_dtype vdtype() const { return dtype == LB2_U8 ? LB2_F32 : dtype; }
+  size_t vrow_bytes() const { return (size_t)d * (vdtype() == LB2_F32 ? 4 : 2); }
   int K = 0, d = 0, M = 0, nbits = 8, metric = 0;
   uint64_t n = 0;
   DevBuf<float> centroids, codebook;
@@ -351,65 +533,88 @@ static void index_load_dev(lb2_index* ix, const uint32_t* part_ids, const uint8_
   sync_stream();
 }
 
-static void index_load_flat_dev(lb2_index* ix, const uint32_t* part_ids, const float* vectors,
-                                const uint64_t* row_ids, uint64_t n, const uint8_t* valid = nullptr) {
-  LB2_REQUIRE(ix->d % 4 == 0, "IVF_FLAT needs a dimension that is a multiple of 4");
+__global__ void copy_row_ids_kernel(const uint32_t* __restrict__ members, uint64_t n, const uint64_t* __restrict__ row_ids,
+                                    uint64_t* __restrict__ out) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) out[g] = row_ids ? row_ids[members[g]] : (uint64_t)members[g];
+}
+__global__ void members_to_u64_kernel(const uint32_t* __restrict__ members, uint64_t n, uint64_t* __restrict__ out) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) out[g] = members[g];
+}
+
+// IVF_FLAT storage: the kept rows grouped by partition (stable), normalised when the metric is cosine
+// (IvfTransformer::new_flat, lance-index/src/vector/ivf.rs:149-185), written in the index's element type.
+// Rows are pulled from the caller's matrix in chunks of output positions (never a whole-matrix f32 copy).
+static void index_load_flat_src(lb2_index* ix, const uint32_t* part_ids, Source& src, const uint64_t* row_ids,
+                                const uint8_t* valid, bool normalize) {
+  const uint64_t n = src.n();
   MemberSort ms;
   const uint64_t kept = member_sort_index(ms, ix, part_ids, valid, n);
-  ix->vectors.alloc(std::max<uint64_t>(1, kept * ix->d));
+  const lb2_dtype vdt = ix->vdtype();
+  ix->vectors.alloc(std::max<size_t>(1, kept * ix->vrow_bytes()));
   ix->row_ids.alloc(std::max<uint64_t>(1, kept));
-  if (kept)
-    LB2_LAUNCH("group_vectors", group_vectors_kernel, cdiv(kept * (ix->d / 4), 256), 256, 0, ms.members.p, kept,
-               ix->d, vectors, row_ids, ix->vectors.p, ix->row_ids.p);
   ix->n = kept;
+  if (!kept) { sync_stream(); return; }
+  LB2_LAUNCH("group_row_ids", copy_row_ids_kernel, cdiv(kept, 256), 256, 0, ms.members.p, kept, row_ids, ix->row_ids.p);
+  const void* nat = src.native_device();
+  if (!nat) fail(LB2_OOM, "IVF_FLAT keeps a copy of the vectors: the %llu x %d matrix must fit in device memory",
+                 (unsigned long long)n, ix->d);
+  const int d = ix->d;
+  const uint64_t chunk = src.rows_per_chunk();
+  DevBuf<uint64_t> rows64(std::min(chunk, kept));
+  DevBuf<float> tmp, tmp2;
+  const bool direct = vdt == LB2_F32 && !normalize;
+  if (!direct) tmp.alloc(std::min(chunk, kept) * d);
+  if (normalize && vdt == LB2_F32) {
+  } else if (normalize) {
+    tmp2.alloc(std::min(chunk, kept) * d);
+  }
+  for (uint64_t p0 = 0; p0 < kept; p0 += chunk) {
+    const uint64_t rows = std::min(chunk, kept - p0);
+    LB2_LAUNCH("group_vectors", members_to_u64_kernel, cdiv(rows, 256), 256, 0, ms.members.p + p0, rows, rows64.p);
+    uint8_t* dst = ix->vectors.p + p0 * ix->vrow_bytes();
+    float* g = direct ? reinterpret_cast<float*>(dst) : tmp.p;
+    LB2_LAUNCH("group_vectors", gather_rows_typed_kernel, cdiv(rows * d, 256), 256, 0, nat, (int)src.dtype(), rows64.p, rows, d, g);
+    if (normalize) {
+      float* o = vdt == LB2_F32 ? reinterpret_cast<float*>(dst) : tmp2.p;
+      LB2_LAUNCH("normalize", normalize_kernel, cdiv(rows, 128), 128, 0, g, rows, d, o);
+      g = o;
+    }
+    if (vdt != LB2_F32)
+      LB2_LAUNCH("convert_from_f32", from_f32_kernel, cdiv(rows * d, 256), 256, 0, g, (int)vdt, (size_t)rows * d, (void*)dst);
+  }
   sync_stream();
 }
 
 // Training sample of a build: rows `rows` (ascending) of x, minus the rows that are not finite
 // (rust/lance/src/index/vector/builder.rs:436 keeps `is_finite` rows only; under cosine a zero vector
 // has become NaN by then).  Returns the number of rows kept in `out` ([rows.size()][d]).
-static uint64_t gather_finite_sample(const float* x, std::vector<uint64_t>& rows, int d, DevBuf<float>& out) {
+static uint64_t gather_finite_sample(Source& src, std::vector<uint64_t>& rows, bool normalize, DevBuf<float>& out) {
+  const int d = src.d();
   uint64_t s = rows.size();
   out.alloc(std::max<uint64_t>(1, s * d));
   if (s == 0) return 0;
-  DevBuf<uint64_t> rows_d(s);
   DevBuf<uint8_t> flag(s);
-  h2d(rows_d.p, rows.data(), s);
-  LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(s * d, 256), 256, 0, x, rows_d.p, s, d, out.p);
-  LB2_LAUNCH("finite_rows", finite_rows_kernel, cdiv(s * 32, 256), 256, 0, out.p, s, d, flag.p);
   std::vector<uint8_t> hf(s);
-  d2h(hf.data(), flag.p, s);
-  sync_stream();
-  uint64_t kept = 0;
-  for (uint64_t i = 0; i < s; ++i)
-    if (hf[i]) rows[kept++] = rows[i];
-  if (kept == s) return s;
-  rows.resize(kept);  // rare: gather again without the dropped rows (order preserved)
-  if (kept) {
-    h2d(rows_d.p, rows.data(), kept);
-    LB2_LAUNCH("gather_rows", gather_rows_kernel, cdiv(kept * d, 256), 256, 0, x, rows_d.p, kept, d, out.p);
+  for (int pass = 0; pass < 2; ++pass) {
+    src.gather_f32(rows, out.p);
+    if (normalize)  // cosine: NormalizeTransformer first (ivf.rs:158-166); a zero vector becomes NaN and is dropped
+      LB2_LAUNCH("normalize", normalize_kernel, cdiv(s, 128), 128, 0, out.p, s, d, out.p);
+    if (pass == 1) break;
+    LB2_LAUNCH("finite_rows", finite_rows_kernel, cdiv(s * 32, 256), 256, 0, out.p, s, d, flag.p);
+    d2h(hf.data(), flag.p, s);
     sync_stream();
+    uint64_t kept = 0;
+    for (uint64_t i = 0; i < s; ++i)
+      if (hf[i]) rows[kept++] = rows[i];
+    if (kept == s) break;
+    rows.resize(kept);  // rare: gather again without the dropped rows (order preserved)
+    s = kept;
+    if (!s) break;
   }
-  return kept;
-}
-
-// s distinct rows out of n, ascending: one uniformly random row from each of s equal strata
-// (the reference draws a random subset through Dataset::sample, rust/lance/src/index/vector/utils.rs:
-// 202-209, with an unseeded rng -> the selection is unpinned; ours is O(s), seeded, already sorted)
-static std::vector<uint64_t> sample_rows(uint64_t n, uint64_t s, uint64_t seed) {
-  std::vector<uint64_t> out;
-  if (s >= n) {
-    out.resize(n);
-    for (uint64_t i = 0; i < n; ++i) out[i] = i;
-    return out;
-  }
-  SplitMix64 rng(seed);
-  out.resize(s);
-  for (uint64_t i = 0; i < s; ++i) {
-    const uint64_t lo = (unsigned __int128)i * n / s, hi = (unsigned __int128)(i + 1) * n / s;
-    out[i] = lo + rng.next() % (hi - lo);
-  }
-  return out;
+  sync_stream();
+  return s;
 }
 
 // ProductQuantizer::transform_impl for either code width (pq.rs:116-191): 8-bit -> [n][M] through the
@@ -456,6 +661,58 @@ static void pq_train_dev(const float* data, uint64_t n, int d, int metric, const
   InArg<float> init(p->codebook, (size_t)M * K * (d / M));
   lloyd_train(data, rows, d, M, d / M, K, metric == METRIC_DOT ? METRIC_DOT : METRIC_L2, 0.0f,
               (int)p->max_iters, 1e-4, p->seed, init.get(), codebook, nullptr, iters);
+}
+
+// s distinct rows out of n, ascending: one uniformly random row from each of s equal strata
+// (the reference draws a random subset through Dataset::sample, rust/lance/src/index/vector/utils.rs:
+// 202-209, with an unseeded rng -> the selection is unpinned; ours is O(s), seeded, already sorted)
+static std::vector<uint64_t> sample_rows(uint64_t n, uint64_t s, uint64_t seed) {
+  std::vector<uint64_t> out;
+  if (s >= n) {
+    out.resize(n);
+    for (uint64_t i = 0; i < n; ++i) out[i] = i;
+    return out;
+  }
+  SplitMix64 rng(seed);
+  out.resize(s);
+  for (uint64_t i = 0; i < s; ++i) {
+    const uint64_t lo = (unsigned __int128)i * n / s, hi = (unsigned __int128)(i + 1) * n / s;
+    out[i] = lo + rng.next() % (hi - lo);
+  }
+  return out;
+}
+
+// one pass over a caller's matrix in chunks of rows: f(xf, r0, rows) with xf = the chunk as f32 on the device
+template <class F>
+static void for_each_chunk(Source& src, F&& f) {
+  const uint64_t n = src.n(), chunk = src.rows_per_chunk();
+  // (a little more than one chunk is not split: SIFT-1M is one call)
+  const uint64_t step = n <= chunk + chunk / 2 ? std::max<uint64_t>(n, 1) : chunk;
+  for (uint64_t r0 = 0; r0 < n; r0 += step) {
+    const uint64_t rows = std::min(step, n - r0);
+    const float* xf = src.rows_f32(r0, rows);
+    if (r0 + rows < n) src.prefetch(r0 + rows, std::min(step, n - r0 - rows));
+    f(xf, r0, rows);
+  }
+}
+
+// IvfTransformer::transform over one chunk of rows already on the device as f32 (lance-index/src/vector/ivf.rs:
+// 188-236,357): [normalise if cosine] -> partition id -> residual -> PQ code.  The quantizer of an index build is
+// trained -- and therefore encodes -- with L2 whatever the index metric is: Q::build(&training_data,
+// DistanceType::L2, ..) (rust/lance/src/index/vector/builder.rs:460); the index metric only decides the partition
+// assignment, whether residuals are taken (not for dot, PQBuildParams::use_residual) and the query-time table.
+static void transform_chunk(const float* xf, uint64_t rows, int d, int m, const float* cent, int K, const float* codebook,
+                            int M, int nbits, DevBuf<float>& normbuf, uint32_t* part, uint8_t* codes, uint8_t* valid) {
+  const float* xp = xf;
+  if (m == METRIC_COSINE) {
+    if (normbuf.n < (size_t)rows * d) normbuf.alloc((size_t)rows * d);
+    LB2_LAUNCH("normalize", normalize_kernel, cdiv(rows, 128), 128, 0, xf, rows, d, normbuf.p);
+    xp = normbuf.p;
+  }
+  const int am = m == METRIC_DOT ? METRIC_DOT : METRIC_L2;
+  assign_f32(xp, rows, d, cent, K, am, nullptr, part, nullptr, valid, nullptr);
+  pq_encode_any(xp, rows, d, M, d / M, codebook, METRIC_L2, am == METRIC_DOT ? nullptr : cent,
+                am == METRIC_DOT ? nullptr : part, valid, nbits, codes);
 }
 
 }  // namespace lb2
@@ -691,11 +948,18 @@ lb2_status lb2_compute_partitions(const void* centroids, uint32_t k, uint32_t d,
   LB2_API_BEGIN
   const int m = metric_of(metric);
   if (m == METRIC_COSINE) fail(LB2_INVALID_ARG, "compute_partitions: normalise and use L2 for cosine");
-  VecIn c(centroids, (size_t)k * d, model_dtype(dtype)), x(vectors, (size_t)n * d, dtype);
+  VecIn c(centroids, (size_t)k * d, model_dtype(dtype));
   OutArg<uint32_t> p(part_out, n);
   OutArg<float> dd(dist_out, n);
   OutArg<uint8_t> v(valid_out, n);
-  assign_f32(x.get(), n, d, c.get(), k, m, nullptr, p.get(), dd.get(), v.get(), nullptr);
+  if (n) {
+    Source src(vectors, n, (int)d, dtype);
+    src.start_resident_copy();
+    for_each_chunk(src, [&](const float* xf, uint64_t r0, uint64_t rows) {
+      assign_f32(xf, rows, d, c.get(), k, m, nullptr, p.get() + r0, dd.get() ? dd.get() + r0 : nullptr,
+                 v.get() ? v.get() + r0 : nullptr, nullptr);
+    });
+  }
   p.commit(); dd.commit(); v.commit();
   sync_stream();
   LB2_API_END
@@ -875,28 +1139,22 @@ lb2_status lb2_ivfpq_transform(const void* centroids, uint32_t k, const void* co
   LB2_REQUIRE(num_bits == 8 || M % 2 == 0, "PQ: num_sub_vectors must be divisible by 2 for num_bits=4, but got %d", M);
   if (!small_d_supported(ds)) fail(LB2_UNSUPPORTED, "PQ sub-vector width %d not supported yet", ds);
   const int m = metric_of(metric);
-  VecIn c(centroids, (size_t)k * d, model_dtype(dtype)), cb(codebook, ((size_t)1 << num_bits) * d, model_dtype(dtype)),
-      x(vectors, (size_t)n * d, dtype);
+  VecIn c(centroids, (size_t)k * d, model_dtype(dtype)), cb(codebook, ((size_t)1 << num_bits) * d, model_dtype(dtype));
+  const size_t cw = num_bits == 4 ? M / 2 : M;
   OutArg<uint32_t> p(part_out, n);
-  OutArg<uint8_t> co(codes_out, (size_t)n * (num_bits == 4 ? M / 2 : M)), v(valid_out, n);
+  OutArg<uint8_t> co(codes_out, (size_t)n * cw), v(valid_out, n);
   DevBuf<uint8_t> vtmp;
   uint8_t* vp = v.get();
   if (!vp) { vtmp.alloc(std::max<uint64_t>(n, 1)); vp = vtmp.p; }
-  const float* xp = x.get();
-  DevBuf<float> xn;
-  if (m == METRIC_COSINE) {  // ivf.rs:198-205: normalise, then L2
-    xn.alloc((size_t)n * d);
-    if (n) LB2_LAUNCH("normalize", normalize_kernel, cdiv(n, 128), 128, 0, xp, n, (int)d, xn.p);
-    xp = xn.p;
+  if (n) {
+    Source src(vectors, n, (int)d, dtype);
+    src.start_resident_copy();
+    DevBuf<float> normbuf;
+    for_each_chunk(src, [&](const float* xf, uint64_t r0, uint64_t rows) {
+      transform_chunk(xf, rows, (int)d, m, c.get(), (int)k, cb.get(), M, (int)num_bits, normbuf, p.get() + r0,
+                      co.get() + r0 * cw, vp + r0);
+    });
   }
-  const int am = m == METRIC_DOT ? METRIC_DOT : METRIC_L2;
-  assign_f32(xp, n, d, c.get(), k, am, nullptr, p.get(), nullptr, vp, nullptr);
-  // The quantizer of an index build is trained -- and therefore encodes -- with L2 whatever the index
-  // metric is: Q::build(&training_data, DistanceType::L2, ..) (rust/lance/src/index/vector/builder.rs:460);
-  // the index metric only decides the partition assignment, whether residuals are taken (not for dot,
-  // PQBuildParams::use_residual) and the query-time lookup table.
-  pq_encode_any(xp, n, d, M, ds, cb.get(), METRIC_L2, am == METRIC_DOT ? nullptr : c.get(),
-                am == METRIC_DOT ? nullptr : p.get(), vp, (int)num_bits, co.get());
   p.commit(); co.commit(); v.commit();
   sync_stream();
   LB2_API_END
@@ -980,7 +1238,7 @@ static void index_search_impl(lb2_index* index, const void* queries, uint64_t nq
   const ScanFilter flt = make_filter(allow_bitmap ? allow.get() : nullptr, has_lower, lower, has_upper, upper);
   if (index->kind == 1)
     ivfflat_search_f32(index->centroids.p, index->K, d, index->metric, index->part_offsets.p, index->vectors.p,
-                       index->row_ids.p, qp, nq, (int)kc, nprobes, si, sd, sc, flt);
+                       (int)index->vdtype(), index->row_ids.p, qp, nq, (int)kc, nprobes, si, sd, sc, flt);
   else
     ivfpq_search_f32(index->centroids.p, index->K, d, index->metric, index->codebook.p, index->M, index->nbits,
                      index->part_offsets.p, index->codes.p, index->row_ids.p, qp, nq, (int)kc, nprobes, si, sd,
@@ -988,9 +1246,9 @@ static void index_search_impl(lb2_index* index, const void* queries, uint64_t nq
   if (refine) {
     // exact re-rank with the true metric on the ORIGINAL (un-normalised) query, as flat_knn does; the
     // plan then filters `_distance >= lower AND _distance < upper` on the exact distances (scanner.rs:3342-3377)
-    VecIn v(vectors, (size_t)num_vectors * d, index->dtype);
-    refine_f32(q.get(), nq, d, index->metric, v.get(), num_vectors, cid.p, ccnt.p, (int)kc, (int)k, oi.get(),
-               od.get(), oc.get(), has_lower, lower, has_upper, upper);
+    InArg<uint8_t> v(vectors, (size_t)num_vectors * d * dtype_size(index->dtype));  // raw column, native type
+    refine_f32(q.get(), nq, d, index->metric, v.get(), (int)index->dtype, num_vectors, cid.p, ccnt.p, (int)kc, (int)k,
+               oi.get(), od.get(), oc.get(), has_lower, lower, has_upper, upper);
     oi.commit(); od.commit(); oc.commit();
     sync_stream();
     return;
@@ -1141,11 +1399,13 @@ lb2_status lb2_index_load_flat(lb2_index* index, const uint32_t* part_ids, const
                                const uint64_t* row_ids, uint64_t n) {
   LB2_API_BEGIN
   LB2_REQUIRE(index && index->kind == 1, "not an IVF_FLAT index");
+  LB2_REQUIRE(index->d % 4 == 0, "IVF_FLAT needs a dimension that is a multiple of 4");
   InArg<uint32_t> p(part_ids, n);
-  VecIn v(vectors, (size_t)n * index->d, index->dtype);
   InArg<uint64_t> r(row_ids, n);
   check_part_ids(p.get(), n, (uint32_t)index->K, "index_load_flat");
-  index_load_flat_dev(index, p.get(), v.get(), r.get(), n);
+  Source src(vectors, n, index->d, index->dtype);
+  src.start_resident_copy();
+  index_load_flat_src(index, p.get(), src, r.get(), nullptr, /*normalize=*/false);
   LB2_API_END
 }
 
@@ -1160,7 +1420,7 @@ lb2_status lb2_index_export_flat(const lb2_index* index, void* centroids_out,
   if (part_offsets_out)
     LB2_CUDA(cudaMemcpyAsync(part_offsets_out, index->part_offsets.p, sizeof(uint64_t) * (index->K + 1), cudaMemcpyDefault, s));
   if (vectors_out && index->n)
-    LB2_CUDA(cudaMemcpyAsync(vectors_out, index->vectors.p, sizeof(float) * index->n * index->d, cudaMemcpyDefault, s));
+    LB2_CUDA(cudaMemcpyAsync(vectors_out, index->vectors.p, index->n * index->vrow_bytes(), cudaMemcpyDefault, s));
   if (row_ids_out && index->n)
     LB2_CUDA(cudaMemcpyAsync(row_ids_out, index->row_ids.p, sizeof(uint64_t) * index->n, cudaMemcpyDefault, s));
   sync_stream();
@@ -1206,6 +1466,7 @@ lb2_status lb2_ivfflat_build(const void* data, uint64_t n, uint32_t d, lb2_dtype
                              const uint64_t* row_ids, lb2_index** out, lb2_build_stats* stats) {
   LB2_API_BEGIN
   LB2_REQUIRE(data && params && out, "null argument");
+  LB2_REQUIRE(d % 4 == 0, "IVF_FLAT needs a dimension that is a multiple of 4");
   const int m = metric_of(metric);
   const int K = params->num_partitions;
   const uint64_t nranks = current_comm() ? current_comm()->nranks : 1;
@@ -1213,14 +1474,7 @@ lb2_status lb2_ivfflat_build(const void* data, uint64_t n, uint32_t d, lb2_dtype
               (unsigned long long)n);
   EventSet ev(4);
   ev.record(0);
-  VecIn xin(data, (size_t)n * d, dtype);
-  const float* x = xin.get();
-  DevBuf<float> xnorm;
-  if (m == METRIC_COSINE) {  // NormalizeTransformer first (ivf.rs:158-166); stored vectors are normalised
-    xnorm.alloc((size_t)n * d);
-    LB2_LAUNCH("normalize", normalize_kernel, cdiv(n, 128), 128, 0, x, n, (int)d, xnorm.p);
-    x = xnorm.p;
-  }
+  Source src(data, n, (int)d, dtype);
   const int am = m == METRIC_DOT ? METRIC_DOT : METRIC_L2;
   std::unique_ptr<lb2_index> ix(new lb2_index());
   ix->kind = 1; ix->K = K; ix->d = d; ix->M = 0; ix->nbits = 0; ix->metric = m; ix->dtype = dtype;
@@ -1232,24 +1486,35 @@ lb2_status lb2_ivfflat_build(const void* data, uint64_t n, uint32_t d, lb2_dtype
     const uint64_t s0 = std::min<uint64_t>(n, ((uint64_t)K * params->ivf.sample_rate + nranks - 1) / nranks);
     std::vector<uint64_t> rows = sample_rows(n, s0, params->seed);
     DevBuf<float> sample;
-    const uint64_t s = gather_finite_sample(x, rows, (int)d, sample);
+    const uint64_t s = gather_finite_sample(src, rows, m == METRIC_COSINE, sample);
+    src.start_resident_copy();  // host rows: the bulk copy runs on its own stream while the centroids train
     LB2_REQUIRE(nranks > 1 || s >= (uint64_t)K, "KMeans: can not train %d centroids with %llu finite vectors", K,
                 (unsigned long long)s);
     VecIn init(params->ivf.init_centroids, (size_t)K * d, model_dtype(dtype));
     train_ivf(sample.p, s, d, K, am, params->ivf, nranks, init.get(), ix->centroids.p, &loss, &iters);
+    round_model(ix->centroids.p, (size_t)K * d, dtype);
   }
   ev.record(1);
   DevBuf<uint32_t> part(std::max<uint64_t>(n, 1));
   DevBuf<uint8_t> valid(std::max<uint64_t>(n, 1));
   {
     TagScope tg("transform");
-    assign_f32(x, n, d, ix->centroids.p, K, am, nullptr, part.p, nullptr, valid.p, nullptr);
+    DevBuf<float> normbuf;
+    for_each_chunk(src, [&](const float* xf, uint64_t r0, uint64_t rows) {
+      const float* xp = xf;
+      if (m == METRIC_COSINE) {  // NormalizeTransformer first (ivf.rs:158-166)
+        if (normbuf.n < (size_t)rows * d) normbuf.alloc((size_t)rows * d);
+        LB2_LAUNCH("normalize", normalize_kernel, cdiv(rows, 128), 128, 0, xf, rows, (int)d, normbuf.p);
+        xp = normbuf.p;
+      }
+      assign_f32(xp, rows, d, ix->centroids.p, K, am, nullptr, part.p + r0, nullptr, valid.p + r0, nullptr);
+    });
   }
   ev.record(2);
   InArg<uint64_t> rid(row_ids, n);
   {
-    TagScope tg("group");
-    index_load_flat_dev(ix.get(), part.p, x, rid.get(), n, valid.p);
+    TagScope tg("group");  // the stored vectors are the normalised ones when the metric is cosine
+    index_load_flat_src(ix.get(), part.p, src, rid.get(), valid.p, m == METRIC_COSINE);
   }
   ev.record(3);
   sync_stream();
@@ -1292,59 +1557,15 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
   LB2_REQUIRE(nbits == 8 || M % 2 == 0, "PQ: num_sub_vectors must be divisible by 2 for num_bits=4, but got %d", M);
   const int ds = d / M;
   if (!small_d_supported(ds)) fail(LB2_UNSUPPORTED, "PQ sub-vector width %d not supported yet", ds);
-  Ctx& c = ctx();
   EventSet ev(5);
   ev.record(0);
 
-  // Staging.  Device pointer: used in place.  PINNED host pointer (L2 / dot): the bulk H2D copy runs
-  // on a second stream (copy engine) while both training phases gather their <= 65 536-row samples
-  // straight out of the pinned buffer (zero-copy reads over PCIe), so the 0.5 GB copy hides behind
-  // training; the transform waits on the copy.  Pageable host pointer: plain staged copy first.
-  VecIn xin;
-  DevBuf<float> xbulk;
-  const float* x = nullptr;         // complete device copy (valid after `copied`)
-  const float* x_sample = nullptr;  // what the training samples are gathered from
-  cudaEvent_t copied = nullptr;
-  cudaStream_t copy_stream = nullptr;
-  {
-    cudaPointerAttributes pa;
-    const bool attr_ok = cudaPointerGetAttributes(&pa, data) == cudaSuccess;
-    if (!attr_ok) cudaGetLastError();
-    if (attr_ok && pa.type == cudaMemoryTypeHost && pa.devicePointer && m != METRIC_COSINE && dtype == LB2_F32) {
-      xbulk.alloc((size_t)n * d);
-      LB2_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-      LB2_CUDA(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
-      x = xbulk.p;  // the copy itself is issued after the two sample gathers (start_bulk_copy below):
-                    // zero-copy reads get no PCIe bandwidth while the copy engine is streaming
-      x_sample = static_cast<const float*>(pa.devicePointer);
-    } else {
-      xin.set(data, (size_t)n * d, dtype);
-      x = xin.get();
-      x_sample = x;
-    }
-  }
-  struct CopyGuard {  // never leave the copy stream / event behind, also on errors
-    cudaStream_t& s; cudaEvent_t& e;
-    ~CopyGuard() {
-      if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
-      if (e) cudaEventDestroy(e);
-    }
-  } copy_guard{copy_stream, copied};
-  auto start_bulk_copy = [&]() {
-    if (!copy_stream) return;
-    // ordered after everything issued so far on c.stream (pool allocation, sample gathers)
-    LB2_CUDA(cudaEventRecord(copied, c.stream));
-    LB2_CUDA(cudaStreamWaitEvent(copy_stream, copied, 0));
-    LB2_CUDA(cudaMemcpyAsync(xbulk.p, data, sizeof(float) * (size_t)n * d, cudaMemcpyHostToDevice, copy_stream));
-    LB2_CUDA(cudaEventRecord(copied, copy_stream));
-  };
-  DevBuf<float> xnorm;
-  if (m == METRIC_COSINE) {  // normalise once; the reference normalises samples and every batch
-    xnorm.alloc((size_t)n * d);
-    LB2_LAUNCH("normalize", normalize_kernel, cdiv(n, 128), 128, 0, x, n, (int)d, xnorm.p);
-    x = xnorm.p;
-    x_sample = x;
-  }
+  // Staging (class Source).  Device rows: used in place.  Host rows: both training samples (<= K * 256 and
+  // 65 536 rows) are gathered straight out of the caller's memory (zero-copy reads over PCIe when it is pinned),
+  // then the matrix is copied ONCE, in its own element type, on a second stream while both trainings run; the
+  // per-row pass waits for it and converts one chunk of rows at a time.  A matrix too large for that is streamed
+  // chunk by chunk during the per-row pass instead (double buffered).  No whole-matrix f32 copy exists.
+  Source src(data, n, (int)d, dtype);
   const int am = m == METRIC_DOT ? METRIC_DOT : METRIC_L2;
 
   std::unique_ptr<lb2_index> ix(new lb2_index());
@@ -1354,27 +1575,29 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
   std::vector<double> ivf_loss;
   std::vector<uint32_t> ivf_iters, pq_iters;
   // 0. both training samples are gathered first (IVF: K*sample_rate rows, rust/lance/src/index/
-  //    vector/ivf.rs:1237-1241; PQ: 256*2^nbits rows, builder.rs:410-421), rows that are not finite are
-  //    dropped from them (builder.rs:436), then the bulk copy starts
+  //    vector/ivf.rs:1237-1241; PQ: 256*2^nbits rows, builder.rs:410-421), normalised for cosine; rows that are
+  //    not finite are dropped from them (builder.rs:436); then the bulk copy starts
   const uint64_t s_ivf0 = std::min<uint64_t>(n, ((uint64_t)K * params->ivf.sample_rate + nranks - 1) / nranks);
   const uint64_t s_pq0 = std::min<uint64_t>(n, (params->pq.sample_rate * ((uint64_t)1 << nbits) + nranks - 1) / nranks);
   DevBuf<float> sample_ivf, sample_pq;
   uint64_t s_ivf = 0, s_pq = 0;
   {
     std::vector<uint64_t> rows = sample_rows(n, s_ivf0, params->seed);
-    s_ivf = gather_finite_sample(x_sample, rows, (int)d, sample_ivf);
+    s_ivf = gather_finite_sample(src, rows, m == METRIC_COSINE, sample_ivf);
     rows = sample_rows(n, s_pq0, params->seed + 1);
-    s_pq = gather_finite_sample(x_sample, rows, (int)d, sample_pq);
+    s_pq = gather_finite_sample(src, rows, m == METRIC_COSINE, sample_pq);
   }
   LB2_REQUIRE(nranks > 1 || s_ivf >= (uint64_t)K, "KMeans: can not train %d centroids with %llu finite vectors", K,
               (unsigned long long)s_ivf);
-  start_bulk_copy();
+  src.start_resident_copy();
   // 1. IVF
   {
     TagScope tg("ivf_train");
     VecIn init(params->ivf.init_centroids, (size_t)K * d, model_dtype(dtype));
     train_ivf(sample_ivf.p, s_ivf, d, K, am, params->ivf, nranks, init.get(), ix->centroids.p, &ivf_loss, &ivf_iters);
+    round_model(ix->centroids.p, (size_t)K * d, dtype);
   }
+  sample_ivf.release();
   ev.record(1);
   // 2. PQ: residuals of its sample w.r.t. the IVF centroids (builder.rs:439-450)
   {
@@ -1391,17 +1614,21 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
     // always L2 k-means (builder.rs:460: Q::build(&training_data, DistanceType::L2, ..)); for a dot index
     // the sample is the raw vectors (no residual), for L2 / cosine the residuals computed above
     pq_train_dev(sample_pq.p, s_pq, d, METRIC_L2, &pqp, ix->codebook.p, &pq_iters);
+    round_model(ix->codebook.p, ix->codebook_len(), dtype);
   }
+  sample_pq.release();
   ev.record(2);
-  // 3. transform every row (lance-index/src/vector/ivf.rs:357: partition -> residual -> PQ)
+  // 3. transform every row (lance-index/src/vector/ivf.rs:357: partition -> residual -> PQ), chunk by chunk
   DevBuf<uint32_t> part(std::max<uint64_t>(n, 1));
   DevBuf<uint8_t> codes(std::max<uint64_t>(1, (size_t)n * ix->code_bytes())), valid(std::max<uint64_t>(n, 1));
-  if (copied) LB2_CUDA(cudaStreamWaitEvent(c.stream, copied, 0));  // the bulk copy must have landed
   {
     TagScope tg("transform");
-    assign_f32(x, n, d, ix->centroids.p, K, am, nullptr, part.p, nullptr, valid.p, nullptr);
-    pq_encode_any(x, n, d, M, ds, ix->codebook.p, METRIC_L2, am == METRIC_DOT ? nullptr : ix->centroids.p,
-                  am == METRIC_DOT ? nullptr : part.p, valid.p, nbits, codes.p);  // L2 codes: see lb2_ivfpq_transform
+    DevBuf<float> normbuf;
+    const size_t cw = ix->code_bytes();
+    for_each_chunk(src, [&](const float* xf, uint64_t r0, uint64_t rows) {
+      transform_chunk(xf, rows, (int)d, m, ix->centroids.p, K, ix->codebook.p, M, nbits, normbuf, part.p + r0,
+                      codes.p + r0 * cw, valid.p + r0);
+    });
   }
   ev.record(3);
   {

@@ -12,6 +12,9 @@
 // 128-bit loads, each row's distance is the reference's m-ascending f32 sum (bit-exact), and
 // warp-level sorting networks (k <= 16) or a block radix select produce the k smallest (distance,
 // position) pairs.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "assign.cuh"
 #include "comm.cuh"
 #include "common.cuh"
@@ -769,14 +772,21 @@ ivfpq_scan_kernel(const ScanArgs a, uint32_t* __restrict__ rlist, uint32_t* __re
 // dot results are bit-identical to l2.rs:57-91 / dot.rs:30-58; cosine follows cosine.rs:143-174 in
 // structure (f32 FMA lanes) and is checked to the reference's own tolerance.
 // ------------------------------------------------------------------------------------------------
-template <int METRIC>
-__device__ __forceinline__ float flat_row_distance(const float* __restrict__ q, const float* __restrict__ v,
+// element of a stored / raw vector as f32 (l2.rs:100-106,156: f16 / bf16 elements are converted one by one)
+template <class T> __device__ __forceinline__ float ldf(const T* p, int e);
+template <> __device__ __forceinline__ float ldf<float>(const float* p, int e) { return p[e]; }
+template <> __device__ __forceinline__ float ldf<__half>(const __half* p, int e) { return __half2float(p[e]); }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p, int e) { return __bfloat162float(p[e]); }
+template <> __device__ __forceinline__ float ldf<uint8_t>(const uint8_t* p, int e) { return (float)p[e]; }
+
+template <int METRIC, class T = float>
+__device__ __forceinline__ float flat_row_distance(const float* __restrict__ q, const T* __restrict__ v,
                                                    int d, int l, unsigned mask, float q_norm) {
   const int n16 = d & ~15;
   if (METRIC == METRIC_COSINE) {
     float xy = 0.0f, yy = 0.0f;
     for (int e = l; e < d; e += 16) {
-      const float y = v[e];
+      const float y = ldf<T>(v, e);
       xy = fmaf(q[e], y, xy);
       yy = fmaf(y, y, yy);
     }
@@ -788,20 +798,20 @@ __device__ __forceinline__ float flat_row_distance(const float* __restrict__ q, 
     return 1.0f - xy / q_norm / sqrtf(yy);
   }
   float acc = 0.0f;
-  for (int e = l; e < n16; e += 16) acc = f_add(acc, term<METRIC>(q[e], v[e]));
+  for (int e = l; e < n16; e += 16) acc = f_add(acc, term<METRIC>(q[e], ldf<T>(v, e)));
   float s = 0.0f;  // sequential tail, every lane redundantly (l2.rs:69-79)
-  for (int e = n16; e < d; ++e) s = f_add(s, term<METRIC>(q[e], v[e]));
+  for (int e = n16; e < d; ++e) s = f_add(s, term<METRIC>(q[e], ldf<T>(v, e)));
   float t = 0.0f;
 #pragma unroll
   for (int qq = 0; qq < 16; ++qq) t = f_add(t, __shfl_sync(mask, acc, qq, 16));
   return finish<METRIC>(f_add(s, t));
 }
 
-template <int METRIC>
+template <int METRIC, class T>
 __global__ void __launch_bounds__(256)
 ivfflat_scan_kernel(const float* __restrict__ queries, int d, const uint32_t* __restrict__ probe_ids,
                     int np, const uint64_t* __restrict__ part_offsets,
-                    const float* __restrict__ vectors, const uint64_t* __restrict__ row_ids, int k,
+                    const T* __restrict__ vectors, const uint64_t* __restrict__ row_ids, int k,
                     float* __restrict__ cand_d, uint64_t* __restrict__ cand_id,
                     uint32_t* __restrict__ cand_cnt, const ScanFilter flt) {
   extern __shared__ float smem[];
@@ -852,7 +862,7 @@ ivfflat_scan_kernel(const float* __restrict__ queries, int d, const uint32_t* __
         if (l == 0) cd[j] = excluded_key;
         continue;
       }
-      const float dist = flat_row_distance<METRIC>(qs, vectors + (off + c0 + j) * (uint64_t)d, d, l, hmask, qn);
+      const float dist = flat_row_distance<METRIC, T>(qs, vectors + (off + c0 + j) * (uint64_t)d, d, l, hmask, qn);
       if (l == 0) cd[j] = key_in_range(flt, total_order_key(dist)) ? dist : excluded_key;
     }
     __syncthreads();
@@ -931,7 +941,7 @@ ivfflat_scan_kernel(const float* __restrict__ queries, int d, const uint32_t* __
   for (uint32_t c0 = 0; c0 < n_p; c0 += SCAN_CHUNK) {
     const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
     for (uint32_t j = tid >> 4; j < clen; j += 16) {
-      const float dist = flat_row_distance<METRIC>(qs, vectors + (off + c0 + j) * (uint64_t)d, d, l, hmask, qn);
+      const float dist = flat_row_distance<METRIC, T>(qs, vectors + (off + c0 + j) * (uint64_t)d, d, l, hmask, qn);
       if (l == 0) cd[j] = dist;
     }
     __syncthreads();
@@ -1241,7 +1251,7 @@ void row_mask_f32(const uint64_t* row_ids, uint64_t n, const uint64_t* allow, ui
 }
 
 void ivfflat_search_f32(const float* centroids, int K, int d, int metric, const uint64_t* part_offsets,
-                        const float* vectors, const uint64_t* row_ids, const float* queries, uint64_t nq,
+                        const void* vectors, int vdt, const uint64_t* row_ids, const float* queries, uint64_t nq,
                         int k, int nprobes, uint64_t* out_ids, float* out_dists, uint32_t* out_counts,
                         const ScanFilter& flt) {
   if (nq == 0 || k == 0) return;
@@ -1258,16 +1268,23 @@ void ivfflat_search_f32(const float* centroids, int K, int d, int metric, const 
   for (uint64_t q0 = 0; q0 < nq; q0 += 32768) {
     const uint64_t qn = std::min<uint64_t>(32768, nq - q0);
     dim3 g(np, (unsigned)qn);
+#define LB2_FLAT_T(MET, TT)                                                                             \
+    {                                                                                                   \
+      set_smem((ivfflat_scan_kernel<MET, TT>), smem);                                                   \
+      LB2_LAUNCH("flat_scan", (ivfflat_scan_kernel<MET, TT>), g, 256, smem, queries + q0 * d, d,         \
+                 pids.p + q0 * np, np, part_offsets, reinterpret_cast<const TT*>(vectors), row_ids, k,   \
+                 cand_d.p + q0 * np * k, cand_id.p + q0 * np * k, cand_cnt.p + q0 * np, flt);            \
+    }
 #define LB2_FLAT(MET)                                                                                   \
     {                                                                                                   \
-      set_smem(ivfflat_scan_kernel<MET>, smem);                                                         \
-      LB2_LAUNCH("flat_scan", (ivfflat_scan_kernel<MET>), g, 256, smem, queries + q0 * d, d,             \
-                 pids.p + q0 * np, np, part_offsets, vectors, row_ids, k, cand_d.p + q0 * np * k,        \
-                 cand_id.p + q0 * np * k, cand_cnt.p + q0 * np, flt);                                    \
+      if (vdt == LB2_F16) LB2_FLAT_T(MET, __half)                                                       \
+      else if (vdt == LB2_BF16) LB2_FLAT_T(MET, __nv_bfloat16)                                          \
+      else LB2_FLAT_T(MET, float)                                                                       \
     }
     if (metric == METRIC_DOT) LB2_FLAT(METRIC_DOT)
     else if (metric == METRIC_COSINE) LB2_FLAT(METRIC_COSINE)
     else LB2_FLAT(METRIC_L2)
+#undef LB2_FLAT_T
 #undef LB2_FLAT
   }
   LB2_LAUNCH("merge_topk", merge_kernel, (unsigned)nq, 128, 0, cand_d.p, cand_id.p, cand_cnt.p, np,
@@ -1278,9 +1295,9 @@ void ivfflat_search_f32(const float* centroids, int K, int d, int metric, const 
 // refine: exact distances of k' = k * refine_factor candidates from the raw vectors, then the k
 // best by (distance, row id)  (scanner.rs:2884-2905, flat.rs:95-148)
 // ------------------------------------------------------------------------------------------------
-template <int METRIC>
+template <int METRIC, class T>
 __global__ void __launch_bounds__(256)
-refine_kernel(const float* __restrict__ queries, int d, const float* __restrict__ vectors,
+refine_kernel(const float* __restrict__ queries, int d, const T* __restrict__ vectors,
               uint64_t num_vectors, const uint64_t* __restrict__ cand_id, const uint32_t* __restrict__ cand_cnt,
               int kc, int k, uint64_t* __restrict__ out_id, float* __restrict__ out_d,
               uint32_t* __restrict__ out_cnt, int has_lower, float lower, int has_upper, float upper) {
@@ -1312,7 +1329,7 @@ refine_kernel(const float* __restrict__ queries, int d, const float* __restrict_
   for (uint32_t c = tid >> 4; c < cnt; c += 16) {
     const uint64_t id = ids[c];
     float dist = __int_as_float(0x7fc00000);
-    if (id < num_vectors) dist = flat_row_distance<METRIC>(qs, vectors + id * (uint64_t)d, d, l, hmask, qn);
+    if (id < num_vectors) dist = flat_row_distance<METRIC, T>(qs, vectors + id * (uint64_t)d, d, l, hmask, qn);
     if (l == 0) cd[c] = dist;
   }
   __syncthreads();
@@ -1354,22 +1371,30 @@ refine_kernel(const float* __restrict__ queries, int d, const float* __restrict_
   if (tid == 0 && out_cnt) out_cnt[qi] = r;
 }
 
-void refine_f32(const float* queries, uint64_t nq, int d, int metric, const float* vectors,
+void refine_f32(const float* queries, uint64_t nq, int d, int metric, const void* vectors, int vdt,
                 uint64_t num_vectors, const uint64_t* cand_id, const uint32_t* cand_cnt, int kc, int k,
                 uint64_t* out_id, float* out_d, uint32_t* out_cnt, int has_lower, float lower, int has_upper,
                 float upper) {
   if (nq == 0) return;
   const size_t smem = sizeof(float) * ((size_t)d + kc);
+#define LB2_REF_T(MET, TT)                                                                           \
+  {                                                                                                   \
+    set_smem((refine_kernel<MET, TT>), smem);                                                         \
+    LB2_LAUNCH("refine", (refine_kernel<MET, TT>), (unsigned)nq, 256, smem, queries, d,                \
+               reinterpret_cast<const TT*>(vectors), num_vectors, cand_id, cand_cnt, kc, k, out_id,    \
+               out_d, out_cnt, has_lower, lower, has_upper, upper);                                    \
+  }
 #define LB2_REF(MET)                                                                                  \
   {                                                                                                   \
-    set_smem(refine_kernel<MET>, smem);                                                               \
-    LB2_LAUNCH("refine", (refine_kernel<MET>), (unsigned)nq, 256, smem, queries, d, vectors,           \
-               num_vectors, cand_id, cand_cnt, kc, k, out_id, out_d, out_cnt, has_lower, lower,        \
-               has_upper, upper);                                                                      \
+    if (vdt == LB2_F16) LB2_REF_T(MET, __half)                                                        \
+    else if (vdt == LB2_BF16) LB2_REF_T(MET, __nv_bfloat16)                                           \
+    else if (vdt == LB2_U8) LB2_REF_T(MET, uint8_t)                                                   \
+    else LB2_REF_T(MET, float)                                                                        \
   }
   if (metric == METRIC_DOT) LB2_REF(METRIC_DOT)
   else if (metric == METRIC_COSINE) LB2_REF(METRIC_COSINE)
   else LB2_REF(METRIC_L2)
+#undef LB2_REF_T
 #undef LB2_REF
 }
 

@@ -23,8 +23,9 @@ void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const fl
                       const uint64_t* row_ids, const float* queries, uint64_t nq, int k, int nprobes,
                       uint64_t* out_ids, float* out_dists, uint32_t* out_counts,
                       const ScanFilter& flt = ScanFilter());
+// vectors: the index's rows in element type vdt (lb2_dtype: f32 / f16 / bf16)
 void ivfflat_search_f32(const float* centroids, int K, int d, int metric, const uint64_t* part_offsets,
-                        const float* vectors, const uint64_t* row_ids, const float* queries, uint64_t nq,
+                        const void* vectors, int vdt, const uint64_t* row_ids, const float* queries, uint64_t nq,
                         int k, int nprobes, uint64_t* out_ids, float* out_dists, uint32_t* out_counts,
                         const ScanFilter& flt = ScanFilter());
 // all ranks' [nq][k] results of a row-sharded index -> the global top-k by (distance, row id) on every rank
@@ -33,7 +34,7 @@ void merge_sharded_topk(const uint64_t* ids, const float* dists, const uint32_t*
 // bit i of bitmap = RowIdMask::selected(row_ids[i]) (lance-core/src/utils/mask.rs:84-93); lists sorted
 void row_mask_f32(const uint64_t* row_ids, uint64_t n, const uint64_t* allow, uint64_t n_allow, bool has_allow,
                   const uint64_t* block, uint64_t n_block, bool has_block, uint64_t* bitmap);
-void refine_f32(const float* queries, uint64_t nq, int d, int metric, const float* vectors,
+void refine_f32(const float* queries, uint64_t nq, int d, int metric, const void* vectors, int vdt,
                 uint64_t num_vectors, const uint64_t* cand_id, const uint32_t* cand_cnt, int kc, int k,
                 uint64_t* out_id, float* out_d, uint32_t* out_cnt, int has_lower = 0, float lower = 0.0f,
                 int has_upper = 0, float upper = 0.0f);

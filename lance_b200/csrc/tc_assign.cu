@@ -646,7 +646,9 @@ static void tc_refine_and_fallback(const float* x, uint64_t n, int d, const floa
                                                     std::max<uint64_t>(TM, ((size_t)3 << 29) / ((size_t)d3 * 4)));
   const GenLayout L = gen_layout();
   const size_t smem = L.total + 1024;
-  const bool refine = !no_refine && smem <= ctx().smem_optin;
+  // worth its four launches only when the first pass was a large one (the undecided list of a 65 536-row
+  // training call is a few hundred rows: the exact kernel finishes them sooner)
+  const bool refine = !no_refine && smem <= ctx().smem_optin && (uint64_t)n * (uint64_t)K >= (1ull << 26);
   if (!refine) {
     assign_rows_f32(x, n, d, cent, K, METRIC_L2, bias, ws->fb_rows.p, ws->fb_count.p, part, dist, valid, active, ws,
                     cT_ready);

@@ -31,9 +31,10 @@ namespace {
 // small helpers
 // ---------------------------------------------------------------------------------------------
 // Persistent worker pool (the reference runs these loops on rayon's global pool: threads are created once
-// and parked between jobs, rust/lance-index/src/vector/kmeans.rs:335-356 `par_chunks`).  Workers spin
-// briefly for the next job before sleeping, like rayon's, so that the ~100 short parallel regions of a
-// k-means run do not each pay thread start-up.  Per-row results are independent of the schedule.
+// and parked between jobs, rust/lance-index/src/vector/kmeans.rs:335-356 `par_chunks`).  Like rayon's
+// workers, ours SPIN for the next job for a while before they sleep, and a job is published with two atomic
+// stores (no lock, no wake-up storm): the ~1000 short parallel regions of a k-means run (one per Lloyd
+// iteration and sub-space) pay microseconds, not thread start-up.  Per-row results do not depend on the schedule.
 class Pool {
  public:
   static Pool& get() {
@@ -42,10 +43,11 @@ class Pool {
   }
   template <class F>
   void run(size_t n, int nthreads, F&& f) {
-    std::lock_guard<std::mutex> run_lock(run_mu_);  // one job at a time (callers are not concurrent in practice)
-    const size_t nt = std::min<size_t>(size_t(nthreads), n);
-    ensure(nt - 1);
-    const size_t chunk = std::max<size_t>(1, n / (nt * 16));
+    std::lock_guard<std::mutex> run_lock(run_mu_);  // one job at a time
+    const size_t nt = std::min<size_t>(std::min<size_t>(size_t(nthreads), n), 4096);
+    const size_t helpers = nt - 1;
+    ensure(helpers);
+    const size_t chunk = std::max<size_t>(1, n / (nt * 8));
     std::atomic<size_t> next{0};
     std::function<void()> body = [&] {
       for (;;) {
@@ -54,71 +56,77 @@ class Pool {
         f(b, std::min(n, b + chunk));
       }
     };
-    {
+    body_ = &body;
+    done_.store(0, std::memory_order_relaxed);
+    const uint64_t g = (state_.load(std::memory_order_relaxed) >> 16) + 1;
+    state_.store((g << 16) | uint64_t(helpers), std::memory_order_release);  // publish (generation, helpers)
+    if (sleepers_.load(std::memory_order_acquire) > 0) {
       std::lock_guard<std::mutex> lk(mu_);
-      job_ = &body;
-      want_ = nt - 1;
-      taken_ = 0;
-      done_ = 0;
-      ++gen_;
+      cv_.notify_all();
     }
-    cv_.notify_all();
     body();
-    // wait for the helpers that picked the job up
-    for (int spin = 0;; ++spin) {
-      if (done_.load(std::memory_order_acquire) == want_) break;
-      if (spin > 2000) std::this_thread::yield();
-    }
-    std::lock_guard<std::mutex> lk(mu_);
-    job_ = nullptr;
+    while (done_.load(std::memory_order_acquire) != helpers) cpu_relax();  // every helper reports, late ones too
   }
 
  private:
   Pool() = default;
   ~Pool() {
+    stop_.store(true);
     {
       std::lock_guard<std::mutex> lk(mu_);
-      stop_ = true;
-      ++gen_;
+      state_.fetch_add(uint64_t(1) << 16);
+      cv_.notify_all();
     }
-    cv_.notify_all();
     for (auto& t : th_) t.join();
   }
-  void ensure(size_t helpers) {
-    while (th_.size() < helpers) th_.emplace_back([this, id = th_.size()] { worker(id); });
+  static void cpu_relax() {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
   }
-  void worker(size_t id) {
-    uint64_t seen = 0;
+  void ensure(size_t helpers) {
+    while (th_.size() < helpers) {
+      const size_t id = th_.size();
+      const uint64_t start_gen = state_.load() >> 16;
+      th_.emplace_back([this, id, start_gen] { worker(id, start_gen); });
+    }
+  }
+  void worker(size_t id, uint64_t seen) {
     for (;;) {
-      std::function<void()>* job = nullptr;
-      {
-        // spin a little on the generation counter before blocking
-        for (int spin = 0; spin < 4000 && gen_relaxed() == seen; ++spin) {
+      uint64_t st = state_.load(std::memory_order_acquire);
+      int spins = 0;
+      while ((st >> 16) == seen) {
+        if (++spins < 20000) {  // ~0.2 ms of polling: the next parallel region is usually that close
+          cpu_relax();
+        } else {
+          sleepers_.fetch_add(1, std::memory_order_acq_rel);
+          {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return (state_.load(std::memory_order_acquire) >> 16) != seen; });
+          }
+          sleepers_.fetch_sub(1, std::memory_order_acq_rel);
+          spins = 0;
         }
-        std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return gen_ != seen; });
-        seen = gen_;
-        if (stop_) return;
-        if (job_ && id < want_) {
-          job = job_;
-          ++taken_;
-        }
+        st = state_.load(std::memory_order_acquire);
       }
-      if (job) {
-        (*job)();
+      seen = st >> 16;
+      if (stop_.load()) return;
+      if (id < (st & 0xffff)) {  // this generation wants helpers 0 .. (st & 0xffff) - 1
+        (*body_)();
         done_.fetch_add(1, std::memory_order_release);
       }
     }
   }
-  uint64_t gen_relaxed() { return gen_.load(std::memory_order_relaxed); }
   std::mutex mu_, run_mu_;
   std::condition_variable cv_;
   std::vector<std::thread> th_;
-  std::function<void()>* job_ = nullptr;
-  size_t want_ = 0, taken_ = 0;
+  std::function<void()>* body_ = nullptr;
+  std::atomic<uint64_t> state_{0};  // generation << 16 | helpers wanted
   std::atomic<size_t> done_{0};
-  std::atomic<uint64_t> gen_{0};
-  bool stop_ = false;
+  std::atomic<int> sleepers_{0};
+  std::atomic<bool> stop_{false};
 };
 
 template <class F>

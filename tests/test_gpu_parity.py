@@ -805,46 +805,94 @@ def test_config2_shape_768d_k300_m96():
         _check_topk(ids[i, :oc[i]], dists[i, :oc[i]], oi[i, :oc[i]], od[i, :oc[i]], 10)
 
 
+def _bf16_to_f32(bits):
+    return (np.asarray(bits, np.uint16).astype(np.uint32) << 16).view(np.float32)
+
+
 def test_config3_shape_f16_cosine():
-    # C3: f16 vectors, cosine (normalise, then L2): same results as the f32 path on the converted values
+    # C3: f16 vectors, cosine (normalise, then L2).  The model of an f16 column is f16-valued like the reference's
+    # (kmeans.rs:405-418 keeps centroids in T); given that model every integer output equals the oracle's on the
+    # converted values, and the search equals the oracle's search
     n, d, K, M = 20000, 128, 64, 16
     data16 = (synth.gaussian_mixture(n, d, n_components=K, seed=83) * 0.25).astype(np.float16)
     p = lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, max_iters=6, pq_max_iters=4)
     i16 = lb.IvfPqIndex.build(data16, "cosine", p)
-    i32 = lb.IvfPqIndex.build(data16.astype(np.float32), "cosine", p)
-    e16, e32 = i16.export(), i32.export()
-    assert np.array_equal(e16["codes"], e32["codes"]) and np.array_equal(e16["row_ids"], e32["row_ids"])
+    e16 = i16.export()
+    for name in ("centroids", "codebook"):
+        assert np.array_equal(e16[name], e16[name].astype(np.float16).astype(np.float32)), name
+    unit = ob.normalize_rows(data16.astype(np.float32), nthreads=NT)
+    order = np.argsort(e16["row_ids"])
+    p_ref, _, _ = ob.compute_membership(e16["centroids"], unit, nthreads=NT)
+    sizes = np.diff(e16["part_offsets"]).astype(np.int64)
+    assert np.array_equal(np.repeat(np.arange(K, dtype=np.uint32), sizes)[order], p_ref)
+    res = ob.compute_residual(e16["centroids"], unit, p_ref, nthreads=NT)
+    assert np.array_equal(e16["codes"][order], ob.pq_encode(e16["codebook"], res, nthreads=NT))
     q16 = data16[:30]
-    r16, r32 = i16.search(q16, k=10, nprobes=5), i32.search(q16.astype(np.float32), k=10, nprobes=5)
-    assert np.array_equal(r16[0], r32[0]) and np.array_equal(r16[1], r32[1])
-    # and against the oracle (cosine index = L2 on unit vectors, _distance = squared L2 of unit vectors)
-    oi, od, oc = ob.ivfpq_search(e32["centroids"], e32["codebook"], e32["part_offsets"], e32["codes"],
-                                 e32["row_ids"], q16.astype(np.float32), 10, 5, metric="cosine", nthreads=NT)
-    for i in range(30):
-        _check_topk(r32[0][i, :oc[i]], r32[1][i, :oc[i]], oi[i, :oc[i]], od[i, :oc[i]], 10)
+    r16 = i16.search(q16, k=10, nprobes=5)
+    # (cosine index = L2 on unit vectors, _distance = squared L2 of unit vectors)
+    oi, od, oc = ob.ivfpq_search(e16["centroids"], e16["codebook"], e16["part_offsets"], e16["codes"],
+                                 e16["row_ids"], q16.astype(np.float32), 10, 5, metric="cosine", nthreads=NT)
+    assert np.array_equal(r16[0], oi) and np.array_equal(r16[1], od)
+
+
+def test_f16_normalize_and_centroid_update_vs_reference_f16_arithmetic():
+    """The reference normalises and sums centroids IN THE ELEMENT TYPE (kernels.rs:141-146: norm = sqrt of a
+    sequential f16 sum, x / norm in f16; kmeans.rs:405-418: centroid += row in f16, * 1/cnt in f16).  We compute
+    in f32 and round once.  This bounds the distance between the two: the f16 loops below restate the reference
+    (numpy float16, one rounding per operation); the tolerance is what f16 accumulation itself loses."""
+    rng = np.random.default_rng(90)
+    d, n = 128, 64
+    x = (rng.standard_normal((n, d)) * 0.5).astype(np.float16)
+    ours = lb.normalize_fsl(x.astype(np.float32))                   # f32 arithmetic on the converted values
+    ref = np.empty((n, d), np.float16)
+    for r in range(n):
+        s = np.float16(0)
+        for i in range(d):
+            s = np.float16(s + np.float16(x[r, i] * x[r, i]))
+        ref[r] = (x[r] / np.sqrt(s, dtype=np.float16)).astype(np.float16)
+    # a 128-term f16 sum carries up to ~sqrt(128) * 2^-11 relative error (0.6 %), worst case 128 * 2^-11 (6 %)
+    assert np.max(np.abs(ours - ref.astype(np.float32))) <= 0.02 * np.max(np.abs(ours))
+    assert np.mean(np.abs(ours - ref.astype(np.float32))) <= 0.003 * np.max(np.abs(ours))
+    # one centroid update: 200 members summed in f16 vs our f32 sum rounded to f16
+    members = (rng.standard_normal((200, d)) * 0.5 + 1.0).astype(np.float16)
+    km = lb.train_kmeans(members, d, 1, max_iters=1, centroids=members[:1])
+    acc = np.zeros(d, np.float16)
+    for r in range(200):
+        acc = (acc + members[r]).astype(np.float16)
+    ref_c = (acc * np.float16(1.0 / 200)).astype(np.float16)
+    rel = np.abs(km.centroids[0].astype(np.float32) - ref_c.astype(np.float32)) / np.maximum(np.abs(ref_c.astype(np.float32)), 1e-3)
+    assert km.centroids.dtype == np.float16 and np.max(rel) <= 0.05, np.max(rel)   # f16 sums near 200 have 0.125 ulps
 
 
 def test_config4_shape_bf16_ivf_flat_1536d():
-    # C4: 1536-d bf16 column, IVF_FLAT (no PQ): coarse assignment through the streamed tensor-core filter,
-    # exact partition scan; bf16 -> f32 is exact, so everything equals the f32 path on the converted values
+    # C4: 1536-d bf16 column, IVF_FLAT (no PQ): coarse assignment through the streamed tensor-core filter, exact
+    # partition scan over vectors STORED AS bf16; bf16 -> f32 is exact, so with the (bf16-valued) model the index
+    # equals the oracle's on the converted values
     n, d, K = 6000, 1536, 48
     f = synth.gaussian_mixture(n, d, n_components=K, seed=87).astype(np.float32)
     bits = (f.view(np.uint32) >> 16).astype(np.uint16)               # truncate to bf16
-    f = (bits.astype(np.uint32) << 16).view(np.float32)              # the exact f32 value of every element
+    f = _bf16_to_f32(bits)                                           # the exact f32 value of every element
     ib = lb.IvfFlatIndex.build(bits, "l2", num_partitions=K, max_iters=6, bf16=True)
-    i32 = lb.IvfFlatIndex.build(f, "l2", num_partitions=K, max_iters=6)
-    eb, e32 = ib.export(), i32.export()
-    assert np.array_equal(eb["part_offsets"], e32["part_offsets"]) and np.array_equal(eb["row_ids"], e32["row_ids"])
-    assert np.array_equal(eb["vectors"], e32["vectors"])
-    p_ref, _, _ = ob.compute_membership(e32["centroids"], f, nthreads=NT)
-    sizes = np.diff(e32["part_offsets"]).astype(np.int64)
-    assert np.array_equal(np.repeat(np.arange(K, dtype=np.uint32), sizes)[np.argsort(e32["row_ids"])], p_ref)
+    eb = ib.export()
+    assert eb["vectors"].dtype == np.uint16 and eb["vectors"].shape == (n, d)
+    order = np.argsort(eb["row_ids"])
+    assert np.array_equal(eb["vectors"][order], bits)                # the rows themselves, regrouped
+    cb = eb["centroids"]
+    assert np.array_equal(cb, _bf16_to_f32((cb.view(np.uint32) >> 16).astype(np.uint16)))   # bf16-valued model
+    p_ref, _, _ = ob.compute_membership(cb, f, nthreads=NT)
+    sizes = np.diff(eb["part_offsets"]).astype(np.int64)
+    assert np.array_equal(np.repeat(np.arange(K, dtype=np.uint32), sizes)[order], p_ref)
     q = f[:20]
     ids, dists = ib.search(bits[:20], k=10, nprobes=4)
-    oi, od, oc = ob.ivfflat_search(e32["centroids"], e32["part_offsets"], e32["vectors"], e32["row_ids"], q, 10, 4,
-                                   nthreads=NT)
-    for i in range(20):
-        _check_topk(ids[i, :oc[i]], dists[i, :oc[i]], oi[i, :oc[i]], od[i, :oc[i]], 10)
+    oi, od, oc = ob.ivfflat_search(cb, eb["part_offsets"], _bf16_to_f32(eb["vectors"]), eb["row_ids"], q, 10, 4, nthreads=NT)
+    assert np.array_equal(ids, oi) and np.array_equal(dists, od)
+    # an f16 column keeps f16 storage
+    h = (f[:2000, :64] * 0.1).astype(np.float16)
+    ih = lb.IvfFlatIndex.build(h, "cosine", num_partitions=8, max_iters=4)
+    eh = ih.export()
+    assert eh["vectors"].dtype == np.float16
+    unit = ob.normalize_rows(h.astype(np.float32), nthreads=NT).astype(np.float16)   # normalised, then stored in T
+    assert np.array_equal(eh["vectors"][np.argsort(eh["row_ids"])], unit)
 
 
 def test_config5_shape_u8_m32():
