@@ -255,6 +255,12 @@ lb2_status lb2_index_info(const lb2_index* index, uint32_t* k, uint32_t* d, uint
  * part_offsets[k+1]; codes [num_rows][M] and row_ids [num_rows] in partition order. */
 lb2_status lb2_index_export(const lb2_index* index, void* centroids_out, void* codebook_out,
                             uint64_t* part_offsets_out, uint8_t* codes_out, uint64_t* row_ids_out);
+/* One partition in the layout the reference's storage holds and merge_partitions writes (`__pq_code` with
+ * "transposed": true -- lance-index/src/vector/pq/storage.rs:52-67,430-450; rust/lance/src/index/vector/builder.rs:
+ * 938-1079): codes column-major [code bytes per row][n_p], row ids [n_p].  Call with NULL outputs first to get
+ * *num_rows_out.  tests/: the bytes equal the reference's own fixture test_data/v0.27.1/pq_in_schema. */
+lb2_status lb2_index_export_partition(const lb2_index* index, uint32_t partition, uint8_t* codes_transposed_out,
+                                      uint64_t* row_ids_out, uint64_t* num_rows_out);
 lb2_status lb2_index_destroy(lb2_index* index);
 
 /* IvfIndexBuilder::build (rust/lance/src/index/vector/builder.rs:236): sample -> train IVF ->

@@ -467,6 +467,18 @@ class IvfPqIndex:
                                      C.c_void_p(rid.ctypes.data)))
         return dict(centroids=cent, codebook=cb, part_offsets=off, codes=codes, row_ids=rid)
 
+    def export_partition_transposed(self, partition):
+        """lb2_index_export_partition: (codes [code bytes][n_p] column-major, row_ids [n_p]) -- the reference's
+        storage / index-file layout of one partition (pq/storage.rs:430-450)."""
+        i = self.info()
+        cw = i["num_sub_vectors"] // 2 if i["num_bits"] == 4 else i["num_sub_vectors"]
+        n = C.c_uint64(0)
+        check(lib().lb2_index_export_partition(self._h, C.c_uint32(partition), None, None, C.byref(n)))
+        codes, rid = np.empty((cw, n.value), np.uint8), np.empty(n.value, np.uint64)
+        check(lib().lb2_index_export_partition(self._h, C.c_uint32(partition), C.c_void_p(codes.ctypes.data),
+                                               C.c_void_p(rid.ctypes.data), C.byref(n)))
+        return codes, rid
+
     def search(self, queries, k=10, nprobes=1, out=None):
         """to_table(nearest={q,k,nprobes}) for a batch of queries: IVFIndex::find_partitions +
         search_in_partition + global merge (v2.rs:455-500, scanner.rs:3450-3466).

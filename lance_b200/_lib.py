@@ -63,7 +63,7 @@ EXPORTS = [
     "lb2_pq_train", "lb2_pq_encode", "lb2_pq_build_lut", "lb2_pq_scan", "lb2_flat_topk", "lb2_flat_topk_range",
     "lb2_ivfpq_transform", "lb2_index_create", "lb2_index_load", "lb2_index_search", "lb2_index_search_refine",
     "lb2_index_search_ex", "lb2_index_row_mask", "lb2_pq_scan_4bit",
-    "lb2_index_info", "lb2_index_export", "lb2_index_destroy", "lb2_ivfpq_build_params_default",
+    "lb2_index_info", "lb2_index_export", "lb2_index_export_partition", "lb2_index_destroy", "lb2_ivfpq_build_params_default",
     "lb2_ivfpq_build", "lb2_ivfflat_build_params_default", "lb2_ivfflat_build", "lb2_index_create_flat",
     "lb2_index_load_flat", "lb2_index_export_flat", "lb2_comm_unique_id", "lb2_comm_init", "lb2_comm_destroy",
     "lb2_comm_info", "lb2_index_search_sharded",

@@ -140,6 +140,15 @@ __global__ void group_vectors_kernel(const uint32_t* __restrict__ members, uint6
   if (c == 0) row_ids_out[r] = row_ids ? row_ids[src] : (uint64_t)src;
 }
 
+// row-major codes [n][cw] of one partition -> the reference's storage layout [cw][n] (pq/storage.rs:430-450)
+__global__ void transpose_codes_kernel(const uint8_t* __restrict__ codes, uint64_t n, int cw, uint8_t* __restrict__ out) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n * cw) return;
+  const uint64_t j = g % n;
+  const int m = (int)(g / n);
+  out[g] = codes[j * cw + m];
+}
+
 __global__ void widen_offsets_kernel(const uint32_t* __restrict__ off32, int K,
                                      uint64_t* __restrict__ off64) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1528,6 +1537,28 @@ lb2_status lb2_ivfflat_build(const void* data, uint64_t n, uint32_t d, lb2_dtype
     stats->ivf_loss = loss.empty() ? 0.0 : loss[0];
   }
   *out = ix.release();
+  LB2_API_END
+}
+
+lb2_status lb2_index_export_partition(const lb2_index* index, uint32_t partition, uint8_t* codes_transposed_out,
+                                      uint64_t* row_ids_out, uint64_t* num_rows_out) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(index && index->kind == 0, "not an IVF_PQ index");
+  LB2_REQUIRE(partition < (uint32_t)index->K, "partition %u out of range (the index has %d)", partition, index->K);
+  uint64_t off[2];
+  d2h(off, index->part_offsets.p + partition, 2);
+  sync_stream();
+  const uint64_t np = off[1] - off[0];
+  const int cw = index->code_bytes();
+  if (num_rows_out) *num_rows_out = np;
+  if (np && codes_transposed_out) {
+    OutArg<uint8_t> o(codes_transposed_out, (size_t)np * cw);
+    LB2_LAUNCH("transpose_codes", transpose_codes_kernel, cdiv(np * cw, 256), 256, 0, index->codes.p + off[0] * cw, np, cw, o.get());
+    o.commit();
+  }
+  if (np && row_ids_out)
+    LB2_CUDA(cudaMemcpyAsync(row_ids_out, index->row_ids.p + off[0], sizeof(uint64_t) * np, cudaMemcpyDefault, ctx().stream));
+  sync_stream();
   LB2_API_END
 }
 

@@ -21,6 +21,7 @@
 #include <condition_variable>
 #include <functional>
 #include <limits>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -31,11 +32,29 @@ namespace {
 // small helpers
 // ---------------------------------------------------------------------------------------------
 // Persistent worker pool (the reference runs these loops on rayon's global pool: threads are created once
-// and parked between jobs, rust/lance-index/src/vector/kmeans.rs:335-356 `par_chunks`).  Like rayon's
-// workers, ours SPIN for the next job for a while before they sleep, and a job is published with two atomic
-// stores (no lock, no wake-up storm): the ~1000 short parallel regions of a k-means run (one per Lloyd
-// iteration and sub-space) pay microseconds, not thread start-up.  Per-row results do not depend on the schedule.
+// and parked between jobs, rust/lance-index/src/vector/kmeans.rs:335-356 `par_chunks`).  Like rayon:
+//   * workers SPIN for the next job for a while before they sleep (the ~1000 short parallel regions of a
+//     k-means run are microseconds apart), a job is published with two atomic stores, no wake-up storm;
+//   * a job is finished when its CHUNKS are finished, not when every worker has shown up: a worker the OS
+//     has descheduled (shared hosts) simply contributes nothing; it can never touch a finished job's closure,
+//     because the closure is only entered after claiming a chunk and all chunks are claimed before the
+//     caller returns (the job record itself is reference counted).
+// Per-row results do not depend on the schedule.
 class Pool {
+  struct Job {
+    std::function<void(size_t, size_t)> f;
+    size_t n = 0, chunk = 1, total_chunks = 0, helpers = 0;
+    std::atomic<size_t> next{0}, done_chunks{0};
+    void work() {
+      for (;;) {
+        const size_t b = next.fetch_add(chunk, std::memory_order_relaxed);
+        if (b >= n) break;
+        f(b, std::min(n, b + chunk));
+        done_chunks.fetch_add(1, std::memory_order_release);
+      }
+    }
+  };
+
  public:
   static Pool& get() {
     static Pool p;
@@ -45,27 +64,22 @@ class Pool {
   void run(size_t n, int nthreads, F&& f) {
     std::lock_guard<std::mutex> run_lock(run_mu_);  // one job at a time
     const size_t nt = std::min<size_t>(std::min<size_t>(size_t(nthreads), n), 4096);
-    const size_t helpers = nt - 1;
-    ensure(helpers);
-    const size_t chunk = std::max<size_t>(1, n / (nt * 8));
-    std::atomic<size_t> next{0};
-    std::function<void()> body = [&] {
-      for (;;) {
-        const size_t b = next.fetch_add(chunk, std::memory_order_relaxed);
-        if (b >= n) break;
-        f(b, std::min(n, b + chunk));
-      }
-    };
-    body_ = &body;
-    done_.store(0, std::memory_order_relaxed);
-    const uint64_t g = (state_.load(std::memory_order_relaxed) >> 16) + 1;
-    state_.store((g << 16) | uint64_t(helpers), std::memory_order_release);  // publish (generation, helpers)
+    ensure(nt - 1);
+    auto job = std::make_shared<Job>();
+    job->f = std::ref(f);
+    job->n = n;
+    job->chunk = std::max<size_t>(1, n / (nt * 8));
+    job->total_chunks = (n + job->chunk - 1) / job->chunk;
+    job->helpers = nt - 1;
+    std::atomic_store(&cur_, job);
+    gen_.fetch_add(1, std::memory_order_release);
     if (sleepers_.load(std::memory_order_acquire) > 0) {
       std::lock_guard<std::mutex> lk(mu_);
       cv_.notify_all();
     }
-    body();
-    while (done_.load(std::memory_order_acquire) != helpers) cpu_relax();  // every helper reports, late ones too
+    job->work();
+    while (job->done_chunks.load(std::memory_order_acquire) != job->total_chunks) cpu_relax();
+    std::atomic_store(&cur_, std::shared_ptr<Job>());
   }
 
  private:
@@ -74,7 +88,7 @@ class Pool {
     stop_.store(true);
     {
       std::lock_guard<std::mutex> lk(mu_);
-      state_.fetch_add(uint64_t(1) << 16);
+      gen_.fetch_add(1);
       cv_.notify_all();
     }
     for (auto& t : th_) t.join();
@@ -89,42 +103,37 @@ class Pool {
   void ensure(size_t helpers) {
     while (th_.size() < helpers) {
       const size_t id = th_.size();
-      const uint64_t start_gen = state_.load() >> 16;
+      const uint64_t start_gen = gen_.load();
       th_.emplace_back([this, id, start_gen] { worker(id, start_gen); });
     }
   }
   void worker(size_t id, uint64_t seen) {
     for (;;) {
-      uint64_t st = state_.load(std::memory_order_acquire);
       int spins = 0;
-      while ((st >> 16) == seen) {
+      while (gen_.load(std::memory_order_acquire) == seen) {
         if (++spins < 20000) {  // ~0.2 ms of polling: the next parallel region is usually that close
           cpu_relax();
         } else {
           sleepers_.fetch_add(1, std::memory_order_acq_rel);
           {
             std::unique_lock<std::mutex> lk(mu_);
-            cv_.wait(lk, [&] { return (state_.load(std::memory_order_acquire) >> 16) != seen; });
+            cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
           }
           sleepers_.fetch_sub(1, std::memory_order_acq_rel);
           spins = 0;
         }
-        st = state_.load(std::memory_order_acquire);
       }
-      seen = st >> 16;
+      seen = gen_.load(std::memory_order_acquire);
       if (stop_.load()) return;
-      if (id < (st & 0xffff)) {  // this generation wants helpers 0 .. (st & 0xffff) - 1
-        (*body_)();
-        done_.fetch_add(1, std::memory_order_release);
-      }
+      std::shared_ptr<Job> job = std::atomic_load(&cur_);
+      if (job && id < job->helpers) job->work();
     }
   }
   std::mutex mu_, run_mu_;
   std::condition_variable cv_;
   std::vector<std::thread> th_;
-  std::function<void()>* body_ = nullptr;
-  std::atomic<uint64_t> state_{0};  // generation << 16 | helpers wanted
-  std::atomic<size_t> done_{0};
+  std::shared_ptr<Job> cur_;
+  std::atomic<uint64_t> gen_{0};
   std::atomic<int> sleepers_{0};
   std::atomic<bool> stop_{false};
 };

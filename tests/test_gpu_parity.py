@@ -1108,3 +1108,28 @@ def test_normalize_fsl_bit_exact(d):
     got, exp = lb.normalize_fsl(x), ob.normalize_rows(x)
     assert np.array_equal(got.view(np.uint32)[np.isfinite(exp)], exp.view(np.uint32)[np.isfinite(exp)])
     assert np.isnan(got[5]).all() and np.isnan(exp[5]).all()
+
+
+def test_reference_fixture_pq_in_schema_on_gpu():
+    """The reference's own index fixture (tests/golden/pq_in_schema.npz, see make_pq_in_schema_fixture.py): the device
+    reproduces the codes Lance 0.27.1 stored, consumes the stored transposed bytes, and searches like the oracle."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "pq_in_schema.npz"))
+    M, n = int(z["num_sub_vectors"]), len(z["row_ids"])
+    codes = z["codes_transposed"].reshape(M, n).T.copy()
+    v = z["vectors"][z["row_ids"].astype(np.int64)]
+    part, pcodes, valid = lb.ivfpq_transform(z["centroids"], z["codebook"], v)
+    assert valid.all() and (part == 0).all() and np.array_equal(pcodes, codes)
+    assert np.array_equal(lb.ProductQuantizer(M, 8, 32, z["codebook"]).quantize(v, centroids=z["centroids"], part_ids=part), codes)
+    q = np.zeros((1, 32), np.float32)
+    lut = lb.build_distance_table_l2(z["codebook"], 8, M, q[0] - z["centroids"][0])
+    assert np.array_equal(lut, ob.build_lut(z["codebook"], q[0] - z["centroids"][0]))
+    d_t = lb.compute_pq_distance(lut, 8, M, z["codes_transposed"])
+    assert np.array_equal(d_t, ob.pq_scan(lut, z["codes_transposed"].reshape(M, n)))
+    ix = lb.IvfPqIndex.from_parts(z["centroids"], z["codebook"], part, codes, row_ids=z["row_ids"])
+    ids, dd = ix.search(q, k=5, nprobes=1)
+    oi, od, oc = ob.ivfpq_search(z["centroids"], z["codebook"], np.array([0, n], np.uint64), codes, z["row_ids"], q, 5, 1)
+    assert oc[0] == 5 and np.array_equal(ids, oi) and np.array_equal(dd, od)
+    # the partition goes back out in the reference's storage layout: the bytes of the `__pq_code` column
+    ct, rid = ix.export_partition_transposed(0)
+    assert np.array_equal(ct.reshape(-1), z["codes_transposed"]) and np.array_equal(rid, z["row_ids"])

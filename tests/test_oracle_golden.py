@@ -157,6 +157,37 @@ def test_range_query_follows_flat_index_semantics():
     assert sorted(dist.tolist()) == [7.0, 9.0]
 
 
+def _pq_in_schema():
+    z = np.load(os.path.join(HERE, "golden", "pq_in_schema.npz"))
+    M, n = int(z["num_sub_vectors"]), len(z["row_ids"])
+    assert bool(z["transposed"]) and len(z["lengths"]) == 1 and int(z["lengths"][0]) == n
+    codes = z["codes_transposed"].reshape(M, n).T.copy()            # pq/storage.rs:430-450: [M][n_p] per partition
+    return z, codes
+
+
+def test_reference_fixture_pq_in_schema_codes_are_reproduced_bit_for_bit():
+    """test_data/v0.27.1/pq_in_schema is a real index written by Lance 0.27.1 (used by ivf/v2.rs:2059): its vectors,
+    IVF centroid, PQ codebook and transposed codes pin the WHOLE transform pipeline of the oracle -- partition id
+    (kmeans.rs:1187-1294), residual (residual.rs:58-154), code assignment (pq.rs:116-191) and the storage layout
+    (pq/storage.rs:430-450, pq/utils.rs:59-76) -- to the reference's own output."""
+    z, codes = _pq_in_schema()
+    v = z["vectors"][z["row_ids"].astype(np.int64)]
+    part, _, valid = ob.compute_membership(z["centroids"], v)
+    assert valid.all() and (part == 0).all()
+    res = ob.compute_residual(z["centroids"], v, part)
+    assert np.array_equal(ob.pq_encode(z["codebook"], res), codes)
+    # the stored bytes ARE the transposed codes the scan consumes (compute_pq_distance, pq/distance.rs:109-144)
+    q = np.zeros(32, np.float32)                                    # the reference test's query (v2.rs:2065)
+    lut = ob.build_lut(z["codebook"], q - z["centroids"][0])
+    d_t = ob.pq_scan(lut, z["codes_transposed"].reshape(4, -1))
+    d_r = np.array([sum(np.float32(lut[m * 256 + int(codes[j, m])]) for m in range(4)) for j in range(8)], np.float32)
+    assert np.allclose(d_t[:8], d_r, rtol=1e-6)
+    off = np.array([0, len(codes)], np.uint64)
+    ids, dd, cnt = ob.ivfpq_search(z["centroids"], z["codebook"], off, codes, z["row_ids"], q[None, :], 5, 1)
+    assert cnt[0] == 5 and np.all(np.diff(dd[0]) >= 0)              # "assert_eq!(search_result.num_rows(), 5)"
+    assert np.array_equal(dd[0], np.sort(d_t)[:5])
+
+
 def test_argmin_semantics():
     # kernels.rs:79-89: first minimum wins; NaN / inf rows -> None (kmeans.rs:1447-1486)
     cent = np.array([[0, 0], [1, 1], [0, 0]], np.float32)
