@@ -227,6 +227,8 @@ def run(args, cfg, B):
         pin = lb.PinnedArray((n, d), npdt)
         import ctypes as C
         _lib.check(lb.lib().lb2_memcpy(C.c_void_p(pin.ptr), C.c_void_p(data_t.data_ptr()), C.c_size_t(n * d * esize)))
+        del data_dev, view, data_t, gt_local      # the device copy of the dataset makes room for the host-fed build
+        torch.cuda.empty_cache()
         barrier()
         t0 = time.perf_counter()
         ixh = build(pin, None)

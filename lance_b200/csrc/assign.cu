@@ -310,15 +310,22 @@ small_d_kernel(const float* __restrict__ x, uint64_t n, int ldx, const float* __
 // (c) generic kernel: 8 rows per CTA in smem, 16 half-warps stride over the centroids, lane l of a
 // half-warp owns lane-accumulator l (elements 16c+l) -> coalesced 64-byte centroid reads.
 // ------------------------------------------------------------------------------------------------
-template <int METRIC, bool WRITE_ALL, int R>
+// SPLIT (short row lists only): blockIdx.y selects one range of kchunk centroids, the partial (key, value,
+// index) of every row goes to split_out and split_merge_kernel picks the winner -- a few hundred rows against
+// thousands of wide centroids are latency bound otherwise (one CTA walks the whole centroid matrix)
+template <int METRIC, bool WRITE_ALL, int R, bool SPLIT = false>
 __global__ void __launch_bounds__(256)
 generic_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __restrict__ cent, int K,
                const float* __restrict__ bias, uint32_t* __restrict__ part, float* __restrict__ dist,
                uint8_t* __restrict__ valid, float* __restrict__ all_out,
                const uint8_t* __restrict__ active, const uint32_t* __restrict__ row_list,
-               const uint32_t* __restrict__ row_count) {
+               const uint32_t* __restrict__ row_count, uint32_t cnt_lo = 0, uint32_t cnt_hi = 0xffffffffu,
+               int kchunk = 0, float* __restrict__ split_out = nullptr) {
   if (active && !active[0]) return;
-  if (row_list) n = *row_count;  // same indirection as the tile kernel
+  if (row_list) {  // same indirection as the tile kernel
+    n = *row_count;
+    if (n < cnt_lo || n >= cnt_hi) return;
+  }
   extern __shared__ float smem[];
   float* xs = smem;  // [R][d]
   __shared__ float red_key[16][R];
@@ -337,7 +344,8 @@ generic_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __re
   float bkey = __int_as_float(0x7f800000), bval = __int_as_float(0x7f800000);
   uint32_t bidx = 0xffffffffu;  // lane l tracks row (l & (R - 1)); R is 8 or 16
   const unsigned hmask = 0xffffu << (16 * ((tid >> 4) & 1));
-  for (int c = hw; c < K; c += 16) {
+  const int k_begin = SPLIT ? (int)blockIdx.y * kchunk : 0, k_end = SPLIT ? min(K, k_begin + kchunk) : K;
+  for (int c = k_begin + hw; c < k_end; c += 16) {
     const float* cp = cent + (size_t)c * d;
     float acc[R];
 #pragma unroll
@@ -379,7 +387,14 @@ generic_kernel(const float* __restrict__ x, uint64_t n, int d, const float* __re
         k0 = red_key[h][tid]; v0 = red_val[h][tid]; i0 = red_idx[h][tid];
       }
     uint64_t r = row0 + tid;
-    if (r < n) {
+    if (SPLIT) {
+      if (r < n) {
+        float* o = split_out + (r * gridDim.y + blockIdx.y) * 3;
+        o[0] = k0;
+        o[1] = v0;
+        o[2] = __uint_as_float(i0);
+      }
+    } else if (r < n) {
       if (row_list) r = row_list[r];
       const bool ok = i0 != 0xffffffffu;
       part[r] = ok ? i0 : 0u;
@@ -458,10 +473,28 @@ void assign_rows_f32(const float* x, uint64_t n_max, int d, const float* cent, i
     // 8 rows per CTA: the list is short, more CTAs beat fewer centroid re-reads (measured)
     const size_t gsmem = sizeof(float) * 8 * (size_t)d;
     if (gsmem > ctx().smem_optin) fail(LB2_UNSUPPORTED, "dimension %d too large for the exact kernel", d);
+    // very short lists against many centroids: one CTA per (8 rows, range of centroids) + a merge
+    const int gchunks = (int)std::min<uint64_t>(64, (uint64_t)K / 128);
+    const uint32_t gtiny = gchunks > 1 ? (uint32_t)std::min<uint64_t>(4096, n_max + 1) : 0u;
+    TcWorkspace glocal;
+    if (!ws) ws = &glocal;
+    if (gtiny) {
+      const int kchunk = ((K + gchunks - 1) / gchunks + 15) / 16 * 16;
+      const int nch = (K + kchunk - 1) / kchunk;
+      if (ws->split_scratch.n < (size_t)gtiny * nch * 3) ws->split_scratch.alloc((size_t)gtiny * nch * 3);
+      set_smem((generic_kernel<METRIC_L2, false, 8, true>), gsmem);
+      LB2_LAUNCH("assign_exact_fallback", (generic_kernel<METRIC_L2, false, 8, true>),
+                 dim3((unsigned)cdiv(gtiny, 8), (unsigned)nch), 256, gsmem, x, n_max, d, cent, K, bias_padded, part, dist,
+                 valid, nullptr, active, row_list, row_count, 0u, gtiny, kchunk, ws->split_scratch.p);
+      LB2_LAUNCH("assign_exact_fallback", split_merge_kernel, cdiv(gtiny, 256), 256, 0, ws->split_scratch.p, nch, row_list,
+                 row_count, gtiny, part, dist, valid, active);
+    }
     set_smem(generic_kernel<METRIC_L2, false, 8>, gsmem);
     LB2_LAUNCH("assign_exact_fallback", (generic_kernel<METRIC_L2, false, 8>),
                (unsigned)std::min<uint64_t>(cdiv(n_max, 8), 8 * (uint64_t)ctx().num_sms), 256, gsmem, x,
-               n_max, d, cent, K, bias_padded, part, dist, valid, nullptr, active, row_list, row_count);
+               n_max, d, cent, K, bias_padded, part, dist, valid, nullptr, active, row_list, row_count, gtiny,
+               0xffffffffu);
+    if (ws == &glocal) sync_stream();  // its scratch is freed on return
     return;
   }
   const int Kp = (K + 63) / 64 * 64;

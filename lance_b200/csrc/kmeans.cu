@@ -141,23 +141,19 @@ __global__ void scatter_kernel(const uint32_t* __restrict__ ids, const uint8_t* 
 // histograms and running counters live in shared memory, and the cross-CTA prefix is read through
 // distributed shared memory between two cluster barriers (no global-memory round trips, no MATCH).
 constexpr int SORT_CLUSTER = 8;
-__global__ void __cluster_dims__(SORT_CLUSTER, 1, 1) __launch_bounds__(1024)
-cluster_sort_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ valid, uint64_t n,
-                    int K, uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
-                    uint32_t* __restrict__ members, const uint8_t* __restrict__ active) {
+// the sort of ONE problem by the calling cluster (8 CTAs x 1024 threads; sm = 34 * K words of shared memory):
+// also the member-list phase of the fused small-problem kernel below
+__device__ __forceinline__ void cluster_sort_body(const uint32_t* __restrict__ idb, const uint8_t* __restrict__ vb,
+                                                  uint64_t n, int K, uint32_t* __restrict__ counts_b,
+                                                  uint32_t* __restrict__ offsets_b, uint32_t* __restrict__ mem,
+                                                  uint32_t* sm, uint32_t* wsum) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
-  const int b = blockIdx.y;
-  if (active && !active[b]) return;  // uniform over the cluster
   const unsigned crank = cluster.block_rank();
-  extern __shared__ uint32_t sm[];
   uint32_t* wh = sm;             // [32][K] per-warp histogram, then running counters
   uint32_t* tot = sm + 32 * K;   // [K]     this CTA's per-key total (read by the other CTAs)
   uint32_t* off = tot + K;       // [K]     first output slot of this CTA's rows, per key
-  __shared__ uint32_t wsum[32];
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  const uint32_t* idb = ids + (size_t)b * n;
-  const uint8_t* vb = valid ? valid + (size_t)b * n : nullptr;
   for (int i = tid; i < 32 * K; i += 1024) wh[i] = 0;
   __syncthreads();
   constexpr uint32_t NONE = 0xffffffffu;
@@ -216,13 +212,12 @@ cluster_sort_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict_
   if (tid < K) {
     off[tid] = excl + before;
     if (crank == 0) {
-      counts[(size_t)b * K + tid] = total;
-      offsets[(size_t)b * (K + 1) + tid] = excl;
-      if (tid == K - 1) offsets[(size_t)b * (K + 1) + K] = excl + total;
+      counts_b[tid] = total;
+      offsets_b[tid] = excl;
+      if (tid == K - 1) offsets_b[K] = excl + total;
     }
   }
   __syncthreads();
-  uint32_t* mem = members + (size_t)b * n;
   const int nbits = 32 - __clz(max(K - 1, 1));
   for (uint64_t base0 = r0; base0 < r1; base0 += 32 * 8) {
     uint32_t keys[8];
@@ -249,6 +244,18 @@ cluster_sort_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict_
     }
   }
   cluster.sync();  // nobody leaves while a neighbour may still read its `tot`
+}
+
+__global__ void __cluster_dims__(SORT_CLUSTER, 1, 1) __launch_bounds__(1024)
+cluster_sort_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ valid, uint64_t n,
+                    int K, uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
+                    uint32_t* __restrict__ members, const uint8_t* __restrict__ active) {
+  const int b = blockIdx.y;
+  if (active && !active[b]) return;  // uniform over the cluster
+  extern __shared__ uint32_t sm[];
+  __shared__ uint32_t wsum[32];
+  cluster_sort_body(ids + (size_t)b * n, valid ? valid + (size_t)b * n : nullptr, n, K, counts + (size_t)b * K,
+                    offsets + (size_t)b * (K + 1), members + (size_t)b * n, sm, wsum);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -715,16 +722,16 @@ __device__ __forceinline__ uint64_t sm64_next(uint64_t& s) {
   return z ^ (z >> 31);
 }
 
-__global__ void __launch_bounds__(256)
-epilogue_kernel(int K, int ds, uint64_t n, float bf_param, double tolerance,
+// (a device function so that the fused small-problem kernel can run it too: problem b, by the NT threads of
+// the calling block)
+template <int NT>
+__device__ __forceinline__ void epilogue_body(int b, int K, int ds, uint64_t n, float bf_param, double tolerance,
                 const uint32_t* __restrict__ counts, const double* __restrict__ losses,
                 const float* __restrict__ radius, const uint32_t* __restrict__ last_row,
                 uint64_t* __restrict__ cluster_sizes, float* __restrict__ bias, int bias_ld,
                 float* __restrict__ centroids, LloydState* __restrict__ states,
                 uint8_t* __restrict__ active, TcPqPrepArgs pq_prep) {
-  const int b = blockIdx.x, tid = threadIdx.x;
-  if (pq_prep.bm && tid == 0) pq_prep.fb_count[b] = 0;  // next iteration's undecided-row list (active or not)
-  if (!active[b]) return;
+  const int tid = threadIdx.x;
   __shared__ int s_i, s_j;
   LloydState& st = states[b];
   uint64_t* cs = cluster_sizes + (size_t)b * K;
@@ -733,9 +740,9 @@ epilogue_kernel(int K, int ds, uint64_t n, float bf_param, double tolerance,
   float* cb = centroids + (size_t)b * K * ds;
   // (1) order-independent parts in parallel: cluster sizes, sum of squares, and the
   //     "first cluster to reach the final maximum" = max count, then smallest last member row
-  __shared__ unsigned long long s_red_a[256];  // packed (count << 32 | ~last_row) -> max
-  __shared__ unsigned long long s_red_sq[256];
-  __shared__ int s_red_id[256];
+  __shared__ unsigned long long s_red_a[NT];  // packed (count << 32 | ~last_row) -> max
+  __shared__ unsigned long long s_red_sq[NT];
+  __shared__ int s_red_id[NT];
   __shared__ double s_chunk[1024];
   __shared__ int s_any_empty;
   {
@@ -759,7 +766,7 @@ epilogue_kernel(int K, int ds, uint64_t n, float bf_param, double tolerance,
     s_red_sq[tid] = sq;
     const int any = __syncthreads_or(empty);
     if (tid == 0) s_any_empty = any;
-    for (int off = 128; off >= 1; off >>= 1) {
+    for (int off = NT / 2; off >= 1; off >>= 1) {
       if (tid < off) {
         const unsigned long long o = s_red_a[tid + off];
         const int oi = s_red_id[tid + off];
@@ -854,11 +861,143 @@ epilogue_kernel(int K, int ds, uint64_t n, float bf_param, double tolerance,
   if (bias)
     for (int k = tid; k < K; k += blockDim.x)
       bias[(size_t)b * bias_ld + k] = __fmul_rn(s_bf, (float)cs[k]);
-  if (pq_prep.bm) {  // PQ tensor path (K == 256 codewords x 8 dims, 256 threads): operands of the NEXT iteration
+  if (NT == 256 && pq_prep.bm) {  // PQ tensor path (K == 256 codewords x 8 dims, 256 threads): operands of the NEXT iteration
     __shared__ float s_n2[256];
     __syncthreads();  // the split above may have rewritten codewords
     tc_pq_prep_block(cb, b, pq_prep, s_n2);
   }
+}
+
+__global__ void __launch_bounds__(256)
+epilogue_kernel(int K, int ds, uint64_t n, float bf_param, double tolerance,
+                const uint32_t* __restrict__ counts, const double* __restrict__ losses,
+                const float* __restrict__ radius, const uint32_t* __restrict__ last_row,
+                uint64_t* __restrict__ cluster_sizes, float* __restrict__ bias, int bias_ld,
+                float* __restrict__ centroids, LloydState* __restrict__ states,
+                uint8_t* __restrict__ active, TcPqPrepArgs pq_prep) {
+  const int b = blockIdx.x;
+  if (pq_prep.bm && threadIdx.x == 0) pq_prep.fb_count[b] = 0;  // next iteration's undecided-row list (active or not)
+  if (!active[b]) return;
+  epilogue_body<256>(b, K, ds, n, bf_param, tolerance, counts, losses, radius, last_row, cluster_sizes, bias, bias_ld,
+                     centroids, states, active, pq_prep);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Small problems (hierarchical k-means splits a cluster with k' <= 16, kmeans.rs:885-895: thousands of
+// Lloyd runs over a few hundred .. a few thousand rows): the WHOLE run in one launch.  A thread-block
+// cluster of 8 CTAs x 1024 threads iterates  assign (exact, 16 lanes per row = the reference's lane
+// accumulators) -> stable member sort (cluster_sort_body) -> ordered centroid sums + f64 loss (the same
+// update_body_warp / stats_body as the general path) -> scalar epilogue (epilogue_body, CTA 0)  with cluster
+// barriers between the phases; nothing returns to the host until the run has converged.  Same device functions,
+// same order of every floating-point operation as the multi-kernel path -> bit-identical models; ~10 us per
+// iteration instead of ~10 launches.
+// ------------------------------------------------------------------------------------------------
+constexpr int SMALL_UPD_WARPS = 8;  // warps per CTA that run update / stats tasks (one 4 KB tile each)
+template <int METRIC>
+__global__ void __cluster_dims__(SORT_CLUSTER, 1, 1) __launch_bounds__(1024)
+lloyd_small_kernel(const float* __restrict__ x, uint32_t n, int d, int K, float* __restrict__ centroids,
+                   float bf_param, double tolerance, int max_iters, uint32_t* __restrict__ ids,
+                   float* __restrict__ dists, uint8_t* __restrict__ valid, uint32_t* __restrict__ counts,
+                   uint32_t* __restrict__ offsets, uint32_t* __restrict__ members, double* __restrict__ losses,
+                   float* __restrict__ radius, uint32_t* __restrict__ last_row,
+                   uint64_t* __restrict__ cluster_sizes, float* __restrict__ bias, LloydState* __restrict__ state,
+                   uint8_t* __restrict__ active, uint8_t* __restrict__ hints, int warp_update) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned crank = cluster.block_rank();
+  extern __shared__ __align__(16) uint8_t small_smem[];
+  float* cs = reinterpret_cast<float*>(small_smem);                    // [K][d] centroids of this iteration
+  float* sb = cs + (size_t)K * d;                                       // [16] bias
+  float* tiles = sb + 16;                                               // [SMALL_UPD_WARPS][UPD_TILE * 8]
+  uint32_t* sort_sm = reinterpret_cast<uint32_t*>(tiles + SMALL_UPD_WARPS * UPD_TILE * 8);  // [34 * K]
+  __shared__ uint32_t wsum[32];
+  const int tid = threadIdx.x, warp = tid >> 5, l = tid & 15;
+  const unsigned hmask = 0xffffu << (16 * ((tid >> 4) & 1));
+  const int n16 = d & ~15;
+  const int nch = d >> 3;
+  const uint32_t hw_global = crank * 64 + (tid >> 4), hw_total = SORT_CLUSTER * 64;  // half-warps of the cluster
+  for (int it = 1; it <= max_iters; ++it) {
+    // ---- centroids + bias of this iteration into shared memory
+    for (int i = tid; i < K * d; i += 1024) cs[i] = centroids[i];
+    if (tid < 16) sb[tid] = tid < K ? bias[tid] : 0.0f;
+    __syncthreads();
+    // ---- membership (kmeans.rs:317-369): lane l of a half-warp owns lane accumulator l (l2.rs:82-88)
+    for (uint32_t r = hw_global; r < n; r += hw_total) {
+      const float* xv = x + (size_t)r * d;
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+      for (int e = l; e < n16; e += 16) {
+        const float xe = xv[e];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < K) acc[j] = f_add(acc[j], term<METRIC>(xe, cs[j * d + e]));
+      }
+      float best_key = __int_as_float(0x7f800000), best_val = best_key;
+      uint32_t best_idx = 0xffffffffu;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j < K) {  // uniform
+          float sq = 0.0f;  // sequential tail (l2.rs:69-79), every lane redundantly
+          for (int e = n16; e < d; ++e) sq = f_add(sq, term<METRIC>(xv[e], cs[j * d + e]));
+          float t = 0.0f;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) t = f_add(t, __shfl_sync(hmask, acc[j], q, 16));
+          const float v = finish<METRIC>(f_add(sq, t));
+          const float key = f_add(v, sb[j]);
+          if (key < best_key) { best_key = key; best_val = v; best_idx = j; }
+        }
+      }
+      if (l == 0) {
+        const bool ok = best_idx != 0xffffffffu;
+        ids[r] = ok ? best_idx : 0u;
+        dists[r] = ok ? best_val : __int_as_float(0x7fc00000);
+        valid[r] = ok ? 1 : 0;
+      }
+    }
+    __threadfence();
+    cluster.sync();
+    // ---- member lists (stable counting sort of the rows by cluster)
+    cluster_sort_body(ids, valid, n, K, counts, offsets, members, sort_sm, wsum);
+    __threadfence();
+    cluster.sync();
+    // ---- ordered centroid sums (kmeans.rs:388-418) and per-cluster f64 loss / radius (kmeans.rs:266-280)
+    if (warp_update) {
+      if (warp < SMALL_UPD_WARPS) {
+        const int ntask = K * nch + K;
+        for (int t = crank * SMALL_UPD_WARPS + warp; t < ntask; t += SORT_CLUSTER * SMALL_UPD_WARPS) {
+          if (t < K * nch)
+            update_body_warp((size_t)t, tiles + warp * UPD_TILE * 8, x, d, d, K, 1, n, members, offsets, centroids,
+                             nullptr, 1, hints);
+          else
+            stats_body(t - K * nch, dists, n, K, 1, members, offsets, losses, radius, last_row, nullptr, hints + 1);
+          __syncwarp();
+        }
+      }
+    } else {
+      for (size_t g = (size_t)crank * 1024 + tid; g < (size_t)K * d; g += (size_t)SORT_CLUSTER * 1024)
+        update_body(g, x, d, d, K, 1, n, members, offsets, centroids, nullptr, 1);
+      for (int t = crank * 32 + warp; t < K; t += SORT_CLUSTER * 32)
+        stats_body(t, dists, n, K, 1, members, offsets, losses, radius, last_row, nullptr, hints + 1);
+    }
+    __threadfence();
+    cluster.sync();
+    // ---- the iteration's scalar bookkeeping (cluster sizes, balance loss, split_clusters, tolerance test, bias)
+    if (crank == 0)
+      epilogue_body<1024>(0, K, d, n, bf_param, tolerance, counts, losses, radius, last_row, cluster_sizes, bias,
+                          16, centroids, state, active, TcPqPrepArgs());
+    __threadfence();
+    cluster.sync();
+    if (!*reinterpret_cast<volatile uint8_t*>(active)) break;  // converged (kmeans.rs:704)
+  }
+}
+
+static bool lloyd_small_ok(uint64_t n, int B, int ds, int K, bool dist) {
+  static const bool off = getenv("LB2_NO_SMALL_KMEANS") && *getenv("LB2_NO_SMALL_KMEANS");
+  // one cluster = 8 SMs of plain FP32: worth it while the membership pass stays below ~50 MFLOP per iteration
+  return !off && !dist && B == 1 && K >= 1 && K <= 16 && n >= 1 && n <= 16384 && (uint64_t)K * ds <= 24576 &&
+         n * (uint64_t)K * ds <= (1ull << 24) && !ctx().profiling;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -974,6 +1113,31 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
   DevBuf<uint8_t> hints((size_t)2 * B);  // order-independent-sum hints (update, loss) per problem
   LB2_CUDA(cudaMemsetAsync(hints.p, 1, (size_t)2 * B, ctx().stream));
   MemberSort ms;
+  if (lloyd_small_ok(n, B, ds, K, dist) && (metric == METRIC_L2 || metric == METRIC_DOT) && ldx == ds) {
+    // the whole run in ONE launch (lloyd_small_kernel)
+    ms.counts.alloc(K);
+    ms.offsets.alloc(K + 1);
+    ms.members.alloc(n);
+    DevBuf<float> bias16(16);
+    bias16.zero();
+    const int warp_update = (ds % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
+    const size_t smem = sizeof(float) * ((size_t)K * ds + 16 + SMALL_UPD_WARPS * UPD_TILE * 8) + sizeof(uint32_t) * 34 * (size_t)K;
+#define LB2_SMALL(MET)                                                                                              \
+    do {                                                                                                            \
+      set_smem(lloyd_small_kernel<MET>, smem);                                                                      \
+      LB2_LAUNCH("kmeans_small_fused", lloyd_small_kernel<MET>, SORT_CLUSTER, 1024, smem, x, (uint32_t)n, ds, K,    \
+                 centroids, balance_factor_param, tolerance, max_iters, ids.p, dists.p, valid.p, ms.counts.p,       \
+                 ms.offsets.p, ms.members.p, losses.p, radius.p, last_row.p, cluster_sizes.p, bias16.p, states.p,   \
+                 active_d.p, hints.p, warp_update);                                                                 \
+    } while (0)
+    if (metric == METRIC_DOT) LB2_SMALL(METRIC_DOT); else LB2_SMALL(METRIC_L2);
+#undef LB2_SMALL
+    d2h(h_states.data(), states.p, B);
+    sync_stream();
+    if (loss_out) loss_out->assign(1, h_states[0].last_loss);
+    if (iters_out) iters_out->assign(1, h_states[0].iters);
+    return;
+  }
   TcWorkspace tcws;
   TcPqWorkspace pqws;
   DevBuf<float> rn2;

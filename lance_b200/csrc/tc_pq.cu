@@ -346,18 +346,56 @@ pq_fallback_kernel(const float* __restrict__ r, uint64_t n, int M, const float* 
     const float* rp = r + row * (uint64_t)(M * DS) + m * DS;
     const float4 r0 = reinterpret_cast<const float4*>(rp)[0], r1 = reinterpret_cast<const float4*>(rp)[1];
     const float rv[DS] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-    float bv = __int_as_float(0x7f800000);
-    uint32_t bi = 0xffffffffu;
-#pragma unroll 4
-    for (int c = l; c < TN; c += 16) {
+    // Pre-screen with fused multiply-adds (8 FFMA per codeword instead of 24 separately rounded operations):
+    // s'(c) = r.c - |c|^2/2 differs from the true score by <= 2^-21 (|r|^2 + |c|^2) (8 fused steps, one rounding
+    // each, plus the rounded |c|^2), so the reference's argmin -- the codeword of maximal TRUE score -- has
+    // s'(c) >= max s' - tau2 with tau2 = 2^-18 (|r|^2 + max|c|^2): the reference's own f32 distances are within
+    // 2^-20 (|r|^2 + |c|^2) of the true ones, the pre-screen within 2^-21 on either side; twice their sum.  Only those
+    // few codewords get the reference-order distance; strict-< / lowest index among them is the reference's rule.
+    float rn = 0.0f;
+#pragma unroll
+    for (int t = 0; t < DS; ++t) rn = fmaf(rv[t], rv[t], rn);
+    float sc[TN / 16];
+    float smax = __int_as_float(0xff800000), cmax = 0.0f;
+#pragma unroll
+    for (int i = 0; i < TN / 16; ++i) {
+      const int c = l + 16 * i;
       const float4 c0 = reinterpret_cast<const float4*>(cbs + c * DS)[0];
       const float4 c1 = reinterpret_cast<const float4*>(cbs + c * DS)[1];
       const float cv[DS] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-      float s = 0.0f;
+      float dot = 0.0f, n2 = 0.0f;
 #pragma unroll
-      for (int t = 0; t < DS; ++t) s = f_add(s, sq_diff(rv[t], cv[t]));
-      const float v = f_add(s, 0.0f);
-      if (v < bv) { bv = v; bi = c; }
+      for (int t = 0; t < DS; ++t) {
+        dot = fmaf(rv[t], cv[t], dot);
+        n2 = fmaf(cv[t], cv[t], n2);
+      }
+      sc[i] = fmaf(-0.5f, n2, dot);
+      smax = fmaxf(smax, sc[i]);
+      cmax = fmaxf(cmax, n2);
+    }
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {
+      smax = fmaxf(smax, __shfl_xor_sync(mask, smax, off, 16));
+      cmax = fmaxf(cmax, __shfl_xor_sync(mask, cmax, off, 16));
+    }
+    const float thr = smax - 3.814697265625e-6f * (rn + cmax);  // 2^-18
+    float bv = __int_as_float(0x7f800000);
+    uint32_t bi = 0xffffffffu;
+    // a NaN anywhere (row or codebook) makes smax / thr NaN or leaves NaN scores: `!(sc < thr)` keeps every
+    // such codeword, and the exact arithmetic below decides exactly as the full scan would
+#pragma unroll
+    for (int i = 0; i < TN / 16; ++i) {
+      if (!(sc[i] < thr)) {
+        const int c = l + 16 * i;
+        const float4 c0 = reinterpret_cast<const float4*>(cbs + c * DS)[0];
+        const float4 c1 = reinterpret_cast<const float4*>(cbs + c * DS)[1];
+        const float cv[DS] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        float sacc = 0.0f;
+#pragma unroll
+        for (int t = 0; t < DS; ++t) sacc = f_add(sacc, sq_diff(rv[t], cv[t]));
+        const float v = f_add(sacc, 0.0f);
+        if (v < bv) { bv = v; bi = c; }
+      }
     }
 #pragma unroll
     for (int off = 8; off >= 1; off >>= 1) {
