@@ -143,6 +143,7 @@ __global__ void scatter_kernel(const uint32_t* __restrict__ ids, const uint8_t* 
 constexpr int SORT_CLUSTER = 8;
 // the sort of ONE problem by the calling cluster (8 CTAs x 1024 threads; sm = 34 * K words of shared memory):
 // also the member-list phase of the fused small-problem kernel below
+template <int NT>
 __device__ __forceinline__ void cluster_sort_body(const uint32_t* __restrict__ idb, const uint8_t* __restrict__ vb,
                                                   uint64_t n, int K, uint32_t* __restrict__ counts_b,
                                                   uint32_t* __restrict__ offsets_b, uint32_t* __restrict__ mem,
@@ -150,16 +151,18 @@ __device__ __forceinline__ void cluster_sort_body(const uint32_t* __restrict__ i
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = cluster.block_rank();
-  uint32_t* wh = sm;             // [32][K] per-warp histogram, then running counters
-  uint32_t* tot = sm + 32 * K;   // [K]     this CTA's per-key total (read by the other CTAs)
+  constexpr int NW = NT / 32;
+  uint32_t* wh = sm;             // [NW][K] per-warp histogram, then running counters
+  uint32_t* tot = sm + NW * K;   // [K]     this CTA's per-key total (read by the other CTAs)
   uint32_t* off = tot + K;       // [K]     first output slot of this CTA's rows, per key
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < 32 * K; i += 1024) wh[i] = 0;
+  for (int i = tid; i < NW * K; i += NT) wh[i] = 0;
+  if (tid < 32) wsum[tid] = 0;
   __syncthreads();
   constexpr uint32_t NONE = 0xffffffffu;
-  const uint64_t nwarps = 32ull * SORT_CLUSTER;
+  const uint64_t nwarps = (uint64_t)NW * SORT_CLUSTER;
   const uint64_t chunk = ((n + nwarps - 1) / nwarps + 31) / 32 * 32;  // rows per warp, multiple of 32
-  const uint64_t r0 = min(n, ((uint64_t)crank * 32 + w) * chunk), r1 = min(n, r0 + chunk);
+  const uint64_t r0 = min(n, ((uint64_t)crank * NW + w) * chunk), r1 = min(n, r0 + chunk);
   for (uint64_t base = r0; base < r1; base += 32 * 8) {  // 8 independent loads in flight per lane
     uint32_t key[8];
 #pragma unroll
@@ -172,9 +175,9 @@ __device__ __forceinline__ void cluster_sort_body(const uint32_t* __restrict__ i
       if (key[u] != NONE) atomicAdd(&wh[w * K + key[u]], 1u);
   }
   __syncthreads();
-  if (tid < K) {  // exclusive scan over this CTA's 32 warps
+  if (tid < K) {  // exclusive scan over this CTA's warps
     uint32_t run = 0;
-    for (int ww = 0; ww < 32; ++ww) {
+    for (int ww = 0; ww < NW; ++ww) {
       const uint32_t t = wh[ww * K + tid];
       wh[ww * K + tid] = run;
       run += t;
@@ -254,8 +257,8 @@ cluster_sort_kernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict_
   if (active && !active[b]) return;  // uniform over the cluster
   extern __shared__ uint32_t sm[];
   __shared__ uint32_t wsum[32];
-  cluster_sort_body(ids + (size_t)b * n, valid ? valid + (size_t)b * n : nullptr, n, K, counts + (size_t)b * K,
-                    offsets + (size_t)b * (K + 1), members + (size_t)b * n, sm, wsum);
+  cluster_sort_body<1024>(ids + (size_t)b * n, valid ? valid + (size_t)b * n : nullptr, n, K, counts + (size_t)b * K,
+                          offsets + (size_t)b * (K + 1), members + (size_t)b * n, sm, wsum);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -886,7 +889,7 @@ epilogue_kernel(int K, int ds, uint64_t n, float bf_param, double tolerance,
 // ------------------------------------------------------------------------------------------------
 // Small problems (hierarchical k-means splits a cluster with k' <= 16, kmeans.rs:885-895: thousands of
 // Lloyd runs over a few hundred .. a few thousand rows): the WHOLE run in one launch.  A thread-block
-// cluster of 8 CTAs x 1024 threads iterates  assign (exact, 16 lanes per row = the reference's lane
+// cluster of 8 CTAs x 512 threads iterates  assign (exact, 16 lanes per row = the reference's lane
 // accumulators) -> stable member sort (cluster_sort_body) -> ordered centroid sums + f64 loss (the same
 // update_body_warp / stats_body as the general path) -> scalar epilogue (epilogue_body, CTA 0)  with cluster
 // barriers between the phases; nothing returns to the host until the run has converged.  Same device functions,
@@ -894,8 +897,9 @@ epilogue_kernel(int K, int ds, uint64_t n, float bf_param, double tolerance,
 // iteration instead of ~10 launches.
 // ------------------------------------------------------------------------------------------------
 constexpr int SMALL_UPD_WARPS = 8;  // warps per CTA that run update / stats tasks (one 4 KB tile each)
+constexpr int SMALL_NT = 512;       // 512 threads: 128 registers each (the update / stats bodies need them)
 template <int METRIC>
-__global__ void __cluster_dims__(SORT_CLUSTER, 1, 1) __launch_bounds__(1024)
+__global__ void __cluster_dims__(SORT_CLUSTER, 1, 1) __launch_bounds__(SMALL_NT)
 lloyd_small_kernel(const float* __restrict__ x, uint32_t n, int d, int K, float* __restrict__ centroids,
                    float bf_param, double tolerance, int max_iters, uint32_t* __restrict__ ids,
                    float* __restrict__ dists, uint8_t* __restrict__ valid, uint32_t* __restrict__ counts,
@@ -910,16 +914,16 @@ lloyd_small_kernel(const float* __restrict__ x, uint32_t n, int d, int K, float*
   float* cs = reinterpret_cast<float*>(small_smem);                    // [K][d] centroids of this iteration
   float* sb = cs + (size_t)K * d;                                       // [16] bias
   float* tiles = sb + 16;                                               // [SMALL_UPD_WARPS][UPD_TILE * 8]
-  uint32_t* sort_sm = reinterpret_cast<uint32_t*>(tiles + SMALL_UPD_WARPS * UPD_TILE * 8);  // [34 * K]
+  uint32_t* sort_sm = reinterpret_cast<uint32_t*>(tiles + SMALL_UPD_WARPS * UPD_TILE * 8);  // [(NT/32 + 2) * K]
   __shared__ uint32_t wsum[32];
   const int tid = threadIdx.x, warp = tid >> 5, l = tid & 15;
   const unsigned hmask = 0xffffu << (16 * ((tid >> 4) & 1));
   const int n16 = d & ~15;
   const int nch = d >> 3;
-  const uint32_t hw_global = crank * 64 + (tid >> 4), hw_total = SORT_CLUSTER * 64;  // half-warps of the cluster
+  const uint32_t hw_global = crank * (SMALL_NT / 16) + (tid >> 4), hw_total = SORT_CLUSTER * (SMALL_NT / 16);  // half-warps
   for (int it = 1; it <= max_iters; ++it) {
     // ---- centroids + bias of this iteration into shared memory
-    for (int i = tid; i < K * d; i += 1024) cs[i] = centroids[i];
+    for (int i = tid; i < K * d; i += SMALL_NT) cs[i] = centroids[i];
     if (tid < 16) sb[tid] = tid < K ? bias[tid] : 0.0f;
     __syncthreads();
     // ---- membership (kmeans.rs:317-369): lane l of a half-warp owns lane accumulator l (l2.rs:82-88)
@@ -959,7 +963,7 @@ lloyd_small_kernel(const float* __restrict__ x, uint32_t n, int d, int K, float*
     __threadfence();
     cluster.sync();
     // ---- member lists (stable counting sort of the rows by cluster)
-    cluster_sort_body(ids, valid, n, K, counts, offsets, members, sort_sm, wsum);
+    cluster_sort_body<SMALL_NT>(ids, valid, n, K, counts, offsets, members, sort_sm, wsum);
     __threadfence();
     cluster.sync();
     // ---- ordered centroid sums (kmeans.rs:388-418) and per-cluster f64 loss / radius (kmeans.rs:266-280)
@@ -976,16 +980,16 @@ lloyd_small_kernel(const float* __restrict__ x, uint32_t n, int d, int K, float*
         }
       }
     } else {
-      for (size_t g = (size_t)crank * 1024 + tid; g < (size_t)K * d; g += (size_t)SORT_CLUSTER * 1024)
+      for (size_t g = (size_t)crank * SMALL_NT + tid; g < (size_t)K * d; g += (size_t)SORT_CLUSTER * SMALL_NT)
         update_body(g, x, d, d, K, 1, n, members, offsets, centroids, nullptr, 1);
-      for (int t = crank * 32 + warp; t < K; t += SORT_CLUSTER * 32)
+      for (int t = crank * (SMALL_NT / 32) + warp; t < K; t += SORT_CLUSTER * (SMALL_NT / 32))
         stats_body(t, dists, n, K, 1, members, offsets, losses, radius, last_row, nullptr, hints + 1);
     }
     __threadfence();
     cluster.sync();
     // ---- the iteration's scalar bookkeeping (cluster sizes, balance loss, split_clusters, tolerance test, bias)
     if (crank == 0)
-      epilogue_body<1024>(0, K, d, n, bf_param, tolerance, counts, losses, radius, last_row, cluster_sizes, bias,
+      epilogue_body<SMALL_NT>(0, K, d, n, bf_param, tolerance, counts, losses, radius, last_row, cluster_sizes, bias,
                           16, centroids, state, active, TcPqPrepArgs());
     __threadfence();
     cluster.sync();
@@ -1121,11 +1125,12 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
     DevBuf<float> bias16(16);
     bias16.zero();
     const int warp_update = (ds % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
-    const size_t smem = sizeof(float) * ((size_t)K * ds + 16 + SMALL_UPD_WARPS * UPD_TILE * 8) + sizeof(uint32_t) * 34 * (size_t)K;
+    const size_t smem = sizeof(float) * ((size_t)K * ds + 16 + SMALL_UPD_WARPS * UPD_TILE * 8) +
+                        sizeof(uint32_t) * (SMALL_NT / 32 + 2) * (size_t)K;
 #define LB2_SMALL(MET)                                                                                              \
     do {                                                                                                            \
       set_smem(lloyd_small_kernel<MET>, smem);                                                                      \
-      LB2_LAUNCH("kmeans_small_fused", lloyd_small_kernel<MET>, SORT_CLUSTER, 1024, smem, x, (uint32_t)n, ds, K,    \
+      LB2_LAUNCH("kmeans_small_fused", lloyd_small_kernel<MET>, SORT_CLUSTER, SMALL_NT, smem, x, (uint32_t)n, ds, K, \
                  centroids, balance_factor_param, tolerance, max_iters, ids.p, dists.p, valid.p, ms.counts.p,       \
                  ms.offsets.p, ms.members.p, losses.p, radius.p, last_row.p, cluster_sizes.p, bias16.p, states.p,   \
                  active_d.p, hints.p, warp_update);                                                                 \

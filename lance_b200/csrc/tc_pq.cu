@@ -318,100 +318,127 @@ __global__ void residual_norms_kernel(const float* x, const float* __restrict__ 
   rn2[g] = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
 }
 
-// exact scan of all 256 codewords for the (row, sub-space) pairs the filter could not decide.  The
-// filter appends the rows to one list per sub-space, so a CTA stages that sub-space's codebook (8 KB)
-// in shared memory once and serves its share of the list from there: half-warp per pair, lane l scans
-// codewords l, l+16, ... (ascending), lexicographic (value, index) min.
+// The (row, sub-space) pairs the filter could not decide.  The filter appends the rows to one list per sub-space,
+// so a CTA stages that sub-space's codebook (8 KB) and -|c|^2/2 in shared memory once and serves its share of the
+// list from there, TWO pairs per half-warp at a time (each codeword fetched from shared memory serves two rows:
+// the kernel is bound by that traffic otherwise), lane l owning codewords l, l+16, ...:
+//   1. pre-screen with fused multiply-adds: s'(c) = r.c - |c|^2/2, 8 FFMA per codeword instead of 24 separately
+//      rounded operations.  s' is within 2^-21 (|r|^2 + |c|^2) of the true score (8 fused steps, one rounding
+//      each, plus the rounded |c|^2), and the reference's own f32 distances are within 2^-20 (|r|^2 + |c|^2) of
+//      the true ones, so the reference's argmin has s'(c) >= max s' - 2^-18 (|r|^2 + max|c|^2) (twice the sum);
+//   2. only those few codewords get the reference-order distance (sequential 8-term sum, l2.rs:69-79), with the
+//      reference's strict-< / lowest-index rule among them.
+// A NaN anywhere makes the threshold or the scores NaN: `!(s' < thr)` then keeps the codeword and the exact
+// arithmetic decides as a full scan would.
+constexpr int FB_P = 2;
+// reference-order distance of one candidate codeword (kept out of line: the 32 unrolled call sites would otherwise
+// be if-converted with all their shared-memory loads hoisted -- 250 registers)
+static __device__ __noinline__ void fb_exact_candidate(const float* rvq, const float* cp, int c, float& bv, uint32_t& bi) {
+  float sacc = 0.0f;
+#pragma unroll
+  for (int t = 0; t < DS; ++t) sacc = f_add(sacc, sq_diff(rvq[t], cp[t]));
+  const float v = f_add(sacc, 0.0f);
+  if (v < bv) { bv = v; bi = (uint32_t)c; }
+}
 template <bool TRAIN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 pq_fallback_kernel(const float* __restrict__ r, uint64_t n, int M, const float* __restrict__ cb,
                    const uint32_t* __restrict__ pairs, const uint32_t* __restrict__ count,
                    const uint8_t* __restrict__ row_valid, uint8_t* __restrict__ codes,
                    uint32_t* __restrict__ ids, float* __restrict__ dists, uint8_t* __restrict__ valid) {
   __shared__ __align__(16) float cbs[TN * DS];
+  __shared__ float cnh_s[TN];
+  __shared__ float s_cmax;
   const int m = blockIdx.x;
   const uint32_t total = count[m];
-  if (blockIdx.y * 16u >= total) return;  // uniform
+  if (blockIdx.y * (16u * FB_P) >= total) return;  // uniform
   {
     const float4* src = reinterpret_cast<const float4*>(cb + (size_t)m * TN * DS);
     float4* dst = reinterpret_cast<float4*>(cbs);
     for (int i = threadIdx.x; i < TN * DS / 4; i += 256) dst[i] = src[i];
   }
   __syncthreads();
+  {
+    const int c = threadIdx.x;  // 256 threads == 256 codewords
+    float n2 = 0.0f;
+#pragma unroll
+    for (int t = 0; t < DS; ++t) n2 = fmaf(cbs[c * DS + t], cbs[c * DS + t], n2);
+    cnh_s[c] = -0.5f * n2;
+    float mx = n2;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (c == 0) s_cmax = 0.0f;
+    __syncthreads();
+    if ((c & 31) == 0) atomicMax(reinterpret_cast<int*>(&s_cmax), __float_as_int(mx));  // n2 >= 0: int order == float order
+    __syncthreads();
+  }
+  const float cmax = s_cmax;  // NaN codewords: mx is NaN -> as an int it is larger than every number: thr turns NaN
   const int l = threadIdx.x & 15;
   const unsigned mask = 0xffffu << (16 * ((threadIdx.x >> 4) & 1));
   const uint32_t* list = pairs + (size_t)m * n;
-  for (uint32_t p = blockIdx.y * 16u + (threadIdx.x >> 4); p < total; p += gridDim.y * 16u) {
-    const uint64_t row = list[p];
-    const float* rp = r + row * (uint64_t)(M * DS) + m * DS;
-    const float4 r0 = reinterpret_cast<const float4*>(rp)[0], r1 = reinterpret_cast<const float4*>(rp)[1];
-    const float rv[DS] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-    // Pre-screen with fused multiply-adds (8 FFMA per codeword instead of 24 separately rounded operations):
-    // s'(c) = r.c - |c|^2/2 differs from the true score by <= 2^-21 (|r|^2 + |c|^2) (8 fused steps, one rounding
-    // each, plus the rounded |c|^2), so the reference's argmin -- the codeword of maximal TRUE score -- has
-    // s'(c) >= max s' - tau2 with tau2 = 2^-18 (|r|^2 + max|c|^2): the reference's own f32 distances are within
-    // 2^-20 (|r|^2 + |c|^2) of the true ones, the pre-screen within 2^-21 on either side; twice their sum.  Only those
-    // few codewords get the reference-order distance; strict-< / lowest index among them is the reference's rule.
-    float rn = 0.0f;
+  for (uint32_t p0 = (blockIdx.y * 16u + (threadIdx.x >> 4)) * FB_P; p0 < total; p0 += gridDim.y * 16u * FB_P) {
+    float rv[FB_P][DS], rn[FB_P];
+    uint64_t rows[FB_P];
 #pragma unroll
-    for (int t = 0; t < DS; ++t) rn = fmaf(rv[t], rv[t], rn);
-    float sc[TN / 16];
-    float smax = __int_as_float(0xff800000), cmax = 0.0f;
+    for (int q = 0; q < FB_P; ++q) {
+      rows[q] = list[min(p0 + q, total - 1)];  // the tail repeats the last pair (same result written twice)
+      const float* rp = r + rows[q] * (uint64_t)(M * DS) + m * DS;
+      const float4 r0 = reinterpret_cast<const float4*>(rp)[0], r1 = reinterpret_cast<const float4*>(rp)[1];
+      rv[q][0] = r0.x; rv[q][1] = r0.y; rv[q][2] = r0.z; rv[q][3] = r0.w;
+      rv[q][4] = r1.x; rv[q][5] = r1.y; rv[q][6] = r1.z; rv[q][7] = r1.w;
+      rn[q] = 0.0f;
+#pragma unroll
+      for (int t = 0; t < DS; ++t) rn[q] = fmaf(rv[q][t], rv[q][t], rn[q]);
+    }
+    float sc[FB_P][TN / 16], smax[FB_P];
+#pragma unroll
+    for (int q = 0; q < FB_P; ++q) smax[q] = __int_as_float(0xff800000);
 #pragma unroll
     for (int i = 0; i < TN / 16; ++i) {
       const int c = l + 16 * i;
       const float4 c0 = reinterpret_cast<const float4*>(cbs + c * DS)[0];
       const float4 c1 = reinterpret_cast<const float4*>(cbs + c * DS)[1];
       const float cv[DS] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-      float dot = 0.0f, n2 = 0.0f;
+      const float ch = cnh_s[c];
 #pragma unroll
-      for (int t = 0; t < DS; ++t) {
-        dot = fmaf(rv[t], cv[t], dot);
-        n2 = fmaf(cv[t], cv[t], n2);
+      for (int q = 0; q < FB_P; ++q) {
+        float dot = ch;
+#pragma unroll
+        for (int t = 0; t < DS; ++t) dot = fmaf(rv[q][t], cv[t], dot);
+        sc[q][i] = dot;
+        smax[q] = fmaxf(smax[q], dot);
       }
-      sc[i] = fmaf(-0.5f, n2, dot);
-      smax = fmaxf(smax, sc[i]);
-      cmax = fmaxf(cmax, n2);
+      // (keeps the compiler from hoisting all 16 codeword loads to the top: 144 live registers otherwise)
+      if ((i & 3) == 3) asm volatile("" ::: "memory");
     }
 #pragma unroll
-    for (int off = 8; off >= 1; off >>= 1) {
-      smax = fmaxf(smax, __shfl_xor_sync(mask, smax, off, 16));
-      cmax = fmaxf(cmax, __shfl_xor_sync(mask, cmax, off, 16));
-    }
-    const float thr = smax - 3.814697265625e-6f * (rn + cmax);  // 2^-18
-    float bv = __int_as_float(0x7f800000);
-    uint32_t bi = 0xffffffffu;
-    // a NaN anywhere (row or codebook) makes smax / thr NaN or leaves NaN scores: `!(sc < thr)` keeps every
-    // such codeword, and the exact arithmetic below decides exactly as the full scan would
+    for (int q = 0; q < FB_P; ++q) {
 #pragma unroll
-    for (int i = 0; i < TN / 16; ++i) {
-      if (!(sc[i] < thr)) {
-        const int c = l + 16 * i;
-        const float4 c0 = reinterpret_cast<const float4*>(cbs + c * DS)[0];
-        const float4 c1 = reinterpret_cast<const float4*>(cbs + c * DS)[1];
-        const float cv[DS] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-        float sacc = 0.0f;
+      for (int off = 8; off >= 1; off >>= 1) smax[q] = fmaxf(smax[q], __shfl_xor_sync(mask, smax[q], off, 16));
+      const float thr = smax[q] - 3.814697265625e-6f * (rn[q] + cmax);  // 2^-18
+      float bv = __int_as_float(0x7f800000);
+      uint32_t bi = 0xffffffffu;
 #pragma unroll
-        for (int t = 0; t < DS; ++t) sacc = f_add(sacc, sq_diff(rv[t], cv[t]));
-        const float v = f_add(sacc, 0.0f);
-        if (v < bv) { bv = v; bi = c; }
+      for (int i = 0; i < TN / 16; ++i) {
+        if (!(sc[q][i] < thr)) fb_exact_candidate(rv[q], cbs + (l + 16 * i) * DS, l + 16 * i, bv, bi);
       }
-    }
 #pragma unroll
-    for (int off = 8; off >= 1; off >>= 1) {
-      const float ov = __shfl_xor_sync(mask, bv, off, 16);
-      const uint32_t oi = __shfl_xor_sync(mask, bi, off, 16);
-      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-    }
-    if (l == 0) {
-      const bool ok = bi != 0xffffffffu;
-      if (TRAIN) {
-        ids[(uint64_t)m * n + row] = ok ? bi : 0u;
-        dists[(uint64_t)m * n + row] = ok ? bv : __int_as_float(0x7fc00000);
-        valid[(uint64_t)m * n + row] = ok ? 1 : 0;
-      } else {
-        const bool rv_ok = row_valid ? row_valid[row] != 0 : true;
-        codes[row * (uint64_t)M + m] = (ok && rv_ok) ? (uint8_t)bi : (uint8_t)0;
+      for (int off = 8; off >= 1; off >>= 1) {
+        const float ov = __shfl_xor_sync(mask, bv, off, 16);
+        const uint32_t oi = __shfl_xor_sync(mask, bi, off, 16);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+      if (l == 0) {
+        const uint64_t row = rows[q];
+        const bool ok = bi != 0xffffffffu;
+        if (TRAIN) {
+          ids[(uint64_t)m * n + row] = ok ? bi : 0u;
+          dists[(uint64_t)m * n + row] = ok ? bv : __int_as_float(0x7fc00000);
+          valid[(uint64_t)m * n + row] = ok ? 1 : 0;
+        } else {
+          const bool rv_ok = row_valid ? row_valid[row] != 0 : true;
+          codes[row * (uint64_t)M + m] = (ok && rv_ok) ? (uint8_t)bi : (uint8_t)0;
+        }
       }
     }
   }
@@ -462,7 +489,7 @@ void tc_pq_assign(const float* r, const float* rn2, uint64_t n, int d, int M, co
   const float* cnh = ws->cnh.p;
   const float* cbmax2 = ws->cnh.p + (size_t)M * tc::TN;
   // per sub-space: enough CTAs (16 pairs per pass each) for the worst case, capped; idle ones exit at once
-  const dim3 fb_grid((unsigned)M, (unsigned)std::min<uint64_t>(cdiv(n, 16), std::max(1, 8 * ctx().num_sms / M)));
+  const dim3 fb_grid((unsigned)M, (unsigned)std::min<uint64_t>(cdiv(n, 16 * tcpq::FB_P), std::max(1, 8 * ctx().num_sms / M)));
 #define LB2_PQ_FILTER(TRAINV, STREAMV)                                                                      \
   do {                                                                                                      \
     set_smem(tc_pq_kernel<TRAINV, STREAMV>, smem);                                                          \
