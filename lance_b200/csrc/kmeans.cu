@@ -932,11 +932,19 @@ lloyd_small_kernel(const float* __restrict__ x, uint32_t n, int d, int K, float*
       float acc[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
-      for (int e = l; e < n16; e += 16) {
-        const float xe = xv[e];
+      for (int e0 = l; e0 < n16; e0 += 16 * 8) {  // eight row elements in flight per lane (the loads are what costs)
+        float xr[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < K) acc[j] = f_add(acc[j], term<METRIC>(xe, cs[j * d + e]));
+        for (int u = 0; u < 8; ++u) xr[u] = e0 + 16 * u < n16 ? xv[e0 + 16 * u] : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + 16 * u;
+          if (e < n16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < K) acc[j] = f_add(acc[j], term<METRIC>(xr[u], cs[j * d + e]));
+          }
+        }
       }
       float best_key = __int_as_float(0x7f800000), best_val = best_key;
       uint32_t best_idx = 0xffffffffu;
@@ -999,9 +1007,10 @@ lloyd_small_kernel(const float* __restrict__ x, uint32_t n, int d, int K, float*
 
 static bool lloyd_small_ok(uint64_t n, int B, int ds, int K, bool dist) {
   static const bool off = getenv("LB2_NO_SMALL_KMEANS") && *getenv("LB2_NO_SMALL_KMEANS");
-  // one cluster = 8 SMs of plain FP32: worth it while the membership pass stays below ~50 MFLOP per iteration
+  // one cluster = 8 SMs of plain FP32 against ~10 launches: measured (tools/small_kmeans_timing.py) to pay off only
+  // for the tiniest runs (n * k * d <= 2^20, e.g. 512 rows x 2 centroids x 128: 43 vs 66 us per iteration)
   return !off && !dist && B == 1 && K >= 1 && K <= 16 && n >= 1 && n <= 16384 && (uint64_t)K * ds <= 24576 &&
-         n * (uint64_t)K * ds <= (1ull << 24) && !ctx().profiling;
+         n * (uint64_t)K * ds <= (1ull << 20) && !ctx().profiling;
 }
 
 // ------------------------------------------------------------------------------------------------
