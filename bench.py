@@ -135,7 +135,7 @@ def device_dataset(torch, n, nq, seed, device, qseed=99):
     return data, draw(nq)
 
 
-def ground_truth(torch, data, queries, k, row_base=0, cosine=False):
+def ground_truth(torch, data, queries, k, row_base=0, cosine=False, return_dists=False):
     """exact top-k by brute force on the device, chunked over the rows (f32, TF32 off)"""
     torch.backends.cuda.matmul.allow_tf32 = False
     q = queries.float()
@@ -153,6 +153,8 @@ def ground_truth(torch, data, queries, k, row_base=0, cosine=False):
         ci = torch.cat([best_i, torch.arange(s, s + x.shape[0], device=q.device)[None, :].expand(q.shape[0], -1) + row_base], 1)
         o = torch.topk(cd, k, dim=1, largest=False)
         best_d, best_i = o.values, torch.gather(ci, 1, o.indices)
+    if return_dists:
+        return best_i, best_d
     return best_i.cpu().numpy()
 
 

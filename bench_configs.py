@@ -138,7 +138,8 @@ def run(args, cfg, B):
     fams = {f: {"launches_per_step": c, "ms_per_step": ms, "share": ms / ms_prof}
             for f, (c, ms) in sorted(lb.profile.dump().items(), key=lambda kv: -kv[1][1])}
     hbm_peak, tensor_peak, peak_src = B.peaks()
-    filt = next((f for f in ("transform:tc_filter_general", "transform:tc_filter") if f in fams), None)
+    filt = next((f for f in ("transform:tc_filter_general16", "transform:tc_filter_general", "transform:tc_filter") if f in fams), None)
+    traffic = B.load_ncu_traffic().get(f"{args.config}:{filt}") if filt else None
     roofline = None
     if filt:
         flops = 2.0 * n * K * d
@@ -146,7 +147,9 @@ def run(args, cfg, B):
         nl = fams[filt]["launches_per_step"]
         ach = flops / (ms * 1e-3) / 1e12
         roofline = {"kernel": filt, "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
-                    "frac": ach / tensor_peak, "traffic": None, "peak_source": peak_src + " bf16 dense, sustained; the kernel runs kind::tf32 (half the bf16 rate)",
+                    "frac": ach / tensor_peak, "traffic": traffic,
+                    "peak_source": peak_src + " bf16 dense, sustained; " + ("the kernel runs kind::f16 on the native 16-bit rows"
+                                                                            if filt.endswith("16") else "the kernel runs kind::tf32 on f32 rows (half the bf16 rate)"),
                     "algorithmic_flops_per_launch": flops / nl, "avg_launch_ms": ms / nl, "launches": nl,
                     "hbm_GBps_streaming_x": n * d * esize / (ms * 1e-3) / 1e9}
     top = dict(list(fams.items())[:14])
@@ -211,14 +214,22 @@ def run(args, cfg, B):
         fn(q_dev, TOPK, nprobes, out=(ids_dev, d_dev))
     q_ms = max_over_ranks(lb.timer_stop() / qsteps)
     NG = 200
-    gt_local = B.ground_truth(torch, data_t, queries_t[:NG], TOPK, row_base=row_base, cosine=(metric == "cosine"))
-    recall = None
-    if world == 1:
-        got = ids_t[:NG].cpu().numpy()
-        recall = float(np.mean([len(set(got[i].tolist()) & set(gt_local[i].tolist())) / TOPK for i in range(NG)]))
+    gi, gd = B.ground_truth(torch, data_t, queries_t[:NG], TOPK, row_base=row_base, cosine=(metric == "cosine"),
+                            return_dists=True)
+    if world > 1:   # exact top-k over ALL shards: gather every rank's exact list, keep the k nearest
+        li = [torch.empty_like(gi) for _ in range(world)]
+        ld = [torch.empty_like(gd) for _ in range(world)]
+        dist.all_gather(li, gi)
+        dist.all_gather(ld, gd)
+        ci, cd = torch.cat(li, 1), torch.cat(ld, 1)
+        o = torch.topk(cd, TOPK, dim=1, largest=False).indices
+        gi = torch.gather(ci, 1, o)
+    gt_local = gi.cpu().numpy()
+    got = ids_t[:NG].cpu().numpy()
+    recall = float(np.mean([len(set(got[i].tolist()) & set(gt_local[i].tolist())) / TOPK for i in range(NG)]))
     query = {"qps": NQ / (q_ms * 1e-3), "ms_per_batch": q_ms, "batch": NQ, "k": TOPK, "nprobes": nprobes,
              "recall_at_10": recall, "indexed_rows": world * n,
-             "note": "recall against exact brute force over this GPU's rows (N=1); sharded runs merge in the library"}
+             "note": "recall against exact brute force over ALL shards; sharded runs merge in the library (lb2_index_search_sharded)"}
     ix.close()
 
     # ---- e2e: pinned host -> build -> export to host ------------------------------------------------------------

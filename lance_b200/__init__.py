@@ -185,10 +185,11 @@ def train_kmeans(array, dimension, k, max_iters=50, redos=1, distance_type="l2",
     return KMeans(out, dimension, distance_type, loss.value, iters.value)
 
 
-def compute_partitions(centroids, vectors, distance_type="l2"):
+def compute_partitions(centroids, vectors, distance_type="l2", bf16=False):
     """compute_partitions_arrow_array (kmeans.rs:1187-1246) ->
-    (part_ids u32[n], dists f32[n], valid bool[n]); valid False == the reference's None."""
-    vectors, dt = _typed(vectors)
+    (part_ids u32[n], dists f32[n], valid bool[n]); valid False == the reference's None.
+    The model has the rows' element type (bf16=True: both are uint16 bit patterns)."""
+    vectors, dt = _typed(vectors, bf16)
     centroids = np.ascontiguousarray(centroids, dtype=_model_np(dt))
     k, d = centroids.shape
     n = vectors.shape[0]

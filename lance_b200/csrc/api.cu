@@ -13,6 +13,7 @@
 #include "exact.cuh"
 #include "kmeans.cuh"
 #include "search.cuh"
+#include "tc_assign.cuh"
 #include "tc_pq.cuh"
 
 namespace lb2 {
@@ -390,8 +391,10 @@ class Source {
   const float* rows_f32(uint64_t r0, uint64_t rows) {
     const void* nat = native_device();
     const size_t off = (size_t)r0 * d_ * es_, cnt = (size_t)rows * d_;
+    last_native_ = nat ? static_cast<const uint8_t*>(nat) + off : nullptr;
     if (nat && dt_ == LB2_F32) return reinterpret_cast<const float*>(static_cast<const uint8_t*>(nat) + off);
     const int slot = (int)(calls_++ & 1);
+    if (!nat && dt_ != LB2_F32) last_native_ = nullptr;  // set below once the slot is known
     if (nat) {
       if (f32_[slot].n < cnt) f32_[slot].alloc(cnt);
       LB2_LAUNCH("convert_to_f32", to_f32_kernel, cdiv(cnt, 256), 256, 0, static_cast<const uint8_t*>(nat) + off,
@@ -403,10 +406,14 @@ class Source {
     if (!(staged_[slot] && staged_r0_[slot] == r0)) issue_copy(slot, r0, rows);
     staged_[slot] = false;
     LB2_CUDA(cudaStreamWaitEvent(ctx().stream, slot_ready_[slot], 0));
-    if (dt_ != LB2_F32)
+    if (dt_ != LB2_F32) {
       LB2_LAUNCH("convert_to_f32", to_f32_kernel, cdiv(cnt, 256), 256, 0, raw_[slot].p, (int)dt_, cnt, f32_[slot].p);
+      last_native_ = raw_[slot].p;
+    }
     return f32_[slot].p;
   }
+  // where the rows of the last rows_f32() view lie on the device in their own element type (nullptr: f32 itself)
+  const void* last_native() const { return last_native_; }
   // start the host-to-device copy of the NEXT chunk; call right after rows_f32() of the current chunk and
   // BEFORE launching the current chunk's kernels (the slot being refilled was last read by the chunk before it)
   void prefetch(uint64_t r0, uint64_t rows) {
@@ -445,6 +452,7 @@ class Source {
  private:
   bool staged_[2] = {false, false};
   uint64_t staged_r0_[2] = {0, 0};
+  const void* last_native_ = nullptr;
   const void* host_;
   uint64_t n_;
   int d_;
@@ -555,6 +563,17 @@ __global__ void members_to_u64_kernel(const uint32_t* __restrict__ members, uint
 // IVF_FLAT storage: the kept rows grouped by partition (stable), normalised when the metric is cosine
 // (IvfTransformer::new_flat, lance-index/src/vector/ivf.rs:149-185), written in the index's element type.
 // Rows are pulled from the caller's matrix in chunks of output positions (never a whole-matrix f32 copy).
+// rows `members[i]` of a matrix in its own element type -> consecutive rows (16 bytes per thread)
+__global__ void gather_rows_native_kernel(const uint4* __restrict__ src, uint32_t vec_per_row,
+                                          const uint32_t* __restrict__ members, uint64_t kept, uint4* __restrict__ dst) {
+  const uint64_t total = kept * vec_per_row;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = g / vec_per_row;
+    const uint32_t v = (uint32_t)(g % vec_per_row);
+    dst[g] = src[(uint64_t)members[i] * vec_per_row + v];
+  }
+}
+
 static void index_load_flat_src(lb2_index* ix, const uint32_t* part_ids, Source& src, const uint64_t* row_ids,
                                 const uint8_t* valid, bool normalize) {
   const uint64_t n = src.n();
@@ -570,6 +589,14 @@ static void index_load_flat_src(lb2_index* ix, const uint32_t* part_ids, Source&
   if (!nat) fail(LB2_OOM, "IVF_FLAT keeps a copy of the vectors: the %llu x %d matrix must fit in device memory",
                  (unsigned long long)n, ix->d);
   const int d = ix->d;
+  if (!normalize && vdt == src.dtype() && ix->vrow_bytes() % 16 == 0 && (reinterpret_cast<uintptr_t>(nat) & 15) == 0) {
+    // stored type == column type: one pass, no f32 round trip (C4: 2 x 55 GB of bf16 at HBM speed)
+    const uint32_t vpr = (uint32_t)(ix->vrow_bytes() / 16);
+    LB2_LAUNCH("group_vectors", gather_rows_native_kernel, (unsigned)std::min<uint64_t>(cdiv(kept * vpr, 256), 64ull * ctx().num_sms),
+               256, 0, static_cast<const uint4*>(nat), vpr, ms.members.p, kept, reinterpret_cast<uint4*>(ix->vectors.p));
+    sync_stream();
+    return;
+  }
   const uint64_t chunk = src.rows_per_chunk();
   DevBuf<uint64_t> rows64(std::min(chunk, kept));
   DevBuf<float> tmp, tmp2;
@@ -701,7 +728,10 @@ static void for_each_chunk(Source& src, F&& f) {
     const uint64_t rows = std::min(step, n - r0);
     const float* xf = src.rows_f32(r0, rows);
     if (r0 + rows < n) src.prefetch(r0 + rows, std::min(step, n - r0 - rows));
+    // f16 / bf16 columns: the tensor-core filter reads the native rows (tc_assign.cu, "native 16-bit rows")
+    tc_set_operand_hint(xf, src.last_native(), (int)src.dtype(), (size_t)rows * src.d());
     f(xf, r0, rows);
+    tc_set_operand_hint(nullptr, nullptr, 0, 0);
   }
 }
 

@@ -114,6 +114,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate)
       : "memory");
 }
+// 16-bit operands (kind::f16): a/b format F16 = 0, BF16 = 1; one instruction covers K = 16 elements (32 B of a
+// 128-byte swizzled row, like K = 8 for TF32), f32 accumulation, twice the TF32 rate
+constexpr uint32_t IDESC_F16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+constexpr uint32_t IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+// OPK: 0 = f32 operands as TF32, 1 = f16, 2 = bf16
+template <int OPK>
+__device__ __forceinline__ void umma_op(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+  if (OPK == 0) {
+    umma_tf32(d_tmem, a_desc, b_desc, accumulate);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(OPK == 1 ? IDESC_F16 : IDESC_BF16), "r"(accumulate)
+        : "memory");
+  }
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -223,9 +241,53 @@ __device__ __forceinline__ void top3_row256(uint32_t taddr, const float* cn, flo
   for (int j = 0; j < TOUR_LEVELS; ++j) top3_insert(L[j], m1, m2, m3);
 }
 
+// ---- candidate pass: every column of a 256-column accumulator row whose score reaches thr -------------------
+// (rows that the top-3 passes could not settle; hits are rare, so the common path is one add + half a 3-input max
+// per column and a single compare per 32-column chunk)
+constexpr int CAND_SLOTS = 16;
+template <int C0>
+__device__ __forceinline__ void cand_chunk(const uint32_t* v, const float* cn, float thr, uint32_t col_base,
+                                           uint32_t* cnt, uint32_t* cand) {
+  float s[32];
+#pragma unroll
+  for (int u = 0; u < 32; ++u) s[u] = __uint_as_float(v[u]) + cn[C0 + u];
+  float m = s[0];
+#pragma unroll
+  for (int u = 1; u < 31; u += 2) m = fmaxf(fmaxf(m, s[u]), s[u + 1]);
+  m = fmaxf(m, s[31]);
+  if (m >= thr) {  // thr = +inf for rows beyond the list; NaN never compares true
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      if (s[u] >= thr) {
+        const uint32_t slot = atomicAdd(cnt, 1u);
+        if (slot < (uint32_t)CAND_SLOTS) cand[slot] = col_base + (uint32_t)(C0 + u);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void cand_row256(uint32_t taddr, const float* cn, float thr, uint32_t col_base,
+                                            uint32_t* cnt, uint32_t* cand) {
+  uint32_t va[32], vb[32];
+  tmem_ld32(taddr, va);
+#define LB2_CAND_STEP(C)                                   \
+  tmem_wait_ld(va);                                        \
+  tmem_ld32(taddr + (C) + 32, vb);                         \
+  cand_chunk<(C)>(va, cn, thr, col_base, cnt, cand);       \
+  tmem_wait_ld(vb);                                        \
+  if ((C) + 64 < TN) tmem_ld32(taddr + (C) + 64, va);      \
+  cand_chunk<(C) + 32>(vb, cn, thr, col_base, cnt, cand);
+  LB2_CAND_STEP(0)
+  LB2_CAND_STEP(64)
+  LB2_CAND_STEP(128)
+  LB2_CAND_STEP(192)
+#undef LB2_CAND_STEP
+}
+
 }  // namespace tc
 
 // host: 2-D f32 tensor map, box = [32 floats (128 B, SWIZZLE_128B)] x box_rows
 CUtensorMap make_map_2d(const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+// same for f16 / bf16 rows: box = [64 elements (128 B)] x box_rows
+CUtensorMap make_map_2d_16(const void* base, bool bf16, uint64_t rows, uint64_t cols, uint32_t box_rows);
 
 }  // namespace lb2

@@ -576,6 +576,78 @@ def test_tc_filter_adversarial_near_ties():
     assert np.array_equal(p1[v1], po[vo]) and np.array_equal(d1[v1], do[vo])
 
 
+def _tight_groups(rng, k, d, dtype=np.float32):
+    """centroids in groups of 8 that differ by ~1e-3 (far below the TF32 / accumulate resolution), duplicates"""
+    base = (rng.standard_normal((k // 8, d)) * 20).astype(np.float32)
+    cent = np.repeat(base, 8, axis=0) + (rng.standard_normal((k, d)) * 1e-3).astype(np.float32)
+    cent = cent.astype(dtype).astype(np.float32)
+    cent[17] = cent[16]
+    cent[40:44] = cent[40]
+    cent[k - 40:k - 20] = cent[k - 40]      # 20 identical: more candidates than slots -> full exact scan
+    return cent
+
+
+@pytest.mark.parametrize("n,d,k", [(5000, 128, 256), (6000, 96, 600), (3000, 768, 1024)])
+def test_tc_candidate_pass_matches_oracle(n, d, k, monkeypatch):
+    # LB2_FORCE_REFINE: the 3xTF32 top-3 pass + candidate pass + exact decision among candidates run even
+    # on small inputs (production takes them when n * K >= 2^26); every row must still match the oracle
+    monkeypatch.setenv("LB2_FORCE_REFINE", "1")
+    rng = np.random.default_rng(n + k)
+    cent = _tight_groups(rng, k, d)
+    data = (cent[rng.integers(0, k, n)] + rng.standard_normal((n, d)) * 0.3).astype(np.float32)
+    data[:64] = ((cent[0] + cent[9]) * 0.5).astype(np.float32)
+    data[64:96] = cent[k - 30]               # exactly on the 20-fold duplicate
+    data[100] = np.nan
+    data[101, 5] = np.inf
+    p1, d1, v1 = lb.compute_partitions(cent, data)
+    po, do, vo = ob.compute_membership(cent, data, nthreads=NT)
+    assert np.array_equal(v1, vo) and not v1[100] and not v1[101]
+    assert np.array_equal(p1[v1], po[vo]) and np.array_equal(d1[v1], do[vo])
+    # balance bias goes through the same passes
+    km = lb.train_kmeans(data[:2000], d, 16, max_iters=3, balance_factor=1.0, seed=3)
+    monkeypatch.delenv("LB2_FORCE_REFINE")
+    km2 = lb.train_kmeans(data[:2000], d, 16, max_iters=3, balance_factor=1.0, seed=3)
+    assert np.array_equal(km.centroids, km2.centroids)
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+@pytest.mark.parametrize("n,d,k", [(5000, 128, 512), (3000, 1536, 304)])
+def test_native_16bit_operands_match_oracle(dtype, n, d, k, monkeypatch):
+    # f16 / bf16 rows (the model has the same element type, so it is exact in it): the tensor-core passes read the
+    # native rows (kind::f16 MMAs).  Results must equal the oracle on the converted values -- with and without the
+    # candidate pass -- and the f32-staged path (LB2_NO_NATIVE16).
+    rng = np.random.default_rng(n + d + len(dtype))
+    if dtype == "f16":
+        to_t = lambda a: a.astype(np.float16)
+        to_f = lambda t: t.astype(np.float32)
+    else:
+        to_t = lambda a: (np.ascontiguousarray(a, np.float32).view(np.uint32) >> 16).astype(np.uint16)
+        to_f = lambda t: (t.astype(np.uint32) << 16).view(np.float32)
+    cent_t = to_t(_tight_groups(rng, k, d) * np.float32(0.05 if dtype == "f16" else 1.0))
+    cent = to_f(cent_t)
+    data = (cent[rng.integers(0, k, n)] + rng.standard_normal((n, d)) * 0.3).astype(np.float32)
+    data[:64] = ((cent[0] + cent[9]) * 0.5).astype(np.float32)
+    data[64:96] = cent[k - 30]
+    data[100] = np.nan
+    data_t = to_t(data)
+    data32 = to_f(data_t)
+    po, do, vo = ob.compute_membership(cent, data32, nthreads=NT)
+    run = lambda: lb.compute_partitions(cent_t, data_t, bf16=(dtype == "bf16"))
+    for force in ("", "1"):
+        monkeypatch.setenv("LB2_FORCE_REFINE", force)
+        p1, d1, v1 = run()
+        assert np.array_equal(v1, vo) and not v1[100]
+        assert np.array_equal(p1[v1], po[vo]) and np.array_equal(d1[v1], do[vo])
+    lb.profile.enable(True)
+    lb.profile.reset()
+    run()
+    lb.profile.enable(False)
+    assert lb.profile.get("tc_filter_general16")[0] == 1 and lb.profile.get("tc_candidates")[0] == 1
+    monkeypatch.setenv("LB2_NO_NATIVE16", "1")
+    p2, d2, v2 = run()
+    assert np.array_equal(p1[v1], p2[v2]) and np.array_equal(d1[v1], d2[v2])
+
+
 def test_tc_filter_sift_shaped_and_training():
     data = synth.sift_like(70000, 128, seed=31)
     init = data[np.random.default_rng(2).choice(70000, 256, replace=False)].copy()

@@ -8,7 +8,8 @@ import lance_b200 as lb
 
 os.environ["LB2_TC_STATS"] = "1"
 lb.set_device(0)
-NAMES = ("tc_filter", "tc_filter_general", "tc_rerank", "tc_refine_gather", "tc_refine_filter", "tc_refine_rerank",
+NAMES = ("tc_filter", "tc_filter_general", "tc_filter_general16", "tc_rerank", "tc_refine_gather", "tc_refine_filter",
+         "tc_refine_rerank", "tc_candidates", "tc_candidates_exact",
          "assign_exact_fallback", "tc_row_norms", "tc_prep_centroids", "assign_exact", "assign_exact_generic",
          "transpose_centroids")
 for n, d, K in ((200000, 768, 1024), (500000, 128, 4096), (500000, 256, 256), (100000, 1536, 512), (500000, 64, 1024)):
