@@ -1489,10 +1489,59 @@ void train_ivf(const float* xs, uint64_t s, int d, int K, int am, const lb2_kmea
                const float* init, float* centroids, std::vector<double>* loss, std::vector<uint32_t>* iters) {
   check_redos(kp.redos, kp.balance_factor);
   if (K > 256 && kp.hierarchical_k > 1 && !init) {
-    hierarchical_train(xs, s, d, K, am, kp.balance_factor / (float)(s * nranks), (int)kp.max_iters, kp.tolerance,
-                       (int)kp.hierarchical_k, kp.seed, centroids);
     loss->assign(1, 0.0);
     iters->assign(1, 0);
+    if (nranks > 1) {
+      // Sharded build: the hierarchical tree is thousands of small dependent Lloyd runs -- with a collective in
+      // every iteration it is latency-bound on the exchange.  The sample (K * sample_rate rows) is small next to
+      // the data, so when it fits every rank gathers ALL sample shards (rank order) and trains the same tree on
+      // them without a communicator: identical arithmetic on identical input gives bit-identical models on all
+      // ranks, and the splits train concurrently (kmeans.cu: SplitWorkers).  Otherwise: the sharded tree.
+      DevBuf<uint64_t> cnt_in(1), cnt_all(nranks);
+      h2d(cnt_in.p, &s, 1);
+      comm_allgather_bytes(cnt_in.p, cnt_all.p, sizeof(uint64_t));
+      std::vector<uint64_t> cnt(nranks);
+      d2h(cnt.data(), cnt_all.p, nranks);
+      sync_stream();
+      uint64_t total = 0, mx = 0;
+      for (uint64_t c : cnt) { total += c; mx = std::max(mx, c); }
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      const bool off = getenv("LB2_SHARDED_TREE") && *getenv("LB2_SHARDED_TREE");
+      if (!off && total < 0xffffffffull && (size_t)nranks * mx * d * 4 * 3 <= free_b) {
+        DevBuf<float> pad, all((size_t)nranks * mx * d);
+        const float* in = xs;
+        if (s < mx) {
+          pad.alloc((size_t)mx * d);
+          pad.zero();
+          if (s) d2d(pad.p, xs, (size_t)s * d);
+          in = pad.p;
+        }
+        comm_allgather_bytes(in, all.p, (size_t)mx * d * sizeof(float));
+        pad.release();
+        if (total != nranks * mx) {  // unequal shards: close the gaps (rank order is kept)
+          DevBuf<float> full(std::max<uint64_t>(total, 1) * d);
+          uint64_t o = 0;
+          for (uint64_t r = 0; r < nranks; ++r) {
+            if (cnt[r]) d2d(full.p + o * d, all.p + r * mx * d, cnt[r] * d);
+            o += cnt[r];
+          }
+          all = std::move(full);
+        }
+        Comm* saved = comm_swap(nullptr);
+        try {
+          hierarchical_train(all.p, total, d, K, am, kp.balance_factor / (float)total, (int)kp.max_iters, kp.tolerance,
+                             (int)kp.hierarchical_k, kp.seed, centroids);
+        } catch (...) {
+          comm_swap(saved);
+          throw;
+        }
+        comm_swap(saved);
+        return;
+      }
+    }
+    hierarchical_train(xs, s, d, K, am, kp.balance_factor / (float)(s * nranks), (int)kp.max_iters, kp.tolerance,
+                       (int)kp.hierarchical_k, kp.seed, centroids);
   } else {
     lloyd_train(xs, s, d, 1, d, K, am, kp.balance_factor / (float)(s * nranks), (int)kp.max_iters, kp.tolerance,
                 kp.seed, init, centroids, loss, iters);

@@ -57,6 +57,11 @@ thread_local Comm* g_comm = nullptr;
 }  // namespace
 
 Comm* current_comm() { return g_comm; }
+Comm* comm_swap(Comm* c) {
+  Comm* prev = g_comm;
+  g_comm = c;
+  return prev;
+}
 
 static void allreduce(void* buf, size_t count, int dtype, RedOp op) {
   Comm* c = g_comm;

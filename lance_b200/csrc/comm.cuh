@@ -10,6 +10,7 @@ struct Comm {
   int rank = 0, nranks = 1;
 };
 Comm* current_comm();  // nullptr when lb2_comm_init has not been called on this thread
+Comm* comm_swap(Comm* c);  // install c (may be nullptr) as this thread's communicator, return the previous one
 enum class RedOp { Sum, Max };
 // in-place all-reduce on the library's stream
 void comm_allreduce_f32(float* buf, size_t count, RedOp op);

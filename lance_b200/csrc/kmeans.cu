@@ -22,7 +22,17 @@
 #include <algorithm>
 #include <cmath>
 #include <limits>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <queue>
+#include <thread>
 #include <unordered_map>
+
+#include "../../include/lance_b200.h"
 
 #include "assign.cuh"
 #include "comm.cuh"
@@ -1213,7 +1223,12 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
   // by ~18 host launches per iteration.  (Event profiling and LB2_TC_STATS need eager launches.)
   const bool stats_env = getenv("LB2_TC_STATS") && *getenv("LB2_TC_STATS");
   // (NCCL collectives are capturable; the sharded iteration is replayed from the graph like the local one)
-  const bool use_graph = max_iters > 1 && !ctx().profiling && !stats_env &&
+  // (eager launches for the small splits of hierarchical training were tried and lose: 577 vs 481 ms for a
+  // K = 8192 tree -- the loop is bound by host launch throughput, which is what the graph relieves;
+  // LB2_GRAPH_MIN_ROWS=<rows> restores eager launches below that size)
+  const char* graph_min = getenv("LB2_GRAPH_MIN_ROWS");
+  const uint64_t graph_rows = graph_min && *graph_min ? strtoull(graph_min, nullptr, 10) : 0;
+  const bool use_graph = max_iters > 1 && !ctx().profiling && !stats_env && (dist || n * (uint64_t)B >= graph_rows) &&
                          !(getenv("LB2_NO_GRAPH") && *getenv("LB2_NO_GRAPH"));
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
@@ -1340,6 +1355,104 @@ __global__ void iota_kernel(uint32_t* p, uint32_t n) {
 }
 }  // namespace
 
+namespace {
+// ---- one split = gather the cluster's rows, Lloyd, membership, stable sort, children's row lists -----------------
+struct SplitOut {
+  int ck = 0;
+  std::vector<uint32_t> counts, offs;
+  DevBuf<float> subc;       // [ck][d]
+  DevBuf<uint32_t> order;   // the parent's row list re-ordered by (child, position), `kept` entries
+  uint32_t kept = 0;
+  std::map<std::string, ProfEntry> prof;  // kernels of a worker thread, merged into the caller's profile
+  uint64_t launches = 0;
+  std::exception_ptr err;
+};
+void split_cluster(const float* x, int d, const uint32_t* idx_seg, uint32_t loc, int ck, int metric, float balance_factor,
+                   int max_iters, double tolerance, uint64_t seed, SplitOut& o) {
+  o.ck = ck;
+  o.subc.alloc((size_t)ck * d);
+  const uint64_t n1 = std::max<uint32_t>(loc, 1);
+  DevBuf<float> sub(n1 * d);
+  DevBuf<uint32_t> ids(n1);
+  DevBuf<uint8_t> valid(n1);
+  if (loc)
+    LB2_LAUNCH("gather_rows", gather_rows_u32_kernel, cdiv((uint64_t)loc * d, 256), 256, 0, x, idx_seg, (uint64_t)loc, d,
+               sub.p);
+  lloyd_train(sub.p, loc, d, 1, d, ck, metric, balance_factor, max_iters, tolerance, seed, nullptr, o.subc.p, nullptr,
+              nullptr);
+  assign_f32(sub.p, loc, d, o.subc.p, ck, metric, nullptr, ids.p, nullptr, valid.p, nullptr);
+  MemberSort ms;
+  ms.run(ids.p, valid.p, loc, ck, 1, nullptr);
+  o.counts.resize(ck);
+  o.offs.resize(ck + 1);
+  d2h(o.counts.data(), ms.counts.p, ck);
+  d2h(o.offs.data(), ms.offsets.p, ck + 1);
+  sync_stream();
+  // children's row lists = parent's list re-ordered by (child, position): stable; rows dropped as None by the
+  // membership step leave the lists
+  o.kept = o.offs[ck];
+  if (o.kept) {
+    o.order.alloc(o.kept);
+    LB2_LAUNCH("compose_index", compose_index_kernel, cdiv(o.kept, 256), 256, 0, idx_seg, ms.members.p, o.kept, o.order.p);
+  }
+  sync_stream();
+}
+
+// ---- worker threads: independent splits train concurrently (each thread has its own stream) ---------------------
+// A split is a chain of small dependent kernels (a few thousand rows, k <= 16): one stream leaves the GPU almost
+// idle.  The sequential algorithm is kept EXACTLY -- splits are committed in the heap's pop order -- but the
+// clusters that will reach the top of the heap soon are trained ahead of time on worker threads; their results
+// wait in a cache keyed by cluster id (a split depends only on the cluster's rows, ck and seed + 1 + id).
+class SplitWorkers {
+ public:
+  static SplitWorkers& get() {
+    static SplitWorkers* w = new SplitWorkers();  // lives (with its detached threads) until the process exits
+    return *w;
+  }
+  int threads() const { return nthreads_; }
+  void submit(std::function<void()> f) {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      q_.push_back(std::move(f));
+      ++pending_;
+    }
+    cv_.notify_one();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [&] { return pending_ == 0; });
+  }
+
+ private:
+  SplitWorkers() {
+    const char* e = getenv("LB2_SPLIT_THREADS");
+    nthreads_ = e && *e ? std::max(0, atoi(e) - 1) : 2;  // measured: 482 / 379 / 378 / 484 ms at 1 / 2 / 4 / 8 threads (launch-throughput bound)
+    for (int i = 0; i < nthreads_; ++i) std::thread([this] { loop(); }).detach();
+  }
+  void loop() {
+    for (;;) {
+      std::function<void()> f;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return !q_.empty(); });
+        f = std::move(q_.front());
+        q_.pop_front();
+      }
+      f();
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        if (--pending_ == 0) done_.notify_all();
+      }
+    }
+  }
+  int nthreads_ = 0;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  std::deque<std::function<void()>> q_;
+  int pending_ = 0;
+};
+}  // namespace
+
 // Sharded: every rank holds a row shard of the sample and runs the SAME split loop -- the heap is
 // ordered by the clusters' global sizes (one small all-reduce of <= 16 counters per split), each Lloyd run
 // exchanges its partial sums once per iteration (lloyd_train), the row index lists stay local to the rank.
@@ -1375,24 +1488,23 @@ void hierarchical_train(const float* x, uint64_t n, int d, int K, int metric, fl
               (unsigned long long)n_global);
   const int k0 = (int)std::min<uint64_t>(std::min(hk, K), n_global);
   const uint64_t n1 = std::max<uint64_t>(n, 1);
-  DevBuf<float> top((size_t)k0 * d), sub(n1 * d), subc((size_t)hk * d), store((size_t)2 * K * d + (size_t)k0 * d);
-  DevBuf<uint32_t> ids(n1), idx(n1), tmp(n1), ident(n1);
+  DevBuf<float> top((size_t)k0 * d), store((size_t)2 * K * d + (size_t)k0 * d);
+  DevBuf<uint32_t> ids(n1), idx(n1);
   DevBuf<uint8_t> valid(n1);
-  uint64_t call = 0;
-  lloyd_train(x, n, d, 1, d, k0, metric, balance_factor, max_iters, tolerance, seed + call++, nullptr, top.p,
-              nullptr, nullptr);
+  lloyd_train(x, n, d, 1, d, k0, metric, balance_factor, max_iters, tolerance, seed, nullptr, top.p, nullptr, nullptr);
   assign_f32(x, n, d, top.p, k0, metric, nullptr, ids.p, nullptr, valid.p, nullptr);
-  MemberSort ms;
-  ms.run(ids.p, valid.p, n, k0, 1, nullptr);
   std::vector<uint32_t> counts(std::max(k0, hk)), offs(std::max(k0, hk) + 1);
   std::vector<uint64_t> gcounts;
-  d2h(counts.data(), ms.counts.p, k0);
-  d2h(offs.data(), ms.offsets.p, k0 + 1);
-  if (n) {
-    d2d(idx.p, ms.members.p, n);
-    LB2_LAUNCH("iota", iota_kernel, cdiv(n, 256), 256, 0, ident.p, (uint32_t)n);
+  {
+    MemberSort ms;
+    ms.run(ids.p, valid.p, n, k0, 1, nullptr);
+    d2h(counts.data(), ms.counts.p, k0);
+    d2h(offs.data(), ms.offsets.p, k0 + 1);
+    if (n) d2d(idx.p, ms.members.p, n);
+    sync_stream();
   }
-  sync_stream();
+  ids.release();
+  valid.release();
   global_counts(counts, k0, gcounts);
   RustHeap heap;
   uint32_t next_id = 0;
@@ -1402,6 +1514,18 @@ void hierarchical_train(const float* x, uint64_t n, int d, int K, int metric, fl
     d2d(store.p + (size_t)next_id * d, top.p + (size_t)i * d, d);
     heap.push(HCluster{next_id++, offs[i], counts[i], gcounts[i], false});
   }
+  auto children_of = [&](uint64_t len, int remaining) {
+    if (len <= (uint64_t)hk) return std::min(std::min(2, remaining), (int)len);
+    return std::max(2, std::min(std::min((int)std::min<uint64_t>(len / hk, 1u << 30), remaining), hk));
+  };
+  // concurrency only without a communicator (NCCL calls of one communicator must not interleave across threads;
+  // sharded builds whose sample fits one GPU gather it and come here without one, api.cu:train_ivf)
+  SplitWorkers* workers = dist ? nullptr : &SplitWorkers::get();
+  const int width = workers ? workers->threads() + 1 : 1;
+  std::unordered_map<uint32_t, std::unique_ptr<SplitOut>> cache;
+  int device = 0;
+  cudaGetDevice(&device);
+  Ctx& me = ctx();
   while ((int)heap.data.size() < K) {
     LB2_REQUIRE(!heap.data.empty(), "No cluster can be further split");
     HCluster big = heap.pop();
@@ -1410,22 +1534,87 @@ void hierarchical_train(const float* x, uint64_t n, int d, int K, int metric, fl
       break;
     }
     const int remaining = K - (int)heap.data.size();
-    int ck;
-    if (big.len <= (uint64_t)hk)
-      ck = std::min(std::min(2, remaining), (int)big.len);
-    else
-      ck = std::max(2, std::min(std::min((int)std::min<uint64_t>(big.len / hk, 1u << 30), remaining), hk));
-    if (big.loc)
-      LB2_LAUNCH("gather_rows", gather_rows_u32_kernel, cdiv((uint64_t)big.loc * d, 256), 256, 0, x,
-                 idx.p + big.off, (uint64_t)big.loc, d, sub.p);
-    lloyd_train(sub.p, big.loc, d, 1, d, ck, metric, balance_factor, max_iters, tolerance, seed + call++,
-                nullptr, subc.p, nullptr, nullptr);
-    assign_f32(sub.p, big.loc, d, subc.p, ck, metric, nullptr, ids.p, nullptr, valid.p, nullptr);
-    ms.run(ids.p, valid.p, big.loc, ck, 1, nullptr);
-    d2h(counts.data(), ms.counts.p, ck);
-    d2h(offs.data(), ms.offsets.p, ck + 1);
-    sync_stream();
-    global_counts(counts, ck, gcounts);
+    const int ck = children_of(big.len, remaining);
+    std::unique_ptr<SplitOut> out;
+    auto hit = cache.find(big.id);
+    if (hit != cache.end()) {
+      if (hit->second->ck == ck) out = std::move(hit->second);  // else: the end game changed ck -> train again
+      cache.erase(hit);
+    }
+    if (!out) {
+      // this cluster + the clusters that will be popped soon (largest first; the exact pop order among equals
+      // does not matter here -- a result is only used when its cluster is popped, and checked against ck then)
+      std::vector<HCluster> wave{big};
+      std::vector<int> wck{ck};
+      if (width > 1 && remaining - ck > 2 * hk) {
+        auto lt = [&](size_t a, size_t b) { return !hc_le(heap.data[b], heap.data[a]); };  // max-first
+        std::priority_queue<size_t, std::vector<size_t>, decltype(lt)> front(lt);
+        if (!heap.data.empty()) front.push(0);
+        uint64_t rows = big.loc;
+        int budget = remaining - ck;
+        while (!front.empty() && (int)wave.size() < width) {
+          const size_t i = front.top();
+          front.pop();
+          const HCluster& c = heap.data[i];
+          if (c.finalized || c.len <= 1) break;  // the sequential loop stops there
+          if (2 * i + 1 < heap.data.size()) front.push(2 * i + 1);
+          if (2 * i + 2 < heap.data.size()) front.push(2 * i + 2);
+          if (cache.count(c.id)) continue;
+          const int cck = children_of(c.len, K);  // `remaining` not binding ...
+          budget -= cck;
+          if (budget <= 2 * hk) break;            // ... which is only certain away from the end game
+          rows += c.loc;
+          if (rows * (uint64_t)d * 4 > (4ull << 30)) break;
+          wave.push_back(c);
+          wck.push_back(cck);
+        }
+      }
+      std::vector<std::unique_ptr<SplitOut>> outs(wave.size());
+      for (auto& o : outs) o.reset(new SplitOut());
+      sync_stream();  // the row lists written by earlier commits are visible to the workers' streams
+      const bool prof_on = me.profiling;
+      const std::string tag = me.tag;
+      for (size_t w = 1; w < wave.size(); ++w) {
+        SplitOut* o = outs[w].get();
+        const HCluster c = wave[w];
+        const int cck = wck[w];
+        workers->submit([=, &idx]() {
+          try {
+            lb2_set_device(device);
+            Ctx& wc = ctx();
+            wc.profiling = prof_on;
+            wc.tag = tag;
+            wc.prof.clear();
+            wc.launches = 0;
+            split_cluster(x, d, idx.p + c.off, c.loc, cck, metric, balance_factor, max_iters, tolerance, seed + 1 + c.id, *o);
+            wc.flush_profile();
+            o->prof.swap(wc.prof);
+            o->launches = wc.launches;
+            wc.profiling = false;
+          } catch (...) {
+            o->err = std::current_exception();
+          }
+        });
+      }
+      try {
+        split_cluster(x, d, idx.p + big.off, big.loc, ck, metric, balance_factor, max_iters, tolerance, seed + 1 + big.id,
+                      *outs[0]);
+      } catch (...) {
+        outs[0]->err = std::current_exception();
+      }
+      if (wave.size() > 1) workers->wait();
+      for (size_t w = 0; w < wave.size(); ++w) {
+        if (outs[w]->err) std::rethrow_exception(outs[w]->err);
+        me.launches += outs[w]->launches;
+        for (auto& kv : outs[w]->prof) {
+          me.prof[kv.first].launches += kv.second.launches;
+          me.prof[kv.first].total_ms += kv.second.total_ms;
+        }
+        if (w) cache[wave[w].id] = std::move(outs[w]);
+      }
+      out = std::move(outs[0]);
+    }
+    global_counts(out->counts, ck, gcounts);
     int nonzero = 0;
     for (int i = 0; i < ck; ++i) nonzero += gcounts[i] > 0;
     if (nonzero <= 1) {  // ineffective split: finalise the original cluster (kmeans.rs:957-962)
@@ -1433,20 +1622,14 @@ void hierarchical_train(const float* x, uint64_t n, int d, int K, int metric, fl
       heap.push(big);
       continue;
     }
-    // children's row lists = parent's list re-ordered by (child, position): stable, rows dropped as
-    // None by the membership step leave the lists
-    const uint32_t kept = offs[ck];
-    if (kept) {
-      LB2_LAUNCH("compose_index", compose_index_kernel, cdiv(kept, 256), 256, 0, idx.p + big.off,
-                 ms.members.p, kept, tmp.p);
-      d2d(idx.p + big.off, tmp.p, kept);
-    }
+    if (out->kept) d2d(idx.p + big.off, out->order.p, out->kept);
     for (int i = 0; i < ck; ++i) {
       if (gcounts[i] == 0) continue;
       LB2_REQUIRE(next_id < store_slots, "hierarchical k-means: centroid store exhausted");
-      d2d(store.p + (size_t)next_id * d, subc.p + (size_t)i * d, d);
-      heap.push(HCluster{next_id++, big.off + offs[i], counts[i], gcounts[i], false});
+      d2d(store.p + (size_t)next_id * d, out->subc.p + (size_t)i * d, d);
+      heap.push(HCluster{next_id++, big.off + out->offs[i], out->counts[i], gcounts[i], false});
     }
+    sync_stream();  // `out` (and its device buffers) goes away here
   }
   if ((int)heap.data.size() != K)
     fail(LB2_INVALID_ARG, "hierarchical k-means produced %zu of %d clusters (no cluster can be further split)",

@@ -564,7 +564,9 @@ int lo_kmeans_train(const float* data_in, uint64_t n_in, uint64_t d, uint64_t k,
 
 // ---------------------------------------------------------------------------------------------
 // A6  hierarchical k-means for k > 256 (kmeans.rs:746-1003).  Heap = Rust BinaryHeap restated,
-// ordered by (not finalized, size); the j-th training call uses seed + j (reference unseeded).
+// ordered by (not finalized, size); the top-level run uses `seed`, the split of cluster id uses seed + 1 + id
+// (the reference's RNG is unseeded; a seed tied to the cluster, not to the call order, lets the product train
+// independent splits concurrently without changing any result).
 // Returns the number of clusters produced (== k unless no cluster can be split further).
 // ---------------------------------------------------------------------------------------------
 int lo_hierarchical_kmeans(const float* data, uint64_t n, uint64_t d, uint64_t target_k, int max_iters,
@@ -621,8 +623,7 @@ int lo_hierarchical_kmeans(const float* data, uint64_t n, uint64_t d, uint64_t t
   const uint64_t k0 = std::min(std::min(hk, target_k), n);
   std::vector<float> top(k0 * d);
   double loss;
-  uint64_t call = 0;
-  lo_kmeans_train(data, n, d, k0, max_iters, tolerance, balance_factor, metric, seed + call++, nullptr,
+  lo_kmeans_train(data, n, d, k0, max_iters, tolerance, balance_factor, metric, seed, nullptr,
                   top.data(), &loss, nthreads);
   std::vector<uint32_t> ids(n);
   std::vector<uint8_t> valid(n);
@@ -654,7 +655,7 @@ int lo_hierarchical_kmeans(const float* data, uint64_t n, uint64_t d, uint64_t t
       ck = std::max<uint64_t>(2, std::min(std::min(size / hk, remaining), hk));
     sub.resize(size * d);
     for (uint64_t r = 0; r < size; ++r) std::memcpy(&sub[r * d], data + uint64_t(big.idx[r]) * d, sizeof(float) * d);
-    lo_kmeans_train(sub.data(), size, d, ck, max_iters, tolerance, balance_factor, metric, seed + call++, nullptr,
+    lo_kmeans_train(sub.data(), size, d, ck, max_iters, tolerance, balance_factor, metric, seed + 1 + big.id, nullptr,
                     subc.data(), &loss, nthreads);
     ids.resize(size);
     valid.resize(size);
