@@ -18,7 +18,11 @@
  *   - There is NO CPU fallback: without a usable CUDA device every compute entry point returns
  *     LB2_NO_DEVICE.
  *   - Calls are blocking (results are complete on return).  All entry points are thread-safe;
- *     each calling thread uses the CUDA device selected by lb2_set_device() on that thread.
+ *     each calling thread uses the CUDA device selected by lb2_set_device() on that thread and its
+ *     own CUDA stream, so concurrent callers (the reference searches up to ncpu-2 partitions at a
+ *     time, rust/lance/src/io/exec/knn.rs:881) overlap on the device.
+ *   - Stream variants: lb2_set_stream() orders every later call of the thread on a caller-owned
+ *     cudaStream_t; lb2_index_search_async() enqueues a whole search and returns without waiting.
  */
 #ifndef LANCE_B200_H_
 #define LANCE_B200_H_
@@ -54,6 +58,12 @@ size_t lb2_last_error(char* buf, size_t len); /* copies the calling thread's las
 int lb2_device_count(void);                   /* 0 when no CUDA device is usable */
 lb2_status lb2_set_device(int device);
 lb2_status lb2_synchronize(void);
+/* Bind the calling thread's library context to a caller-owned CUDA stream (cudaStream_t passed as
+ * void*): all work of later calls from this thread -- kernels, copies, stream-ordered allocations --
+ * is enqueued on it, after whatever the caller enqueued before.  Blocking entry points still wait for
+ * their own results (that is a cudaStreamSynchronize of this stream).  NULL returns to the thread's
+ * private stream.  The stream must belong to the thread's device and outlive the binding. */
+lb2_status lb2_set_stream(void* cuda_stream);
 /* device / pinned-host buffers for callers that keep data resident (bench, the Rust shim's ring) */
 lb2_status lb2_malloc(void** ptr, size_t bytes);
 lb2_status lb2_free(void* ptr);
@@ -243,6 +253,16 @@ typedef struct {
 lb2_status lb2_index_search_ex(lb2_index* index, const void* queries, uint64_t nq,
                                const lb2_search_params* params, uint64_t* row_ids_out, float* dists_out,
                                uint32_t* counts_out);
+/* Asynchronous search (SURVEY 8b "Threading": `_async` variants taking a stream/event).  Same
+ * arguments and results as lb2_index_search_ex, but the call only ENQUEUES the work on `cuda_stream`
+ * (cudaStream_t; NULL = the calling thread's current library stream) and returns: probe selection, LUT
+ * build, scan, tie replay, merge and the optional refine run in stream order, with no host round trip.
+ * Buffers must be device memory or pinned host memory and stay valid until the stream reaches the end of
+ * the search; if `done_event` (cudaEvent_t) is not NULL it is recorded there.  Errors detected while
+ * enqueueing are returned; the results are defined once the stream (or the event) has completed. */
+lb2_status lb2_index_search_async(lb2_index* index, const void* queries, uint64_t nq,
+                                  const lb2_search_params* params, uint64_t* row_ids_out, float* dists_out,
+                                  uint32_t* counts_out, void* cuda_stream, void* done_event);
 /* bitmap_out[(num_rows+63)/64]: bit i = RowIdMask::selected(row id stored at position i)
  * (lance-core/src/utils/mask.rs:84-93: in the allow list if there is one, and not in the block
  * list if there is one). Lists are sorted ascending (RoaringTreemap order); has_* = list present. */

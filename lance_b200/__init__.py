@@ -69,6 +69,12 @@ def synchronize():
     check(lib().lb2_synchronize())
 
 
+def set_stream(cuda_stream=None):
+    """lb2_set_stream: order every later call of this thread on a caller-owned cudaStream_t (int handle); None =
+    back to the thread's private stream."""
+    check(lib().lb2_set_stream(C.c_void_p(cuda_stream)))
+
+
 def launch_count(reset=False):
     n = C.c_uint64(0)
     check(lib().lb2_launch_count(C.byref(n), C.c_int(int(reset))))
@@ -566,6 +572,22 @@ class IvfPqIndex:
                           float(lower_bound or 0.0), float(upper_bound or 0.0))
         check(lib().lb2_index_search_ex(self._h, qp, C.c_uint64(nq), C.byref(sp), ip, dp, None))
         return ids, dists
+
+    def search_async(self, queries, out, k=10, nprobes=1, cuda_stream=None, done_event=None, allow_bitmap=None,
+                     lower_bound=None, upper_bound=None):
+        """lb2_index_search_async: enqueue a search on `cuda_stream` (cudaStream_t handle as int) and return at once.
+        queries / out = (ids, dists) are DeviceArray or PinnedArray and must stay alive until the stream is done."""
+        from ._lib import SearchParams
+        assert all(isinstance(a, (DeviceArray, PinnedArray)) for a in (queries, out[0], out[1]))
+        qp, _k1 = as_ptr(queries)
+        ip, _k2 = as_ptr(out[0])
+        dp, _k3 = as_ptr(out[1])
+        bp, _k4 = as_ptr(allow_bitmap)
+        sp = SearchParams(k, nprobes, 0, None, 0, bp.value if bp is not None else None,
+                          int(lower_bound is not None), int(upper_bound is not None),
+                          float(lower_bound or 0.0), float(upper_bound or 0.0))
+        check(lib().lb2_index_search_async(self._h, qp, C.c_uint64(queries.shape[0]), C.byref(sp), ip, dp, None,
+                                           C.c_void_p(cuda_stream), C.c_void_p(done_event)))
 
     def search_sharded(self, queries, k=10, nprobes=1, out=None):
         """lb2_index_search_sharded: this index holds ONE RANK'S rows (global row ids); every rank calls with

@@ -45,7 +45,8 @@ Ctx& ctx() {
   LB2_CUDA(cudaSetDevice(g_requested_device));
   Ctx* c = new Ctx();  // one per (thread, device); lives for the thread's lifetime
   c->device = g_requested_device;
-  LB2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  LB2_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
   LB2_CUDA(cudaEventCreate(&c->t0));
   LB2_CUDA(cudaEventCreate(&c->t1));
   cudaDeviceProp prop;
@@ -500,6 +501,9 @@ struct lb2_index {
   DevBuf<float> centroids, codebook;
   DevBuf<uint64_t> part_offsets, row_ids;
   DevBuf<uint8_t> codes;
+  // the conflict-free scan's skewed copy of `codes` (search.cu: ivfpq_scan_skew_kernel); empty for other shapes
+  DevBuf<uint64_t> slab_off;
+  DevBuf<uint8_t> codes_skew;
   int code_bytes() const { return nbits == 4 ? M / 2 : M; }  // bytes per row of `codes` (pq.rs:168-173)
   size_t codebook_len() const { return ((size_t)1 << nbits) * d; }
 };
@@ -547,6 +551,14 @@ static void index_load_dev(lb2_index* ix, const uint32_t* part_ids, const uint8_
     LB2_LAUNCH("group_by_partition", group_kernel, cdiv(kept, 256), 256, 0, ms.members.p, kept, ix->code_bytes(),
                codes, row_ids, ix->codes.p, ix->row_ids.p);
   ix->n = kept;
+  if (kept && skew_layout_applies(ix->M, ix->d, ix->nbits)) {
+    ix->slab_off.alloc(ix->K + 1);
+    ix->codes_skew.alloc(skew_bytes_bound(kept, ix->K));
+    build_skew_codes(ix->part_offsets.p, ix->K, ix->codes.p, kept, ix->slab_off.p, ix->codes_skew.p);
+  } else {
+    ix->slab_off.release();
+    ix->codes_skew.release();
+  }
   sync_stream();
 }
 
@@ -784,6 +796,13 @@ lb2_status lb2_set_device(int device) {
 lb2_status lb2_synchronize(void) {
   LB2_API_BEGIN
   sync_stream();
+  LB2_API_END
+}
+lb2_status lb2_set_stream(void* cuda_stream) {
+  LB2_API_BEGIN
+  Ctx& c = ctx();
+  c.flush_profile();  // pending profile events belong to the stream they were recorded on
+  c.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c.own_stream;
   LB2_API_END
 }
 lb2_status lb2_malloc(void** ptr, size_t bytes) {
@@ -1281,7 +1300,7 @@ static void index_search_impl(lb2_index* index, const void* queries, uint64_t nq
   else
     ivfpq_search_f32(index->centroids.p, index->K, d, index->metric, index->codebook.p, index->M, index->nbits,
                      index->part_offsets.p, index->codes.p, index->row_ids.p, qp, nq, (int)kc, nprobes, si, sd,
-                     sc, flt);
+                     sc, flt, index->slab_off.p, index->codes_skew.p);
   if (refine) {
     // exact re-rank with the true metric on the ORIGINAL (un-normalised) query, as flat_knn does; the
     // plan then filters `_distance >= lower AND _distance < upper` on the exact distances (scanner.rs:3342-3377)
@@ -1289,11 +1308,11 @@ static void index_search_impl(lb2_index* index, const void* queries, uint64_t nq
     refine_f32(q.get(), nq, d, index->metric, v.get(), (int)index->dtype, num_vectors, cid.p, ccnt.p, (int)kc, (int)k,
                oi.get(), od.get(), oc.get(), has_lower, lower, has_upper, upper);
     oi.commit(); od.commit(); oc.commit();
-    sync_stream();
+    if (!ctx().async_call) sync_stream();
     return;
   }
   oi.commit(); od.commit(); oc.commit();
-  sync_stream();
+  if (!ctx().async_call) sync_stream();
 }
 
 lb2_status lb2_index_search(lb2_index* index, const void* queries, uint64_t nq, uint32_t k,
@@ -1324,6 +1343,36 @@ lb2_status lb2_index_search_ex(lb2_index* index, const void* queries, uint64_t n
   index_search_impl(index, queries, nq, sp->k, sp->nprobes, sp->refine_factor, sp->refine_vectors,
                     sp->num_vectors, sp->allow_bitmap, row_ids_out, dists_out, counts_out, sp->has_lower_bound != 0,
                     sp->lower_bound, sp->has_upper_bound != 0, sp->upper_bound);
+  LB2_API_END
+}
+
+// RAII: route the thread's work to the caller's stream for one asynchronous call
+namespace {
+struct AsyncScope {
+  Ctx& c;
+  cudaStream_t saved;
+  explicit AsyncScope(void* stream) : c(ctx()), saved(c.stream) {
+    if (stream) c.stream = static_cast<cudaStream_t>(stream);
+    c.async_call = true;
+  }
+  ~AsyncScope() {
+    c.async_call = false;
+    c.stream = saved;
+  }
+};
+}  // namespace
+
+lb2_status lb2_index_search_async(lb2_index* index, const void* queries, uint64_t nq,
+                                  const lb2_search_params* sp, uint64_t* row_ids_out, float* dists_out,
+                                  uint32_t* counts_out, void* cuda_stream, void* done_event) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(sp, "null search params");
+  LB2_REQUIRE(sp->refine_factor == 0 || sp->refine_vectors, "refine_factor > 0 needs refine_vectors");
+  AsyncScope scope(cuda_stream);
+  index_search_impl(index, queries, nq, sp->k, sp->nprobes, sp->refine_factor, sp->refine_vectors,
+                    sp->num_vectors, sp->allow_bitmap, row_ids_out, dists_out, counts_out, sp->has_lower_bound != 0,
+                    sp->lower_bound, sp->has_upper_bound != 0, sp->upper_bound);
+  if (done_event) LB2_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(done_event), ctx().stream));
   LB2_API_END
 }
 

@@ -78,7 +78,9 @@ struct ProfEntry {
 
 struct Ctx {
   int device = -1;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // where work is enqueued: own_stream, or the caller's (lb2_set_stream / _async)
+  cudaStream_t own_stream = nullptr;  // the thread's private non-blocking stream
+  bool async_call = false;            // inside an _async entry point: the trailing synchronise is skipped
   uint64_t launches = 0;
   bool profiling = false;
   std::string tag;  // phase prefix of the profile key: "ivf_train", "pq_train", "transform", "search" ...

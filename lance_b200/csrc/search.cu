@@ -766,6 +766,352 @@ ivfpq_scan_kernel(const ScanArgs a, uint32_t* __restrict__ rlist, uint32_t* __re
 }
 
 // ------------------------------------------------------------------------------------------------
+// Conflict-free scan for the headline shape (8-bit codes, M = 16 sub-spaces of 8 dimensions; C1 / C3).
+//
+// What bounds the scan above is the shared-memory gather: 32 lanes look up LUT[m][code] for the SAME m and random
+// codes, i.e. random banks -- 3.3 wavefronts per request (ncu: 454 M bank conflicts per 10 000 x 10 probes) -- and
+// every (query, partition) CTA re-reads the 128 KB codebook through L2.  This kernel removes both:
+//
+//  * the LUT is stored as [code][team][copy][m] (two copies per team, 256 B per code for the CTA's two teams):
+//    sub-space m lives in bank m (copy 0) and 16 + m (copy 1).  Lane l works on sub-space (t - l) mod 16 at step t, lanes 0-15 on copy 0 and lanes 16-31 on copy 1,
+//    so the 32 lookups of a request always hit 32 different banks: ONE wavefront.
+//  * the reference's sum is m-ascending and sequential in f32, so a lane cannot start its row at m != 0.  Instead
+//    the lanes are SKEWED IN TIME: lane l starts each row l steps late.  The index keeps, next to the row-major
+//    codes, a skewed copy (`build_skew_codes`): per 512-row slab and lane the 16 rows of that lane (rows l + 32 i)
+//    form one byte stream that is preceded by l mod 16 pad bytes and cut into 17 units of 16 bytes, unit (r, lane)
+//    at (r * 32 + lane) * 16 -- one coalesced 128-bit load per lane and round, and byte t of a unit is a
+//    compile-time register/byte position.  Two accumulators take the steps before / after the lane's row boundary,
+//    selected by per-lane 0/1 weights through FFMA: fma(v, 1, acc) is the reference's separately rounded add,
+//    fma(v, 0, acc) leaves acc unchanged (all LUT entries finite, checked while the LUT is built; a slot whose
+//    LUT is not goes to the replay list).  Per lookup: one PRMT (code byte -> address bits 8-15, the lane's
+//    bank bits into the low byte), LDS, 2 FFMA.
+//  * persistent CTAs (one per SM, two teams of 8 warps) keep the codebook in shared memory (padded so that the
+//    16 sub-spaces a half-warp reads are in different banks) and build each slot's LUT from there; thread (m, c)
+//    keeps its residual sub-vector in registers.  Team barriers are named barriers, so one team scans while the
+//    other builds its LUT.
+// Distances, candidate order and the tie / replay rule are those of ivfpq_scan_kernel (same bits).
+// ------------------------------------------------------------------------------------------------
+constexpr int SKEW_ROUNDS = 17;                          // 16 rows per lane and slab + one unit of skew
+constexpr int SKEW_SLAB_ROWS = 512;
+constexpr int SKEW_SLAB_BYTES = SKEW_ROUNDS * 32 * 16;   // 8704
+constexpr int SKEW_CB_STRIDE = 256 * 8 + 4;              // floats per sub-space in shared memory (+16 B pad)
+constexpr int SKEW_LUT_BYTES = 256 * 256;                // both teams' LUTs, interleaved per code
+constexpr int SKEW_LIST = 1024;                          // capacity of a team's candidate list
+constexpr int SKEW_TEAM_BYTES = SKEW_LIST * 8 + 2 * SCAN_KFAST * 8 + 8 * 32 * 4 + 8 * 4 + 16;
+constexpr int SKEW_SMEM_BYTES = SKEW_LUT_BYTES + 16 * SKEW_CB_STRIDE * 4 + 2 * SKEW_TEAM_BYTES;
+
+__device__ __forceinline__ void team_sync(int team) {
+  asm volatile("bar.sync %0, 256;" ::"r"(team + 1) : "memory");
+}
+__device__ __forceinline__ bool team_or(int team, bool v) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %2, 0;\n\tbar.red.or.pred p, %1, 256, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "r"(team + 1), "r"((uint32_t)v)
+      : "memory");
+  return r != 0;
+}
+
+// slab_off[p] = number of 512-row slabs before partition p (exclusive scan of ceil(n_p / 512)); slab_off[K] = total
+__global__ void __launch_bounds__(1024)
+skew_offsets_kernel(const uint64_t* __restrict__ part_offsets, int K, uint64_t* __restrict__ slab_off) {
+  __shared__ uint64_t part[1024];
+  const int tid = threadIdx.x;
+  const int per = (K + 1023) / 1024;
+  const int b = tid * per, e = min(K, b + per);
+  uint64_t s = 0;
+  for (int p = b; p < e; ++p) s += (part_offsets[p + 1] - part_offsets[p] + SKEW_SLAB_ROWS - 1) / SKEW_SLAB_ROWS;
+  part[tid] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const uint64_t v = tid >= o ? part[tid - o] : 0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  uint64_t run = tid ? part[tid - 1] : 0;
+  for (int p = b; p < e; ++p) {
+    slab_off[p] = run;
+    run += (part_offsets[p + 1] - part_offsets[p] + SKEW_SLAB_ROWS - 1) / SKEW_SLAB_ROWS;
+  }
+  if (tid == 1023) slab_off[K] = part[1023];
+}
+
+// one warp per slab: unit (r, lane) = bytes [16 r - l16, 16 r - l16 + 16) of the lane's row stream (rows lane + 32 i)
+__global__ void __launch_bounds__(256)
+skew_fill_kernel(const uint64_t* __restrict__ part_offsets, int K, const uint64_t* __restrict__ slab_off,
+                 const uint8_t* __restrict__ codes, uint8_t* __restrict__ skew) {
+  const uint64_t nslab = slab_off[K];
+  const int lane = threadIdx.x & 31, l16 = lane & 15;
+  for (uint64_t s = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); s < nslab; s += (uint64_t)gridDim.x * 8) {
+    int lo = 0, hi = K;  // last p with slab_off[p] <= s  (empty partitions share their successor's offset)
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (slab_off[mid] <= s) lo = mid; else hi = mid;
+    }
+    const int p = lo;
+    const uint64_t off = part_offsets[p];
+    const uint32_t n_p = (uint32_t)(part_offsets[p + 1] - off);
+    const uint32_t base = (uint32_t)(s - slab_off[p]) * SKEW_SLAB_ROWS;
+    const uint4* rows = reinterpret_cast<const uint4*>(codes) + off;
+    uint4* out = reinterpret_cast<uint4*>(skew + s * SKEW_SLAB_BYTES) + lane;
+    uint4 prev = make_uint4(0, 0, 0, 0);
+    for (int r = 0; r < SKEW_ROUNDS; ++r) {
+      const uint32_t j = base + lane + 32 * r;
+      const uint4 cur = (r < 16 && j < n_p) ? __ldg(rows + j) : make_uint4(0, 0, 0, 0);
+      uint4 u = cur;
+      if (l16) {  // bytes [16 - l16, 32 - l16) of prev|cur
+        const uint32_t w[8] = {prev.x, prev.y, prev.z, prev.w, cur.x, cur.y, cur.z, cur.w};
+        const int b0 = 16 - l16, wq = b0 >> 2, sh = (b0 & 3) * 8;
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t lo32 = 0, hi32 = 0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {  // static indexing of w[]
+            if (q == wq + i) lo32 = w[q];
+            if (q == wq + i + 1) hi32 = w[q];
+          }
+          o[i] = sh ? (lo32 >> sh) | (hi32 << (32 - sh)) : lo32;
+        }
+        u = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      out[r * 32] = u;
+      prev = cur;
+    }
+  }
+}
+
+template <int METRIC, bool FILTER>
+__global__ void __launch_bounds__(512, 1)
+ivfpq_scan_skew_kernel(const ScanArgs a, const uint64_t* __restrict__ slab_off, const uint8_t* __restrict__ skew,
+                       uint32_t nslots, uint32_t* __restrict__ rlist, uint32_t* __restrict__ rcount) {
+  extern __shared__ __align__(16) unsigned char sk_smem[];
+  const int d = a.d, k = a.k, np = a.np;
+  const int kk = k + 1;  // one more than asked for, to expose ties that overflow the k-th place
+  const uint64_t* __restrict__ allow = a.flt.allow;
+  const int tid = threadIdx.x, team = tid >> 8, ttid = tid & 255, lane = tid & 31, warp = ttid >> 5;
+  const int l16 = lane & 15, half = lane >> 4;
+  float* lut2 = reinterpret_cast<float*>(sk_smem) + team * 32;                     // [256 codes][64]: + copy * 16 + m
+  float* cb = reinterpret_cast<float*>(sk_smem + SKEW_LUT_BYTES);
+  unsigned char* tb = sk_smem + SKEW_LUT_BYTES + 16 * SKEW_CB_STRIDE * 4 + team * SKEW_TEAM_BYTES;
+  uint64_t* tl = reinterpret_cast<uint64_t*>(tb);                                  // [SKEW_LIST] team candidate list
+  uint64_t* car = tl + SKEW_LIST;                                                  // [2][SCAN_KFAST] winners so far
+  int32_t* wmin = reinterpret_cast<int32_t*>(car + 2 * SCAN_KFAST);               // [8][32] lane minima
+  int32_t* s_tw = wmin + 8 * 32;                                                   // [8] warp thresholds
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_tw + 8);                         // candidates in tl
+
+  // codebook -> shared memory, once per CTA (sub-space stride padded by 16 B)
+  for (int i = tid; i < 16 * 256 * 2; i += 512) {
+    const int e = i >> 1;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(a.codebook) + i);
+    *reinterpret_cast<float4*>(cb + (e >> 8) * SKEW_CB_STRIDE + (e & 255) * 8 + (i & 1) * 4) = v;
+  }
+  __syncthreads();
+
+  // per-lane constants of the skewed schedule
+  const int th = l16 ? l16 : 16;  // steps [0, th) of a round still belong to the row begun one round earlier
+  float wA[16], wB[16];
+  uint32_t lp[16];  // low address byte of LUT[.][team][this lane's copy][sub-space of step t]
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    wA[t] = t < th ? 1.0f : 0.0f;
+    wB[t] = t < th ? 0.0f : 1.0f;
+    lp[t] = (uint32_t)((team * 32 + half * 16 + ((t - l16) & 15)) << 2);
+  }
+  const unsigned char* lut_bytes = sk_smem;
+  const int sh = l16 != 0;  // the row finished in round u is row u - sh of the lane
+  const int lm = ttid & 15;                  // LUT build: this thread's sub-space
+  const float* cbm = cb + lm * SKEW_CB_STRIDE;
+  const float dot_fix = 16.0f - 1.0f;
+  constexpr int32_t MAXKEY = 0x7fffffff;     // no live row carries it: the LUT is finite, sums are at most +inf
+  int par = 0;                               // which half of car[] holds the winners
+
+  // slot metadata is a chain of dependent global loads (probe id -> partition offsets -> slab offset): it is
+  // fetched one slot ahead, and the first code unit of a slot is requested before its LUT is built
+  const uint32_t stride = gridDim.x * 2;
+  uint32_t slot = blockIdx.x * 2 + team;
+  uint32_t p_n = slot < nslots ? a.probe_ids[slot] : 0u;
+  uint64_t off_n = a.part_offsets[p_n], end_n = a.part_offsets[p_n + 1], so_n = slab_off[p_n];
+  for (; slot < nslots; slot += stride) {
+    const size_t qi = slot / np;
+    const uint32_t p = p_n;
+    const uint64_t off = off_n;
+    const uint32_t n_p = (uint32_t)(end_n - off_n);
+    const uint8_t* sp = skew + so_n * SKEW_SLAB_BYTES;
+    p_n = slot + stride < nslots ? a.probe_ids[slot + stride] : 0u;
+    if (n_p == 0) {
+      off_n = a.part_offsets[p_n]; end_n = a.part_offsets[p_n + 1]; so_n = slab_off[p_n];
+      if (ttid == 0) a.cand_cnt[slot] = 0;
+      continue;
+    }
+    const uint4* up0 = reinterpret_cast<const uint4*>(sp + (size_t)warp * SKEW_SLAB_BYTES) + lane;
+    uint4 first_unit = make_uint4(0, 0, 0, 0);
+    if ((uint32_t)warp * SKEW_SLAB_ROWS < n_p) first_unit = __ldg(up0);
+    // ---- residual query of this thread's sub-space (v2.rs:316-332) and the LUT (pq/distance.rs:38-56).
+    // No barrier is needed before lut2 is overwritten: every warp of the team left its scan before the last
+    // team barrier of the previous slot.
+    float qm[8];
+    {
+      const float4* q4 = reinterpret_cast<const float4*>(a.queries + qi * d + lm * 8);
+      const float4* c4 = reinterpret_cast<const float4*>(a.centroids + (size_t)p * d + lm * 8);
+      const float4 x0 = __ldg(q4), x1 = __ldg(q4 + 1);
+      qm[0] = x0.x; qm[1] = x0.y; qm[2] = x0.z; qm[3] = x0.w; qm[4] = x1.x; qm[5] = x1.y; qm[6] = x1.z; qm[7] = x1.w;
+      if (METRIC != METRIC_DOT) {
+        const float4 y0 = __ldg(c4), y1 = __ldg(c4 + 1);
+        const float cv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+        for (int t = 0; t < 8; ++t) qm[t] = __fsub_rn(qm[t], cv[t]);
+      }
+    }
+    bool bad = false;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int c = (ttid >> 4) + 16 * i;
+      const float4 b0 = *reinterpret_cast<const float4*>(cbm + c * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(cbm + c * 8 + 4);
+      const float cv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float s = 0.0f;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) s = f_add(s, term<METRIC>(qm[t], cv[t]));
+      const float val = finish<METRIC>(f_add(s, 0.0f));
+      bad |= !(fabsf(val) < 1.0e30f);
+      lut2[c * 64 + half * 16 + lm] = val;
+      lut2[c * 64 + (half ^ 1) * 16 + lm] = val;
+    }
+    // Inf / NaN in the LUT: 0 * v would poison the idle accumulator -> the exact replay takes the slot
+    off_n = a.part_offsets[p_n]; end_n = a.part_offsets[p_n + 1]; so_n = slab_off[p_n];
+    bool replay = team_or(team, bad);
+    uint32_t nw = 0;  // winners carried from earlier chunks (uniform)
+    for (uint32_t c0 = 0; c0 < n_p && !replay; c0 += SCAN_CHUNK) {
+      const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
+      const uint32_t wbase = warp * SKEW_SLAB_ROWS;
+      if (ttid == 0) *s_cnt = 0;  // read last before the previous chunk's / slot's final barrier
+      int32_t key[SKEW_ROUNDS];
+      int32_t mk = MAXKEY;  // this lane's smallest live key
+      if (wbase < clen) {   // warp-uniform: this warp's slab exists
+        // rows of this lane: wbase + lane + 32 i < clen, i < 16; they finish in rounds sh .. sh + cnt - 1
+        uint32_t livemask = 0;
+        if (!FILTER) {
+          const uint32_t first = wbase + lane;
+          const uint32_t cnt = first < clen ? min(16u, (clen - first + 31u) >> 5) : 0u;
+          livemask = ((1u << cnt) - 1u) << sh;
+        }
+        const uint4* up = reinterpret_cast<const uint4*>(sp + (size_t)((c0 >> 9) + warp) * SKEW_SLAB_BYTES) + lane;
+        float A = 0.0f, B = 0.0f;
+        uint4 cur = c0 == 0 ? first_unit : __ldg(up);
+#pragma unroll
+        for (int r = 0; r < SKEW_ROUNDS; ++r) {
+          uint4 nxt = cur;
+          if (r + 1 < SKEW_ROUNDS) nxt = __ldg(up + (r + 1) * 32);
+          const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            // address = code * 256 + the lane's bank bits: one byte permute (byte 0 <- lp, byte 1 <- the code)
+            const uint32_t idx = __byte_perm(w[t >> 2], lp[t], 0x5504u | ((uint32_t)(t & 3) << 4));
+            const float v = *reinterpret_cast<const float*>(lut_bytes + idx);
+            A = __fmaf_rn(v, wA[t], A);
+            B = __fmaf_rn(v, wB[t], B);
+          }
+          float dist = A;
+          A = B;
+          B = 0.0f;
+          if (METRIC == METRIC_DOT) dist = __fsub_rn(dist, dot_fix);  // pq/storage.rs:957-958
+          const int32_t kv = total_order_key(dist);
+          bool live;
+          if (FILTER) {
+            const int ri = r - sh;
+            const uint32_t j = wbase + lane + 32 * ri;
+            live = ri >= 0 && ri < 16 && j < clen && row_allowed(allow, off + c0 + j) && key_in_range(a.flt, kv);
+          } else {
+            live = ((livemask >> r) & 1u) != 0;
+          }
+          key[r] = live ? kv : MAXKEY;
+          mk = min(mk, key[r]);
+          cur = nxt;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < SKEW_ROUNDS; ++r) key[r] = MAXKEY;
+      }
+      // ---- selection.  With two teams per SM nothing hides the dependent shuffle steps of sorting networks, and
+      // instruction issue is what bounds the kernel, so: (1) per warp, Tw = kk-th smallest lane minimum = the
+      // largest lane minimum with fewer than kk smaller ones (32 broadcast reads + one warp reduction);
+      wmin[warp * 32 + lane] = mk;
+      __syncwarp();
+      {
+        int lt = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) lt += wmin[warp * 32 + j] < mk ? 1 : 0;
+        const int32_t twv = __reduce_max_sync(0xffffffffu, lt < kk ? mk : (int32_t)0x80000000);
+        if (lane == 0) s_tw[warp] = twv;
+      }
+      team_sync(team);
+      // (2) T = the smallest warp threshold: at least kk rows of the team have key <= T; every row with key <= T
+      // goes to the team list (typically kk + a few rows; ballots that come back empty cost three instructions);
+      int32_t T = s_tw[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) T = min(T, s_tw[w]);
+      T = min(T, MAXKEY - 1);
+      if (__any_sync(0xffffffffu, mk <= T)) {
+#pragma unroll
+        for (int u = 0; u < SKEW_ROUNDS; ++u) {
+          const bool take = key[u] <= T;
+          const unsigned bal = __ballot_sync(0xffffffffu, take);
+          if (bal) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(s_cnt, (uint32_t)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0) + __popc(bal & ((1u << lane) - 1));
+            if (take && base < (uint32_t)SKEW_LIST) tl[base] = pack_cand(key[u], c0 + wbase + lane + 32 * (u - sh));
+          }
+        }
+      }
+      team_sync(team);
+      // (3) the kk smallest of list + carried winners by RANK (packed (key, position) words are unique): thread i
+      // counts the entries smaller than its own and stores it at that rank.
+      const uint32_t cnt = *s_cnt;
+      if (cnt > (uint32_t)SKEW_LIST) {  // a flood of equal keys: the exact replay takes the slot
+        replay = true;
+      } else {
+        const uint32_t tot = cnt + nw;
+        const uint64_t* cold = car + par * SCAN_KFAST;
+        uint64_t* cnew = car + (par ^ 1) * SCAN_KFAST;
+        for (uint32_t i = ttid; i < tot; i += 256) {
+          const uint64_t v = i < cnt ? tl[i] : cold[i - cnt];
+          int rank = 0;
+          for (uint32_t j = 0; j < cnt; ++j) rank += tl[j] < v ? 1 : 0;
+          for (uint32_t j = 0; j < nw; ++j) rank += cold[j] < v ? 1 : 0;
+          if (rank < kk) cnew[rank] = v;
+        }
+        nw = min((uint32_t)kk, tot);
+        par ^= 1;
+      }
+      team_sync(team);
+    }
+    const uint64_t* win = car + par * SCAN_KFAST;  // ascending by (key, position)
+    // If the k-th and the (k+1)-th share a key, more rows tie at the k-th distance than fit: which of them the
+    // reference's BinaryHeap keeps depends on its sift order, so the slot goes on the replay list.
+    if (!replay && nw == (uint32_t)kk) {
+      if (cand_key(win[k]) == cand_key(win[k - 1])) replay = true;
+      nw = k;
+    }
+    if (replay) {
+      if (ttid == 0) {
+        rlist[atomicAdd(rcount, 1u)] = slot;
+        a.cand_cnt[slot] = 0;
+      }
+      continue;
+    }
+    for (uint32_t i = ttid; i < nw; i += 256) {
+      a.cand_d[(size_t)slot * k + i] = key_to_float(cand_key(win[i]));
+      a.cand_id[(size_t)slot * k + i] = a.row_ids[off + cand_pos(win[i])];
+    }
+    if (ttid == 0) a.cand_cnt[slot] = nw;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // IVF_FLAT: exact distances of the query to every row of a probed partition
 // (FlatDistanceCal::distance_all, lance-index/src/vector/flat/storage.rs:397-403) + top-k.
 // 16 lanes per row: lane l owns the reference's lane-accumulator l (elements 16c + l), so the L2 /
@@ -1134,13 +1480,36 @@ void find_partitions_f32(const float* centroids, int K, int d, int metric, const
   LB2_LAUNCH("select_probes", select_probes_kernel, (unsigned)nq, 128, 0, all.p, K, nprobes, ids, dists);
 }
 
+// which fast kernel serves an 8-bit scan: LB2_SCAN=classic|skew overrides the size rule (tests run both)
+static int scan_mode_env() {
+  const char* e = getenv("LB2_SCAN");
+  return !e ? 0 : (!strcmp(e, "classic") ? 1 : (!strcmp(e, "skew") ? 2 : 0));
+}
+
 template <int METRIC>
-static void scan_launch(int nbits, dim3 grid, size_t smem, const ScanArgs& a, uint32_t* rlist, uint32_t* rcount) {
+static void scan_launch(int nbits, dim3 grid, size_t smem, const ScanArgs& a, uint32_t* rlist, uint32_t* rcount,
+                        const uint64_t* slab_off, const uint8_t* skew) {
   const bool filtering = a.flt.allow != nullptr || a.flt.range;
   if (nbits == 8 && a.k + 1 <= SCAN_KFAST) {
     const size_t smem_fast = sizeof(float) * ((size_t)a.M * 256 + a.d);
     LB2_CUDA(cudaMemsetAsync(rcount, 0, sizeof(uint32_t), ctx().stream));
-    if (filtering) {  // filtered rows never enter the candidate lists
+    const uint64_t nslots = (uint64_t)grid.x * grid.y;
+    const bool skew_ok = skew && a.M == 16 && a.ds == 8 && (reinterpret_cast<uintptr_t>(a.queries) & 15) == 0 &&
+                         (size_t)SKEW_SMEM_BYTES <= ctx().smem_optin;
+    // the persistent kernel loads the 128 KB codebook once per CTA: worth it from a few slots per SM on
+    const bool use_skew = skew_ok && scan_mode_env() != 1 && (scan_mode_env() == 2 || nslots >= 2ull * ctx().num_sms);
+    if (use_skew) {
+      const unsigned g = (unsigned)std::min<uint64_t>((nslots + 1) / 2, (uint64_t)ctx().num_sms);
+      if (filtering) {
+        set_smem(ivfpq_scan_skew_kernel<METRIC, true>, SKEW_SMEM_BYTES);
+        LB2_LAUNCH("pq_scan_skew", (ivfpq_scan_skew_kernel<METRIC, true>), g, 512, SKEW_SMEM_BYTES, a, slab_off, skew,
+                   (uint32_t)nslots, rlist, rcount);
+      } else {
+        set_smem(ivfpq_scan_skew_kernel<METRIC, false>, SKEW_SMEM_BYTES);
+        LB2_LAUNCH("pq_scan_skew", (ivfpq_scan_skew_kernel<METRIC, false>), g, 512, SKEW_SMEM_BYTES, a, slab_off, skew,
+                   (uint32_t)nslots, rlist, rcount);
+      }
+    } else if (filtering) {  // filtered rows never enter the candidate lists
       set_smem(ivfpq_scan_kernel<METRIC, true>, smem_fast);
       LB2_LAUNCH("pq_scan", (ivfpq_scan_kernel<METRIC, true>), grid, 256, smem_fast, a, rlist, rcount);
     } else {
@@ -1165,10 +1534,22 @@ static void scan_launch(int nbits, dim3 grid, size_t smem, const ScanArgs& a, ui
              (const uint32_t*)nullptr);
 }
 
+// the skewed copy of an index's codes (see ivfpq_scan_skew_kernel); sizes: slab_off u64[K + 1],
+// skew (n / 512 + K) slabs of 8704 bytes at most
+bool skew_layout_applies(int M, int d, int nbits) { return nbits == 8 && M == 16 && d == 128; }
+size_t skew_bytes_bound(uint64_t n, int K) { return (size_t)(n / SKEW_SLAB_ROWS + (uint64_t)K) * SKEW_SLAB_BYTES; }
+void build_skew_codes(const uint64_t* part_offsets, int K, const uint8_t* codes, uint64_t n, uint64_t* slab_off,
+                      uint8_t* skew) {
+  LB2_LAUNCH("skew_offsets", skew_offsets_kernel, 1, 1024, 0, part_offsets, K, slab_off);
+  const unsigned g = (unsigned)std::min<uint64_t>(cdiv(n / SKEW_SLAB_ROWS + (uint64_t)K, 8), 8ull * ctx().num_sms);
+  if (n) LB2_LAUNCH("skew_fill", skew_fill_kernel, std::max(1u, g), 256, 0, part_offsets, K, (const uint64_t*)slab_off, codes, skew);
+}
+
 void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const float* codebook, int M,
                       int nbits, const uint64_t* part_offsets, const uint8_t* codes,
                       const uint64_t* row_ids, const float* queries, uint64_t nq, int k, int nprobes,
-                      uint64_t* out_ids, float* out_dists, uint32_t* out_counts, const ScanFilter& flt) {
+                      uint64_t* out_ids, float* out_dists, uint32_t* out_counts, const ScanFilter& flt,
+                      const uint64_t* slab_off, const uint8_t* skew) {
   if (nq == 0 || k == 0) return;
   if (nbits != 8 && nbits != 4) fail(LB2_INVALID_ARG, "PQ: num_bits must be 4 or 8, got %d", nbits);
   if (nbits == 4 && (M % 2 != 0 || M > 256)) fail(LB2_UNSUPPORTED, "4-bit PQ needs an even num_sub_vectors <= 256");
@@ -1190,9 +1571,9 @@ void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const fl
     ScanArgs a{queries + q0 * d, d, centroids, codebook, M, ds, pids.p + q0 * np, np, part_offsets, codes, row_ids, k,
                cand_d.p + q0 * np * k, cand_id.p + q0 * np * k, cand_cnt.p + q0 * np, flt};
     if (cmetric == METRIC_DOT)
-      scan_launch<METRIC_DOT>(nbits, g, smem, a, rlist.p, rcount.p);
+      scan_launch<METRIC_DOT>(nbits, g, smem, a, rlist.p, rcount.p, slab_off, skew);
     else
-      scan_launch<METRIC_L2>(nbits, g, smem, a, rlist.p, rcount.p);
+      scan_launch<METRIC_L2>(nbits, g, smem, a, rlist.p, rcount.p, slab_off, skew);
   }
   LB2_LAUNCH("merge_topk", merge_kernel, (unsigned)nq, 128, 0, cand_d.p, cand_id.p, cand_cnt.p, np,
              k, (size_t)k, (size_t)k, (size_t)np * k, (size_t)1, (size_t)np, out_ids, out_dists, out_counts);

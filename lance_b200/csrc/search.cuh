@@ -22,7 +22,14 @@ void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const fl
                       int nbits, const uint64_t* part_offsets, const uint8_t* codes,
                       const uint64_t* row_ids, const float* queries, uint64_t nq, int k, int nprobes,
                       uint64_t* out_ids, float* out_dists, uint32_t* out_counts,
-                      const ScanFilter& flt = ScanFilter());
+                      const ScanFilter& flt = ScanFilter(), const uint64_t* slab_off = nullptr,
+                      const uint8_t* skew = nullptr);
+// the conflict-free scan's copy of the codes (8-bit, 16 sub-spaces of 8 dimensions): per 512-row slab and lane the
+// lane's 16 rows as one byte stream delayed by lane mod 16 bytes, in 17 coalesced 16-byte units
+bool skew_layout_applies(int M, int d, int nbits);
+size_t skew_bytes_bound(uint64_t n, int K);
+void build_skew_codes(const uint64_t* part_offsets, int K, const uint8_t* codes, uint64_t n, uint64_t* slab_off,
+                      uint8_t* skew);
 // vectors: the index's rows in element type vdt (lb2_dtype: f32 / f16 / bf16)
 void ivfflat_search_f32(const float* centroids, int K, int d, int metric, const uint64_t* part_offsets,
                         const void* vectors, int vdt, const uint64_t* row_ids, const float* queries, uint64_t nq,

@@ -23,7 +23,7 @@ KEYS = [
 TRAFFIC_KEYS = [
     ("c1_train", "tc_pq_kernel<1", "pq_train:tc_pq_filter"), ("c1_train", "tc_filter_kernel", "ivf_train:tc_filter"),
     ("c1_transform", "tc_pq_kernel<0", "transform:tc_pq_filter"), ("c1_transform", "tc_filter_kernel", "transform:tc_filter"),
-    ("c1_query", "ivfpq_scan_kernel", "search:pq_scan"),
+    ("c1_query", "ivfpq_scan_kernel", "search:pq_scan"), ("c1_query", "ivfpq_scan_skew_kernel", "search:pq_scan_skew"),
     ("c2_transform", "tc_filter_general_kernel<0, 0>", "C2:transform:tc_filter_general"),
     ("c4_assign", "tc_filter_general_kernel<2, 0>", "C4:transform:tc_filter_general16"),
 ]

@@ -1206,3 +1206,132 @@ def test_reference_fixture_pq_in_schema_on_gpu():
     # the partition goes back out in the reference's storage layout: the bytes of the `__pq_code` column
     ct, rid = ix.export_partition_transposed(0)
     assert np.array_equal(ct.reshape(-1), z["codes_transposed"]) and np.array_equal(rid, z["row_ids"])
+
+
+# ---- the conflict-free ("skewed") scan kernel: same bits as the classic kernel and the oracle ----------------
+def _with_scan(mode, fn):
+    import os
+    old = os.environ.get("LB2_SCAN")
+    os.environ["LB2_SCAN"] = mode
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ["LB2_SCAN"]
+        else:
+            os.environ["LB2_SCAN"] = old
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+def test_skew_scan_kernel_matches_oracle_and_classic(metric):
+    """ivfpq_scan_skew_kernel (8-bit, 16 sub-spaces x 8 dims): partitions that are empty, shorter than a warp,
+    shorter than a slab, several chunks long; k = 1 .. 15; plain, prefiltered and range searches."""
+    rng = np.random.default_rng(3101)
+    d, M = 128, 16
+    sizes = [0, 1, 17, 31, 32, 33, 500, 512, 513, 1000, 4095, 4096, 4097, 9000, 0, 700]
+    K = len(sizes)
+    cent = (rng.standard_normal((K, d)) * 4).astype(np.float32)
+    part = np.repeat(np.arange(K, dtype=np.uint32), sizes)
+    n = len(part)
+    data = (cent[part] + rng.standard_normal((n, d))).astype(np.float32)
+    if metric == "dot":
+        data /= np.linalg.norm(data, axis=1, keepdims=True)
+        cent /= np.linalg.norm(cent, axis=1, keepdims=True)
+    perm = rng.permutation(n)
+    data, part = data[perm], part[perm]
+    res = data - cent[part]
+    pq = lb.PQBuildParams(M, 8, max_iters=4, seed=5).build(res[rng.choice(n, 8000, replace=False)])
+    codes = pq.quantize(res)
+    rid = (rng.permutation(n).astype(np.uint64) * 5 + 3)
+    ix = lb.IvfPqIndex.from_parts(cent, pq.codebook, part, codes, rid, metric)
+    parts = ix.export()
+    q = (cent[rng.integers(0, K, 48)] + rng.standard_normal((48, d))).astype(np.float32)
+    allow = rng.choice(rid, n // 3, replace=False)
+    bm = ix.row_mask(allow, None)
+    lb.profile.reset()
+    lb.profile.enable(True)
+    for k, nprobes in ((1, 3), (10, K), (15, 7), (5, 1)):
+        oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
+                                     parts["row_ids"], q, k, nprobes, metric=metric, nthreads=NT)
+        for mode in ("skew", "classic"):
+            ids, dists = _with_scan(mode, lambda: ix.search(q, k=k, nprobes=nprobes))
+            assert np.array_equal(ids, oi) and np.array_equal(dists, od), (mode, k, nprobes)
+        oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
+                                     parts["row_ids"], q, k, nprobes, metric=metric, nthreads=NT, allow=allow)
+        ids, dists = _with_scan("skew", lambda: ix.search_ex(q, k=k, nprobes=nprobes, allow_bitmap=bm))
+        assert np.array_equal(ids, oi) and np.array_equal(dists, od), ("skew+mask", k, nprobes)
+    i0, d0 = ix.search(q, k=15, nprobes=K)
+    lo, hi = float(np.median(d0[:, 2])), float(np.median(d0[:, 12]))
+    oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
+                                 parts["row_ids"], q, 10, K, metric=metric, nthreads=NT, lower=lo, upper=hi)
+    ids, dists = _with_scan("skew", lambda: ix.search_ex(q, k=10, nprobes=K, lower_bound=lo, upper_bound=hi))
+    assert np.array_equal(ids, oi) and np.array_equal(dists, od)
+    lb.profile.enable(False)
+    prof = lb.profile.dump()
+    assert prof.get("search:pq_scan_skew", (0, 0))[0] >= 9 and prof.get("search:pq_scan", (0, 0))[0] >= 4, prof
+
+
+def test_skew_scan_kernel_ties_and_non_finite_lut_go_to_the_replay():
+    """duplicated rows tie at the k-th place (reference heap order decides); a query with an Inf component makes
+    the LUT non-finite, which the skewed kernel must hand to the exact replay instead of poisoning its sums."""
+    rng = np.random.default_rng(3102)
+    d, M, K, distinct, n = 128, 16, 5, 150, 7000
+    base = (rng.integers(0, 6, (distinct, d))).astype(np.float32)
+    data = base[rng.integers(0, distinct, n)]
+    ix = lb.IvfPqIndex.build(data, "l2", lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, max_iters=5, pq_max_iters=4))
+    parts = ix.export()
+    q = base[rng.integers(0, distinct, 64)] + np.float32(0.25)
+    q[3, 7] = np.inf
+    q[9, 100] = 3.0e38
+    for k, nprobes in ((1, 1), (7, 3), (15, 5)):
+        oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
+                                     parts["row_ids"], q, k, nprobes, nthreads=NT)
+        for mode in ("skew", "classic"):
+            ids, dists = _with_scan(mode, lambda: ix.search(q, k=k, nprobes=nprobes))
+            assert np.array_equal(ids, oi), (mode, k, nprobes)
+            assert np.array_equal(dists, od, equal_nan=True), (mode, k, nprobes)
+
+
+# ---- stream / async variants of the boundary (SURVEY 8b "Threading") ------------------------------------------
+def test_search_async_and_set_stream_equal_blocking_calls():
+    """lb2_index_search_async only enqueues: several searches on two caller-owned streams, results read after the
+    streams finish, equal the blocking lb2_index_search results; lb2_set_stream routes blocking calls to a caller
+    stream (same results) and NULL restores the private stream."""
+    import torch  # CUDA stream / event handles only
+    from lance_b200._lib import DeviceArray, PinnedArray
+    rng = np.random.default_rng(3201)
+    n, d, K, M = 40000, 128, 32, 16
+    data = synth.sift_like(n, d, n_components=64, seed=3201)
+    ix = lb.IvfPqIndex.build(data, "l2", lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, max_iters=6, pq_max_iters=5))
+    batches = [synth.sift_like_queries(nq, d, n_components=64, seed=3300 + i) for i, nq in enumerate((400, 7, 256, 64))]
+    want = [ix.search(q, k=10, nprobes=6) for q in batches]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    ev = torch.cuda.Event()
+    ev.record()                                                       # torch creates the cudaEvent_t lazily
+    qs, outs = [], []
+    for i, q in enumerate(batches):                                   # device buffers and pinned host buffers
+        qd = DeviceArray.from_numpy(q)
+        if i % 2 == 0:
+            o = (DeviceArray((len(q), 10), np.uint64), DeviceArray((len(q), 10), np.float32))
+        else:
+            o = (PinnedArray((len(q), 10), np.uint64), PinnedArray((len(q), 10), np.float32))
+        qs.append(qd)
+        outs.append(o)
+        ix.search_async(qd, o, k=10, nprobes=6, cuda_stream=streams[i % 2].cuda_stream,
+                        done_event=ev.cuda_event if i == len(batches) - 1 else None)
+    ev.synchronize()
+    for s in streams:
+        s.synchronize()
+    for (wi, wd), o in zip(want, outs):
+        gi = o[0].numpy() if isinstance(o[0], DeviceArray) else o[0].array
+        gd = o[1].numpy() if isinstance(o[1], DeviceArray) else o[1].array
+        assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
+    lb.set_stream(streams[0].cuda_stream)
+    try:
+        gi, gd = ix.search(batches[0], k=10, nprobes=6)
+        p, dd, v = lb.compute_partitions(ix.export()["centroids"], data[:5000])
+    finally:
+        lb.set_stream(None)
+    assert np.array_equal(gi, want[0][0]) and np.array_equal(gd, want[0][1])
+    p2, dd2, v2 = lb.compute_partitions(ix.export()["centroids"], data[:5000])
+    assert np.array_equal(p, p2) and np.array_equal(dd, dd2)
