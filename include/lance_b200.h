@@ -253,6 +253,25 @@ typedef struct {
 lb2_status lb2_index_search_ex(lb2_index* index, const void* queries, uint64_t nq,
                                const lb2_search_params* params, uint64_t* row_ids_out, float* dists_out,
                                uint32_t* counts_out);
+/* Incremental update: the device half of optimize_indices / split / join.
+ * The reference expresses an optimize step as per-partition AssignOp::Add / AssignOp::Remove lists against a new
+ * centroid set (rust/lance/src/index/vector/builder.rs:1219-1333 split_partition_impl, :1476-1530
+ * join_partition_impl, :1534-1650 build_assign_batch) and merges them with the stored partitions.  The decisions
+ * (should_split :1152, should_join :1343, assign_vectors :1690 -- built from lb2_kmeans_train(k = 2),
+ * lb2_distance_batch and lb2_ivfpq_transform on the moved rows) stay with the host, which owns the dataset;
+ * this call is the merge on the device and returns a NEW index:
+ *   - new_centroids [new_k][d] in the model's element type (NULL = unchanged, then new_k must equal the old k);
+ *   - part_map[old_k] (nullable = identity): new partition id of every old partition, UINT32_MAX = the partition's
+ *     rows are dropped (split: the split partition's rows come back through the add list; join: ids after the
+ *     deleted partition shift down by one);
+ *   - remove_row_ids (sorted ascending): old rows to drop (AssignOp::Remove; also deletions);
+ *   - add_*: n_add rows already transformed (partition id, PQ code, row id); inside a partition the surviving old
+ *     rows keep their order and the added rows follow in list order.
+ * Appending new data to an index (optimize without retraining) is the add list alone. */
+lb2_status lb2_index_update(const lb2_index* old_index, const void* new_centroids, uint32_t new_k,
+                            const uint32_t* part_map, const uint32_t* add_part_ids, const uint8_t* add_codes,
+                            const uint64_t* add_row_ids, uint64_t n_add, const uint64_t* remove_row_ids,
+                            uint64_t n_remove, lb2_index** out);
 /* Asynchronous search (SURVEY 8b "Threading": `_async` variants taking a stream/event).  Same
  * arguments and results as lb2_index_search_ex, but the call only ENQUEUES the work on `cuda_stream`
  * (cudaStream_t; NULL = the calling thread's current library stream) and returns: probe selection, LUT
@@ -344,6 +363,17 @@ lb2_status lb2_comm_info(int* rank, int* nranks); /* (0, 1) without a communicat
 lb2_status lb2_index_search_sharded(lb2_index* index, const void* queries, uint64_t nq,
                                     const lb2_search_params* params, uint64_t* row_ids_out, float* dists_out,
                                     uint32_t* counts_out);
+/* Partition ownership by device all-to-all (SURVEY 8e "partition build" / 8f-4).  The reference groups the
+ * transformed rows by partition with a host/disk shuffler (rust/lance-index/src/vector/v3/shuffler.rs:105).
+ * For a build sharded by rows over G ranks this call is that shuffle on the device: every rank passes its
+ * row-shard index (same model on all ranks, global row ids); afterwards rank g holds ALL rows of the partitions
+ * p with p % G == g (its other partitions are empty) in a NEW index.  Inside a partition rows are ordered by
+ * source rank, then by the source's storage order -- with contiguous row shards that is the order a single-GPU
+ * index has, so a partition is scanned exactly as on one GPU (heap tie order included).  One all-gather of the K
+ * partition sizes, one grouped ncclSend/ncclRecv of (codes | vectors, row ids) over NVLink.  Without a
+ * communicator it returns a copy.  lb2_index_search_sharded works on the result unchanged: partitions a rank
+ * does not own are empty, so every probed partition is scanned by exactly one rank. */
+lb2_status lb2_index_repartition(const lb2_index* shard, lb2_index** owned_out);
 
 #ifdef __cplusplus
 }

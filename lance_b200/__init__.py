@@ -589,6 +589,39 @@ class IvfPqIndex:
         check(lib().lb2_index_search_async(self._h, qp, C.c_uint64(queries.shape[0]), C.byref(sp), ip, dp, None,
                                            C.c_void_p(cuda_stream), C.c_void_p(done_event)))
 
+    def update(self, new_centroids=None, part_map=None, add_part_ids=None, add_codes=None, add_row_ids=None,
+               remove_row_ids=None):
+        """lb2_index_update: merge AssignOp-style changes (append / remove / re-map partitions) into a NEW index."""
+        info = self.info()
+        dt = getattr(self, "_dt", F32)
+        cent = None if new_centroids is None else _typed(new_centroids, dt == BF16)[0]
+        new_k = info["num_partitions"] if cent is None else cent.shape[0]
+        pm = None if part_map is None else np.ascontiguousarray(part_map, dtype=np.uint32)
+        ap = None if add_part_ids is None else np.ascontiguousarray(add_part_ids, dtype=np.uint32)
+        ac = None if add_codes is None else np.ascontiguousarray(add_codes, dtype=np.uint8)
+        ar = None if add_row_ids is None else np.ascontiguousarray(add_row_ids, dtype=np.uint64)
+        rm = None if remove_row_ids is None else np.sort(np.ascontiguousarray(remove_row_ids, dtype=np.uint64))
+        ptrs = [as_ptr(x)[0] for x in (cent, pm, ap, ac, ar, rm)]
+        h = C.c_void_p()
+        check(lib().lb2_index_update(self._h, ptrs[0], C.c_uint32(new_k), ptrs[1], ptrs[2], ptrs[3], ptrs[4],
+                                     C.c_uint64(0 if ap is None else ap.size), ptrs[5],
+                                     C.c_uint64(0 if rm is None else rm.size), C.byref(h)))
+        out = type(self)(h)
+        if hasattr(self, "_dt"):
+            out._dt = self._dt
+        return out
+
+    def repartition(self):
+        """lb2_index_repartition: row-sharded index -> the index of the partitions this rank owns (p % nranks == rank),
+        by one device all-to-all; a copy without a communicator."""
+        h = C.c_void_p()
+        check(lib().lb2_index_repartition(self._h, C.byref(h)))
+        out = type(self)(h)
+        for a in ("_dt",):
+            if hasattr(self, a):
+                setattr(out, a, getattr(self, a))
+        return out
+
     def search_sharded(self, queries, k=10, nprobes=1, out=None):
         """lb2_index_search_sharded: this index holds ONE RANK'S rows (global row ids); every rank calls with
         the same queries and gets the global top-k (per-rank lists exchanged + merged in the library)."""

@@ -1401,6 +1401,264 @@ lb2_status lb2_index_search_sharded(lb2_index* index, const void* queries, uint6
   LB2_API_END
 }
 
+// ---- partition ownership: device all-to-all (SURVEY 8e "partition build", 8f-4) ---------------------------------
+// The reference groups the transformed rows by partition with a disk shuffler on the host
+// (rust/lance-index/src/vector/v3/shuffler.rs:105).  For a build sharded by rows over G GPUs the same grouping
+// is one exchange over NVLink: rank g becomes the owner of every partition p with p % G == g.
+namespace lb2 {
+// row i of the shard (storage order) -> slot in the send buffer: rows are grouped by destination rank, inside a
+// destination by partition, inside a partition in storage order
+__global__ void repart_pack_kernel(const uint64_t* __restrict__ part_offsets, int K, uint64_t n, int row_bytes,
+                                   const uint64_t* __restrict__ send_base /*[K]*/, const uint8_t* __restrict__ payload,
+                                   const uint64_t* __restrict__ row_ids, uint8_t* __restrict__ payload_out,
+                                   uint64_t* __restrict__ row_ids_out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lo = 0, hi = K;  // last p with part_offsets[p] <= i
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (part_offsets[mid] <= i) lo = mid; else hi = mid;
+  }
+  const uint64_t dst = send_base[lo] + (i - part_offsets[lo]);
+  row_ids_out[dst] = row_ids[i];
+  const uint8_t* src = payload + i * (uint64_t)row_bytes;
+  uint8_t* o = payload_out + dst * (uint64_t)row_bytes;
+  if ((row_bytes & 15) == 0) {
+    for (int b = 0; b < row_bytes; b += 16) *reinterpret_cast<uint4*>(o + b) = *reinterpret_cast<const uint4*>(src + b);
+  } else {
+    for (int b = 0; b < row_bytes; ++b) o[b] = src[b];
+  }
+}
+// received row j of source rank r (rows of my partitions in ascending partition order) -> final storage position
+__global__ void repart_unpack_kernel(const uint64_t* __restrict__ seg_prefix /*[nown + 1] rows of r before owned part i*/,
+                                     const uint64_t* __restrict__ seg_dst /*[nown] final position of r's first row*/,
+                                     int nown, uint64_t nrows, int row_bytes, const uint8_t* __restrict__ payload,
+                                     const uint64_t* __restrict__ row_ids, uint8_t* __restrict__ payload_out,
+                                     uint64_t* __restrict__ row_ids_out) {
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nrows) return;
+  int lo = 0, hi = nown;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (seg_prefix[mid] <= j) lo = mid; else hi = mid;
+  }
+  const uint64_t dst = seg_dst[lo] + (j - seg_prefix[lo]);
+  row_ids_out[dst] = row_ids[j];
+  const uint8_t* src = payload + j * (uint64_t)row_bytes;
+  uint8_t* o = payload_out + dst * (uint64_t)row_bytes;
+  if ((row_bytes & 15) == 0) {
+    for (int b = 0; b < row_bytes; b += 16) *reinterpret_cast<uint4*>(o + b) = *reinterpret_cast<const uint4*>(src + b);
+  } else {
+    for (int b = 0; b < row_bytes; ++b) o[b] = src[b];
+  }
+}
+}  // namespace lb2
+
+lb2_status lb2_index_repartition(const lb2_index* shard, lb2_index** owned_out) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(shard && owned_out, "null argument");
+  Comm* cm = current_comm();
+  const int G = cm ? cm->nranks : 1, me = cm ? cm->rank : 0;
+  const int K = shard->K;
+  const int rb = shard->kind == 1 ? (int)shard->vrow_bytes() : shard->code_bytes();
+  const uint8_t* payload = shard->kind == 1 ? shard->vectors.p : shard->codes.p;
+  // every rank's partition sizes (one all-gather of K counters), then the layouts on the host
+  std::vector<uint64_t> offs(K + 1);
+  d2h(offs.data(), shard->part_offsets.p, (size_t)K + 1);
+  sync_stream();
+  std::vector<uint64_t> mine(K), all((size_t)G * K);
+  for (int p = 0; p < K; ++p) mine[p] = offs[p + 1] - offs[p];
+  {
+    DevBuf<uint64_t> dm(K), da((size_t)G * K);
+    h2d(dm.p, mine.data(), K);
+    comm_allgather_bytes(dm.p, da.p, (size_t)K * 8);
+    d2h(all.data(), da.p, (size_t)G * K);
+    sync_stream();
+  }
+  // send side: rows for destination g = partitions p % G == g, ascending p
+  std::vector<size_t> s_off(G), s_bytes(G), r_off(G), r_bytes(G);
+  std::vector<uint64_t> s_rows(G, 0), r_rows(G, 0), send_base(K);
+  for (int p = 0; p < K; ++p) s_rows[p % G] += mine[p];
+  {
+    std::vector<uint64_t> run(G, 0);
+    uint64_t acc = 0;
+    std::vector<uint64_t> gbase(G);
+    for (int g = 0; g < G; ++g) { gbase[g] = acc; acc += s_rows[g]; }
+    for (int p = 0; p < K; ++p) { send_base[p] = gbase[p % G] + run[p % G]; run[p % G] += mine[p]; }
+    for (int g = 0; g < G; ++g) { s_off[g] = gbase[g]; s_bytes[g] = s_rows[g]; }
+  }
+  // receive side: from source r the rows of my partitions; final order inside a partition = source rank order
+  const int nown = (K - me + G - 1) / G;  // partitions me, me + G, ...
+  uint64_t n_new = 0;
+  std::vector<uint64_t> new_off(K + 1, 0);
+  for (int p = 0; p < K; ++p) {
+    new_off[p] = n_new;
+    if (p % G == me) for (int r = 0; r < G; ++r) n_new += all[(size_t)r * K + p];
+  }
+  new_off[K] = n_new;
+  LB2_REQUIRE(n_new < 0xffffffffull, "more than 2^32-1 rows per index shard");
+  {
+    uint64_t acc = 0;
+    for (int r = 0; r < G; ++r) {
+      for (int i = 0; i < nown; ++i) r_rows[r] += all[(size_t)r * K + (me + (size_t)i * G)];
+      r_off[r] = acc; r_bytes[r] = r_rows[r]; acc += r_rows[r];
+    }
+  }
+  const uint64_t n = shard->n;
+  DevBuf<uint8_t> sp(std::max<uint64_t>(1, n * rb)), rp(std::max<uint64_t>(1, n_new * rb));
+  DevBuf<uint64_t> si(std::max<uint64_t>(1, n)), ri(std::max<uint64_t>(1, n_new)), dbase(K);
+  h2d(dbase.p, send_base.data(), K);
+  if (n)
+    LB2_LAUNCH("repartition_pack", repart_pack_kernel, cdiv(n, 256), 256, 0, shard->part_offsets.p, K, n, rb,
+               (const uint64_t*)dbase.p, payload, (const uint64_t*)shard->row_ids.p, sp.p, si.p);
+  {
+    std::vector<size_t> so(G), sb(G), ro(G), rbv(G);
+    for (int g = 0; g < G; ++g) { so[g] = s_off[g] * rb; sb[g] = s_bytes[g] * rb; ro[g] = r_off[g] * rb; rbv[g] = r_bytes[g] * rb; }
+    comm_alltoallv_bytes(sp.p, so.data(), sb.data(), rp.p, ro.data(), rbv.data());
+    for (int g = 0; g < G; ++g) { so[g] = s_off[g] * 8; sb[g] = s_bytes[g] * 8; ro[g] = r_off[g] * 8; rbv[g] = r_bytes[g] * 8; }
+    comm_alltoallv_bytes(si.p, so.data(), sb.data(), ri.p, ro.data(), rbv.data());
+  }
+  std::unique_ptr<lb2_index> ix(new lb2_index());
+  ix->kind = shard->kind; ix->dtype = shard->dtype; ix->K = K; ix->d = shard->d; ix->M = shard->M;
+  ix->nbits = shard->nbits; ix->metric = shard->metric; ix->n = n_new;
+  ix->centroids.alloc((size_t)K * shard->d);
+  d2d(ix->centroids.p, shard->centroids.p, (size_t)K * shard->d);
+  if (shard->kind == 0) {
+    ix->codebook.alloc(shard->codebook_len());
+    d2d(ix->codebook.p, shard->codebook.p, shard->codebook_len());
+  }
+  ix->part_offsets.alloc(K + 1);
+  h2d(ix->part_offsets.p, new_off.data(), (size_t)K + 1);
+  DevBuf<uint8_t>& dstp = shard->kind == 1 ? ix->vectors : ix->codes;
+  dstp.alloc(std::max<uint64_t>(1, n_new * rb));
+  ix->row_ids.alloc(std::max<uint64_t>(1, n_new));
+  // place every (source rank, owned partition) segment: seg_prefix = rows of r before its i-th owned partition
+  std::vector<uint64_t> pre((size_t)nown + 1), dst(std::max(1, nown));
+  DevBuf<uint64_t> dpre((size_t)nown + 1), ddst(std::max(1, nown));
+  std::vector<uint64_t> before(std::max(1, nown), 0);  // rows of lower ranks already placed in owned partition i
+  for (int r = 0; r < G; ++r) {
+    uint64_t acc = 0;
+    for (int i = 0; i < nown; ++i) {
+      const int p = me + i * G;
+      pre[i] = acc;
+      dst[i] = new_off[p] + before[i];
+      acc += all[(size_t)r * K + p];
+      before[i] += all[(size_t)r * K + p];
+    }
+    pre[nown] = acc;
+    if (!acc) continue;
+    h2d(dpre.p, pre.data(), (size_t)nown + 1);
+    h2d(ddst.p, dst.data(), (size_t)nown);
+    LB2_LAUNCH("repartition_unpack", repart_unpack_kernel, cdiv(acc, 256), 256, 0, (const uint64_t*)dpre.p,
+               (const uint64_t*)ddst.p, nown, acc, rb, (const uint8_t*)(rp.p + r_off[r] * rb),
+               (const uint64_t*)(ri.p + r_off[r]), dstp.p, ix->row_ids.p);
+    sync_stream();  // pre / dst are reused by the next source rank
+  }
+  if (shard->kind == 0 && n_new && skew_layout_applies(ix->M, ix->d, ix->nbits)) {
+    ix->slab_off.alloc(K + 1);
+    ix->codes_skew.alloc(skew_bytes_bound(n_new, K));
+    build_skew_codes(ix->part_offsets.p, K, ix->codes.p, n_new, ix->slab_off.p, ix->codes_skew.p);
+  }
+  sync_stream();
+  *owned_out = ix.release();
+  LB2_API_END
+}
+
+// ---- incremental update of an IVF_PQ index: the data path of optimize / split / join --------------
+// The reference turns an optimize step into per-partition AssignOp::Add / AssignOp::Remove lists against a new
+// centroid set (rust/lance/src/index/vector/builder.rs:1219-1333 split, :1476-1530 join, :1534-1650
+// build_assign_batch) and merges them with the existing partitions when it writes the index.  The decisions --
+// which partition to split or join, which rows to move -- stay on the host (they need the dataset); this entry
+// point is the merge: old rows keep their codes, follow `part_map`, removed row ids are dropped, added rows join
+// the end of their partitions.
+namespace lb2 {
+__device__ __forceinline__ bool in_sorted_u64(const uint64_t* __restrict__ a, uint64_t n, uint64_t v) {
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo < n && a[lo] == v;
+}
+__global__ void update_old_rows_kernel(const uint64_t* __restrict__ part_offsets, int K, uint64_t n,
+                                       const uint32_t* __restrict__ part_map /*nullable*/,
+                                       const uint64_t* __restrict__ row_ids, const uint64_t* __restrict__ removed,
+                                       uint64_t n_removed, uint32_t new_k, uint32_t* __restrict__ part_out,
+                                       uint8_t* __restrict__ valid_out, uint32_t* __restrict__ bad) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lo = 0, hi = K;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (part_offsets[mid] <= i) lo = mid; else hi = mid;
+  }
+  const uint32_t np_ = part_map ? part_map[lo] : (uint32_t)lo;
+  bool keep = np_ != 0xffffffffu;
+  if (keep && np_ >= new_k) { atomicMax(bad, np_); keep = false; }
+  if (keep && n_removed) keep = !in_sorted_u64(removed, n_removed, row_ids[i]);
+  part_out[i] = keep ? np_ : 0u;
+  valid_out[i] = keep ? 1 : 0;
+}
+__global__ void fill_u8_kernel(uint8_t* __restrict__ p, uint64_t n, uint8_t v) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+}  // namespace lb2
+
+lb2_status lb2_index_update(const lb2_index* old, const void* new_centroids, uint32_t new_k, const uint32_t* part_map,
+                            const uint32_t* add_part_ids, const uint8_t* add_codes, const uint64_t* add_row_ids,
+                            uint64_t n_add, const uint64_t* remove_row_ids, uint64_t n_remove, lb2_index** out) {
+  LB2_API_BEGIN
+  LB2_REQUIRE(old && out && old->kind == 0, "lb2_index_update takes an IVF_PQ index");
+  LB2_REQUIRE(new_k > 0 && (new_centroids || new_k == (uint32_t)old->K), "a changed partition count needs new centroids");
+  LB2_REQUIRE(n_add == 0 || (add_part_ids && add_codes && add_row_ids), "added rows need partition ids, codes and row ids");
+  LB2_REQUIRE(n_remove == 0 || remove_row_ids, "null remove list");
+  const int d = old->d, cbw = old->code_bytes();
+  const uint64_t n_old = old->n, n_all = n_old + n_add;
+  LB2_REQUIRE(n_all < 0xffffffffull, "more than 2^32-1 rows per index shard");
+  std::unique_ptr<lb2_index> ix(new lb2_index());
+  ix->kind = 0; ix->dtype = old->dtype; ix->K = (int)new_k; ix->d = d; ix->M = old->M; ix->nbits = old->nbits;
+  ix->metric = old->metric;
+  ix->centroids.alloc((size_t)new_k * d);
+  if (new_centroids) {
+    VecIn c(new_centroids, (size_t)new_k * d, model_dtype(old->dtype));
+    d2d(ix->centroids.p, c.get(), (size_t)new_k * d);
+    sync_stream();
+  } else {
+    d2d(ix->centroids.p, old->centroids.p, (size_t)new_k * d);
+  }
+  ix->codebook.alloc(old->codebook_len());
+  d2d(ix->codebook.p, old->codebook.p, old->codebook_len());
+  InArg<uint32_t> pm(part_map, part_map ? (size_t)old->K : 0), ap(add_part_ids, n_add);
+  InArg<uint8_t> ac(add_codes, (size_t)n_add * cbw);
+  InArg<uint64_t> ar(add_row_ids, n_add), rm(remove_row_ids, n_remove);
+  if (n_add) check_part_ids(ap.get(), n_add, new_k, "index_update");
+  // one row list: old rows in storage order, then the added rows (so a partition keeps its old rows first)
+  DevBuf<uint32_t> part(std::max<uint64_t>(1, n_all)), bad(1);
+  DevBuf<uint8_t> valid(std::max<uint64_t>(1, n_all)), codes(std::max<uint64_t>(1, n_all * cbw));
+  DevBuf<uint64_t> rid(std::max<uint64_t>(1, n_all));
+  bad.zero();
+  if (n_old) {
+    LB2_LAUNCH("update_old_rows", update_old_rows_kernel, cdiv(n_old, 256), 256, 0, old->part_offsets.p, old->K, n_old,
+               pm.get(), (const uint64_t*)old->row_ids.p, rm.get(), n_remove, new_k, part.p, valid.p, bad.p);
+    d2d(codes.p, old->codes.p, (size_t)n_old * cbw);
+    d2d(rid.p, old->row_ids.p, (size_t)n_old);
+  }
+  if (n_add) {
+    d2d(part.p + n_old, ap.get(), (size_t)n_add);
+    d2d(codes.p + n_old * cbw, ac.get(), (size_t)n_add * cbw);
+    d2d(rid.p + n_old, ar.get(), (size_t)n_add);
+    LB2_LAUNCH("fill_valid", fill_u8_kernel, cdiv(n_add, 256), 256, 0, valid.p + n_old, n_add, (uint8_t)1);
+  }
+  uint32_t hbad = 0;
+  d2h(&hbad, bad.p, 1);
+  sync_stream();
+  if (hbad) fail(LB2_INVALID_ARG, "index_update: part_map sends a partition to %u, the new index has %u partitions", hbad, new_k);
+  index_load_dev(ix.get(), part.p, codes.p, rid.p, n_all, valid.p);
+  *out = ix.release();
+  LB2_API_END
+}
+
 lb2_status lb2_comm_info(int* rank, int* nranks) {
   LB2_API_BEGIN
   Comm* c = current_comm();

@@ -25,6 +25,10 @@ struct Api {
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 Api& api() {
@@ -43,6 +47,10 @@ Api& api() {
     a.AllReduce = (decltype(a.AllReduce))dlsym(a.lib, "ncclAllReduce");
     a.Broadcast = (decltype(a.Broadcast))dlsym(a.lib, "ncclBroadcast");
     a.AllGather = (decltype(a.AllGather))dlsym(a.lib, "ncclAllGather");
+    a.Send = (decltype(a.Send))dlsym(a.lib, "ncclSend");
+    a.Recv = (decltype(a.Recv))dlsym(a.lib, "ncclRecv");
+    a.GroupStart = (decltype(a.GroupStart))dlsym(a.lib, "ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.lib, "ncclGroupEnd");
     a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.lib, "ncclGetErrorString");
   });
   if (!a.lib || !a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.Broadcast || !a.AllGather)
@@ -81,6 +89,34 @@ void comm_allgather_bytes(const void* in, void* out, size_t bytes) {
     return;
   }
   nccl_check(api().AllGather(in, out, bytes, ncclUint8, (ncclComm_t)c->handle, ctx().stream), "ncclAllGather");
+  ctx().launches++;
+}
+// all-to-all with per-peer sizes (one grouped send/recv over NVLink): this rank's bytes for peer r start at
+// send + send_off[r], the bytes from peer r land at recv + recv_off[r]
+void comm_alltoallv_bytes(const void* send, const size_t* send_off, const size_t* send_bytes, void* recv,
+                          const size_t* recv_off, const size_t* recv_bytes) {
+  Comm* c = g_comm;
+  const int G = c ? c->nranks : 1, me = c ? c->rank : 0;
+  if (G <= 1) {
+    if (send_bytes[0])
+      LB2_CUDA(cudaMemcpyAsync((char*)recv + recv_off[0], (const char*)send + send_off[0], send_bytes[0],
+                               cudaMemcpyDeviceToDevice, ctx().stream));
+    return;
+  }
+  if (!api().Send || !api().Recv || !api().GroupStart || !api().GroupEnd)
+    fail(LB2_NCCL_ERROR, "this NCCL has no ncclSend / ncclRecv");
+  nccl_check(api().GroupStart(), "ncclGroupStart");
+  for (int r = 0; r < G; ++r) {
+    if (r == me) continue;
+    if (send_bytes[r])
+      nccl_check(api().Send((const char*)send + send_off[r], send_bytes[r], ncclUint8, r, (ncclComm_t)c->handle, ctx().stream), "ncclSend");
+    if (recv_bytes[r])
+      nccl_check(api().Recv((char*)recv + recv_off[r], recv_bytes[r], ncclUint8, r, (ncclComm_t)c->handle, ctx().stream), "ncclRecv");
+  }
+  nccl_check(api().GroupEnd(), "ncclGroupEnd");
+  if (send_bytes[me])
+    LB2_CUDA(cudaMemcpyAsync((char*)recv + recv_off[me], (const char*)send + send_off[me], send_bytes[me],
+                             cudaMemcpyDeviceToDevice, ctx().stream));
   ctx().launches++;
 }
 void comm_broadcast_bytes(void* buf, size_t bytes, int root) {

@@ -19,4 +19,7 @@ void comm_allreduce_u32(uint32_t* buf, size_t count, RedOp op);
 void comm_broadcast_bytes(void* buf, size_t bytes, int root);
 // out[r * bytes ..] = rank r's `in`: one collective whose result every rank reduces in the same (rank) order
 void comm_allgather_bytes(const void* in, void* out, size_t bytes);
+// this rank's bytes for peer r: send + send_off[r] (send_bytes[r]); peer r's bytes land at recv + recv_off[r]
+void comm_alltoallv_bytes(const void* send, const size_t* send_off, const size_t* send_bytes, void* recv,
+                          const size_t* recv_off, const size_t* recv_bytes);
 }  // namespace lb2

@@ -796,19 +796,30 @@ constexpr int SKEW_SLAB_ROWS = 512;
 constexpr int SKEW_SLAB_BYTES = SKEW_ROUNDS * 32 * 16;   // 8704
 constexpr int SKEW_CB_STRIDE = 256 * 8 + 4;              // floats per sub-space in shared memory (+16 B pad)
 constexpr int SKEW_LUT_BYTES = 256 * 256;                // both teams' LUTs, interleaved per code
-constexpr int SKEW_LIST = 1024;                          // capacity of a team's candidate list
-constexpr int SKEW_TEAM_BYTES = SKEW_LIST * 8 + 2 * SCAN_KFAST * 8 + 8 * 32 * 4 + 8 * 4 + 16;
-constexpr int SKEW_SMEM_BYTES = SKEW_LUT_BYTES + 16 * SKEW_CB_STRIDE * 4 + 2 * SKEW_TEAM_BYTES;
+constexpr int SKEW_LIST = 1024;                          // capacity of a team's candidate list (two teams)
+constexpr int SKEW_DEFAULT_TEAMS = 2;
+constexpr int SKEW_SMALL_BYTES = 2 * SCAN_KFAST * 8 + 8 * 32 * 4 + 8 * 4 + 16;   // per team (sized for 8 warps): winners, lane minima, ...
+// the LUT at shared address 0x10000: [base, 0x10000) holds 7 codebook sub-spaces + the small scratch, above the LUT
+// come 9 sub-spaces and the two candidate lists; the dynamic allocation covers the highest address for base = 0
+constexpr uint32_t SKEW_MAX_BASE = 0x10000u - (7 * SKEW_CB_STRIDE * 4 + 4 * SKEW_SMALL_BYTES);
+constexpr int SKEW_SMEM_BYTES = 0x10000 + SKEW_LUT_BYTES + 112 + 9 * SKEW_CB_STRIDE * 4 + 2 * SKEW_LIST * 8;
 
-__device__ __forceinline__ void team_sync(int team) {
-  asm volatile("bar.sync %0, 256;" ::"r"(team + 1) : "memory");
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
 }
+template <int NT>
+__device__ __forceinline__ void team_sync(int team) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(NT) : "memory");
+}
+template <int NT>
 __device__ __forceinline__ bool team_or(int team, bool v) {
   uint32_t r;
   asm volatile(
-      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %2, 0;\n\tbar.red.or.pred p, %1, 256, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %2, 0;\n\tbar.red.or.pred p, %1, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(r)
-      : "r"(team + 1), "r"((uint32_t)v)
+      : "r"(team + 1), "r"((uint32_t)v), "n"(NT)
       : "memory");
   return r != 0;
 }
@@ -883,7 +894,7 @@ skew_fill_kernel(const uint64_t* __restrict__ part_offsets, int K, const uint64_
   }
 }
 
-template <int METRIC, bool FILTER>
+template <int METRIC, bool FILTER, int NTEAM>
 __global__ void __launch_bounds__(512, 1)
 ivfpq_scan_skew_kernel(const ScanArgs a, const uint64_t* __restrict__ slab_off, const uint8_t* __restrict__ skew,
                        uint32_t nslots, uint32_t* __restrict__ rlist, uint32_t* __restrict__ rcount) {
@@ -891,22 +902,43 @@ ivfpq_scan_skew_kernel(const ScanArgs a, const uint64_t* __restrict__ slab_off, 
   const int d = a.d, k = a.k, np = a.np;
   const int kk = k + 1;  // one more than asked for, to expose ties that overflow the k-th place
   const uint64_t* __restrict__ allow = a.flt.allow;
-  const int tid = threadIdx.x, team = tid >> 8, ttid = tid & 255, lane = tid & 31, warp = ttid >> 5;
+  // NTEAM = 2: teams of 8 warps, two LUT copies (no bank conflicts).  NTEAM = 4: teams of 4 warps, ONE copy each
+  // (lanes l and l + 16 share a bank: two wavefronts per request) -- twice as many independent teams to fill the
+  // issue slots a team leaves empty at its barriers and in its low-parallelism phases.
+  constexpr int TT = 512 / NTEAM, TW = TT / 32, COPIES = NTEAM == 2 ? 2 : 1;
+  constexpr int LIST = SKEW_LIST * 2 / NTEAM;          // candidate-list capacity per team
+  constexpr uint32_t CHUNK = TW * SKEW_SLAB_ROWS;       // rows a team scans between two selections
+  const int tid = threadIdx.x, team = tid / TT, ttid = tid % TT, lane = tid & 31, warp = ttid >> 5;
   const int l16 = lane & 15, half = lane >> 4;
-  float* lut2 = reinterpret_cast<float*>(sk_smem) + team * 32;                     // [256 codes][64]: + copy * 16 + m
-  float* cb = reinterpret_cast<float*>(sk_smem + SKEW_LUT_BYTES);
-  unsigned char* tb = sk_smem + SKEW_LUT_BYTES + 16 * SKEW_CB_STRIDE * 4 + team * SKEW_TEAM_BYTES;
-  uint64_t* tl = reinterpret_cast<uint64_t*>(tb);                                  // [SKEW_LIST] team candidate list
-  uint64_t* car = tl + SKEW_LIST;                                                  // [2][SCAN_KFAST] winners so far
-  int32_t* wmin = reinterpret_cast<int32_t*>(car + 2 * SCAN_KFAST);               // [8][32] lane minima
-  int32_t* s_tw = wmin + 8 * 32;                                                   // [8] warp thresholds
+  // Shared-memory map.  The LUT sits at SHARED ADDRESS 0x10000 exactly, so that a lookup address is
+  // 0x10000 | code << 8 | bank bits -- all of it produced by the one byte permute.  The codebook is split around
+  // it (sub-spaces 0-6 below, 7-15 above), the small per-team scratch goes below, the candidate lists above.
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sk_smem);
+  if (sbase > SKEW_MAX_BASE) {  // never seen (the runtime reserves 1 KB: sbase = 0x400); the exact replay takes every slot
+    for (uint32_t slot = blockIdx.x * 512 + tid; slot < nslots; slot += gridDim.x * 512) {
+      rlist[atomicAdd(rcount, 1u)] = slot;
+      a.cand_cnt[slot] = 0;
+    }
+    return;
+  }
+  unsigned char* lut_g = sk_smem + (0x10000u - sbase);                             // generic pointer to the LUT
+  float* lut2 = reinterpret_cast<float*>(lut_g) + team * (16 * COPIES);            // [256 codes][64]: + copy * 16 + m
+  float* cb_lo = reinterpret_cast<float*>(sk_smem);                                // sub-spaces 0..6
+  // sub-spaces 7..15; the 112 bytes keep sub-space m in 16-byte bank group (m + 2 c + h) mod 8 on both sides of the LUT
+  float* cb_hi = reinterpret_cast<float*>(lut_g + SKEW_LUT_BYTES + 112);
+  unsigned char* tb = sk_smem + 7 * SKEW_CB_STRIDE * 4 + team * SKEW_SMALL_BYTES;  // small scratch (below the LUT)
+  uint64_t* car = reinterpret_cast<uint64_t*>(tb);                                 // [2][SCAN_KFAST] winners so far
+  int32_t* wmin = reinterpret_cast<int32_t*>(car + 2 * SCAN_KFAST);               // [TW][32] lane minima
+  int32_t* s_tw = wmin + TW * 32;                                                  // [8] warp thresholds
   uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_tw + 8);                         // candidates in tl
+  uint64_t* tl = reinterpret_cast<uint64_t*>(lut_g + SKEW_LUT_BYTES + 112 + 9 * SKEW_CB_STRIDE * 4) + team * LIST;
 
   // codebook -> shared memory, once per CTA (sub-space stride padded by 16 B)
   for (int i = tid; i < 16 * 256 * 2; i += 512) {
-    const int e = i >> 1;
+    const int e = i >> 1, m = e >> 8;
     const float4 v = __ldg(reinterpret_cast<const float4*>(a.codebook) + i);
-    *reinterpret_cast<float4*>(cb + (e >> 8) * SKEW_CB_STRIDE + (e & 255) * 8 + (i & 1) * 4) = v;
+    float* dstm = m < 7 ? cb_lo + m * SKEW_CB_STRIDE : cb_hi + (m - 7) * SKEW_CB_STRIDE;
+    *reinterpret_cast<float4*>(dstm + (e & 255) * 8 + (i & 1) * 4) = v;
   }
   __syncthreads();
 
@@ -918,20 +950,19 @@ ivfpq_scan_skew_kernel(const ScanArgs a, const uint64_t* __restrict__ slab_off, 
   for (int t = 0; t < 16; ++t) {
     wA[t] = t < th ? 1.0f : 0.0f;
     wB[t] = t < th ? 0.0f : 1.0f;
-    lp[t] = (uint32_t)((team * 32 + half * 16 + ((t - l16) & 15)) << 2);
+    lp[t] = 0x10000u | (uint32_t)((team * (16 * COPIES) + (COPIES == 2 ? half * 16 : 0) + ((t - l16) & 15)) << 2);
   }
-  const unsigned char* lut_bytes = sk_smem;
   const int sh = l16 != 0;  // the row finished in round u is row u - sh of the lane
   const int lm = ttid & 15;                  // LUT build: this thread's sub-space
-  const float* cbm = cb + lm * SKEW_CB_STRIDE;
+  const float* cbm = lm < 7 ? cb_lo + lm * SKEW_CB_STRIDE : cb_hi + (lm - 7) * SKEW_CB_STRIDE;
   const float dot_fix = 16.0f - 1.0f;
   constexpr int32_t MAXKEY = 0x7fffffff;     // no live row carries it: the LUT is finite, sums are at most +inf
   int par = 0;                               // which half of car[] holds the winners
 
   // slot metadata is a chain of dependent global loads (probe id -> partition offsets -> slab offset): it is
   // fetched one slot ahead, and the first code unit of a slot is requested before its LUT is built
-  const uint32_t stride = gridDim.x * 2;
-  uint32_t slot = blockIdx.x * 2 + team;
+  const uint32_t stride = gridDim.x * NTEAM;
+  uint32_t slot = blockIdx.x * NTEAM + team;
   uint32_t p_n = slot < nslots ? a.probe_ids[slot] : 0u;
   uint64_t off_n = a.part_offsets[p_n], end_n = a.part_offsets[p_n + 1], so_n = slab_off[p_n];
   for (; slot < nslots; slot += stride) {
@@ -967,8 +998,8 @@ ivfpq_scan_skew_kernel(const ScanArgs a, const uint64_t* __restrict__ slab_off, 
     }
     bool bad = false;
 #pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-      const int c = (ttid >> 4) + 16 * i;
+    for (int i = 0; i < 256 / (TT / 16); ++i) {
+      const int c = (ttid >> 4) + (TT / 16) * i;
       const float4 b0 = *reinterpret_cast<const float4*>(cbm + c * 8);
       const float4 b1 = *reinterpret_cast<const float4*>(cbm + c * 8 + 4);
       const float cv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -977,15 +1008,18 @@ ivfpq_scan_skew_kernel(const ScanArgs a, const uint64_t* __restrict__ slab_off, 
       for (int t = 0; t < 8; ++t) s = f_add(s, term<METRIC>(qm[t], cv[t]));
       const float val = finish<METRIC>(f_add(s, 0.0f));
       bad |= !(fabsf(val) < 1.0e30f);
-      lut2[c * 64 + half * 16 + lm] = val;
-      lut2[c * 64 + (half ^ 1) * 16 + lm] = val;
+      if (COPIES == 2) {
+        lut2[c * 64 + half * 16 + lm] = val;
+        lut2[c * 64 + (half ^ 1) * 16 + lm] = val;
+      } else {
+        lut2[c * 64 + lm] = val;
+      }
     }
-    // Inf / NaN in the LUT: 0 * v would poison the idle accumulator -> the exact replay takes the slot
     off_n = a.part_offsets[p_n]; end_n = a.part_offsets[p_n + 1]; so_n = slab_off[p_n];
-    bool replay = team_or(team, bad);
+    bool replay = team_or<TT>(team, bad);
     uint32_t nw = 0;  // winners carried from earlier chunks (uniform)
-    for (uint32_t c0 = 0; c0 < n_p && !replay; c0 += SCAN_CHUNK) {
-      const uint32_t clen = min((uint32_t)SCAN_CHUNK, n_p - c0);
+    for (uint32_t c0 = 0; c0 < n_p && !replay; c0 += CHUNK) {
+      const uint32_t clen = min(CHUNK, n_p - c0);
       const uint32_t wbase = warp * SKEW_SLAB_ROWS;
       if (ttid == 0) *s_cnt = 0;  // read last before the previous chunk's / slot's final barrier
       int32_t key[SKEW_ROUNDS];
@@ -1008,9 +1042,8 @@ ivfpq_scan_skew_kernel(const ScanArgs a, const uint64_t* __restrict__ slab_off, 
           const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
           for (int t = 0; t < 16; ++t) {
-            // address = code * 256 + the lane's bank bits: one byte permute (byte 0 <- lp, byte 1 <- the code)
-            const uint32_t idx = __byte_perm(w[t >> 2], lp[t], 0x5504u | ((uint32_t)(t & 3) << 4));
-            const float v = *reinterpret_cast<const float*>(lut_bytes + idx);
+            // shared address = 0x10000 | code << 8 | bank bits: one byte permute (bytes 0, 2, 3 <- lp, byte 1 <- code)
+            const float v = lds_f32(__byte_perm(w[t >> 2], lp[t], 0x7604u | ((uint32_t)(t & 3) << 4)));
             A = __fmaf_rn(v, wA[t], A);
             B = __fmaf_rn(v, wB[t], B);
           }
@@ -1047,12 +1080,12 @@ ivfpq_scan_skew_kernel(const ScanArgs a, const uint64_t* __restrict__ slab_off, 
         const int32_t twv = __reduce_max_sync(0xffffffffu, lt < kk ? mk : (int32_t)0x80000000);
         if (lane == 0) s_tw[warp] = twv;
       }
-      team_sync(team);
+      team_sync<TT>(team);
       // (2) T = the smallest warp threshold: at least kk rows of the team have key <= T; every row with key <= T
       // goes to the team list (typically kk + a few rows; ballots that come back empty cost three instructions);
       int32_t T = s_tw[0];
 #pragma unroll
-      for (int w = 1; w < 8; ++w) T = min(T, s_tw[w]);
+      for (int w = 1; w < TW; ++w) T = min(T, s_tw[w]);
       T = min(T, MAXKEY - 1);
       if (__any_sync(0xffffffffu, mk <= T)) {
 #pragma unroll
@@ -1063,21 +1096,21 @@ ivfpq_scan_skew_kernel(const ScanArgs a, const uint64_t* __restrict__ slab_off, 
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(s_cnt, (uint32_t)__popc(bal));
             base = __shfl_sync(0xffffffffu, base, 0) + __popc(bal & ((1u << lane) - 1));
-            if (take && base < (uint32_t)SKEW_LIST) tl[base] = pack_cand(key[u], c0 + wbase + lane + 32 * (u - sh));
+            if (take && base < (uint32_t)LIST) tl[base] = pack_cand(key[u], c0 + wbase + lane + 32 * (u - sh));
           }
         }
       }
-      team_sync(team);
+      team_sync<TT>(team);
       // (3) the kk smallest of list + carried winners by RANK (packed (key, position) words are unique): thread i
       // counts the entries smaller than its own and stores it at that rank.
       const uint32_t cnt = *s_cnt;
-      if (cnt > (uint32_t)SKEW_LIST) {  // a flood of equal keys: the exact replay takes the slot
+      if (cnt > (uint32_t)LIST) {  // a flood of equal keys: the exact replay takes the slot
         replay = true;
       } else {
         const uint32_t tot = cnt + nw;
         const uint64_t* cold = car + par * SCAN_KFAST;
         uint64_t* cnew = car + (par ^ 1) * SCAN_KFAST;
-        for (uint32_t i = ttid; i < tot; i += 256) {
+        for (uint32_t i = ttid; i < tot; i += TT) {
           const uint64_t v = i < cnt ? tl[i] : cold[i - cnt];
           int rank = 0;
           for (uint32_t j = 0; j < cnt; ++j) rank += tl[j] < v ? 1 : 0;
@@ -1087,7 +1120,7 @@ ivfpq_scan_skew_kernel(const ScanArgs a, const uint64_t* __restrict__ slab_off, 
         nw = min((uint32_t)kk, tot);
         par ^= 1;
       }
-      team_sync(team);
+      team_sync<TT>(team);
     }
     const uint64_t* win = car + par * SCAN_KFAST;  // ascending by (key, position)
     // If the k-th and the (k+1)-th share a key, more rows tie at the k-th distance than fit: which of them the
@@ -1103,7 +1136,7 @@ ivfpq_scan_skew_kernel(const ScanArgs a, const uint64_t* __restrict__ slab_off, 
       }
       continue;
     }
-    for (uint32_t i = ttid; i < nw; i += 256) {
+    for (uint32_t i = ttid; i < nw; i += TT) {
       a.cand_d[(size_t)slot * k + i] = key_to_float(cand_key(win[i]));
       a.cand_id[(size_t)slot * k + i] = a.row_ids[off + cand_pos(win[i])];
     }
@@ -1499,15 +1532,17 @@ static void scan_launch(int nbits, dim3 grid, size_t smem, const ScanArgs& a, ui
     // the persistent kernel loads the 128 KB codebook once per CTA: worth it from a few slots per SM on
     const bool use_skew = skew_ok && scan_mode_env() != 1 && (scan_mode_env() == 2 || nslots >= 2ull * ctx().num_sms);
     if (use_skew) {
-      const unsigned g = (unsigned)std::min<uint64_t>((nslots + 1) / 2, (uint64_t)ctx().num_sms);
+      const char* te = getenv("LB2_SCAN_TEAMS");
+      const int nteam = te && atoi(te) == 2 ? 2 : (te && atoi(te) == 4 ? 4 : SKEW_DEFAULT_TEAMS);
+      const unsigned g = (unsigned)std::min<uint64_t>((nslots + nteam - 1) / nteam, (uint64_t)ctx().num_sms);
+      auto go = [&](auto kern) {
+        set_smem(kern, SKEW_SMEM_BYTES);
+        LB2_LAUNCH("pq_scan_skew", kern, g, 512, SKEW_SMEM_BYTES, a, slab_off, skew, (uint32_t)nslots, rlist, rcount);
+      };
       if (filtering) {
-        set_smem(ivfpq_scan_skew_kernel<METRIC, true>, SKEW_SMEM_BYTES);
-        LB2_LAUNCH("pq_scan_skew", (ivfpq_scan_skew_kernel<METRIC, true>), g, 512, SKEW_SMEM_BYTES, a, slab_off, skew,
-                   (uint32_t)nslots, rlist, rcount);
+        if (nteam == 2) go(ivfpq_scan_skew_kernel<METRIC, true, 2>); else go(ivfpq_scan_skew_kernel<METRIC, true, 4>);
       } else {
-        set_smem(ivfpq_scan_skew_kernel<METRIC, false>, SKEW_SMEM_BYTES);
-        LB2_LAUNCH("pq_scan_skew", (ivfpq_scan_skew_kernel<METRIC, false>), g, 512, SKEW_SMEM_BYTES, a, slab_off, skew,
-                   (uint32_t)nslots, rlist, rcount);
+        if (nteam == 2) go(ivfpq_scan_skew_kernel<METRIC, false, 2>); else go(ivfpq_scan_skew_kernel<METRIC, false, 4>);
       }
     } else if (filtering) {  // filtered rows never enter the candidate lists
       set_smem(ivfpq_scan_kernel<METRIC, true>, smem_fast);

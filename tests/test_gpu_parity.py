@@ -1210,16 +1210,19 @@ def test_reference_fixture_pq_in_schema_on_gpu():
 
 # ---- the conflict-free ("skewed") scan kernel: same bits as the classic kernel and the oracle ----------------
 def _with_scan(mode, fn):
+    """mode: classic | skew (two teams of 8 warps, two LUT copies) | skew4 (four teams of 4 warps, one copy)"""
     import os
-    old = os.environ.get("LB2_SCAN")
-    os.environ["LB2_SCAN"] = mode
+    old = {k: os.environ.get(k) for k in ("LB2_SCAN", "LB2_SCAN_TEAMS")}
+    os.environ["LB2_SCAN"] = "classic" if mode == "classic" else "skew"
+    os.environ["LB2_SCAN_TEAMS"] = "4" if mode == "skew4" else "2"
     try:
         return fn()
     finally:
-        if old is None:
-            del os.environ["LB2_SCAN"]
-        else:
-            os.environ["LB2_SCAN"] = old
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
 @pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
@@ -1253,22 +1256,24 @@ def test_skew_scan_kernel_matches_oracle_and_classic(metric):
     for k, nprobes in ((1, 3), (10, K), (15, 7), (5, 1)):
         oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
                                      parts["row_ids"], q, k, nprobes, metric=metric, nthreads=NT)
-        for mode in ("skew", "classic"):
+        for mode in ("skew", "skew4", "classic"):
             ids, dists = _with_scan(mode, lambda: ix.search(q, k=k, nprobes=nprobes))
             assert np.array_equal(ids, oi) and np.array_equal(dists, od), (mode, k, nprobes)
         oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
                                      parts["row_ids"], q, k, nprobes, metric=metric, nthreads=NT, allow=allow)
-        ids, dists = _with_scan("skew", lambda: ix.search_ex(q, k=k, nprobes=nprobes, allow_bitmap=bm))
-        assert np.array_equal(ids, oi) and np.array_equal(dists, od), ("skew+mask", k, nprobes)
+        for mode in ("skew", "skew4"):
+            ids, dists = _with_scan(mode, lambda: ix.search_ex(q, k=k, nprobes=nprobes, allow_bitmap=bm))
+            assert np.array_equal(ids, oi) and np.array_equal(dists, od), (mode + "+mask", k, nprobes)
     i0, d0 = ix.search(q, k=15, nprobes=K)
     lo, hi = float(np.median(d0[:, 2])), float(np.median(d0[:, 12]))
     oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
                                  parts["row_ids"], q, 10, K, metric=metric, nthreads=NT, lower=lo, upper=hi)
-    ids, dists = _with_scan("skew", lambda: ix.search_ex(q, k=10, nprobes=K, lower_bound=lo, upper_bound=hi))
-    assert np.array_equal(ids, oi) and np.array_equal(dists, od)
+    for mode in ("skew", "skew4"):
+        ids, dists = _with_scan(mode, lambda: ix.search_ex(q, k=10, nprobes=K, lower_bound=lo, upper_bound=hi))
+        assert np.array_equal(ids, oi) and np.array_equal(dists, od), mode
     lb.profile.enable(False)
     prof = lb.profile.dump()
-    assert prof.get("search:pq_scan_skew", (0, 0))[0] >= 9 and prof.get("search:pq_scan", (0, 0))[0] >= 4, prof
+    assert prof.get("search:pq_scan_skew", (0, 0))[0] >= 18 and prof.get("search:pq_scan", (0, 0))[0] >= 4, prof
 
 
 def test_skew_scan_kernel_ties_and_non_finite_lut_go_to_the_replay():
@@ -1286,7 +1291,7 @@ def test_skew_scan_kernel_ties_and_non_finite_lut_go_to_the_replay():
     for k, nprobes in ((1, 1), (7, 3), (15, 5)):
         oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
                                      parts["row_ids"], q, k, nprobes, nthreads=NT)
-        for mode in ("skew", "classic"):
+        for mode in ("skew", "skew4", "classic"):
             ids, dists = _with_scan(mode, lambda: ix.search(q, k=k, nprobes=nprobes))
             assert np.array_equal(ids, oi), (mode, k, nprobes)
             assert np.array_equal(dists, od, equal_nan=True), (mode, k, nprobes)
@@ -1335,3 +1340,105 @@ def test_search_async_and_set_stream_equal_blocking_calls():
     assert np.array_equal(gi, want[0][0]) and np.array_equal(gd, want[0][1])
     p2, dd2, v2 = lb.compute_partitions(ix.export()["centroids"], data[:5000])
     assert np.array_equal(p, p2) and np.array_equal(dd, dd2)
+
+
+def test_index_repartition_without_communicator_is_a_copy():
+    """lb2_index_repartition on one rank owns every partition: same storage, same search (the N-rank exchange is
+    checked by tools/nccl_check.py under torchrun)."""
+    for kind in ("pq", "flat"):
+        data = synth.gaussian_mixture(12000, 128 if kind == "pq" else 32, n_components=20, seed=3301)
+        if kind == "pq":
+            ix = lb.IvfPqIndex.build(data, "l2", lb.IvfBuildParams(num_partitions=20, num_sub_vectors=16, max_iters=5, pq_max_iters=4))
+        else:
+            ix = lb.IvfFlatIndex.build(data, "l2", num_partitions=20, max_iters=5)
+        own = ix.repartition()
+        a, b = ix.export(), own.export()
+        for key in a:
+            assert np.array_equal(a[key], b[key]), (kind, key)
+        q = data[:40] + np.float32(0.1)
+        for mode in ("skew", "classic"):
+            r0 = _with_scan(mode, lambda: ix.search(q, k=10, nprobes=5))
+            r1 = _with_scan(mode, lambda: own.search(q, k=10, nprobes=5))
+            assert np.array_equal(r0[0], r1[0]) and np.array_equal(r0[1], r1[1])
+
+
+# ---- incremental update: the data path of optimize / split / join (builder.rs:1152-1650) ----------------------
+def test_index_update_append_remove_and_remap_equal_a_fresh_load():
+    rng = np.random.default_rng(3401)
+    n, d, K, M = 30000, 128, 24, 16
+    data = synth.gaussian_mixture(n, d, n_components=K, seed=3401)
+    ix = lb.IvfPqIndex.build(data[:20000], "l2", lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, max_iters=6, pq_max_iters=5),
+                             row_ids=np.arange(20000, dtype=np.uint64) * 2)
+    parts = ix.export()
+    sizes = np.diff(parts["part_offsets"]).astype(np.int64)
+    old_part = np.repeat(np.arange(K, dtype=np.uint32), sizes)
+    # (1) append (optimize without retraining): new rows are transformed with the index's model and merged
+    add_p, add_c, _ = lb.ivfpq_transform(parts["centroids"], parts["codebook"], data[20000:])
+    add_r = np.arange(20000, n, dtype=np.uint64) * 2
+    up = ix.update(add_part_ids=add_p, add_codes=add_c, add_row_ids=add_r)
+    want = lb.IvfPqIndex.from_parts(parts["centroids"], parts["codebook"], np.concatenate([old_part, add_p]),
+                                    np.concatenate([parts["codes"], add_c]), np.concatenate([parts["row_ids"], add_r]))
+    a, b = up.export(), want.export()
+    for key in a:
+        assert np.array_equal(a[key], b[key]), ("append", key)
+    # (2) remove row ids (AssignOp::Remove / deletions) + drop partition 3 entirely + shift the later ids down (join)
+    removed = rng.choice(parts["row_ids"], 3000, replace=False)
+    pm = np.arange(K, dtype=np.uint32)
+    pm[3] = 0xFFFFFFFF
+    pm[4:] -= 1
+    cent2 = np.delete(parts["centroids"], 3, axis=0)
+    keep = ~np.isin(parts["row_ids"], removed) & (old_part != 3)
+    moved = np.flatnonzero(old_part == 3)                             # the joined partition's rows re-enter via the add list
+    mp = rng.integers(0, K - 1, len(moved)).astype(np.uint32)
+    up2 = ix.update(new_centroids=cent2, part_map=pm, remove_row_ids=removed, add_part_ids=mp,
+                    add_codes=parts["codes"][moved], add_row_ids=parts["row_ids"][moved] + np.uint64(1))
+    want2 = lb.IvfPqIndex.from_parts(cent2, parts["codebook"], np.concatenate([pm[old_part[keep]], mp]),
+                                     np.concatenate([parts["codes"][keep], parts["codes"][moved]]),
+                                     np.concatenate([parts["row_ids"][keep], parts["row_ids"][moved] + np.uint64(1)]))
+    a, b = up2.export(), want2.export()
+    assert up2.info()["num_partitions"] == K - 1
+    for key in a:
+        assert np.array_equal(a[key], b[key]), ("join", key)
+    q = data[:64] + np.float32(0.05)
+    r0, r1 = up2.search(q, k=10, nprobes=6), want2.search(q, k=10, nprobes=6)
+    assert np.array_equal(r0[0], r1[0]) and np.array_equal(r0[1], r1[1])
+    with pytest.raises(lb.LanceB200Error):                             # a map beyond the new partition count is rejected
+        ix.update(part_map=np.full(K, K + 5, np.uint32))
+
+
+def test_split_partition_flow_on_device_primitives():
+    """split_partition_impl (builder.rs:1219-1333) on the device primitives: k-means with k = 2 on the partition's raw
+    vectors, distances to the old and the two new centroids, the reference's assign rule, then lb2_index_update.  The
+    result must equal an index loaded from the same decisions computed with the oracle's distances."""
+    n, d, K, M = 24000, 128, 12, 16
+    data = synth.gaussian_mixture(n, d, n_components=K + 1, seed=3402)
+    ix = lb.IvfPqIndex.build(data, "l2", lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, max_iters=8, pq_max_iters=5))
+    parts = ix.export()
+    sizes = np.diff(parts["part_offsets"]).astype(np.int64)
+    ps = int(np.argmax(sizes))                                          # should_split picks the largest partition
+    lo, hi = int(parts["part_offsets"][ps]), int(parts["part_offsets"][ps + 1])
+    rows = parts["row_ids"][lo:hi].astype(np.int64)
+    vec = data[rows]
+    km = lb.train_kmeans(vec, d, 2, max_iters=50, seed=3)
+    c0, c1, c2 = parts["centroids"][ps], km.centroids[0], km.centroids[1]
+    d0, d1, d2 = (lb.l2_distance_batch(c, vec, d) for c in (c0, c1, c2))
+    assert all(np.array_equal(g, ob.l2_batch(c, vec, d)) for g, c in ((d0, c0), (d1, c1), (d2, c2)))
+    # rows of the split partition: the closer of the two new centroids (no reassign candidates in this test)
+    to2 = ~(d1 <= d2)
+    newc = np.concatenate([parts["centroids"], c2[None]], 0)
+    newc[ps] = c1
+    npart = np.where(to2, K, ps).astype(np.uint32)
+    codes = lb.ProductQuantizer(M, 8, d, parts["codebook"]).quantize(vec, centroids=newc, part_ids=npart)
+    pm = np.arange(K, dtype=np.uint32)
+    pm[ps] = 0xFFFFFFFF
+    up = ix.update(new_centroids=newc, part_map=pm, add_part_ids=npart, add_codes=codes, add_row_ids=rows.astype(np.uint64))
+    old_part = np.repeat(np.arange(K, dtype=np.uint32), sizes)
+    keep = old_part != ps
+    res = vec - newc[npart]
+    want = lb.IvfPqIndex.from_parts(newc, parts["codebook"], np.concatenate([old_part[keep], npart]),
+                                    np.concatenate([parts["codes"][keep], ob.pq_encode(parts["codebook"], res, nthreads=NT)]),
+                                    np.concatenate([parts["row_ids"][keep], rows.astype(np.uint64)]))
+    a, b = up.export(), want.export()
+    assert up.info()["num_partitions"] == K + 1 and up.info()["num_rows"] == n
+    for key in a:
+        assert np.array_equal(a[key], b[key]), key

@@ -4,6 +4,8 @@
   2. hierarchical k-means (K > 256) on row shards: bit-identical centroids on every rank, K distinct clusters,
      loss within a few % of the single-GPU tree.
   3. sharded index build + lb2_index_search_sharded == one index over all rows with the same model.
+  4. lb2_index_repartition (device all-to-all): rank g ends with exactly the partitions p % world == g of the
+     one-index-over-all-rows (codes and row ids in its storage order); search_sharded on it is unchanged.
 """
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -66,6 +68,26 @@ parts = ix.export()
 ok4 = same_everywhere(parts["centroids"]) and same_everywhere(parts["codebook"])
 ids, dd = ix.search_sharded(q, k=10, nprobes=6)
 ok5 = same_everywhere(ids) and same_everywhere(dd)
+# partition ownership: every rank derives the whole index itself (same model, deterministic transform) and compares
+own = ix.repartition()
+op = own.export()
+wpart, wcodes, _ = lb.ivfpq_transform(parts["centroids"], parts["codebook"], bdata)
+wref = lb.IvfPqIndex.from_parts(parts["centroids"], parts["codebook"], wpart, wcodes).export()
+sizes_w, sizes_o = np.diff(wref["part_offsets"]), np.diff(op["part_offsets"])
+ok7 = True
+for p_ in range(Kb):
+    if p_ % world == rank:
+        a0, a1 = int(wref["part_offsets"][p_]), int(wref["part_offsets"][p_ + 1])
+        b0, b1 = int(op["part_offsets"][p_]), int(op["part_offsets"][p_ + 1])
+        ok7 &= (a1 - a0 == b1 - b0) and np.array_equal(wref["row_ids"][a0:a1], op["row_ids"][b0:b1]) \
+            and np.array_equal(wref["codes"][a0:a1], op["codes"][b0:b1])
+    else:
+        ok7 &= sizes_o[p_] == 0
+ri, rd = own.search_sharded(q, k=10, nprobes=6)
+ok7 = bool(ok7) and bool(np.array_equal(ri, ids) and np.array_equal(rd, dd))
+f7 = torch.tensor([int(ok7)], device="cuda")
+dist.all_reduce(f7, op=dist.ReduceOp.MIN)
+ok7 = bool(f7.item())
 if rank == 0:
     rel = abs(km.loss - single.loss) / single.loss
     relr = abs(km_r.loss - single_rand.loss) / single_rand.loss
@@ -81,7 +103,8 @@ if rank == 0:
     print(f"[nccl_check world={world}] flat: identical={ok1} (random init {ok1r}), pq identical={ok2}, loss rel {rel:.2e} "
           f"(random init {relr:.2e}), iters {km.iters} vs {single.iters}, {t_flat*1e3:.1f} ms | hierarchical K={big_k}: "
           f"identical+distinct={ok3}, loss sharded/single {lh/ls:.4f}, {t_h*1e3:.0f} ms | sharded build identical={ok4}, "
-          f"search_sharded identical on ranks={ok5}, equals whole-index search={ok6}")
-    assert ok1 and ok1r and ok2 and ok3 and ok4 and ok5 and ok6 and rel < 1e-5 and relr < 1e-5 and 0.9 < lh / ls < 1.1
+          f"search_sharded identical on ranks={ok5}, equals whole-index search={ok6}, repartition (all-to-all) == whole index "
+          f"per owned partition + same search={ok7}")
+    assert ok1 and ok1r and ok2 and ok3 and ok4 and ok5 and ok6 and ok7 and rel < 1e-5 and relr < 1e-5 and 0.9 < lh / ls < 1.1
 parallel.comm_destroy()
 dist.destroy_process_group()
