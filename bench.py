@@ -471,11 +471,12 @@ def main():
         import ctypes as C
         lb._lib.check(lb.lib().lb2_memcpy(C.c_void_p(pin.ptr), C.c_void_p(data_t.data_ptr()), C.c_size_t(n * DIM * 4)))
 
-        # host result buffers are allocated (and touched) once, like a caller's reusable batch buffers
-        host_out = {"centroids": np.zeros((NUM_PARTITIONS, DIM), np.float32),
-                    "codebook": np.zeros((NUM_SUB_VECTORS, 256, DIM // NUM_SUB_VECTORS), np.float32),
-                    "part_offsets": np.zeros(NUM_PARTITIONS + 1, np.uint64),
-                    "codes": np.zeros((n, NUM_SUB_VECTORS), np.uint8), "row_ids": np.zeros(n, np.uint64)}
+        # host result buffers are allocated once, like a caller's reusable (pinned) batch buffers
+        pins = {"centroids": lb.PinnedArray((NUM_PARTITIONS, DIM), np.float32),
+                "codebook": lb.PinnedArray((NUM_SUB_VECTORS, 256, DIM // NUM_SUB_VECTORS), np.float32),
+                "part_offsets": lb.PinnedArray((NUM_PARTITIONS + 1,), np.uint64),
+                "codes": lb.PinnedArray((n, NUM_SUB_VECTORS), np.uint8), "row_ids": lb.PinnedArray((n,), np.uint64)}
+        host_out = {k: v.array for k, v in pins.items()}
 
         def e2e_step():
             ix = lb.IvfPqIndex.build(pin, "l2", params)

@@ -797,7 +797,6 @@ constexpr int SKEW_SLAB_BYTES = SKEW_ROUNDS * 32 * 16;   // 8704
 constexpr int SKEW_CB_STRIDE = 256 * 8 + 4;              // floats per sub-space in shared memory (+16 B pad)
 constexpr int SKEW_LUT_BYTES = 256 * 256;                // both teams' LUTs, interleaved per code
 constexpr int SKEW_LIST = 1024;                          // capacity of a team's candidate list (two teams)
-constexpr int SKEW_DEFAULT_TEAMS = 2;
 constexpr int SKEW_SMALL_BYTES = 2 * SCAN_KFAST * 8 + 8 * 32 * 4 + 8 * 4 + 16;   // per team (sized for 8 warps): winners, lane minima, ...
 // the LUT at shared address 0x10000: [base, 0x10000) holds 7 codebook sub-spaces + the small scratch, above the LUT
 // come 9 sub-spaces and the two candidate lists; the dynamic allocation covers the highest address for base = 0
@@ -1346,6 +1345,57 @@ ivfflat_scan_kernel(const float* __restrict__ queries, int d, const uint32_t* __
 // global merge per query: ascending (distance, row id), first k.  Candidate e of list pi of query qi sits
 // at cand[pi * stride_p + qi * stride_q + e] (per-partition lists of one GPU: stride_p = k, stride_q = np * k;
 // per-rank results gathered from a sharded index: stride_p = the rank stride, stride_q = k).
+// Lists of up to MERGE_RANK_MAX candidates in total are merged by RANK COUNTING in shared memory: every candidate
+// counts the candidates that precede it in (distance, row id) order -- the pairs are unique -- and the ones with rank
+// < k are the output, already in place.  (The k-round argmin below re-reads all candidates from global memory per
+// round: 3.6 ms for 10 000 queries x 10 lists x k = 100; it remains for larger totals.)
+constexpr int MERGE_RANK_MAX = 2048;
+__global__ void __launch_bounds__(256)
+merge_rank_kernel(const float* __restrict__ cand_d, const uint64_t* __restrict__ cand_id,
+                  const uint32_t* __restrict__ cand_cnt, int np, int k, size_t stride_p_d, size_t stride_p_id,
+                  size_t stride_q, size_t cnt_stride_p, size_t cnt_stride_q, uint64_t* __restrict__ out_id,
+                  float* __restrict__ out_d, uint32_t* __restrict__ out_cnt) {
+  extern __shared__ __align__(16) unsigned char mr_smem[];
+  const int total = np * k;
+  uint64_t* s_id = reinterpret_cast<uint64_t*>(mr_smem);             // [total]
+  int32_t* s_key = reinterpret_cast<int32_t*>(s_id + total);         // [total]; invalid entries: key = INT_MAX, id = ~0
+  __shared__ uint32_t s_valid;
+  const size_t qi = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_valid = 0;
+  __syncthreads();
+  uint32_t myvalid = 0;
+  for (int c = tid; c < total; c += 256) {
+    const int pi = c / k, e = c % k;
+    const bool ok = (uint32_t)e < cand_cnt[pi * cnt_stride_p + qi * cnt_stride_q];
+    s_key[c] = ok ? total_order_key(cand_d[pi * stride_p_d + qi * stride_q + e]) : 0x7fffffff;
+    s_id[c] = ok ? cand_id[pi * stride_p_id + qi * stride_q + e] : ~0ull;
+    myvalid += ok ? 1u : 0u;
+  }
+  if (myvalid) atomicAdd(&s_valid, myvalid);
+  __syncthreads();
+  for (int c = tid; c < total; c += 256) {
+    const uint64_t id = s_id[c];
+    if (id == ~0ull && s_key[c] == 0x7fffffff) continue;
+    const int32_t key = s_key[c];
+    int rank = 0;
+    for (int j = 0; j < total; ++j) {
+      const int32_t kj = s_key[j];
+      rank += (kj < key || (kj == key && s_id[j] < id)) ? 1 : 0;
+    }
+    if (rank < k) {
+      out_id[qi * k + rank] = id;
+      out_d[qi * k + rank] = key_to_float(key);
+    }
+  }
+  const int r = min((uint32_t)k, s_valid);
+  for (int e = r + tid; e < k; e += 256) {
+    out_id[qi * k + e] = ~0ull;
+    out_d[qi * k + e] = __int_as_float(0x7f800000);
+  }
+  if (tid == 0 && out_cnt) out_cnt[qi] = r;
+}
+
 __global__ void __launch_bounds__(128)
 merge_kernel(const float* __restrict__ cand_d, const uint64_t* __restrict__ cand_id,
              const uint32_t* __restrict__ cand_cnt, int np, int k, size_t stride_p_d, size_t stride_p_id,
@@ -1529,11 +1579,13 @@ static void scan_launch(int nbits, dim3 grid, size_t smem, const ScanArgs& a, ui
     const uint64_t nslots = (uint64_t)grid.x * grid.y;
     const bool skew_ok = skew && a.M == 16 && a.ds == 8 && (reinterpret_cast<uintptr_t>(a.queries) & 15) == 0 &&
                          (size_t)SKEW_SMEM_BYTES <= ctx().smem_optin;
-    // the persistent kernel loads the 128 KB codebook once per CTA: worth it from a few slots per SM on
-    const bool use_skew = skew_ok && scan_mode_env() != 1 && (scan_mode_env() == 2 || nslots >= 2ull * ctx().num_sms);
+    // The persistent kernel wins at every batch size measured (profiles/scan_variants_r02.json: 19 vs 33 us for one
+    // query, 3.9 vs 5.9 ms for 10 000 x 10 probes); LB2_SCAN=classic|skew and LB2_SCAN_TEAMS=2|4 override for tests.
+    const bool use_skew = skew_ok && scan_mode_env() != 1;
     if (use_skew) {
       const char* te = getenv("LB2_SCAN_TEAMS");
-      const int nteam = te && atoi(te) == 2 ? 2 : (te && atoi(te) == 4 ? 4 : SKEW_DEFAULT_TEAMS);
+      // four single-copy teams per SM once every SM has several slots per team; two double-copy teams below that
+      const int nteam = te && atoi(te) == 2 ? 2 : (te && atoi(te) == 4 ? 4 : (nslots >= 16ull * ctx().num_sms ? 4 : 2));
       const unsigned g = (unsigned)std::min<uint64_t>((nslots + nteam - 1) / nteam, (uint64_t)ctx().num_sms);
       auto go = [&](auto kern) {
         set_smem(kern, SKEW_SMEM_BYTES);
@@ -1567,6 +1619,21 @@ static void scan_launch(int nbits, dim3 grid, size_t smem, const ScanArgs& a, ui
   set_smem((ivfpq_scan_radix_kernel<METRIC, 8>), smem);
   LB2_LAUNCH("pq_scan", (ivfpq_scan_radix_kernel<METRIC, 8>), grid, 256, smem, a, (const uint32_t*)nullptr,
              (const uint32_t*)nullptr);
+}
+
+// np lists of <= k candidates per query -> the k smallest by (distance, row id)
+static void merge_lists(const char* name, uint64_t nq, const float* cand_d, const uint64_t* cand_id, const uint32_t* cand_cnt,
+                        int np, int k, size_t stride_p_d, size_t stride_p_id, size_t stride_q, size_t cnt_stride_p,
+                        size_t cnt_stride_q, uint64_t* out_ids, float* out_dists, uint32_t* out_counts) {
+  if (nq == 0) return;
+  const size_t total = (size_t)np * k;
+  if (total <= (size_t)MERGE_RANK_MAX) {
+    LB2_LAUNCH(name, merge_rank_kernel, (unsigned)nq, 256, total * 12, cand_d, cand_id, cand_cnt, np, k, stride_p_d, stride_p_id,
+               stride_q, cnt_stride_p, cnt_stride_q, out_ids, out_dists, out_counts);
+  } else {
+    LB2_LAUNCH(name, merge_kernel, (unsigned)nq, 128, 0, cand_d, cand_id, cand_cnt, np, k, stride_p_d, stride_p_id, stride_q,
+               cnt_stride_p, cnt_stride_q, out_ids, out_dists, out_counts);
+  }
 }
 
 // the skewed copy of an index's codes (see ivfpq_scan_skew_kernel); sizes: slab_off u64[K + 1],
@@ -1610,8 +1677,8 @@ void ivfpq_search_f32(const float* centroids, int K, int d, int metric, const fl
     else
       scan_launch<METRIC_L2>(nbits, g, smem, a, rlist.p, rcount.p, slab_off, skew);
   }
-  LB2_LAUNCH("merge_topk", merge_kernel, (unsigned)nq, 128, 0, cand_d.p, cand_id.p, cand_cnt.p, np,
-             k, (size_t)k, (size_t)k, (size_t)np * k, (size_t)1, (size_t)np, out_ids, out_dists, out_counts);
+  merge_lists("merge_topk", nq, cand_d.p, cand_id.p, cand_cnt.p, np, k, (size_t)k, (size_t)k, (size_t)np * k, (size_t)1,
+              (size_t)np, out_ids, out_dists, out_counts);
 }
 
 // Row-sharded index (SURVEY 8e search (ii)): every rank has searched its own shard; the per-rank top-k lists
@@ -1629,10 +1696,9 @@ void merge_sharded_topk(const uint64_t* ids, const float* dists, const uint32_t*
   LB2_CUDA(cudaMemcpyAsync(blob.p + id_bytes, dists, (size_t)nq * k * 4, cudaMemcpyDeviceToDevice, ctx().stream));
   LB2_CUDA(cudaMemcpyAsync(blob.p + id_bytes + d_bytes, counts, (size_t)nq * 4, cudaMemcpyDeviceToDevice, ctx().stream));
   comm_allgather_bytes(blob.p, gathered.p, S);
-  LB2_LAUNCH("merge_sharded_topk", merge_kernel, (unsigned)nq, 128, 0,
-             reinterpret_cast<const float*>(gathered.p + id_bytes), reinterpret_cast<const uint64_t*>(gathered.p),
-             reinterpret_cast<const uint32_t*>(gathered.p + id_bytes + d_bytes), nr, k, S / 4, S / 8, (size_t)k,
-             S / 4, (size_t)1, out_ids, out_dists, out_counts);
+  merge_lists("merge_sharded_topk", nq, reinterpret_cast<const float*>(gathered.p + id_bytes),
+              reinterpret_cast<const uint64_t*>(gathered.p), reinterpret_cast<const uint32_t*>(gathered.p + id_bytes + d_bytes),
+              nr, k, S / 4, S / 8, (size_t)k, S / 4, (size_t)1, out_ids, out_dists, out_counts);
   sync_stream();  // the exchange buffers are freed on return
 }
 
@@ -1703,8 +1769,8 @@ void ivfflat_search_f32(const float* centroids, int K, int d, int metric, const 
 #undef LB2_FLAT_T
 #undef LB2_FLAT
   }
-  LB2_LAUNCH("merge_topk", merge_kernel, (unsigned)nq, 128, 0, cand_d.p, cand_id.p, cand_cnt.p, np,
-             k, (size_t)k, (size_t)k, (size_t)np * k, (size_t)1, (size_t)np, out_ids, out_dists, out_counts);
+  merge_lists("merge_topk", nq, cand_d.p, cand_id.p, cand_cnt.p, np, k, (size_t)k, (size_t)k, (size_t)np * k, (size_t)1,
+              (size_t)np, out_ids, out_dists, out_counts);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1253,7 +1253,7 @@ def test_skew_scan_kernel_matches_oracle_and_classic(metric):
     bm = ix.row_mask(allow, None)
     lb.profile.reset()
     lb.profile.enable(True)
-    for k, nprobes in ((1, 3), (10, K), (15, 7), (5, 1)):
+    for k, nprobes in ((1, 3), (10, K), (15, 7), (5, 1), (100, 6), (135, K), (40, 2)):   # k > 15: the refine sizes
         oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
                                      parts["row_ids"], q, k, nprobes, metric=metric, nthreads=NT)
         for mode in ("skew", "skew4", "classic"):
@@ -1288,7 +1288,7 @@ def test_skew_scan_kernel_ties_and_non_finite_lut_go_to_the_replay():
     q = base[rng.integers(0, distinct, 64)] + np.float32(0.25)
     q[3, 7] = np.inf
     q[9, 100] = 3.0e38
-    for k, nprobes in ((1, 1), (7, 3), (15, 5)):
+    for k, nprobes in ((1, 1), (7, 3), (15, 5), (60, 4), (120, 2)):
         oi, od, oc = ob.ivfpq_search(parts["centroids"], parts["codebook"], parts["part_offsets"], parts["codes"],
                                      parts["row_ids"], q, k, nprobes, nthreads=NT)
         for mode in ("skew", "skew4", "classic"):

@@ -41,4 +41,28 @@ for nq in (10000, 64, 1):
             same = bool(torch.equal(ref[0], res[0]) and torch.equal(ref[1], res[1]))
             out[f"nq{nq}_np{nprobes}_{mode}"] = {"search_ms": round(ms, 4), "scan_ms": round(scan, 4), "qps": round(nq / ms * 1e3), "same_as_classic": same}
             print(f"nq={nq} nprobes={nprobes} {mode}: search {ms:.4f} ms scan {scan:.4f} ms same={same}", flush=True)
+# the refine operating point: k * refine_factor = 100 candidates per (query, partition), exact re-rank on the raw column
+q = wrap_tensor(lb, q_t, np.float32)
+ids_t = torch.empty((10000, 10), dtype=torch.int64, device=dev)
+d_t = torch.empty((10000, 10), dtype=torch.float32, device=dev)
+o = (wrap_tensor(lb, ids_t, np.uint64), wrap_tensor(lb, d_t, np.float32))
+ref = None
+for mode in ("classic", "skew", "skew4"):
+    os.environ["LB2_SCAN"] = "classic" if mode == "classic" else "skew"
+    os.environ["LB2_SCAN_TEAMS"] = "4" if mode == "skew4" else "2"
+    for _ in range(3):
+        ix.search_refine(data, q, 10, 10, 10, out=o)
+    lb.profile.reset(); lb.profile.enable(True)
+    lb.timer_start()
+    for _ in range(10):
+        ix.search_refine(data, q, 10, 10, 10, out=o)
+    ms = lb.timer_stop() / 10
+    lb.profile.enable(False)
+    prof = {k: round(v[1] / 10, 4) for k, v in lb.profile.dump().items() if v[1] / 10 > 0.02}
+    res = (ids_t.clone(), d_t.clone())
+    if ref is None:
+        ref = res
+    same = bool(torch.equal(ref[0], res[0]) and torch.equal(ref[1], res[1]))
+    out[f"refine10_nq10000_np10_{mode}"] = {"search_ms": round(ms, 4), "qps": round(10000 / ms * 1e3), "kernels_ms": prof, "same_as_classic": same}
+    print(f"refine x10 nq=10000 nprobes=10 {mode}: {ms:.4f} ms same={same} {prof}", flush=True)
 json.dump(out, open("gpurun_out/scan_timing.json", "w"), indent=1)
