@@ -58,6 +58,11 @@ size_t lb2_last_error(char* buf, size_t len); /* copies the calling thread's las
 int lb2_device_count(void);                   /* 0 when no CUDA device is usable */
 lb2_status lb2_set_device(int device);
 lb2_status lb2_synchronize(void);
+/* Give cached device memory back: the calling thread's bulk-copy staging buffer (host-sourced builds keep one
+ * of up to LB2_STAGING_CACHE_MB, default 1024 MB, between calls so that the copy of the next build starts at
+ * once) and every free block of the stream-ordered pool.  The reference has no counterpart (its buffers are
+ * Arrow arrays dropped with the batch); call it when a burst of index builds is over. */
+lb2_status lb2_trim_memory(void);
 /* Bind the calling thread's library context to a caller-owned CUDA stream (cudaStream_t passed as
  * void*): all work of later calls from this thread -- kernels, copies, stream-ordered allocations --
  * is enqueued on it, after whatever the caller enqueued before.  Blocking entry points still wait for

@@ -69,6 +69,11 @@ def synchronize():
     check(lib().lb2_synchronize())
 
 
+def trim_memory():
+    """lb2_trim_memory: release this thread's cached bulk-copy staging buffer and the pool's free blocks."""
+    check(lib().lb2_trim_memory())
+
+
 def set_stream(cuda_stream=None):
     """lb2_set_stream: order every later call of this thread on a caller-owned cudaStream_t (int handle); None =
     back to the thread's private stream."""

@@ -66,7 +66,7 @@ EXPORTS = [
     "lb2_index_info", "lb2_index_export", "lb2_index_export_partition", "lb2_index_destroy", "lb2_ivfpq_build_params_default",
     "lb2_ivfpq_build", "lb2_ivfflat_build_params_default", "lb2_ivfflat_build", "lb2_index_create_flat",
     "lb2_index_load_flat", "lb2_index_export_flat", "lb2_comm_unique_id", "lb2_comm_init", "lb2_comm_destroy",
-    "lb2_comm_info", "lb2_index_search_sharded", "lb2_set_stream", "lb2_index_search_async", "lb2_index_repartition", "lb2_index_update",
+    "lb2_comm_info", "lb2_index_search_sharded", "lb2_set_stream", "lb2_trim_memory", "lb2_index_search_async", "lb2_index_repartition", "lb2_index_update",
 ]
 
 _lib = None

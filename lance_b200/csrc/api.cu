@@ -1,5 +1,6 @@
 // api.cu -- the extern "C" surface declared in include/lance_b200.h, the per-thread runtime
 // context, the device-resident index handle and the whole-index builder.
+#include <chrono>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -315,6 +316,38 @@ static void round_model(float* v, size_t count, lb2_dtype dt) {
 // host rows are either copied once, in their native type, on a second stream while training runs (when they
 // fit the budget), or streamed chunk by chunk through two staging slots during the per-row pass.  f32 views
 // exist for one chunk of rows at a time (zero-copy when the rows already are f32 on the device).
+// What a host-sourced build needs every time, kept per (thread, device) between calls: the copy stream, its
+// event and the device-side landing buffer of the bulk copy.  Measured on a B200 box (tools/e2e_trace.py):
+// re-creating them per build -- above all a fresh 512 MB cudaMallocAsync, which the pool serves by mapping new
+// physical memory whenever its free blocks are fragmented -- cost 0.1 .. 20 ms of HOST time at random before the
+// copy could even start (end-to-end C1 build 20 .. 45 ms per step); with the cache the copy is issued ~0.1 ms
+// after the sample gathers.  Only buffers <= LB2_STAGING_CACHE_MB (default 1024) are retained;
+// lb2_trim_memory() gives everything back.
+struct StagingCache {
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copied = nullptr;
+  void* buf = nullptr;
+  size_t bytes = 0;
+  bool in_use = false;
+};
+static thread_local std::map<int, StagingCache> g_staging;
+static size_t staging_cache_cap() {
+  static const size_t cap = [] {
+    const char* e = getenv("LB2_STAGING_CACHE_MB");
+    return (size_t)(e && *e ? strtoull(e, nullptr, 10) : 1024ull) << 20;
+  }();
+  return cap;
+}
+static void staging_cache_release() {  // the calling thread's cache on the current device
+  auto it = g_staging.find(ctx().device);
+  if (it == g_staging.end() || it->second.in_use) return;
+  StagingCache& sc = it->second;
+  if (sc.copy_stream) { cudaStreamSynchronize(sc.copy_stream); cudaStreamDestroy(sc.copy_stream); }
+  if (sc.copied) cudaEventDestroy(sc.copied);
+  if (sc.buf) cudaFreeAsync(sc.buf, ctx().stream);
+  g_staging.erase(it);
+}
+
 class Source {
  public:
   Source(const void* p, uint64_t n, int d, lb2_dtype dt) : host_(p), n_(n), d_(d), dt_(dt), es_(dtype_size(dt)) {
@@ -324,10 +357,18 @@ class Source {
     if (ok && (pa.type == cudaMemoryTypeDevice || pa.type == cudaMemoryTypeManaged)) {
       dev_native_ = p;
     } else if (ok && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
-      zero_copy_ = pa.devicePointer;  // pinned: the device can read it over PCIe
+      static const bool no_zc = getenv("LB2_NO_ZERO_COPY") && *getenv("LB2_NO_ZERO_COPY");  // diagnostics
+      if (!no_zc) zero_copy_ = pa.devicePointer;  // pinned: the device can read it over PCIe
     }
   }
   ~Source() {
+    if (cache_) {  // stream, event and (maybe) the buffer go back to the thread's cache
+      cudaStreamSynchronize(copy_stream_);
+      cudaEventRecord(copied_, ctx().stream);  // the buffer's last reader: the next bulk copy waits for it
+      cache_->in_use = false;
+      copy_stream_ = nullptr;
+      copied_ = nullptr;
+    }
     if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
     if (copied_) cudaEventDestroy(copied_);
     for (auto& e : slot_ready_) if (e) cudaEventDestroy(e);
@@ -366,25 +407,55 @@ class Source {
   // zero-copy reads get no PCIe bandwidth while the copy engine streams).  Otherwise chunks are staged on demand.
   void start_resident_copy() {
     if (dev_native_ || n_ == 0) return;
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
     const size_t bytes = (size_t)n_ * d_ * es_;
-    if (bytes > free_b / 2) return;  // streamed
-    bulk_.alloc(bytes);
-    LB2_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
-    LB2_CUDA(cudaEventCreateWithFlags(&copied_, cudaEventDisableTiming));
-    LB2_CUDA(cudaEventRecord(copied_, ctx().stream));  // after the pool allocation and the gathers
+    StagingCache& sc = g_staging[ctx().device];
+    if (!sc.in_use) {  // (a second Source alive on the same thread falls back to private resources)
+      cache_ = &sc;
+      sc.in_use = true;
+    }
+    const bool cached_buf = cache_ && bytes <= staging_cache_cap();
+    if (!(cached_buf && sc.bytes >= bytes)) {
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      if (bytes > (free_b + (cached_buf ? sc.bytes : 0)) / 2) {  // streamed
+        if (cache_) { cache_->in_use = false; cache_ = nullptr; }
+        return;
+      }
+      if (cached_buf) {
+        if (sc.buf) cudaFreeAsync(sc.buf, ctx().stream);
+        sc.buf = nullptr;
+        sc.bytes = 0;
+        LB2_CUDA(cudaMallocAsync(&sc.buf, bytes, ctx().stream));
+        sc.bytes = bytes;
+      } else {
+        bulk_.alloc(bytes);
+      }
+    }
+    bulk_p_ = cached_buf ? static_cast<uint8_t*>(sc.buf) : bulk_.p;
+    if (cache_) {
+      if (!sc.copy_stream) LB2_CUDA(cudaStreamCreateWithFlags(&sc.copy_stream, cudaStreamNonBlocking));
+      if (!sc.copied) LB2_CUDA(cudaEventCreateWithFlags(&sc.copied, cudaEventDisableTiming));
+      copy_stream_ = sc.copy_stream;
+      copied_ = sc.copied;
+    } else {
+      LB2_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+      LB2_CUDA(cudaEventCreateWithFlags(&copied_, cudaEventDisableTiming));
+    }
+    // after the cached buffer's last reader (recorded by ~Source, whatever stream that call ran on), the allocation
+    // and the gathers
+    if (cache_) LB2_CUDA(cudaStreamWaitEvent(copy_stream_, copied_, 0));
+    LB2_CUDA(cudaEventRecord(copied_, ctx().stream));
     LB2_CUDA(cudaStreamWaitEvent(copy_stream_, copied_, 0));
-    LB2_CUDA(cudaMemcpyAsync(bulk_.p, host_, bytes, cudaMemcpyHostToDevice, copy_stream_));
+    LB2_CUDA(cudaMemcpyAsync(bulk_p_, host_, bytes, cudaMemcpyHostToDevice, copy_stream_));
     LB2_CUDA(cudaEventRecord(copied_, copy_stream_));
     bulk_pending_ = true;
   }
   // device pointer to ALL rows in their native type, or nullptr when the matrix is streamed
   const void* native_device() {
     if (dev_native_) return dev_native_;
-    if (bulk_.p) {
+    if (bulk_p_) {
       if (bulk_pending_) { LB2_CUDA(cudaStreamWaitEvent(ctx().stream, copied_, 0)); bulk_pending_ = false; }
-      return bulk_.p;
+      return bulk_p_;
     }
     return nullptr;
   }
@@ -462,6 +533,8 @@ class Source {
   const void* dev_native_ = nullptr;
   const void* zero_copy_ = nullptr;
   DevBuf<uint8_t> bulk_, raw_[2];
+  uint8_t* bulk_p_ = nullptr;       // landing buffer of the bulk copy: bulk_ (private) or the thread's cached one
+  StagingCache* cache_ = nullptr;   // non-null while this Source holds the thread's cached stream / event / buffer
   DevBuf<float> f32_[2];
   cudaStream_t copy_stream_ = nullptr;
   cudaEvent_t copied_ = nullptr, slot_ready_[2] = {nullptr, nullptr}, slot_free_[2] = {nullptr, nullptr};
@@ -796,6 +869,15 @@ lb2_status lb2_set_device(int device) {
 lb2_status lb2_synchronize(void) {
   LB2_API_BEGIN
   sync_stream();
+  LB2_API_END
+}
+lb2_status lb2_trim_memory(void) {
+  LB2_API_BEGIN
+  sync_stream();
+  staging_cache_release();
+  sync_stream();
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, ctx().device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
   LB2_API_END
 }
 lb2_status lb2_set_stream(void* cuda_stream) {
@@ -1998,15 +2080,29 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
   const uint64_t s_pq0 = std::min<uint64_t>(n, (params->pq.sample_rate * ((uint64_t)1 << nbits) + nranks - 1) / nranks);
   DevBuf<float> sample_ivf, sample_pq;
   uint64_t s_ivf = 0, s_pq = 0;
+  // LB2_TRACE_BUILD=1: host wall-clock stamps of the staging steps on stderr (diagnostics; adds synchronisations)
+  static const bool trace = getenv("LB2_TRACE_BUILD") && *getenv("LB2_TRACE_BUILD");
+  const auto tr0 = std::chrono::steady_clock::now();
+  auto stamp = [&](const char* what) {
+    if (!trace) return;
+    sync_stream();
+    fprintf(stderr, "[lb2 build] %-22s +%.3f ms\n", what,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count());
+  };
   {
     std::vector<uint64_t> rows = sample_rows(n, s_ivf0, params->seed);
+    stamp("sample_rows(ivf)");
     s_ivf = gather_finite_sample(src, rows, m == METRIC_COSINE, sample_ivf);
+    stamp("gather(ivf sample)");
     rows = sample_rows(n, s_pq0, params->seed + 1);
     s_pq = gather_finite_sample(src, rows, m == METRIC_COSINE, sample_pq);
+    stamp("gather(pq sample)");
   }
   LB2_REQUIRE(nranks > 1 || s_ivf >= (uint64_t)K, "KMeans: can not train %d centroids with %llu finite vectors", K,
               (unsigned long long)s_ivf);
   src.start_resident_copy();
+  if (trace) fprintf(stderr, "[lb2 build] %-22s +%.3f ms (host, no sync)\n", "bulk copy issued",
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count());
   // 1. IVF
   {
     TagScope tg("ivf_train");
@@ -2014,6 +2110,7 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
     train_ivf(sample_ivf.p, s_ivf, d, K, am, params->ivf, nranks, init.get(), ix->centroids.p, &ivf_loss, &ivf_iters);
     round_model(ix->centroids.p, (size_t)K * d, dtype);
   }
+  stamp("ivf trained");
   sample_ivf.release();
   ev.record(1);
   // 2. PQ: residuals of its sample w.r.t. the IVF centroids (builder.rs:439-450)

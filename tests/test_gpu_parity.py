@@ -1442,3 +1442,28 @@ def test_split_partition_flow_on_device_primitives():
     assert up.info()["num_partitions"] == K + 1 and up.info()["num_rows"] == n
     for key in a:
         assert np.array_equal(a[key], b[key]), key
+
+
+# ---- the bulk-copy staging cache (api.cu StagingCache): repeated host-sourced builds reuse one landing buffer --
+def test_host_sourced_builds_reuse_staging_buffer_and_equal_device_builds():
+    n, d, K, M = 30000, 64, 16, 8
+    prm = lb.IvfBuildParams(num_partitions=K, num_sub_vectors=M, max_iters=6, pq_max_iters=5, seed=11)
+    pin = lb.PinnedArray((n, d), np.float32)
+    exports = []
+    for rep, (rows, seed) in enumerate(((n, 1), (n, 2), (n // 2, 3), (n, 4))):  # same, same size, smaller, larger again
+        x = synth.sift_like(rows, d, seed=seed)
+        pin.array[:rows] = x
+        src = pin if rows == n else np.ascontiguousarray(pin.array[:rows])   # pinned (zero-copy gathers) and pageable
+        e_host = lb.IvfPqIndex.build(src, "l2", prm).export()
+        e_dev = lb.IvfPqIndex.build(lb.DeviceArray.from_numpy(x), "l2", prm).export()
+        for key in ("centroids", "codebook", "part_offsets", "codes", "row_ids"):
+            assert np.array_equal(e_host[key], e_dev[key]), (rep, key)
+        exports.append(e_host["codes"])
+    assert not np.array_equal(exports[0], exports[1])  # the second build did read its own rows, not stale ones
+    # transform through the same cache, then give everything back and build once more
+    p_h, c_h, _ = lb.ivfpq_transform(e_dev["centroids"], e_dev["codebook"], pin.array[:5000])
+    p_d, c_d, _ = lb.ivfpq_transform(e_dev["centroids"], e_dev["codebook"], lb.DeviceArray.from_numpy(pin.array[:5000].copy()))
+    assert np.array_equal(p_h, p_d) and np.array_equal(c_h, c_d)
+    lb.trim_memory()
+    e_again = lb.IvfPqIndex.build(pin, "l2", prm).export()
+    assert np.array_equal(e_again["codes"], e_host["codes"])
