@@ -796,9 +796,16 @@ static std::vector<uint64_t> sample_rows(uint64_t n, uint64_t s, uint64_t seed) 
   }
   SplitMix64 rng(seed);
   out.resize(s);
+  // stratum i = [floor(i n / s), floor((i + 1) n / s)): the quotients are carried incrementally (i n = q s + r),
+  // not recomputed with two 128-bit divisions per row -- this loop is host time in front of every build
+  const uint64_t qn = n / s, rn = n % s;
+  uint64_t lo = 0, rem = 0;
   for (uint64_t i = 0; i < s; ++i) {
-    const uint64_t lo = (unsigned __int128)i * n / s, hi = (unsigned __int128)(i + 1) * n / s;
+    uint64_t hi = lo + qn;
+    rem += rn;
+    if (rem >= s) { rem -= s; ++hi; }
     out[i] = lo + rng.next() % (hi - lo);
+    lo = hi;
   }
   return out;
 }

@@ -887,12 +887,19 @@ epilogue_kernel(int K, int ds, uint64_t n, float bf_param, double tolerance,
                 const float* __restrict__ radius, const uint32_t* __restrict__ last_row,
                 uint64_t* __restrict__ cluster_sizes, float* __restrict__ bias, int bias_ld,
                 float* __restrict__ centroids, LloydState* __restrict__ states,
-                uint8_t* __restrict__ active, TcPqPrepArgs pq_prep) {
+                uint8_t* __restrict__ active, TcPqPrepArgs pq_prep, volatile uint32_t* host_words) {
   const int b = blockIdx.x;
   if (pq_prep.bm && threadIdx.x == 0) pq_prep.fb_count[b] = 0;  // next iteration's undecided-row list (active or not)
-  if (!active[b]) return;
-  epilogue_body<256>(b, K, ds, n, bf_param, tolerance, counts, losses, radius, last_row, cluster_sizes, bias, bias_ld,
-                     centroids, states, active, pq_prep);
+  if (active[b])
+    epilogue_body<256>(b, K, ds, n, bf_param, tolerance, counts, losses, radius, last_row, cluster_sizes, bias, bias_ld,
+                       centroids, states, active, pq_prep);
+  // progress word of problem b in PINNED HOST memory (one posted 4-byte write over PCIe, no copy-engine operation
+  // in the stream): (number of epilogues run so far) << 1 | still active.  The host reads it to stop enqueuing
+  // iterations, without ever draining the stream (lloyd_train).
+  if (host_words && threadIdx.x == 0) {  // thread 0 also wrote active[b] above
+    const uint32_t tick = ++states[b].pad;
+    host_words[b] = (tick << 1) | (active[b] ? 1u : 0u);
+  }
 }
 
 
@@ -1026,6 +1033,23 @@ static bool lloyd_small_ok(uint64_t n, int B, int ds, int K, bool dist) {
 // ------------------------------------------------------------------------------------------------
 // the Lloyd loop: no host round trip per iteration; the host only polls the `active` flags
 // ------------------------------------------------------------------------------------------------
+// per-problem progress words in pinned (device-mapped) host memory, one block per (thread, device), kept for the
+// thread's lifetime: written by epilogue_kernel, read by lloyd_train's host loop
+struct PollWords {
+  static constexpr int LAG = 1, MAX_B = 256;
+  volatile uint32_t* host = nullptr;
+};
+static PollWords* poll_words() {
+  static thread_local std::map<int, PollWords> words;
+  PollWords& r = words[ctx().device];
+  if (!r.host) {
+    void* p = nullptr;
+    LB2_CUDA(cudaHostAlloc(&p, sizeof(uint32_t) * PollWords::MAX_B, cudaHostAllocMapped | cudaHostAllocPortable));
+    r.host = static_cast<volatile uint32_t*>(p);
+  }
+  return &r;
+}
+
 void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, int metric,
                  float balance_factor_param, int max_iters, double tolerance, uint64_t seed,
                  const float* init_dev, float* centroids, std::vector<double>* loss_out,
@@ -1175,6 +1199,16 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
   }
   sync_stream();
 
+  // progress words in pinned host memory (see "Convergence is polled" below)
+  static const bool blocking_poll = getenv("LB2_BLOCKING_POLL") && *getenv("LB2_BLOCKING_POLL");
+  PollWords* words = B <= PollWords::MAX_B && !blocking_poll && !ctx().profiling ? poll_words() : nullptr;
+  volatile uint32_t* words_dev = nullptr;
+  if (words) {
+    for (int b = 0; b < B; ++b) words->host[b] = 0;  // (the previous run of this thread ended with a synchronise)
+    void* dp = nullptr;
+    LB2_CUDA(cudaHostGetDevicePointer(&dp, const_cast<uint32_t*>(words->host), 0));
+    words_dev = static_cast<volatile uint32_t*>(dp);
+  }
   // one Lloyd iteration = ~18 short kernels: membership, member sort, stats, update, scalar epilogue
   auto iteration = [&]() {
     if (!small) {
@@ -1216,7 +1250,7 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
     }
     LB2_LAUNCH("kmeans_epilogue", epilogue_kernel, B, 256, 0, K, ds, n_global, balance_factor_param,
                tolerance, ms.counts.p, losses.p, radius.p, last_row.p, cluster_sizes.p,
-               small ? nullptr : bias.p, Kp, centroids, states.p, active_d.p, pq_prep);
+               small ? nullptr : bias.p, Kp, centroids, states.p, active_d.p, pq_prep, words_dev);
   };
   // The first iteration runs eagerly (allocates every workspace, sets kernel attributes); the
   // iteration is then captured ONCE into a CUDA graph and replayed, so that the loop is not bound
@@ -1239,6 +1273,34 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
     for (int b = 0; b < B; ++b)
       if (active[b]) return false;
     return true;
+  };
+  // Convergence is polled WITHOUT draining the stream and without any operation in it: the epilogue kernel of every
+  // iteration posts one progress word per problem -- (epilogues run) << 1 | active -- into pinned host memory,
+  // and after enqueuing iteration `it` the host waits (plain memory reads) until every problem has reported
+  // iteration it - LAG, then looks at the active bits.  The device therefore always has the next iteration queued.
+  // (A blocking copy + synchronise every 4 iterations left the GPU idle for a copy and a graph launch each time;
+  // an asynchronous copy + event per iteration cost as much in the stream: measured, tools/iter_timing.py.)
+  // Iterations enqueued past convergence are no-ops: every kernel of an iteration returns at once for a problem
+  // whose `active` flag is 0; the flags are the same on all ranks of a sharded run, so all ranks enqueue the same
+  // number of exchanges.  (Event profiling keeps the blocking poll: launch counts are then those of real iterations.)
+  auto words_done = [&](int it) {
+    const uint32_t want = (uint32_t)it;
+    uint64_t spins = 0;
+    bool any_active = false;
+    for (int b = 0; b < B; ++b) {
+      uint32_t w;
+      while (((w = words->host[b]) >> 1) < want) {
+        if ((++spins & 0xFFFFF) == 0) {  // every ~1M reads: has the stream died or drained without reporting?
+          const cudaError_t q = cudaStreamQuery(ctx().stream);
+          if (q != cudaErrorNotReady) {
+            if (q != cudaSuccess) LB2_CUDA(q);
+            if ((words->host[b] >> 1) < want) fail(LB2_CUDA_ERROR, "k-means progress word %d never arrived", b);
+          }
+        }
+      }
+      any_active |= (w & 1u) != 0;
+    }
+    return !any_active;
   };
   iteration();
   bool done = max_iters == 1;
@@ -1264,7 +1326,11 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
     } else {
       iteration();
     }
-    if ((it & 3) == 0 || it == max_iters) done = poll_done();  // poll convergence every 4 iterations
+    if (words) {
+      if (it - PollWords::LAG >= 1) done = words_done(it - PollWords::LAG);
+    } else if ((it & 3) == 0 || it == max_iters) {
+      done = poll_done();  // blocking poll every 4 iterations
+    }
   }
   if (exec) cudaGraphExecDestroy(exec);
   if (graph) cudaGraphDestroy(graph);
