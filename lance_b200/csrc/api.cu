@@ -298,6 +298,16 @@ __global__ void gather_rows_typed_kernel(const void* __restrict__ x, int dt, con
   else v = (float)reinterpret_cast<const uint8_t*>(x)[src];
   out[g] = v;
 }
+// The same gather for f32 rows with d % 4 == 0 as a SMALL grid-stride kernel (16 bytes per thread and step): it is
+// run on the copy stream while the first training uses the SMs, so it must not occupy them -- 64 CTAs keep
+// 256 KB of reads in flight, more than the PCIe bandwidth-latency product of the zero-copy path it reads from.
+__global__ void __launch_bounds__(256)
+gather_rows_f32x4_kernel(const float4* __restrict__ x, const uint64_t* __restrict__ rows, uint64_t s, int d4,
+                         float4* __restrict__ out) {
+  const uint64_t total = s * (uint64_t)d4, stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride)
+    out[g] = x[rows[g / d4] * (uint64_t)d4 + g % d4];
+}
 // values of an f32 buffer rounded to what element type `dt` can hold (f16 / bf16 models: the reference keeps
 // centroids and codebooks in the vectors' own type, kmeans.rs:405-418, pq/builder.rs:139-157)
 __global__ void round_to_dtype_kernel(float* __restrict__ v, size_t count, int dt) {
@@ -328,6 +338,9 @@ struct StagingCache {
   cudaEvent_t copied = nullptr;
   void* buf = nullptr;
   size_t bytes = 0;
+  uint8_t* flags_host = nullptr;  // pinned: the finite-row flags of a sample gathered on the copy stream
+  size_t flags_cap = 0;
+  cudaEvent_t flags_ready = nullptr;
   bool in_use = false;
 };
 static thread_local std::map<int, StagingCache> g_staging;
@@ -344,6 +357,8 @@ static void staging_cache_release() {  // the calling thread's cache on the curr
   StagingCache& sc = it->second;
   if (sc.copy_stream) { cudaStreamSynchronize(sc.copy_stream); cudaStreamDestroy(sc.copy_stream); }
   if (sc.copied) cudaEventDestroy(sc.copied);
+  if (sc.flags_ready) cudaEventDestroy(sc.flags_ready);
+  if (sc.flags_host) cudaFreeHost(sc.flags_host);
   if (sc.buf) cudaFreeAsync(sc.buf, ctx().stream);
   g_staging.erase(it);
 }
@@ -382,7 +397,8 @@ class Source {
   void gather_f32(const std::vector<uint64_t>& rows, float* out) {
     const uint64_t s = rows.size();
     if (!s) return;
-    const void* src = dev_native_ ? dev_native_ : zero_copy_;
+    // (once a bulk copy has been started the rows are read from it: zero-copy reads starve behind the copy engine)
+    const void* src = dev_native_ ? dev_native_ : (bulk_p_ ? native_device() : zero_copy_);
     if (src) {
       DevBuf<uint64_t> rows_d(s);
       h2d(rows_d.p, rows.data(), s);
@@ -403,24 +419,64 @@ class Source {
     }
     sync_stream();
   }
+  // A second training sample gathered on the COPY stream, in front of the bulk copy, while the first training
+  // already runs on the library's stream (pinned f32 rows only).  Enqueues: rows -> device, the bounded-grid
+  // gather into `out`, the finite-row flags, their copy into pinned host memory, an event.  Returns false when
+  // the preconditions do not hold (the caller then gathers synchronously).  finish_async_sample() tells whether
+  // every row was finite.
+  bool gather_f32_async(const std::vector<uint64_t>& rows, float* out) {
+    const uint64_t s = rows.size();
+    if (!zero_copy_ || dt_ != LB2_F32 || d_ % 4 != 0 || s == 0 || ctx().profiling) return false;
+    if ((reinterpret_cast<uintptr_t>(zero_copy_) & 15) != 0) return false;
+    if (!acquire_cache()) return false;
+    StagingCache& sc = *cache_;
+    if (sc.flags_cap < s) {
+      if (sc.flags_host) cudaFreeHost(sc.flags_host);
+      sc.flags_host = nullptr;
+      sc.flags_cap = 0;
+      LB2_CUDA(cudaMallocHost(reinterpret_cast<void**>(&sc.flags_host), s));
+      sc.flags_cap = s;
+    }
+    if (!sc.flags_ready) LB2_CUDA(cudaEventCreateWithFlags(&sc.flags_ready, cudaEventDisableTiming));
+    async_rows_.alloc(s);   // (allocated on the library's stream, used on the copy stream behind the event below)
+    async_flag_.alloc(s);
+    cudaStream_t cs = copy_stream_;
+    LB2_CUDA(cudaEventRecord(copied_, ctx().stream));
+    LB2_CUDA(cudaStreamWaitEvent(cs, copied_, 0));
+    LB2_CUDA(cudaMemcpyAsync(async_rows_.p, rows.data(), s * sizeof(uint64_t), cudaMemcpyHostToDevice, cs));
+    ctx().launches += 2;
+    gather_rows_f32x4_kernel<<<64, 256, 0, cs>>>(static_cast<const float4*>(zero_copy_), async_rows_.p, s, d_ / 4,
+                                                 reinterpret_cast<float4*>(out));
+    finite_rows_kernel<<<(unsigned)cdiv(s * 32, 256), 256, 0, cs>>>(out, s, d_, async_flag_.p);
+    LB2_CUDA(cudaGetLastError());
+    LB2_CUDA(cudaMemcpyAsync(sc.flags_host, async_flag_.p, s, cudaMemcpyDeviceToHost, cs));
+    LB2_CUDA(cudaEventRecord(sc.flags_ready, cs));
+    async_s_ = s;
+    return true;
+  }
+  // after gather_f32_async(): waits for the gather, orders the library's stream behind it; true = all rows finite
+  bool finish_async_sample() {
+    StagingCache& sc = *cache_;
+    LB2_CUDA(cudaEventSynchronize(sc.flags_ready));
+    LB2_CUDA(cudaStreamWaitEvent(ctx().stream, sc.flags_ready, 0));
+    bool all = true;
+    for (uint64_t i = 0; i < async_s_; ++i) all &= sc.flags_host[i] != 0;
+    async_rows_.release();
+    async_flag_.release();
+    return all;
+  }
   // Host rows that fit: one bulk copy in the NATIVE type on a second stream (call after the sample gathers --
   // zero-copy reads get no PCIe bandwidth while the copy engine streams).  Otherwise chunks are staged on demand.
   void start_resident_copy() {
     if (dev_native_ || n_ == 0) return;
     const size_t bytes = (size_t)n_ * d_ * es_;
+    acquire_cache();  // (a second Source alive on the same thread falls back to private resources)
     StagingCache& sc = g_staging[ctx().device];
-    if (!sc.in_use) {  // (a second Source alive on the same thread falls back to private resources)
-      cache_ = &sc;
-      sc.in_use = true;
-    }
     const bool cached_buf = cache_ && bytes <= staging_cache_cap();
     if (!(cached_buf && sc.bytes >= bytes)) {
       size_t free_b = 0, total_b = 0;
       cudaMemGetInfo(&free_b, &total_b);
-      if (bytes > (free_b + (cached_buf ? sc.bytes : 0)) / 2) {  // streamed
-        if (cache_) { cache_->in_use = false; cache_ = nullptr; }
-        return;
-      }
+      if (bytes > (free_b + (cached_buf ? sc.bytes : 0)) / 2) return;  // streamed (issue_copy uses the stream too)
       if (cached_buf) {
         if (sc.buf) cudaFreeAsync(sc.buf, ctx().stream);
         sc.buf = nullptr;
@@ -432,18 +488,11 @@ class Source {
       }
     }
     bulk_p_ = cached_buf ? static_cast<uint8_t*>(sc.buf) : bulk_.p;
-    if (cache_) {
-      if (!sc.copy_stream) LB2_CUDA(cudaStreamCreateWithFlags(&sc.copy_stream, cudaStreamNonBlocking));
-      if (!sc.copied) LB2_CUDA(cudaEventCreateWithFlags(&sc.copied, cudaEventDisableTiming));
-      copy_stream_ = sc.copy_stream;
-      copied_ = sc.copied;
-    } else {
-      LB2_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
-      LB2_CUDA(cudaEventCreateWithFlags(&copied_, cudaEventDisableTiming));
+    if (!cache_) {
+      if (!copy_stream_) LB2_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+      if (!copied_) LB2_CUDA(cudaEventCreateWithFlags(&copied_, cudaEventDisableTiming));
     }
-    // after the cached buffer's last reader (recorded by ~Source, whatever stream that call ran on), the allocation
-    // and the gathers
-    if (cache_) LB2_CUDA(cudaStreamWaitEvent(copy_stream_, copied_, 0));
+    // after the cached buffer's last reader (acquire_cache), the allocation and the gathers
     LB2_CUDA(cudaEventRecord(copied_, ctx().stream));
     LB2_CUDA(cudaStreamWaitEvent(copy_stream_, copied_, 0));
     LB2_CUDA(cudaMemcpyAsync(bulk_p_, host_, bytes, cudaMemcpyHostToDevice, copy_stream_));
@@ -493,7 +542,25 @@ class Source {
     issue_copy((int)(calls_ & 1), r0, rows);
   }
 
+  bool has_bulk() const { return bulk_p_ != nullptr; }
+
  private:
+  // take the thread's cached copy stream / event (and with them the right to the cached landing buffer); the copy
+  // stream is first ordered behind the buffer's last reader, recorded by the previous holder's destructor
+  bool acquire_cache() {
+    if (cache_) return true;
+    if (copy_stream_) return false;  // already on private resources
+    StagingCache& sc = g_staging[ctx().device];
+    if (sc.in_use) return false;
+    if (!sc.copy_stream) LB2_CUDA(cudaStreamCreateWithFlags(&sc.copy_stream, cudaStreamNonBlocking));
+    if (!sc.copied) LB2_CUDA(cudaEventCreateWithFlags(&sc.copied, cudaEventDisableTiming));
+    sc.in_use = true;
+    cache_ = &sc;
+    copy_stream_ = sc.copy_stream;
+    copied_ = sc.copied;
+    LB2_CUDA(cudaStreamWaitEvent(copy_stream_, copied_, 0));
+    return true;
+  }
   void issue_copy(int slot, uint64_t r0, uint64_t rows) {
     const size_t off = (size_t)r0 * d_ * es_, cnt = (size_t)rows * d_;
     if (!copy_stream_) LB2_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
@@ -533,6 +600,9 @@ class Source {
   const void* dev_native_ = nullptr;
   const void* zero_copy_ = nullptr;
   DevBuf<uint8_t> bulk_, raw_[2];
+  DevBuf<uint64_t> async_rows_;     // gather_f32_async: the row list and the finite flags on the device
+  DevBuf<uint8_t> async_flag_;
+  uint64_t async_s_ = 0;
   uint8_t* bulk_p_ = nullptr;       // landing buffer of the bulk copy: bulk_ (private) or the thread's cached one
   StagingCache* cache_ = nullptr;   // non-null while this Source holds the thread's cached stream / event / buffer
   DevBuf<float> f32_[2];
@@ -2087,6 +2157,8 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
   const uint64_t s_pq0 = std::min<uint64_t>(n, (params->pq.sample_rate * ((uint64_t)1 << nbits) + nranks - 1) / nranks);
   DevBuf<float> sample_ivf, sample_pq;
   uint64_t s_ivf = 0, s_pq = 0;
+  std::vector<uint64_t> rows_pq;
+  bool pq_deferred = false;
   // LB2_TRACE_BUILD=1: host wall-clock stamps of the staging steps on stderr (diagnostics; adds synchronisations)
   static const bool trace = getenv("LB2_TRACE_BUILD") && *getenv("LB2_TRACE_BUILD");
   const auto tr0 = std::chrono::steady_clock::now();
@@ -2101,9 +2173,17 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
     stamp("sample_rows(ivf)");
     s_ivf = gather_finite_sample(src, rows, m == METRIC_COSINE, sample_ivf);
     stamp("gather(ivf sample)");
-    rows = sample_rows(n, s_pq0, params->seed + 1);
-    s_pq = gather_finite_sample(src, rows, m == METRIC_COSINE, sample_pq);
-    stamp("gather(pq sample)");
+    rows_pq = sample_rows(n, s_pq0, params->seed + 1);
+    // the PQ sample is not needed before the IVF model exists: from pinned f32 rows it is gathered on the copy
+    // stream (in front of the bulk copy) while the IVF training runs; otherwise here
+    if (m != METRIC_COSINE && !trace && !rows_pq.empty()) {
+      sample_pq.alloc(rows_pq.size() * (uint64_t)d);
+      pq_deferred = src.gather_f32_async(rows_pq, sample_pq.p);
+    }
+    if (!pq_deferred) {
+      s_pq = gather_finite_sample(src, rows_pq, m == METRIC_COSINE, sample_pq);
+      stamp("gather(pq sample)");
+    }
   }
   LB2_REQUIRE(nranks > 1 || s_ivf >= (uint64_t)K, "KMeans: can not train %d centroids with %llu finite vectors", K,
               (unsigned long long)s_ivf);
@@ -2118,6 +2198,13 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
     round_model(ix->centroids.p, (size_t)K * d, dtype);
   }
   stamp("ivf trained");
+  if (pq_deferred) {
+    if (src.finish_async_sample()) {
+      s_pq = rows_pq.size();
+    } else {  // rare: some sampled rows are not finite -> the synchronous path drops them and gathers again
+      s_pq = gather_finite_sample(src, rows_pq, false, sample_pq);
+    }
+  }
   sample_ivf.release();
   ev.record(1);
   // 2. PQ: residuals of its sample w.r.t. the IVF centroids (builder.rs:439-450)

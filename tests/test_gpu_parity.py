@@ -1460,6 +1460,20 @@ def test_host_sourced_builds_reuse_staging_buffer_and_equal_device_builds():
             assert np.array_equal(e_host[key], e_dev[key]), (rep, key)
         exports.append(e_host["codes"])
     assert not np.array_equal(exports[0], exports[1])  # the second build did read its own rows, not stale ones
+    # rows that are not finite: the PQ sample gathered on the copy stream reports them and the build falls back
+    # to the synchronous gather that drops them (builder.rs:436) -- same index as from device-resident rows
+    x = synth.sift_like(n, d, seed=9)
+    x[::7, 3] = np.nan
+    x[5::11, 0] = np.inf
+    pin.array[:] = x
+    e_host = lb.IvfPqIndex.build(pin, "l2", prm).export()
+    e_dev = lb.IvfPqIndex.build(lb.DeviceArray.from_numpy(x), "l2", prm).export()
+    for key in ("centroids", "codebook", "part_offsets", "codes", "row_ids"):
+        assert np.array_equal(e_host[key], e_dev[key]), ("non-finite", key)
+    bad = np.flatnonzero(~np.isfinite(x).all(1))
+    assert len(e_host["row_ids"]) == n - len(bad) and not np.isin(bad, e_host["row_ids"]).any()
+    pin.array[:] = synth.sift_like(n, d, seed=4)
+    e_host = lb.IvfPqIndex.build(pin, "l2", prm).export()
     # transform through the same cache, then give everything back and build once more
     p_h, c_h, _ = lb.ivfpq_transform(e_dev["centroids"], e_dev["codebook"], pin.array[:5000])
     p_d, c_d, _ = lb.ivfpq_transform(e_dev["centroids"], e_dev["codebook"], lb.DeviceArray.from_numpy(pin.array[:5000].copy()))
