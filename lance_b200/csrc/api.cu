@@ -2141,6 +2141,9 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
   // then the matrix is copied ONCE, in its own element type, on a second stream while both trainings run; the
   // per-row pass waits for it and converts one chunk of rows at a time.  A matrix too large for that is streamed
   // chunk by chunk during the per-row pass instead (double buffered).  No whole-matrix f32 copy exists.
+  // (declared before `src`: on an error path ~Source waits for the copy stream, which may still be writing the PQ
+  // sample, before these buffers go back to the pool)
+  DevBuf<float> sample_ivf, sample_pq;
   Source src(data, n, (int)d, dtype);
   const int am = m == METRIC_DOT ? METRIC_DOT : METRIC_L2;
 
@@ -2155,7 +2158,6 @@ lb2_status lb2_ivfpq_build(const void* data, uint64_t n, uint32_t d, lb2_dtype d
   //    not finite are dropped from them (builder.rs:436); then the bulk copy starts
   const uint64_t s_ivf0 = std::min<uint64_t>(n, ((uint64_t)K * params->ivf.sample_rate + nranks - 1) / nranks);
   const uint64_t s_pq0 = std::min<uint64_t>(n, (params->pq.sample_rate * ((uint64_t)1 << nbits) + nranks - 1) / nranks);
-  DevBuf<float> sample_ivf, sample_pq;
   uint64_t s_ivf = 0, s_pq = 0;
   std::vector<uint64_t> rows_pq;
   bool pq_deferred = false;
