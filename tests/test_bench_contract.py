@@ -53,3 +53,27 @@ def test_committed_bench_line_follows_the_contract():
     assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
     assert j["gpu_launches"] > 0 and not set(j["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(j["clocks"])
+
+
+def test_committed_round2_bench_lines_follow_the_contract():
+    """profiles/bench_r02_C1.json (with the CPU baseline) and bench_r02_C1_final.json (final state of the round,
+    run with --no-cpu-baseline) are lines `python bench.py` printed on B200 boxes."""
+    base = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+            "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"}
+    for name, with_cpu in (("bench_r02_C1.json", True), ("bench_r02_C1_final.json", False)):
+        lines = [ln for ln in open(os.path.join(ROOT, "profiles", name)).read().splitlines() if ln.startswith("{")]
+        j = json.loads(lines[-1])
+        assert base <= set(j), name
+        assert j["metric"] == "ivf_pq_index_build_mvec_per_s" and j["n_gpus"] == 1 and j["warmup"] >= 3
+        assert abs(j["value"] - 1e6 / (j["ms_per_step"] * 1e-3) / 1e6) < 1e-6 * j["value"]
+        r = j["roofline"]
+        assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        e = j["e2e"]
+        assert e["h2d_bytes_per_step"] == 1_000_000 * 128 * 4 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < j["value"]
+        assert e["steps"] == j["steps"]                       # round 1 timed 3 e2e steps whatever --steps said
+        assert j["gpu_launches"] > 0 and not set(j["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if with_cpu:
+            c = j["cpu_baseline"]
+            assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "timed, not scaled" in c["sample"]
+        q = j["query"]
+        assert q["batch"] == 10000 and q["nprobes"] == 10 and 0 < q["recall_at_10"] <= 1
