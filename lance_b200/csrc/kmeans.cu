@@ -1201,7 +1201,11 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
 
   // progress words in pinned host memory (see "Convergence is polled" below)
   static const bool blocking_poll = getenv("LB2_BLOCKING_POLL") && *getenv("LB2_BLOCKING_POLL");
-  PollWords* words = B <= PollWords::MAX_B && !blocking_poll && !ctx().profiling ? poll_words() : nullptr;
+  // Single-rank runs only.  The host may read a word late and see the active bit of a LATER iteration than the one
+  // it waited for: harmless alone (it just stops a no-op earlier), but two ranks of a sharded run could then enqueue
+  // different numbers of iterations -- and the exchange inside the extra one would wait forever.  Sharded runs keep
+  // the blocking poll, which reads the flags of exactly iteration `it` on every rank.
+  PollWords* words = B <= PollWords::MAX_B && !blocking_poll && !ctx().profiling && !dist ? poll_words() : nullptr;
   volatile uint32_t* words_dev = nullptr;
   if (words) {
     for (int b = 0; b < B; ++b) words->host[b] = 0;  // (the previous run of this thread ended with a synchronise)
@@ -1281,8 +1285,8 @@ void lloyd_train(const float* x, uint64_t n_in, int ldx, int B, int ds, int K, i
   // (A blocking copy + synchronise every 4 iterations left the GPU idle for a copy and a graph launch each time;
   // an asynchronous copy + event per iteration cost as much in the stream: measured, tools/iter_timing.py.)
   // Iterations enqueued past convergence are no-ops: every kernel of an iteration returns at once for a problem
-  // whose `active` flag is 0; the flags are the same on all ranks of a sharded run, so all ranks enqueue the same
-  // number of exchanges.  (Event profiling keeps the blocking poll: launch counts are then those of real iterations.)
+  // whose `active` flag is 0.  (Event profiling keeps the blocking poll: launch counts are then those of real
+  // iterations; so do sharded runs, see `words` above.)
   auto words_done = [&](int it) {
     const uint32_t want = (uint32_t)it;
     uint64_t spins = 0;
