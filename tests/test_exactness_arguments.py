@@ -1,4 +1,4 @@
-"""Two arguments the device code relies on, checked on the CPU (no GPU, no product code).
+"""Arguments the device code relies on, checked on the CPU (no GPU, no product code; section 3 is at the end).
 
 1. Order-independent sums (kmeans.cu `update_body_warp` / `stats_body` fast paths): the reference
    adds a cluster's members sequentially (f32 centroid sums kmeans.rs:388-418, f64 loss :266-280).  If every term is an
@@ -196,3 +196,33 @@ def test_reporting_the_tick_of_convergence_is_independent_of_read_timing():
         ranks = _simulate(len(late), 5, 50, mode="conv_tick", late=late, iter_s=0.0005)
         assert not any(r.hung for r in ranks)
         assert {r.enqueued for r in ranks} == {6} and all(r.executed_active == 5 for r in ranks)
+
+
+# ---- 3. the k + 1 rule of every top-k path (DESIGN.md section 5 "Ties at the k-th distance"; search.cu) ----------
+# The GPU selects k + 1 candidates per list.  Argument: when the (k+1)-th smallest distance differs from the k-th, the
+# reference's BinaryHeap result (flat/index.rs:82-177, restated in the oracle) is the unique set of the k smallest --
+# whatever order the rows were pushed in -- so any selection algorithm returns it; only when they are equal does the
+# result depend on the heap's sift order, and only then the slot is replayed with the heap's own operations.
+def test_topk_set_is_order_free_unless_the_boundary_is_tied():
+    from oracle import binding as ob
+    rng = np.random.default_rng(4)
+    tied_boundaries = 0
+    for trial in range(200):
+        n, k = int(rng.integers(5, 400)), int(rng.integers(1, 20))
+        d = rng.integers(0, 40, n).astype(np.float32)                      # small integers: ties everywhere
+        if trial % 3 == 0:
+            d = d + rng.random(n).astype(np.float32)                        # and some tie-free inputs
+        rid = np.arange(n, dtype=np.uint64)
+        ids, dd = ob.flat_topk(d, rid, k)
+        srt = np.sort(d, kind="stable")
+        kk = min(k, n)
+        assert np.array_equal(np.sort(dd), srt[:kk])                        # the distance multiset is always exact
+        if kk < n and srt[kk] == srt[kk - 1]:
+            tied_boundaries += 1                                            # heap order decides: the replay's domain
+            continue
+        expect = set(np.flatnonzero(d <= srt[kk - 1]).tolist()) if kk else set()
+        assert set(ids.tolist()) == expect and len(expect) == kk
+        perm = rng.permutation(n)                                           # push order does not matter here
+        ids2, _ = ob.flat_topk(d[perm], rid[perm], k)
+        assert set(ids2.tolist()) == expect
+    assert tied_boundaries > 20                                             # the tied case is common on such data
