@@ -178,3 +178,44 @@ def test_model_would_catch_a_tau_that_is_too_small():
     n2 = (cent * cent).sum(1, dtype=np.float32)
     flag, idx = certificate(tf32_trunc(x), tf32_trunc(cent), np.float32(-0.5) * n2, np.zeros(n, np.float32), "toward_zero")
     assert (flag == 0).all() and (idx[:, 0] != ref).any()
+
+
+# ---- the FMA pre-screen of pq_fallback_kernel (tc_pq.cu) -------------------------------------------------------
+# Undecided (row, sub-space) pairs are finished by a scan of all 256 codewords that first computes
+#   s'(c) = fma-chain(r . c) - |c|^2/2   (8 fused steps, cnh from an fma chain too)
+# and gives the reference-order distance only to the codewords with s'(c) >= max s' - 2^-18 (|r|^2 + max|c|^2).
+# Claim: the reference's argmin (sequential 8-term f32 sum, l2.rs:69-79; strict `<`, lowest index) is among them.
+def _fma(a, b, c):
+    """fused multiply-add in f32: the product of two f32 is exact in f64; one rounding of the f64 sum to f32
+    (double rounding could differ from a true fma in the last bit of rare cases -- far inside the budget tested)"""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def test_pq_fallback_prescreen_keeps_the_reference_argmin():
+    rng = np.random.default_rng(21)
+    ds, K = 8, 256
+    for scale, near_ties in ((1.0, False), (300.0, False), (1.0, True), (40.0, True)):
+        cb = (rng.standard_normal((K, ds)) * scale).astype(np.float32)
+        n = 1500
+        if near_ties:   # residuals on bisectors of two codewords, and exactly duplicated codewords
+            a, b = rng.integers(0, K, n), rng.integers(0, K, n)
+            r = ((cb[a] + cb[b]) * np.float32(0.5) + (rng.standard_normal((n, ds)) * scale * 1e-4).astype(np.float32)).astype(np.float32)
+            cb[K - 8:] = cb[:8]
+        else:
+            r = (cb[rng.integers(0, K, n)] + rng.standard_normal((n, ds)).astype(np.float32) * np.float32(scale)).astype(np.float32)
+        ref, _, valid = ob.compute_membership(cb, r)
+        assert valid.all()
+        n2 = np.zeros(K, np.float32)
+        for t in range(ds):
+            n2 = _fma(cb[:, t], cb[:, t], n2)
+        cnh = (np.float32(-0.5) * n2).astype(np.float32)
+        rn = np.zeros(n, np.float32)
+        for t in range(ds):
+            rn = _fma(r[:, t], r[:, t], rn)
+        s = np.broadcast_to(cnh[None, :], (n, K)).astype(np.float32)
+        for t in range(ds):
+            s = _fma(np.broadcast_to(r[:, t:t + 1], (n, K)), np.broadcast_to(cb[None, :, t], (n, K)), s)
+        thr = s.max(1) - np.float32(2.0 ** -18) * (rn + n2.max())
+        kept = ~(s < thr[:, None])
+        assert kept[np.arange(n), ref].all(), "the pre-screen dropped the reference's argmin"
+        assert kept.sum(1).mean() < (64 if near_ties else 8)      # ... and it is selective (that is its point)
