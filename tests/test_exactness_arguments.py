@@ -111,7 +111,7 @@ class _Rank:
                     return
                 j = self.queue.pop(0)
             try:
-                self.barrier_for(j).wait(timeout=1.0)  # the exchange inside the captured iteration
+                self.barrier_for(j).wait(timeout=4.0)  # the exchange inside the captured iteration
             except threading.BrokenBarrierError:
                 self.hung = True                       # a peer never enqueued iteration j: NCCL would wait forever
                 return
@@ -143,7 +143,7 @@ class _Rank:
                 assert time.monotonic() - t0 < 20, "progress word never arrived"
             seen = min(want + self.late_by, self.enqueued)     # the tick whose posting this (late) read observes
             t1 = time.monotonic()
-            while (self.word >> 1) < seen and not self.hung and time.monotonic() - t1 < 2.0:
+            while (self.word >> 1) < seen and not self.hung and time.monotonic() - t1 < 6.0:
                 time.sleep(0.0001)
             word, conv = self.hist[min(seen, self.word >> 1)]
             if self.mode == "active_bit":
@@ -152,7 +152,7 @@ class _Rank:
                 done = conv != 0 and conv <= want              # independent of WHEN the host reads
             it += 1
         t0 = time.monotonic()
-        while (self.word >> 1) < self.enqueued and not self.hung and time.monotonic() - t0 < 5:
+        while (self.word >> 1) < self.enqueued and not self.hung and time.monotonic() - t0 < 8:
             time.sleep(0.0001)                                 # the final synchronise of lloyd_train
         self.stop = True
 
