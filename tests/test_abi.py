@@ -48,3 +48,18 @@ def test_no_gpu_fails_loudly():
     assert e.value.status == _lib.NO_DEVICE
     with pytest.raises(lb.LanceB200Error):
         lb.IvfPqIndex.build(np.zeros((300, 16), np.float32), params=lb.IvfBuildParams(num_partitions=4, num_sub_vectors=2))
+
+
+def test_header_is_plain_c11_and_cxx17(tmp_path):
+    """the boundary is a C ABI: include/lance_b200.h must compile as C and as C++ with no CUDA / torch headers"""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cc, std, ext in (("gcc", "-std=c11", "c"), ("g++", "-std=c++17", "cc")):
+        if shutil.which(cc) is None:
+            continue
+        src = tmp_path / f"use_header.{ext}"
+        src.write_text('#include "lance_b200.h"\nint main(void) { return lb2_device_count == 0; }\n')
+        out = subprocess.run([cc, std, "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-I", os.path.join(root, "include"), str(src)],
+                             capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
